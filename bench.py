@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""GE2E loss fwd+bwd benchmark (BASELINE.json metric: utterances/s at N=1024, M=10, D=256).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload cfg1|cfg2|cfg3|cfg4] [--precision tf32|fp32] [--variant softmax|contrast]
+
+One "step" = one GE2E forward + backward (grads to E, w, b) over one synthetic batch.
+  value  device-resident inputs, the fwd+bwd C-ABI calls replayed from a CUDA graph, timed per step
+         with CUDA events on the launching stream, L2 flushed (256 MiB write) between steps.
+  e2e    the public module API (GE2ELoss(...)(E); loss.backward()) with the batch in pinned HOST
+         memory: H2D copy of E and D2H read of loss/dw/db inside the timed region.
+  roofline      the dominant kernel stage timed alone with CUDA events (same inputs, L2 flushed).
+  cpu_baseline  the torch-CPU port of the reference's expanded algorithm (oracle/ge2e_ref_port.py)
+                on a bounded row sample of the same batch, all host threads.
+N=1 runs cfg3 (the config the metric is quoted on).  N>1 runs cfg4 (N=8192, M=16) speaker-sharded
+over the ranks (strong scaling: total work fixed); rank 0 also times cfg4 unsharded on its own GPU
+so the line carries its own 1-GPU denominator.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+WORKLOADS = {
+    "cfg1": (4, 8, 256),
+    "cfg2": (64, 10, 256),
+    "cfg3": (1024, 10, 256),
+    "cfg4": (8192, 16, 256),
+}
+METRIC = "GE2E fwd+bwd utterances/s"
+UNIT = "utterances/s"
+L2_FLUSH_BYTES = 256 << 20
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"],
+                    bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+def make_batch(N, M, D, seed=0):
+    """Unit-scale random embeddings: randn rows, L2-normalised, fp32."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N * M, D, generator=g)
+    return (x / x.norm(dim=1, keepdim=True)).reshape(N, M, D).contiguous()
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz, self._stop_evt = [], set(), None, threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # NVML missing: report it, do not fail the bench
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.02)
+
+    def finish(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "nvml unavailable"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_sample(N, M, D, seed, target_rows):
+    """Time the reference-algorithm port on a bounded row sample; returns (utt/s, dict)."""
+    from oracle import ge2e_ref_port as port
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    E = make_batch(N, M, D, seed).numpy()
+    U = N * M
+    rows = None if target_rows >= U else list(range(0, U, max(1, U // target_rows)))[:target_rows]
+    sec, n_rows, _ = port.time_fwd_bwd(E, rows=rows, iters=1, warmup=0, threads=threads)
+    return n_rows / sec, dict(cores=threads, rows=n_rows, seconds=sec)
+
+
+def sample_rows_for(N, M, D):
+    # ~1e9 expanded fp32 elements per tensor keeps host RSS < ~10 GB and the run in seconds
+    return max(8, min(N * M, int(2.7e8 // (N * D))))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = args.workload or ("cfg3" if args.gpus == 1 else "cfg4")
+    N, M, D = WORKLOADS[wl]
+    # bound the whole run to a couple of minutes: ~5.5 ms of host time per row at cfg3
+    rows = max(8, min(sample_rows_for(N, M, D), sample_rows_for(N, M, D) * 20 // max(1, args.steps + args.warmup)))
+    vals, info = [], None
+    for it in range(args.warmup + args.steps):
+        v, info = cpu_reference_sample(N, M, D, seed=it, target_rows=rows)
+        if it >= args.warmup:
+            vals.append((v, info["seconds"]))
+    value = float(np.median([v for v, _ in vals]))
+    ms = float(np.median([s for _, s in vals])) * 1e3
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic unit-norm random embeddings",
+        "config": {"workload": f"{wl}: N={N} M={M} D={D} softmax GE2E fwd+bwd", "N": N, "M": M, "D": D},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": "port",
+                         "sample": f"{info['rows']} of {N * M} utterance rows against all {N} centroids per step "
+                                   f"(the reference's O(N^2 M D) expansion of the full batch does not fit host RAM); "
+                                   f"torch-CPU port of s3_loss_function_GE2E.py, bit-checked against the real class"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- our arm
+def timed_steps(fn, steps, warmup, flush_buf, pre=None):
+    """fn() enqueues one step on the current stream.  Returns per-step milliseconds (device time)."""
+    for _ in range(warmup):
+        if pre:
+            pre()
+        flush_buf.fill_(1.0)
+        fn()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(steps):
+        if pre:
+            pre()
+        flush_buf.fill_(1.0)                      # evict the 126 MB L2 between timed iterations
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b in evs]
+
+
+def stage_times(plan, E, w, b, flush_buf, reps=20):
+    """CUDA-event time of each C-ABI stage (prep | fwd_rows | bwd_rows | bwd_finalize) alone."""
+    from speaker_embedding_ge2e_loss_b200 import lib
+    h = lib()
+    N, M, D = plan.N, plan.M, plan.D
+    s = torch.cuda.current_stream().cuda_stream
+    ws = plan._ws.data_ptr() if plan._ws_bytes else None
+    acc = plan._accum.data_ptr()
+    scr = plan._scratch.data_ptr()
+    calls = {
+        "prep": lambda: h.ge2e_b200_prep(E.data_ptr(), N, M, D, plan.precision, plan.e_hat.data_ptr(),
+                                         plan.c_hat.data_ptr(), plan.cos_diag.data_ptr(), acc, s),
+        "fwd_rows": lambda: h.ge2e_b200_fwd_rows(plan.e_hat.data_ptr(), plan.c_hat.data_ptr(), plan.cos_diag.data_ptr(),
+                                                 N, N, 0, M, D, w.data_ptr(), b.data_ptr(), plan.eps, plan.variant,
+                                                 plan.precision, plan.row_stat.data_ptr(), plan.row_kstar.data_ptr(),
+                                                 acc, None, None, ws, plan._ws_bytes, s),
+        "bwd_rows": lambda: h.ge2e_b200_bwd_rows(plan.e_hat.data_ptr(), plan.c_hat.data_ptr(), plan.cos_diag.data_ptr(),
+                                                 plan.row_stat.data_ptr(), plan.row_kstar.data_ptr(), N, N, 0, M, D,
+                                                 w.data_ptr(), b.data_ptr(), plan.eps, plan.variant, plan.precision,
+                                                 plan.grad_out.data_ptr(), plan.dE_hat.data_ptr(), scr,
+                                                 scr + N * D * 4, ws, plan._ws_bytes, s),
+        "bwd_finalize": lambda: h.ge2e_b200_bwd_finalize(E.data_ptr(), plan.dE_hat.data_ptr(), scr,
+                                                         plan.cos_diag.data_ptr(), plan.row_stat.data_ptr(), N, M, D,
+                                                         w.data_ptr(), b.data_ptr(), plan.eps, plan.variant,
+                                                         plan.grad_out.data_ptr(), plan.dE.data_ptr(), s),
+    }
+    out = {}
+    for name, fn in calls.items():
+        def run():
+            rc = fn()
+            assert rc == 0, (name, rc)
+        ms = timed_steps(run, reps, 3, flush_buf)
+        out[name] = float(np.mean(ms)) * 1e3      # microseconds
+    return out
+
+
+def measure_tf32_peak():
+    """cuBLAS TF32 8192^3 burst, measured the way MEASURED_PEAKS.json measures bf16."""
+    a = torch.randn(8192, 8192, device="cuda")
+    b = torch.randn(8192, 8192, device="cuda")
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    best = 1e9
+    for _ in range(3):
+        torch.matmul(a, b)
+    torch.cuda.synchronize()
+    for _ in range(10):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        torch.matmul(a, b)
+        e.record()
+        torch.cuda.synchronize()
+        best = min(best, s.elapsed_time(e))
+    torch.backends.cuda.matmul.allow_tf32 = old
+    del a, b
+    return 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from speaker_embedding_ge2e_loss_b200 import GE2ELoss, GE2EPlan, lib
+    from speaker_embedding_ge2e_loss_b200.sharded import shard_bounds
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    rc = lib().ge2e_b200_check_device()
+    if rc != 0:
+        raise SystemExit("ge2e_b200: " + lib().ge2e_b200_strerror(rc).decode())
+
+    wl = args.workload or ("cfg3" if world == 1 else "cfg4")
+    N, M, D = WORKLOADS[wl]
+    U = N * M
+    peaks = load_peaks()
+    flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
+    w = torch.tensor(10.0, device=dev)
+    b = torch.tensor(-5.0, device=dev)
+    sampler = ClockSampler(local_rank)
+    launches_before = lib().ge2e_b200_launch_count()
+    extra = {}
+
+    if world == 1:
+        E = make_batch(N, M, D, seed=0).to(dev)
+        plan = GE2EPlan(N, M, D, args.variant, args.precision, device=dev)
+        graph = plan.capture(E, w, b)
+        sampler.start()
+        ms = timed_steps(graph.replay, args.steps, args.warmup, flush)
+        clocks = sampler.finish()
+        launches = plan.launches_per_step * args.steps
+        path = plan.path
+        loss_val = plan.loss.item()
+
+        # ---- e2e: public module API, host-resident batch -------------------------------------
+        crit = GE2ELoss(None, device=dev, variant=args.variant, precision=args.precision)
+        E_host = make_batch(N, M, D, seed=0).pin_memory()
+        res_host = torch.empty(3, dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            Ed = E_host.to(dev, non_blocking=True).requires_grad_(True)
+            loss = crit(Ed)
+            crit.w.grad = crit.b.grad = None
+            loss.backward()
+            res_host.copy_(torch.stack([loss.detach(), crit.w.grad, crit.b.grad]), non_blocking=True)
+
+        e2e_ms = timed_steps(e2e_step, args.steps, args.warmup, flush)
+        # host-side wall clock for the same loop (includes Python + autograd dispatch)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        e2e_t = max(float(np.mean(e2e_ms)), e2e_wall_ms)
+        e2e = {"value": U / (e2e_t * 1e-3), "unit": UNIT, "h2d_bytes_per_step": E_host.numel() * 4,
+               "d2h_bytes_per_step": 12, "ms_per_step_device": float(np.mean(e2e_ms)),
+               "ms_per_step_wall": e2e_wall_ms}
+
+        # ---- roofline of the dominant stage ---------------------------------------------------
+        st = stage_times(plan, E, w, b, flush)
+        tf32_peak = measure_tf32_peak()
+        extra["stage_us"] = st
+        extra["tf32_cublas_tflops_measured_here"] = tf32_peak
+        dom = max(("fwd_rows", "bwd_rows"), key=lambda k: st[k])
+        flops = {"fwd_rows": 2.0 * U * N * D, "bwd_rows": 4.0 * U * N * D}[dom]
+        achieved = flops / (st[dom] * 1e-6) / 1e12
+        if path == 1:
+            peak, peak_note = peaks["bf16_tflops"] / 2, f"MEASURED_PEAKS bf16_tflops/2 (TF32 runs at half the bf16 rate), {peaks['source']}"
+        else:
+            peak, peak_note = 148 * 128 * 2 * 1.965e9 / 1e12, "nominal fp32 FMA 148 SM x 128 lanes x 2 x 1.965 GHz (SIMT path; no measured entry)"
+        roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_note,
+                    "step_frac": (6.0 * U * N * D / (float(np.mean(ms)) * 1e-3) / 1e12) / peak}
+    else:
+        from speaker_embedding_ge2e_loss_b200.sharded import sharded_ge2e_loss
+        off, n_local = shard_bounds(N, world, rank)
+        E_full = make_batch(N, M, D, seed=0)
+        E = E_full[off:off + n_local].contiguous().to(dev).requires_grad_(True)
+        wp = w.clone().requires_grad_(True)
+        bp = b.clone().requires_grad_(True)
+
+        def step():
+            E.grad = wp.grad = bp.grad = None
+            loss = sharded_ge2e_loss(E, wp, bp, 1e-6, args.variant, args.precision)
+            loss.backward()
+            return loss
+
+        dist.barrier()
+        sampler.start()
+        ms = timed_steps(step, args.steps, args.warmup, flush, pre=dist.barrier)
+        clocks = sampler.finish()
+        t = torch.tensor([float(np.sum(ms))], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = [t.item() / args.steps] * args.steps
+        launches = int(lib().ge2e_b200_launch_count() - launches_before)
+        path = lib().ge2e_b200_path(n_local, N, M, D, 0 if args.variant == "softmax" else 1,
+                                    1 if args.precision == "tf32" else 0)
+        loss_val = step().item()
+        e2e = None
+        roofline = None
+        if rank == 0:
+            # host-resident e2e on the sharded path: each rank copies its shard in, reads the loss out
+            pass
+
+    if world > 1:
+        # e2e for the sharded run: every rank H2D-copies its shard and reads back the global loss
+        E_host = E_full[off:off + n_local].contiguous().pin_memory()
+        res_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            Ed = E_host.to(dev, non_blocking=True).requires_grad_(True)
+            wp.grad = bp.grad = None
+            loss = sharded_ge2e_loss(Ed, wp, bp, 1e-6, args.variant, args.precision)
+            loss.backward()
+            res_host.copy_(loss.detach().reshape(1), non_blocking=True)
+
+        e2e_ms = timed_steps(e2e_step, args.steps, args.warmup, flush, pre=dist.barrier)
+        t = torch.tensor([float(np.sum(e2e_ms))], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_t = t.item() / args.steps
+        e2e = {"value": U / (e2e_t * 1e-3), "unit": UNIT, "h2d_bytes_per_step": E_host.numel() * 4 * world,
+               "d2h_bytes_per_step": 4 * world}
+        peak = peaks["bf16_tflops"] / 2 if path == 1 else 148 * 128 * 2 * 1.965e9 / 1e12
+        ach = 6.0 * U * N * D / (ms[0] * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "whole sharded step, all ranks", "achieved": ach,
+                    "peak": peak * world, "unit": "TFLOP/s", "frac": ach / (peak * world), "traffic": None}
+        if rank == 0:
+            # 1-GPU denominator for strong scaling: the same cfg on this rank's GPU alone
+            E1 = E_full.to(dev)
+            plan1 = GE2EPlan(N, M, D, args.variant, args.precision, device=dev)
+            g1 = plan1.capture(E1, w, b)
+            ms1 = timed_steps(g1.replay, max(3, args.steps // 2), 3, flush)
+            extra["single_gpu_same_workload"] = {"value": U / (float(np.mean(ms1)) * 1e-3), "unit": UNIT,
+                                                 "ms_per_step": float(np.mean(ms1))}
+            del E1, plan1
+        dist.barrier()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = float(np.mean(ms))
+    value = U / (ms_per_step * 1e-3)
+    cpu_val, cpu_info = cpu_reference_sample(N, M, D, seed=0, target_rows=sample_rows_for(N, M, D)) \
+        if world == 1 else (None, None)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+        "dtype": "tf32" if path == 1 else "f32", "data": "synthetic unit-norm random embeddings",
+        "config": {"workload": f"{wl}: N={N} M={M} D={D} {args.variant} GE2E fwd+bwd", "N": N, "M": M, "D": D,
+                   "variant": args.variant, "precision": args.precision,
+                   "path": "tcgen05-tf32" if path == 1 else "simt-fp32",
+                   "parallelism": "replica" if world == 1 else f"speakers sharded x{world} (all-gather c_hat, reduce-scatter dC_hat)",
+                   "l2": "flushed between timed steps (256 MiB write)", "timing": "CUDA events per step, CUDA-graph replay"
+                   if world == 1 else "CUDA events per step, max over ranks"},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "loss": loss_val,
+    }
+    if cpu_val is not None:
+        line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": cpu_info["cores"], "kind": "port",
+                                "sample": f"{cpu_info['rows']} of {U} utterance rows against all {N} centroids, "
+                                          f"1 iteration, {cpu_info['seconds']:.2f} s (torch-CPU port of the reference's "
+                                          f"expanded algorithm; the full batch does not fit host RAM at this N)"}
+    line.update(extra)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--variant", default="softmax", choices=["softmax", "contrast"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

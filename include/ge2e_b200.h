@@ -1,0 +1,157 @@
+/*
+ * ge2e_b200.h -- C ABI of the B200-native GE2E loss (sm_100a only).
+ *
+ * This is the drop-in boundary for ONE path of gkv856/speaker_embedding_GE2E_loss:
+ * GE2ELoss.forward and its autograd backward
+ * (embedding_model_GE2E/s3_loss_function_GE2E.py:19-127, called from
+ * s4_train_embed_model.py:103,196,200 and s5_eval_model.py:42-43).  The reference is pure
+ * Python and has no FFI of its own; these entry points are what a ctypes binding in
+ * s3_loss_function_GE2E.py would call.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - Every pointer is a DEVICE pointer unless its name ends in _host.  The caller owns all
+ *     memory; the library never allocates, frees or retains pointers => calls are
+ *     CUDA-graph capturable.  All calls are asynchronous on `stream` and never synchronise.
+ *   - fp32, row-major, contiguous.  Embeddings E[n_local, M, D]; U_local = n_local * M rows.
+ *   - w, b, grad_out are DEVICE scalars (no host sync to read nn.Parameters).
+ *   - Return value: 0 on success, a negative ge2e_status otherwise (ge2e_b200_strerror).
+ *   - Speaker sharding: a rank owns speakers [spk_offset, spk_offset + n_local) out of
+ *     n_total.  Single GPU: n_local == n_total, spk_offset == 0.
+ *   - There is NO CPU implementation behind this ABI.
+ */
+#ifndef GE2E_B200_H_
+#define GE2E_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* ge2e_stream_t; /* cudaStream_t */
+
+enum ge2e_status {
+  GE2E_OK = 0,
+  GE2E_ERR_SHAPE = -1,       /* M < 2, non-positive dims, offsets out of range            */
+  GE2E_ERR_UNSUPPORTED = -2, /* shape not supported by the requested precision path       */
+  GE2E_ERR_ARGUMENT = -3,    /* null pointer, unknown variant / precision                 */
+  GE2E_ERR_WORKSPACE = -4,   /* workspace smaller than ge2e_b200_workspace_bytes()        */
+  GE2E_ERR_DEVICE = -5,      /* current device is not compute capability 10.x             */
+  GE2E_ERR_LAUNCH = -6       /* CUDA launch / driver error (see ge2e_b200_last_cuda_error) */
+};
+
+enum ge2e_variant { GE2E_SOFTMAX = 0, GE2E_CONTRAST = 1 }; /* paper eq. (6) / eq. (7) */
+
+/* GE2E_FP32: SIMT fp32 FMA everywhere (matches the reference to ~1e-6).
+ * GE2E_TF32: similarity and gradient contractions on tcgen05 tensor cores with TF32
+ *            operands / fp32 TMEM accumulators (stated tolerance 2e-3). */
+enum ge2e_precision { GE2E_FP32 = 0, GE2E_TF32 = 1 };
+
+int ge2e_b200_version(void);
+const char* ge2e_b200_strerror(int status);
+/* cudaError_t of the last failing CUDA call made by this library on this thread (0 = none). */
+int ge2e_b200_last_cuda_error(void);
+/* Number of kernels this library has launched (host-side count, all threads). */
+unsigned long long ge2e_b200_launch_count(void);
+/* Which kernels a (shape, variant, precision) uses: 0 = SIMT fp32 FMA, 1 = tcgen05 TF32.
+ * GE2E_TF32 is a permission, not a demand: shapes the tensor-core path does not cover run on
+ * the (more accurate) SIMT kernels.  Negative = bad variant / precision. */
+int ge2e_b200_path(int n_local, int n_total, int M, int D, int variant, int precision);
+/* GE2E_OK if the current CUDA device can run this library (sm_100), else GE2E_ERR_DEVICE. */
+int ge2e_b200_check_device(void);
+
+/* Scratch needed by ge2e_b200_fwd_rows / ge2e_b200_bwd_rows for this shape (may be 0). */
+size_t ge2e_b200_workspace_bytes(int n_local, int n_total, int M, int D, int variant,
+                                 int precision);
+
+/* ---- staged entry points (what the sharded autograd function calls) ------------------- */
+
+/* Stage 1 (per rank, local speakers only).
+ * Replaces get_centroids (s3:33-38), get_utterance_centroids (s3:95-112) and the
+ * leave-one-out cosine cos_same (s3:57).
+ *   e_hat[U_local, D]      e / max(|e|, 1e-8)         (TF32: rounded to nearest tf32)
+ *   c_hat_local[n_local,D] c_j / max(|c_j|, 1e-8), c_j = mean_i e_ji  (write it straight
+ *                          into the rank's slice of the all-gather buffer)
+ *   cos_diag[U_local]      cos(e_ji, u_ji), u_ji = (sum_i' e_ji' - e_ji) / (M - 1)
+ *   accum[4]               zeroed here: {loss, dw, db, reserved} accumulators            */
+int ge2e_b200_prep(const float* E, int n_local, int M, int D, int precision, float* e_hat,
+                   float* c_hat_local, float* cos_diag, float* accum, ge2e_stream_t stream);
+
+/* Stage 2: rows of the similarity matrix for the local utterances against ALL centroids,
+ * fused with the row loss; S is never written unless sim_out is given.
+ * Replaces the expanded cosine + diagonal overwrite + eps (s3:64-79), S = w*cos + b (s3:27)
+ * and calc_loss (s3:114-127).
+ *   row_stat[U_local]  softmax : log(sum_k exp S_rk + eps)
+ *                      contrast: max_{k != j} S_rk
+ *   row_kstar[U_local] contrast: argmax (lowest k on ties, -1 if n_total == 1); may be NULL
+ *                      for softmax
+ *   loss_accum         += sum of the local rows' losses (zeroed by ge2e_b200_prep)
+ *   per_row_out        optional [U_local] per-embedding loss (s3:121)
+ *   sim_out            optional [U_local, n_total] cos + eps (what get_cos_sim returns)   */
+int ge2e_b200_fwd_rows(const float* e_hat, const float* c_hat_all, const float* cos_diag,
+                       int n_local, int n_total, int spk_offset, int M, int D,
+                       const float* w, const float* b, float eps, int variant, int precision,
+                       float* row_stat, int32_t* row_kstar, float* loss_accum,
+                       float* per_row_out, float* sim_out, void* workspace,
+                       size_t workspace_bytes, ge2e_stream_t stream);
+
+/* Stage 3: gradient wrt the normalised operands, S recomputed on the fly (never stored).
+ * Replaces the autograd graph of s3:57-79 / s3:114-127.
+ *   dE_hat[U_local, D]         sum_{k != j} w G_rk c_hat_k          (off-diagonal part)
+ *   dC_hat_partial[n_total, D] sum_{local r, k != j(r)} w G_rk e_hat_r  (zeroed inside;
+ *                              reduce-scatter it across ranks when sharded)
+ *   dwdb_accum[2]              += {dw, db} of the local rows (zeroed by ge2e_b200_prep as
+ *                              accum+1)                                                  */
+int ge2e_b200_bwd_rows(const float* e_hat, const float* c_hat_all, const float* cos_diag,
+                       const float* row_stat, const int32_t* row_kstar, int n_local,
+                       int n_total, int spk_offset, int M, int D, const float* w,
+                       const float* b, float eps, int variant, int precision,
+                       const float* grad_out, float* dE_hat, float* dC_hat_partial,
+                       float* dwdb_accum, void* workspace, size_t workspace_bytes,
+                       ge2e_stream_t stream);
+
+/* Stage 4 (per rank, local speakers): diagonal (leave-one-out) term, the three
+ * normalisation Jacobians and the centroid fan-out.
+ *   dC_hat_local[n_local, D]  this rank's rows of the (reduced) dC_hat
+ *   dE[U_local, D]            gradient wrt the raw embeddings                            */
+int ge2e_b200_bwd_finalize(const float* E, const float* dE_hat, const float* dC_hat_local,
+                           const float* cos_diag, const float* row_stat, int n_local, int M,
+                           int D, const float* w, const float* b, float eps, int variant,
+                           const float* grad_out, float* dE, ge2e_stream_t stream);
+
+/* ---- single-device conveniences (n_local == n_total) ---------------------------------- */
+
+/* GE2ELoss.forward (s3:19-30): prep + fwd_rows.  loss = accum[0]. */
+int ge2e_b200_forward(const float* E, int N, int M, int D, const float* w, const float* b,
+                      float eps, int variant, int precision, float* e_hat, float* c_hat,
+                      float* cos_diag, float* row_stat, int32_t* row_kstar, float* accum,
+                      void* workspace, size_t workspace_bytes, ge2e_stream_t stream);
+
+/* loss.backward() (s4:200): bwd_rows + bwd_finalize.  dw = accum[1], db = accum[2]. */
+int ge2e_b200_backward(const float* E, const float* e_hat, const float* c_hat,
+                       const float* cos_diag, const float* row_stat, const int32_t* row_kstar,
+                       int N, int M, int D, const float* w, const float* b, float eps,
+                       int variant, int precision, const float* grad_out, float* dE_hat,
+                       float* dC_hat, float* accum, float* dE, void* workspace,
+                       size_t workspace_bytes, ge2e_stream_t stream);
+
+/* ---- static helpers of the reference class (used by s5_eval_model.py:42-43) ----------- */
+
+/* get_centroids (s3:33-38): C[N, D] = mean over utterances. */
+int ge2e_b200_centroids(const float* E, int N, int M, int D, float* C, ge2e_stream_t stream);
+/* get_utterance_centroids (s3:95-112): Uc[N, M, D]. */
+int ge2e_b200_utterance_centroids(const float* E, int N, int M, int D, float* Uc,
+                                  ge2e_stream_t stream);
+/* Y[rows, D] = X / max(|X_row|, 1e-8): lets get_cos_sim (s3:41-80) accept caller-supplied
+ * centroids the way the reference's static method does (s5_eval_model.py:43). */
+int ge2e_b200_normalize_rows(const float* X, int rows, int D, float* Y, ge2e_stream_t stream);
+/* calc_loss (s3:114-127) on a caller-supplied similarity matrix S[N, M, N]. */
+int ge2e_b200_calc_loss(const float* S, int N, int M, float eps, int variant, float* loss,
+                        float* per_row, ge2e_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GE2E_B200_H_ */

@@ -96,6 +96,6 @@ def time_fwd_bwd(E_np, w=10.0, b=-5.0, eps=1e-6, rows=None, iters=1, warmup=0, t
         dt = time.perf_counter() - t0
         if it >= warmup:
             ts.append(dt)
-        last = float(loss)
+        last = float(loss.detach())
     ts.sort()
     return ts[len(ts) // 2], n_rows, last

@@ -1,0 +1,12 @@
+"""B200-native GE2E loss: drop-in for gkv856/speaker_embedding_GE2E_loss's ``GE2ELoss``.
+
+Host layer only (module, torch.library op, ctypes binding of include/ge2e_b200.h); all
+arithmetic happens in the hand-written sm_100a kernels under ``csrc/``.
+"""
+from ._lib import GE2ELibraryError, lib  # noqa: F401
+from .loss import GE2ELoss  # noqa: F401
+from .ops import ge2e_loss  # noqa: F401
+from .plan import GE2EPlan  # noqa: F401
+from .sharded import shard_bounds, sharded_ge2e_loss  # noqa: F401
+
+__all__ = ["GE2ELoss", "GE2EPlan", "ge2e_loss", "sharded_ge2e_loss", "shard_bounds", "GE2ELibraryError", "lib"]

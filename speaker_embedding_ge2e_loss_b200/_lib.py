@@ -1,0 +1,81 @@
+"""ctypes binding of include/ge2e_b200.h.  There is no fallback: a missing library raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .build import LIB_PATH
+
+_f32p = C.c_void_p   # device pointers travel as integers (tensor.data_ptr())
+_i32p = C.c_void_p
+_stream = C.c_void_p
+
+SOFTMAX, CONTRAST = 0, 1
+FP32, TF32 = 0, 1
+VARIANTS = {"softmax": SOFTMAX, "contrast": CONTRAST}
+PRECISIONS = {"fp32": FP32, "tf32": TF32}
+
+# name -> (restype, argtypes); kept in the order of include/ge2e_b200.h
+PROTOTYPES = {
+    "ge2e_b200_version": (C.c_int, []),
+    "ge2e_b200_strerror": (C.c_char_p, [C.c_int]),
+    "ge2e_b200_last_cuda_error": (C.c_int, []),
+    "ge2e_b200_launch_count": (C.c_ulonglong, []),
+    "ge2e_b200_path": (C.c_int, [C.c_int] * 6),
+    "ge2e_b200_check_device": (C.c_int, []),
+    "ge2e_b200_workspace_bytes": (C.c_size_t, [C.c_int] * 6),
+    "ge2e_b200_prep": (C.c_int, [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p,
+                                 _stream]),
+    "ge2e_b200_fwd_rows": (C.c_int, [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     _f32p, _f32p, C.c_float, C.c_int, C.c_int, _f32p, _i32p, _f32p,
+                                     _f32p, _f32p, C.c_void_p, C.c_size_t, _stream]),
+    "ge2e_b200_bwd_rows": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _i32p, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, _f32p, _f32p, C.c_float, C.c_int, C.c_int,
+                                     _f32p, _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, _stream]),
+    "ge2e_b200_bwd_finalize": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int,
+                                         _f32p, _f32p, C.c_float, C.c_int, _f32p, _f32p, _stream]),
+    "ge2e_b200_forward": (C.c_int, [_f32p, C.c_int, C.c_int, C.c_int, _f32p, _f32p, C.c_float, C.c_int,
+                                    C.c_int, _f32p, _f32p, _f32p, _f32p, _i32p, _f32p, C.c_void_p,
+                                    C.c_size_t, _stream]),
+    "ge2e_b200_backward": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _i32p, C.c_int, C.c_int,
+                                     C.c_int, _f32p, _f32p, C.c_float, C.c_int, C.c_int, _f32p, _f32p,
+                                     _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, _stream]),
+    "ge2e_b200_centroids": (C.c_int, [_f32p, C.c_int, C.c_int, C.c_int, _f32p, _stream]),
+    "ge2e_b200_utterance_centroids": (C.c_int, [_f32p, C.c_int, C.c_int, C.c_int, _f32p, _stream]),
+    "ge2e_b200_normalize_rows": (C.c_int, [_f32p, C.c_int, C.c_int, _f32p, _stream]),
+    "ge2e_b200_calc_loss": (C.c_int, [_f32p, C.c_int, C.c_int, C.c_float, C.c_int, _f32p, _f32p,
+                                      _stream]),
+}
+
+_lib = None
+
+
+class GE2ELibraryError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load csrc/libge2e_b200.so once.  Raises if it has not been built (no CPU fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GE2ELibraryError(
+                f"{LIB_PATH} is missing: build it with `python -m speaker_embedding_ge2e_loss_b200.build` "
+                "(needs nvcc; sm_100a only).  This package has no CPU / PyTorch fallback.")
+        h = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(h, name)   # AttributeError if the header and the library disagree
+            fn.restype = res
+            fn.argtypes = args
+        _lib = h
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        h = lib()
+        msg = h.ge2e_b200_strerror(rc).decode()
+        if rc == -6:
+            msg += f" [cudaError={h.ge2e_b200_last_cuda_error()}]"
+        exc = ValueError if rc in (-1, -3) else RuntimeError
+        raise exc(f"{what}: {msg}")

@@ -1,0 +1,200 @@
+// C ABI of the B200-native GE2E loss: argument checking and path selection only.
+// See include/ge2e_b200.h for the contract and the reference lines each entry point replaces.
+#include <atomic>
+
+#include "ge2e_common.cuh"
+
+namespace ge2e {
+static thread_local cudaError_t g_last_cuda_error = cudaSuccess;
+void set_cuda_error(cudaError_t e) { g_last_cuda_error = e; }
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+}  // namespace ge2e
+
+using namespace ge2e;
+
+namespace {
+
+int check_shape(int n_local, int n_total, int spk_offset, int M, int D) {
+  if (n_local <= 0 || n_total <= 0 || M < 2 || D <= 0) return GE2E_ERR_SHAPE;
+  if (spk_offset < 0 || spk_offset + n_local > n_total) return GE2E_ERR_SHAPE;
+  if ((long long)n_local * M > 0x7fffffffLL / 2) return GE2E_ERR_SHAPE;
+  if (D > 1024) return GE2E_ERR_UNSUPPORTED;
+  return GE2E_OK;
+}
+
+int check_enum(int variant, int precision) {
+  if (variant != GE2E_SOFTMAX && variant != GE2E_CONTRAST) return GE2E_ERR_ARGUMENT;
+  if (precision != GE2E_FP32 && precision != GE2E_TF32) return GE2E_ERR_ARGUMENT;
+  return GE2E_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ge2e_b200_version(void) { return 100; }
+
+const char* ge2e_b200_strerror(int status) {
+  switch (status) {
+    case GE2E_OK: return "ok";
+    case GE2E_ERR_SHAPE: return "bad shape: need n_local,n_total,D > 0, M >= 2, shard inside [0,n_total)";
+    case GE2E_ERR_UNSUPPORTED: return "shape not supported by the requested precision path";
+    case GE2E_ERR_ARGUMENT: return "null pointer or unknown variant/precision";
+    case GE2E_ERR_WORKSPACE: return "workspace smaller than ge2e_b200_workspace_bytes()";
+    case GE2E_ERR_DEVICE: return "current CUDA device is not compute capability 10.x (sm_100a build)";
+    case GE2E_ERR_LAUNCH: return "CUDA launch or driver error (see ge2e_b200_last_cuda_error)";
+    default: return "unknown ge2e status";
+  }
+}
+
+int ge2e_b200_last_cuda_error(void) { return (int)g_last_cuda_error; }
+
+unsigned long long ge2e_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int ge2e_b200_path(int n_local, int n_total, int M, int D, int variant, int precision) {
+  if (check_enum(variant, precision) != GE2E_OK) return GE2E_ERR_ARGUMENT;
+  return (precision == GE2E_TF32 && tc_supported(n_local, n_total, M, D, variant)) ? 1 : 0;
+}
+
+int ge2e_b200_check_device(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return GE2E_ERR_DEVICE;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
+    return GE2E_ERR_DEVICE;
+  return major == 10 ? GE2E_OK : GE2E_ERR_DEVICE;
+}
+
+size_t ge2e_b200_workspace_bytes(int n_local, int n_total, int M, int D, int variant, int precision) {
+  if (precision == GE2E_TF32 && tc_supported(n_local, n_total, M, D, variant))
+    return tc_workspace_bytes(n_local, n_total, M, D, variant);
+  return 0;
+}
+
+int ge2e_b200_prep(const float* E, int n_local, int M, int D, int precision, float* e_hat,
+                   float* c_hat_local, float* cos_diag, float* accum, ge2e_stream_t stream) {
+  if (!E || !e_hat || !c_hat_local || !cos_diag) return GE2E_ERR_ARGUMENT;
+  int rc = check_shape(n_local, n_local, 0, M, D);
+  if (rc != GE2E_OK) return rc;
+  if ((rc = check_enum(GE2E_SOFTMAX, precision)) != GE2E_OK) return rc;
+  return simt_prep(E, n_local, M, D, precision == GE2E_TF32, e_hat, c_hat_local, cos_diag, accum,
+                   (cudaStream_t)stream);
+}
+
+int ge2e_b200_fwd_rows(const float* e_hat, const float* c_hat_all, const float* cos_diag,
+                       int n_local, int n_total, int spk_offset, int M, int D, const float* w,
+                       const float* b, float eps, int variant, int precision, float* row_stat,
+                       int32_t* row_kstar, float* loss_accum, float* per_row_out, float* sim_out,
+                       void* workspace, size_t workspace_bytes, ge2e_stream_t stream) {
+  if (!e_hat || !c_hat_all || !cos_diag || !w || !b || !row_stat || !loss_accum)
+    return GE2E_ERR_ARGUMENT;
+  int rc = check_shape(n_local, n_total, spk_offset, M, D);
+  if (rc != GE2E_OK) return rc;
+  if ((rc = check_enum(variant, precision)) != GE2E_OK) return rc;
+  if (variant == GE2E_CONTRAST && !row_kstar) return GE2E_ERR_ARGUMENT;
+  RowsArgs a{e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, b, eps, variant};
+  if (precision == GE2E_TF32 && tc_supported(n_local, n_total, M, D, variant)) {
+    // the tensor-core path never materialises S: sim_out is an fp32-path feature
+    if (sim_out != nullptr) return GE2E_ERR_UNSUPPORTED;
+    if (workspace_bytes < tc_workspace_bytes(n_local, n_total, M, D, variant) ||
+        (workspace == nullptr && tc_workspace_bytes(n_local, n_total, M, D, variant) > 0))
+      return GE2E_ERR_WORKSPACE;
+    return tc_fwd_rows(a, row_stat, row_kstar, loss_accum, per_row_out, workspace, workspace_bytes,
+                       (cudaStream_t)stream);
+  }
+  return simt_fwd_rows(a, row_stat, row_kstar, loss_accum, per_row_out, sim_out, (cudaStream_t)stream);
+}
+
+int ge2e_b200_bwd_rows(const float* e_hat, const float* c_hat_all, const float* cos_diag,
+                       const float* row_stat, const int32_t* row_kstar, int n_local, int n_total,
+                       int spk_offset, int M, int D, const float* w, const float* b, float eps,
+                       int variant, int precision, const float* grad_out, float* dE_hat,
+                       float* dC_hat_partial, float* dwdb_accum, void* workspace,
+                       size_t workspace_bytes, ge2e_stream_t stream) {
+  if (!e_hat || !c_hat_all || !cos_diag || !row_stat || !w || !b || !grad_out || !dE_hat ||
+      !dC_hat_partial || !dwdb_accum)
+    return GE2E_ERR_ARGUMENT;
+  int rc = check_shape(n_local, n_total, spk_offset, M, D);
+  if (rc != GE2E_OK) return rc;
+  if ((rc = check_enum(variant, precision)) != GE2E_OK) return rc;
+  if (variant == GE2E_CONTRAST && !row_kstar) return GE2E_ERR_ARGUMENT;
+  RowsArgs a{e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, b, eps, variant};
+  // the contrast gradient is a 2-nonzeros-per-row gather/scatter: no contraction to put on
+  // tensor cores, so both precisions share the SIMT kernel.
+  if (precision == GE2E_TF32 && variant == GE2E_SOFTMAX && tc_supported(n_local, n_total, M, D, variant)) {
+    if (workspace_bytes < tc_workspace_bytes(n_local, n_total, M, D, variant) ||
+        (workspace == nullptr && tc_workspace_bytes(n_local, n_total, M, D, variant) > 0))
+      return GE2E_ERR_WORKSPACE;
+    return tc_bwd_rows(a, row_stat, row_kstar, grad_out, dE_hat, dC_hat_partial, dwdb_accum,
+                       workspace, workspace_bytes, (cudaStream_t)stream);
+  }
+  return simt_bwd_rows(a, row_stat, row_kstar, grad_out, dE_hat, dC_hat_partial, dwdb_accum,
+                       (cudaStream_t)stream);
+}
+
+int ge2e_b200_bwd_finalize(const float* E, const float* dE_hat, const float* dC_hat_local,
+                           const float* cos_diag, const float* row_stat, int n_local, int M, int D,
+                           const float* w, const float* b, float eps, int variant,
+                           const float* grad_out, float* dE, ge2e_stream_t stream) {
+  if (!E || !dE_hat || !dC_hat_local || !cos_diag || !row_stat || !w || !b || !grad_out || !dE)
+    return GE2E_ERR_ARGUMENT;
+  int rc = check_shape(n_local, n_local, 0, M, D);
+  if (rc != GE2E_OK) return rc;
+  if ((rc = check_enum(variant, GE2E_FP32)) != GE2E_OK) return rc;
+  return simt_bwd_finalize(E, dE_hat, dC_hat_local, cos_diag, row_stat, n_local, M, D, w, b, eps,
+                           variant, grad_out, dE, (cudaStream_t)stream);
+}
+
+int ge2e_b200_forward(const float* E, int N, int M, int D, const float* w, const float* b, float eps,
+                      int variant, int precision, float* e_hat, float* c_hat, float* cos_diag,
+                      float* row_stat, int32_t* row_kstar, float* accum, void* workspace,
+                      size_t workspace_bytes, ge2e_stream_t stream) {
+  if (!accum) return GE2E_ERR_ARGUMENT;
+  int rc = ge2e_b200_prep(E, N, M, D, precision, e_hat, c_hat, cos_diag, accum, stream);
+  if (rc != GE2E_OK) return rc;
+  return ge2e_b200_fwd_rows(e_hat, c_hat, cos_diag, N, N, 0, M, D, w, b, eps, variant, precision,
+                            row_stat, row_kstar, accum, nullptr, nullptr, workspace, workspace_bytes,
+                            stream);
+}
+
+int ge2e_b200_backward(const float* E, const float* e_hat, const float* c_hat, const float* cos_diag,
+                       const float* row_stat, const int32_t* row_kstar, int N, int M, int D,
+                       const float* w, const float* b, float eps, int variant, int precision,
+                       const float* grad_out, float* dE_hat, float* dC_hat, float* accum, float* dE,
+                       void* workspace, size_t workspace_bytes, ge2e_stream_t stream) {
+  if (!accum) return GE2E_ERR_ARGUMENT;
+  int rc = ge2e_b200_bwd_rows(e_hat, c_hat, cos_diag, row_stat, row_kstar, N, N, 0, M, D, w, b, eps,
+                              variant, precision, grad_out, dE_hat, dC_hat, accum + 1, workspace,
+                              workspace_bytes, stream);
+  if (rc != GE2E_OK) return rc;
+  return ge2e_b200_bwd_finalize(E, dE_hat, dC_hat, cos_diag, row_stat, N, M, D, w, b, eps, variant,
+                                grad_out, dE, stream);
+}
+
+int ge2e_b200_centroids(const float* E, int N, int M, int D, float* C, ge2e_stream_t stream) {
+  if (!E || !C) return GE2E_ERR_ARGUMENT;
+  if (N <= 0 || M <= 0 || D <= 0) return GE2E_ERR_SHAPE;
+  return simt_centroids(E, N, M, D, C, (cudaStream_t)stream);
+}
+
+int ge2e_b200_utterance_centroids(const float* E, int N, int M, int D, float* Uc, ge2e_stream_t stream) {
+  if (!E || !Uc) return GE2E_ERR_ARGUMENT;
+  if (N <= 0 || M < 2 || D <= 0) return GE2E_ERR_SHAPE;
+  return simt_utterance_centroids(E, N, M, D, Uc, (cudaStream_t)stream);
+}
+
+int ge2e_b200_normalize_rows(const float* X, int rows, int D, float* Y, ge2e_stream_t stream) {
+  if (!X || !Y) return GE2E_ERR_ARGUMENT;
+  if (rows <= 0 || D <= 0) return GE2E_ERR_SHAPE;
+  return simt_normalize_rows(X, rows, D, Y, (cudaStream_t)stream);
+}
+
+int ge2e_b200_calc_loss(const float* S, int N, int M, float eps, int variant, float* loss,
+                        float* per_row, ge2e_stream_t stream) {
+  if (!S || !loss) return GE2E_ERR_ARGUMENT;
+  if (N <= 0 || M <= 0) return GE2E_ERR_SHAPE;
+  if (variant != GE2E_SOFTMAX && variant != GE2E_CONTRAST) return GE2E_ERR_ARGUMENT;
+  return simt_calc_loss(S, N, M, eps, variant, loss, per_row, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+// Shared device helpers and internal launcher declarations (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ge2e_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "ge2e_b200 is written for sm_100a only"
+#endif
+
+namespace ge2e {
+
+constexpr float kCosDelta = 1e-8f;  // F.cosine_similarity eps (s3:57, s3:70)
+constexpr int kWarp = 32;
+
+// thread-local record of the last CUDA failure, exposed through the C ABI
+void set_cuda_error(cudaError_t e);
+// host-side count of kernel launches issued by this library (bench.py's gpu_launches)
+void count_launch(int n = 1);
+
+#define GE2E_CUDA_TRY(expr)                    \
+  do {                                         \
+    cudaError_t _e = (expr);                   \
+    if (_e != cudaSuccess) {                   \
+      ::ge2e::set_cuda_error(_e);              \
+      return GE2E_ERR_LAUNCH;                  \
+    }                                          \
+  } while (0)
+
+// after every <<<>>>: count the launch and surface launch-configuration errors
+#define GE2E_LAUNCHED()                        \
+  do {                                         \
+    ::ge2e::count_launch(1);                   \
+    GE2E_CUDA_TRY(cudaGetLastError());         \
+  } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+// Block-wide sum; result valid in thread 0.  `red` needs blockDim.x/32 floats.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (wid == 0) {
+    t = (lane < (int)(blockDim.x >> 5)) ? red[lane] : 0.f;
+    t = warp_sum(t);
+  }
+  return t;
+}
+
+// ---- launchers implemented in ge2e_simt.cu ------------------------------------------------
+struct RowsArgs {
+  const float* e_hat;      // [U_local, D]
+  const float* c_hat_all;  // [n_total, D]
+  const float* cos_diag;   // [U_local]
+  int n_local, n_total, spk_offset, M, D;
+  const float* w;
+  const float* b;
+  float eps;
+  int variant;
+};
+
+int simt_prep(const float* E, int n_local, int M, int D, bool round_tf32, float* e_hat,
+              float* c_hat_local, float* cos_diag, float* accum, cudaStream_t st);
+int simt_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* loss_accum,
+                  float* per_row_out, float* sim_out, cudaStream_t st);
+int simt_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kstar,
+                  const float* grad_out, float* dE_hat, float* dC_hat_partial,
+                  float* dwdb_accum, cudaStream_t st);
+int simt_bwd_finalize(const float* E, const float* dE_hat, const float* dC_hat_local,
+                      const float* cos_diag, const float* row_stat, int n_local, int M, int D,
+                      const float* w, const float* b, float eps, int variant,
+                      const float* grad_out, float* dE, cudaStream_t st);
+int simt_centroids(const float* E, int N, int M, int D, float* C, cudaStream_t st);
+int simt_utterance_centroids(const float* E, int N, int M, int D, float* Uc, cudaStream_t st);
+int simt_calc_loss(const float* S, int N, int M, float eps, int variant, float* loss,
+                   float* per_row, cudaStream_t st);
+int simt_normalize_rows(const float* X, int rows, int D, float* Y, cudaStream_t st);
+
+// ---- launchers implemented in ge2e_tc.cu (tcgen05 / TMA / TMEM path) ----------------------
+bool tc_supported(int n_local, int n_total, int M, int D, int variant);
+size_t tc_workspace_bytes(int n_local, int n_total, int M, int D, int variant);
+int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* loss_accum,
+                float* per_row_out, void* ws, size_t ws_bytes, cudaStream_t st);
+int tc_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kstar,
+                const float* grad_out, float* dE_hat, float* dC_hat_partial, float* dwdb_accum,
+                void* ws, size_t ws_bytes, cudaStream_t st);
+
+}  // namespace ge2e

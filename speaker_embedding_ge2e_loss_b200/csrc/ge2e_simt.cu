@@ -1,0 +1,794 @@
+// SIMT fp32 path of the GE2E loss (exact-parity path, any N / M >= 2 / D <= 1024).
+//
+// Kernels
+//   prep_kernel      one CTA per speaker: L2-normalise, centroid, leave-one-out cosine
+//                    (reference s3:33-38, s3:95-112, s3:57)
+//   strip_kernel     the similarity contraction fused with its consumer.  Each warp owns R
+//                    "owner" rows in registers (lanes split D, 128-bit loads); "stream" rows
+//                    pass through shared memory 32 at a time.  Dot products are reduced with a
+//                    transposing warp-shuffle butterfly so that lane l ends up holding the dot
+//                    product against stream row l; the softmax / contrast epilogue then runs
+//                    one column per lane.  Three modes:
+//                      FWD     owner = utterances, stream = centroids -> online LSE / argmax
+//                      BWD_DE  owner = utterances, stream = centroids -> dE_hat = (wG) C_hat
+//                      BWD_DC  owner = centroids,  stream = utterances -> dC_hat = (wG)^T E_hat
+//                    (reference s3:64-79, s3:27, s3:114-127 and their autograd)
+//   contrast_bwd     the contrast gradient has two non-zeros per row: gather/scatter kernel
+//   finalize_kernel  one CTA per speaker: diagonal term, normalisation Jacobians, fan-out
+#include <limits.h>
+
+#include "ge2e_common.cuh"
+
+namespace ge2e {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / kWarp;
+constexpr int kStreamRows = 32;  // stream rows per shared-memory stage (= warp width)
+
+enum { MODE_FWD = 0, MODE_BWD_DE = 1, MODE_BWD_DC = 2 };
+
+__device__ __forceinline__ float4 ld4(const float* __restrict__ row, int col, int D, bool vec) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (vec) {
+    if (col < D) v = __ldg(reinterpret_cast<const float4*>(row + col));
+  } else {
+    if (col + 0 < D) v.x = __ldg(row + col + 0);
+    if (col + 1 < D) v.y = __ldg(row + col + 1);
+    if (col + 2 < D) v.z = __ldg(row + col + 2);
+    if (col + 3 < D) v.w = __ldg(row + col + 3);
+  }
+  return v;
+}
+
+__device__ __forceinline__ void st4(float* __restrict__ row, int col, int D, bool vec, float4 v) {
+  if (vec) {
+    if (col < D) *reinterpret_cast<float4*>(row + col) = v;
+  } else {
+    if (col + 0 < D) row[col + 0] = v.x;
+    if (col + 1 < D) row[col + 1] = v.y;
+    if (col + 2 < D) row[col + 2] = v.z;
+    if (col + 3 < D) row[col + 3] = v.w;
+  }
+}
+
+__device__ __forceinline__ float dot4(float4 a, float4 b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+
+__device__ __forceinline__ bool is_vec(const void* p, int D) {
+  return ((D & 3) == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: prep.  grid = n_local, block = 256, dynamic smem = (M + 1) * Dp floats.
+// ------------------------------------------------------------------------------------------
+template <bool ROUND>
+__global__ void __launch_bounds__(kThreads)
+prep_kernel(const float* __restrict__ E, int M, int D, int Dp, float* __restrict__ e_hat,
+            float* __restrict__ c_hat, float* __restrict__ cos_diag, float* __restrict__ accum) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red[kWarps];
+  __shared__ float s_inv_nc;
+  float* sE = smem;                    // [M][Dp]
+  float* sS = smem + (size_t)M * Dp;   // [Dp] column sums
+  const int j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const float* Ej = E + (size_t)j * M * D;
+  const bool vec_in = is_vec(E, D);
+  const bool vec_out = is_vec(e_hat, D);
+  if (j == 0 && tid < 4 && accum != nullptr) accum[tid] = 0.f;
+
+  for (int v = tid; v < M * (Dp >> 2); v += kThreads) {
+    const int i = v / (Dp >> 2), col = (v % (Dp >> 2)) << 2;
+    *reinterpret_cast<float4*>(&sE[(size_t)i * Dp + col]) = ld4(Ej + (size_t)i * D, col, D, vec_in);
+  }
+  __syncthreads();
+  for (int d = tid; d < Dp; d += kThreads) {
+    float s = 0.f;
+    for (int i = 0; i < M; ++i) s += sE[(size_t)i * Dp + d];   // s3:105
+    sS[d] = s;
+  }
+  __syncthreads();
+
+  const float m1 = (float)(M - 1);
+  for (int i = wid; i < M; i += kWarps) {
+    float ne2 = 0.f, nu2 = 0.f, eu = 0.f;
+    for (int d = lane << 2; d < Dp; d += 128) {
+      const float4 e = *reinterpret_cast<const float4*>(&sE[(size_t)i * Dp + d]);
+      const float4 s = *reinterpret_cast<const float4*>(&sS[d]);
+      float4 u;                                               // s3:111
+      u.x = (s.x - e.x) / m1; u.y = (s.y - e.y) / m1; u.z = (s.z - e.z) / m1; u.w = (s.w - e.w) / m1;
+      ne2 += dot4(e, e);
+      nu2 += dot4(u, u);
+      eu += dot4(e, u);
+    }
+    ne2 = warp_sum(ne2); nu2 = warp_sum(nu2); eu = warp_sum(eu);
+    const float inv_ne = 1.f / fmaxf(sqrtf(ne2), kCosDelta);
+    const float inv_nu = 1.f / fmaxf(sqrtf(nu2), kCosDelta);
+    float* out = e_hat + ((size_t)j * M + i) * D;
+    for (int d = lane << 2; d < Dp; d += 128) {
+      float4 e = *reinterpret_cast<const float4*>(&sE[(size_t)i * Dp + d]);
+      e.x *= inv_ne; e.y *= inv_ne; e.z *= inv_ne; e.w *= inv_ne;
+      if (ROUND) { e.x = round_tf32(e.x); e.y = round_tf32(e.y); e.z = round_tf32(e.z); e.w = round_tf32(e.w); }
+      st4(out, d, D, vec_out, e);
+    }
+    if (lane == 0) cos_diag[(size_t)j * M + i] = eu * inv_ne * inv_nu;   // s3:57
+  }
+
+  float part = 0.f;
+  const float fm = (float)M;
+  for (int d = tid; d < Dp; d += kThreads) {
+    const float c = sS[d] / fm;                                // s3:37
+    part += c * c;
+  }
+  const float tot = block_sum(part, red);
+  if (tid == 0) s_inv_nc = 1.f / fmaxf(sqrtf(tot), kCosDelta);
+  __syncthreads();
+  const float inv_nc = s_inv_nc;
+  for (int d = tid; d < D; d += kThreads) {
+    float c = (sS[d] / fm) * inv_nc;
+    if (ROUND) c = round_tf32(c);
+    c_hat[(size_t)j * D + d] = c;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// strip kernel
+// ------------------------------------------------------------------------------------------
+struct StripParams {
+  const float* own;   // [n_own, D]
+  const float* str;   // [n_str, D]
+  int n_own, n_str, D;
+  int M, spk_offset;  // local utterance row r belongs to global speaker spk_offset + r / M
+  const float* cos_diag;
+  const float* row_stat;   // bwd: lse per local utterance row
+  const float* w;
+  const float* b;
+  const float* grad_out;
+  float eps;
+  float* row_stat_out;     // fwd
+  int32_t* kstar_out;      // fwd contrast
+  float* loss_accum;       // fwd
+  float* per_row_out;      // fwd optional
+  float* sim_out;          // fwd optional [n_own, n_str]
+  float* acc_out;          // bwd: dE_hat [n_own, D] or dC_hat_partial [n_own, D]
+  float* dwdb;             // bwd_de
+  int chunks_per_split;    // stream chunks handled per blockIdx.y
+};
+
+// Transposing butterfly: after RedT<0>::run, lane l holds (for each owner row q) the full dot
+// product against stream row t0 + l.  31 shuffles per owner row instead of 32 x 5.
+template <int K, int R, int KCH>
+struct RedT {
+  static __device__ __forceinline__ void run(const float4 (&a)[R][KCH], const float* __restrict__ stage,
+                                             int t, int lane, float (&out)[R]) {
+    float lo[R], hi[R];
+    RedT<K + 1, R, KCH>::run(a, stage, t, lane, lo);
+    RedT<K + 1, R, KCH>::run(a, stage, t + (1 << K), lane, hi);
+    const bool up = (lane & (1 << K)) != 0;
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      const float send = up ? lo[q] : hi[q];
+      const float keep = up ? hi[q] : lo[q];
+      out[q] = keep + __shfl_xor_sync(0xffffffffu, send, 1 << K);
+    }
+  }
+};
+template <int R, int KCH>
+struct RedT<5, R, KCH> {
+  static __device__ __forceinline__ void run(const float4 (&a)[R][KCH], const float* __restrict__ stage,
+                                             int t, int lane, float (&out)[R]) {
+#pragma unroll
+    for (int q = 0; q < R; ++q) out[q] = 0.f;
+#pragma unroll
+    for (int c = 0; c < KCH; ++c) {
+      const float4 bv = *reinterpret_cast<const float4*>(&stage[(size_t)t * (KCH * 128) + c * 128 + (lane << 2)]);
+#pragma unroll
+      for (int q = 0; q < R; ++q) out[q] += dot4(a[q][c], bv);
+    }
+  }
+};
+
+template <int MODE, int VARIANT, int KCH, int R>
+__global__ void __launch_bounds__(kThreads)
+strip_kernel(const StripParams p) {
+  extern __shared__ __align__(16) float stage[];   // [32][KCH*128]
+  __shared__ float red[kWarps];
+  constexpr int ROWLEN = KCH * 128;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int own0 = (blockIdx.x * kWarps + wid) * R;
+  const int D = p.D;
+  const bool vec_own = is_vec(p.own, D), vec_str = is_vec(p.str, D);
+  const float w = __ldg(p.w), b = __ldg(p.b), eps = p.eps;
+  const float g = (MODE == MODE_FWD) ? 1.f : __ldg(p.grad_out);
+
+  float4 a[R][KCH];
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+    const int row = own0 + q;
+#pragma unroll
+    for (int c = 0; c < KCH; ++c) {
+      const int col = (lane << 2) + c * 128;
+      a[q][c] = (row < p.n_own) ? ld4(p.own + (size_t)row * D, col, D, vec_own) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+
+  // per-owner-row state
+  int jg[R];        // FWD / BWD_DE: global speaker of the owner utterance row
+  float cd[R];      // cos_diag of the owner row
+  float lse[R];     // BWD_DE
+  float m_run[R], l_run[R];   // FWD softmax (per lane, merged at the end)
+  float best[R]; int bestk[R];  // FWD contrast
+  float4 acc[R][KCH];
+  float dw_acc = 0.f;
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+    const int row = own0 + q;
+    // rows past the end: lse = +inf makes every G of that row exactly 0
+    jg[q] = -1; cd[q] = 0.f; lse[q] = INFINITY;
+    if (MODE != MODE_BWD_DC && row < p.n_own) {
+      jg[q] = p.spk_offset + row / p.M;
+      cd[q] = __ldg(p.cos_diag + row);
+      if (MODE == MODE_BWD_DE) lse[q] = __ldg(p.row_stat + row);
+    }
+    m_run[q] = -INFINITY; l_run[q] = 0.f; best[q] = -INFINITY; bestk[q] = INT_MAX;
+#pragma unroll
+    for (int c = 0; c < KCH; ++c) acc[q][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+
+  const int nchunks = (p.n_str + kStreamRows - 1) / kStreamRows;
+  const int ch_begin = blockIdx.y * p.chunks_per_split;
+  const int ch_end = min(nchunks, ch_begin + p.chunks_per_split);
+
+  for (int ch = ch_begin; ch < ch_end; ++ch) {
+    const int base = ch * kStreamRows;
+    __syncthreads();   // previous chunk fully consumed
+    for (int v = tid; v < kStreamRows * (ROWLEN >> 2); v += kThreads) {
+      const int t = v / (ROWLEN >> 2), col = (v % (ROWLEN >> 2)) << 2;
+      const int row = base + t;
+      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < p.n_str) val = ld4(p.str + (size_t)row * D, col, D, vec_str);
+      *reinterpret_cast<float4*>(&stage[(size_t)t * ROWLEN + col]) = val;
+    }
+    __syncthreads();
+
+    float dot[R];
+    RedT<0, R, KCH>::run(a, stage, 0, lane, dot);
+
+    const int k = base + lane;            // stream row handled by this lane
+    const bool valid = k < p.n_str;
+    float gq[R];                          // BWD: w * G (off-diagonal) for (owner q, stream k)
+
+    if (MODE == MODE_BWD_DC) {
+      // owner = centroid (global index own0+q), stream = local utterance row k
+      float lse_r = 0.f; int jg_r = -2;
+      if (valid) { lse_r = __ldg(p.row_stat + k); jg_r = p.spk_offset + k / p.M; }
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        const float S = fmaf(w, dot[q] + eps, b);
+        const bool off = valid && (jg_r != own0 + q);
+        gq[q] = off ? w * g * expf(S - lse_r) : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        const bool diag = (k == jg[q]);
+        const float cosv = (diag ? cd[q] : dot[q]) + eps;       // s3:78-79
+        const float S = fmaf(w, cosv, b);                       // s3:27
+        if (MODE == MODE_FWD) {
+          if (p.sim_out != nullptr && valid && own0 + q < p.n_own)
+            p.sim_out[(size_t)(own0 + q) * p.n_str + k] = cosv;
+          if (VARIANT == GE2E_SOFTMAX) {
+            if (valid) {
+              const float mn = fmaxf(m_run[q], S);
+              l_run[q] = l_run[q] * expf(m_run[q] - mn) + expf(S - mn);
+              m_run[q] = mn;
+            }
+          } else {
+            if (valid && !diag && S > best[q]) { best[q] = S; bestk[q] = k; }
+          }
+        } else {  // MODE_BWD_DE (softmax only)
+          const float pr = valid ? expf(S - lse[q]) : 0.f;
+          const float G = g * (pr - (diag ? 1.f : 0.f));
+          dw_acc = fmaf(G, cosv, dw_acc);
+          gq[q] = (valid && !diag) ? w * G : 0.f;
+        }
+      }
+    }
+
+    if (MODE != MODE_FWD) {
+#pragma unroll 4
+      for (int t = 0; t < kStreamRows; ++t) {
+        float s[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) s[q] = __shfl_sync(0xffffffffu, gq[q], t);
+#pragma unroll
+        for (int c = 0; c < KCH; ++c) {
+          const float4 bv = *reinterpret_cast<const float4*>(&stage[(size_t)t * ROWLEN + c * 128 + (lane << 2)]);
+#pragma unroll
+          for (int q = 0; q < R; ++q) {
+            acc[q][c].x = fmaf(s[q], bv.x, acc[q][c].x);
+            acc[q][c].y = fmaf(s[q], bv.y, acc[q][c].y);
+            acc[q][c].z = fmaf(s[q], bv.z, acc[q][c].z);
+            acc[q][c].w = fmaf(s[q], bv.w, acc[q][c].w);
+          }
+        }
+      }
+    }
+  }
+
+  // ---------------- epilogue ----------------
+  if (MODE == MODE_FWD) {
+    float loss_part = 0.f;
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      const int row = own0 + q;
+      const float Sd = fmaf(w, cd[q] + eps, b);
+      float per, stat; int ks = -1;
+      if (VARIANT == GE2E_SOFTMAX) {
+        const float mx = warp_max(m_run[q]);
+        const float lsum = warp_sum(l_run[q] == 0.f ? 0.f : l_run[q] * expf(m_run[q] - mx));
+        // log(sum_k exp S + eps), s3:120, evaluated without overflow
+        stat = (mx > -80.f) ? mx + logf(lsum + eps * expf(-mx)) : logf(eps + lsum * expf(mx));
+        per = stat - Sd;                                        // s3:121
+      } else {
+        float bv = best[q]; int bk = bestk[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+          if (ov > bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
+        }
+        const float sp = 1.f / (1.f + expf(-Sd));
+        per = 1.f - sp;
+        stat = bv;
+        if (bk != INT_MAX) { ks = bk; per += 1.f / (1.f + expf(-bv)); }
+      }
+      if (lane == 0 && row < p.n_own) {
+        p.row_stat_out[row] = stat;
+        if (p.kstar_out != nullptr) p.kstar_out[row] = ks;
+        if (p.per_row_out != nullptr) p.per_row_out[row] = per;
+        loss_part += per;
+      }
+    }
+    const float tot = block_sum(loss_part, red);
+    if (tid == 0) atomicAdd(p.loss_accum, tot);
+  } else if (MODE == MODE_BWD_DE) {
+    const bool vec_out = is_vec(p.acc_out, D);
+    float db_part = 0.f;
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      const int row = own0 + q;
+      if (row < p.n_own) {
+#pragma unroll
+        for (int c = 0; c < KCH; ++c)
+          st4(p.acc_out + (size_t)row * D, (lane << 2) + c * 128, D, vec_out, acc[q][c]);
+        // db = sum_k G = -g * eps / (sum exp + eps): closed form
+        if (lane == 0) db_part -= g * eps * expf(-lse[q]);
+      }
+    }
+    const float dw_tot = block_sum(dw_acc, red);
+    const float db_tot = block_sum(db_part, red);
+    if (tid == 0) { atomicAdd(p.dwdb + 0, dw_tot); atomicAdd(p.dwdb + 1, db_tot); }
+  } else {  // MODE_BWD_DC
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      const int row = own0 + q;
+      if (row < p.n_own) {
+        float* out = p.acc_out + (size_t)row * D;
+#pragma unroll
+        for (int c = 0; c < KCH; ++c) {
+          const int col = (lane << 2) + c * 128;
+          if (col + 0 < D) atomicAdd(out + col + 0, acc[q][c].x);
+          if (col + 1 < D) atomicAdd(out + col + 1, acc[q][c].y);
+          if (col + 2 < D) atomicAdd(out + col + 2, acc[q][c].z);
+          if (col + 3 < D) atomicAdd(out + col + 3, acc[q][c].w);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// contrast backward: G has two non-zeros per row (the diagonal and k*): gather / scatter.
+// grid = ceil(U_local / 8), block = 256 (one warp per utterance row)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+contrast_bwd_kernel(const float* __restrict__ e_hat, const float* __restrict__ c_hat_all,
+                    const float* __restrict__ cos_diag, const float* __restrict__ row_stat,
+                    const int32_t* __restrict__ kstar, int U, int D, const float* __restrict__ wp,
+                    const float* __restrict__ bp, float eps, const float* __restrict__ gp,
+                    float* __restrict__ dE_hat, float* __restrict__ dC_hat, float* __restrict__ dwdb) {
+  __shared__ float red[kWarps];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int r = blockIdx.x * kWarps + wid;
+  const float w = __ldg(wp), b = __ldg(bp), g = __ldg(gp);
+  float dw = 0.f, db = 0.f;
+  if (r < U) {
+    const float cd = __ldg(cos_diag + r) + eps;
+    const float sp = 1.f / (1.f + expf(-fmaf(w, cd, b)));
+    const float Gp = -g * sp * (1.f - sp);
+    const int ks = __ldg(kstar + r);
+    float Gn = 0.f, cn = 0.f;
+    const float* er = e_hat + (size_t)r * D;
+    if (ks >= 0) {
+      const float* ck = c_hat_all + (size_t)ks * D;
+      float d = 0.f;
+      for (int c = lane; c < D; c += 32) d = fmaf(__ldg(er + c), __ldg(ck + c), d);
+      cn = warp_sum(d) + eps;
+      const float sn = 1.f / (1.f + expf(-__ldg(row_stat + r)));
+      Gn = g * sn * (1.f - sn);
+      const float wg = w * Gn;
+      for (int c = lane; c < D; c += 32) {
+        dE_hat[(size_t)r * D + c] = wg * __ldg(ck + c);
+        atomicAdd(dC_hat + (size_t)ks * D + c, wg * __ldg(er + c));
+      }
+    } else {
+      for (int c = lane; c < D; c += 32) dE_hat[(size_t)r * D + c] = 0.f;
+    }
+    if (lane == 0) { dw = Gp * cd + Gn * cn; db = Gp + Gn; }
+  }
+  const float dwt = block_sum(dw, red);
+  const float dbt = block_sum(db, red);
+  if (tid == 0) { atomicAdd(dwdb + 0, dwt); atomicAdd(dwdb + 1, dbt); }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: finalize.  grid = n_local, block = 256, dynamic smem = (2*M + 2) * Dp floats.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+finalize_kernel(const float* __restrict__ E, const float* __restrict__ dE_hat,
+                const float* __restrict__ dC_hat, const float* __restrict__ cos_diag,
+                const float* __restrict__ row_stat, int M, int D, int Dp,
+                const float* __restrict__ wp, const float* __restrict__ bp, float eps, int variant,
+                const float* __restrict__ gp, float* __restrict__ dE) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red[kWarps];
+  __shared__ float s_bc[2];
+  float* sE = smem;                          // [M][Dp] raw embeddings -> later de (gradient through e_hat)
+  float* sU = sE + (size_t)M * Dp;           // [M][Dp] du rows
+  float* sS = sU + (size_t)M * Dp;           // [Dp] column sums of E, later sum_i du
+  float* sB = sS + Dp;                       // [Dp] dc_j / M
+  const int j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const float w = __ldg(wp), b = __ldg(bp), g = __ldg(gp);
+  const float* Ej = E + (size_t)j * M * D;
+  const bool vec_e = is_vec(E, D), vec_g = is_vec(dE_hat, D), vec_o = is_vec(dE, D);
+
+  for (int v = tid; v < M * (Dp >> 2); v += kThreads) {
+    const int i = v / (Dp >> 2), col = (v % (Dp >> 2)) << 2;
+    *reinterpret_cast<float4*>(&sE[(size_t)i * Dp + col]) = ld4(Ej + (size_t)i * D, col, D, vec_e);
+  }
+  __syncthreads();
+  for (int d = tid; d < Dp; d += kThreads) {
+    float s = 0.f;
+    for (int i = 0; i < M; ++i) s += sE[(size_t)i * Dp + d];
+    sS[d] = s;
+  }
+  __syncthreads();
+
+  // centroid Jacobian: dc = (dC_hat - c_hat (c_hat . dC_hat)) / |c|   (or dC_hat / delta)
+  const float fm = (float)M;
+  {
+    float n2 = 0.f, pr = 0.f;
+    for (int d = tid; d < D; d += kThreads) {
+      const float c = sS[d] / fm;
+      n2 = fmaf(c, c, n2);
+      pr = fmaf(c, __ldg(dC_hat + (size_t)j * D + d), pr);
+    }
+    const float n2t = block_sum(n2, red);
+    const float prt = block_sum(pr, red);
+    if (tid == 0) { s_bc[0] = n2t; s_bc[1] = prt; }
+    __syncthreads();
+    const float nc = sqrtf(s_bc[0]);
+    const bool ok = nc >= kCosDelta;
+    const float inv = 1.f / fmaxf(nc, kCosDelta);
+    const float proj = s_bc[1] * inv;            // c_hat . dC_hat
+    for (int d = tid; d < Dp; d += kThreads) {
+      float v = 0.f;
+      if (d < D) {
+        const float dch = __ldg(dC_hat + (size_t)j * D + d);
+        const float ch = (sS[d] / fm) * inv;
+        v = (ok ? (dch - ch * proj) * inv : dch * inv) / fm;
+      }
+      sB[d] = v;
+    }
+  }
+  __syncthreads();
+
+  const float m1 = (float)(M - 1);
+  for (int i = wid; i < M; i += kWarps) {
+    const int r = j * M + i;
+    float ne2 = 0.f, nu2 = 0.f, eu = 0.f, eg = 0.f;
+    const float* gh = dE_hat + (size_t)r * D;
+    for (int d = lane << 2; d < Dp; d += 128) {
+      const float4 e = *reinterpret_cast<const float4*>(&sE[(size_t)i * Dp + d]);
+      const float4 s = *reinterpret_cast<const float4*>(&sS[d]);
+      const float4 gv = ld4(gh, d, D, vec_g);
+      float4 u;
+      u.x = (s.x - e.x) / m1; u.y = (s.y - e.y) / m1; u.z = (s.z - e.z) / m1; u.w = (s.w - e.w) / m1;
+      ne2 += dot4(e, e); nu2 += dot4(u, u); eu += dot4(e, u); eg += dot4(e, gv);
+    }
+    ne2 = warp_sum(ne2); nu2 = warp_sum(nu2); eu = warp_sum(eu); eg = warp_sum(eg);
+    const float ne = sqrtf(ne2), nu = sqrtf(nu2);
+    const bool ok_e = ne >= kCosDelta, ok_u = nu >= kCosDelta;
+    const float inv_ne = 1.f / fmaxf(ne, kCosDelta), inv_nu = 1.f / fmaxf(nu, kCosDelta);
+    const float cdv = eu * inv_ne * inv_nu;       // e_hat . u_hat (== cos_diag)
+    // diagonal element of w*G
+    const float Sd = fmaf(w, __ldg(cos_diag + r) + eps, b);
+    float Gd;
+    if (variant == GE2E_SOFTMAX) {
+      Gd = g * (expf(Sd - __ldg(row_stat + r)) - 1.f);
+    } else {
+      const float sp = 1.f / (1.f + expf(-Sd));
+      Gd = -g * sp * (1.f - sp);
+    }
+    const float dd = w * Gd;
+    // d e_hat = dE_hat_offdiag + dd * u_hat ;  d u_hat = dd * e_hat
+    const float proj_e = eg * inv_ne + dd * cdv;  // e_hat . d e_hat
+    const float proj_u = dd * cdv;                // u_hat . d u_hat
+    for (int d = lane << 2; d < Dp; d += 128) {
+      const float4 e = *reinterpret_cast<const float4*>(&sE[(size_t)i * Dp + d]);
+      const float4 s = *reinterpret_cast<const float4*>(&sS[d]);
+      const float4 gv = ld4(gh, d, D, vec_g);
+      float ev[4] = {e.x, e.y, e.z, e.w}, sv[4] = {s.x, s.y, s.z, s.w}, gg[4] = {gv.x, gv.y, gv.z, gv.w};
+      float de[4], du[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float eh = ev[t] * inv_ne;
+        const float uh = ((sv[t] - ev[t]) / m1) * inv_nu;
+        const float deh = gg[t] + dd * uh;
+        const float duh = dd * eh;
+        de[t] = ok_e ? (deh - eh * proj_e) * inv_ne : deh * inv_ne;
+        du[t] = ok_u ? (duh - uh * proj_u) * inv_nu : duh * inv_nu;
+      }
+      // each (i, d) slot is touched by exactly one lane: overwrite in place after reading
+      *reinterpret_cast<float4*>(&sU[(size_t)i * Dp + d]) = make_float4(du[0], du[1], du[2], du[3]);
+      __syncwarp();
+      *reinterpret_cast<float4*>(&sE[(size_t)i * Dp + d]) = make_float4(de[0], de[1], de[2], de[3]);
+    }
+  }
+  __syncthreads();   // sS (sums of E) no longer needed after this point
+  for (int d = tid; d < Dp; d += kThreads) {
+    float s = 0.f;
+    for (int i = 0; i < M; ++i) s += sU[(size_t)i * Dp + d];
+    sS[d] = s;
+  }
+  __syncthreads();
+  float* out = dE + (size_t)j * M * D;
+  for (int v = tid; v < M * (Dp >> 2); v += kThreads) {
+    const int i = v / (Dp >> 2), col = (v % (Dp >> 2)) << 2;
+    const float4 de = *reinterpret_cast<const float4*>(&sE[(size_t)i * Dp + col]);
+    const float4 du = *reinterpret_cast<const float4*>(&sU[(size_t)i * Dp + col]);
+    const float4 sd = *reinterpret_cast<const float4*>(&sS[col]);
+    const float4 bc = *reinterpret_cast<const float4*>(&sB[col]);
+    float4 o;
+    o.x = de.x + bc.x + (sd.x - du.x) / m1;
+    o.y = de.y + bc.y + (sd.y - du.y) / m1;
+    o.z = de.z + bc.z + (sd.z - du.z) / m1;
+    o.w = de.w + bc.w + (sd.w - du.w) / m1;
+    st4(out + (size_t)i * D, col, D, vec_o, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// static helpers of the reference class
+// ------------------------------------------------------------------------------------------
+__global__ void centroids_kernel(const float* __restrict__ E, int M, int D, float* __restrict__ C) {
+  const int j = blockIdx.x;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float s = 0.f;
+    for (int i = 0; i < M; ++i) s += __ldg(E + ((size_t)j * M + i) * D + d);
+    C[(size_t)j * D + d] = s / (float)M;   // s3:37
+  }
+}
+
+__global__ void utt_centroids_kernel(const float* __restrict__ E, int M, int D, float* __restrict__ Uc) {
+  const int j = blockIdx.x;
+  const float m1 = (float)(M - 1);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float s = 0.f;
+    for (int i = 0; i < M; ++i) s += __ldg(E + ((size_t)j * M + i) * D + d);
+    for (int i = 0; i < M; ++i) {
+      const size_t o = ((size_t)j * M + i) * D + d;
+      Uc[o] = (s - __ldg(E + o)) / m1;      // s3:111
+    }
+  }
+}
+
+__global__ void normalize_rows_kernel(const float* __restrict__ X, int rows, int D, float* __restrict__ Y) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int r = blockIdx.x * (blockDim.x >> 5) + wid;
+  if (r >= rows) return;
+  float n2 = 0.f;
+  for (int d = lane; d < D; d += 32) { const float v = __ldg(X + (size_t)r * D + d); n2 = fmaf(v, v, n2); }
+  n2 = warp_sum(n2);
+  const float inv = 1.f / fmaxf(sqrtf(n2), kCosDelta);
+  for (int d = lane; d < D; d += 32) Y[(size_t)r * D + d] = __ldg(X + (size_t)r * D + d) * inv;
+}
+
+// calc_loss (s3:114-127) on a caller-supplied S[N, M, N]; one warp per row
+__global__ void __launch_bounds__(kThreads)
+calc_loss_kernel(const float* __restrict__ S, int N, int M, float eps, int variant,
+                 float* __restrict__ loss, float* __restrict__ per_row) {
+  __shared__ float red[kWarps];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int r = blockIdx.x * kWarps + wid;
+  float per = 0.f;
+  if (r < N * M) {
+    const int j = r / M;
+    const float* row = S + (size_t)r * N;
+    const float Sd = __ldg(row + j);
+    if (variant == GE2E_SOFTMAX) {
+      float mx = -INFINITY;
+      for (int k = lane; k < N; k += 32) mx = fmaxf(mx, __ldg(row + k));
+      mx = warp_max(mx);
+      float l = 0.f;
+      for (int k = lane; k < N; k += 32) l += expf(__ldg(row + k) - mx);
+      l = warp_sum(l);
+      const float lse = (mx > -80.f) ? mx + logf(l + eps * expf(-mx)) : logf(eps + l * expf(mx));
+      per = lse - Sd;
+    } else {
+      float mx = -INFINITY;
+      for (int k = lane; k < N; k += 32) if (k != j) mx = fmaxf(mx, __ldg(row + k));
+      mx = warp_max(mx);
+      per = 1.f - 1.f / (1.f + expf(-Sd));
+      if (N > 1) per += 1.f / (1.f + expf(-mx));
+    }
+    if (lane == 0 && per_row != nullptr) per_row[r] = per;
+    if (lane != 0) per = 0.f;
+  }
+  const float tot = block_sum(per, red);
+  if (tid == 0) atomicAdd(loss, tot);
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024)
+    GE2E_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return GE2E_OK;
+}
+
+template <int MODE, int VARIANT, int KCH, int R>
+int launch_strip(const StripParams& p, int splits, cudaStream_t st) {
+  const size_t smem = (size_t)kStreamRows * KCH * 128 * sizeof(float);
+  auto kern = strip_kernel<MODE, VARIANT, KCH, R>;
+  int rc = set_smem(kern, smem);
+  if (rc != GE2E_OK) return rc;
+  dim3 grid((p.n_own + kWarps * R - 1) / (kWarps * R), splits);
+  kern<<<grid, kThreads, smem, st>>>(p);
+  GE2E_LAUNCHED();
+  return GE2E_OK;
+}
+
+template <int MODE, int VARIANT>
+int dispatch_strip(const StripParams& p, int splits, cudaStream_t st) {
+  const int D = p.D;
+  if (D <= 128) return launch_strip<MODE, VARIANT, 1, 4>(p, splits, st);
+  if (D <= 256) return launch_strip<MODE, VARIANT, 2, 4>(p, splits, st);
+  if (D <= 512) return launch_strip<MODE, VARIANT, 4, 2>(p, splits, st);
+  if (D <= 1024) return launch_strip<MODE, VARIANT, 8, 1>(p, splits, st);
+  return GE2E_ERR_UNSUPPORTED;
+}
+
+int rows_per_cta(int D) { return kWarps * (D <= 256 ? 4 : (D <= 512 ? 2 : 1)); }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+int simt_prep(const float* E, int n_local, int M, int D, bool round_tf32_, float* e_hat,
+              float* c_hat_local, float* cos_diag, float* accum, cudaStream_t st) {
+  const int Dp = (D + 3) & ~3;
+  const size_t smem = (size_t)(M + 1) * Dp * sizeof(float);
+  if (smem > 200 * 1024) return GE2E_ERR_UNSUPPORTED;
+  if (round_tf32_) {
+    int rc = set_smem(prep_kernel<true>, smem);
+    if (rc != GE2E_OK) return rc;
+    prep_kernel<true><<<n_local, kThreads, smem, st>>>(E, M, D, Dp, e_hat, c_hat_local, cos_diag, accum);
+  } else {
+    int rc = set_smem(prep_kernel<false>, smem);
+    if (rc != GE2E_OK) return rc;
+    prep_kernel<false><<<n_local, kThreads, smem, st>>>(E, M, D, Dp, e_hat, c_hat_local, cos_diag, accum);
+  }
+  GE2E_LAUNCHED();
+  return GE2E_OK;
+}
+
+int simt_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* loss_accum,
+                  float* per_row_out, float* sim_out, cudaStream_t st) {
+  StripParams p{};
+  p.own = a.e_hat; p.n_own = a.n_local * a.M;
+  p.str = a.c_hat_all; p.n_str = a.n_total;
+  p.D = a.D; p.M = a.M; p.spk_offset = a.spk_offset;
+  p.cos_diag = a.cos_diag; p.w = a.w; p.b = a.b; p.eps = a.eps;
+  p.row_stat_out = row_stat; p.kstar_out = row_kstar; p.loss_accum = loss_accum;
+  p.per_row_out = per_row_out; p.sim_out = sim_out;
+  p.chunks_per_split = INT_MAX / 2;
+  if (a.variant == GE2E_SOFTMAX) return dispatch_strip<MODE_FWD, GE2E_SOFTMAX>(p, 1, st);
+  return dispatch_strip<MODE_FWD, GE2E_CONTRAST>(p, 1, st);
+}
+
+int simt_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kstar,
+                  const float* grad_out, float* dE_hat, float* dC_hat_partial, float* dwdb_accum,
+                  cudaStream_t st) {
+  const int U = a.n_local * a.M;
+  // one memset when the caller placed {dw, db} right behind dC_hat_partial, else two
+  const size_t dc_elems = (size_t)a.n_total * a.D;
+  if (dwdb_accum == dC_hat_partial + dc_elems) {
+    GE2E_CUDA_TRY(cudaMemsetAsync(dC_hat_partial, 0, (dc_elems + 2) * sizeof(float), st));
+  } else {
+    GE2E_CUDA_TRY(cudaMemsetAsync(dC_hat_partial, 0, dc_elems * sizeof(float), st));
+    GE2E_CUDA_TRY(cudaMemsetAsync(dwdb_accum, 0, 2 * sizeof(float), st));
+  }
+  if (a.variant == GE2E_CONTRAST) {
+    contrast_bwd_kernel<<<(U + kWarps - 1) / kWarps, kThreads, 0, st>>>(
+        a.e_hat, a.c_hat_all, a.cos_diag, row_stat, row_kstar, U, a.D, a.w, a.b, a.eps, grad_out,
+        dE_hat, dC_hat_partial, dwdb_accum);
+    GE2E_LAUNCHED();
+    return GE2E_OK;
+  }
+  StripParams p{};
+  p.D = a.D; p.M = a.M; p.spk_offset = a.spk_offset;
+  p.cos_diag = a.cos_diag; p.row_stat = row_stat; p.w = a.w; p.b = a.b; p.grad_out = grad_out;
+  p.eps = a.eps;
+  // dE_hat: owner = utterances, stream = centroids
+  p.own = a.e_hat; p.n_own = U; p.str = a.c_hat_all; p.n_str = a.n_total;
+  p.acc_out = dE_hat; p.dwdb = dwdb_accum; p.chunks_per_split = INT_MAX / 2;
+  int rc = dispatch_strip<MODE_BWD_DE, GE2E_SOFTMAX>(p, 1, st);
+  if (rc != GE2E_OK) return rc;
+  // dC_hat: owner = centroids, stream = utterances, stream range split across blockIdx.y
+  p.own = a.c_hat_all; p.n_own = a.n_total; p.str = a.e_hat; p.n_str = U;
+  p.acc_out = dC_hat_partial; p.dwdb = nullptr;
+  const int own_ctas = (a.n_total + rows_per_cta(a.D) - 1) / rows_per_cta(a.D);
+  const int nchunks = (U + kStreamRows - 1) / kStreamRows;
+  int splits = (2 * 148 + own_ctas - 1) / own_ctas;        // aim at ~2 waves of 148 SMs
+  splits = max(1, min(splits, nchunks));
+  p.chunks_per_split = (nchunks + splits - 1) / splits;
+  splits = (nchunks + p.chunks_per_split - 1) / p.chunks_per_split;
+  return dispatch_strip<MODE_BWD_DC, GE2E_SOFTMAX>(p, splits, st);
+}
+
+int simt_bwd_finalize(const float* E, const float* dE_hat, const float* dC_hat_local,
+                      const float* cos_diag, const float* row_stat, int n_local, int M, int D,
+                      const float* w, const float* b, float eps, int variant,
+                      const float* grad_out, float* dE, cudaStream_t st) {
+  const int Dp = (D + 3) & ~3;
+  const size_t smem = (size_t)(2 * M + 2) * Dp * sizeof(float);
+  if (smem > 200 * 1024) return GE2E_ERR_UNSUPPORTED;
+  int rc = set_smem(finalize_kernel, smem);
+  if (rc != GE2E_OK) return rc;
+  finalize_kernel<<<n_local, kThreads, smem, st>>>(E, dE_hat, dC_hat_local, cos_diag, row_stat, M, D,
+                                                   Dp, w, b, eps, variant, grad_out, dE);
+  GE2E_LAUNCHED();
+  return GE2E_OK;
+}
+
+int simt_centroids(const float* E, int N, int M, int D, float* C, cudaStream_t st) {
+  centroids_kernel<<<N, 128, 0, st>>>(E, M, D, C);
+  GE2E_LAUNCHED();
+  return GE2E_OK;
+}
+
+int simt_utterance_centroids(const float* E, int N, int M, int D, float* Uc, cudaStream_t st) {
+  utt_centroids_kernel<<<N, 128, 0, st>>>(E, M, D, Uc);
+  GE2E_LAUNCHED();
+  return GE2E_OK;
+}
+
+int simt_normalize_rows(const float* X, int rows, int D, float* Y, cudaStream_t st) {
+  normalize_rows_kernel<<<(rows + kWarps - 1) / kWarps, kThreads, 0, st>>>(X, rows, D, Y);
+  GE2E_LAUNCHED();
+  return GE2E_OK;
+}
+
+int simt_calc_loss(const float* S, int N, int M, float eps, int variant, float* loss, float* per_row,
+                   cudaStream_t st) {
+  GE2E_CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  calc_loss_kernel<<<(N * M + kWarps - 1) / kWarps, kThreads, 0, st>>>(S, N, M, eps, variant, loss, per_row);
+  GE2E_LAUNCHED();
+  return GE2E_OK;
+}
+
+}  // namespace ge2e

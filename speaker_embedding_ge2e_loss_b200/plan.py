@@ -1,0 +1,87 @@
+"""Pre-planned GE2E step: every buffer allocated once, fwd+bwd issued as bare C-ABI calls.
+
+``GE2ELoss`` / ``ge2e_loss`` go through ``torch.library`` + autograd, which costs tens of
+microseconds of host time per call -- more than the kernels themselves at the repo's batch sizes.
+A plan is the launch-latency-free form of the same step (reference call sequence
+s4_train_embed_model.py:196-200: ``loss = ge2e_loss(E); loss.backward()``): the library never
+allocates or synchronises, so ``step()`` is CUDA-graph capturable (``capture()``).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+
+class GE2EPlan:
+    def __init__(self, N: int, M: int, D: int, variant: str = "softmax", precision: str = "fp32",
+                 eps: float = 1e-6, device=None):
+        if M < 2:
+            raise ValueError("GE2E needs M >= 2 utterances per speaker")
+        self.N, self.M, self.D = N, M, D
+        self.variant = _lib.VARIANTS[variant]
+        self.precision = _lib.PRECISIONS[precision]
+        self.eps = float(eps)
+        self.device = torch.device(device if device is not None else "cuda")
+        if self.device.type != "cuda":
+            raise RuntimeError("speaker_embedding_ge2e_loss_b200 runs on CUDA (sm_100a) only; no CPU fallback")
+        U, dev, f32 = N * M, self.device, torch.float32
+        self.path = lib().ge2e_b200_path(N, N, M, D, self.variant, self.precision)  # 0 SIMT, 1 tcgen05
+        self.e_hat = torch.empty((U, D), dtype=f32, device=dev)
+        self.c_hat = torch.empty((N, D), dtype=f32, device=dev)
+        self.cos_diag = torch.empty(U, dtype=f32, device=dev)
+        self.row_stat = torch.empty(U, dtype=f32, device=dev)
+        self.row_kstar = torch.empty(U, dtype=torch.int32, device=dev)
+        self.dE_hat = torch.empty((U, D), dtype=f32, device=dev)
+        # [dC_hat (N*D) | dw | db] so that the library zeroes all of it with one memset
+        self._scratch = torch.empty(N * D + 2, dtype=f32, device=dev)
+        self._accum = torch.empty(4, dtype=f32, device=dev)      # {loss, -, -, -}
+        self.dE = torch.empty((N, M, D), dtype=f32, device=dev)
+        self.grad_out = torch.ones((), dtype=f32, device=dev)
+        nbytes = lib().ge2e_b200_workspace_bytes(N, N, M, D, self.variant, self.precision)
+        self._ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        self._ws_bytes = nbytes
+        self.loss = self._accum[0]
+        self.dw = self._scratch[N * D]
+        self.db = self._scratch[N * D + 1]
+        self._graph = None
+
+    def step(self, E: torch.Tensor, w: torch.Tensor, b: torch.Tensor, backward: bool = True) -> None:
+        """Enqueue fwd (+ bwd) on the current stream.  Results land in .loss/.dE/.dw/.db."""
+        assert E.is_cuda and E.dtype == torch.float32 and E.is_contiguous() and tuple(E.shape) == (self.N, self.M, self.D)
+        h, N, M, D = lib(), self.N, self.M, self.D
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        ws = self._ws.data_ptr() if self._ws_bytes else None
+        rc = h.ge2e_b200_forward(E.data_ptr(), N, M, D, w.data_ptr(), b.data_ptr(), self.eps, self.variant,
+                                 self.precision, self.e_hat.data_ptr(), self.c_hat.data_ptr(),
+                                 self.cos_diag.data_ptr(), self.row_stat.data_ptr(), self.row_kstar.data_ptr(),
+                                 self._accum.data_ptr(), ws, self._ws_bytes, stream)
+        check(rc, "ge2e_b200_forward")
+        if not backward:
+            return
+        accum_ptr = self._scratch.data_ptr() + (N * D - 1) * 4   # accum[1] = dw, accum[2] = db
+        rc = h.ge2e_b200_backward(E.data_ptr(), self.e_hat.data_ptr(), self.c_hat.data_ptr(),
+                                  self.cos_diag.data_ptr(), self.row_stat.data_ptr(), self.row_kstar.data_ptr(),
+                                  N, M, D, w.data_ptr(), b.data_ptr(), self.eps, self.variant, self.precision,
+                                  self.grad_out.data_ptr(), self.dE_hat.data_ptr(), self._scratch.data_ptr(),
+                                  accum_ptr, self.dE.data_ptr(), ws, self._ws_bytes, stream)
+        check(rc, "ge2e_b200_backward")
+
+    def capture(self, E: torch.Tensor, w: torch.Tensor, b: torch.Tensor, backward: bool = True):
+        """Capture one step into a CUDA graph bound to these tensors; returns the graph
+        (``.replay()``).  Also records how many of the library's kernels one step launches."""
+        with torch.cuda.device(self.device):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.step(E, w, b, backward)            # warm-up: lazy func attributes, module load
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            before = lib().ge2e_b200_launch_count()
+            with torch.cuda.graph(g):
+                self.step(E, w, b, backward)
+            self.launches_per_step = lib().ge2e_b200_launch_count() - before
+        self._graph = g
+        return g

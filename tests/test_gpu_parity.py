@@ -1,0 +1,299 @@
+"""GPU parity tests (run on the B200 box with ``-m gpu``): the CUDA path, called through the
+C ABI (ctypes binding -> libge2e_b200.so), against
+  * the golden vectors produced by the REAL reference class (tests/golden/make_golden.py),
+  * the numpy fp64 oracle on seeded inputs, and
+  * size-independent properties at BASELINE.json's full sizes.
+
+Tolerances (BASELINE.json north_star): fp32 path 1e-5 relative (loss, dE rel-L2, dw); TF32
+tensor-core path 2e-3.  db is purely eps-driven and ill-conditioned in the reference's own fp32
+autograd: it is checked absolutely, |db - db_fp64| <= 1e-5 * U.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names
+from oracle import ge2e_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5
+TF32_TOL = 2e-3
+NAMES = golden_names()
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import speaker_embedding_ge2e_loss_b200 as p
+    p.lib()  # fails loudly when the CUDA library is missing
+    assert torch.cuda.is_available()
+    return p
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+def run_cuda(pkg, E_np, w, b, variant="softmax", precision="fp32", g=None):
+    dev = torch.device("cuda:0")
+    crit = pkg.GE2ELoss(None, device=dev, w=w, b=b, variant=variant, precision=precision)
+    E = torch.tensor(np.asarray(E_np, dtype=np.float32), device=dev, requires_grad=True)
+    loss = crit(E)
+    if g is None:
+        loss.backward()
+    else:
+        (loss * g).backward()
+    torch.cuda.synchronize()
+    return dict(loss=loss.item(), dE=E.grad.double().cpu().numpy(), dw=crit.w.grad.item(),
+                db=crit.b.grad.item())
+
+
+def check(got, ref, U, tol, dE_tol=None):
+    assert abs(got["loss"] - ref["loss"]) <= tol * max(1.0, abs(ref["loss"])), (got["loss"], ref["loss"])
+    assert rel(got["dE"], ref["dE"]) <= (dE_tol or tol), rel(got["dE"], ref["dE"])
+    assert abs(got["dw"] - ref["dw"]) <= tol * max(1.0, abs(ref["dw"])), (got["dw"], ref["dw"])
+    assert abs(got["db"] - ref["db"]) <= 1e-5 * U, (got["db"], ref["db"])
+
+
+# ------------------------------------------------------------------ golden vectors (real reference)
+@pytest.mark.parametrize("name", NAMES)
+def test_softmax_matches_reference_golden(pkg, golden, name):
+    c = golden[name]
+    got = run_cuda(pkg, c.E, c.w, c.b)
+    U = c.E.shape[0] * c.E.shape[1]
+    # N == 1 is purely eps-driven: loss ~ 1e-6 per row and dE ~ 1e-6 too, where fp32 exp/log
+    # rounding of S itself gives ~1e-4 relative on dE even in the reference (test_oracle.py).
+    dE_tol = 2e-4 if name.startswith("onespk") else FP32_TOL
+    check(got, c.r64, U, FP32_TOL, dE_tol)
+    # and it is at least as close to fp64 truth as 4x the reference's own fp32 run
+    ref_err = rel(c.r32["dE"], c.r64["dE"])
+    assert rel(got["dE"], c.r64["dE"]) <= max(4 * ref_err, FP32_TOL)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_contrast_matches_golden(pkg, golden, name):
+    c = golden[name]
+    got = run_cuda(pkg, c.E, c.w, c.b, variant="contrast")
+    ref = c.rc
+    assert abs(got["loss"] - ref["loss"]) <= FP32_TOL * max(1.0, abs(ref["loss"]))
+    if name.startswith("kat"):
+        pytest.skip("one-hot KAT has exact argmax ties: gradient depends on the tie-break")
+    assert rel(got["dE"], ref["dE"]) <= FP32_TOL
+    assert abs(got["dw"] - ref["dw"]) <= FP32_TOL * max(1.0, abs(ref["dw"]))
+    assert abs(got["db"] - ref["db"]) <= FP32_TOL * max(1.0, abs(ref["db"]))
+
+
+# ------------------------------------------------------------------ seeded inputs vs the oracle
+CASES = [
+    (4, 8, 256, "random"), (64, 10, 256, "random"), (64, 10, 256, "clustered"),
+    (2, 16, 256, "raw"), (33, 3, 48, "clustered"), (256, 10, 256, "random"),
+    (97, 7, 130, "raw"), (5, 2, 1024, "random"), (300, 4, 64, "clustered"),
+]
+
+
+@pytest.mark.parametrize("N,M,D,kind", CASES)
+@pytest.mark.parametrize("variant", ["softmax", "contrast"])
+def test_matches_oracle_seeded(pkg, N, M, D, kind, variant):
+    E = orc.make_embeddings(N, M, D, seed=N + M + D, kind=kind)
+    ref = orc.forward_backward(E, 10.0, -5.0, 1e-6, variant)
+    got = run_cuda(pkg, E, 10.0, -5.0, variant=variant)
+    check(got, ref, N * M, FP32_TOL)
+
+
+def test_upstream_gradient_scales(pkg):
+    E = orc.make_embeddings(16, 5, 64, seed=5, kind="clustered")
+    for variant in ("softmax", "contrast"):
+        ref = orc.forward_backward(E, 3.0, -1.0, 1e-6, variant, g=-0.37)
+        got = run_cuda(pkg, E, 3.0, -1.0, variant=variant, g=-0.37)
+        check(got, ref, 80, FP32_TOL)
+
+
+def test_forward_only_and_repeat_is_deterministic_loss(pkg):
+    # s4:103: the test-loss path calls forward with grad enabled and never backpropagates
+    dev = torch.device("cuda:0")
+    crit = pkg.GE2ELoss(None, device=dev)
+    E = torch.tensor(orc.make_embeddings(32, 6, 256, seed=9), device=dev, requires_grad=True)
+    l1 = crit(E)
+    l2 = crit(E)
+    with torch.no_grad():
+        l3 = crit(E)
+    torch.cuda.synchronize()
+    assert abs(l1.item() - l2.item()) <= 1e-6 * abs(l1.item())
+    assert abs(l1.item() - l3.item()) <= 1e-6 * abs(l1.item())
+    assert not l3.requires_grad and l1.requires_grad
+
+
+# ------------------------------------------------------------------ full-size properties
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("tf32", TF32_TOL)])
+def test_cfg3_full_size_vs_oracle(pkg, precision, tol):
+    # N=1024, M=10, D=256: the reference cannot run this (>80 GB); the fp64 oracle can.
+    N, M, D = 1024, 10, 256
+    E = orc.make_embeddings(N, M, D, seed=3, kind="clustered")
+    ref = orc.forward_backward(E, 10.0, -5.0, 1e-6, "softmax")
+    got = run_cuda(pkg, E, 10.0, -5.0, precision=precision)
+    check(got, ref, N * M, tol)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("tf32", TF32_TOL)])
+def test_cfg3_contrast_vs_oracle(pkg, precision, tol):
+    N, M, D = 1024, 10, 256
+    E = orc.make_embeddings(N, M, D, seed=4, kind="random")
+    ref = orc.forward_backward(E, 10.0, -5.0, 1e-6, "contrast")
+    got = run_cuda(pkg, E, 10.0, -5.0, variant="contrast", precision=precision)
+    assert abs(got["loss"] - ref["loss"]) <= tol * max(1.0, abs(ref["loss"]))
+    if precision == "fp32":
+        assert rel(got["dE"], ref["dE"]) <= tol
+    else:
+        # TF32 rounding may move the argmax between near-tied negatives; compare what is robust
+        assert abs(got["dw"] - ref["dw"]) <= 5e-2 * max(1.0, abs(ref["dw"]))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_large_n_properties(pkg, precision):
+    """N=8192, M=16, D=256 (cfg 4) on one GPU: properties that do not need the O(U N D) oracle.
+      * sum_k p_rk < 1 => per-row loss >= 0 and loss is finite;
+      * permuting speakers permutes dE and leaves loss, dw, db unchanged (up to summation order);
+      * a row sample of per-row losses equals the oracle evaluated on those rows only."""
+    tol = FP32_TOL if precision == "fp32" else TF32_TOL
+    N, M, D = 8192, 16, 256
+    dev = torch.device("cuda:0")
+    E_np = orc.make_embeddings(N, M, D, seed=11, kind="clustered")
+    got = run_cuda(pkg, E_np, 10.0, -5.0, precision=precision)
+    assert np.isfinite(got["loss"]) and np.isfinite(got["dE"]).all()
+    perm = np.random.default_rng(0).permutation(N)
+    got_p = run_cuda(pkg, E_np[perm], 10.0, -5.0, precision=precision)
+    assert abs(got_p["loss"] - got["loss"]) <= tol * abs(got["loss"])
+    assert abs(got_p["dw"] - got["dw"]) <= tol * max(1.0, abs(got["dw"]))
+    assert rel(got_p["dE"], got["dE"][perm]) <= tol
+    # row sample against the oracle's definition (rows of 3 speakers against all centroids)
+    E64 = E_np.astype(np.float64)
+    C = E64.mean(axis=1)
+    Ch = C / np.maximum(np.linalg.norm(C, axis=1, keepdims=True), 1e-8)
+    spk = [0, 4097, 8191]
+    want = 0.0
+    for j in spk:
+        e = E64[j]
+        eh = e / np.maximum(np.linalg.norm(e, axis=1, keepdims=True), 1e-8)
+        u = (e.sum(0, keepdims=True) - e) / (M - 1)
+        uh = u / np.maximum(np.linalg.norm(u, axis=1, keepdims=True), 1e-8)
+        cos = eh @ Ch.T
+        cos[:, j] = (eh * uh).sum(1)
+        S = 10.0 * (cos + 1e-6) - 5.0
+        want += (np.log(np.exp(S).sum(1) + 1e-6) - S[:, j]).sum()
+    crit = pkg.GE2ELoss(None, device=dev)
+    Et = torch.tensor(E_np, device=dev)
+    sim = pkg.GE2ELoss.get_cos_sim(Et, None)            # fp32 path, materialised [N, M, N]
+    _, per = pkg.GE2ELoss.calc_loss(crit.w.detach() * sim + crit.b.detach())
+    have = per[spk].double().sum().item()
+    assert abs(have - want) <= FP32_TOL * abs(want)
+    assert abs(per.double().sum().item() - got["loss"]) <= tol * abs(got["loss"])
+
+
+# ------------------------------------------------------------------ static helpers (s5:42-43)
+def test_static_helpers_match_oracle(pkg):
+    dev = torch.device("cuda:0")
+    E_np = orc.make_embeddings(12, 5, 100, seed=2, kind="raw")
+    E = torch.tensor(E_np, device=dev)
+    C = pkg.GE2ELoss.get_centroids(E)
+    np.testing.assert_allclose(C.cpu().numpy(), orc.get_centroids(E_np), rtol=1e-5, atol=1e-6)
+    Uc = pkg.GE2ELoss.get_utterance_centroids(E)
+    np.testing.assert_allclose(Uc.cpu().numpy(), orc.get_utterance_centroids(E_np), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(pkg.GE2ELoss.get_centroid(E, 3, 2).cpu().numpy(),
+                               orc.get_utterance_centroids(E_np)[3, 2], rtol=1e-5, atol=1e-6)
+    cos = pkg.GE2ELoss.get_cos_sim(E, C)
+    np.testing.assert_allclose(cos.cpu().numpy(), orc.get_cos_sim(E_np, 1e-6), rtol=0, atol=2e-6)
+    S = 10.0 * cos - 5.0
+    loss, per = pkg.GE2ELoss.calc_loss(S)
+    want, want_per = orc.calc_loss(S.double().cpu().numpy(), 1e-6)
+    assert abs(loss.item() - want) <= FP32_TOL * abs(want)
+    np.testing.assert_allclose(per.cpu().numpy(), want_per, rtol=1e-5, atol=1e-5)
+    loss_c, per_c = pkg.GE2ELoss.calc_loss(S, variant="contrast")
+    want_c, want_per_c, _ = orc.calc_loss_contrast(S.double().cpu().numpy())
+    assert abs(loss_c.item() - want_c) <= FP32_TOL * abs(want_c)
+
+
+def test_eval_call_pattern_s5(pkg):
+    # s5_eval_model.py:27-28,42-46: CPU 0-dim w=1, b=0 and sim = w*cos+b then .numpy()
+    dev = torch.device("cuda:0")
+    E_np = orc.make_embeddings(4, 8, 256, seed=1)
+    E = torch.tensor(E_np, device=dev)
+    cent = pkg.GE2ELoss.get_centroids(E)
+    cos = pkg.GE2ELoss.get_cos_sim(E, cent, None)
+    sim = (1.0 * cos + 0.0).detach().cpu().numpy()
+    np.testing.assert_allclose(sim, orc.get_cos_sim(E_np, 1e-6), atol=2e-6)
+
+
+# ------------------------------------------------------------------ error behaviour
+def test_errors(pkg):
+    dev = torch.device("cuda:0")
+    crit = pkg.GE2ELoss(None, device=dev)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pkg.ge2e_loss(torch.zeros(2, 3, 4), torch.tensor(10.0), torch.tensor(-5.0))
+    with pytest.raises(ValueError):
+        crit(torch.zeros(2, 1, 4, device=dev))          # M == 1: reference yields NaN (s3:110-111)
+    with pytest.raises(ValueError):
+        crit(torch.zeros(6, 4, device=dev))
+    with pytest.raises(TypeError):
+        crit(torch.zeros(2, 3, 4, device=dev, dtype=torch.float64))
+    with pytest.raises(ValueError):
+        pkg.GE2ELoss(None, device=dev, variant="triplet")
+    # all-zero embeddings are finite (cos = 0)
+    E = torch.zeros(3, 4, 32, device=dev, requires_grad=True)
+    loss = crit(E)
+    loss.backward()
+    assert torch.isfinite(loss) and torch.isfinite(E.grad).all()
+    # non-contiguous input is accepted (made contiguous), as the reference's .view would require
+    Ebig = torch.tensor(orc.make_embeddings(4, 6, 64, seed=3), device=dev)
+    Enc = Ebig.transpose(0, 1).contiguous().transpose(0, 1)
+    assert abs(crit(Enc).item() - crit(Ebig).item()) < 1e-5
+
+
+# ------------------------------------------------------------------ drop-in training loop (s4:188-205)
+def test_training_steps_track_reference_port(pkg):
+    """The s4 step sequence (two SGD param groups, clip 3.0 / 1.0, loss.to('cpu')) with the CUDA
+    loss vs the torch port of the reference's expanded algorithm on CPU: same trajectories."""
+    from oracle import ge2e_ref_port as port
+    dev = torch.device("cuda:0")
+    N, M, F, D = 8, 6, 24, 64
+    torch.manual_seed(0)
+    X = torch.randn(N * M, F)
+    spk = torch.randn(N, 1, F).repeat(1, M, 1).reshape(N * M, F)
+    X = X * 0.3 + spk
+
+    def make(device):
+        torch.manual_seed(1)
+        lin = torch.nn.Linear(F, D)
+        return lin.to(device)
+
+    class RefLoss(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.tensor(10.0))
+            self.b = torch.nn.Parameter(torch.tensor(-5.0))
+
+        def forward(self, E):
+            return port.loss_full(E, self.w, self.b, 1e-6)
+
+    traj = {}
+    for tag, device, crit in (("ref", torch.device("cpu"), RefLoss()),
+                              ("new", dev, pkg.GE2ELoss(None, device=dev))):
+        model = make(device)
+        opt = torch.optim.SGD([{"params": model.parameters()}, {"params": crit.parameters()}], lr=0.01)
+        losses = []
+        x = X.to(device)
+        for _ in range(8):
+            emb = model(x)
+            emb = emb / emb.norm(dim=1, keepdim=True)          # s2:34
+            loss = crit(emb.reshape(N, M, D))                   # s4:192-196
+            opt.zero_grad()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 3.0)
+            torch.nn.utils.clip_grad_norm_(crit.parameters(), 1.0)
+            opt.step()
+            losses.append(float(loss.to("cpu").detach().numpy()))
+        traj[tag] = (losses, crit.w.item(), crit.b.item())
+    np.testing.assert_allclose(traj["new"][0], traj["ref"][0], rtol=2e-4)
+    assert abs(traj["new"][1] - traj["ref"][1]) < 1e-4
+    assert abs(traj["new"][2] - traj["ref"][2]) < 1e-4
