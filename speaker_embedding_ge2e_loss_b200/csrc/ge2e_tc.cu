@@ -1,16 +1,672 @@
-// tcgen05 / TMA / TMEM path (TF32 operands, fp32 accumulators in tensor memory).
+// tcgen05 / TMA / TMEM path of the GE2E loss (TF32 operands, fp32 accumulators in tensor memory).
+//
+// One warp-specialised kernel, three modes (the tensor-core twin of ge2e_simt.cu's strip kernel).
+// An "owner" operand tile X[128, D] stays resident in shared memory, a "stream" operand Y is
+// pulled through a TMA ring 128 rows at a time:
+//
+//   MMA1   T[128 x 128] = X . Y_tile^T          (SS, both K-major, K = D)          -> TMEM
+//   FWD    epilogue: online log-sum-exp (softmax) / running arg-max (contrast) over T's columns;
+//          S = w (cos + eps) + b is never written anywhere (reference s3:64-79, s3:27, s3:114-127)
+//   BWD    epilogue: G = w g (softmax(S) - onehot) with the leave-one-out diagonal masked,
+//          rounded to TF32 and written back over T in TMEM;
+//   MMA2   Acc[128 x D] += G . Y_tile            (A from TMEM, B MN-major from smem) -> TMEM
+//            BWD_DE: X = E_hat rows, Y = C_hat     -> dE_hat = (wG) C_hat
+//            BWD_DC: X = C_hat rows, Y = E_hat     -> dC_hat = (wG)^T E_hat
+//
+// Work is a flat list of (owner tile, stream tile) pairs, cut into equal contiguous ranges over a
+// persistent grid (stream-K): a CTA whose range covers only part of an owner tile publishes a
+// partial result (FWD: (max, sum) per row, merged by the last CTA to finish that tile; BWD: fp32
+// atomic adds into a zeroed output).
+//
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread),
+// warp 2 = TMEM allocator, warps 4-7 = epilogue (thread t owns TMEM lane / tile row t).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <limits.h>
+
+#include <algorithm>
+
 #include "ge2e_common.cuh"
+#include "ge2e_tc_ptx.cuh"
 
 namespace ge2e {
 
-bool tc_supported(int, int, int, int, int) { return false; }
-size_t tc_workspace_bytes(int, int, int, int, int) { return 0; }
-int tc_fwd_rows(const RowsArgs&, float*, int32_t*, float*, float*, void*, size_t, cudaStream_t) {
-  return GE2E_ERR_UNSUPPORTED;
+namespace {
+
+using namespace ptx;
+
+constexpr int kTile = 128;            // owner / stream tile rows (= UMMA M = MMA1 N)
+constexpr int kSlabCols = 32;         // fp32 columns per 128-byte swizzled row
+constexpr int kSlabBytes = kTile * 128;       // one [128 x 32] K-major slab = 16 KB
+constexpr int kStages = 6;            // TMA ring depth (16 KB each)
+constexpr int kStageBytes = 16384;
+constexpr int kMma2Rows = 16;         // stream rows per MMA2 ring stage ([D/32][16][32] MN-major)
+constexpr int kMaxSlabs = 8;          // D <= 256
+constexpr int kThreadsTc = 256;
+constexpr int kEpiWarp0 = 4;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+enum { TC_FWD = 0, TC_BWD_DE = 1, TC_BWD_DC = 2 };
+
+// barrier indices inside the shared barrier array
+enum {
+  BAR_FULL = 0,                       // [kStages]  TMA -> MMA
+  BAR_EMPTY = BAR_FULL + kStages,     // [kStages]  MMA -> TMA
+  BAR_A_FULL = BAR_EMPTY + kStages,   // owner tile landed
+  BAR_A_EMPTY,                        // owner tile no longer read by MMA1
+  BAR_S_FULL,                         // [2] MMA1 result in TMEM
+  BAR_S_EMPTY = BAR_S_FULL + 2,       // [2] FWD: epilogue drained T
+  BAR_G_FULL = BAR_S_EMPTY + 2,       // [2] BWD: G written back to TMEM
+  BAR_ACC_FULL = BAR_G_FULL + 2,      // BWD: accumulator complete for this segment
+  BAR_ACC_EMPTY,                      // BWD: accumulator drained
+  BAR_COUNT
+};
+
+struct TcParams {
+  int n_own, n_str, D, kslabs;
+  int M, spk_offset;
+  int OT, ST;                 // owner tiles, stream tiles
+  long long P;                // OT * ST pairs
+  const float* cos_diag;      // [U_local]
+  const float* row_stat;      // BWD: lse per local utterance row
+  const float* w;
+  const float* b;
+  const float* grad_out;
+  float eps;
+  // FWD outputs
+  float* row_stat_out;
+  int32_t* kstar_out;
+  float* loss_accum;
+  float* per_row_out;
+  int* seg_done;              // [OT] stream tiles finished per owner tile (zeroed by the host)
+  float2* seg_part;           // [OT][maxseg][128] partial row state
+  int maxseg;
+  // BWD outputs
+  float* acc_out;             // dE_hat [n_own, D] or dC_hat_partial [n_own, D]
+  float* dwdb;                // BWD_DE
+  int acc_atomic;             // 1: output was zeroed, always accumulate with atomics
+};
+
+struct SharedTail {
+  uint64_t bars[BAR_COUNT];
+  uint32_t tmem_base;
+  int flag;
+  float red[8];
+  float lse_s[2][kTile];      // BWD_DC: lse (log2 domain) of the current stream rows
+};
+
+__device__ __forceinline__ int cta_of_pair(long long p, long long P, int G) {
+  // largest c with floor(c * P / G) <= p
+  return static_cast<int>(((p + 1) * G + P - 1) / P) - 1;
 }
-int tc_bwd_rows(const RowsArgs&, const float*, const int32_t*, const float*, float*, float*, float*,
-                void*, size_t, cudaStream_t) {
-  return GE2E_ERR_UNSUPPORTED;
+
+template <int MODE, int VARIANT>
+__global__ void __launch_bounds__(kThreadsTc, 1)
+tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constant__ CUtensorMap tm_str2,
+                const __grid_constant__ CUtensorMap tm_str3, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr bool kBwd = (MODE != TC_FWD);
+  constexpr int kTmemCols = kBwd ? 512 : 256;
+
+  // carve: [owner slabs 8 x 16 KB][ring kStages x 16 KB][tail]
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t a_smem = smem_base;
+  const uint32_t ring_smem = smem_base + kMaxSlabs * kSlabBytes;
+  SharedTail* tail = reinterpret_cast<SharedTail*>(smem_al + kMaxSlabs * kSlabBytes + kStages * kStageBytes);
+  const uint32_t bars = smem_u32(&tail->bars[0]);
+  auto bar = [&](int i) { return bars + 8u * i; };
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int G = gridDim.x, c = blockIdx.x;
+  const long long p_begin = (static_cast<long long>(c) * p.P) / G;
+  const long long p_end = (static_cast<long long>(c + 1) * p.P) / G;
+  const int kslabs = p.kslabs;
+  const uint32_t slab_tx = kSlabBytes;                       // MMA1 stage bytes ([128][32] fp32)
+  const uint32_t mma2_tx = kslabs * kMma2Rows * 128;         // MMA2 stage bytes ([D/32][16][32])
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_own);
+    prefetch_tmap(&tm_str2);
+    if (kBwd) prefetch_tmap(&tm_str3);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(bar(BAR_FULL + i), 1); mbar_init(bar(BAR_EMPTY + i), 1); }
+    mbar_init(bar(BAR_A_FULL), 1);
+    mbar_init(bar(BAR_A_EMPTY), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(BAR_S_FULL + i), 1);
+      mbar_init(bar(BAR_S_EMPTY + i), 4);
+      mbar_init(bar(BAR_G_FULL + i), 4);
+    }
+    mbar_init(bar(BAR_ACC_FULL), 1);
+    mbar_init(bar(BAR_ACC_EMPTY), 4);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<kTmemCols>(smem_u32(&tail->tmem_base));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tail->tmem_base;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0, phase = 0, sg = 0;
+      auto load_mma1 = [&](int st) {
+        for (int ks = 0; ks < kslabs; ++ks) {
+          mbar_wait(bar(BAR_EMPTY + stage), phase ^ 1);
+          mbar_expect_tx(bar(BAR_FULL + stage), slab_tx);
+          tma_load_2d(ring_smem + stage * kStageBytes, &tm_str2, ks * kSlabCols, st * kTile, bar(BAR_FULL + stage));
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      };
+      auto load_mma2 = [&](int st) {
+        for (int kc = 0; kc < kTile / kMma2Rows; ++kc) {
+          mbar_wait(bar(BAR_EMPTY + stage), phase ^ 1);
+          mbar_expect_tx(bar(BAR_FULL + stage), mma2_tx);
+          tma_load_3d(ring_smem + stage * kStageBytes, &tm_str3, 0, st * kTile + kc * kMma2Rows, 0,
+                      bar(BAR_FULL + stage));
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      };
+      for (long long pp = p_begin; pp < p_end; ++sg) {
+        const int ot = static_cast<int>(pp / p.ST), s0 = static_cast<int>(pp % p.ST);
+        const int s1 = static_cast<int>(min(static_cast<long long>(p.ST), s0 + (p_end - pp)));
+        if (sg > 0) mbar_wait(bar(BAR_A_EMPTY), (sg - 1) & 1);
+        mbar_expect_tx(bar(BAR_A_FULL), kslabs * kSlabBytes);
+        for (int ks = 0; ks < kslabs; ++ks)
+          tma_load_2d(a_smem + ks * kSlabBytes, &tm_own, ks * kSlabCols, ot * kTile, bar(BAR_A_FULL));
+        if (!kBwd) {
+          for (int st = s0; st < s1; ++st) load_mma1(st);
+        } else {
+          load_mma1(s0);
+          for (int st = s0; st < s1; ++st) {
+            if (st + 1 < s1) load_mma1(st + 1);
+            load_mma2(st);
+          }
+        }
+        pp += s1 - s0;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc1 = idesc_tf32(kTile, kTile, 0, 0);
+      const uint32_t idesc2 = idesc_tf32(kTile, p.D, 0, 1);
+      int stage = 0, phase = 0, sg = 0, it = 0;
+      auto mma1 = [&](int iter) {
+        const int buf = iter & 1;
+        const uint32_t d_tmem = tmem + buf * kTile;
+        for (int ks = 0; ks < kslabs; ++ks) {
+          mbar_wait(bar(BAR_FULL + stage), phase);
+          tc_fence_after();
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint64_t da = smem_desc_sw128(a_smem + ks * kSlabBytes + k4 * 32, 16, 1024);
+            const uint64_t db = smem_desc_sw128(ring_smem + stage * kStageBytes + k4 * 32, 16, 1024);
+            umma_tf32_ss(d_tmem, da, db, idesc1, (ks | k4) != 0);
+          }
+          umma_commit(bar(BAR_EMPTY + stage));
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(bar(BAR_S_FULL + buf));
+      };
+      auto mma2 = [&](int iter, bool first) {
+        const int buf = iter & 1;
+        const uint32_t a_tmem = tmem + buf * kTile;
+        const uint32_t d_tmem = tmem + 2 * kTile;
+        for (int kc = 0; kc < kTile / kMma2Rows; ++kc) {
+          mbar_wait(bar(BAR_FULL + stage), phase);
+          tc_fence_after();
+#pragma unroll
+          for (int k2 = 0; k2 < kMma2Rows / 8; ++k2) {
+            const uint64_t db = smem_desc_sw128(ring_smem + stage * kStageBytes + k2 * 1024, kMma2Rows * 128, 1024);
+            umma_tf32_ts(d_tmem, a_tmem + kc * kMma2Rows + k2 * 8, db, idesc2, !(first && kc == 0 && k2 == 0));
+          }
+          umma_commit(bar(BAR_EMPTY + stage));
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      };
+      for (long long pp = p_begin; pp < p_end; ++sg) {
+        const int s0 = static_cast<int>(pp % p.ST);
+        const int s1 = static_cast<int>(min(static_cast<long long>(p.ST), s0 + (p_end - pp)));
+        mbar_wait(bar(BAR_A_FULL), sg & 1);
+        tc_fence_after();
+        if (!kBwd) {
+          for (int st = s0; st < s1; ++st, ++it) {
+            mbar_wait(bar(BAR_S_EMPTY + (it & 1)), ((it >> 1) & 1) ^ 1);
+            tc_fence_after();
+            mma1(it);
+          }
+          umma_commit(bar(BAR_A_EMPTY));
+        } else {
+          if (sg > 0) { mbar_wait(bar(BAR_ACC_EMPTY), (sg - 1) & 1); tc_fence_after(); }
+          mma1(it);
+          for (int st = s0; st < s1; ++st, ++it) {
+            if (st + 1 < s1) mma1(it + 1); else umma_commit(bar(BAR_A_EMPTY));
+            mbar_wait(bar(BAR_G_FULL + (it & 1)), (it >> 1) & 1);
+            tc_fence_after();
+            mma2(it, st == s0);
+          }
+          umma_commit(bar(BAR_ACC_FULL));
+        }
+        pp += s1 - s0;
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================================================================== epilogue
+    const int ew = warp - kEpiWarp0;                 // TMEM lanes [32 ew, 32 ew + 32)
+    const int trow = ew * 32 + lane;                 // row inside the owner tile
+    const uint32_t lane_addr = static_cast<uint32_t>(ew * 32) << 16;
+    const float w = __ldg(p.w), b = __ldg(p.b), eps = p.eps;
+    const float w2 = w * kLog2e, b2 = fmaf(w, eps, b) * kLog2e;   // log2-domain affine: S*log2e
+    const float bb = fmaf(w, eps, b);
+    const float g = kBwd ? __ldg(p.grad_out) : 1.f;
+    const float wg = w * g;
+    float dw_acc = 0.f, db_acc = 0.f, loss_acc = 0.f;
+    int sg = 0, it = 0;
+
+    for (long long pp = p_begin; pp < p_end; ++sg) {
+      const int ot = static_cast<int>(pp / p.ST), s0 = static_cast<int>(pp % p.ST);
+      const int s1 = static_cast<int>(min(static_cast<long long>(p.ST), s0 + (p_end - pp)));
+      const int orow = ot * kTile + trow;            // owner row (utterance, or centroid for DC)
+      const bool ovalid = orow < p.n_own;
+      // per-owner-row metadata
+      int jg = -1;            // FWD / DE: global speaker of this utterance row
+      float cd = 0.f, lse2 = INFINITY;
+      int dlo = 0, dhi = 0;   // DC: local utterance rows [dlo, dhi) belong to this centroid
+      if (MODE != TC_BWD_DC) {
+        if (ovalid) {
+          jg = p.spk_offset + orow / p.M;
+          cd = __ldg(p.cos_diag + orow);
+          if (MODE == TC_BWD_DE) lse2 = __ldg(p.row_stat + orow) * kLog2e;
+        }
+      } else {
+        const int jl = orow - p.spk_offset;
+        if (ovalid && jl >= 0 && (long long)jl * p.M < p.n_str) { dlo = jl * p.M; dhi = dlo + p.M; }
+      }
+      float m2 = -INFINITY, lsum = 0.f;      // FWD softmax running state (log2 domain)
+      float best = -INFINITY; int bestk = INT_MAX;   // FWD contrast
+
+      for (int st = s0; st < s1; ++st, ++it) {
+        const int buf = it & 1;
+        if (MODE == TC_BWD_DC) {
+          // stage the lse of the 128 stream rows (utterances) of this tile
+          const int u = st * kTile + trow;
+          tail->lse_s[buf][trow] = (u < p.n_str) ? __ldg(p.row_stat + u) * kLog2e : INFINITY;
+          named_bar_sync(1, 128);
+        }
+        mbar_wait(bar(BAR_S_FULL + buf), (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t t_addr = tmem + lane_addr + buf * kTile;
+#pragma unroll 1
+        for (int ch = 0; ch < kTile / 32; ++ch) {
+          const int c0 = st * kTile + ch * 32;       // first stream row (column of T) of this chunk
+          uint32_t v[32];
+          tmem_ld32(t_addr + ch * 32, v);
+          tmem_ld_wait();
+          if (MODE == TC_FWD) {
+            if (c0 < p.n_str) {
+              const bool tailc = c0 + 32 > p.n_str;
+              const bool diagc = static_cast<unsigned>(jg - c0) < 32u;
+              if (VARIANT == GE2E_SOFTMAX) {
+                float x[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) x[i] = fmaf(__uint_as_float(v[i]), w2, b2);
+                if (__any_sync(0xffffffffu, tailc || diagc)) {
+                  const float xd = fmaf(cd, w2, b2);
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) {
+                    if (c0 + i == jg) x[i] = xd;                 // leave-one-out diagonal (s3:78)
+                    if (c0 + i >= p.n_str) x[i] = -INFINITY;
+                  }
+                }
+                float cm = x[0];
+#pragma unroll
+                for (int i = 1; i < 32; ++i) cm = fmaxf(cm, x[i]);
+                const float mn = fmaxf(m2, cm);
+                float s = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) s += ex2(x[i] - mn);
+                lsum = fmaf(lsum, ex2(m2 - mn), s);
+                m2 = mn;
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  float s = fmaf(__uint_as_float(v[i]), w, bb);
+                  if (c0 + i == jg || c0 + i >= p.n_str) s = -INFINITY;
+                  if (s > best) { best = s; bestk = c0 + i; }
+                }
+              }
+            }
+          } else {
+            // ---- backward: G tile, written back over T
+            uint32_t gq[32];
+            if (MODE == TC_BWD_DE) {
+              const bool special = (c0 + 32 > p.n_str) || (static_cast<unsigned>(jg - c0) < 32u);
+              const bool any_special = __any_sync(0xffffffffu, special);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float dot = __uint_as_float(v[i]);
+                float pr = ex2(fmaf(dot, w2, b2) - lse2);        // softmax prob (0 for padded rows)
+                if (any_special) {
+                  if (c0 + i >= p.n_str) pr = 0.f;
+                  if (c0 + i == jg) {
+                    // diagonal: uses cos_diag, contributes to dw but not to the contraction
+                    const float pd = ex2(fmaf(cd, w2, b2) - lse2);
+                    dw_acc = fmaf(pd - 1.f, cd + eps, dw_acc);
+                    pr = 0.f;
+                  }
+                }
+                dw_acc = fmaf(pr, dot + eps, dw_acc);
+                gq[i] = __float_as_uint(round_tf32(wg * pr));
+              }
+            } else {
+              const float4* ls4 = reinterpret_cast<const float4*>(&tail->lse_s[buf][ch * 32]);
+              const bool special = (c0 < dhi) && (c0 + 32 > dlo);
+              const bool any_special = __any_sync(0xffffffffu, special);
+#pragma unroll
+              for (int i4 = 0; i4 < 8; ++i4) {
+                const float4 l4 = ls4[i4];
+                const float ls[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const int i = i4 * 4 + q;
+                  float pr = ex2(fmaf(__uint_as_float(v[i]), w2, b2) - ls[q]);   // lse = +inf past the end
+                  if (any_special && c0 + i >= dlo && c0 + i < dhi) pr = 0.f;    // own speaker's rows
+                  gq[i] = __float_as_uint(round_tf32(wg * pr));
+                }
+              }
+            }
+            tmem_st32(t_addr + ch * 32, gq);
+          }
+        }
+        if (MODE == TC_FWD) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(BAR_S_EMPTY + buf));
+        } else {
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(BAR_G_FULL + buf));
+        }
+      }
+
+      // ------------------------------------------------------------ segment flush
+      const bool full = (s0 == 0 && s1 == p.ST);
+      if (MODE == TC_FWD) {
+        // publish the partial row state, last finisher of this owner tile merges
+        const int first_cta = cta_of_pair(static_cast<long long>(ot) * p.ST, p.P, G);
+        const int slot = c - first_cta;
+        float2 part;
+        if (VARIANT == GE2E_SOFTMAX) part = make_float2(m2, lsum);
+        else part = make_float2(best, __int_as_float(bestk));
+        bool last = full;
+        if (!full) {
+          p.seg_part[(static_cast<size_t>(ot) * p.maxseg + slot) * kTile + trow] = part;
+          __threadfence();
+          named_bar_sync(1, 128);
+          if (trow == 0) {
+            const int done = atomicAdd(p.seg_done + ot, s1 - s0) + (s1 - s0);
+            tail->flag = (done == p.ST);
+          }
+          named_bar_sync(1, 128);
+          last = tail->flag != 0;
+          if (last) {
+            __threadfence();
+            const int last_cta = cta_of_pair(static_cast<long long>(ot) * p.ST + p.ST - 1, p.P, G);
+            const int nseg = last_cta - first_cta + 1;
+            m2 = -INFINITY; lsum = 0.f; best = -INFINITY; bestk = INT_MAX;
+            for (int sgi = 0; sgi < nseg; ++sgi) {
+              const float2 q = __ldcg(&p.seg_part[(static_cast<size_t>(ot) * p.maxseg + sgi) * kTile + trow]);
+              if (VARIANT == GE2E_SOFTMAX) {
+                const float mn = fmaxf(m2, q.x);
+                if (mn > -INFINITY) lsum = lsum * ex2(m2 - mn) + q.y * ex2(q.x - mn);
+                m2 = mn;
+              } else {
+                const int qk = __float_as_int(q.y);
+                if (q.x > best || (q.x == best && qk < bestk)) { best = q.x; bestk = qk; }
+              }
+            }
+          }
+        }
+        if (last && ovalid) {
+          const float Sd = fmaf(w, cd + eps, b);
+          float per, stat;
+          int ks = -1;
+          if (VARIANT == GE2E_SOFTMAX) {
+            const float mx = m2 * kLn2;                         // natural-log running max
+            stat = (mx > -80.f) ? mx + logf(lsum + eps * expf(-mx)) : logf(eps + lsum * expf(mx));   // s3:120
+            per = stat - Sd;                                    // s3:121
+          } else {
+            per = 1.f - 1.f / (1.f + expf(-Sd));
+            stat = best;
+            if (bestk != INT_MAX) { ks = bestk; per += 1.f / (1.f + expf(-best)); }
+          }
+          p.row_stat_out[orow] = stat;
+          if (p.kstar_out != nullptr) p.kstar_out[orow] = ks;
+          if (p.per_row_out != nullptr) p.per_row_out[orow] = per;
+          loss_acc += per;
+        }
+      } else {
+        // drain the accumulator [128 x D] of this segment
+        if (MODE == TC_BWD_DE && ovalid && s0 == 0) db_acc -= g * eps * ex2(-lse2);   // closed form, item 12
+        mbar_wait(bar(BAR_ACC_FULL), sg & 1);
+        tc_fence_after();
+        const bool atomic = p.acc_atomic || !full;
+        float* out = p.acc_out + static_cast<size_t>(orow) * p.D;
+        for (int ch = 0; ch < kslabs; ++ch) {
+          uint32_t v[32];
+          tmem_ld32(tmem + lane_addr + 2 * kTile + ch * 32, v);
+          tmem_ld_wait();
+          if (ovalid) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              float4 o = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                                     __uint_as_float(v[i + 3]));
+              float4* dst = reinterpret_cast<float4*>(out + ch * 32 + i);
+              if (atomic) atomicAdd(dst, o); else *dst = o;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(BAR_ACC_EMPTY));
+      }
+      pp += s1 - s0;
+    }
+
+    // ------------------------------------------------------------ scalar reductions (once per CTA)
+    if (MODE == TC_FWD) {
+      loss_acc = warp_sum(loss_acc);
+      if (lane == 0) tail->red[ew] = loss_acc;
+      named_bar_sync(1, 128);
+      if (trow == 0) atomicAdd(p.loss_accum, tail->red[0] + tail->red[1] + tail->red[2] + tail->red[3]);
+    } else if (MODE == TC_BWD_DE) {
+      dw_acc = warp_sum(dw_acc) * g;
+      db_acc = warp_sum(db_acc);
+      if (lane == 0) { tail->red[ew] = dw_acc; tail->red[4 + ew] = db_acc; }
+      named_bar_sync(1, 128);
+      if (trow == 0) {
+        atomicAdd(p.dwdb + 0, tail->red[0] + tail->red[1] + tail->red[2] + tail->red[3]);
+        atomicAdd(p.dwdb + 1, tail->red[4] + tail->red[5] + tail->red[6] + tail->red[7]);
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<kTmemCols>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+// 2-D map over X[rows, D] fp32: box = [128 rows][32 cols], 128-byte swizzle (K-major slabs).
+int make_map_2d(CUtensorMap* m, const float* base, int rows, int D) {
+  auto enc = get_encode();
+  if (enc == nullptr) return GE2E_ERR_LAUNCH;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(D) * 4};
+  cuuint32_t box[2] = {kSlabCols, kTile};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? GE2E_OK : GE2E_ERR_LAUNCH;
+}
+
+// 3-D map over the same X viewed as [D/32][rows][32]: box = [D/32][16 rows][32 cols]
+// (MN-major operand chunks for MMA2: 16 k-rows x all D columns per ring stage).
+int make_map_3d(CUtensorMap* m, const float* base, int rows, int D) {
+  auto enc = get_encode();
+  if (enc == nullptr) return GE2E_ERR_LAUNCH;
+  cuuint64_t dims[3] = {kSlabCols, static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(D / kSlabCols)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(D) * 4, kSlabCols * 4};
+  cuuint32_t box[3] = {kSlabCols, kMma2Rows, static_cast<cuuint32_t>(D / kSlabCols)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? GE2E_OK : GE2E_ERR_LAUNCH;
+}
+
+constexpr size_t kSmemBytes = 1024 + kMaxSlabs * kSlabBytes + kStages * kStageBytes + sizeof(SharedTail);
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+int fwd_maxseg(long long P, int ST, int G) {
+  const long long per = P / G;                 // >= 1 because G <= P
+  return static_cast<int>(std::min<long long>(ST, ST / per + 2));
+}
+
+struct FwdLayout {
+  int OT, ST, G, maxseg;
+  size_t done_bytes, part_bytes;
+};
+
+FwdLayout fwd_layout(int n_local, int n_total, int M) {
+  FwdLayout L{};
+  const long long U = static_cast<long long>(n_local) * M;
+  L.OT = static_cast<int>((U + kTile - 1) / kTile);
+  L.ST = (n_total + kTile - 1) / kTile;
+  const long long P = static_cast<long long>(L.OT) * L.ST;
+  L.G = static_cast<int>(std::min<long long>(sm_count(), P));
+  L.maxseg = fwd_maxseg(P, L.ST, L.G);
+  L.done_bytes = (static_cast<size_t>(L.OT) * sizeof(int) + 255) & ~static_cast<size_t>(255);
+  L.part_bytes = static_cast<size_t>(L.OT) * L.maxseg * kTile * sizeof(float2);
+  return L;
+}
+
+template <int MODE, int VARIANT>
+int launch_tc(const CUtensorMap& own, const CUtensorMap& s2, const CUtensorMap& s3, const TcParams& p, int G,
+              cudaStream_t st) {
+  auto kern = tc_strip_kernel<MODE, VARIANT>;
+  GE2E_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  kern<<<G, kThreadsTc, kSmemBytes, st>>>(own, s2, s3, p);
+  GE2E_LAUNCHED();
+  return GE2E_OK;
+}
+
+}  // namespace
+
+bool tc_supported(int n_local, int n_total, int M, int D, int variant) {
+  (void)variant;
+  if (D % kSlabCols != 0 || D < kSlabCols || D > kMaxSlabs * kSlabCols) return false;
+  if (n_total < 256 || static_cast<long long>(n_local) * M < 256) return false;
+  return get_encode() != nullptr;
+}
+
+size_t tc_workspace_bytes(int n_local, int n_total, int M, int D, int variant) {
+  (void)D; (void)variant;
+  const FwdLayout L = fwd_layout(n_local, n_total, M);
+  return L.done_bytes + L.part_bytes;
+}
+
+int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* loss_accum, float* per_row_out,
+                void* ws, size_t ws_bytes, cudaStream_t st) {
+  const FwdLayout L = fwd_layout(a.n_local, a.n_total, a.M);
+  if (ws_bytes < L.done_bytes + L.part_bytes) return GE2E_ERR_WORKSPACE;
+  const int U = a.n_local * a.M;
+  CUtensorMap tmE, tmC;
+  int rc = make_map_2d(&tmE, a.e_hat, U, a.D);
+  if (rc != GE2E_OK) return rc;
+  if ((rc = make_map_2d(&tmC, a.c_hat_all, a.n_total, a.D)) != GE2E_OK) return rc;
+  TcParams p{};
+  p.n_own = U; p.n_str = a.n_total; p.D = a.D; p.kslabs = a.D / kSlabCols;
+  p.M = a.M; p.spk_offset = a.spk_offset;
+  p.OT = L.OT; p.ST = L.ST; p.P = static_cast<long long>(L.OT) * L.ST;
+  p.cos_diag = a.cos_diag; p.w = a.w; p.b = a.b; p.eps = a.eps;
+  p.row_stat_out = row_stat; p.kstar_out = row_kstar; p.loss_accum = loss_accum; p.per_row_out = per_row_out;
+  p.seg_done = static_cast<int*>(ws);
+  p.seg_part = reinterpret_cast<float2*>(static_cast<uint8_t*>(ws) + L.done_bytes);
+  p.maxseg = L.maxseg;
+  GE2E_CUDA_TRY(cudaMemsetAsync(ws, 0, L.done_bytes, st));
+  if (a.variant == GE2E_SOFTMAX) return launch_tc<TC_FWD, GE2E_SOFTMAX>(tmE, tmC, tmC, p, L.G, st);
+  return launch_tc<TC_FWD, GE2E_CONTRAST>(tmE, tmC, tmC, p, L.G, st);
+}
+
+int tc_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kstar, const float* grad_out,
+                float* dE_hat, float* dC_hat_partial, float* dwdb_accum, void* ws, size_t ws_bytes,
+                cudaStream_t st) {
+  (void)row_kstar; (void)ws; (void)ws_bytes;
+  const int U = a.n_local * a.M;
+  const size_t dc_elems = static_cast<size_t>(a.n_total) * a.D;
+  if (dwdb_accum == dC_hat_partial + dc_elems) {
+    GE2E_CUDA_TRY(cudaMemsetAsync(dC_hat_partial, 0, (dc_elems + 2) * sizeof(float), st));
+  } else {
+    GE2E_CUDA_TRY(cudaMemsetAsync(dC_hat_partial, 0, dc_elems * sizeof(float), st));
+    GE2E_CUDA_TRY(cudaMemsetAsync(dwdb_accum, 0, 2 * sizeof(float), st));
+  }
+  CUtensorMap tmE2, tmC2, tmE3, tmC3;
+  int rc;
+  if ((rc = make_map_2d(&tmE2, a.e_hat, U, a.D)) != GE2E_OK) return rc;
+  if ((rc = make_map_2d(&tmC2, a.c_hat_all, a.n_total, a.D)) != GE2E_OK) return rc;
+  if ((rc = make_map_3d(&tmE3, a.e_hat, U, a.D)) != GE2E_OK) return rc;
+  if ((rc = make_map_3d(&tmC3, a.c_hat_all, a.n_total, a.D)) != GE2E_OK) return rc;
+  const int UT = (U + kTile - 1) / kTile, CT = (a.n_total + kTile - 1) / kTile;
+
+  TcParams p{};
+  p.D = a.D; p.kslabs = a.D / kSlabCols; p.M = a.M; p.spk_offset = a.spk_offset;
+  p.cos_diag = a.cos_diag; p.row_stat = row_stat; p.w = a.w; p.b = a.b; p.grad_out = grad_out; p.eps = a.eps;
+
+  // dE_hat = (wG) C_hat: owner = utterance tiles, each CTA runs one whole owner tile (plain stores)
+  p.n_own = U; p.n_str = a.n_total; p.OT = UT; p.ST = CT; p.P = static_cast<long long>(UT) * CT;
+  p.acc_out = dE_hat; p.dwdb = dwdb_accum; p.acc_atomic = 0;
+  rc = launch_tc<TC_BWD_DE, GE2E_SOFTMAX>(tmE2, tmC2, tmC3, p, UT, st);
+  if (rc != GE2E_OK) return rc;
+
+  // dC_hat = (wG)^T E_hat: owner = centroid tiles, the utterance range is cut stream-K style over
+  // the whole grid, partial tiles are accumulated with fp32 atomics into the zeroed output
+  p.n_own = a.n_total; p.n_str = U; p.OT = CT; p.ST = UT; p.P = static_cast<long long>(UT) * CT;
+  p.acc_out = dC_hat_partial; p.dwdb = nullptr; p.acc_atomic = 1;
+  const int G = static_cast<int>(std::min<long long>(sm_count(), p.P));
+  return launch_tc<TC_BWD_DC, GE2E_SOFTMAX>(tmC2, tmE2, tmE3, p, G, st);
 }
 
 }  // namespace ge2e

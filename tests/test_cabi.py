@@ -1,0 +1,116 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU and exports exactly
+what include/ge2e_b200.h declares; host-side argument checking; module surface."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "ge2e_b200.h")
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    from speaker_embedding_ge2e_loss_b200 import build
+    build.build()   # nvcc cross-compiles sm_100a without a GPU
+    import speaker_embedding_ge2e_loss_b200 as p
+    return p
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ge2e_b200_\w+)\s*\(", src)))
+
+
+def test_header_declares_entry_points():
+    names = declared_functions()
+    for must in ("ge2e_b200_forward", "ge2e_b200_backward", "ge2e_b200_prep", "ge2e_b200_fwd_rows",
+                 "ge2e_b200_bwd_rows", "ge2e_b200_bwd_finalize", "ge2e_b200_centroids",
+                 "ge2e_b200_utterance_centroids", "ge2e_b200_calc_loss", "ge2e_b200_workspace_bytes"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    from speaker_embedding_ge2e_loss_b200.build import LIB_PATH
+    h = ctypes.CDLL(LIB_PATH)
+    for name in declared_functions():
+        assert hasattr(h, name), f"{name} declared in include/ge2e_b200.h but not exported"
+    out = subprocess.run(["nm", "-D", "--defined-only", LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (ge2e_b200_\w+)", out))
+    assert exported == set(declared_functions())
+
+
+def test_binding_prototypes_cover_header(pkg):
+    from speaker_embedding_ge2e_loss_b200 import _lib
+    assert sorted(_lib.PROTOTYPES) == declared_functions()
+
+
+def test_host_side_status_codes(pkg):
+    h = pkg.lib()
+    assert h.ge2e_b200_version() >= 100
+    assert h.ge2e_b200_strerror(0) == b"ok"
+    for code in range(-6, 0):
+        assert h.ge2e_b200_strerror(code) not in (b"ok", b"unknown ge2e status")
+    # argument checking happens before any CUDA call: safe without a GPU
+    assert h.ge2e_b200_forward(None, 4, 8, 256, None, None, 1e-6, 0, 0, None, None, None, None, None, None,
+                               None, 0, None) == -3
+    assert h.ge2e_b200_prep(1, 4, 1, 256, 0, 1, 1, 1, 1, None) == -1          # M < 2
+    assert h.ge2e_b200_prep(1, 4, 8, 256, 7, 1, 1, 1, 1, None) == -3          # unknown precision
+    assert h.ge2e_b200_fwd_rows(1, 1, 1, 4, 2, 0, 8, 256, 1, 1, 1e-6, 0, 0, 1, None, 1, None, None, None, 0,
+                                None) == -1                                    # shard outside [0, n_total)
+    assert h.ge2e_b200_calc_loss(1, 4, 8, 1e-6, 9, 1, None, None) == -3
+    assert h.ge2e_b200_path(64, 64, 10, 256, 0, 0) == 0                        # fp32 -> SIMT kernels
+    assert h.ge2e_b200_path(64, 64, 10, 256, 5, 0) < 0
+
+
+def test_module_surface_matches_reference(pkg):
+    # reference: s3_loss_function_GE2E.py:6-127 -- ctor(hp), w/b parameters, static helpers
+    class General:
+        device = torch.device("cpu")
+        small_err = 1e-6
+
+    class HP:
+        general = General()
+
+    crit = pkg.GE2ELoss(HP())
+    names = dict(crit.named_parameters())
+    assert set(names) == {"w", "b"}
+    assert crit.w.item() == 10.0 and crit.b.item() == -5.0 and crit.w.dim() == 0
+    assert crit.w.requires_grad and crit.b.requires_grad
+    assert crit.eps == 1e-6 and crit.device == torch.device("cpu") and crit.hp is not None
+    assert set(crit.state_dict()) == {"w", "b"}
+    for helper in ("get_centroids", "get_cos_sim", "get_centroid", "get_utterance_centroids", "calc_loss"):
+        assert callable(getattr(pkg.GE2ELoss, helper))
+    # dict-style hp (utils/dict_to_dot.py builds a dict subclass)
+    crit2 = pkg.GE2ELoss({"general": {"device": torch.device("cpu"), "small_err": 1e-5}})
+    assert crit2.eps == 1e-5
+
+
+def test_no_cpu_fallback(pkg):
+    crit = pkg.GE2ELoss(None, device=torch.device("cpu"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        crit(torch.randn(4, 8, 16))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pkg.GE2ELoss.get_centroids(torch.randn(4, 8, 16))
+    with pytest.raises(RuntimeError):
+        pkg.GE2EPlan(4, 8, 16, device="cpu")
+
+
+def test_missing_library_fails_loudly(pkg, monkeypatch):
+    from speaker_embedding_ge2e_loss_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libge2e_b200.so")
+    with pytest.raises(_lib.GE2ELibraryError, match="no CPU"):
+        _lib.lib()
+
+
+def test_product_does_not_import_oracle():
+    pkg_dir = os.path.join(ROOT, "speaker_embedding_ge2e_loss_b200")
+    for fn in os.listdir(pkg_dir):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg_dir, fn)).read()
+            assert "oracle" not in src, f"{fn} references oracle/"
