@@ -195,14 +195,16 @@ def stage_times(plan, E, w, b, flush_buf, reps=20):
         "fwd_rows": lambda: h.ge2e_b200_fwd_rows(plan.e_hat.data_ptr(), plan.c_hat.data_ptr(), plan.cos_diag.data_ptr(),
                                                  N, N, 0, M, D, w.data_ptr(), b.data_ptr(), plan.eps, plan.variant,
                                                  plan.precision, plan.row_stat.data_ptr(), plan.row_kstar.data_ptr(),
-                                                 acc, None, None, ws, plan._ws_bytes, s),
+                                                 plan.row_aux.data_ptr(), acc, None, None, ws, plan._ws_bytes, s),
         "bwd_rows": lambda: h.ge2e_b200_bwd_rows(plan.e_hat.data_ptr(), plan.c_hat.data_ptr(), plan.cos_diag.data_ptr(),
-                                                 plan.row_stat.data_ptr(), plan.row_kstar.data_ptr(), N, N, 0, M, D,
+                                                 plan.row_stat.data_ptr(), plan.row_kstar.data_ptr(),
+                                                 plan.row_aux.data_ptr(), N, N, 0, M, D,
                                                  w.data_ptr(), b.data_ptr(), plan.eps, plan.variant, plan.precision,
                                                  plan.grad_out.data_ptr(), plan.dE_hat.data_ptr(), scr,
                                                  scr + N * D * 4, ws, plan._ws_bytes, s),
         "bwd_finalize": lambda: h.ge2e_b200_bwd_finalize(E.data_ptr(), plan.dE_hat.data_ptr(), scr,
-                                                         plan.cos_diag.data_ptr(), plan.row_stat.data_ptr(), N, M, D,
+                                                         plan.cos_diag.data_ptr(), plan.row_stat.data_ptr(),
+                                                         plan.row_aux.data_ptr(), N, M, D,
                                                          w.data_ptr(), b.data_ptr(), plan.eps, plan.variant,
                                                          plan.grad_out.data_ptr(), plan.dE.data_ptr(), s),
     }

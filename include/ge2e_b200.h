@@ -87,13 +87,17 @@ int ge2e_b200_prep(const float* E, int n_local, int M, int D, int precision, flo
  *                      contrast: max_{k != j} S_rk
  *   row_kstar[U_local] contrast: argmax (lowest k on ties, -1 if n_total == 1); may be NULL
  *                      for softmax
+ *   row_aux[U_local]   softmax : q_r = 1 - p_rj = (sum_{k != j} exp S_rk + eps) / (sum_k exp S_rk
+ *                      + eps), accumulated without the diagonal so that the own-speaker
+ *                      gradient G_rj = -g q_r does not cancel (the reference's exp(S - lse) - 1
+ *                      loses all digits on well-separated speakers); may be NULL for contrast
  *   loss_accum         += sum of the local rows' losses (zeroed by ge2e_b200_prep)
  *   per_row_out        optional [U_local] per-embedding loss (s3:121)
  *   sim_out            optional [U_local, n_total] cos + eps (what get_cos_sim returns)   */
 int ge2e_b200_fwd_rows(const float* e_hat, const float* c_hat_all, const float* cos_diag,
                        int n_local, int n_total, int spk_offset, int M, int D,
                        const float* w, const float* b, float eps, int variant, int precision,
-                       float* row_stat, int32_t* row_kstar, float* loss_accum,
+                       float* row_stat, int32_t* row_kstar, float* row_aux, float* loss_accum,
                        float* per_row_out, float* sim_out, void* workspace,
                        size_t workspace_bytes, ge2e_stream_t stream);
 
@@ -105,8 +109,8 @@ int ge2e_b200_fwd_rows(const float* e_hat, const float* c_hat_all, const float* 
  *   dwdb_accum[2]              += {dw, db} of the local rows (zeroed by ge2e_b200_prep as
  *                              accum+1)                                                  */
 int ge2e_b200_bwd_rows(const float* e_hat, const float* c_hat_all, const float* cos_diag,
-                       const float* row_stat, const int32_t* row_kstar, int n_local,
-                       int n_total, int spk_offset, int M, int D, const float* w,
+                       const float* row_stat, const int32_t* row_kstar, const float* row_aux,
+                       int n_local, int n_total, int spk_offset, int M, int D, const float* w,
                        const float* b, float eps, int variant, int precision,
                        const float* grad_out, float* dE_hat, float* dC_hat_partial,
                        float* dwdb_accum, void* workspace, size_t workspace_bytes,
@@ -117,22 +121,22 @@ int ge2e_b200_bwd_rows(const float* e_hat, const float* c_hat_all, const float* 
  *   dC_hat_local[n_local, D]  this rank's rows of the (reduced) dC_hat
  *   dE[U_local, D]            gradient wrt the raw embeddings                            */
 int ge2e_b200_bwd_finalize(const float* E, const float* dE_hat, const float* dC_hat_local,
-                           const float* cos_diag, const float* row_stat, int n_local, int M,
-                           int D, const float* w, const float* b, float eps, int variant,
-                           const float* grad_out, float* dE, ge2e_stream_t stream);
+                           const float* cos_diag, const float* row_stat, const float* row_aux,
+                           int n_local, int M, int D, const float* w, const float* b, float eps,
+                           int variant, const float* grad_out, float* dE, ge2e_stream_t stream);
 
 /* ---- single-device conveniences (n_local == n_total) ---------------------------------- */
 
 /* GE2ELoss.forward (s3:19-30): prep + fwd_rows.  loss = accum[0]. */
 int ge2e_b200_forward(const float* E, int N, int M, int D, const float* w, const float* b,
                       float eps, int variant, int precision, float* e_hat, float* c_hat,
-                      float* cos_diag, float* row_stat, int32_t* row_kstar, float* accum,
-                      void* workspace, size_t workspace_bytes, ge2e_stream_t stream);
+                      float* cos_diag, float* row_stat, int32_t* row_kstar, float* row_aux,
+                      float* accum, void* workspace, size_t workspace_bytes, ge2e_stream_t stream);
 
 /* loss.backward() (s4:200): bwd_rows + bwd_finalize.  dw = accum[1], db = accum[2]. */
 int ge2e_b200_backward(const float* E, const float* e_hat, const float* c_hat,
                        const float* cos_diag, const float* row_stat, const int32_t* row_kstar,
-                       int N, int M, int D, const float* w, const float* b, float eps,
+                       const float* row_aux, int N, int M, int D, const float* w, const float* b, float eps,
                        int variant, int precision, const float* grad_out, float* dE_hat,
                        float* dC_hat, float* accum, float* dE, void* workspace,
                        size_t workspace_bytes, ge2e_stream_t stream);

@@ -27,17 +27,17 @@ PROTOTYPES = {
     "ge2e_b200_prep": (C.c_int, [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p,
                                  _stream]),
     "ge2e_b200_fwd_rows": (C.c_int, [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                     _f32p, _f32p, C.c_float, C.c_int, C.c_int, _f32p, _i32p, _f32p,
+                                     _f32p, _f32p, C.c_float, C.c_int, C.c_int, _f32p, _i32p, _f32p, _f32p,
                                      _f32p, _f32p, C.c_void_p, C.c_size_t, _stream]),
-    "ge2e_b200_bwd_rows": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _i32p, C.c_int, C.c_int, C.c_int,
+    "ge2e_b200_bwd_rows": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _i32p, _f32p, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_int, _f32p, _f32p, C.c_float, C.c_int, C.c_int,
                                      _f32p, _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, _stream]),
-    "ge2e_b200_bwd_finalize": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int,
+    "ge2e_b200_bwd_finalize": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int,
                                          _f32p, _f32p, C.c_float, C.c_int, _f32p, _f32p, _stream]),
     "ge2e_b200_forward": (C.c_int, [_f32p, C.c_int, C.c_int, C.c_int, _f32p, _f32p, C.c_float, C.c_int,
-                                    C.c_int, _f32p, _f32p, _f32p, _f32p, _i32p, _f32p, C.c_void_p,
+                                    C.c_int, _f32p, _f32p, _f32p, _f32p, _i32p, _f32p, _f32p, C.c_void_p,
                                     C.c_size_t, _stream]),
-    "ge2e_b200_backward": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _i32p, C.c_int, C.c_int,
+    "ge2e_b200_backward": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _i32p, _f32p, C.c_int, C.c_int,
                                      C.c_int, _f32p, _f32p, C.c_float, C.c_int, C.c_int, _f32p, _f32p,
                                      _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, _stream]),
     "ge2e_b200_centroids": (C.c_int, [_f32p, C.c_int, C.c_int, C.c_int, _f32p, _stream]),

@@ -84,14 +84,15 @@ int ge2e_b200_prep(const float* E, int n_local, int M, int D, int precision, flo
 int ge2e_b200_fwd_rows(const float* e_hat, const float* c_hat_all, const float* cos_diag,
                        int n_local, int n_total, int spk_offset, int M, int D, const float* w,
                        const float* b, float eps, int variant, int precision, float* row_stat,
-                       int32_t* row_kstar, float* loss_accum, float* per_row_out, float* sim_out,
-                       void* workspace, size_t workspace_bytes, ge2e_stream_t stream) {
+                       int32_t* row_kstar, float* row_aux, float* loss_accum, float* per_row_out,
+                       float* sim_out, void* workspace, size_t workspace_bytes, ge2e_stream_t stream) {
   if (!e_hat || !c_hat_all || !cos_diag || !w || !b || !row_stat || !loss_accum)
     return GE2E_ERR_ARGUMENT;
   int rc = check_shape(n_local, n_total, spk_offset, M, D);
   if (rc != GE2E_OK) return rc;
   if ((rc = check_enum(variant, precision)) != GE2E_OK) return rc;
   if (variant == GE2E_CONTRAST && !row_kstar) return GE2E_ERR_ARGUMENT;
+  if (variant == GE2E_SOFTMAX && !row_aux) return GE2E_ERR_ARGUMENT;
   RowsArgs a{e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, b, eps, variant};
   if (precision == GE2E_TF32 && tc_supported(n_local, n_total, M, D, variant)) {
     // the tensor-core path never materialises S: sim_out is an fp32-path feature
@@ -99,15 +100,17 @@ int ge2e_b200_fwd_rows(const float* e_hat, const float* c_hat_all, const float* 
     if (workspace_bytes < tc_workspace_bytes(n_local, n_total, M, D, variant) ||
         (workspace == nullptr && tc_workspace_bytes(n_local, n_total, M, D, variant) > 0))
       return GE2E_ERR_WORKSPACE;
-    return tc_fwd_rows(a, row_stat, row_kstar, loss_accum, per_row_out, workspace, workspace_bytes,
+    return tc_fwd_rows(a, row_stat, row_kstar, row_aux, loss_accum, per_row_out, workspace, workspace_bytes,
                        (cudaStream_t)stream);
   }
-  return simt_fwd_rows(a, row_stat, row_kstar, loss_accum, per_row_out, sim_out, (cudaStream_t)stream);
+  return simt_fwd_rows(a, row_stat, row_kstar, row_aux, loss_accum, per_row_out, sim_out,
+                       (cudaStream_t)stream);
 }
 
 int ge2e_b200_bwd_rows(const float* e_hat, const float* c_hat_all, const float* cos_diag,
-                       const float* row_stat, const int32_t* row_kstar, int n_local, int n_total,
-                       int spk_offset, int M, int D, const float* w, const float* b, float eps,
+                       const float* row_stat, const int32_t* row_kstar, const float* row_aux,
+                       int n_local, int n_total, int spk_offset, int M, int D, const float* w,
+                       const float* b, float eps,
                        int variant, int precision, const float* grad_out, float* dE_hat,
                        float* dC_hat_partial, float* dwdb_accum, void* workspace,
                        size_t workspace_bytes, ge2e_stream_t stream) {
@@ -118,6 +121,7 @@ int ge2e_b200_bwd_rows(const float* e_hat, const float* c_hat_all, const float* 
   if (rc != GE2E_OK) return rc;
   if ((rc = check_enum(variant, precision)) != GE2E_OK) return rc;
   if (variant == GE2E_CONTRAST && !row_kstar) return GE2E_ERR_ARGUMENT;
+  if (variant == GE2E_SOFTMAX && !row_aux) return GE2E_ERR_ARGUMENT;
   RowsArgs a{e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, b, eps, variant};
   // the contrast gradient is a 2-nonzeros-per-row gather/scatter: no contraction to put on
   // tensor cores, so both precisions share the SIMT kernel.
@@ -125,49 +129,50 @@ int ge2e_b200_bwd_rows(const float* e_hat, const float* c_hat_all, const float* 
     if (workspace_bytes < tc_workspace_bytes(n_local, n_total, M, D, variant) ||
         (workspace == nullptr && tc_workspace_bytes(n_local, n_total, M, D, variant) > 0))
       return GE2E_ERR_WORKSPACE;
-    return tc_bwd_rows(a, row_stat, row_kstar, grad_out, dE_hat, dC_hat_partial, dwdb_accum,
+    return tc_bwd_rows(a, row_stat, row_kstar, row_aux, grad_out, dE_hat, dC_hat_partial, dwdb_accum,
                        workspace, workspace_bytes, (cudaStream_t)stream);
   }
-  return simt_bwd_rows(a, row_stat, row_kstar, grad_out, dE_hat, dC_hat_partial, dwdb_accum,
+  return simt_bwd_rows(a, row_stat, row_kstar, row_aux, grad_out, dE_hat, dC_hat_partial, dwdb_accum,
                        (cudaStream_t)stream);
 }
 
 int ge2e_b200_bwd_finalize(const float* E, const float* dE_hat, const float* dC_hat_local,
-                           const float* cos_diag, const float* row_stat, int n_local, int M, int D,
-                           const float* w, const float* b, float eps, int variant,
-                           const float* grad_out, float* dE, ge2e_stream_t stream) {
+                           const float* cos_diag, const float* row_stat, const float* row_aux,
+                           int n_local, int M, int D, const float* w, const float* b, float eps,
+                           int variant, const float* grad_out, float* dE, ge2e_stream_t stream) {
   if (!E || !dE_hat || !dC_hat_local || !cos_diag || !row_stat || !w || !b || !grad_out || !dE)
     return GE2E_ERR_ARGUMENT;
+  if (variant == GE2E_SOFTMAX && !row_aux) return GE2E_ERR_ARGUMENT;
   int rc = check_shape(n_local, n_local, 0, M, D);
   if (rc != GE2E_OK) return rc;
   if ((rc = check_enum(variant, GE2E_FP32)) != GE2E_OK) return rc;
-  return simt_bwd_finalize(E, dE_hat, dC_hat_local, cos_diag, row_stat, n_local, M, D, w, b, eps,
+  return simt_bwd_finalize(E, dE_hat, dC_hat_local, cos_diag, row_stat, row_aux, n_local, M, D, w, b, eps,
                            variant, grad_out, dE, (cudaStream_t)stream);
 }
 
 int ge2e_b200_forward(const float* E, int N, int M, int D, const float* w, const float* b, float eps,
                       int variant, int precision, float* e_hat, float* c_hat, float* cos_diag,
-                      float* row_stat, int32_t* row_kstar, float* accum, void* workspace,
+                      float* row_stat, int32_t* row_kstar, float* row_aux, float* accum, void* workspace,
                       size_t workspace_bytes, ge2e_stream_t stream) {
   if (!accum) return GE2E_ERR_ARGUMENT;
   int rc = ge2e_b200_prep(E, N, M, D, precision, e_hat, c_hat, cos_diag, accum, stream);
   if (rc != GE2E_OK) return rc;
   return ge2e_b200_fwd_rows(e_hat, c_hat, cos_diag, N, N, 0, M, D, w, b, eps, variant, precision,
-                            row_stat, row_kstar, accum, nullptr, nullptr, workspace, workspace_bytes,
+                            row_stat, row_kstar, row_aux, accum, nullptr, nullptr, workspace, workspace_bytes,
                             stream);
 }
 
 int ge2e_b200_backward(const float* E, const float* e_hat, const float* c_hat, const float* cos_diag,
-                       const float* row_stat, const int32_t* row_kstar, int N, int M, int D,
-                       const float* w, const float* b, float eps, int variant, int precision,
+                       const float* row_stat, const int32_t* row_kstar, const float* row_aux, int N,
+                       int M, int D, const float* w, const float* b, float eps, int variant, int precision,
                        const float* grad_out, float* dE_hat, float* dC_hat, float* accum, float* dE,
                        void* workspace, size_t workspace_bytes, ge2e_stream_t stream) {
   if (!accum) return GE2E_ERR_ARGUMENT;
-  int rc = ge2e_b200_bwd_rows(e_hat, c_hat, cos_diag, row_stat, row_kstar, N, N, 0, M, D, w, b, eps,
+  int rc = ge2e_b200_bwd_rows(e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, N, N, 0, M, D, w, b, eps,
                               variant, precision, grad_out, dE_hat, dC_hat, accum + 1, workspace,
                               workspace_bytes, stream);
   if (rc != GE2E_OK) return rc;
-  return ge2e_b200_bwd_finalize(E, dE_hat, dC_hat, cos_diag, row_stat, N, M, D, w, b, eps, variant,
+  return ge2e_b200_bwd_finalize(E, dE_hat, dC_hat, cos_diag, row_stat, row_aux, N, M, D, w, b, eps, variant,
                                 grad_out, dE, stream);
 }
 

@@ -55,6 +55,27 @@ __device__ __forceinline__ float round_tf32(float x) {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
+// Closes one softmax row (reference s3:119-121) from the OFF-diagonal running state: mx >= Sd is
+// the running maximum over all logits incl. the diagonal one, loff = sum_{k != j} exp(S_k - mx).
+//   stat = log(sum_k exp S_k + eps)                      (s3:120)
+//   q    = 1 - p_j = (sum_{k != j} exp S_k + eps) / (sum_k exp S_k + eps)
+//   per  = stat - Sd = -log(1 - q)                        (s3:121), via log1p when q is small
+__device__ __forceinline__ void close_softmax_row(float mx, float loff, float Sd, float eps, float& stat,
+                                                  float& q, float& per) {
+  if (mx > -80.f) {
+    const float em = eps * expf(-mx);
+    const float Z = loff + expf(Sd - mx) + em;
+    stat = mx + logf(Z);
+    q = (loff + em) / Z;
+  } else {  // every logit below -80: eps dominates
+    const float s = expf(mx);
+    const float Z = eps + (loff + expf(Sd - mx)) * s;
+    stat = logf(Z);
+    q = (eps + loff * s) / Z;
+  }
+  per = (q < 0.5f) ? -log1pf(-q) : stat - Sd;
+}
+
 // Block-wide sum; result valid in thread 0.  `red` needs blockDim.x/32 floats.
 __device__ __forceinline__ float block_sum(float v, float* red) {
   v = warp_sum(v);
@@ -84,13 +105,14 @@ struct RowsArgs {
 
 int simt_prep(const float* E, int n_local, int M, int D, bool round_tf32, float* e_hat,
               float* c_hat_local, float* cos_diag, float* accum, cudaStream_t st);
-int simt_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* loss_accum,
-                  float* per_row_out, float* sim_out, cudaStream_t st);
+int simt_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* row_aux,
+                  float* loss_accum, float* per_row_out, float* sim_out, cudaStream_t st);
 int simt_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kstar,
-                  const float* grad_out, float* dE_hat, float* dC_hat_partial,
+                  const float* row_aux, const float* grad_out, float* dE_hat, float* dC_hat_partial,
                   float* dwdb_accum, cudaStream_t st);
 int simt_bwd_finalize(const float* E, const float* dE_hat, const float* dC_hat_local,
-                      const float* cos_diag, const float* row_stat, int n_local, int M, int D,
+                      const float* cos_diag, const float* row_stat, const float* row_aux,
+                      int n_local, int M, int D,
                       const float* w, const float* b, float eps, int variant,
                       const float* grad_out, float* dE, cudaStream_t st);
 int simt_centroids(const float* E, int N, int M, int D, float* C, cudaStream_t st);
@@ -102,10 +124,10 @@ int simt_normalize_rows(const float* X, int rows, int D, float* Y, cudaStream_t 
 // ---- launchers implemented in ge2e_tc.cu (tcgen05 / TMA / TMEM path) ----------------------
 bool tc_supported(int n_local, int n_total, int M, int D, int variant);
 size_t tc_workspace_bytes(int n_local, int n_total, int M, int D, int variant);
-int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* loss_accum,
-                float* per_row_out, void* ws, size_t ws_bytes, cudaStream_t st);
+int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* row_aux,
+                float* loss_accum, float* per_row_out, void* ws, size_t ws_bytes, cudaStream_t st);
 int tc_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kstar,
-                const float* grad_out, float* dE_hat, float* dC_hat_partial, float* dwdb_accum,
+                const float* row_aux, const float* grad_out, float* dE_hat, float* dC_hat_partial, float* dwdb_accum,
                 void* ws, size_t ws_bytes, cudaStream_t st);
 
 }  // namespace ge2e

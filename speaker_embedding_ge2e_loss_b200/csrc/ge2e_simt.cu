@@ -143,6 +143,8 @@ struct StripParams {
   int M, spk_offset;  // local utterance row r belongs to global speaker spk_offset + r / M
   const float* cos_diag;
   const float* row_stat;   // bwd: lse per local utterance row
+  const float* row_aux;    // bwd: q = 1 - p_jj per local utterance row
+  float* row_aux_out;      // fwd softmax
   const float* w;
   const float* b;
   const float* grad_out;
@@ -218,6 +220,7 @@ strip_kernel(const StripParams p) {
   int jg[R];        // FWD / BWD_DE: global speaker of the owner utterance row
   float cd[R];      // cos_diag of the owner row
   float lse[R];     // BWD_DE
+  float qd[R];      // BWD_DE: 1 - p_jj
   float m_run[R], l_run[R];   // FWD softmax (per lane, merged at the end)
   float best[R]; int bestk[R];  // FWD contrast
   float4 acc[R][KCH];
@@ -226,11 +229,11 @@ strip_kernel(const StripParams p) {
   for (int q = 0; q < R; ++q) {
     const int row = own0 + q;
     // rows past the end: lse = +inf makes every G of that row exactly 0
-    jg[q] = -1; cd[q] = 0.f; lse[q] = INFINITY;
+    jg[q] = -1; cd[q] = 0.f; lse[q] = INFINITY; qd[q] = 0.f;
     if (MODE != MODE_BWD_DC && row < p.n_own) {
       jg[q] = p.spk_offset + row / p.M;
       cd[q] = __ldg(p.cos_diag + row);
-      if (MODE == MODE_BWD_DE) lse[q] = __ldg(p.row_stat + row);
+      if (MODE == MODE_BWD_DE) { lse[q] = __ldg(p.row_stat + row); qd[q] = __ldg(p.row_aux + row); }
     }
     m_run[q] = -INFINITY; l_run[q] = 0.f; best[q] = -INFINITY; bestk[q] = INT_MAX;
 #pragma unroll
@@ -280,7 +283,7 @@ strip_kernel(const StripParams p) {
           if (p.sim_out != nullptr && valid && own0 + q < p.n_own)
             p.sim_out[(size_t)(own0 + q) * p.n_str + k] = cosv;
           if (VARIANT == GE2E_SOFTMAX) {
-            if (valid) {
+            if (valid && !diag) {   // off-diagonal running state; the diagonal joins in the epilogue
               const float mn = fmaxf(m_run[q], S);
               l_run[q] = l_run[q] * expf(m_run[q] - mn) + expf(S - mn);
               m_run[q] = mn;
@@ -290,7 +293,7 @@ strip_kernel(const StripParams p) {
           }
         } else {  // MODE_BWD_DE (softmax only)
           const float pr = valid ? expf(S - lse[q]) : 0.f;
-          const float G = g * (pr - (diag ? 1.f : 0.f));
+          const float G = g * (diag ? -qd[q] : pr);     // own speaker: p_jj - 1 = -q, no cancellation
           dw_acc = fmaf(G, cosv, dw_acc);
           gq[q] = (valid && !diag) ? w * G : 0.f;
         }
@@ -326,12 +329,11 @@ strip_kernel(const StripParams p) {
       const int row = own0 + q;
       const float Sd = fmaf(w, cd[q] + eps, b);
       float per, stat; int ks = -1;
+      float aux = 0.f;
       if (VARIANT == GE2E_SOFTMAX) {
-        const float mx = warp_max(m_run[q]);
-        const float lsum = warp_sum(l_run[q] == 0.f ? 0.f : l_run[q] * expf(m_run[q] - mx));
-        // log(sum_k exp S + eps), s3:120, evaluated without overflow
-        stat = (mx > -80.f) ? mx + logf(lsum + eps * expf(-mx)) : logf(eps + lsum * expf(mx));
-        per = stat - Sd;                                        // s3:121
+        const float mx = fmaxf(warp_max(m_run[q]), Sd);
+        const float loff = warp_sum(l_run[q] == 0.f ? 0.f : l_run[q] * expf(m_run[q] - mx));
+        close_softmax_row(mx, loff, Sd, eps, stat, aux, per);   // s3:120-121 without overflow
       } else {
         float bv = best[q]; int bk = bestk[q];
 #pragma unroll
@@ -347,6 +349,7 @@ strip_kernel(const StripParams p) {
       }
       if (lane == 0 && row < p.n_own) {
         p.row_stat_out[row] = stat;
+        if (p.row_aux_out != nullptr) p.row_aux_out[row] = aux;
         if (p.kstar_out != nullptr) p.kstar_out[row] = ks;
         if (p.per_row_out != nullptr) p.per_row_out[row] = per;
         loss_part += per;
@@ -440,7 +443,7 @@ contrast_bwd_kernel(const float* __restrict__ e_hat, const float* __restrict__ c
 __global__ void __launch_bounds__(kThreads)
 finalize_kernel(const float* __restrict__ E, const float* __restrict__ dE_hat,
                 const float* __restrict__ dC_hat, const float* __restrict__ cos_diag,
-                const float* __restrict__ row_stat, int M, int D, int Dp,
+                const float* __restrict__ row_stat, const float* __restrict__ row_aux, int M, int D, int Dp,
                 const float* __restrict__ wp, const float* __restrict__ bp, float eps, int variant,
                 const float* __restrict__ gp, float* __restrict__ dE) {
   extern __shared__ __align__(16) float smem[];
@@ -518,7 +521,7 @@ finalize_kernel(const float* __restrict__ E, const float* __restrict__ dE_hat,
     const float Sd = fmaf(w, __ldg(cos_diag + r) + eps, b);
     float Gd;
     if (variant == GE2E_SOFTMAX) {
-      Gd = g * (expf(Sd - __ldg(row_stat + r)) - 1.f);
+      Gd = -g * __ldg(row_aux + r);                 // g (p_jj - 1), accumulated off-diagonal in fwd
     } else {
       const float sp = 1.f / (1.f + expf(-Sd));
       Gd = -g * sp * (1.f - sp);
@@ -542,9 +545,9 @@ finalize_kernel(const float* __restrict__ E, const float* __restrict__ dE_hat,
         de[t] = ok_e ? (deh - eh * proj_e) * inv_ne : deh * inv_ne;
         du[t] = ok_u ? (duh - uh * proj_u) * inv_nu : duh * inv_nu;
       }
-      // each (i, d) slot is touched by exactly one lane: overwrite in place after reading
+      // each (i, d) slot is read and then overwritten by the same single lane: no cross-lane hazard
+      // (and no __syncwarp here: for D < 128 only some lanes enter this loop)
       *reinterpret_cast<float4*>(&sU[(size_t)i * Dp + d]) = make_float4(du[0], du[1], du[2], du[3]);
-      __syncwarp();
       *reinterpret_cast<float4*>(&sE[(size_t)i * Dp + d]) = make_float4(de[0], de[1], de[2], de[3]);
     }
   }
@@ -696,21 +699,21 @@ int simt_prep(const float* E, int n_local, int M, int D, bool round_tf32_, float
   return GE2E_OK;
 }
 
-int simt_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* loss_accum,
+int simt_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* row_aux, float* loss_accum,
                   float* per_row_out, float* sim_out, cudaStream_t st) {
   StripParams p{};
   p.own = a.e_hat; p.n_own = a.n_local * a.M;
   p.str = a.c_hat_all; p.n_str = a.n_total;
   p.D = a.D; p.M = a.M; p.spk_offset = a.spk_offset;
   p.cos_diag = a.cos_diag; p.w = a.w; p.b = a.b; p.eps = a.eps;
-  p.row_stat_out = row_stat; p.kstar_out = row_kstar; p.loss_accum = loss_accum;
+  p.row_stat_out = row_stat; p.kstar_out = row_kstar; p.row_aux_out = row_aux; p.loss_accum = loss_accum;
   p.per_row_out = per_row_out; p.sim_out = sim_out;
   p.chunks_per_split = INT_MAX / 2;
   if (a.variant == GE2E_SOFTMAX) return dispatch_strip<MODE_FWD, GE2E_SOFTMAX>(p, 1, st);
   return dispatch_strip<MODE_FWD, GE2E_CONTRAST>(p, 1, st);
 }
 
-int simt_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kstar,
+int simt_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kstar, const float* row_aux,
                   const float* grad_out, float* dE_hat, float* dC_hat_partial, float* dwdb_accum,
                   cudaStream_t st) {
   const int U = a.n_local * a.M;
@@ -731,7 +734,7 @@ int simt_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_k
   }
   StripParams p{};
   p.D = a.D; p.M = a.M; p.spk_offset = a.spk_offset;
-  p.cos_diag = a.cos_diag; p.row_stat = row_stat; p.w = a.w; p.b = a.b; p.grad_out = grad_out;
+  p.cos_diag = a.cos_diag; p.row_stat = row_stat; p.row_aux = row_aux; p.w = a.w; p.b = a.b; p.grad_out = grad_out;
   p.eps = a.eps;
   // dE_hat: owner = utterances, stream = centroids
   p.own = a.e_hat; p.n_own = U; p.str = a.c_hat_all; p.n_str = a.n_total;
@@ -751,15 +754,15 @@ int simt_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_k
 }
 
 int simt_bwd_finalize(const float* E, const float* dE_hat, const float* dC_hat_local,
-                      const float* cos_diag, const float* row_stat, int n_local, int M, int D,
-                      const float* w, const float* b, float eps, int variant,
+                      const float* cos_diag, const float* row_stat, const float* row_aux, int n_local, int M,
+                      int D, const float* w, const float* b, float eps, int variant,
                       const float* grad_out, float* dE, cudaStream_t st) {
   const int Dp = (D + 3) & ~3;
   const size_t smem = (size_t)(2 * M + 2) * Dp * sizeof(float);
   if (smem > 200 * 1024) return GE2E_ERR_UNSUPPORTED;
   int rc = set_smem(finalize_kernel, smem);
   if (rc != GE2E_OK) return rc;
-  finalize_kernel<<<n_local, kThreads, smem, st>>>(E, dE_hat, dC_hat_local, cos_diag, row_stat, M, D,
+  finalize_kernel<<<n_local, kThreads, smem, st>>>(E, dE_hat, dC_hat_local, cos_diag, row_stat, row_aux, M, D,
                                                    Dp, w, b, eps, variant, grad_out, dE);
   GE2E_LAUNCHED();
   return GE2E_OK;

@@ -70,6 +70,8 @@ struct TcParams {
   long long P;                // OT * ST pairs
   const float* cos_diag;      // [U_local]
   const float* row_stat;      // BWD: lse per local utterance row
+  const float* row_aux;       // BWD_DE: q = 1 - p_jj per local utterance row
+  float* row_aux_out;         // FWD softmax
   const float* w;
   const float* b;
   const float* grad_out;
@@ -93,7 +95,7 @@ struct SharedTail {
   uint32_t tmem_base;
   int flag;
   float red[8];
-  float lse_s[2][kTile];      // BWD_DC: lse (log2 domain) of the current stream rows
+  alignas(16) float lse_s[2][kTile];      // BWD_DC: lse (log2 domain) of the current stream rows
 };
 
 __device__ __forceinline__ int cta_of_pair(long long p, long long P, int G) {
@@ -275,19 +277,22 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
       const bool ovalid = orow < p.n_own;
       // per-owner-row metadata
       int jg = -1;            // FWD / DE: global speaker of this utterance row
-      float cd = 0.f, lse2 = INFINITY;
+      float cd = 0.f, lse2 = INFINITY, qd = 0.f;
       int dlo = 0, dhi = 0;   // DC: local utterance rows [dlo, dhi) belong to this centroid
       if (MODE != TC_BWD_DC) {
         if (ovalid) {
           jg = p.spk_offset + orow / p.M;
           cd = __ldg(p.cos_diag + orow);
-          if (MODE == TC_BWD_DE) lse2 = __ldg(p.row_stat + orow) * kLog2e;
+          if (MODE == TC_BWD_DE) { lse2 = __ldg(p.row_stat + orow) * kLog2e; qd = __ldg(p.row_aux + orow); }
         }
       } else {
         const int jl = orow - p.spk_offset;
         if (ovalid && jl >= 0 && (long long)jl * p.M < p.n_str) { dlo = jl * p.M; dhi = dlo + p.M; }
       }
-      float m2 = -INFINITY, lsum = 0.f;      // FWD softmax running state (log2 domain)
+      // FWD softmax running state, log2 domain, OFF-diagonal columns only: the running max starts at
+      // the diagonal logit (known from cos_diag) and the diagonal term joins when the row is closed
+      const float xd2 = fmaf(cd, w2, b2);
+      float m2 = xd2, lsum = 0.f;
       float best = -INFINITY; int bestk = INT_MAX;   // FWD contrast
 
       for (int st = s0; st < s1; ++st, ++it) {
@@ -316,12 +321,9 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
 #pragma unroll
                 for (int i = 0; i < 32; ++i) x[i] = fmaf(__uint_as_float(v[i]), w2, b2);
                 if (__any_sync(0xffffffffu, tailc || diagc)) {
-                  const float xd = fmaf(cd, w2, b2);
 #pragma unroll
-                  for (int i = 0; i < 32; ++i) {
-                    if (c0 + i == jg) x[i] = xd;                 // leave-one-out diagonal (s3:78)
-                    if (c0 + i >= p.n_str) x[i] = -INFINITY;
-                  }
+                  for (int i = 0; i < 32; ++i)   // own-speaker column (s3:78) and padding leave the sum
+                    if (c0 + i == jg || c0 + i >= p.n_str) x[i] = -INFINITY;
                 }
                 float cm = x[0];
 #pragma unroll
@@ -354,9 +356,9 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
                 if (any_special) {
                   if (c0 + i >= p.n_str) pr = 0.f;
                   if (c0 + i == jg) {
-                    // diagonal: uses cos_diag, contributes to dw but not to the contraction
-                    const float pd = ex2(fmaf(cd, w2, b2) - lse2);
-                    dw_acc = fmaf(pd - 1.f, cd + eps, dw_acc);
+                    // diagonal: p_jj - 1 = -q (saved by the forward), uses cos_diag, contributes to
+                    // dw but not to the contraction
+                    dw_acc = fmaf(-qd, cd + eps, dw_acc);
                     pr = 0.f;
                   }
                 }
@@ -419,7 +421,7 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
             __threadfence();
             const int last_cta = cta_of_pair(static_cast<long long>(ot) * p.ST + p.ST - 1, p.P, G);
             const int nseg = last_cta - first_cta + 1;
-            m2 = -INFINITY; lsum = 0.f; best = -INFINITY; bestk = INT_MAX;
+            m2 = xd2; lsum = 0.f; best = -INFINITY; bestk = INT_MAX;
             for (int sgi = 0; sgi < nseg; ++sgi) {
               const float2 q = __ldcg(&p.seg_part[(static_cast<size_t>(ot) * p.maxseg + sgi) * kTile + trow]);
               if (VARIANT == GE2E_SOFTMAX) {
@@ -435,18 +437,17 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
         }
         if (last && ovalid) {
           const float Sd = fmaf(w, cd + eps, b);
-          float per, stat;
+          float per, stat, aux = 0.f;
           int ks = -1;
           if (VARIANT == GE2E_SOFTMAX) {
-            const float mx = m2 * kLn2;                         // natural-log running max
-            stat = (mx > -80.f) ? mx + logf(lsum + eps * expf(-mx)) : logf(eps + lsum * expf(mx));   // s3:120
-            per = stat - Sd;                                    // s3:121
+            close_softmax_row(m2 * kLn2, lsum, Sd, eps, stat, aux, per);   // s3:120-121
           } else {
             per = 1.f - 1.f / (1.f + expf(-Sd));
             stat = best;
             if (bestk != INT_MAX) { ks = bestk; per += 1.f / (1.f + expf(-best)); }
           }
           p.row_stat_out[orow] = stat;
+          if (p.row_aux_out != nullptr) p.row_aux_out[orow] = aux;
           if (p.kstar_out != nullptr) p.kstar_out[orow] = ks;
           if (p.per_row_out != nullptr) p.per_row_out[orow] = per;
           loss_acc += per;
@@ -608,8 +609,8 @@ size_t tc_workspace_bytes(int n_local, int n_total, int M, int D, int variant) {
   return L.done_bytes + L.part_bytes;
 }
 
-int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* loss_accum, float* per_row_out,
-                void* ws, size_t ws_bytes, cudaStream_t st) {
+int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* row_aux, float* loss_accum,
+                float* per_row_out, void* ws, size_t ws_bytes, cudaStream_t st) {
   const FwdLayout L = fwd_layout(a.n_local, a.n_total, a.M);
   if (ws_bytes < L.done_bytes + L.part_bytes) return GE2E_ERR_WORKSPACE;
   const int U = a.n_local * a.M;
@@ -622,7 +623,8 @@ int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* l
   p.M = a.M; p.spk_offset = a.spk_offset;
   p.OT = L.OT; p.ST = L.ST; p.P = static_cast<long long>(L.OT) * L.ST;
   p.cos_diag = a.cos_diag; p.w = a.w; p.b = a.b; p.eps = a.eps;
-  p.row_stat_out = row_stat; p.kstar_out = row_kstar; p.loss_accum = loss_accum; p.per_row_out = per_row_out;
+  p.row_stat_out = row_stat; p.kstar_out = row_kstar; p.row_aux_out = row_aux; p.loss_accum = loss_accum;
+  p.per_row_out = per_row_out;
   p.seg_done = static_cast<int*>(ws);
   p.seg_part = reinterpret_cast<float2*>(static_cast<uint8_t*>(ws) + L.done_bytes);
   p.maxseg = L.maxseg;
@@ -631,7 +633,8 @@ int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* l
   return launch_tc<TC_FWD, GE2E_CONTRAST>(tmE, tmC, tmC, p, L.G, st);
 }
 
-int tc_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kstar, const float* grad_out,
+int tc_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kstar, const float* row_aux,
+                const float* grad_out,
                 float* dE_hat, float* dC_hat_partial, float* dwdb_accum, void* ws, size_t ws_bytes,
                 cudaStream_t st) {
   (void)row_kstar; (void)ws; (void)ws_bytes;
@@ -653,7 +656,8 @@ int tc_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kst
 
   TcParams p{};
   p.D = a.D; p.kslabs = a.D / kSlabCols; p.M = a.M; p.spk_offset = a.spk_offset;
-  p.cos_diag = a.cos_diag; p.row_stat = row_stat; p.w = a.w; p.b = a.b; p.grad_out = grad_out; p.eps = a.eps;
+  p.cos_diag = a.cos_diag; p.row_stat = row_stat; p.row_aux = row_aux; p.w = a.w; p.b = a.b;
+  p.grad_out = grad_out; p.eps = a.eps;
 
   // dE_hat = (wG) C_hat: owner = utterance tiles, each CTA runs one whole owner tile (plain stores)
   p.n_own = U; p.n_str = a.n_total; p.OT = UT; p.ST = CT; p.P = static_cast<long long>(UT) * CT;

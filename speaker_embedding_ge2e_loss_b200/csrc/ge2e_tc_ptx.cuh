@@ -25,10 +25,16 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 // Spin on try_wait (hardware-suspended).  A wait that never completes is a programming error in
-// the pipeline: trap after ~seconds instead of hanging the GPU.
+// the pipeline: trap after 2 s of wall time instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
+  uint64_t t0 = 0;
   for (uint32_t spins = 0; !done; ++spins) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -37,7 +43,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
-    if (spins > (1u << 24)) __trap();
+    if (!done && (spins & 255u) == 255u) {
+      const uint64_t t = globaltimer_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 2000000000ull) __trap();
+    }
   }
 }
 

@@ -46,9 +46,9 @@ def _workspace(n_local: int, n_total: int, M: int, D: int, variant: int, precisi
 # --------------------------------------------------------------------------- single device
 @torch.library.custom_op("ge2e_b200::fwd", mutates_args=())
 def ge2e_fwd(E: Tensor, w: Tensor, b: Tensor, eps: float, variant: int,
-             precision: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+             precision: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     """GE2ELoss.forward (reference s3:19-30).  Returns (loss, e_hat, c_hat, cos_diag, row_stat,
-    row_kstar); everything after loss is saved for the backward."""
+    row_kstar, row_aux); everything after loss is saved for the backward."""
     _need_cuda(E, w, b)
     E, w, b = _f32c(E), _f32c(w), _f32c(b)
     N, M, D = E.shape
@@ -61,13 +61,14 @@ def ge2e_fwd(E: Tensor, w: Tensor, b: Tensor, eps: float, variant: int,
         cos_diag = torch.empty(U, dtype=torch.float32, device=dev)
         row_stat = torch.empty(U, dtype=torch.float32, device=dev)
         row_kstar = torch.empty(U if variant == _lib.CONTRAST else 1, dtype=torch.int32, device=dev)
+        row_aux = torch.empty(U, dtype=torch.float32, device=dev)
         ws, ws_bytes = _workspace(N, N, M, D, variant, precision, dev)
         rc = lib().ge2e_b200_forward(E.data_ptr(), N, M, D, w.data_ptr(), b.data_ptr(), eps, variant,
                                      precision, e_hat.data_ptr(), c_hat.data_ptr(), cos_diag.data_ptr(),
-                                     row_stat.data_ptr(), row_kstar.data_ptr(), accum.data_ptr(),
-                                     _ptr(ws), ws_bytes, _stream())
+                                     row_stat.data_ptr(), row_kstar.data_ptr(), row_aux.data_ptr(),
+                                     accum.data_ptr(), _ptr(ws), ws_bytes, _stream())
     check(rc, "ge2e_b200_forward")
-    return accum[0], e_hat, c_hat, cos_diag, row_stat, row_kstar
+    return accum[0], e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux
 
 
 @ge2e_fwd.register_fake
@@ -75,12 +76,12 @@ def _(E, w, b, eps, variant, precision):
     N, M, D = E.shape
     U = N * M
     return (E.new_empty(()), E.new_empty((U, D)), E.new_empty((N, D)), E.new_empty(U), E.new_empty(U),
-            E.new_empty(U if variant == _lib.CONTRAST else 1, dtype=torch.int32))
+            E.new_empty(U if variant == _lib.CONTRAST else 1, dtype=torch.int32), E.new_empty(U))
 
 
 @torch.library.custom_op("ge2e_b200::bwd", mutates_args=())
 def ge2e_bwd(grad_out: Tensor, E: Tensor, w: Tensor, b: Tensor, e_hat: Tensor, c_hat: Tensor,
-             cos_diag: Tensor, row_stat: Tensor, row_kstar: Tensor, eps: float, variant: int,
+             cos_diag: Tensor, row_stat: Tensor, row_kstar: Tensor, row_aux: Tensor, eps: float, variant: int,
              precision: int) -> Tuple[Tensor, Tensor]:
     """Backward of ge2e_b200::fwd.  Returns (dE[N,M,D], dwdb[2])."""
     _need_cuda(grad_out, E, w, b)
@@ -98,8 +99,8 @@ def ge2e_bwd(grad_out: Tensor, E: Tensor, w: Tensor, b: Tensor, e_hat: Tensor, c
         ws, ws_bytes = _workspace(N, N, M, D, variant, precision, dev)
         accum_ptr = scratch.data_ptr() + (N * D - 1) * 4
         rc = lib().ge2e_b200_backward(E.data_ptr(), e_hat.data_ptr(), c_hat.data_ptr(), cos_diag.data_ptr(),
-                                      row_stat.data_ptr(), row_kstar.data_ptr(), N, M, D, w.data_ptr(),
-                                      b.data_ptr(), eps, variant, precision, g.data_ptr(),
+                                      row_stat.data_ptr(), row_kstar.data_ptr(), row_aux.data_ptr(), N, M, D,
+                                      w.data_ptr(), b.data_ptr(), eps, variant, precision, g.data_ptr(),
                                       dE_hat.data_ptr(), scratch.data_ptr(), accum_ptr, dE.data_ptr(),
                                       _ptr(ws), ws_bytes, _stream())
     check(rc, "ge2e_b200_backward")
@@ -107,21 +108,21 @@ def ge2e_bwd(grad_out: Tensor, E: Tensor, w: Tensor, b: Tensor, e_hat: Tensor, c
 
 
 @ge2e_bwd.register_fake
-def _(grad_out, E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, eps, variant, precision):
+def _(grad_out, E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, eps, variant, precision):
     return torch.empty_like(E), E.new_empty(2)
 
 
 def _fwd_setup(ctx, inputs, output):
     E, w, b, eps, variant, precision = inputs
-    _, e_hat, c_hat, cos_diag, row_stat, row_kstar = output
-    ctx.save_for_backward(E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar)
+    _, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux = output
+    ctx.save_for_backward(E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux)
     ctx.cfg = (eps, variant, precision)
 
 
 def _fwd_backward(ctx, g_loss, *_unused):
-    E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar = ctx.saved_tensors
+    E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux = ctx.saved_tensors
     eps, variant, precision = ctx.cfg
-    dE, dwdb = ge2e_bwd(g_loss, E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, eps, variant,
+    dE, dwdb = ge2e_bwd(g_loss, E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, eps, variant,
                         precision)
     return dE, dwdb[0], dwdb[1], None, None, None
 
@@ -162,20 +163,21 @@ def fwd_rows(e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, 
     U = n_local * M
     row_stat = torch.empty(U, dtype=torch.float32, device=dev)
     row_kstar = torch.empty(U if variant == _lib.CONTRAST else 1, dtype=torch.int32, device=dev)
+    row_aux = torch.empty(U, dtype=torch.float32, device=dev)
     per = torch.empty(U, dtype=torch.float32, device=dev) if per_row else None
     sim_out = torch.empty((U, n_total), dtype=torch.float32, device=dev) if sim else None
     with torch.cuda.device(dev):
         ws, ws_bytes = _workspace(n_local, n_total, M, D, variant, precision, dev)
         rc = lib().ge2e_b200_fwd_rows(e_hat.data_ptr(), c_hat_all.data_ptr(), cos_diag.data_ptr(), n_local,
                                       n_total, spk_offset, M, D, w.data_ptr(), b.data_ptr(), eps, variant,
-                                      precision, row_stat.data_ptr(), row_kstar.data_ptr(), accum.data_ptr(),
-                                      _ptr(per), _ptr(sim_out), _ptr(ws), ws_bytes, _stream())
+                                      precision, row_stat.data_ptr(), row_kstar.data_ptr(), row_aux.data_ptr(),
+                                      accum.data_ptr(), _ptr(per), _ptr(sim_out), _ptr(ws), ws_bytes, _stream())
     check(rc, "ge2e_b200_fwd_rows")
-    return row_stat, row_kstar, per, sim_out
+    return row_stat, row_kstar, row_aux, per, sim_out
 
 
-def bwd_rows(e_hat, c_hat_all, cos_diag, row_stat, row_kstar, n_local, n_total, spk_offset, M, D, w, b, eps,
-             variant, precision, grad_out):
+def bwd_rows(e_hat, c_hat_all, cos_diag, row_stat, row_kstar, row_aux, n_local, n_total, spk_offset, M, D, w, b,
+             eps, variant, precision, grad_out):
     """Returns (dE_hat[U_local, D], dC_hat_partial[n_total, D], dwdb[2])."""
     dev = e_hat.device
     dE_hat = torch.empty((n_local * M, D), dtype=torch.float32, device=dev)
@@ -183,20 +185,21 @@ def bwd_rows(e_hat, c_hat_all, cos_diag, row_stat, row_kstar, n_local, n_total, 
     with torch.cuda.device(dev):
         ws, ws_bytes = _workspace(n_local, n_total, M, D, variant, precision, dev)
         rc = lib().ge2e_b200_bwd_rows(e_hat.data_ptr(), c_hat_all.data_ptr(), cos_diag.data_ptr(),
-                                      row_stat.data_ptr(), row_kstar.data_ptr(), n_local, n_total, spk_offset,
-                                      M, D, w.data_ptr(), b.data_ptr(), eps, variant, precision,
+                                      row_stat.data_ptr(), row_kstar.data_ptr(), row_aux.data_ptr(), n_local,
+                                      n_total, spk_offset, M, D, w.data_ptr(), b.data_ptr(), eps, variant, precision,
                                       grad_out.data_ptr(), dE_hat.data_ptr(), scratch.data_ptr(),
                                       scratch.data_ptr() + n_total * D * 4, _ptr(ws), ws_bytes, _stream())
     check(rc, "ge2e_b200_bwd_rows")
     return dE_hat, scratch[:n_total * D].view(n_total, D), scratch[n_total * D:]
 
 
-def bwd_finalize(E, dE_hat, dC_hat_local, cos_diag, row_stat, w, b, eps, variant, grad_out):
+def bwd_finalize(E, dE_hat, dC_hat_local, cos_diag, row_stat, row_aux, w, b, eps, variant, grad_out):
     n, M, D = E.shape
     dE = torch.empty_like(E)
     with torch.cuda.device(E.device):
         rc = lib().ge2e_b200_bwd_finalize(E.data_ptr(), dE_hat.data_ptr(), dC_hat_local.data_ptr(),
-                                          cos_diag.data_ptr(), row_stat.data_ptr(), n, M, D, w.data_ptr(),
+                                          cos_diag.data_ptr(), row_stat.data_ptr(), row_aux.data_ptr(), n, M, D,
+                                          w.data_ptr(),
                                           b.data_ptr(), eps, variant, grad_out.data_ptr(), dE.data_ptr(),
                                           _stream())
     check(rc, "ge2e_b200_bwd_finalize")

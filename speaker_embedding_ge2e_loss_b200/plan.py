@@ -33,6 +33,7 @@ class GE2EPlan:
         self.cos_diag = torch.empty(U, dtype=f32, device=dev)
         self.row_stat = torch.empty(U, dtype=f32, device=dev)
         self.row_kstar = torch.empty(U, dtype=torch.int32, device=dev)
+        self.row_aux = torch.empty(U, dtype=f32, device=dev)
         self.dE_hat = torch.empty((U, D), dtype=f32, device=dev)
         # [dC_hat (N*D) | dw | db] so that the library zeroes all of it with one memset
         self._scratch = torch.empty(N * D + 2, dtype=f32, device=dev)
@@ -56,14 +57,14 @@ class GE2EPlan:
         rc = h.ge2e_b200_forward(E.data_ptr(), N, M, D, w.data_ptr(), b.data_ptr(), self.eps, self.variant,
                                  self.precision, self.e_hat.data_ptr(), self.c_hat.data_ptr(),
                                  self.cos_diag.data_ptr(), self.row_stat.data_ptr(), self.row_kstar.data_ptr(),
-                                 self._accum.data_ptr(), ws, self._ws_bytes, stream)
+                                 self.row_aux.data_ptr(), self._accum.data_ptr(), ws, self._ws_bytes, stream)
         check(rc, "ge2e_b200_forward")
         if not backward:
             return
         accum_ptr = self._scratch.data_ptr() + (N * D - 1) * 4   # accum[1] = dw, accum[2] = db
         rc = h.ge2e_b200_backward(E.data_ptr(), self.e_hat.data_ptr(), self.c_hat.data_ptr(),
                                   self.cos_diag.data_ptr(), self.row_stat.data_ptr(), self.row_kstar.data_ptr(),
-                                  N, M, D, w.data_ptr(), b.data_ptr(), self.eps, self.variant, self.precision,
+                                  self.row_aux.data_ptr(), N, M, D, w.data_ptr(), b.data_ptr(), self.eps, self.variant, self.precision,
                                   self.grad_out.data_ptr(), self.dE_hat.data_ptr(), self._scratch.data_ptr(),
                                   accum_ptr, self.dE.data_ptr(), ws, self._ws_bytes, stream)
         check(rc, "ge2e_b200_backward")

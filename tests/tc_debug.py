@@ -48,22 +48,25 @@ def main():
     out = {}
     for tag, prec in (("simt", _lib.FP32), ("tc", _lib.TF32)):
         accum.zero_()
-        rs, ks, per, _ = ops.fwd_rows(e_hat, c_hat, cos_diag, N, N, 0, M, D, w, b, eps, variant, prec, accum,
-                                      per_row=True)
+        rs, ks, aux, per, _ = ops.fwd_rows(e_hat, c_hat, cos_diag, N, N, 0, M, D, w, b, eps, variant, prec, accum,
+                                           per_row=True)
         torch.cuda.synchronize()
-        out[tag] = dict(rs=rs.clone(), per=per.clone(), loss=accum[0].item(), ks=ks.clone())
+        out[tag] = dict(rs=rs.clone(), per=per.clone(), loss=accum[0].item(), ks=ks.clone(), aux=aux.clone())
+        print(f"  [{tag}] nan counts: row_stat={torch.isnan(rs).sum().item()} per={torch.isnan(per).sum().item()} "
+              f"aux={torch.isnan(aux).sum().item()}")
     print("forward:")
     print(f"  loss simt={out['simt']['loss']:.6f} tc={out['tc']['loss']:.6f}")
     summarize("row_stat", out["tc"]["rs"], out["simt"]["rs"])
     summarize("per_row", out["tc"]["per"], out["simt"]["per"])
+    summarize("row_aux", out["tc"]["aux"], out["simt"]["aux"])
     if variant == _lib.CONTRAST:
         print("  kstar mismatches:", (out["tc"]["ks"] != out["simt"]["ks"]).sum().item())
         return
     rs = out["simt"]["rs"]
     bw = {}
     for tag, prec in (("simt", _lib.FP32), ("tc", _lib.TF32)):
-        dE_hat, dC, dwdb = ops.bwd_rows(e_hat, c_hat, cos_diag, rs, out["simt"]["ks"], N, N, 0, M, D, w, b, eps,
-                                        variant, prec, g)
+        dE_hat, dC, dwdb = ops.bwd_rows(e_hat, c_hat, cos_diag, rs, out["simt"]["ks"], out["simt"]["aux"], N, N, 0,
+                                        M, D, w, b, eps, variant, prec, g)
         torch.cuda.synchronize()
         bw[tag] = (dE_hat.clone(), dC.clone(), dwdb.clone())
     print("backward:")

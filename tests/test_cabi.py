@@ -56,11 +56,11 @@ def test_host_side_status_codes(pkg):
     for code in range(-6, 0):
         assert h.ge2e_b200_strerror(code) not in (b"ok", b"unknown ge2e status")
     # argument checking happens before any CUDA call: safe without a GPU
-    assert h.ge2e_b200_forward(None, 4, 8, 256, None, None, 1e-6, 0, 0, None, None, None, None, None, None,
+    assert h.ge2e_b200_forward(None, 4, 8, 256, None, None, 1e-6, 0, 0, None, None, None, None, None, None, None,
                                None, 0, None) == -3
     assert h.ge2e_b200_prep(1, 4, 1, 256, 0, 1, 1, 1, 1, None) == -1          # M < 2
     assert h.ge2e_b200_prep(1, 4, 8, 256, 7, 1, 1, 1, 1, None) == -3          # unknown precision
-    assert h.ge2e_b200_fwd_rows(1, 1, 1, 4, 2, 0, 8, 256, 1, 1, 1e-6, 0, 0, 1, None, 1, None, None, None, 0,
+    assert h.ge2e_b200_fwd_rows(1, 1, 1, 4, 2, 0, 8, 256, 1, 1, 1e-6, 0, 0, 1, None, 1, 1, None, None, None, 0,
                                 None) == -1                                    # shard outside [0, n_total)
     assert h.ge2e_b200_calc_loss(1, 4, 8, 1e-6, 9, 1, None, None) == -3
     assert h.ge2e_b200_path(64, 64, 10, 256, 0, 0) == 0                        # fp32 -> SIMT kernels

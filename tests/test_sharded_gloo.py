@@ -51,9 +51,12 @@ class TorchStages:
     def fwd_rows(e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, b, eps, variant, precision,
                  accum, per_row=False, sim=False):
         S, _, rows, spk = TorchStages._S(e_hat, c_hat_all, cos_diag, n_local, spk_offset, M, w, b, eps)
+        aux = torch.zeros_like(cos_diag)
         if variant == 0:
-            stat = torch.log(torch.exp(S).sum(1) + eps)
+            Z = torch.exp(S).sum(1) + eps
+            stat = torch.log(Z)
             per = stat - S[rows, spk]
+            aux = (Z - torch.exp(S[rows, spk])) / Z          # q = 1 - p_jj
             kstar = torch.zeros(1, dtype=torch.int32)
         else:
             Sm = S.clone()
@@ -61,15 +64,15 @@ class TorchStages:
             stat, kstar = Sm.max(dim=1)
             per = 1 - torch.sigmoid(S[rows, spk]) + torch.sigmoid(stat)
         accum[0] += per.sum()
-        return stat, kstar, per, None
+        return stat, kstar, aux, per, None
 
     @staticmethod
-    def bwd_rows(e_hat, c_hat_all, cos_diag, row_stat, row_kstar, n_local, n_total, spk_offset, M, D, w, b, eps,
-                 variant, precision, grad_out):
+    def bwd_rows(e_hat, c_hat_all, cos_diag, row_stat, row_kstar, row_aux, n_local, n_total, spk_offset, M, D, w,
+                 b, eps, variant, precision, grad_out):
         S, cos, rows, spk = TorchStages._S(e_hat, c_hat_all, cos_diag, n_local, spk_offset, M, w, b, eps)
         if variant == 0:
             G = torch.exp(S - row_stat[:, None])
-            G[rows, spk] -= 1
+            G[rows, spk] = -row_aux
         else:
             G = torch.zeros_like(S)
             sp = torch.sigmoid(S[rows, spk])
@@ -83,7 +86,7 @@ class TorchStages:
         return Goff @ c_hat_all, Goff.T @ e_hat, dwdb
 
     @staticmethod
-    def bwd_finalize(E, dE_hat, dC_hat_local, cos_diag, row_stat, w, b, eps, variant, grad_out):
+    def bwd_finalize(E, dE_hat, dC_hat_local, cos_diag, row_stat, row_aux, w, b, eps, variant, grad_out):
         n, M, D = E.shape
         Ef = E.reshape(n * M, D)
         s = E.sum(dim=1, keepdim=True)
@@ -93,7 +96,7 @@ class TorchStages:
         ch, nc = TorchStages._unit(s[:, 0] / M)
         Sd = w * (cos_diag + eps) + b
         if variant == 0:
-            Gd = grad_out * (torch.exp(Sd - row_stat) - 1)
+            Gd = -grad_out * row_aux
         else:
             sp = torch.sigmoid(Sd)
             Gd = -grad_out * sp * (1 - sp)
