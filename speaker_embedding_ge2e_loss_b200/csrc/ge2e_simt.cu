@@ -350,7 +350,7 @@ strip_kernel(const StripParams p) {
       if (lane == 0 && row < p.n_own) {
         p.row_stat_out[row] = stat;
         if (p.row_aux_out != nullptr) p.row_aux_out[row] = aux;
-        if (p.kstar_out != nullptr) p.kstar_out[row] = ks;
+        if (VARIANT == GE2E_CONTRAST && p.kstar_out != nullptr) p.kstar_out[row] = ks;   // softmax: buffer may be a dummy
         if (p.per_row_out != nullptr) p.per_row_out[row] = per;
         loss_part += per;
       }

@@ -224,7 +224,10 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
           tc_fence_after();
 #pragma unroll
           for (int k2 = 0; k2 < kMma2Rows / 8; ++k2) {
-            const uint64_t db = smem_desc_sw128(ring_smem + stage * kStageBytes + k2 * 1024, kMma2Rows * 128, 1024);
+            // MN-major TF32 operand: 32-byte-atom 128B swizzle, chunks of 32 columns kMma2Rows*128 B
+            // apart (LBO), groups of 4 k-rows 512 B apart (SBO); one MMA consumes 8 k-rows = 1024 B
+            const uint64_t db = smem_desc(ring_smem + stage * kStageBytes + k2 * 1024, kMma2Rows * 128, 512,
+                                          kLayoutSw128Base32);
             umma_tf32_ts(d_tmem, a_tmem + kc * kMma2Rows + k2 * 8, db, idesc2, !(first && kc == 0 && k2 == 0));
           }
           umma_commit(bar(BAR_EMPTY + stage));
@@ -448,7 +451,7 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
           }
           p.row_stat_out[orow] = stat;
           if (p.row_aux_out != nullptr) p.row_aux_out[orow] = aux;
-          if (p.kstar_out != nullptr) p.kstar_out[orow] = ks;
+          if (VARIANT == GE2E_CONTRAST && p.kstar_out != nullptr) p.kstar_out[orow] = ks;
           if (p.per_row_out != nullptr) p.per_row_out[orow] = per;
           loss_acc += per;
         }
@@ -534,7 +537,8 @@ int make_map_2d(CUtensorMap* m, const float* base, int rows, int D) {
 }
 
 // 3-D map over the same X viewed as [D/32][rows][32]: box = [D/32][16 rows][32 cols]
-// (MN-major operand chunks for MMA2: 16 k-rows x all D columns per ring stage).
+// (MN-major operand chunks for MMA2: 16 k-rows x all D columns per ring stage).  32-bit MN-major
+// operands must use the 32-byte-atom flavour of the 128B swizzle (UMMA SWIZZLE_128B_BASE32B).
 int make_map_3d(CUtensorMap* m, const float* base, int rows, int D) {
   auto enc = get_encode();
   if (enc == nullptr) return GE2E_ERR_LAUNCH;
@@ -543,7 +547,7 @@ int make_map_3d(CUtensorMap* m, const float* base, int rows, int D) {
   cuuint32_t box[3] = {kSlabCols, kMma2Rows, static_cast<cuuint32_t>(D / kSlabCols)};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? GE2E_OK : GE2E_ERR_LAUNCH;
 }

@@ -83,17 +83,26 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // ---------------------------------------------------------------- tcgen05: MMA
-// Shared-memory matrix descriptor, 128-byte swizzle (rows of 128 B, 8-row atoms of 1024 B).
-//   K-major  operand [rows][32 tf32]: SBO = 1024 (next 8 rows); LBO unused.
-//   MN-major operand [k][32 tf32]   : LBO = stride between 32-element MN chunks, SBO = next 8 k.
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// Shared-memory matrix descriptors (version 1 = Blackwell).
+//   K-major operand  [rows][32 tf32], SWIZZLE_128B (16-byte chunks XOR row, 8-row atoms of 1024 B):
+//       SBO = 1024 (next 8 rows), LBO unused.  TMA: CU_TENSOR_MAP_SWIZZLE_128B.
+//   MN-major TF32 operand [k][32 tf32], SWIZZLE_128B_BASE32B -- the only MN-major layout the
+//   hardware accepts for 32-bit operands (32-byte chunks XOR row, 4-row atoms of 512 B):
+//       LBO = stride between 32-element MN chunks, SBO = 512 (next 4 k-rows).
+//       TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1;
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((addr & 0x3FFFFu) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= 1ull << 46;   // descriptor version (Blackwell)
-  d |= 2ull << 61;   // SWIZZLE_128B
+  d |= static_cast<uint64_t>(layout_type) << 61;
   return d;
+}
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return smem_desc(addr, lbo_bytes, sbo_bytes, kLayoutSw128);
 }
 // Instruction descriptor for kind::tf32, fp32 accumulate.
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
