@@ -52,6 +52,8 @@ int ge2e_b200_last_cuda_error(void) { return (int)g_last_cuda_error; }
 
 unsigned long long ge2e_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+void ge2e_b200_debug_trace(unsigned long long* device_buf, int kernel) { tc_set_trace(device_buf, kernel); }
+
 int ge2e_b200_path(int n_local, int n_total, int M, int D, int variant, int precision) {
   if (check_enum(variant, precision) != GE2E_OK) return GE2E_ERR_ARGUMENT;
   return (precision == GE2E_TF32 && tc_supported(n_local, n_total, M, D, variant)) ? 1 : 0;

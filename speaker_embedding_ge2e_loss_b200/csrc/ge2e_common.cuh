@@ -123,6 +123,7 @@ int simt_normalize_rows(const float* X, int rows, int D, float* Y, cudaStream_t 
 
 // ---- launchers implemented in ge2e_tc.cu (tcgen05 / TMA / TMEM path) ----------------------
 bool tc_supported(int n_local, int n_total, int M, int D, int variant);
+void tc_set_trace(unsigned long long* device_buf, int mode);
 size_t tc_workspace_bytes(int n_local, int n_total, int M, int D, int variant);
 int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* row_aux,
                 float* loss_accum, float* per_row_out, void* ws, size_t ws_bytes, cudaStream_t st);

@@ -88,6 +88,18 @@ struct TcParams {
   float* acc_out;             // dE_hat [n_own, D] or dC_hat_partial [n_own, D]
   float* dwdb;                // BWD_DE
   int acc_atomic;             // 1: output was zeroed, always accumulate with atomics
+  unsigned long long* trace;  // debug: [CTA][3 roles][kTraceEvents] globaltimer stamps, or nullptr
+};
+
+constexpr int kTraceEvents = 64;
+struct Tracer {
+  unsigned long long* buf;
+  int n;
+  __device__ __forceinline__ Tracer(unsigned long long* base, int role)
+      : buf(base ? base + (static_cast<size_t>(blockIdx.x) * 3 + role) * kTraceEvents : nullptr), n(0) {}
+  __device__ __forceinline__ void mark() {
+    if (buf != nullptr && n < kTraceEvents) buf[n++] = globaltimer_ns();
+  }
 };
 
 struct SharedTail {
@@ -155,6 +167,8 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (lane == 0) {
+      Tracer tr(p.trace, 0);
+      tr.mark();
       int stage = 0, phase = 0, sg = 0;
       auto load_mma1 = [&](int st) {
         for (int ks = 0; ks < kslabs; ++ks) {
@@ -177,6 +191,7 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
         const int ot = static_cast<int>(pp / p.ST), s0 = static_cast<int>(pp % p.ST);
         const int s1 = static_cast<int>(min(static_cast<long long>(p.ST), s0 + (p_end - pp)));
         if (sg > 0) mbar_wait(bar(BAR_A_EMPTY), (sg - 1) & 1);
+        tr.mark();   // owner tile issue
         mbar_expect_tx(bar(BAR_A_FULL), kslabs * kSlabBytes);
         for (int ks = 0; ks < kslabs; ++ks)
           tma_load_2d(a_smem + ks * kSlabBytes, &tm_own, ks * kSlabCols, ot * kTile, bar(BAR_A_FULL));
@@ -190,6 +205,7 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
           }
         }
         pp += s1 - s0;
+        tr.mark();   // all loads of the segment issued
       }
     }
   } else if (warp == 1) {
@@ -198,6 +214,8 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
       const uint32_t idesc1 = idesc_tf32(kTile, kTile, 0, 0);
       const uint32_t idesc2 = idesc_tf32(kTile, p.D, 0, 1);
       int stage = 0, phase = 0, sg = 0, it = 0;
+      Tracer tr(p.trace, 1);
+      tr.mark();
       auto mma1 = [&](int iter) {
         const int buf = iter & 1;
         const uint32_t d_tmem = tmem + buf * kTile;
@@ -239,11 +257,13 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
         const int s1 = static_cast<int>(min(static_cast<long long>(p.ST), s0 + (p_end - pp)));
         mbar_wait(bar(BAR_A_FULL), sg & 1);
         tc_fence_after();
+        tr.mark();   // owner tile landed
         if (!kBwd) {
           for (int st = s0; st < s1; ++st, ++it) {
             mbar_wait(bar(BAR_S_EMPTY + (it & 1)), ((it >> 1) & 1) ^ 1);
             tc_fence_after();
             mma1(it);
+            tr.mark();   // pair issued
           }
           umma_commit(bar(BAR_A_EMPTY));
         } else {
@@ -251,9 +271,12 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
           mma1(it);
           for (int st = s0; st < s1; ++st, ++it) {
             if (st + 1 < s1) mma1(it + 1); else umma_commit(bar(BAR_A_EMPTY));
+            tr.mark();   // MMA1(next) issued
             mbar_wait(bar(BAR_G_FULL + (it & 1)), (it >> 1) & 1);
             tc_fence_after();
+            tr.mark();   // G landed
             mma2(it, st == s0);
+            tr.mark();   // MMA2 issued
           }
           umma_commit(bar(BAR_ACC_FULL));
         }
@@ -272,6 +295,8 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
     const float wg = w * g;
     float dw_acc = 0.f, db_acc = 0.f, loss_acc = 0.f;
     int sg = 0, it = 0;
+    Tracer tr(trow == 0 ? p.trace : nullptr, 2);
+    tr.mark();
 
     for (long long pp = p_begin; pp < p_end; ++sg) {
       const int ot = static_cast<int>(pp / p.ST), s0 = static_cast<int>(pp % p.ST);
@@ -308,6 +333,7 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
         }
         mbar_wait(bar(BAR_S_FULL + buf), (it >> 1) & 1);
         tc_fence_after();
+        tr.mark();   // T tile ready
         const uint32_t t_addr = tmem + lane_addr + buf * kTile;
 #pragma unroll 1
         for (int ch = 0; ch < kTile / 32; ++ch) {
@@ -388,6 +414,7 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
             tmem_st32(t_addr + ch * 32, gq);
           }
         }
+        tr.mark();   // tile consumed
         if (MODE == TC_FWD) {
           tc_fence_before();
           __syncwarp();
@@ -481,6 +508,7 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
         if (lane == 0) mbar_arrive(bar(BAR_ACC_EMPTY));
       }
       pp += s1 - s0;
+      tr.mark();   // segment flushed
     }
 
     // ------------------------------------------------------------ scalar reductions (once per CTA)
@@ -552,6 +580,9 @@ int make_map_3d(CUtensorMap* m, const float* base, int rows, int D) {
   return r == CUDA_SUCCESS ? GE2E_OK : GE2E_ERR_LAUNCH;
 }
 
+unsigned long long* g_trace = nullptr;   // set through tc_set_trace (debug only)
+int g_trace_mode = -1;                   // -1: every kernel, else only TC_FWD / TC_BWD_DE / TC_BWD_DC
+
 constexpr size_t kSmemBytes = 1024 + kMaxSlabs * kSlabBytes + kStages * kStageBytes + sizeof(SharedTail);
 
 int sm_count() {
@@ -593,12 +624,16 @@ int launch_tc(const CUtensorMap& own, const CUtensorMap& s2, const CUtensorMap& 
               cudaStream_t st) {
   auto kern = tc_strip_kernel<MODE, VARIANT>;
   GE2E_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-  kern<<<G, kThreadsTc, kSmemBytes, st>>>(own, s2, s3, p);
+  TcParams q = p;
+  q.trace = (g_trace_mode < 0 || g_trace_mode == MODE) ? g_trace : nullptr;
+  kern<<<G, kThreadsTc, kSmemBytes, st>>>(own, s2, s3, q);
   GE2E_LAUNCHED();
   return GE2E_OK;
 }
 
 }  // namespace
+
+void tc_set_trace(unsigned long long* device_buf, int mode) { g_trace = device_buf; g_trace_mode = mode; }
 
 bool tc_supported(int n_local, int n_total, int M, int D, int variant) {
   (void)variant;
