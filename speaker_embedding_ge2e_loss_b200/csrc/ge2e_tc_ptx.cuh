@@ -68,6 +68,41 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int 
       : "memory");
 }
 
+// multicast variants: the box lands at the same CTA-relative offset in every CTA of `mask` and
+// completes tx bytes on the mbarrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const void* tmap, int x, int y, uint32_t bar,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const void* tmap, int x, int y, int z, uint32_t bar,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%2, %3, %4}], [%5], %6;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(z), "r"(bar), "h"(mask)
+      : "memory");
+}
+
+// ---------------------------------------------------------------- clusters
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05: TMEM management
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t holder_smem) {
@@ -134,6 +169,14 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// same, arriving on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(mask)
+      : "memory");
 }
 
 // ---------------------------------------------------------------- tcgen05: TMEM <-> registers
