@@ -2,30 +2,34 @@
 //
 // One warp-specialised kernel, three modes (the tensor-core twin of ge2e_simt.cu's strip kernel).
 // An "owner" operand tile X[128, D] stays resident in shared memory, a "stream" operand Y is
-// pulled through a TMA ring 128 rows at a time:
+// pulled through a TMA ring one work unit (128 rows) at a time:
 //
-//   MMA1   T[128 x 128] = X . Y_tile^T          (SS, both K-major, K = D)          -> TMEM
+//   MMA1   T[128 x n] = X . Y_unit^T            (SS, both K-major, K = D)            -> TMEM
 //   FWD    epilogue: online log-sum-exp (softmax) / running arg-max (contrast) over T's columns;
 //          S = w (cos + eps) + b is never written anywhere (reference s3:64-79, s3:27, s3:114-127)
+//          n = 256 (two units per step) whenever two units are left in the CTA's range
 //   BWD    epilogue: G = w g (softmax(S) - onehot) with the leave-one-out diagonal masked,
-//          rounded to TF32 and written back over T in TMEM;
-//   MMA2   Acc[128 x D] += G . Y_tile            (A from TMEM, B MN-major from smem) -> TMEM
+//          rounded to TF32 and written back over T in TMEM (n = 128);
+//   MMA2   Acc[128 x D] += G . Y_unit            (A from TMEM, B MN-major from smem)  -> TMEM
 //            BWD_DE: X = E_hat rows, Y = C_hat     -> dE_hat = (wG) C_hat
 //            BWD_DC: X = C_hat rows, Y = E_hat     -> dC_hat = (wG)^T E_hat
 //
-// Thread-block clusters: the C CTAs of a cluster own C consecutive owner tiles and walk the SAME
-// stream tiles in lock step; every stream slab is fetched from L2 once per cluster (each CTA
-// issues 1/C of it with TMA multicast), which is what the measured ~6.3 TB/s L2->SM ceiling
-// demands (one CTA alone needs 128 KB of stream operand per 128x128x256 tile).
+// CG = 2 runs every MMA on a CTA pair (tcgen05 cta_group::2, UMMA M = 256): the two CTAs of a
+// cluster own two consecutive owner tiles and each fetches HALF of every stream operand, which
+// halves the L2 -> SM traffic and the shared-memory read rate per MMA (the limits of CG = 1: the
+// probe in tests/probe/pipe_probe.cu measures 80 clk for a 128x128x8 TF32 MMA against 65 for
+// the paired 256x128x8).  The leader CTA (cluster rank 0) issues the MMAs; every barrier the MMA
+// warp waits on lives in the leader and is signalled by both CTAs.
 //
-// Work is a flat list of (owner group, stream tile) pairs cut into equal contiguous ranges over
+// Work is a flat list of (owner group, stream unit) pairs cut into equal contiguous ranges over
 // the clusters (stream-K): a cluster whose range covers only part of an owner group publishes a
 // partial result (FWD: (max, sum) per row, merged by the last CTA to finish that tile; BWD: fp32
-// atomic adds into a zeroed output).
+// vector atomics into a zeroed output).
 //
-// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread),
-// warp 2 = TMEM allocator, warps 4-11 = epilogue (TMEM lane quarter = warp % 4, column half =
-// (warp - 4) / 4: two threads share a tile row).
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4-11 = epilogue (TMEM lane quarter = warp % 4, column half = (warp - 4) / 4: two threads
+// share a tile row).  Producer and MMA warps run their loops with all 32 lanes and issue through
+// elect.sync: what looks like a detail is a 2.5x difference in MMA issue rate (see the probe).
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <limits.h>
@@ -42,18 +46,19 @@ namespace {
 
 using namespace ptx;
 
-constexpr int kTile = 128;            // owner / stream tile rows (= UMMA M = MMA1 N)
+constexpr int kTile = 128;            // owner rows per CTA (= UMMA M per CTA = TMEM lanes)
+constexpr int kUnit = 128;            // stream rows per work unit
 constexpr int kSlabCols = 32;         // fp32 columns per 128-byte swizzled row
-constexpr int kSlabBytes = kTile * 128;       // one [128 x 32] K-major slab = 16 KB
-constexpr int kStages = 6;            // TMA ring depth (16 KB each)
-constexpr int kStageBytes = 16384;
-constexpr int kMma2Rows = 16;         // stream rows per MMA2 ring stage ([D/32][16][32] MN-major)
+constexpr int kSlabBytes = kTile * 128;       // one owner [128 x 32] K-major slab = 16 KB
 constexpr int kMaxSlabs = 8;          // D <= 256
+constexpr int kRingBytes = 96 * 1024;
+constexpr int kBoxRows = 64;          // rows of one K-major stream TMA box
+constexpr int kMma2Rows = 32;         // stream rows (K of MMA2) per ring stage
+constexpr int kMaxStages = 6;
 constexpr int kEpiWarp0 = 4;
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreadsTc = (kEpiWarp0 + kEpiWarps) * 32;
-constexpr int kMaxCluster = 4;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -61,24 +66,24 @@ enum { TC_FWD = 0, TC_BWD_DE = 1, TC_BWD_DC = 2 };
 
 // barrier indices inside the shared barrier array
 enum {
-  BAR_FULL = 0,                       // [kStages]  TMA -> MMA
-  BAR_EMPTY = BAR_FULL + kStages,     // [kStages]  MMA (of every CTA in the cluster) -> TMA
-  BAR_A_FULL = BAR_EMPTY + kStages,   // owner tile landed
-  BAR_A_EMPTY,                        // owner tile no longer read by MMA1
-  BAR_S_FULL,                         // [2] MMA1 result in TMEM
-  BAR_S_EMPTY = BAR_S_FULL + 2,       // [2] FWD: epilogue drained T
-  BAR_G_FULL = BAR_S_EMPTY + 2,       // [2] BWD: G written back to TMEM
-  BAR_ACC_FULL = BAR_G_FULL + 2,      // BWD: accumulator complete for this segment
-  BAR_ACC_EMPTY,                      // BWD: accumulator drained
+  BAR_FULL = 0,                         // [stages] TMA -> MMA                         (leader)
+  BAR_EMPTY = BAR_FULL + kMaxStages,    // [stages] MMA -> TMA                         (every CTA)
+  BAR_A_FULL = BAR_EMPTY + kMaxStages,  // [slabs]  owner slab landed                  (leader)
+  BAR_A_EMPTY = BAR_A_FULL + kMaxSlabs, // owner tile no longer read by MMA1           (every CTA)
+  BAR_S_FULL,                           // [2] MMA1 result in TMEM                     (every CTA)
+  BAR_S_EMPTY = BAR_S_FULL + 2,         // [2] FWD: epilogue drained T                 (leader)
+  BAR_G_FULL = BAR_S_EMPTY + 2,         // [2] BWD: G written back to TMEM             (leader)
+  BAR_ACC_FULL = BAR_G_FULL + 2,        // BWD: accumulator complete for this segment  (every CTA)
+  BAR_ACC_EMPTY,                        // BWD: accumulator drained                    (leader)
   BAR_COUNT
 };
 
 struct TcParams {
   int n_own, n_str, D, kslabs;
   int M, spk_offset;
-  int OT, ST;                 // owner tiles, stream tiles
-  int C, OG;                  // cluster size, owner groups = ceil(OT / C)
-  long long GP;               // OG * ST (group, stream tile) pairs
+  int OT, ST;                 // owner tiles, stream units
+  int OG;                     // owner groups = ceil(OT / CG)
+  long long GP;               // OG * ST (group, stream unit) pairs
   const float* cos_diag;      // [U_local]
   const float* row_stat;      // BWD: lse per local utterance row
   const float* row_aux;       // BWD_DE: q = 1 - p_jj per local utterance row
@@ -92,7 +97,7 @@ struct TcParams {
   int32_t* kstar_out;
   float* loss_accum;
   float* per_row_out;
-  int* seg_done;              // [OT] stream tiles finished per owner tile (zeroed by the host)
+  int* seg_done;              // [OT] stream units finished per owner tile (zeroed by the host)
   float2* seg_part;           // [OT][maxseg][128] partial row state
   int maxseg;
   // BWD outputs
@@ -120,198 +125,269 @@ struct SharedTail {
   int flag;
   float red[2 * kEpiWarps];
   union {                                 // 1 KB either way: the budget above the ring is ~2 KB
-    alignas(16) float lse_s[2][kTile];    // BWD_DC: lse (log2 domain) of the current stream rows
+    alignas(16) float lse_s[2][kUnit];    // BWD_DC: lse (log2 domain) of the current stream rows
     alignas(16) float2 xch[kTile];        // FWD: row state of the upper column half
   };
 };
-static_assert(1024 + kMaxSlabs * kSlabBytes + kStages * kStageBytes + sizeof(SharedTail) <= 232448,
-              "dynamic shared memory over the 227 KB per-CTA limit");
+constexpr size_t kSmemBytes = 1024 + kMaxSlabs * kSlabBytes + kRingBytes + sizeof(SharedTail);
+static_assert(kSmemBytes <= 232448, "dynamic shared memory over the 227 KB per-CTA limit");
 
 __device__ __forceinline__ int cluster_of_pair(long long gp, long long GP, int NC) {
   // largest c with floor(c * GP / NC) <= gp
   return static_cast<int>(((gp + 1) * NC + GP - 1) / GP) - 1;
 }
 
-template <int MODE, int VARIANT>
+template <int MODE, int VARIANT, int CG>
 __global__ void __launch_bounds__(kThreadsTc, 1)
-tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constant__ CUtensorMap tm_str2,
-                const __grid_constant__ CUtensorMap tm_str3, const TcParams p) {
+tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constant__ CUtensorMap tm_strk,
+                const __grid_constant__ CUtensorMap tm_strmn, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr bool kBwd = (MODE != TC_FWD);
-  constexpr int kTmemCols = kBwd ? 512 : 256;
+  constexpr int kStageBytes = 32768 / CG;
+  constexpr int kStages = 3 * CG;
+  constexpr uint16_t kPairMask = (CG == 2) ? 3 : 1;
+  constexpr uint32_t kEpiArrivals = kEpiWarps * CG;
 
-  // carve: [owner slabs 8 x 16 KB][ring kStages x 16 KB][tail]; the dynamic window starts at the
-  // same CTA-relative offset in every CTA of the cluster, so multicast offsets line up
+  // carve: [owner slabs 8 x 16 KB][ring 96 KB][tail]; the dynamic window starts at the same
+  // CTA-relative offset in both CTAs of a pair, so descriptors and multicast offsets line up
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t a_smem = smem_base;
   const uint32_t ring_smem = smem_base + kMaxSlabs * kSlabBytes;
-  SharedTail* tail = reinterpret_cast<SharedTail*>(smem_al + kMaxSlabs * kSlabBytes + kStages * kStageBytes);
+  SharedTail* tail = reinterpret_cast<SharedTail*>(smem_al + kMaxSlabs * kSlabBytes + kRingBytes);
   const uint32_t bars = smem_u32(&tail->bars[0]);
   auto bar = [&](int i) { return bars + 8u * i; };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int C = p.C;
-  const int NC = gridDim.x / C, cl = blockIdx.x / C, cr = blockIdx.x % C;   // cluster id / rank in cluster
-  const uint16_t cmask = static_cast<uint16_t>((1u << C) - 1u);
+  const int NC = gridDim.x / CG, cl = blockIdx.x / CG;
+  const int cr = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;     // rank in the CTA pair
+  const bool leader = (cr == 0);
+  // barriers the MMA warp waits on live in the leader: address them through the cluster window
+  auto lbar = [&](int i) { return (CG == 2) ? mapa(bar(i), 0) : bar(i); };
   const long long gp_begin = (static_cast<long long>(cl) * p.GP) / NC;
   const long long gp_end = (static_cast<long long>(cl + 1) * p.GP) / NC;
   const int kslabs = p.kslabs;
-  const uint32_t mma2_tx = kslabs * kMma2Rows * 128;         // MMA2 stage bytes ([D/32][16][32])
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_own);
-    prefetch_tmap(&tm_str2);
-    if (kBwd) prefetch_tmap(&tm_str3);
+    prefetch_tmap(&tm_strk);
+    if (kBwd) prefetch_tmap(&tm_strmn);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(bar(BAR_FULL + i), 1); mbar_init(bar(BAR_EMPTY + i), C); }
-    mbar_init(bar(BAR_A_FULL), 1);
+    for (int i = 0; i < kStages; ++i) { mbar_init(bar(BAR_FULL + i), 1); mbar_init(bar(BAR_EMPTY + i), 1); }
+    for (int i = 0; i < kMaxSlabs; ++i) mbar_init(bar(BAR_A_FULL + i), 1);
     mbar_init(bar(BAR_A_EMPTY), 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar(BAR_S_FULL + i), 1);
-      mbar_init(bar(BAR_S_EMPTY + i), kEpiWarps);
-      mbar_init(bar(BAR_G_FULL + i), kEpiWarps);
+      mbar_init(bar(BAR_S_EMPTY + i), kEpiArrivals);
+      mbar_init(bar(BAR_G_FULL + i), kEpiArrivals);
     }
     mbar_init(bar(BAR_ACC_FULL), 1);
-    mbar_init(bar(BAR_ACC_EMPTY), kEpiWarps);
+    mbar_init(bar(BAR_ACC_EMPTY), kEpiArrivals);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<kTmemCols>(smem_u32(&tail->tmem_base));
+  if (warp == 2) {
+    if (CG == 1) tmem_alloc<512>(smem_u32(&tail->tmem_base));
+    else tmem_alloc_2cta<512>(smem_u32(&tail->tmem_base));
+  }
   tc_fence_before();
   __syncthreads();
-  if (C > 1) cluster_sync_all();     // peers' barriers are initialised before any multicast / remote arrive
+  if (CG > 1) cluster_sync_all();     // the peer's barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem = tail->tmem_base;
 
+  // ---- the walk over this cluster's (owner group, stream unit) range, identical in every role
+  // segment = maximal run of pairs inside one owner group; step = 1 or 2 (FWD) units of it
+  auto seg_bounds = [&](long long gp, int& og, int& s0, int& s1) {
+    og = static_cast<int>(gp / p.ST);
+    s0 = static_cast<int>(gp % p.ST);
+    s1 = static_cast<int>(min(static_cast<long long>(p.ST), s0 + (gp_end - gp)));
+  };
+  constexpr int kStepUnits = kBwd ? 1 : 2;
+
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
-      Tracer tr(p.trace, 0);
-      tr.mark();
-      int stage = 0, phase = 0, sg = 0;
-      const int rows_c = kTile / C;                 // this CTA's share of an MMA1 slab (rows)
-      const int slabs_c = kslabs / C;               // ... and of an MMA2 stage (32-column chunks)
-      auto load_mma1 = [&](int st) {
-        for (int ks = 0; ks < kslabs; ++ks) {
-          mbar_wait(bar(BAR_EMPTY + stage), phase ^ 1);
-          if (p.dbg & 1) { mbar_arrive(bar(BAR_FULL + stage)); if (++stage == kStages) { stage = 0; phase ^= 1; } continue; }
-          mbar_expect_tx(bar(BAR_FULL + stage), kSlabBytes);
-          const uint32_t dst = ring_smem + stage * kStageBytes;
-          if (C == 1) tma_load_2d(dst, &tm_str2, ks * kSlabCols, st * kTile, bar(BAR_FULL + stage));
-          else tma_load_2d_mc(dst + cr * rows_c * 128, &tm_str2, ks * kSlabCols, st * kTile + cr * rows_c,
-                              bar(BAR_FULL + stage), cmask);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
-        }
-      };
-      auto load_mma2 = [&](int st) {
-        for (int kc = 0; kc < kTile / kMma2Rows; ++kc) {
-          mbar_wait(bar(BAR_EMPTY + stage), phase ^ 1);
-          if (p.dbg & 1) { mbar_arrive(bar(BAR_FULL + stage)); if (++stage == kStages) { stage = 0; phase ^= 1; } continue; }
-          mbar_expect_tx(bar(BAR_FULL + stage), mma2_tx);
-          const uint32_t dst = ring_smem + stage * kStageBytes;
-          const int row0 = st * kTile + kc * kMma2Rows;
-          if (C == 1) tma_load_3d(dst, &tm_str3, 0, row0, 0, bar(BAR_FULL + stage));
-          else tma_load_3d_mc(dst + cr * slabs_c * kMma2Rows * 128, &tm_str3, 0, row0, cr * slabs_c,
-                              bar(BAR_FULL + stage), cmask);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
-        }
-      };
-      for (long long gp = gp_begin; gp < gp_end; ++sg) {
-        const int og = static_cast<int>(gp / p.ST), s0 = static_cast<int>(gp % p.ST);
-        const int s1 = static_cast<int>(min(static_cast<long long>(p.ST), s0 + (gp_end - gp)));
-        const int ot = og * C + cr;       // may be >= OT in the last group: TMA zero-fills, nothing is stored
-        if (sg > 0) mbar_wait(bar(BAR_A_EMPTY), (sg - 1) & 1);
-        tr.mark();   // owner tile issue
-        mbar_expect_tx(bar(BAR_A_FULL), kslabs * kSlabBytes);
-        for (int ks = 0; ks < kslabs; ++ks)
-          tma_load_2d(a_smem + ks * kSlabBytes, &tm_own, ks * kSlabCols, ot * kTile, bar(BAR_A_FULL));
-        if (!kBwd) {
-          for (int st = s0; st < s1; ++st) load_mma1(st);
+    Tracer tr(lane == 0 ? p.trace : nullptr, 0);
+    tr.mark();
+    int stage = 0, phase = 0, sg = 0;
+    auto advance = [&]() { if (++stage == kStages) { stage = 0; phase ^= 1; } };
+    // one K-major stage: `nslab` slabs of [rows_cta x 32] starting at slab ks0, stream rows
+    // [row0 + cr * rows_cta, + rows_cta) of a step that covers rows_cta * CG rows
+    auto load_k = [&](int row0, int rows_cta, int ks0, int nslab) {
+      mbar_wait(bar(BAR_EMPTY + stage), phase ^ 1);
+      if (elect_one()) {
+        const uint32_t bytes = static_cast<uint32_t>(nslab * rows_cta * 128);
+        if (p.dbg & 1) {
+          if (leader) mbar_arrive(bar(BAR_FULL + stage));
         } else {
-          load_mma1(s0);
-          for (int st = s0; st < s1; ++st) {
-            if (st + 1 < s1) load_mma1(st + 1);
-            load_mma2(st);
-          }
+          if (leader) mbar_expect_tx(bar(BAR_FULL + stage), bytes * CG);
+          const uint32_t full = lbar(BAR_FULL + stage);
+          uint32_t dst = ring_smem + stage * kStageBytes;
+          for (int sl = 0; sl < nslab; ++sl)
+            for (int r = 0; r < rows_cta; r += kBoxRows, dst += kBoxRows * 128) {
+              if (CG == 1) tma_load_2d(dst, &tm_strk, (ks0 + sl) * kSlabCols, row0 + r, full);
+              else tma_load_2d_2cta(dst, &tm_strk, (ks0 + sl) * kSlabCols, row0 + cr * rows_cta + r, full);
+            }
         }
-        gp += s1 - s0;
-        tr.mark();   // all loads of the segment issued
       }
+      __syncwarp();
+      advance();
+    };
+    // one MN-major stage: kMma2Rows stream rows x this CTA's share of the D columns
+    auto load_mn = [&](int row0) {
+      mbar_wait(bar(BAR_EMPTY + stage), phase ^ 1);
+      if (elect_one()) {
+        const int slabs_c = kslabs / CG;
+        const uint32_t bytes = static_cast<uint32_t>(slabs_c * kMma2Rows * 128);
+        if (p.dbg & 1) {
+          if (leader) mbar_arrive(bar(BAR_FULL + stage));
+        } else {
+          if (leader) mbar_expect_tx(bar(BAR_FULL + stage), bytes * CG);
+          const uint32_t full = lbar(BAR_FULL + stage);
+          const uint32_t dst = ring_smem + stage * kStageBytes;
+          if (CG == 1) tma_load_3d(dst, &tm_strmn, 0, row0, 0, full);
+          else tma_load_3d_2cta(dst, &tm_strmn, 0, row0, cr * slabs_c, full);
+        }
+      }
+      __syncwarp();
+      advance();
+    };
+    auto load_mma1_unit = [&](int u) {       // BWD: stages of two slabs, n = 128
+      for (int ks = 0; ks < kslabs; ks += 2) load_k(u * kUnit, kUnit / CG, ks, min(2, kslabs - ks));
+    };
+    for (long long gp = gp_begin; gp < gp_end; ++sg) {
+      int og, s0, s1;
+      seg_bounds(gp, og, s0, s1);
+      const int ot = og * CG + cr;      // may be >= OT in the last group: TMA zero-fills, nothing is stored
+      if (sg > 0) mbar_wait(bar(BAR_A_EMPTY), (sg - 1) & 1);
+      tr.mark();   // owner tile issue
+      if (elect_one()) {
+        for (int ks = 0; ks < kslabs; ++ks) {
+          if (leader) mbar_expect_tx(bar(BAR_A_FULL + ks), kSlabBytes * CG);
+          if (CG == 1) tma_load_2d(a_smem + ks * kSlabBytes, &tm_own, ks * kSlabCols, ot * kTile, bar(BAR_A_FULL + ks));
+          else tma_load_2d_2cta(a_smem + ks * kSlabBytes, &tm_own, ks * kSlabCols, ot * kTile, lbar(BAR_A_FULL + ks));
+        }
+      }
+      __syncwarp();
+      if (!kBwd) {
+        for (int u = s0; u < s1; u += kStepUnits) {
+          const int nu = min(kStepUnits, s1 - u);
+          for (int ks = 0; ks < kslabs; ++ks) load_k(u * kUnit, nu * kUnit / CG, ks, 1);
+        }
+      } else {
+        load_mma1_unit(s0);
+        for (int u = s0; u < s1; ++u) {
+          if (u + 1 < s1) load_mma1_unit(u + 1);
+          for (int kc = 0; kc < kUnit / kMma2Rows; ++kc) load_mn(u * kUnit + kc * kMma2Rows);
+        }
+      }
+      gp += s1 - s0;
+      tr.mark();   // all loads of the segment issued
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc1 = idesc_tf32(kTile, kTile, 0, 0);
-      const uint32_t idesc2 = idesc_tf32(kTile, p.D, 0, 1);
+    // ===================================================================== MMA issuer (leader CTA)
+    if (leader) {
+      const uint32_t idesc2 = idesc_tf32(kTile * CG, p.D, 0, 1);
       // descriptor templates: only the 14-bit start-address field changes per MMA
       const uint64_t dk = smem_desc(0, 16, 1024, kLayoutSw128);                        // K-major
       const uint64_t dmn = smem_desc(0, kMma2Rows * 128, 512, kLayoutSw128Base32);     // MN-major TF32
       int stage = 0, phase = 0, sg = 0, it = 0;
-      Tracer tr(p.trace, 1);
+      Tracer tr(lane == 0 ? p.trace : nullptr, 1);
       tr.mark();
-      auto release = [&](int s) {
-        if (C == 1) umma_commit(bar(BAR_EMPTY + s)); else umma_commit_mc(bar(BAR_EMPTY + s), cmask);
+      auto advance = [&]() { if (++stage == kStages) { stage = 0; phase ^= 1; } };
+      auto commit = [&](int b) {
+        if (CG == 1) umma_commit(bar(b)); else umma_commit_2cta(bar(b), kPairMask);
       };
-      auto mma1 = [&](int iter) {
-        const uint32_t d_tmem = tmem + (iter & 1) * kTile;
-        for (int ks = 0; ks < kslabs; ++ks) {
-          mbar_wait(bar(BAR_FULL + stage), phase);
-          tc_fence_after();
-          const uint64_t da = dk | ((a_smem + ks * kSlabBytes) >> 4);
-          const uint64_t db = dk | ((ring_smem + stage * kStageBytes) >> 4);
-#pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4)     // +32 B per K step of 8 inside the 128 B swizzled row
-            if (!(p.dbg & 2)) umma_tf32_ss(d_tmem, da + 2 * k4, db + 2 * k4, idesc1, (ks | k4) != 0);
-          release(stage);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+      auto ss = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+        if (p.dbg & 2) return;
+        if (CG == 1) umma_tf32_ss(d, da, db, idesc, acc); else umma_tf32_ss_2cta(d, da, db, idesc, acc);
+      };
+      auto ts = [&](uint32_t d, uint32_t a, uint64_t db, uint32_t idesc, uint32_t acc) {
+        if (p.dbg & 2) return;
+        if (CG == 1) umma_tf32_ts(d, a, db, idesc, acc); else umma_tf32_ts_2cta(d, a, db, idesc, acc);
+      };
+      // MMA1 over one stage holding `nslab` K-slabs of [rows_cta x 32] starting at slab ks0
+      auto mma1_stage = [&](uint32_t d_tmem, int n, int rows_cta, int ks0, int nslab, bool first_of_seg) {
+        if (first_of_seg) {
+          for (int sl = 0; sl < nslab; ++sl) mbar_wait(bar(BAR_A_FULL + ks0 + sl), sg & 1);
         }
-        umma_commit(bar(BAR_S_FULL + (iter & 1)));
+        mbar_wait(bar(BAR_FULL + stage), phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t idesc1 = idesc_tf32(kTile * CG, n, 0, 0);
+          for (int sl = 0; sl < nslab; ++sl) {
+            const uint64_t da = dk | ((a_smem + (ks0 + sl) * kSlabBytes) >> 4);
+            const uint64_t db = dk | ((ring_smem + stage * kStageBytes + sl * rows_cta * 128) >> 4);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)     // +32 B per K step of 8 inside the 128 B swizzled row
+              ss(d_tmem, da + 2 * k4, db + 2 * k4, idesc1, ((ks0 + sl) | k4) != 0);
+          }
+          commit(BAR_EMPTY + stage);
+        }
+        __syncwarp();
+        advance();
       };
-      auto mma2 = [&](int iter, bool first) {
-        const uint32_t a_tmem = tmem + (iter & 1) * kTile;
-        const uint32_t d_tmem = tmem + 2 * kTile;
-        for (int kc = 0; kc < kTile / kMma2Rows; ++kc) {
+      auto mma1_unit = [&](int iter, bool first_of_seg) {   // BWD: n = 128 into T[iter & 1]
+        const uint32_t d_tmem = tmem + (iter & 1) * kUnit;
+        for (int ks = 0; ks < kslabs; ks += 2)
+          mma1_stage(d_tmem, kUnit, kUnit / CG, ks, min(2, kslabs - ks), first_of_seg);
+        if (elect_one()) commit(BAR_S_FULL + (iter & 1));
+        __syncwarp();
+      };
+      auto mma2_unit = [&](int iter, bool first) {
+        const uint32_t a_tmem = tmem + (iter & 1) * kUnit;
+        const uint32_t d_tmem = tmem + 2 * kUnit;
+        for (int kc = 0; kc < kUnit / kMma2Rows; ++kc) {
           mbar_wait(bar(BAR_FULL + stage), phase);
           tc_fence_after();
-          // MN-major TF32 operand: 32-byte-atom 128B swizzle, chunks of 32 columns kMma2Rows*128 B
-          // apart (LBO), groups of 4 k-rows 512 B apart (SBO); one MMA consumes 8 k-rows = 1024 B
-          const uint64_t db = dmn | ((ring_smem + stage * kStageBytes) >> 4);
+          if (elect_one()) {
+            // MN-major TF32 operand: 32-byte-atom 128B swizzle, chunks of 32 columns kMma2Rows*128 B
+            // apart (LBO), groups of 4 k-rows 512 B apart (SBO); one MMA consumes 8 k-rows = 1024 B
+            const uint64_t db = dmn | ((ring_smem + stage * kStageBytes) >> 4);
 #pragma unroll
-          for (int k2 = 0; k2 < kMma2Rows / 8; ++k2)
-            if (!(p.dbg & 2)) umma_tf32_ts(d_tmem, a_tmem + kc * kMma2Rows + k2 * 8, db + 64 * k2, idesc2,
-                         !(first && kc == 0 && k2 == 0));
-          release(stage);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+            for (int k2 = 0; k2 < kMma2Rows / 8; ++k2)
+              ts(d_tmem, a_tmem + kc * kMma2Rows + k2 * 8, db + 64 * k2, idesc2, !(first && kc == 0 && k2 == 0));
+            commit(BAR_EMPTY + stage);
+          }
+          __syncwarp();
+          advance();
         }
       };
       for (long long gp = gp_begin; gp < gp_end; ++sg) {
-        const int s0 = static_cast<int>(gp % p.ST);
-        const int s1 = static_cast<int>(min(static_cast<long long>(p.ST), s0 + (gp_end - gp)));
-        mbar_wait(bar(BAR_A_FULL), sg & 1);
-        tc_fence_after();
-        tr.mark();   // owner tile landed
+        int og, s0, s1;
+        seg_bounds(gp, og, s0, s1);
         if (!kBwd) {
-          for (int st = s0; st < s1; ++st, ++it) {
+          for (int u = s0; u < s1; u += kStepUnits, ++it) {
+            const int nu = min(kStepUnits, s1 - u);
             mbar_wait(bar(BAR_S_EMPTY + (it & 1)), ((it >> 1) & 1) ^ 1);
             tc_fence_after();
-            mma1(it);
-            tr.mark();   // pair issued
+            const uint32_t d_tmem = tmem + (it & 1) * (kStepUnits * kUnit);
+            for (int ks = 0; ks < kslabs; ++ks) mma1_stage(d_tmem, nu * kUnit, nu * kUnit / CG, ks, 1, u == s0);
+            if (elect_one()) commit(BAR_S_FULL + (it & 1));
+            __syncwarp();
+            tr.mark();   // step issued
           }
-          umma_commit(bar(BAR_A_EMPTY));
+          if (elect_one()) commit(BAR_A_EMPTY);
+          __syncwarp();
         } else {
-          if (sg > 0) { mbar_wait(bar(BAR_ACC_EMPTY), (sg - 1) & 1); tc_fence_after(); }
-          mma1(it);
-          for (int st = s0; st < s1; ++st, ++it) {
-            if (st + 1 < s1) mma1(it + 1); else umma_commit(bar(BAR_A_EMPTY));
+          mma1_unit(it, true);
+          for (int u = s0; u < s1; ++u, ++it) {
+            if (u + 1 < s1) {
+              mma1_unit(it + 1, false);
+            } else {
+              if (elect_one()) commit(BAR_A_EMPTY);
+              __syncwarp();
+            }
             tr.mark();   // MMA1(next) issued
+            if (u == s0 && sg > 0) { mbar_wait(bar(BAR_ACC_EMPTY), (sg - 1) & 1); tc_fence_after(); }
             mbar_wait(bar(BAR_G_FULL + (it & 1)), (it >> 1) & 1);
             tc_fence_after();
             tr.mark();   // G landed
-            mma2(it, st == s0);
+            mma2_unit(it, u == s0);
             tr.mark();   // MMA2 issued
           }
-          umma_commit(bar(BAR_ACC_FULL));
+          if (elect_one()) commit(BAR_ACC_FULL);
+          __syncwarp();
         }
         gp += s1 - s0;
       }
@@ -319,7 +395,7 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
   } else if (warp >= kEpiWarp0) {
     // ===================================================================== epilogue
     const int ew = warp - kEpiWarp0;
-    const int quarter = ew & 3, half = ew >> 2;      // TMEM lanes [32 q, 32 q + 32); columns [64 h, 64 h + 64)
+    const int quarter = ew & 3, half = ew >> 2;      // TMEM lanes [32 q, 32 q + 32); column half h
     const int trow = quarter * 32 + lane;            // row inside the owner tile
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const float w = __ldg(p.w), b = __ldg(p.b), eps = p.eps;
@@ -331,11 +407,16 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
     int sg = 0, it = 0;
     Tracer tr((trow == 0 && half == 0) ? p.trace : nullptr, 2);
     tr.mark();
+    // epilogue -> MMA signals go to the leader CTA of the pair
+    const uint32_t s_empty0 = lbar(BAR_S_EMPTY), g_full0 = lbar(BAR_G_FULL), acc_empty = lbar(BAR_ACC_EMPTY);
+    auto arrive_leader = [&](uint32_t addr) {
+      if (CG == 1) mbar_arrive(addr); else mbar_arrive_cluster(addr);
+    };
 
     for (long long gp = gp_begin; gp < gp_end; ++sg) {
-      const int og = static_cast<int>(gp / p.ST), s0 = static_cast<int>(gp % p.ST);
-      const int s1 = static_cast<int>(min(static_cast<long long>(p.ST), s0 + (gp_end - gp)));
-      const int ot = og * C + cr;
+      int og, s0, s1;
+      seg_bounds(gp, og, s0, s1);
+      const int ot = og * CG + cr;
       const bool tile_valid = ot < p.OT;             // CTA-uniform
       const int orow = ot * kTile + trow;            // owner row (utterance, or centroid for DC)
       const bool ovalid = orow < p.n_own;
@@ -359,23 +440,25 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
       float m2 = xd2, lsum = 0.f;
       float best = -INFINITY; int bestk = INT_MAX;   // FWD contrast
 
-      for (int st = s0; st < s1; ++st, ++it) {
+      for (int u = s0; u < s1; u += kStepUnits, ++it) {
+        const int nu = min(kStepUnits, s1 - u);
         const int buf = it & 1;
         if (MODE == TC_BWD_DC) {
-          // stage the lse of the 128 stream rows (utterances) of this tile
+          // stage the lse of the 128 stream rows (utterances) of this unit
           if (half == 0) {
-            const int u = st * kTile + trow;
-            tail->lse_s[buf][trow] = (u < p.n_str) ? __ldg(p.row_stat + u) * kLog2e : INFINITY;
+            const int ur = u * kUnit + trow;
+            tail->lse_s[buf][trow] = (ur < p.n_str) ? __ldg(p.row_stat + ur) * kLog2e : INFINITY;
           }
           named_bar_sync(1, kEpiThreads);
         }
         mbar_wait(bar(BAR_S_FULL + buf), (it >> 1) & 1);
         tc_fence_after();
         tr.mark();   // T tile ready
-        const uint32_t t_addr = tmem + lane_addr + buf * kTile;
+        const uint32_t t_addr = tmem + lane_addr + buf * (kStepUnits * kUnit);
+        const int nch = nu * (kUnit / 32) / 2;       // 32-column chunks per column half
 #pragma unroll 1
-        for (int ch = 2 * half; ch < 2 * half + 2; ++ch) {
-          const int c0 = st * kTile + ch * 32;       // first stream row (column of T) of this chunk
+        for (int ch = half * nch; ch < (half + 1) * nch; ++ch) {
+          const int c0 = u * kUnit + ch * 32;        // first stream row (column of T) of this chunk
           uint32_t v[32];
           tmem_ld32(t_addr + ch * 32, v);
           tmem_ld_wait();
@@ -460,12 +543,12 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
         if (MODE == TC_FWD) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar(BAR_S_EMPTY + buf));
+          if (lane == 0) arrive_leader(s_empty0 + 8u * buf);
         } else {
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar(BAR_G_FULL + buf));
+          if (lane == 0) arrive_leader(g_full0 + 8u * buf);
         }
       }
 
@@ -544,7 +627,7 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
         const int ch0 = half ? kslabs / 2 : 0, ch1 = half ? kslabs : kslabs / 2;
         for (int ch = ch0; ch < ch1; ++ch) {
           uint32_t v[32];
-          tmem_ld32(tmem + lane_addr + 2 * kTile + ch * 32, v);
+          tmem_ld32(tmem + lane_addr + 2 * kUnit + ch * 32, v);
           tmem_ld_wait();
           if (ovalid) {
 #pragma unroll
@@ -558,7 +641,7 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(BAR_ACC_EMPTY));
+        if (lane == 0) arrive_leader(acc_empty);
       }
       gp += s1 - s0;
       tr.mark();   // segment flushed
@@ -591,8 +674,10 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
   // ------------------------------------------------------------------------- teardown
   tc_fence_before();
   __syncthreads();
-  if (C > 1) cluster_sync_all();     // no CTA leaves while a peer may still multicast into it / arrive on it
-  if (warp == 2) tmem_dealloc<kTmemCols>(tmem);
+  if (CG > 1) cluster_sync_all();     // no CTA leaves while its peer may still arrive on it / read its smem
+  if (warp == 2) {
+    if (CG == 1) tmem_dealloc<512>(tmem); else tmem_dealloc_2cta<512>(tmem);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -624,8 +709,8 @@ int make_map_2d(CUtensorMap* m, const float* base, int rows, int D, int box_rows
   return r == CUDA_SUCCESS ? GE2E_OK : GE2E_ERR_LAUNCH;
 }
 
-// 3-D map over the same X viewed as [D/32][rows][32]: box = [box_slabs][16 rows][32 cols]
-// (MN-major operand chunks for MMA2: 16 k-rows x D columns per ring stage).  32-bit MN-major
+// 3-D map over the same X viewed as [D/32][rows][32]: box = [box_slabs][32 rows][32 cols]
+// (MN-major operand chunks for MMA2: 32 k-rows x D columns per ring stage).  32-bit MN-major
 // operands must use the 32-byte-atom flavour of the 128B swizzle (UMMA SWIZZLE_128B_BASE32B).
 int make_map_3d(CUtensorMap* m, const float* base, int rows, int D, int box_slabs) {
   auto enc = get_encode();
@@ -643,8 +728,6 @@ int make_map_3d(CUtensorMap* m, const float* base, int rows, int D, int box_slab
 unsigned long long* g_trace = nullptr;   // set through tc_set_trace (debug only)
 int g_trace_mode = -1;                   // -1: every kernel, else only TC_FWD / TC_BWD_DE / TC_BWD_DC
 
-constexpr size_t kSmemBytes = 1024 + kMaxSlabs * kSlabBytes + kStages * kStageBytes + sizeof(SharedTail);
-
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -656,61 +739,60 @@ int sm_count() {
   return n;
 }
 
-// Cluster size: GE2E_TC_CLUSTER overrides (1, 2 or 4); it must divide the number of 32-column
-// chunks of D so that an MMA2 stage splits evenly between the CTAs.
-int pick_cluster(int D) {
+// CTA-pair mode (cta_group::2) needs an even number of 32-column chunks of D so that an MMA2 stage
+// splits evenly between the two CTAs.  GE2E_TC_CG = 1 | 2 overrides.
+int pick_cg(int D) {
   static int env = -1;
   if (env < 0) {
-    const char* s = getenv("GE2E_TC_CLUSTER");
+    const char* s = getenv("GE2E_TC_CG");
     env = s ? atoi(s) : 0;
   }
-  int C = (env == 1 || env == 2 || env == 4) ? env : 1;
-  while (C > 1 && (D / kSlabCols) % C != 0) C >>= 1;
-  return C;
+  int cg = (env == 1 || env == 2) ? env : 1;
+  if ((D / kSlabCols) % 2 != 0) cg = 1;
+  return cg;
 }
 
-// How many clusters of size C can be co-resident (1 CTA per SM: the kernel needs ~225 KB smem).
-// Cluster size 4 strands a few SMs per GPC; measured by the occupancy API when available.
-template <int MODE, int VARIANT>
-int max_clusters(int C) {
-  static int cache[kMaxCluster + 1] = {0, 0, 0, 0, 0};
-  if (cache[C] == 0) {
+// How many clusters of size CG can be co-resident (1 CTA per SM: the kernel needs ~225 KB smem).
+template <int MODE, int VARIANT, int CG>
+int max_clusters() {
+  static int cache = 0;
+  if (cache == 0) {
     int n = 0;
-    if (C > 1) {
+    if (CG > 1) {
       cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(sm_count() / C * C);
+      cfg.gridDim = dim3(sm_count() / CG * CG);
       cfg.blockDim = dim3(kThreadsTc);
       cfg.dynamicSmemBytes = kSmemBytes;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
-      cudaFuncSetAttribute(tc_strip_kernel<MODE, VARIANT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaFuncSetAttribute(tc_strip_kernel<MODE, VARIANT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)kSmemBytes);
-      if (cudaOccupancyMaxActiveClusters(&n, tc_strip_kernel<MODE, VARIANT>, &cfg) != cudaSuccess) n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, tc_strip_kernel<MODE, VARIANT, CG>, &cfg) != cudaSuccess) n = 0;
       (void)cudaGetLastError();
     }
-    if (n <= 0) n = sm_count() / C;
-    cache[C] = n;
+    if (n <= 0) n = sm_count() / CG;
+    cache = n;
   }
-  return cache[C];
+  return cache;
 }
 
 struct Layout {
-  int OT, ST, C, OG, NC, maxseg;
+  int OT, ST, CG, OG, NC, maxseg;
   long long GP;
   size_t done_bytes, part_bytes;
   bool whole;       // every cluster's range is a whole number of owner groups: no partial flushes
 };
 
-Layout make_layout(int n_own, int n_str, int D, int max_cl_of_C(int)) {
+Layout make_layout(int n_own, int n_str, int cg, int max_cl) {
   Layout L{};
   L.OT = (n_own + kTile - 1) / kTile;
-  L.ST = (n_str + kTile - 1) / kTile;
-  L.C = pick_cluster(D);
-  L.OG = (L.OT + L.C - 1) / L.C;
+  L.ST = (n_str + kUnit - 1) / kUnit;
+  L.CG = cg;
+  L.OG = (L.OT + L.CG - 1) / L.CG;
   L.GP = static_cast<long long>(L.OG) * L.ST;
-  L.NC = static_cast<int>(std::min<long long>(max_cl_of_C(L.C), L.GP));
+  L.NC = static_cast<int>(std::min<long long>(max_cl, L.GP));
   const long long per = L.GP / L.NC;                 // >= 1
   L.maxseg = static_cast<int>(std::min<long long>(L.ST, L.ST / per + 2));
   L.done_bytes = (static_cast<size_t>(L.OT) * sizeof(int) + 255) & ~static_cast<size_t>(255);
@@ -719,10 +801,10 @@ Layout make_layout(int n_own, int n_str, int D, int max_cl_of_C(int)) {
   return L;
 }
 
-template <int MODE, int VARIANT>
-int launch_tc(const CUtensorMap& own, const CUtensorMap& s2, const CUtensorMap& s3, const TcParams& p, int NC,
+template <int MODE, int VARIANT, int CG>
+int launch_tc(const CUtensorMap& own, const CUtensorMap& sk, const CUtensorMap& smn, const TcParams& p, int NC,
               cudaStream_t st) {
-  auto kern = tc_strip_kernel<MODE, VARIANT>;
+  auto kern = tc_strip_kernel<MODE, VARIANT, CG>;
   GE2E_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   TcParams q = p;
   q.trace = (g_trace_mode < 0 || g_trace_mode == MODE) ? g_trace : nullptr;
@@ -732,23 +814,41 @@ int launch_tc(const CUtensorMap& own, const CUtensorMap& s2, const CUtensorMap& 
     q.dbg = dbg;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(NC * p.C);
+  cfg.gridDim = dim3(NC * CG);
   cfg.blockDim = dim3(kThreadsTc);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = p.C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  GE2E_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, own, s2, s3, q));
+  GE2E_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, own, sk, smn, q));
   GE2E_LAUNCHED();
   return GE2E_OK;
 }
 
+template <int MODE, int VARIANT>
+int max_clusters_cg(int cg) {
+  return cg == 2 ? max_clusters<MODE, VARIANT, 2>() : max_clusters<MODE, VARIANT, 1>();
+}
+template <int MODE, int VARIANT>
+int launch_tc_cg(int cg, const CUtensorMap& own, const CUtensorMap& sk, const CUtensorMap& smn, const TcParams& p,
+                 int NC, cudaStream_t st) {
+  return cg == 2 ? launch_tc<MODE, VARIANT, 2>(own, sk, smn, p, NC, st)
+                 : launch_tc<MODE, VARIANT, 1>(own, sk, smn, p, NC, st);
+}
+
 void fill_common(TcParams& p, const RowsArgs& a, const Layout& L) {
   p.D = a.D; p.kslabs = a.D / kSlabCols; p.M = a.M; p.spk_offset = a.spk_offset;
-  p.OT = L.OT; p.ST = L.ST; p.C = L.C; p.OG = L.OG; p.GP = L.GP;
+  p.OT = L.OT; p.ST = L.ST; p.OG = L.OG; p.GP = L.GP;
   p.cos_diag = a.cos_diag; p.w = a.w; p.b = a.b; p.eps = a.eps;
+}
+
+Layout fwd_layout(int U, int n_total, int D, int variant) {
+  const int cg = pick_cg(D);
+  const int mc = (variant == GE2E_SOFTMAX) ? max_clusters_cg<TC_FWD, GE2E_SOFTMAX>(cg)
+                                           : max_clusters_cg<TC_FWD, GE2E_CONTRAST>(cg);
+  return make_layout(U, n_total, cg, mc);
 }
 
 }  // namespace
@@ -763,21 +863,19 @@ bool tc_supported(int n_local, int n_total, int M, int D, int variant) {
 }
 
 size_t tc_workspace_bytes(int n_local, int n_total, int M, int D, int variant) {
-  const Layout L = (variant == GE2E_SOFTMAX) ? make_layout(n_local * M, n_total, D, max_clusters<TC_FWD, GE2E_SOFTMAX>)
-                                             : make_layout(n_local * M, n_total, D, max_clusters<TC_FWD, GE2E_CONTRAST>);
+  const Layout L = fwd_layout(n_local * M, n_total, D, variant);
   return L.done_bytes + L.part_bytes;
 }
 
 int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* row_aux, float* loss_accum,
                 float* per_row_out, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int U = a.n_local * a.M;
-  const Layout L = (a.variant == GE2E_SOFTMAX) ? make_layout(U, a.n_total, a.D, max_clusters<TC_FWD, GE2E_SOFTMAX>)
-                                               : make_layout(U, a.n_total, a.D, max_clusters<TC_FWD, GE2E_CONTRAST>);
+  const Layout L = fwd_layout(U, a.n_total, a.D, a.variant);
   if (ws_bytes < L.done_bytes + L.part_bytes) return GE2E_ERR_WORKSPACE;
   CUtensorMap tmE, tmC;
   int rc = make_map_2d(&tmE, a.e_hat, U, a.D, kTile);
   if (rc != GE2E_OK) return rc;
-  if ((rc = make_map_2d(&tmC, a.c_hat_all, a.n_total, a.D, kTile / L.C)) != GE2E_OK) return rc;
+  if ((rc = make_map_2d(&tmC, a.c_hat_all, a.n_total, a.D, kBoxRows)) != GE2E_OK) return rc;
   TcParams p{};
   fill_common(p, a, L);
   p.n_own = U; p.n_str = a.n_total;
@@ -787,8 +885,8 @@ int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* r
   p.seg_part = reinterpret_cast<float2*>(static_cast<uint8_t*>(ws) + L.done_bytes);
   p.maxseg = L.maxseg;
   if (!L.whole) GE2E_CUDA_TRY(cudaMemsetAsync(ws, 0, L.done_bytes, st));
-  if (a.variant == GE2E_SOFTMAX) return launch_tc<TC_FWD, GE2E_SOFTMAX>(tmE, tmC, tmC, p, L.NC, st);
-  return launch_tc<TC_FWD, GE2E_CONTRAST>(tmE, tmC, tmC, p, L.NC, st);
+  if (a.variant == GE2E_SOFTMAX) return launch_tc_cg<TC_FWD, GE2E_SOFTMAX>(L.CG, tmE, tmC, tmC, p, L.NC, st);
+  return launch_tc_cg<TC_FWD, GE2E_CONTRAST>(L.CG, tmE, tmC, tmC, p, L.NC, st);
 }
 
 int tc_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kstar, const float* row_aux,
@@ -803,17 +901,18 @@ int tc_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kst
     GE2E_CUDA_TRY(cudaMemsetAsync(dC_hat_partial, 0, dc_elems * sizeof(float), st));
     GE2E_CUDA_TRY(cudaMemsetAsync(dwdb_accum, 0, 2 * sizeof(float), st));
   }
-  const Layout Le = make_layout(U, a.n_total, a.D, max_clusters<TC_BWD_DE, GE2E_SOFTMAX>);
-  const Layout Lc = make_layout(a.n_total, U, a.D, max_clusters<TC_BWD_DC, GE2E_SOFTMAX>);
+  const int cg = pick_cg(a.D);
+  const Layout Le = make_layout(U, a.n_total, cg, max_clusters_cg<TC_BWD_DE, GE2E_SOFTMAX>(cg));
+  const Layout Lc = make_layout(a.n_total, U, cg, max_clusters_cg<TC_BWD_DC, GE2E_SOFTMAX>(cg));
   const int slabs = a.D / kSlabCols;
-  CUtensorMap tmE_own, tmC_own, tmE_s2, tmC_s2, tmE_s3, tmC_s3;
+  CUtensorMap tmE_own, tmC_own, tmE_k, tmC_k, tmE_mn, tmC_mn;
   int rc;
   if ((rc = make_map_2d(&tmE_own, a.e_hat, U, a.D, kTile)) != GE2E_OK) return rc;
   if ((rc = make_map_2d(&tmC_own, a.c_hat_all, a.n_total, a.D, kTile)) != GE2E_OK) return rc;
-  if ((rc = make_map_2d(&tmC_s2, a.c_hat_all, a.n_total, a.D, kTile / Le.C)) != GE2E_OK) return rc;
-  if ((rc = make_map_3d(&tmC_s3, a.c_hat_all, a.n_total, a.D, slabs / Le.C)) != GE2E_OK) return rc;
-  if ((rc = make_map_2d(&tmE_s2, a.e_hat, U, a.D, kTile / Lc.C)) != GE2E_OK) return rc;
-  if ((rc = make_map_3d(&tmE_s3, a.e_hat, U, a.D, slabs / Lc.C)) != GE2E_OK) return rc;
+  if ((rc = make_map_2d(&tmC_k, a.c_hat_all, a.n_total, a.D, kBoxRows)) != GE2E_OK) return rc;
+  if ((rc = make_map_3d(&tmC_mn, a.c_hat_all, a.n_total, a.D, slabs / cg)) != GE2E_OK) return rc;
+  if ((rc = make_map_2d(&tmE_k, a.e_hat, U, a.D, kBoxRows)) != GE2E_OK) return rc;
+  if ((rc = make_map_3d(&tmE_mn, a.e_hat, U, a.D, slabs / cg)) != GE2E_OK) return rc;
 
   // dE_hat = (wG) C_hat: owner = utterance tiles; partial owner-group ranges add into a zeroed output
   TcParams p{};
@@ -822,14 +921,14 @@ int tc_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kst
   p.n_own = U; p.n_str = a.n_total;
   p.acc_out = dE_hat; p.dwdb = dwdb_accum;
   if (!Le.whole) GE2E_CUDA_TRY(cudaMemsetAsync(dE_hat, 0, static_cast<size_t>(U) * a.D * sizeof(float), st));
-  rc = launch_tc<TC_BWD_DE, GE2E_SOFTMAX>(tmE_own, tmC_s2, tmC_s3, p, Le.NC, st);
+  rc = launch_tc_cg<TC_BWD_DE, GE2E_SOFTMAX>(cg, tmE_own, tmC_k, tmC_mn, p, Le.NC, st);
   if (rc != GE2E_OK) return rc;
 
   // dC_hat = (wG)^T E_hat: owner = centroid tiles, the utterance range is cut stream-K style
   fill_common(p, a, Lc);
   p.n_own = a.n_total; p.n_str = U;
   p.acc_out = dC_hat_partial; p.dwdb = nullptr;
-  return launch_tc<TC_BWD_DC, GE2E_SOFTMAX>(tmC_own, tmE_s2, tmE_s3, p, Lc.NC, st);
+  return launch_tc_cg<TC_BWD_DC, GE2E_SOFTMAX>(cg, tmC_own, tmE_k, tmE_mn, p, Lc.NC, st);
 }
 
 }  // namespace ge2e

@@ -179,6 +179,82 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
       : "memory");
 }
 
+
+// ---------------------------------------------------------------- warp election, cluster addressing
+// One lane of a fully converged warp.  Gating tcgen05 / TMA issue with elect.sync (instead of
+// `lane == 0`) lets ptxas keep descriptors in uniform registers and emit the instruction once;
+// a plain lane test costs a per-lane ELECT loop around every UTCHMMA (probe: 87 vs <35 clk/MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// arrive on an mbarrier given by a shared::cluster address (own or peer CTA)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+
+// ---------------------------------------------------------------- cta_group::2 (CTA pair) variants
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t holder_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(holder_smem), "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts_2cta(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this CTA-relative offset in every CTA of `mask` once all MMAs issued
+// so far by this thread have completed
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(mask)
+      : "memory");
+}
+// TMA loads of a CTA pair: the data lands in this CTA's shared memory, the transaction bytes are
+// counted on `cluster_bar`, an mbarrier of the pair's leader CTA (shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const void* tmap, int x, int y, uint32_t cluster_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(cluster_bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2cta(uint32_t dst, const void* tmap, int x, int y, int z,
+                                                 uint32_t cluster_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(z), "r"(cluster_bar)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05: TMEM <-> registers
 // 32 lanes x 32 consecutive 32-bit columns: thread t of the warp gets lane (base_lane + t).
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
