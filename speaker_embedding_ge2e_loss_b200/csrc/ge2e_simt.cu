@@ -17,6 +17,8 @@
 //   finalize_kernel  one CTA per speaker: diagonal term, normalisation Jacobians, fan-out
 #include <limits.h>
 
+#include <initializer_list>
+
 #include "ge2e_common.cuh"
 
 namespace ge2e {
@@ -130,6 +132,109 @@ prep_kernel(const float* __restrict__ E, int M, int D, int Dp, float* __restrict
     float c = (sS[d] / fm) * inv_nc;
     if (ROUND) c = round_tf32(c);
     c_hat[(size_t)j * D + d] = c;
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// K1 (fast path): one WARP per speaker, no shared memory, no block barriers, no divisions.
+// Lane l owns the float4 columns {4 l + 128 c}.  Pass 1 sums the speaker's rows (s3:105), pass 2
+// re-reads them (L1 hits) for the norms / leave-one-out cosine (s3:57) and writes e_hat.
+// Requires D = 128 KCH, 16-byte aligned rows.  grid = ceil(n_local / 4), block = 128.
+// ------------------------------------------------------------------------------------------
+constexpr int kPrepWarps = 4;
+constexpr int kRowBatch = 4;   // rows in flight per lane (KCH float4 loads each)
+
+template <int KCH, bool ROUND>
+__global__ void __launch_bounds__(kPrepWarps * 32)
+prep_warp_kernel(const float* __restrict__ E, int n_local, int M, float* __restrict__ e_hat,
+                 float* __restrict__ c_hat, float* __restrict__ cos_diag, float* __restrict__ accum) {
+  constexpr int D = KCH * 128;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int j = blockIdx.x * kPrepWarps + wid;
+  if (blockIdx.x == 0 && threadIdx.x < 4 && accum != nullptr) accum[threadIdx.x] = 0.f;
+  if (j >= n_local) return;
+  const float4* Ej = reinterpret_cast<const float4*>(E + (size_t)j * M * D) + lane;   // + i * (D/4) + c * 32
+  float4 s[KCH];
+#pragma unroll
+  for (int c = 0; c < KCH; ++c) s[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i0 = 0; i0 < M; i0 += kRowBatch) {
+    float4 v[kRowBatch][KCH];
+#pragma unroll
+    for (int r = 0; r < kRowBatch; ++r)
+#pragma unroll
+      for (int c = 0; c < KCH; ++c)
+        v[r][c] = (i0 + r < M) ? __ldg(Ej + (size_t)(i0 + r) * (D / 4) + c * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < kRowBatch; ++r)
+#pragma unroll
+      for (int c = 0; c < KCH; ++c) {
+        s[c].x += v[r][c].x; s[c].y += v[r][c].y; s[c].z += v[r][c].z; s[c].w += v[r][c].w;
+      }
+  }
+  // centroid (s3:37): c = s / M, c_hat = c / max(|c|, delta)
+  const float inv_m = 1.f / (float)M, inv_m1 = 1.f / (float)(M - 1);
+  float ss = 0.f;
+#pragma unroll
+  for (int c = 0; c < KCH; ++c) ss += dot4(s[c], s[c]);
+  ss = warp_sum(ss);
+  const float sc = inv_m / fmaxf(sqrtf(ss) * inv_m, kCosDelta);
+  float4* Cj = reinterpret_cast<float4*>(c_hat + (size_t)j * D) + lane;
+#pragma unroll
+  for (int c = 0; c < KCH; ++c) {
+    float4 o = make_float4(s[c].x * sc, s[c].y * sc, s[c].z * sc, s[c].w * sc);
+    if (ROUND) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+    Cj[c * 32] = o;
+  }
+  // rows: |e|, |u| and e.u with u = (s - e) / (M - 1)   (s3:105-111, s3:57)
+  float4* Oj = reinterpret_cast<float4*>(e_hat + (size_t)j * M * D) + lane;
+  float my_cos = 0.f;
+  for (int i0 = 0; i0 < M; i0 += kRowBatch) {
+    float4 v[kRowBatch][KCH];
+    float ne2[kRowBatch], nd2[kRowBatch], ed[kRowBatch];
+#pragma unroll
+    for (int r = 0; r < kRowBatch; ++r)
+#pragma unroll
+      for (int c = 0; c < KCH; ++c)
+        v[r][c] = (i0 + r < M) ? __ldg(Ej + (size_t)(i0 + r) * (D / 4) + c * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < kRowBatch; ++r) {
+      ne2[r] = 0.f; nd2[r] = 0.f; ed[r] = 0.f;
+#pragma unroll
+      for (int c = 0; c < KCH; ++c) {
+        const float4 e = v[r][c];
+        const float4 d = make_float4(s[c].x - e.x, s[c].y - e.y, s[c].z - e.z, s[c].w - e.w);
+        ne2[r] += dot4(e, e); nd2[r] += dot4(d, d); ed[r] += dot4(e, d);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < kRowBatch; ++r) {
+        ne2[r] += __shfl_xor_sync(0xffffffffu, ne2[r], o);
+        nd2[r] += __shfl_xor_sync(0xffffffffu, nd2[r], o);
+        ed[r] += __shfl_xor_sync(0xffffffffu, ed[r], o);
+      }
+#pragma unroll
+    for (int r = 0; r < kRowBatch; ++r) {
+      if (i0 + r < M) {
+        const float inv_ne = 1.f / fmaxf(sqrtf(ne2[r]), kCosDelta);
+        const float inv_nu = 1.f / fmaxf(sqrtf(nd2[r]) * inv_m1, kCosDelta);
+        if (lane == ((i0 + r) & 31)) my_cos = (ed[r] * inv_m1) * inv_ne * inv_nu;
+#pragma unroll
+        for (int c = 0; c < KCH; ++c) {
+          float4 e = v[r][c];
+          e.x *= inv_ne; e.y *= inv_ne; e.z *= inv_ne; e.w *= inv_ne;
+          if (ROUND) { e.x = round_tf32(e.x); e.y = round_tf32(e.y); e.z = round_tf32(e.z); e.w = round_tf32(e.w); }
+          Oj[(size_t)(i0 + r) * (D / 4) + c * 32] = e;
+        }
+      }
+    }
+    // flush the cosines every 32 rows (one coalesced store per 32 rows)
+    if (((i0 + kRowBatch) & 31) == 0 || i0 + kRowBatch >= M) {
+      const int base = (i0 + kRowBatch - 1) & ~31;
+      if (base + lane < M) cos_diag[(size_t)j * M + base + lane] = my_cos;
+    }
   }
 }
 
@@ -574,6 +679,162 @@ finalize_kernel(const float* __restrict__ E, const float* __restrict__ dE_hat,
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// K4 (fast path): one WARP per speaker (M <= 32, D = 128 KCH, aligned), same math as
+// finalize_kernel below without shared memory / block barriers / divisions.  Three passes over
+// the speaker's rows (the 2nd and 3rd hit L1): column sums; per-row scalars + sum_i du_i;
+// outputs.  Row i's scalars live in lane i between the passes.
+// ------------------------------------------------------------------------------------------
+template <int KCH>
+__global__ void __launch_bounds__(kPrepWarps * 32)
+finalize_warp_kernel(const float* __restrict__ E, const float* __restrict__ dE_hat,
+                     const float* __restrict__ dC_hat, const float* __restrict__ cos_diag,
+                     const float* __restrict__ row_aux, int n_local, int M,
+                     const float* __restrict__ wp, const float* __restrict__ bp, float eps, int variant,
+                     const float* __restrict__ gp, float* __restrict__ dE) {
+  constexpr int D = KCH * 128;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int j = blockIdx.x * kPrepWarps + wid;
+  if (j >= n_local) return;
+  const float w = __ldg(wp), b = __ldg(bp), g = __ldg(gp);
+  const float4* Ej = reinterpret_cast<const float4*>(E + (size_t)j * M * D) + lane;
+  const float4* Gj = reinterpret_cast<const float4*>(dE_hat + (size_t)j * M * D) + lane;
+  float4 s[KCH];
+#pragma unroll
+  for (int c = 0; c < KCH; ++c) s[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i0 = 0; i0 < M; i0 += kRowBatch) {
+    float4 v[kRowBatch][KCH];
+#pragma unroll
+    for (int r = 0; r < kRowBatch; ++r)
+#pragma unroll
+      for (int c = 0; c < KCH; ++c)
+        v[r][c] = (i0 + r < M) ? __ldg(Ej + (size_t)(i0 + r) * (D / 4) + c * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < kRowBatch; ++r)
+#pragma unroll
+      for (int c = 0; c < KCH; ++c) {
+        s[c].x += v[r][c].x; s[c].y += v[r][c].y; s[c].z += v[r][c].z; s[c].w += v[r][c].w;
+      }
+  }
+  const float inv_m = 1.f / (float)M, inv_m1 = 1.f / (float)(M - 1);
+  // centroid Jacobian: bc = dc_j / M with dc = (dC_hat - c_hat (c_hat . dC_hat)) / |c|  (or dC_hat / delta)
+  float4 bc[KCH];
+  {
+    float4 dch[KCH];
+    float ss = 0.f, pr = 0.f;
+#pragma unroll
+    for (int c = 0; c < KCH; ++c) {
+      dch[c] = __ldg(reinterpret_cast<const float4*>(dC_hat + (size_t)j * D) + lane + c * 32);
+      ss += dot4(s[c], s[c]);
+      pr += dot4(s[c], dch[c]);
+    }
+    ss = warp_sum(ss); pr = warp_sum(pr);
+    const float nc = sqrtf(ss) * inv_m;
+    const bool ok = nc >= kCosDelta;
+    const float inv = 1.f / fmaxf(nc, kCosDelta);
+    const float proj = (pr * inv_m) * inv;          // c_hat . dC_hat
+    const float k1 = inv * inv_m;                   // dC_hat coefficient
+    const float k2 = ok ? proj * inv * inv * inv_m * inv_m : 0.f;   // coefficient of s (c_hat = s inv / M)
+#pragma unroll
+    for (int c = 0; c < KCH; ++c) {
+      bc[c].x = dch[c].x * k1 - s[c].x * k2; bc[c].y = dch[c].y * k1 - s[c].y * k2;
+      bc[c].z = dch[c].z * k1 - s[c].z * k2; bc[c].w = dch[c].w * k1 - s[c].w * k2;
+    }
+  }
+  // pass 2: per-row scalars (kept in lane i) and sd = sum_i du_i
+  // de = a_g gv + a_e e + a_d d ,  du = b_e e + b_d d   with d = s - e (u = d / (M-1))
+  float a_g = 0.f, a_e = 0.f, a_d = 0.f, b_e = 0.f, b_d = 0.f;     // this lane's row (row index == lane)
+  float4 sd[KCH];
+#pragma unroll
+  for (int c = 0; c < KCH; ++c) sd[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i0 = 0; i0 < M; i0 += kRowBatch) {
+    float4 v[kRowBatch][KCH];
+    float ne2[kRowBatch], nd2[kRowBatch], ed[kRowBatch], eg[kRowBatch];
+#pragma unroll
+    for (int r = 0; r < kRowBatch; ++r) {
+      ne2[r] = 0.f; nd2[r] = 0.f; ed[r] = 0.f; eg[r] = 0.f;
+#pragma unroll
+      for (int c = 0; c < KCH; ++c) {
+        const bool in = i0 + r < M;
+        v[r][c] = in ? __ldg(Ej + (size_t)(i0 + r) * (D / 4) + c * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 gv = in ? __ldg(Gj + (size_t)(i0 + r) * (D / 4) + c * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 e = v[r][c];
+        const float4 d = make_float4(s[c].x - e.x, s[c].y - e.y, s[c].z - e.z, s[c].w - e.w);
+        ne2[r] += dot4(e, e); nd2[r] += dot4(d, d); ed[r] += dot4(e, d); eg[r] += dot4(e, gv);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < kRowBatch; ++r) {
+        ne2[r] += __shfl_xor_sync(0xffffffffu, ne2[r], o);
+        nd2[r] += __shfl_xor_sync(0xffffffffu, nd2[r], o);
+        ed[r] += __shfl_xor_sync(0xffffffffu, ed[r], o);
+        eg[r] += __shfl_xor_sync(0xffffffffu, eg[r], o);
+      }
+#pragma unroll
+    for (int r = 0; r < kRowBatch; ++r) {
+      if (i0 + r < M) {
+        const int row = j * M + i0 + r;
+        const float ne = sqrtf(ne2[r]), nu = sqrtf(nd2[r]) * inv_m1;
+        const bool ok_e = ne >= kCosDelta, ok_u = nu >= kCosDelta;
+        const float inv_ne = 1.f / fmaxf(ne, kCosDelta), inv_nu = 1.f / fmaxf(nu, kCosDelta);
+        const float cdv = (ed[r] * inv_m1) * inv_ne * inv_nu;       // e_hat . u_hat
+        float Gd;                                                   // diagonal element of G
+        if (variant == GE2E_SOFTMAX) {
+          Gd = -g * __ldg(row_aux + row);                           // g (p_jj - 1)
+        } else {
+          const float sp = 1.f / (1.f + expf(-fmaf(w, __ldg(cos_diag + row) + eps, b)));
+          Gd = -g * sp * (1.f - sp);
+        }
+        const float dd = w * Gd;
+        const float proj_e = eg[r] * inv_ne + dd * cdv;             // e_hat . d e_hat
+        const float proj_u = dd * cdv;                              // u_hat . d u_hat
+        // d e_hat = gv + dd u_hat, d u_hat = dd e_hat; Jacobians of the two normalisations:
+        //   de = (deh - e_hat proj_e) / |e|  ->  gv inv_ne + d (dd inv_nu inv_m1 inv_ne) - e (proj_e inv_ne^2)
+        //   du = (duh - u_hat proj_u) / |u|  ->  e (dd inv_ne inv_nu) - d (proj_u inv_nu^2 inv_m1)
+        const float r_ag = inv_ne;
+        const float r_ad = dd * inv_nu * inv_m1 * inv_ne;
+        const float r_ae = ok_e ? -proj_e * inv_ne * inv_ne : 0.f;
+        const float r_be = dd * inv_ne * inv_nu;
+        const float r_bd = ok_u ? -proj_u * inv_nu * inv_nu * inv_m1 : 0.f;
+        if (lane == i0 + r) { a_g = r_ag; a_e = r_ae; a_d = r_ad; b_e = r_be; b_d = r_bd; }
+#pragma unroll
+        for (int c = 0; c < KCH; ++c) {
+          const float4 e = v[r][c];
+          sd[c].x += r_be * e.x + r_bd * (s[c].x - e.x); sd[c].y += r_be * e.y + r_bd * (s[c].y - e.y);
+          sd[c].z += r_be * e.z + r_bd * (s[c].z - e.z); sd[c].w += r_be * e.w + r_bd * (s[c].w - e.w);
+        }
+      }
+    }
+  }
+  // pass 3: dE_i = de_i + dc_j / M + (sd - du_i) / (M - 1)
+  float4* Oj = reinterpret_cast<float4*>(dE + (size_t)j * M * D) + lane;
+  for (int i = 0; i < M; ++i) {
+    const float r_ag = __shfl_sync(0xffffffffu, a_g, i), r_ae = __shfl_sync(0xffffffffu, a_e, i);
+    const float r_ad = __shfl_sync(0xffffffffu, a_d, i), r_be = __shfl_sync(0xffffffffu, b_e, i);
+    const float r_bd = __shfl_sync(0xffffffffu, b_d, i);
+#pragma unroll
+    for (int c = 0; c < KCH; ++c) {
+      const float4 e = __ldg(Ej + (size_t)i * (D / 4) + c * 32);
+      const float4 gv = __ldg(Gj + (size_t)i * (D / 4) + c * 32);
+      const float ev[4] = {e.x, e.y, e.z, e.w}, gg[4] = {gv.x, gv.y, gv.z, gv.w};
+      const float sv[4] = {s[c].x, s[c].y, s[c].z, s[c].w}, sdv[4] = {sd[c].x, sd[c].y, sd[c].z, sd[c].w};
+      const float bv[4] = {bc[c].x, bc[c].y, bc[c].z, bc[c].w};
+      float o[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float d = sv[t] - ev[t];
+        const float de = r_ag * gg[t] + r_ae * ev[t] + r_ad * d;
+        const float du = r_be * ev[t] + r_bd * d;
+        o[t] = de + bv[t] + (sdv[t] - du) * inv_m1;
+      }
+      Oj[(size_t)i * (D / 4) + c * 32] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // static helpers of the reference class
 // ------------------------------------------------------------------------------------------
@@ -681,8 +942,39 @@ int rows_per_cta(int D) { return kWarps * (D <= 256 ? 4 : (D <= 512 ? 2 : 1)); }
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
+bool warp_path_ok(int D, std::initializer_list<const void*> ptrs) {
+  if (D != 128 && D != 256 && D != 512) return false;
+  for (const void* q : ptrs)
+    if ((reinterpret_cast<uintptr_t>(q) & 15) != 0) return false;
+  return true;
+}
+
+template <int KCH>
+void launch_prep_warp(const float* E, int n_local, int M, bool rnd, float* e_hat, float* c_hat, float* cos_diag,
+                      float* accum, cudaStream_t st) {
+  const int grid = (n_local + kPrepWarps - 1) / kPrepWarps;
+  if (rnd) prep_warp_kernel<KCH, true><<<grid, kPrepWarps * 32, 0, st>>>(E, n_local, M, e_hat, c_hat, cos_diag, accum);
+  else prep_warp_kernel<KCH, false><<<grid, kPrepWarps * 32, 0, st>>>(E, n_local, M, e_hat, c_hat, cos_diag, accum);
+}
+
+template <int KCH>
+void launch_finalize_warp(const float* E, const float* dE_hat, const float* dC_hat, const float* cos_diag,
+                          const float* row_aux, int n_local, int M, const float* w, const float* b, float eps,
+                          int variant, const float* g, float* dE, cudaStream_t st) {
+  const int grid = (n_local + kPrepWarps - 1) / kPrepWarps;
+  finalize_warp_kernel<KCH><<<grid, kPrepWarps * 32, 0, st>>>(E, dE_hat, dC_hat, cos_diag, row_aux, n_local, M, w, b,
+                                                             eps, variant, g, dE);
+}
+
 int simt_prep(const float* E, int n_local, int M, int D, bool round_tf32_, float* e_hat,
               float* c_hat_local, float* cos_diag, float* accum, cudaStream_t st) {
+  if (warp_path_ok(D, {E, e_hat, c_hat_local})) {
+    if (D == 128) launch_prep_warp<1>(E, n_local, M, round_tf32_, e_hat, c_hat_local, cos_diag, accum, st);
+    else if (D == 256) launch_prep_warp<2>(E, n_local, M, round_tf32_, e_hat, c_hat_local, cos_diag, accum, st);
+    else launch_prep_warp<4>(E, n_local, M, round_tf32_, e_hat, c_hat_local, cos_diag, accum, st);
+    GE2E_LAUNCHED();
+    return GE2E_OK;
+  }
   const int Dp = (D + 3) & ~3;
   const size_t smem = (size_t)(M + 1) * Dp * sizeof(float);
   if (smem > 200 * 1024) return GE2E_ERR_UNSUPPORTED;
@@ -757,6 +1049,13 @@ int simt_bwd_finalize(const float* E, const float* dE_hat, const float* dC_hat_l
                       const float* cos_diag, const float* row_stat, const float* row_aux, int n_local, int M,
                       int D, const float* w, const float* b, float eps, int variant,
                       const float* grad_out, float* dE, cudaStream_t st) {
+  if (M <= 32 && warp_path_ok(D, {E, dE_hat, dC_hat_local, dE})) {
+    if (D == 128) launch_finalize_warp<1>(E, dE_hat, dC_hat_local, cos_diag, row_aux, n_local, M, w, b, eps, variant, grad_out, dE, st);
+    else if (D == 256) launch_finalize_warp<2>(E, dE_hat, dC_hat_local, cos_diag, row_aux, n_local, M, w, b, eps, variant, grad_out, dE, st);
+    else launch_finalize_warp<4>(E, dE_hat, dC_hat_local, cos_diag, row_aux, n_local, M, w, b, eps, variant, grad_out, dE, st);
+    GE2E_LAUNCHED();
+    return GE2E_OK;
+  }
   const int Dp = (D + 3) & ~3;
   const size_t smem = (size_t)(2 * M + 2) * Dp * sizeof(float);
   if (smem > 200 * 1024) return GE2E_ERR_UNSUPPORTED;
