@@ -1,5 +1,7 @@
 // C ABI of the B200-native GE2E loss: argument checking and path selection only.
 // See include/ge2e_b200.h for the contract and the reference lines each entry point replaces.
+#include <stdlib.h>
+
 #include <atomic>
 
 #include "ge2e_common.cuh"
@@ -9,6 +11,11 @@ static thread_local cudaError_t g_last_cuda_error = cudaSuccess;
 void set_cuda_error(cudaError_t e) { g_last_cuda_error = e; }
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+int debug_skip_mask() {
+  static int m = -1;
+  if (m < 0) { const char* e = getenv("GE2E_SKIP"); m = e ? atoi(e) : 0; }
+  return m;
+}
 }  // namespace ge2e
 
 using namespace ge2e;
@@ -79,15 +86,17 @@ int ge2e_b200_prep(const float* E, int n_local, int M, int D, int precision, flo
   int rc = check_shape(n_local, n_local, 0, M, D);
   if (rc != GE2E_OK) return rc;
   if ((rc = check_enum(GE2E_SOFTMAX, precision)) != GE2E_OK) return rc;
+  if (debug_skip_mask() & 1) return GE2E_OK;
   return simt_prep(E, n_local, M, D, precision == GE2E_TF32, e_hat, c_hat_local, cos_diag, accum,
                    (cudaStream_t)stream);
 }
 
-int ge2e_b200_fwd_rows(const float* e_hat, const float* c_hat_all, const float* cos_diag,
+static int fwd_rows_impl(const float* e_hat, const float* c_hat_all, const float* cos_diag,
                        int n_local, int n_total, int spk_offset, int M, int D, const float* w,
                        const float* b, float eps, int variant, int precision, float* row_stat,
                        int32_t* row_kstar, float* row_aux, float* loss_accum, float* per_row_out,
-                       float* sim_out, void* workspace, size_t workspace_bytes, ge2e_stream_t stream) {
+                       float* sim_out, void* workspace, size_t workspace_bytes, bool after_prep,
+                       ge2e_stream_t stream) {
   if (!e_hat || !c_hat_all || !cos_diag || !w || !b || !row_stat || !loss_accum)
     return GE2E_ERR_ARGUMENT;
   int rc = check_shape(n_local, n_total, spk_offset, M, D);
@@ -96,6 +105,7 @@ int ge2e_b200_fwd_rows(const float* e_hat, const float* c_hat_all, const float* 
   if (variant == GE2E_CONTRAST && !row_kstar) return GE2E_ERR_ARGUMENT;
   if (variant == GE2E_SOFTMAX && !row_aux) return GE2E_ERR_ARGUMENT;
   RowsArgs a{e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, b, eps, variant};
+  if (debug_skip_mask() & 2) return GE2E_OK;
   if (precision == GE2E_TF32 && tc_supported(n_local, n_total, M, D, variant)) {
     // the tensor-core path never materialises S: sim_out is an fp32-path feature
     if (sim_out != nullptr) return GE2E_ERR_UNSUPPORTED;
@@ -103,10 +113,20 @@ int ge2e_b200_fwd_rows(const float* e_hat, const float* c_hat_all, const float* 
         (workspace == nullptr && tc_workspace_bytes(n_local, n_total, M, D, variant) > 0))
       return GE2E_ERR_WORKSPACE;
     return tc_fwd_rows(a, row_stat, row_kstar, row_aux, loss_accum, per_row_out, workspace, workspace_bytes,
-                       (cudaStream_t)stream);
+                       after_prep, (cudaStream_t)stream);
   }
   return simt_fwd_rows(a, row_stat, row_kstar, row_aux, loss_accum, per_row_out, sim_out,
                        (cudaStream_t)stream);
+}
+
+int ge2e_b200_fwd_rows(const float* e_hat, const float* c_hat_all, const float* cos_diag,
+                       int n_local, int n_total, int spk_offset, int M, int D, const float* w,
+                       const float* b, float eps, int variant, int precision, float* row_stat,
+                       int32_t* row_kstar, float* row_aux, float* loss_accum, float* per_row_out,
+                       float* sim_out, void* workspace, size_t workspace_bytes, ge2e_stream_t stream) {
+  return fwd_rows_impl(e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, b, eps, variant,
+                       precision, row_stat, row_kstar, row_aux, loss_accum, per_row_out, sim_out, workspace,
+                       workspace_bytes, false, stream);
 }
 
 int ge2e_b200_bwd_rows(const float* e_hat, const float* c_hat_all, const float* cos_diag,
@@ -138,18 +158,27 @@ int ge2e_b200_bwd_rows(const float* e_hat, const float* c_hat_all, const float* 
                        (cudaStream_t)stream);
 }
 
-int ge2e_b200_bwd_finalize(const float* E, const float* dE_hat, const float* dC_hat_local,
+static int bwd_finalize_impl(const float* E, const float* dE_hat, const float* dC_hat_local,
                            const float* cos_diag, const float* row_stat, const float* row_aux,
                            int n_local, int M, int D, const float* w, const float* b, float eps,
-                           int variant, const float* grad_out, float* dE, ge2e_stream_t stream) {
+                           int variant, const float* grad_out, float* dE, bool pdl, ge2e_stream_t stream) {
   if (!E || !dE_hat || !dC_hat_local || !cos_diag || !row_stat || !w || !b || !grad_out || !dE)
     return GE2E_ERR_ARGUMENT;
   if (variant == GE2E_SOFTMAX && !row_aux) return GE2E_ERR_ARGUMENT;
   int rc = check_shape(n_local, n_local, 0, M, D);
   if (rc != GE2E_OK) return rc;
   if ((rc = check_enum(variant, GE2E_FP32)) != GE2E_OK) return rc;
+  if (debug_skip_mask() & 16) return GE2E_OK;
   return simt_bwd_finalize(E, dE_hat, dC_hat_local, cos_diag, row_stat, row_aux, n_local, M, D, w, b, eps,
-                           variant, grad_out, dE, (cudaStream_t)stream);
+                           variant, grad_out, dE, pdl, (cudaStream_t)stream);
+}
+
+int ge2e_b200_bwd_finalize(const float* E, const float* dE_hat, const float* dC_hat_local,
+                           const float* cos_diag, const float* row_stat, const float* row_aux,
+                           int n_local, int M, int D, const float* w, const float* b, float eps,
+                           int variant, const float* grad_out, float* dE, ge2e_stream_t stream) {
+  return bwd_finalize_impl(E, dE_hat, dC_hat_local, cos_diag, row_stat, row_aux, n_local, M, D, w, b, eps,
+                           variant, grad_out, dE, false, stream);
 }
 
 int ge2e_b200_forward(const float* E, int N, int M, int D, const float* w, const float* b, float eps,
@@ -157,11 +186,20 @@ int ge2e_b200_forward(const float* E, int N, int M, int D, const float* w, const
                       float* row_stat, int32_t* row_kstar, float* row_aux, float* accum, void* workspace,
                       size_t workspace_bytes, ge2e_stream_t stream) {
   if (!accum) return GE2E_ERR_ARGUMENT;
-  int rc = ge2e_b200_prep(E, N, M, D, precision, e_hat, c_hat, cos_diag, accum, stream);
+  int rc = check_enum(variant, precision);
   if (rc != GE2E_OK) return rc;
-  return ge2e_b200_fwd_rows(e_hat, c_hat, cos_diag, N, N, 0, M, D, w, b, eps, variant, precision,
-                            row_stat, row_kstar, row_aux, accum, nullptr, nullptr, workspace, workspace_bytes,
-                            stream);
+  // tensor-core path: zero the stream-K bookkeeping BEFORE prep so that the two kernels are adjacent
+  // in the stream and the second one can be launched programmatically under the first one's tail
+  const bool tc = precision == GE2E_TF32 && N > 0 && M >= 2 && D > 0 && tc_supported(N, N, M, D, variant);
+  if (tc) {
+    if (workspace == nullptr) return GE2E_ERR_WORKSPACE;
+    if ((rc = tc_fwd_zero_workspace(N, N, M, D, variant, workspace, workspace_bytes, (cudaStream_t)stream)) != GE2E_OK)
+      return rc;
+  }
+  rc = ge2e_b200_prep(E, N, M, D, precision, e_hat, c_hat, cos_diag, accum, stream);
+  if (rc != GE2E_OK) return rc;
+  return fwd_rows_impl(e_hat, c_hat, cos_diag, N, N, 0, M, D, w, b, eps, variant, precision, row_stat, row_kstar,
+                       row_aux, accum, nullptr, nullptr, workspace, workspace_bytes, tc, stream);
 }
 
 int ge2e_b200_backward(const float* E, const float* e_hat, const float* c_hat, const float* cos_diag,
@@ -174,8 +212,10 @@ int ge2e_b200_backward(const float* E, const float* e_hat, const float* c_hat, c
                               variant, precision, grad_out, dE_hat, dC_hat, accum + 1, workspace,
                               workspace_bytes, stream);
   if (rc != GE2E_OK) return rc;
-  return ge2e_b200_bwd_finalize(E, dE_hat, dC_hat, cos_diag, row_stat, row_aux, N, M, D, w, b, eps, variant,
-                                grad_out, dE, stream);
+  // the finalize kernel directly follows the dC_hat tensor-core kernel: programmatic launch
+  const bool tc = precision == GE2E_TF32 && variant == GE2E_SOFTMAX && tc_supported(N, N, M, D, variant);
+  return bwd_finalize_impl(E, dE_hat, dC_hat, cos_diag, row_stat, row_aux, N, M, D, w, b, eps, variant,
+                           grad_out, dE, tc, stream);
 }
 
 int ge2e_b200_centroids(const float* E, int N, int M, int D, float* C, ge2e_stream_t stream) {

@@ -47,6 +47,13 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Programmatic dependent launch: a kernel launched with launch_pdl() may start while its stream
+// predecessor is still running.  pdl_trigger() lets the successor's CTAs be scheduled as soon as
+// every CTA of this grid has executed it (or exited); pdl_wait() blocks until the predecessor grid
+// has completed and its writes are visible.  Both are no-ops without the launch attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float round_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -91,6 +98,23 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;
 }
 
+// cudaLaunchKernelEx with the programmatic-stream-serialization attribute (see pdl_wait above)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                              Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// GE2E_SKIP (debug, timing only): bitmask of kernels NOT to launch -- 1 prep, 2 forward rows, 4 dE_hat,
+// 8 dC_hat, 16 finalize.  Results are garbage; scripts/stage_costs.py uses it to price each kernel in situ.
+int debug_skip_mask();
+
 // ---- launchers implemented in ge2e_simt.cu ------------------------------------------------
 struct RowsArgs {
   const float* e_hat;      // [U_local, D]
@@ -114,7 +138,7 @@ int simt_bwd_finalize(const float* E, const float* dE_hat, const float* dC_hat_l
                       const float* cos_diag, const float* row_stat, const float* row_aux,
                       int n_local, int M, int D,
                       const float* w, const float* b, float eps, int variant,
-                      const float* grad_out, float* dE, cudaStream_t st);
+                      const float* grad_out, float* dE, bool pdl, cudaStream_t st);
 int simt_centroids(const float* E, int N, int M, int D, float* C, cudaStream_t st);
 int simt_utterance_centroids(const float* E, int N, int M, int D, float* Uc, cudaStream_t st);
 int simt_calc_loss(const float* S, int N, int M, float eps, int variant, float* loss,
@@ -125,8 +149,11 @@ int simt_normalize_rows(const float* X, int rows, int D, float* Y, cudaStream_t 
 bool tc_supported(int n_local, int n_total, int M, int D, int variant);
 void tc_set_trace(unsigned long long* device_buf, int mode);
 size_t tc_workspace_bytes(int n_local, int n_total, int M, int D, int variant);
+int tc_fwd_zero_workspace(int n_local, int n_total, int M, int D, int variant, void* ws, size_t ws_bytes,
+                          cudaStream_t st);
 int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* row_aux,
-                float* loss_accum, float* per_row_out, void* ws, size_t ws_bytes, cudaStream_t st);
+                float* loss_accum, float* per_row_out, void* ws, size_t ws_bytes, bool after_prep,
+                cudaStream_t st);
 int tc_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kstar,
                 const float* row_aux, const float* grad_out, float* dE_hat, float* dC_hat_partial, float* dwdb_accum,
                 void* ws, size_t ws_bytes, cudaStream_t st);

@@ -144,6 +144,7 @@ prep_kernel(const float* __restrict__ E, int M, int D, int Dp, float* __restrict
 // ------------------------------------------------------------------------------------------
 constexpr int kPrepWarps = 4;
 constexpr int kRowBatch = 4;   // rows in flight per lane (KCH float4 loads each)
+constexpr int kRegRows = 16;   // register-resident variants hold up to this many rows per speaker
 
 template <int KCH, bool ROUND>
 __global__ void __launch_bounds__(kPrepWarps * 32)
@@ -152,6 +153,7 @@ prep_warp_kernel(const float* __restrict__ E, int n_local, int M, float* __restr
   constexpr int D = KCH * 128;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int j = blockIdx.x * kPrepWarps + wid;
+  pdl_trigger();     // the forward tensor-core kernel may set itself up while this grid runs
   if (blockIdx.x == 0 && threadIdx.x < 4 && accum != nullptr) accum[threadIdx.x] = 0.f;
   if (j >= n_local) return;
   const float4* Ej = reinterpret_cast<const float4*>(E + (size_t)j * M * D) + lane;   // + i * (D/4) + c * 32
@@ -234,6 +236,103 @@ prep_warp_kernel(const float* __restrict__ E, int n_local, int M, float* __restr
     if (((i0 + kRowBatch) & 31) == 0 || i0 + kRowBatch >= M) {
       const int base = (i0 + kRowBatch - 1) & ~31;
       if (base + lane < M) cos_diag[(size_t)j * M + base + lane] = my_cos;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1 (register-resident variant, M <= 16): as prep_warp_kernel, but every row of the speaker is
+// loaded ONCE, all loads in flight together (16 KCH 16-byte loads per lane), and kept in
+// registers.  The per-row sums go through a transposing butterfly (reduce16_transposed): lane l
+// ends up with the totals of row rev4(l & 15), so the square roots / reciprocals of all rows are
+// evaluated once, lane-parallel, instead of row after row by the whole warp.  With ~7 warps per
+// SM the kernel time is the latency of one warp's dependency chain; this is what keeps it short.
+// ------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int rev4(int i) {
+  return ((i & 1) << 3) | ((i & 2) << 1) | ((i & 4) >> 1) | ((i & 8) >> 3);
+}
+// warp total of v[rev4(lane & 15)]: 16 shuffles for 16 values
+__device__ __forceinline__ float reduce16_transposed(const float (&v)[16], int lane) {
+  float a[8], b[4], c[2];
+  const bool u1 = (lane & 1) != 0, u2 = (lane & 2) != 0, u4 = (lane & 4) != 0, u8 = (lane & 8) != 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) a[q] = (u1 ? v[q + 8] : v[q]) + __shfl_xor_sync(0xffffffffu, u1 ? v[q] : v[q + 8], 1);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) b[q] = (u2 ? a[q + 4] : a[q]) + __shfl_xor_sync(0xffffffffu, u2 ? a[q] : a[q + 4], 2);
+#pragma unroll
+  for (int q = 0; q < 2; ++q) c[q] = (u4 ? b[q + 2] : b[q]) + __shfl_xor_sync(0xffffffffu, u4 ? b[q] : b[q + 2], 4);
+  const float e = (u8 ? c[1] : c[0]) + __shfl_xor_sync(0xffffffffu, u8 ? c[0] : c[1], 8);
+  return e + __shfl_xor_sync(0xffffffffu, e, 16);
+}
+
+template <int KCH, bool ROUND>
+__global__ void __launch_bounds__(kPrepWarps * 32)
+prep_reg_kernel(const float* __restrict__ E, int n_local, int M, float* __restrict__ e_hat,
+                float* __restrict__ c_hat, float* __restrict__ cos_diag, float* __restrict__ accum) {
+  constexpr int D = KCH * 128, R = kRegRows;
+  static_assert(R == 16, "reduce16_transposed handles 16 rows");
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int j = blockIdx.x * kPrepWarps + wid;
+  pdl_trigger();     // the forward tensor-core kernel may set itself up while this grid runs
+  if (blockIdx.x == 0 && threadIdx.x < 4 && accum != nullptr) accum[threadIdx.x] = 0.f;
+  if (j >= n_local) return;
+  const float4* Ej = reinterpret_cast<const float4*>(E + (size_t)j * M * D) + lane;
+  float4 v[R][KCH];
+#pragma unroll
+  for (int i = 0; i < R; ++i)
+#pragma unroll
+    for (int c = 0; c < KCH; ++c)
+      v[i][c] = (i < M) ? __ldg(Ej + (size_t)i * (D / 4) + c * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 s[KCH];
+#pragma unroll
+  for (int c = 0; c < KCH; ++c) {
+    s[c] = v[0][c];
+#pragma unroll
+    for (int i = 1; i < R; ++i) { s[c].x += v[i][c].x; s[c].y += v[i][c].y; s[c].z += v[i][c].z; s[c].w += v[i][c].w; }
+  }
+  const float inv_m = 1.f / (float)M, inv_m1 = 1.f / (float)(M - 1);
+  float ss = 0.f;
+#pragma unroll
+  for (int c = 0; c < KCH; ++c) ss += dot4(s[c], s[c]);
+  ss = warp_sum(ss);
+  const float sc = inv_m / fmaxf(sqrtf(ss) * inv_m, kCosDelta);       // s3:37 + normalisation
+  float4* Cj = reinterpret_cast<float4*>(c_hat + (size_t)j * D) + lane;
+#pragma unroll
+  for (int c = 0; c < KCH; ++c) {
+    float4 o = make_float4(s[c].x * sc, s[c].y * sc, s[c].z * sc, s[c].w * sc);
+    if (ROUND) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+    Cj[c * 32] = o;
+  }
+  // |e|^2, |s - e|^2, e.(s - e) of every row (u = (s - e) / (M - 1): s3:105-111)
+  float ne2[R], nd2[R], ed[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    ne2[i] = 0.f; nd2[i] = 0.f; ed[i] = 0.f;
+#pragma unroll
+    for (int c = 0; c < KCH; ++c) {
+      const float4 e = v[i][c];
+      const float4 d = make_float4(s[c].x - e.x, s[c].y - e.y, s[c].z - e.z, s[c].w - e.w);
+      ne2[i] += dot4(e, e); nd2[i] += dot4(d, d); ed[i] += dot4(e, d);
+    }
+  }
+  const float t_ne2 = reduce16_transposed(ne2, lane), t_nd2 = reduce16_transposed(nd2, lane);
+  const float t_ed = reduce16_transposed(ed, lane);
+  const int my_row = rev4(lane & 15);
+  const float inv_ne = 1.f / fmaxf(sqrtf(t_ne2), kCosDelta);
+  const float inv_nu = 1.f / fmaxf(sqrtf(t_nd2) * inv_m1, kCosDelta);
+  if (lane < 16 && my_row < M) cos_diag[(size_t)j * M + my_row] = (t_ed * inv_m1) * inv_ne * inv_nu;   // s3:57
+  float4* Oj = reinterpret_cast<float4*>(e_hat + (size_t)j * M * D) + lane;
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    if (i < M) {      // warp-uniform
+      const float k = __shfl_sync(0xffffffffu, inv_ne, rev4(i));
+#pragma unroll
+      for (int c = 0; c < KCH; ++c) {
+        float4 e = v[i][c];
+        e.x *= k; e.y *= k; e.z *= k; e.w *= k;
+        if (ROUND) { e.x = round_tf32(e.x); e.y = round_tf32(e.y); e.z = round_tf32(e.z); e.w = round_tf32(e.w); }
+        Oj[(size_t)i * (D / 4) + c * 32] = e;
+      }
     }
   }
 }
@@ -696,6 +795,7 @@ finalize_warp_kernel(const float* __restrict__ E, const float* __restrict__ dE_h
   constexpr int D = KCH * 128;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int j = blockIdx.x * kPrepWarps + wid;
+  pdl_wait();        // launched with the PDL attribute: dE_hat / dC_hat come from the preceding grids
   if (j >= n_local) return;
   const float w = __ldg(wp), b = __ldg(bp), g = __ldg(gp);
   const float4* Ej = reinterpret_cast<const float4*>(E + (size_t)j * M * D) + lane;
@@ -836,6 +936,151 @@ finalize_warp_kernel(const float* __restrict__ E, const float* __restrict__ dE_h
 }
 
 // ------------------------------------------------------------------------------------------
+// K4 (register-resident variant, M <= 16): the speaker's E rows are loaded once (before the
+// programmatic-launch wait: E is not produced by the preceding grids) and stay in registers;
+// dE_hat rows are read twice (L2 / L1 hits).  Row sums through reduce16_transposed, the per-row
+// Jacobian coefficients are computed lane-parallel (lane l owns row rev4(l & 15)) and broadcast.
+//   de_i = a_g gv_i + a_e e_i + a_d d_i ,  du_i = b_e e_i + b_d d_i ,  d_i = s - e_i
+//   dE_i = de_i + dc_j / M + (sum_i' du_i' - du_i) / (M - 1)
+// ------------------------------------------------------------------------------------------
+template <int KCH>
+__global__ void __launch_bounds__(kPrepWarps * 32)
+finalize_reg_kernel(const float* __restrict__ E, const float* __restrict__ dE_hat,
+                    const float* __restrict__ dC_hat, const float* __restrict__ cos_diag,
+                    const float* __restrict__ row_aux, int n_local, int M,
+                    const float* __restrict__ wp, const float* __restrict__ bp, float eps, int variant,
+                    const float* __restrict__ gp, float* __restrict__ dE) {
+  constexpr int D = KCH * 128, R = kRegRows;
+  static_assert(R == 16, "reduce16_transposed handles 16 rows");
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int j = blockIdx.x * kPrepWarps + wid;
+  const bool active = j < n_local;
+  float4 v[R][KCH];
+  const float4* Ej = reinterpret_cast<const float4*>(E + (size_t)(active ? j : 0) * M * D) + lane;
+#pragma unroll
+  for (int i = 0; i < R; ++i)
+#pragma unroll
+    for (int c = 0; c < KCH; ++c)
+      v[i][c] = (active && i < M) ? __ldg(Ej + (size_t)i * (D / 4) + c * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+  pdl_wait();        // launched with the PDL attribute: dE_hat / dC_hat come from the preceding grids
+  if (!active) return;
+  const float w = __ldg(wp), b = __ldg(bp), g = __ldg(gp);
+  const float4* Gj = reinterpret_cast<const float4*>(dE_hat + (size_t)j * M * D) + lane;
+  float4 s[KCH];
+#pragma unroll
+  for (int c = 0; c < KCH; ++c) {
+    s[c] = v[0][c];
+#pragma unroll
+    for (int i = 1; i < R; ++i) { s[c].x += v[i][c].x; s[c].y += v[i][c].y; s[c].z += v[i][c].z; s[c].w += v[i][c].w; }
+  }
+  float ne2[R], nd2[R], ed[R], eg[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    ne2[i] = 0.f; nd2[i] = 0.f; ed[i] = 0.f; eg[i] = 0.f;
+#pragma unroll
+    for (int c = 0; c < KCH; ++c) {
+      const float4 gv = (i < M) ? __ldcg(Gj + (size_t)i * (D / 4) + c * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 e = v[i][c];
+      const float4 d = make_float4(s[c].x - e.x, s[c].y - e.y, s[c].z - e.z, s[c].w - e.w);
+      ne2[i] += dot4(e, e); nd2[i] += dot4(d, d); ed[i] += dot4(e, d); eg[i] += dot4(e, gv);
+    }
+  }
+  const float inv_m = 1.f / (float)M, inv_m1 = 1.f / (float)(M - 1);
+  // centroid Jacobian: bc = dc_j / M with dc = (dC_hat - c_hat (c_hat . dC_hat)) / |c|  (or dC_hat / delta)
+  float4 bc[KCH];
+  {
+    float4 dch[KCH];
+    float ss = 0.f, pr = 0.f;
+#pragma unroll
+    for (int c = 0; c < KCH; ++c) {
+      dch[c] = __ldcg(reinterpret_cast<const float4*>(dC_hat + (size_t)j * D) + lane + c * 32);
+      ss += dot4(s[c], s[c]);
+      pr += dot4(s[c], dch[c]);
+    }
+    ss = warp_sum(ss); pr = warp_sum(pr);
+    const float nc = sqrtf(ss) * inv_m;
+    const bool ok = nc >= kCosDelta;
+    const float inv = 1.f / fmaxf(nc, kCosDelta);
+    const float proj = (pr * inv_m) * inv;          // c_hat . dC_hat
+    const float k1 = inv * inv_m;
+    const float k2 = ok ? proj * inv * inv * inv_m * inv_m : 0.f;
+#pragma unroll
+    for (int c = 0; c < KCH; ++c) {
+      bc[c].x = dch[c].x * k1 - s[c].x * k2; bc[c].y = dch[c].y * k1 - s[c].y * k2;
+      bc[c].z = dch[c].z * k1 - s[c].z * k2; bc[c].w = dch[c].w * k1 - s[c].w * k2;
+    }
+  }
+  const float t_ne2 = reduce16_transposed(ne2, lane), t_nd2 = reduce16_transposed(nd2, lane);
+  const float t_ed = reduce16_transposed(ed, lane), t_eg = reduce16_transposed(eg, lane);
+  // this lane's row
+  const int my_row = rev4(lane & 15);
+  float a_g, a_e, a_d, b_e, b_d;
+  {
+    const int row = j * M + min(my_row, M - 1);
+    const float ne = sqrtf(t_ne2), nu = sqrtf(t_nd2) * inv_m1;
+    const bool ok_e = ne >= kCosDelta, ok_u = nu >= kCosDelta;
+    const float inv_ne = 1.f / fmaxf(ne, kCosDelta), inv_nu = 1.f / fmaxf(nu, kCosDelta);
+    const float cdv = (t_ed * inv_m1) * inv_ne * inv_nu;          // e_hat . u_hat
+    float Gd;                                                     // diagonal element of G
+    if (variant == GE2E_SOFTMAX) {
+      Gd = -g * __ldcg(row_aux + row);                            // g (p_jj - 1)
+    } else {
+      const float sp = 1.f / (1.f + expf(-fmaf(w, __ldg(cos_diag + row) + eps, b)));
+      Gd = -g * sp * (1.f - sp);
+    }
+    const float dd = w * Gd;
+    const float proj_e = t_eg * inv_ne + dd * cdv;                // e_hat . d e_hat
+    const float proj_u = dd * cdv;                                // u_hat . d u_hat
+    a_g = inv_ne;
+    a_d = dd * inv_nu * inv_m1 * inv_ne;
+    a_e = ok_e ? -proj_e * inv_ne * inv_ne : 0.f;
+    b_e = dd * inv_ne * inv_nu;
+    b_d = ok_u ? -proj_u * inv_nu * inv_nu * inv_m1 : 0.f;
+  }
+  float4 sd[KCH];
+#pragma unroll
+  for (int c = 0; c < KCH; ++c) sd[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    if (i < M) {
+      const float r_be = __shfl_sync(0xffffffffu, b_e, rev4(i)), r_bd = __shfl_sync(0xffffffffu, b_d, rev4(i));
+#pragma unroll
+      for (int c = 0; c < KCH; ++c) {
+        const float4 e = v[i][c];
+        sd[c].x += r_be * e.x + r_bd * (s[c].x - e.x); sd[c].y += r_be * e.y + r_bd * (s[c].y - e.y);
+        sd[c].z += r_be * e.z + r_bd * (s[c].z - e.z); sd[c].w += r_be * e.w + r_bd * (s[c].w - e.w);
+      }
+    }
+  }
+  float4* Oj = reinterpret_cast<float4*>(dE + (size_t)j * M * D) + lane;
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    if (i < M) {
+      const float r_ag = __shfl_sync(0xffffffffu, a_g, rev4(i)), r_ae = __shfl_sync(0xffffffffu, a_e, rev4(i));
+      const float r_ad = __shfl_sync(0xffffffffu, a_d, rev4(i)), r_be = __shfl_sync(0xffffffffu, b_e, rev4(i));
+      const float r_bd = __shfl_sync(0xffffffffu, b_d, rev4(i));
+#pragma unroll
+      for (int c = 0; c < KCH; ++c) {
+        const float4 e = v[i][c];
+        const float4 gv = __ldcg(Gj + (size_t)i * (D / 4) + c * 32);
+        const float ev[4] = {e.x, e.y, e.z, e.w}, gg[4] = {gv.x, gv.y, gv.z, gv.w};
+        const float sv[4] = {s[c].x, s[c].y, s[c].z, s[c].w}, sdv[4] = {sd[c].x, sd[c].y, sd[c].z, sd[c].w};
+        const float bv[4] = {bc[c].x, bc[c].y, bc[c].z, bc[c].w};
+        float o[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float d = sv[t] - ev[t];
+          const float de = r_ag * gg[t] + r_ae * ev[t] + r_ad * d;
+          const float du = r_be * ev[t] + r_bd * d;
+          o[t] = de + bv[t] + (sdv[t] - du) * inv_m1;
+        }
+        Oj[(size_t)i * (D / 4) + c * 32] = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // static helpers of the reference class
 // ------------------------------------------------------------------------------------------
 __global__ void centroids_kernel(const float* __restrict__ E, int M, int D, float* __restrict__ C) {
@@ -953,6 +1198,12 @@ template <int KCH>
 void launch_prep_warp(const float* E, int n_local, int M, bool rnd, float* e_hat, float* c_hat, float* cos_diag,
                       float* accum, cudaStream_t st) {
   const int grid = (n_local + kPrepWarps - 1) / kPrepWarps;
+  if (KCH <= 2 && M <= kRegRows) {
+    constexpr int K2 = KCH <= 2 ? KCH : 1;    // the register-resident variant is only instantiated for D <= 256
+    if (rnd) prep_reg_kernel<K2, true><<<grid, kPrepWarps * 32, 0, st>>>(E, n_local, M, e_hat, c_hat, cos_diag, accum);
+    else prep_reg_kernel<K2, false><<<grid, kPrepWarps * 32, 0, st>>>(E, n_local, M, e_hat, c_hat, cos_diag, accum);
+    return;
+  }
   if (rnd) prep_warp_kernel<KCH, true><<<grid, kPrepWarps * 32, 0, st>>>(E, n_local, M, e_hat, c_hat, cos_diag, accum);
   else prep_warp_kernel<KCH, false><<<grid, kPrepWarps * 32, 0, st>>>(E, n_local, M, e_hat, c_hat, cos_diag, accum);
 }
@@ -960,10 +1211,16 @@ void launch_prep_warp(const float* E, int n_local, int M, bool rnd, float* e_hat
 template <int KCH>
 void launch_finalize_warp(const float* E, const float* dE_hat, const float* dC_hat, const float* cos_diag,
                           const float* row_aux, int n_local, int M, const float* w, const float* b, float eps,
-                          int variant, const float* g, float* dE, cudaStream_t st) {
+                          int variant, const float* g, float* dE, bool pdl, cudaStream_t st) {
   const int grid = (n_local + kPrepWarps - 1) / kPrepWarps;
-  finalize_warp_kernel<KCH><<<grid, kPrepWarps * 32, 0, st>>>(E, dE_hat, dC_hat, cos_diag, row_aux, n_local, M, w, b,
-                                                             eps, variant, g, dE);
+  if (KCH <= 2 && M <= kRegRows) {
+    constexpr int K2 = KCH <= 2 ? KCH : 1;
+    launch_pdl(finalize_reg_kernel<K2>, dim3(grid), dim3(kPrepWarps * 32), 0, st, pdl, E, dE_hat, dC_hat,
+               cos_diag, row_aux, n_local, M, w, b, eps, variant, g, dE);
+    return;
+  }
+  launch_pdl(finalize_warp_kernel<KCH>, dim3(grid), dim3(kPrepWarps * 32), 0, st, pdl, E, dE_hat, dC_hat, cos_diag,
+             row_aux, n_local, M, w, b, eps, variant, g, dE);
 }
 
 int simt_prep(const float* E, int n_local, int M, int D, bool round_tf32_, float* e_hat,
@@ -1048,11 +1305,11 @@ int simt_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_k
 int simt_bwd_finalize(const float* E, const float* dE_hat, const float* dC_hat_local,
                       const float* cos_diag, const float* row_stat, const float* row_aux, int n_local, int M,
                       int D, const float* w, const float* b, float eps, int variant,
-                      const float* grad_out, float* dE, cudaStream_t st) {
+                      const float* grad_out, float* dE, bool pdl, cudaStream_t st) {
   if (M <= 32 && warp_path_ok(D, {E, dE_hat, dC_hat_local, dE})) {
-    if (D == 128) launch_finalize_warp<1>(E, dE_hat, dC_hat_local, cos_diag, row_aux, n_local, M, w, b, eps, variant, grad_out, dE, st);
-    else if (D == 256) launch_finalize_warp<2>(E, dE_hat, dC_hat_local, cos_diag, row_aux, n_local, M, w, b, eps, variant, grad_out, dE, st);
-    else launch_finalize_warp<4>(E, dE_hat, dC_hat_local, cos_diag, row_aux, n_local, M, w, b, eps, variant, grad_out, dE, st);
+    if (D == 128) launch_finalize_warp<1>(E, dE_hat, dC_hat_local, cos_diag, row_aux, n_local, M, w, b, eps, variant, grad_out, dE, pdl, st);
+    else if (D == 256) launch_finalize_warp<2>(E, dE_hat, dC_hat_local, cos_diag, row_aux, n_local, M, w, b, eps, variant, grad_out, dE, pdl, st);
+    else launch_finalize_warp<4>(E, dE_hat, dC_hat_local, cos_diag, row_aux, n_local, M, w, b, eps, variant, grad_out, dE, pdl, st);
     GE2E_LAUNCHED();
     return GE2E_OK;
   }

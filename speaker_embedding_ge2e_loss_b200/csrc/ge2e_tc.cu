@@ -23,8 +23,8 @@
 //
 // Work is a flat list of (owner group, stream unit) pairs cut into equal contiguous ranges over
 // the clusters (stream-K): a cluster whose range covers only part of an owner group publishes a
-// partial result (FWD: (max, sum) per row, merged by the last CTA to finish that tile; BWD: fp32
-// vector atomics into a zeroed output).
+// partial result (FWD: (max, sum) per row, merged by the last CTA to finish that tile; BWD: the
+// accumulator is added into a zeroed output by a TMA reduce, cp.reduce.async.bulk).
 //
 // Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
 // warps 4-11 = epilogue (TMEM lane quarter = warp % 4, column half = (warp - 4) / 4: two threads
@@ -75,6 +75,7 @@ enum {
   BAR_G_FULL = BAR_S_EMPTY + 2,         // [2] BWD: G written back to TMEM             (leader)
   BAR_ACC_FULL = BAR_G_FULL + 2,        // BWD: accumulator complete for this segment  (every CTA)
   BAR_ACC_EMPTY,                        // BWD: accumulator drained                    (leader)
+  BAR_A_FREE,                           // BWD: accumulator flush no longer reads the owner area
   BAR_COUNT
 };
 
@@ -104,6 +105,7 @@ struct TcParams {
   float* acc_out;             // dE_hat [n_own, D] or dC_hat_partial [n_own, D]
   float* dwdb;                // BWD_DE
   unsigned long long* trace;  // debug: [CTA][3 roles][kTraceEvents] globaltimer stamps, or nullptr
+  int pdl_wait_at_end;        // 1: no input comes from the stream predecessor (BWD_DC after BWD_DE)
   int dbg;                    // debug (GE2E_TC_DEBUG): 1 = no TMA for stream stages, 2 = no MMA issue,
                               //                        4 = epilogue skips the math (results are garbage)
 };
@@ -140,7 +142,8 @@ __device__ __forceinline__ int cluster_of_pair(long long gp, long long GP, int N
 template <int MODE, int VARIANT, int CG>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constant__ CUtensorMap tm_strk,
-                const __grid_constant__ CUtensorMap tm_strmn, const TcParams p) {
+                const __grid_constant__ CUtensorMap tm_strmn, const __grid_constant__ CUtensorMap tm_out,
+                const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr bool kBwd = (MODE != TC_FWD);
   constexpr int kStageBytes = 32768 / CG;
@@ -171,7 +174,7 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_own);
     prefetch_tmap(&tm_strk);
-    if (kBwd) prefetch_tmap(&tm_strmn);
+    if (kBwd) { prefetch_tmap(&tm_strmn); prefetch_tmap(&tm_out); }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(bar(BAR_FULL + i), 1); mbar_init(bar(BAR_EMPTY + i), 1); }
@@ -184,6 +187,7 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
     }
     mbar_init(bar(BAR_ACC_FULL), 1);
     mbar_init(bar(BAR_ACC_EMPTY), kEpiArrivals);
+    mbar_init(bar(BAR_A_FREE), 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -195,6 +199,9 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
   if (CG > 1) cluster_sync_all();     // the peer's barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem = tail->tmem_base;
+  // programmatic dependent launch: everything above overlapped the stream predecessor's tail
+  pdl_trigger();
+  if (!p.pdl_wait_at_end) pdl_wait();
 
   // ---- the walk over this cluster's (owner group, stream unit) range, identical in every role
   // segment = maximal run of pairs inside one owner group; step = 1 or 2 (FWD) units of it
@@ -259,7 +266,10 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
       int og, s0, s1;
       seg_bounds(gp, og, s0, s1);
       const int ot = og * CG + cr;      // may be >= OT in the last group: TMA zero-fills, nothing is stored
-      if (sg > 0) mbar_wait(bar(BAR_A_EMPTY), (sg - 1) & 1);
+      if (sg > 0) {
+        mbar_wait(bar(BAR_A_EMPTY), (sg - 1) & 1);
+        if (kBwd) mbar_wait(bar(BAR_A_FREE), (sg - 1) & 1);   // the accumulator flush stages through the owner area
+      }
       tr.mark();   // owner tile issue
       if (elect_one()) {
         for (int ks = 0; ks < kslabs; ++ks) {
@@ -623,25 +633,39 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
         if (MODE == TC_BWD_DE && ovalid && s0 == 0 && half == 0) db_acc -= g * eps * ex2(-lse2);   // item 12
         mbar_wait(bar(BAR_ACC_FULL), sg & 1);
         tc_fence_after();
-        float* out = p.acc_out + static_cast<size_t>(orow) * p.D;
+        // TMEM -> registers -> owner area of shared memory (free: every MMA of the segment has
+        // completed) in the 128B-swizzled slab layout -> one TMA store per 32-column slab.  A range
+        // that covers the whole owner group stores, a partial range adds into the zeroed output
+        // (cp.reduce.async.bulk: the fp32 add happens at the L2).  Rows past n_own are clipped.
+        fence_proxy_async_smem();
         const int ch0 = half ? kslabs / 2 : 0, ch1 = half ? kslabs : kslabs / 2;
         for (int ch = ch0; ch < ch1; ++ch) {
           uint32_t v[32];
           tmem_ld32(tmem + lane_addr + 2 * kUnit + ch * 32, v);
           tmem_ld_wait();
-          if (ovalid) {
+          const uint32_t row_smem = a_smem + ch * kSlabBytes + trow * 128;
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              float4 o = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
-                                     __uint_as_float(v[i + 3]));
-              float4* dst = reinterpret_cast<float4*>(out + ch * 32 + i);
-              if (full) *dst = o; else atomicAdd(dst, o);   // partial segments add into the zeroed output
-            }
-          }
+          for (int c = 0; c < 8; ++c)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_smem + ((c ^ (trow & 7)) << 4)),
+                         "r"(v[4 * c]), "r"(v[4 * c + 1]), "r"(v[4 * c + 2]), "r"(v[4 * c + 3])
+                         : "memory");
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) arrive_leader(acc_empty);
+        fence_proxy_async_smem();
+        named_bar_sync(1, kEpiThreads);
+        if (ew == 0 && lane == 0) {
+          if (tile_valid) {
+            for (int ks = 0; ks < kslabs; ++ks) {
+              if (full) tma_store_2d(&tm_out, ks * kSlabCols, ot * kTile, a_smem + ks * kSlabBytes);
+              else tma_reduce_add_2d(&tm_out, ks * kSlabCols, ot * kTile, a_smem + ks * kSlabBytes);
+            }
+            tma_store_commit();
+            tma_store_wait_read();
+          }
+          mbar_arrive(bar(BAR_A_FREE));
+        }
       }
       gp += s1 - s0;
       tr.mark();   // segment flushed
@@ -672,6 +696,7 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
   }
 
   // ------------------------------------------------------------------------- teardown
+  if (p.pdl_wait_at_end) pdl_wait();   // this grid's completion must imply the predecessor's
   tc_fence_before();
   __syncthreads();
   if (CG > 1) cluster_sync_all();     // no CTA leaves while its peer may still arrive on it / read its smem
@@ -802,8 +827,8 @@ Layout make_layout(int n_own, int n_str, int cg, int max_cl) {
 }
 
 template <int MODE, int VARIANT, int CG>
-int launch_tc(const CUtensorMap& own, const CUtensorMap& sk, const CUtensorMap& smn, const TcParams& p, int NC,
-              cudaStream_t st) {
+int launch_tc(const CUtensorMap& own, const CUtensorMap& sk, const CUtensorMap& smn, const CUtensorMap& out,
+              const TcParams& p, int NC, bool pdl, cudaStream_t st) {
   auto kern = tc_strip_kernel<MODE, VARIANT, CG>;
   GE2E_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   TcParams q = p;
@@ -818,11 +843,13 @@ int launch_tc(const CUtensorMap& own, const CUtensorMap& sk, const CUtensorMap& 
   cfg.blockDim = dim3(kThreadsTc);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  GE2E_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, own, sk, smn, q));
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 2 : 1;
+  GE2E_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, own, sk, smn, out, q));
   GE2E_LAUNCHED();
   return GE2E_OK;
 }
@@ -832,10 +859,10 @@ int max_clusters_cg(int cg) {
   return cg == 2 ? max_clusters<MODE, VARIANT, 2>() : max_clusters<MODE, VARIANT, 1>();
 }
 template <int MODE, int VARIANT>
-int launch_tc_cg(int cg, const CUtensorMap& own, const CUtensorMap& sk, const CUtensorMap& smn, const TcParams& p,
-                 int NC, cudaStream_t st) {
-  return cg == 2 ? launch_tc<MODE, VARIANT, 2>(own, sk, smn, p, NC, st)
-                 : launch_tc<MODE, VARIANT, 1>(own, sk, smn, p, NC, st);
+int launch_tc_cg(int cg, const CUtensorMap& own, const CUtensorMap& sk, const CUtensorMap& smn, const CUtensorMap& out,
+                 const TcParams& p, int NC, bool pdl, cudaStream_t st) {
+  return cg == 2 ? launch_tc<MODE, VARIANT, 2>(own, sk, smn, out, p, NC, pdl, st)
+                 : launch_tc<MODE, VARIANT, 1>(own, sk, smn, out, p, NC, pdl, st);
 }
 
 void fill_common(TcParams& p, const RowsArgs& a, const Layout& L) {
@@ -867,8 +894,16 @@ size_t tc_workspace_bytes(int n_local, int n_total, int M, int D, int variant) {
   return L.done_bytes + L.part_bytes;
 }
 
+int tc_fwd_zero_workspace(int n_local, int n_total, int M, int D, int variant, void* ws, size_t ws_bytes,
+                          cudaStream_t st) {
+  const Layout L = fwd_layout(n_local * M, n_total, D, variant);
+  if (ws_bytes < L.done_bytes + L.part_bytes) return GE2E_ERR_WORKSPACE;
+  if (!L.whole) GE2E_CUDA_TRY(cudaMemsetAsync(ws, 0, L.done_bytes, st));
+  return GE2E_OK;
+}
+
 int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* row_aux, float* loss_accum,
-                float* per_row_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+                float* per_row_out, void* ws, size_t ws_bytes, bool after_prep, cudaStream_t st) {
   const int U = a.n_local * a.M;
   const Layout L = fwd_layout(U, a.n_total, a.D, a.variant);
   if (ws_bytes < L.done_bytes + L.part_bytes) return GE2E_ERR_WORKSPACE;
@@ -884,9 +919,12 @@ int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* r
   p.seg_done = static_cast<int*>(ws);
   p.seg_part = reinterpret_cast<float2*>(static_cast<uint8_t*>(ws) + L.done_bytes);
   p.maxseg = L.maxseg;
-  if (!L.whole) GE2E_CUDA_TRY(cudaMemsetAsync(ws, 0, L.done_bytes, st));
-  if (a.variant == GE2E_SOFTMAX) return launch_tc_cg<TC_FWD, GE2E_SOFTMAX>(L.CG, tmE, tmC, tmC, p, L.NC, st);
-  return launch_tc_cg<TC_FWD, GE2E_CONTRAST>(L.CG, tmE, tmC, tmC, p, L.NC, st);
+  // after_prep: the caller zeroed the workspace before ge2e prep and this launch directly follows the
+  // prep kernel in the stream, so it may start (barrier init, TMEM allocation) under prep's tail
+  if (!after_prep && !L.whole) GE2E_CUDA_TRY(cudaMemsetAsync(ws, 0, L.done_bytes, st));
+  if (a.variant == GE2E_SOFTMAX)
+    return launch_tc_cg<TC_FWD, GE2E_SOFTMAX>(L.CG, tmE, tmC, tmC, tmC, p, L.NC, after_prep, st);
+  return launch_tc_cg<TC_FWD, GE2E_CONTRAST>(L.CG, tmE, tmC, tmC, tmC, p, L.NC, after_prep, st);
 }
 
 int tc_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kstar, const float* row_aux,
@@ -905,8 +943,10 @@ int tc_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kst
   const Layout Le = make_layout(U, a.n_total, cg, max_clusters_cg<TC_BWD_DE, GE2E_SOFTMAX>(cg));
   const Layout Lc = make_layout(a.n_total, U, cg, max_clusters_cg<TC_BWD_DC, GE2E_SOFTMAX>(cg));
   const int slabs = a.D / kSlabCols;
-  CUtensorMap tmE_own, tmC_own, tmE_k, tmC_k, tmE_mn, tmC_mn;
+  CUtensorMap tmE_own, tmC_own, tmE_k, tmC_k, tmE_mn, tmC_mn, tm_dE, tm_dC;
   int rc;
+  if ((rc = make_map_2d(&tm_dE, dE_hat, U, a.D, kTile)) != GE2E_OK) return rc;
+  if ((rc = make_map_2d(&tm_dC, dC_hat_partial, a.n_total, a.D, kTile)) != GE2E_OK) return rc;
   if ((rc = make_map_2d(&tmE_own, a.e_hat, U, a.D, kTile)) != GE2E_OK) return rc;
   if ((rc = make_map_2d(&tmC_own, a.c_hat_all, a.n_total, a.D, kTile)) != GE2E_OK) return rc;
   if ((rc = make_map_2d(&tmC_k, a.c_hat_all, a.n_total, a.D, kBoxRows)) != GE2E_OK) return rc;
@@ -921,14 +961,17 @@ int tc_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kst
   p.n_own = U; p.n_str = a.n_total;
   p.acc_out = dE_hat; p.dwdb = dwdb_accum;
   if (!Le.whole) GE2E_CUDA_TRY(cudaMemsetAsync(dE_hat, 0, static_cast<size_t>(U) * a.D * sizeof(float), st));
-  rc = launch_tc_cg<TC_BWD_DE, GE2E_SOFTMAX>(cg, tmE_own, tmC_k, tmC_mn, p, Le.NC, st);
+  rc = (debug_skip_mask() & 4) ? GE2E_OK
+                               : launch_tc_cg<TC_BWD_DE, GE2E_SOFTMAX>(cg, tmE_own, tmC_k, tmC_mn, tm_dE, p, Le.NC, false, st);
   if (rc != GE2E_OK) return rc;
 
   // dC_hat = (wG)^T E_hat: owner = centroid tiles, the utterance range is cut stream-K style
   fill_common(p, a, Lc);
   p.n_own = a.n_total; p.n_str = U;
   p.acc_out = dC_hat_partial; p.dwdb = nullptr;
-  return launch_tc_cg<TC_BWD_DC, GE2E_SOFTMAX>(cg, tmC_own, tmE_k, tmE_mn, p, Lc.NC, st);
+  p.pdl_wait_at_end = 1;      // reads nothing the dE_hat grid writes: the two overlap
+  if (debug_skip_mask() & 8) return GE2E_OK;
+  return launch_tc_cg<TC_BWD_DC, GE2E_SOFTMAX>(cg, tmC_own, tmE_k, tmE_mn, tm_dC, p, Lc.NC, !(debug_skip_mask() & 4), st);
 }
 
 }  // namespace ge2e

@@ -87,6 +87,25 @@ __device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const void* tmap, i
       : "memory");
 }
 
+
+// ---------------------------------------------------------------- TMA stores (shared -> global)
+// generic-proxy writes to shared memory become visible to the async proxy (TMA) after this fence
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_2d(const void* tmap, int x, int y, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(src)
+               : "memory");
+}
+// element-wise fp32 add into global memory, performed at the L2 (no read-back to the SM)
+__device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, int x, int y, uint32_t src) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(src)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk stores of this thread have finished READING shared memory
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // ---------------------------------------------------------------- clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
