@@ -265,12 +265,12 @@ __device__ __forceinline__ float reduce16_transposed(const float (&v)[16], int l
   return e + __shfl_xor_sync(0xffffffffu, e, 16);
 }
 
-template <int KCH, bool ROUND>
+template <int KCH, int RR, bool ROUND>
 __global__ void __launch_bounds__(kPrepWarps * 32)
 prep_reg_kernel(const float* __restrict__ E, int n_local, int M, float* __restrict__ e_hat,
                 float* __restrict__ c_hat, float* __restrict__ cos_diag, float* __restrict__ accum) {
-  constexpr int D = KCH * 128, R = kRegRows;
-  static_assert(R == 16, "reduce16_transposed handles 16 rows");
+  constexpr int D = KCH * 128, R = RR;     // rows held in registers (M <= R <= 16)
+  static_assert(R <= 16, "reduce16_transposed handles 16 rows");
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int j = blockIdx.x * kPrepWarps + wid;
   pdl_trigger();     // the forward tensor-core kernel may set itself up while this grid runs
@@ -304,7 +304,9 @@ prep_reg_kernel(const float* __restrict__ E, int n_local, int M, float* __restri
     Cj[c * 32] = o;
   }
   // |e|^2, |s - e|^2, e.(s - e) of every row (u = (s - e) / (M - 1): s3:105-111)
-  float ne2[R], nd2[R], ed[R];
+  float ne2[16], nd2[16], ed[16];
+#pragma unroll
+  for (int i = R; i < 16; ++i) { ne2[i] = 0.f; nd2[i] = 0.f; ed[i] = 0.f; }
 #pragma unroll
   for (int i = 0; i < R; ++i) {
     ne2[i] = 0.f; nd2[i] = 0.f; ed[i] = 0.f;
@@ -943,15 +945,15 @@ finalize_warp_kernel(const float* __restrict__ E, const float* __restrict__ dE_h
 //   de_i = a_g gv_i + a_e e_i + a_d d_i ,  du_i = b_e e_i + b_d d_i ,  d_i = s - e_i
 //   dE_i = de_i + dc_j / M + (sum_i' du_i' - du_i) / (M - 1)
 // ------------------------------------------------------------------------------------------
-template <int KCH>
+template <int KCH, int RR>
 __global__ void __launch_bounds__(kPrepWarps * 32)
 finalize_reg_kernel(const float* __restrict__ E, const float* __restrict__ dE_hat,
                     const float* __restrict__ dC_hat, const float* __restrict__ cos_diag,
                     const float* __restrict__ row_aux, int n_local, int M,
                     const float* __restrict__ wp, const float* __restrict__ bp, float eps, int variant,
                     const float* __restrict__ gp, float* __restrict__ dE) {
-  constexpr int D = KCH * 128, R = kRegRows;
-  static_assert(R == 16, "reduce16_transposed handles 16 rows");
+  constexpr int D = KCH * 128, R = RR;     // rows held in registers (M <= R <= 16)
+  static_assert(R <= 16, "reduce16_transposed handles 16 rows");
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int j = blockIdx.x * kPrepWarps + wid;
   const bool active = j < n_local;
@@ -973,17 +975,52 @@ finalize_reg_kernel(const float* __restrict__ E, const float* __restrict__ dE_ha
 #pragma unroll
     for (int i = 1; i < R; ++i) { s[c].x += v[i][c].x; s[c].y += v[i][c].y; s[c].z += v[i][c].z; s[c].w += v[i][c].w; }
   }
-  float ne2[R], nd2[R], ed[R], eg[R];
+  // row sums, one quantity at a time (16 live partials instead of 64: the rows already hold 128 registers)
+  float t_ne2, t_nd2, t_ed, t_eg;
+  {
+    float q[16];
 #pragma unroll
-  for (int i = 0; i < R; ++i) {
-    ne2[i] = 0.f; nd2[i] = 0.f; ed[i] = 0.f; eg[i] = 0.f;
+    for (int i = R; i < 16; ++i) q[i] = 0.f;
 #pragma unroll
-    for (int c = 0; c < KCH; ++c) {
-      const float4 gv = (i < M) ? __ldcg(Gj + (size_t)i * (D / 4) + c * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 e = v[i][c];
-      const float4 d = make_float4(s[c].x - e.x, s[c].y - e.y, s[c].z - e.z, s[c].w - e.w);
-      ne2[i] += dot4(e, e); nd2[i] += dot4(d, d); ed[i] += dot4(e, d); eg[i] += dot4(e, gv);
+    for (int i = 0; i < R; ++i) {
+      if (i == R / 2) asm volatile("" ::: "memory");   // two batches of dE_hat loads: bounds the registers in flight
+      q[i] = 0.f;
+#pragma unroll
+      for (int c = 0; c < KCH; ++c) {
+        const float4 gv = (i < M) ? __ldcg(Gj + (size_t)i * (D / 4) + c * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+        q[i] += dot4(v[i][c], gv);
+      }
     }
+    t_eg = reduce16_transposed(q, lane);
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      q[i] = 0.f;
+#pragma unroll
+      for (int c = 0; c < KCH; ++c) q[i] += dot4(v[i][c], v[i][c]);
+    }
+    t_ne2 = reduce16_transposed(q, lane);
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      q[i] = 0.f;
+#pragma unroll
+      for (int c = 0; c < KCH; ++c) {
+        const float4 e = v[i][c];
+        const float4 d = make_float4(s[c].x - e.x, s[c].y - e.y, s[c].z - e.z, s[c].w - e.w);
+        q[i] += dot4(d, d);
+      }
+    }
+    t_nd2 = reduce16_transposed(q, lane);
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      q[i] = 0.f;
+#pragma unroll
+      for (int c = 0; c < KCH; ++c) {
+        const float4 e = v[i][c];
+        const float4 d = make_float4(s[c].x - e.x, s[c].y - e.y, s[c].z - e.z, s[c].w - e.w);
+        q[i] += dot4(e, d);
+      }
+    }
+    t_ed = reduce16_transposed(q, lane);
   }
   const float inv_m = 1.f / (float)M, inv_m1 = 1.f / (float)(M - 1);
   // centroid Jacobian: bc = dc_j / M with dc = (dC_hat - c_hat (c_hat . dC_hat)) / |c|  (or dC_hat / delta)
@@ -1010,8 +1047,6 @@ finalize_reg_kernel(const float* __restrict__ E, const float* __restrict__ dE_ha
       bc[c].z = dch[c].z * k1 - s[c].z * k2; bc[c].w = dch[c].w * k1 - s[c].w * k2;
     }
   }
-  const float t_ne2 = reduce16_transposed(ne2, lane), t_nd2 = reduce16_transposed(nd2, lane);
-  const float t_ed = reduce16_transposed(ed, lane), t_eg = reduce16_transposed(eg, lane);
   // this lane's row
   const int my_row = rev4(lane & 15);
   float a_g, a_e, a_d, b_e, b_d;
@@ -1200,8 +1235,12 @@ void launch_prep_warp(const float* E, int n_local, int M, bool rnd, float* e_hat
   const int grid = (n_local + kPrepWarps - 1) / kPrepWarps;
   if (KCH <= 2 && M <= kRegRows) {
     constexpr int K2 = KCH <= 2 ? KCH : 1;    // the register-resident variant is only instantiated for D <= 256
-    if (rnd) prep_reg_kernel<K2, true><<<grid, kPrepWarps * 32, 0, st>>>(E, n_local, M, e_hat, c_hat, cos_diag, accum);
-    else prep_reg_kernel<K2, false><<<grid, kPrepWarps * 32, 0, st>>>(E, n_local, M, e_hat, c_hat, cos_diag, accum);
+    const dim3 g(grid), bl(kPrepWarps * 32);
+#define GE2E_PREP_REG(RR)                                                                                        \
+  (rnd ? prep_reg_kernel<K2, RR, true><<<g, bl, 0, st>>>(E, n_local, M, e_hat, c_hat, cos_diag, accum)            \
+       : prep_reg_kernel<K2, RR, false><<<g, bl, 0, st>>>(E, n_local, M, e_hat, c_hat, cos_diag, accum))
+    if (M <= 4) GE2E_PREP_REG(4); else if (M <= 8) GE2E_PREP_REG(8); else if (M <= 12) GE2E_PREP_REG(12); else GE2E_PREP_REG(16);
+#undef GE2E_PREP_REG
     return;
   }
   if (rnd) prep_warp_kernel<KCH, true><<<grid, kPrepWarps * 32, 0, st>>>(E, n_local, M, e_hat, c_hat, cos_diag, accum);
@@ -1215,8 +1254,11 @@ void launch_finalize_warp(const float* E, const float* dE_hat, const float* dC_h
   const int grid = (n_local + kPrepWarps - 1) / kPrepWarps;
   if (KCH <= 2 && M <= kRegRows) {
     constexpr int K2 = KCH <= 2 ? KCH : 1;
-    launch_pdl(finalize_reg_kernel<K2>, dim3(grid), dim3(kPrepWarps * 32), 0, st, pdl, E, dE_hat, dC_hat,
-               cos_diag, row_aux, n_local, M, w, b, eps, variant, g, dE);
+#define GE2E_FIN_REG(RR)                                                                                     \
+  launch_pdl(finalize_reg_kernel<K2, RR>, dim3(grid), dim3(kPrepWarps * 32), 0, st, pdl, E, dE_hat, dC_hat, cos_diag, \
+             row_aux, n_local, M, w, b, eps, variant, g, dE)
+    if (M <= 4) GE2E_FIN_REG(4); else if (M <= 8) GE2E_FIN_REG(8); else if (M <= 12) GE2E_FIN_REG(12); else GE2E_FIN_REG(16);
+#undef GE2E_FIN_REG
     return;
   }
   launch_pdl(finalize_warp_kernel<KCH>, dim3(grid), dim3(kPrepWarps * 32), 0, st, pdl, E, dE_hat, dC_hat, cos_diag,
