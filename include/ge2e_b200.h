@@ -61,7 +61,7 @@ unsigned long long ge2e_b200_launch_count(void);
 int ge2e_b200_path(int n_local, int n_total, int M, int D, int variant, int precision);
 /* Debug: while device_buf is non-NULL the tensor-core kernels stamp %globaltimer at their pipeline
  * events into device_buf[grid][3 roles (TMA, MMA, epilogue)][64]; NULL switches it off.
- * kernel: -1 = all, 0 = forward, 1 = dE_hat backward, 2 = dC_hat backward. */
+ * kernel: -1 = all, 0 = forward rows, 1 = backward rows. */
 void ge2e_b200_debug_trace(unsigned long long* device_buf, int kernel);
 /* GE2E_OK if the current CUDA device can run this library (sm_100), else GE2E_ERR_DEVICE. */
 int ge2e_b200_check_device(void);

@@ -7,8 +7,8 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-MASKS = [("full", 0), ("-prep", 1), ("-fwd_rows", 2), ("-dE", 4), ("-dC", 8), ("-finalize", 16),
-         ("-dE-dC", 12), ("only prep+fwd", 28), ("only bwd kernels", 3), ("nothing (memsets)", 31)]
+MASKS = [("full", 0), ("-prep", 1), ("-fwd_rows", 2), ("-bwd_rows", 12), ("-finalize", 16),
+         ("only prep+fwd", 28), ("only bwd kernels", 3), ("nothing (memsets)", 31)]
 
 if len(sys.argv) > 2 and sys.argv[1] == "--child":
     import numpy as np

@@ -52,7 +52,7 @@ for rep in range(2):
     lib().ge2e_b200_debug_trace(None, -1)
     if rep == 1:
         show("fwd (warm)", trace)
-for mode, name in ((1, "bwd dE"), (2, "bwd dC")):
+for mode, name in ((1, "bwd (dC then dE segments)"),):
     for rep in range(2):
         trace.zero_()
         lib().ge2e_b200_debug_trace(trace.data_ptr(), mode)

@@ -1,8 +1,9 @@
 // tcgen05 / TMA / TMEM path of the GE2E loss (TF32 operands, fp32 accumulators in tensor memory).
 //
-// One warp-specialised kernel, three modes (the tensor-core twin of ge2e_simt.cu's strip kernel).
-// An "owner" operand tile X[128, D] stays resident in shared memory, a "stream" operand Y is
-// pulled through a TMA ring one work unit (128 rows) at a time:
+// One warp-specialised persistent kernel, two instantiations: the forward rows and the whole
+// backward contraction (the tensor-core twin of ge2e_simt.cu's strip kernel).  An "owner" operand
+// tile X[128, D] stays resident in shared memory, a "stream" operand Y is pulled through a TMA
+// ring one work unit (128 rows) at a time:
 //
 //   MMA1   T[128 x n] = X . Y_unit^T            (SS, both K-major, K = D)            -> TMEM
 //   FWD    epilogue: online log-sum-exp (softmax) / running arg-max (contrast) over T's columns;
@@ -11,8 +12,9 @@
 //   BWD    epilogue: G = w g (softmax(S) - onehot) with the leave-one-out diagonal masked,
 //          rounded to TF32 and written back over T in TMEM (n = 128);
 //   MMA2   Acc[128 x D] += G . Y_unit            (A from TMEM, B MN-major from smem)  -> TMEM
-//            BWD_DE: X = E_hat rows, Y = C_hat     -> dE_hat = (wG) C_hat
-//            BWD_DC: X = C_hat rows, Y = E_hat     -> dC_hat = (wG)^T E_hat
+//            DE segments: X = E_hat rows, Y = C_hat     -> dE_hat = (wG) C_hat
+//            DC segments: X = C_hat rows, Y = E_hat     -> dC_hat = (wG)^T E_hat
+//          the accumulator leaves through shared memory and a TMA store / TMA reduce-add.
 //
 // CG = 2 runs every MMA on a CTA pair (tcgen05 cta_group::2, UMMA M = 256): the two CTAs of a
 // cluster own two consecutive owner tiles and each fetches HALF of every stream operand, which
@@ -21,10 +23,16 @@
 // the paired 256x128x8).  The leader CTA (cluster rank 0) issues the MMAs; every barrier the MMA
 // warp waits on lives in the leader and is signalled by both CTAs.
 //
-// Work is a flat list of (owner group, stream unit) pairs cut into equal contiguous ranges over
-// the clusters (stream-K): a cluster whose range covers only part of an owner group publishes a
-// partial result (FWD: (max, sum) per row, merged by the last CTA to finish that tile; BWD: the
-// accumulator is added into a zeroed output by a TMA reduce, cp.reduce.async.bulk).
+// Work = (owner group, stream unit) pairs; a segment is a run of pairs inside one owner group.
+//   FWD   the flat pair list is cut into equal contiguous ranges over the clusters (stream-K); a
+//         cluster whose range covers only part of an owner group publishes (max, sum) per row and
+//         the last cluster to finish that tile merges.
+//   BWD   both contractions in ONE launch.  dE_hat owner groups are short (n_total / 128 units):
+//         a cluster takes WHOLE groups (plain store, no zero-fill of dE_hat), and the long dC_hat
+//         groups are the divisible filler that balances the clusters; their partial accumulators
+//         are added into the zeroed dC_hat at the L2 (cp.reduce.async.bulk).  Shapes whose dE_hat
+//         groups are too coarse for that fall back to a flat cut of [dC pairs | dE pairs].
+//         The per-cluster ranges are computed on the host (make_bwd_sched) and passed by value.
 //
 // Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
 // warps 4-11 = epilogue (TMEM lane quarter = warp % 4, column half = (warp - 4) / 4: two threads
@@ -59,10 +67,12 @@ constexpr int kEpiWarp0 = 4;
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreadsTc = (kEpiWarp0 + kEpiWarps) * 32;
+constexpr int kMaxClusters = 160;     // >= SM count / cluster size
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
-enum { TC_FWD = 0, TC_BWD_DE = 1, TC_BWD_DC = 2 };
+enum { TC_FWD = 0, TC_BWD = 1 };
+enum { SEG_DE = 0, SEG_DC = 1 };      // index into the per-segment-kind arrays (FWD uses index 0)
 
 // barrier indices inside the shared barrier array
 enum {
@@ -79,15 +89,29 @@ enum {
   BAR_COUNT
 };
 
+// tensor maps of one launch; index = segment kind (FWD: [SEG_DE] only)
+struct TmSet {
+  CUtensorMap own[2];    // owner tiles        box [128 rows][32 cols], 128B swizzle
+  CUtensorMap strk[2];   // stream, K-major    box [64 rows][32 cols], 128B swizzle
+  CUtensorMap strmn[2];  // stream, MN-major   box [D/32/CG][32 rows][32 cols], 32B-atom 128B swizzle
+  CUtensorMap out[2];    // accumulator output box [128 rows][32 cols], 128B swizzle
+};
+
+// BWD: pair range [begin[c], begin[c + 1]) of cluster c in the dE_hat / dC_hat pair lists
+struct BwdSched {
+  int de[kMaxClusters + 1];
+  int dc[kMaxClusters + 1];
+};
+
 struct TcParams {
-  int n_own, n_str, D, kslabs;
+  int D, kslabs;
   int M, spk_offset;
-  int OT, ST;                 // owner tiles, stream units
-  int OG;                     // owner groups = ceil(OT / CG)
-  long long GP;               // OG * ST (group, stream unit) pairs
+  int n_own[2], n_str[2];     // rows of the owner / stream matrix per segment kind
+  int OT[2], ST[2];           // owner tiles, stream units
+  long long GP;               // FWD: owner groups * ST (group, stream unit) pairs
   const float* cos_diag;      // [U_local]
   const float* row_stat;      // BWD: lse per local utterance row
-  const float* row_aux;       // BWD_DE: q = 1 - p_jj per local utterance row
+  const float* row_aux;       // BWD: q = 1 - p_jj per local utterance row
   float* row_aux_out;         // FWD softmax
   const float* w;
   const float* b;
@@ -101,11 +125,10 @@ struct TcParams {
   int* seg_done;              // [OT] stream units finished per owner tile (zeroed by the host)
   float2* seg_part;           // [OT][maxseg][128] partial row state
   int maxseg;
-  // BWD outputs
-  float* acc_out;             // dE_hat [n_own, D] or dC_hat_partial [n_own, D]
-  float* dwdb;                // BWD_DE
+  // BWD outputs (dE_hat / dC_hat go through the `out` tensor maps)
+  float* dwdb;
+  int pdl_wait_at_end;        // unused by the current launches (kept for stand-alone launches)
   unsigned long long* trace;  // debug: [CTA][3 roles][kTraceEvents] globaltimer stamps, or nullptr
-  int pdl_wait_at_end;        // 1: no input comes from the stream predecessor (BWD_DC after BWD_DE)
   int dbg;                    // debug (GE2E_TC_DEBUG): 1 = no TMA for stream stages, 2 = no MMA issue,
                               //                        4 = epilogue skips the math (results are garbage)
 };
@@ -127,7 +150,7 @@ struct SharedTail {
   int flag;
   float red[2 * kEpiWarps];
   union {                                 // 1 KB either way: the budget above the ring is ~2 KB
-    alignas(16) float lse_s[2][kUnit];    // BWD_DC: lse (log2 domain) of the current stream rows
+    alignas(16) float lse_s[2][kUnit];    // DC segments: lse (log2 domain) of the current stream rows
     alignas(16) float2 xch[kTile];        // FWD: row state of the upper column half
   };
 };
@@ -139,11 +162,29 @@ __device__ __forceinline__ int cluster_of_pair(long long gp, long long GP, int N
   return static_cast<int>(((gp + 1) * NC + GP - 1) / GP) - 1;
 }
 
+// The walk over a cluster's segments, identical in every warp role.
+struct Walk {
+  long long gp, end;      // remaining pair range of the current part
+  long long de0, de1;     // BWD: the dE_hat part, visited after the dC_hat part
+  int kind;               // kind of the current part
+  __device__ __forceinline__ bool next(const TcParams& p, int& kind_out, int& og, int& s0, int& s1) {
+    while (gp >= end) {
+      if (kind != SEG_DC) return false;
+      kind = SEG_DE; gp = de0; end = de1;
+    }
+    const int st = p.ST[kind];
+    kind_out = kind;
+    og = static_cast<int>(gp / st);
+    s0 = static_cast<int>(gp % st);
+    s1 = static_cast<int>(min(static_cast<long long>(st), s0 + (end - gp)));
+    gp += s1 - s0;
+    return true;
+  }
+};
+
 template <int MODE, int VARIANT, int CG>
 __global__ void __launch_bounds__(kThreadsTc, 1)
-tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constant__ CUtensorMap tm_strk,
-                const __grid_constant__ CUtensorMap tm_strmn, const __grid_constant__ CUtensorMap tm_out,
-                const TcParams p) {
+tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSched sched, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr bool kBwd = (MODE != TC_FWD);
   constexpr int kStageBytes = 32768 / CG;
@@ -167,14 +208,16 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
   const bool leader = (cr == 0);
   // barriers the MMA warp waits on live in the leader: address them through the cluster window
   auto lbar = [&](int i) { return (CG == 2) ? mapa(bar(i), 0) : bar(i); };
-  const long long gp_begin = (static_cast<long long>(cl) * p.GP) / NC;
-  const long long gp_end = (static_cast<long long>(cl + 1) * p.GP) / NC;
   const int kslabs = p.kslabs;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tm_own);
-    prefetch_tmap(&tm_strk);
-    if (kBwd) { prefetch_tmap(&tm_strmn); prefetch_tmap(&tm_out); }
+    prefetch_tmap(&tms.own[0]);
+    prefetch_tmap(&tms.strk[0]);
+    if (kBwd) {
+      prefetch_tmap(&tms.own[1]); prefetch_tmap(&tms.strk[1]);
+      prefetch_tmap(&tms.strmn[0]); prefetch_tmap(&tms.strmn[1]);
+      prefetch_tmap(&tms.out[0]); prefetch_tmap(&tms.out[1]);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(bar(BAR_FULL + i), 1); mbar_init(bar(BAR_EMPTY + i), 1); }
@@ -203,12 +246,20 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
   pdl_trigger();
   if (!p.pdl_wait_at_end) pdl_wait();
 
-  // ---- the walk over this cluster's (owner group, stream unit) range, identical in every role
-  // segment = maximal run of pairs inside one owner group; step = 1 or 2 (FWD) units of it
-  auto seg_bounds = [&](long long gp, int& og, int& s0, int& s1) {
-    og = static_cast<int>(gp / p.ST);
-    s0 = static_cast<int>(gp % p.ST);
-    s1 = static_cast<int>(min(static_cast<long long>(p.ST), s0 + (gp_end - gp)));
+  // ---- this cluster's work
+  auto make_walk = [&]() {
+    Walk wk;
+    if (!kBwd) {
+      wk.kind = SEG_DE;
+      wk.gp = (static_cast<long long>(cl) * p.GP) / NC;
+      wk.end = (static_cast<long long>(cl + 1) * p.GP) / NC;
+      wk.de0 = wk.de1 = 0;
+    } else {
+      wk.kind = SEG_DC;
+      wk.gp = sched.dc[cl]; wk.end = sched.dc[cl + 1];
+      wk.de0 = sched.de[cl]; wk.de1 = sched.de[cl + 1];
+    }
+    return wk;
   };
   constexpr int kStepUnits = kBwd ? 1 : 2;
 
@@ -216,11 +267,11 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
     // ===================================================================== TMA producer
     Tracer tr(lane == 0 ? p.trace : nullptr, 0);
     tr.mark();
-    int stage = 0, phase = 0, sg = 0;
+    int stage = 0, phase = 0;
     auto advance = [&]() { if (++stage == kStages) { stage = 0; phase ^= 1; } };
     // one K-major stage: `nslab` slabs of [rows_cta x 32] starting at slab ks0, stream rows
     // [row0 + cr * rows_cta, + rows_cta) of a step that covers rows_cta * CG rows
-    auto load_k = [&](int row0, int rows_cta, int ks0, int nslab) {
+    auto load_k = [&](const CUtensorMap* tm, int row0, int rows_cta, int ks0, int nslab) {
       mbar_wait(bar(BAR_EMPTY + stage), phase ^ 1);
       if (elect_one()) {
         const uint32_t bytes = static_cast<uint32_t>(nslab * rows_cta * 128);
@@ -232,8 +283,8 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
           uint32_t dst = ring_smem + stage * kStageBytes;
           for (int sl = 0; sl < nslab; ++sl)
             for (int r = 0; r < rows_cta; r += kBoxRows, dst += kBoxRows * 128) {
-              if (CG == 1) tma_load_2d(dst, &tm_strk, (ks0 + sl) * kSlabCols, row0 + r, full);
-              else tma_load_2d_2cta(dst, &tm_strk, (ks0 + sl) * kSlabCols, row0 + cr * rows_cta + r, full);
+              if (CG == 1) tma_load_2d(dst, tm, (ks0 + sl) * kSlabCols, row0 + r, full);
+              else tma_load_2d_2cta(dst, tm, (ks0 + sl) * kSlabCols, row0 + cr * rows_cta + r, full);
             }
         }
       }
@@ -241,7 +292,7 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
       advance();
     };
     // one MN-major stage: kMma2Rows stream rows x this CTA's share of the D columns
-    auto load_mn = [&](int row0) {
+    auto load_mn = [&](const CUtensorMap* tm, int row0) {
       mbar_wait(bar(BAR_EMPTY + stage), phase ^ 1);
       if (elect_one()) {
         const int slabs_c = kslabs / CG;
@@ -252,19 +303,19 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
           if (leader) mbar_expect_tx(bar(BAR_FULL + stage), bytes * CG);
           const uint32_t full = lbar(BAR_FULL + stage);
           const uint32_t dst = ring_smem + stage * kStageBytes;
-          if (CG == 1) tma_load_3d(dst, &tm_strmn, 0, row0, 0, full);
-          else tma_load_3d_2cta(dst, &tm_strmn, 0, row0, cr * slabs_c, full);
+          if (CG == 1) tma_load_3d(dst, tm, 0, row0, 0, full);
+          else tma_load_3d_2cta(dst, tm, 0, row0, cr * slabs_c, full);
         }
       }
       __syncwarp();
       advance();
     };
-    auto load_mma1_unit = [&](int u) {       // BWD: stages of two slabs, n = 128
-      for (int ks = 0; ks < kslabs; ks += 2) load_k(u * kUnit, kUnit / CG, ks, min(2, kslabs - ks));
-    };
-    for (long long gp = gp_begin; gp < gp_end; ++sg) {
-      int og, s0, s1;
-      seg_bounds(gp, og, s0, s1);
+    Walk wk = make_walk();
+    int kind, og, s0, s1;
+    for (int sg = 0; wk.next(p, kind, og, s0, s1); ++sg) {
+      const CUtensorMap* tm_own = &tms.own[kind];
+      const CUtensorMap* tm_k = &tms.strk[kind];
+      const CUtensorMap* tm_mn = &tms.strmn[kind];
       const int ot = og * CG + cr;      // may be >= OT in the last group: TMA zero-fills, nothing is stored
       if (sg > 0) {
         mbar_wait(bar(BAR_A_EMPTY), (sg - 1) & 1);
@@ -274,24 +325,26 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
       if (elect_one()) {
         for (int ks = 0; ks < kslabs; ++ks) {
           if (leader) mbar_expect_tx(bar(BAR_A_FULL + ks), kSlabBytes * CG);
-          if (CG == 1) tma_load_2d(a_smem + ks * kSlabBytes, &tm_own, ks * kSlabCols, ot * kTile, bar(BAR_A_FULL + ks));
-          else tma_load_2d_2cta(a_smem + ks * kSlabBytes, &tm_own, ks * kSlabCols, ot * kTile, lbar(BAR_A_FULL + ks));
+          if (CG == 1) tma_load_2d(a_smem + ks * kSlabBytes, tm_own, ks * kSlabCols, ot * kTile, bar(BAR_A_FULL + ks));
+          else tma_load_2d_2cta(a_smem + ks * kSlabBytes, tm_own, ks * kSlabCols, ot * kTile, lbar(BAR_A_FULL + ks));
         }
       }
       __syncwarp();
       if (!kBwd) {
         for (int u = s0; u < s1; u += kStepUnits) {
           const int nu = min(kStepUnits, s1 - u);
-          for (int ks = 0; ks < kslabs; ++ks) load_k(u * kUnit, nu * kUnit / CG, ks, 1);
+          for (int ks = 0; ks < kslabs; ++ks) load_k(tm_k, u * kUnit, nu * kUnit / CG, ks, 1);
         }
       } else {
+        auto load_mma1_unit = [&](int u) {       // stages of two slabs, n = 128
+          for (int ks = 0; ks < kslabs; ks += 2) load_k(tm_k, u * kUnit, kUnit / CG, ks, min(2, kslabs - ks));
+        };
         load_mma1_unit(s0);
         for (int u = s0; u < s1; ++u) {
           if (u + 1 < s1) load_mma1_unit(u + 1);
-          for (int kc = 0; kc < kUnit / kMma2Rows; ++kc) load_mn(u * kUnit + kc * kMma2Rows);
+          for (int kc = 0; kc < kUnit / kMma2Rows; ++kc) load_mn(tm_mn, u * kUnit + kc * kMma2Rows);
         }
       }
-      gp += s1 - s0;
       tr.mark();   // all loads of the segment issued
     }
   } else if (warp == 1) {
@@ -363,9 +416,9 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
           advance();
         }
       };
-      for (long long gp = gp_begin; gp < gp_end; ++sg) {
-        int og, s0, s1;
-        seg_bounds(gp, og, s0, s1);
+      Walk wk = make_walk();
+      int kind, og, s0, s1;
+      for (; wk.next(p, kind, og, s0, s1); ++sg) {
         if (!kBwd) {
           for (int u = s0; u < s1; u += kStepUnits, ++it) {
             const int nu = min(kStepUnits, s1 - u);
@@ -399,7 +452,6 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
           if (elect_one()) commit(BAR_ACC_FULL);
           __syncwarp();
         }
-        gp += s1 - s0;
       }
     }
   } else if (warp >= kEpiWarp0) {
@@ -414,7 +466,7 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
     const float g = kBwd ? __ldg(p.grad_out) : 1.f;
     const float wg = w * g;
     float dw_acc = 0.f, db_acc = 0.f, loss_acc = 0.f;
-    int sg = 0, it = 0;
+    int it = 0;
     Tracer tr((trow == 0 && half == 0) ? p.trace : nullptr, 2);
     tr.mark();
     // epilogue -> MMA signals go to the leader CTA of the pair
@@ -423,26 +475,28 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
       if (CG == 1) mbar_arrive(addr); else mbar_arrive_cluster(addr);
     };
 
-    for (long long gp = gp_begin; gp < gp_end; ++sg) {
-      int og, s0, s1;
-      seg_bounds(gp, og, s0, s1);
+    Walk wk = make_walk();
+    int kind, og, s0, s1;
+    for (int sg = 0; wk.next(p, kind, og, s0, s1); ++sg) {
+      const bool is_dc = kBwd && kind == SEG_DC;       // CTA-uniform
+      const int n_str = p.n_str[kind];
       const int ot = og * CG + cr;
-      const bool tile_valid = ot < p.OT;             // CTA-uniform
-      const int orow = ot * kTile + trow;            // owner row (utterance, or centroid for DC)
-      const bool ovalid = orow < p.n_own;
+      const bool tile_valid = ot < p.OT[kind];         // CTA-uniform
+      const int orow = ot * kTile + trow;              // owner row (utterance, or centroid in a DC segment)
+      const bool ovalid = orow < p.n_own[kind];
       // per-owner-row metadata
       int jg = -1;            // FWD / DE: global speaker of this utterance row
       float cd = 0.f, lse2 = INFINITY, qd = 0.f;
       int dlo = 0, dhi = 0;   // DC: local utterance rows [dlo, dhi) belong to this centroid
-      if (MODE != TC_BWD_DC) {
+      if (!is_dc) {
         if (ovalid) {
           jg = p.spk_offset + orow / p.M;
           cd = __ldg(p.cos_diag + orow);
-          if (MODE == TC_BWD_DE) { lse2 = __ldg(p.row_stat + orow) * kLog2e; qd = __ldg(p.row_aux + orow); }
+          if (kBwd) { lse2 = __ldg(p.row_stat + orow) * kLog2e; qd = __ldg(p.row_aux + orow); }
         }
       } else {
         const int jl = orow - p.spk_offset;
-        if (ovalid && jl >= 0 && (long long)jl * p.M < p.n_str) { dlo = jl * p.M; dhi = dlo + p.M; }
+        if (ovalid && jl >= 0 && (long long)jl * p.M < n_str) { dlo = jl * p.M; dhi = dlo + p.M; }
       }
       // FWD softmax running state, log2 domain, OFF-diagonal columns only: the running max starts at
       // the diagonal logit (known from cos_diag) and the diagonal term joins when the row is closed
@@ -453,11 +507,11 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
       for (int u = s0; u < s1; u += kStepUnits, ++it) {
         const int nu = min(kStepUnits, s1 - u);
         const int buf = it & 1;
-        if (MODE == TC_BWD_DC) {
+        if (is_dc) {
           // stage the lse of the 128 stream rows (utterances) of this unit
           if (half == 0) {
             const int ur = u * kUnit + trow;
-            tail->lse_s[buf][trow] = (ur < p.n_str) ? __ldg(p.row_stat + ur) * kLog2e : INFINITY;
+            tail->lse_s[buf][trow] = (ur < n_str) ? __ldg(p.row_stat + ur) * kLog2e : INFINITY;
           }
           named_bar_sync(1, kEpiThreads);
         }
@@ -473,12 +527,12 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
           tmem_ld32(t_addr + ch * 32, v);
           tmem_ld_wait();
           if (p.dbg & 4) {
-            if (MODE != TC_FWD) tmem_st32(t_addr + ch * 32, v);
+            if (kBwd) tmem_st32(t_addr + ch * 32, v);
             continue;
           }
-          if (MODE == TC_FWD) {
-            if (c0 < p.n_str) {
-              const bool tailc = c0 + 32 > p.n_str;
+          if (!kBwd) {
+            if (c0 < n_str) {
+              const bool tailc = c0 + 32 > n_str;
               const bool diagc = static_cast<unsigned>(jg - c0) < 32u;
               if (VARIANT == GE2E_SOFTMAX) {
                 float x[32];
@@ -487,7 +541,7 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
                 if (__any_sync(0xffffffffu, tailc || diagc)) {
 #pragma unroll
                   for (int i = 0; i < 32; ++i)   // own-speaker column (s3:78) and padding leave the sum
-                    if (c0 + i == jg || c0 + i >= p.n_str) x[i] = -INFINITY;
+                    if (c0 + i == jg || c0 + i >= n_str) x[i] = -INFINITY;
                 }
                 float cm = x[0];
 #pragma unroll
@@ -502,7 +556,7 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                   float s = fmaf(__uint_as_float(v[i]), w, bb);
-                  if (c0 + i == jg || c0 + i >= p.n_str) s = -INFINITY;
+                  if (c0 + i == jg || c0 + i >= n_str) s = -INFINITY;
                   if (s > best) { best = s; bestk = c0 + i; }
                 }
               }
@@ -510,15 +564,15 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
           } else {
             // ---- backward: G tile, written back over T
             uint32_t gq[32];
-            if (MODE == TC_BWD_DE) {
-              const bool special = (c0 + 32 > p.n_str) || (static_cast<unsigned>(jg - c0) < 32u);
+            if (!is_dc) {
+              const bool special = (c0 + 32 > n_str) || (static_cast<unsigned>(jg - c0) < 32u);
               const bool any_special = __any_sync(0xffffffffu, special);
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
                 const float dot = __uint_as_float(v[i]);
                 float pr = ex2(fmaf(dot, w2, b2) - lse2);        // softmax prob (0 for padded rows)
                 if (any_special) {
-                  if (c0 + i >= p.n_str) pr = 0.f;
+                  if (c0 + i >= n_str) pr = 0.f;
                   if (c0 + i == jg) {
                     // diagonal: p_jj - 1 = -q (saved by the forward), uses cos_diag, contributes to
                     // dw but not to the contraction
@@ -550,7 +604,7 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
           }
         }
         tr.mark();   // tile consumed
-        if (MODE == TC_FWD) {
+        if (!kBwd) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) arrive_leader(s_empty0 + 8u * buf);
@@ -563,8 +617,8 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
       }
 
       // ------------------------------------------------------------ segment flush
-      const bool full = (s0 == 0 && s1 == p.ST);
-      if (MODE == TC_FWD) {
+      const bool full = (s0 == 0 && s1 == p.ST[kind]);
+      if (!kBwd) {
         // fold the two column halves of every row (upper half hands its state over through smem)
         float2 mine;
         if (VARIANT == GE2E_SOFTMAX) mine = make_float2(m2, lsum);
@@ -586,7 +640,8 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
           };
           fold(theirs);
           // publish the partial row state, last finisher of this owner tile merges
-          const int first_cl = cluster_of_pair(static_cast<long long>(og) * p.ST, p.GP, NC);
+          const int st = p.ST[SEG_DE];
+          const int first_cl = cluster_of_pair(static_cast<long long>(og) * st, p.GP, NC);
           bool last = full;
           if (!full) {
             float2 part;
@@ -597,13 +652,13 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
             named_bar_sync(2, kTile);
             if (trow == 0) {
               const int done = atomicAdd(p.seg_done + ot, s1 - s0) + (s1 - s0);
-              tail->flag = (done == p.ST);
+              tail->flag = (done == st);
             }
             named_bar_sync(2, kTile);
             last = tail->flag != 0;
             if (last) {
               __threadfence();
-              const int last_cl = cluster_of_pair(static_cast<long long>(og) * p.ST + p.ST - 1, p.GP, NC);
+              const int last_cl = cluster_of_pair(static_cast<long long>(og) * st + st - 1, p.GP, NC);
               const int nseg = last_cl - first_cl + 1;
               m2 = xd2; lsum = 0.f; best = -INFINITY; bestk = INT_MAX;
               for (int sgi = 0; sgi < nseg; ++sgi)
@@ -630,7 +685,7 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
         }
       } else {
         // drain the accumulator [128 x D] of this segment (columns split between the two halves)
-        if (MODE == TC_BWD_DE && ovalid && s0 == 0 && half == 0) db_acc -= g * eps * ex2(-lse2);   // item 12
+        if (!is_dc && ovalid && s0 == 0 && half == 0) db_acc -= g * eps * ex2(-lse2);   // item 12
         mbar_wait(bar(BAR_ACC_FULL), sg & 1);
         tc_fence_after();
         // TMEM -> registers -> owner area of shared memory (free: every MMA of the segment has
@@ -657,9 +712,10 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
         named_bar_sync(1, kEpiThreads);
         if (ew == 0 && lane == 0) {
           if (tile_valid) {
+            const CUtensorMap* tm_out = &tms.out[kind];
             for (int ks = 0; ks < kslabs; ++ks) {
-              if (full) tma_store_2d(&tm_out, ks * kSlabCols, ot * kTile, a_smem + ks * kSlabBytes);
-              else tma_reduce_add_2d(&tm_out, ks * kSlabCols, ot * kTile, a_smem + ks * kSlabBytes);
+              if (full) tma_store_2d(tm_out, ks * kSlabCols, ot * kTile, a_smem + ks * kSlabBytes);
+              else tma_reduce_add_2d(tm_out, ks * kSlabCols, ot * kTile, a_smem + ks * kSlabBytes);
             }
             tma_store_commit();
             tma_store_wait_read();
@@ -667,12 +723,11 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
           mbar_arrive(bar(BAR_A_FREE));
         }
       }
-      gp += s1 - s0;
       tr.mark();   // segment flushed
     }
 
     // ------------------------------------------------------------ scalar reductions (once per CTA)
-    if (MODE == TC_FWD) {
+    if (!kBwd) {
       loss_acc = warp_sum(loss_acc);
       if (lane == 0) tail->red[ew] = loss_acc;
       named_bar_sync(1, kEpiThreads);
@@ -681,7 +736,7 @@ tc_strip_kernel(const __grid_constant__ CUtensorMap tm_own, const __grid_constan
         for (int i = 0; i < kEpiWarps; ++i) t += tail->red[i];
         atomicAdd(p.loss_accum, t);
       }
-    } else if (MODE == TC_BWD_DE) {
+    } else {
       dw_acc = warp_sum(dw_acc) * g;
       db_acc = warp_sum(db_acc);
       if (lane == 0) { tail->red[ew] = dw_acc; tail->red[kEpiWarps + ew] = db_acc; }
@@ -751,7 +806,7 @@ int make_map_3d(CUtensorMap* m, const float* base, int rows, int D, int box_slab
 }
 
 unsigned long long* g_trace = nullptr;   // set through tc_set_trace (debug only)
-int g_trace_mode = -1;                   // -1: every kernel, else only TC_FWD / TC_BWD_DE / TC_BWD_DC
+int g_trace_mode = -1;                   // -1: every kernel, else only TC_FWD / TC_BWD
 
 int sm_count() {
   static int n = 0;
@@ -772,7 +827,7 @@ int pick_cg(int D) {
     const char* s = getenv("GE2E_TC_CG");
     env = s ? atoi(s) : 0;
   }
-  int cg = (env == 1 || env == 2) ? env : 1;
+  int cg = (env == 1 || env == 2) ? env : 2;
   if ((D / kSlabCols) % 2 != 0) cg = 1;
   return cg;
 }
@@ -798,7 +853,7 @@ int max_clusters() {
       (void)cudaGetLastError();
     }
     if (n <= 0) n = sm_count() / CG;
-    cache = n;
+    cache = std::min(n, kMaxClusters);
   }
   return cache;
 }
@@ -826,9 +881,42 @@ Layout make_layout(int n_own, int n_str, int cg, int max_cl) {
   return L;
 }
 
+// Backward schedule (see the header comment).  Returns the number of clusters; *de_partial tells the
+// caller whether some dE_hat owner group is cut between clusters (then dE_hat must be zero-filled).
+int make_bwd_sched(int OGe, int STe, int OGc, int STc, int max_cl, BwdSched* S, bool* de_partial) {
+  const long long GPe = static_cast<long long>(OGe) * STe, GPc = static_cast<long long>(OGc) * STc, W = GPe + GPc;
+  const int NC = static_cast<int>(std::min<long long>(max_cl, W));
+  const long long T = (W + NC - 1) / NC;             // balanced share, in units
+  if (2LL * STe <= T) {
+    // whole dE_hat groups per cluster, dC_hat units fill every cluster up to the same level
+    *de_partial = false;
+    for (int c = 0; c <= NC; ++c) S->de[c] = static_cast<int>((static_cast<long long>(c) * OGe / NC) * STe);
+    long long wsum = 0;
+    long long wgt[kMaxClusters];
+    for (int c = 0; c < NC; ++c) {
+      wgt[c] = std::max<long long>(0, T - (S->de[c + 1] - S->de[c]));
+      wsum += wgt[c];
+    }
+    if (wsum == 0) { for (int c = 0; c < NC; ++c) wgt[c] = 1; wsum = NC; }
+    long long cum = 0;
+    for (int c = 0; c <= NC; ++c) {
+      S->dc[c] = static_cast<int>(GPc * cum / wsum);
+      if (c < NC) cum += wgt[c];
+    }
+  } else {
+    // dE_hat groups too coarse: flat cut of [dC pairs | dE pairs]
+    *de_partial = true;
+    for (int c = 0; c <= NC; ++c) {
+      const long long lo = static_cast<long long>(c) * W / NC;
+      S->dc[c] = static_cast<int>(std::min(lo, GPc));
+      S->de[c] = static_cast<int>(std::max<long long>(0, lo - GPc));
+    }
+  }
+  return NC;
+}
+
 template <int MODE, int VARIANT, int CG>
-int launch_tc(const CUtensorMap& own, const CUtensorMap& sk, const CUtensorMap& smn, const CUtensorMap& out,
-              const TcParams& p, int NC, bool pdl, cudaStream_t st) {
+int launch_tc(const TmSet& tms, const BwdSched& sched, const TcParams& p, int NC, bool pdl, cudaStream_t st) {
   auto kern = tc_strip_kernel<MODE, VARIANT, CG>;
   GE2E_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   TcParams q = p;
@@ -849,7 +937,7 @@ int launch_tc(const CUtensorMap& own, const CUtensorMap& sk, const CUtensorMap& 
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl ? 2 : 1;
-  GE2E_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, own, sk, smn, out, q));
+  GE2E_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tms, sched, q));
   GE2E_LAUNCHED();
   return GE2E_OK;
 }
@@ -859,15 +947,14 @@ int max_clusters_cg(int cg) {
   return cg == 2 ? max_clusters<MODE, VARIANT, 2>() : max_clusters<MODE, VARIANT, 1>();
 }
 template <int MODE, int VARIANT>
-int launch_tc_cg(int cg, const CUtensorMap& own, const CUtensorMap& sk, const CUtensorMap& smn, const CUtensorMap& out,
-                 const TcParams& p, int NC, bool pdl, cudaStream_t st) {
-  return cg == 2 ? launch_tc<MODE, VARIANT, 2>(own, sk, smn, out, p, NC, pdl, st)
-                 : launch_tc<MODE, VARIANT, 1>(own, sk, smn, out, p, NC, pdl, st);
+int launch_tc_cg(int cg, const TmSet& tms, const BwdSched& sched, const TcParams& p, int NC, bool pdl,
+                 cudaStream_t st) {
+  return cg == 2 ? launch_tc<MODE, VARIANT, 2>(tms, sched, p, NC, pdl, st)
+                 : launch_tc<MODE, VARIANT, 1>(tms, sched, p, NC, pdl, st);
 }
 
-void fill_common(TcParams& p, const RowsArgs& a, const Layout& L) {
+void fill_common(TcParams& p, const RowsArgs& a) {
   p.D = a.D; p.kslabs = a.D / kSlabCols; p.M = a.M; p.spk_offset = a.spk_offset;
-  p.OT = L.OT; p.ST = L.ST; p.OG = L.OG; p.GP = L.GP;
   p.cos_diag = a.cos_diag; p.w = a.w; p.b = a.b; p.eps = a.eps;
 }
 
@@ -907,13 +994,13 @@ int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* r
   const int U = a.n_local * a.M;
   const Layout L = fwd_layout(U, a.n_total, a.D, a.variant);
   if (ws_bytes < L.done_bytes + L.part_bytes) return GE2E_ERR_WORKSPACE;
-  CUtensorMap tmE, tmC;
-  int rc = make_map_2d(&tmE, a.e_hat, U, a.D, kTile);
+  TmSet tms{};
+  int rc = make_map_2d(&tms.own[0], a.e_hat, U, a.D, kTile);
   if (rc != GE2E_OK) return rc;
-  if ((rc = make_map_2d(&tmC, a.c_hat_all, a.n_total, a.D, kBoxRows)) != GE2E_OK) return rc;
+  if ((rc = make_map_2d(&tms.strk[0], a.c_hat_all, a.n_total, a.D, kBoxRows)) != GE2E_OK) return rc;
   TcParams p{};
-  fill_common(p, a, L);
-  p.n_own = U; p.n_str = a.n_total;
+  fill_common(p, a);
+  p.n_own[0] = U; p.n_str[0] = a.n_total; p.OT[0] = L.OT; p.ST[0] = L.ST; p.GP = L.GP;
   p.row_stat_out = row_stat; p.kstar_out = row_kstar; p.row_aux_out = row_aux; p.loss_accum = loss_accum;
   p.per_row_out = per_row_out;
   p.seg_done = static_cast<int*>(ws);
@@ -922,9 +1009,10 @@ int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* r
   // after_prep: the caller zeroed the workspace before ge2e prep and this launch directly follows the
   // prep kernel in the stream, so it may start (barrier init, TMEM allocation) under prep's tail
   if (!after_prep && !L.whole) GE2E_CUDA_TRY(cudaMemsetAsync(ws, 0, L.done_bytes, st));
+  static const BwdSched no_sched{};
   if (a.variant == GE2E_SOFTMAX)
-    return launch_tc_cg<TC_FWD, GE2E_SOFTMAX>(L.CG, tmE, tmC, tmC, tmC, p, L.NC, after_prep, st);
-  return launch_tc_cg<TC_FWD, GE2E_CONTRAST>(L.CG, tmE, tmC, tmC, tmC, p, L.NC, after_prep, st);
+    return launch_tc_cg<TC_FWD, GE2E_SOFTMAX>(L.CG, tms, no_sched, p, L.NC, after_prep, st);
+  return launch_tc_cg<TC_FWD, GE2E_CONTRAST>(L.CG, tms, no_sched, p, L.NC, after_prep, st);
 }
 
 int tc_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kstar, const float* row_aux,
@@ -932,6 +1020,25 @@ int tc_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kst
                 size_t ws_bytes, cudaStream_t st) {
   (void)row_kstar; (void)ws; (void)ws_bytes;
   const int U = a.n_local * a.M;
+  const int cg = pick_cg(a.D);
+  const int slabs = a.D / kSlabCols;
+  // segment kind DE: owner = utterance tiles, stream = centroids; DC: owner = centroid tiles, stream = utterances
+  TcParams p{};
+  fill_common(p, a);
+  p.row_stat = row_stat; p.row_aux = row_aux; p.grad_out = grad_out; p.dwdb = dwdb_accum;
+  p.n_own[SEG_DE] = U; p.n_str[SEG_DE] = a.n_total;
+  p.n_own[SEG_DC] = a.n_total; p.n_str[SEG_DC] = U;
+  for (int k = 0; k < 2; ++k) {
+    p.OT[k] = (p.n_own[k] + kTile - 1) / kTile;
+    p.ST[k] = (p.n_str[k] + kUnit - 1) / kUnit;
+  }
+  BwdSched sched{};
+  bool de_partial = false;
+  const int NC = make_bwd_sched((p.OT[SEG_DE] + cg - 1) / cg, p.ST[SEG_DE], (p.OT[SEG_DC] + cg - 1) / cg, p.ST[SEG_DC],
+                                max_clusters_cg<TC_BWD, GE2E_SOFTMAX>(cg), &sched, &de_partial);
+
+  // dC_hat is always assembled from partial accumulators (TMA reduce-add): zero it, together with
+  // {dw, db} when the caller placed them right behind it
   const size_t dc_elems = static_cast<size_t>(a.n_total) * a.D;
   if (dwdb_accum == dC_hat_partial + dc_elems) {
     GE2E_CUDA_TRY(cudaMemsetAsync(dC_hat_partial, 0, (dc_elems + 2) * sizeof(float), st));
@@ -939,39 +1046,21 @@ int tc_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kst
     GE2E_CUDA_TRY(cudaMemsetAsync(dC_hat_partial, 0, dc_elems * sizeof(float), st));
     GE2E_CUDA_TRY(cudaMemsetAsync(dwdb_accum, 0, 2 * sizeof(float), st));
   }
-  const int cg = pick_cg(a.D);
-  const Layout Le = make_layout(U, a.n_total, cg, max_clusters_cg<TC_BWD_DE, GE2E_SOFTMAX>(cg));
-  const Layout Lc = make_layout(a.n_total, U, cg, max_clusters_cg<TC_BWD_DC, GE2E_SOFTMAX>(cg));
-  const int slabs = a.D / kSlabCols;
-  CUtensorMap tmE_own, tmC_own, tmE_k, tmC_k, tmE_mn, tmC_mn, tm_dE, tm_dC;
+  if (de_partial) GE2E_CUDA_TRY(cudaMemsetAsync(dE_hat, 0, static_cast<size_t>(U) * a.D * sizeof(float), st));
+
+  TmSet tms{};
   int rc;
-  if ((rc = make_map_2d(&tm_dE, dE_hat, U, a.D, kTile)) != GE2E_OK) return rc;
-  if ((rc = make_map_2d(&tm_dC, dC_hat_partial, a.n_total, a.D, kTile)) != GE2E_OK) return rc;
-  if ((rc = make_map_2d(&tmE_own, a.e_hat, U, a.D, kTile)) != GE2E_OK) return rc;
-  if ((rc = make_map_2d(&tmC_own, a.c_hat_all, a.n_total, a.D, kTile)) != GE2E_OK) return rc;
-  if ((rc = make_map_2d(&tmC_k, a.c_hat_all, a.n_total, a.D, kBoxRows)) != GE2E_OK) return rc;
-  if ((rc = make_map_3d(&tmC_mn, a.c_hat_all, a.n_total, a.D, slabs / cg)) != GE2E_OK) return rc;
-  if ((rc = make_map_2d(&tmE_k, a.e_hat, U, a.D, kBoxRows)) != GE2E_OK) return rc;
-  if ((rc = make_map_3d(&tmE_mn, a.e_hat, U, a.D, slabs / cg)) != GE2E_OK) return rc;
+  if ((rc = make_map_2d(&tms.own[SEG_DE], a.e_hat, U, a.D, kTile)) != GE2E_OK) return rc;
+  if ((rc = make_map_2d(&tms.strk[SEG_DE], a.c_hat_all, a.n_total, a.D, kBoxRows)) != GE2E_OK) return rc;
+  if ((rc = make_map_3d(&tms.strmn[SEG_DE], a.c_hat_all, a.n_total, a.D, slabs / cg)) != GE2E_OK) return rc;
+  if ((rc = make_map_2d(&tms.out[SEG_DE], dE_hat, U, a.D, kTile)) != GE2E_OK) return rc;
+  if ((rc = make_map_2d(&tms.own[SEG_DC], a.c_hat_all, a.n_total, a.D, kTile)) != GE2E_OK) return rc;
+  if ((rc = make_map_2d(&tms.strk[SEG_DC], a.e_hat, U, a.D, kBoxRows)) != GE2E_OK) return rc;
+  if ((rc = make_map_3d(&tms.strmn[SEG_DC], a.e_hat, U, a.D, slabs / cg)) != GE2E_OK) return rc;
+  if ((rc = make_map_2d(&tms.out[SEG_DC], dC_hat_partial, a.n_total, a.D, kTile)) != GE2E_OK) return rc;
 
-  // dE_hat = (wG) C_hat: owner = utterance tiles; partial owner-group ranges add into a zeroed output
-  TcParams p{};
-  fill_common(p, a, Le);
-  p.row_stat = row_stat; p.row_aux = row_aux; p.grad_out = grad_out;
-  p.n_own = U; p.n_str = a.n_total;
-  p.acc_out = dE_hat; p.dwdb = dwdb_accum;
-  if (!Le.whole) GE2E_CUDA_TRY(cudaMemsetAsync(dE_hat, 0, static_cast<size_t>(U) * a.D * sizeof(float), st));
-  rc = (debug_skip_mask() & 4) ? GE2E_OK
-                               : launch_tc_cg<TC_BWD_DE, GE2E_SOFTMAX>(cg, tmE_own, tmC_k, tmC_mn, tm_dE, p, Le.NC, false, st);
-  if (rc != GE2E_OK) return rc;
-
-  // dC_hat = (wG)^T E_hat: owner = centroid tiles, the utterance range is cut stream-K style
-  fill_common(p, a, Lc);
-  p.n_own = a.n_total; p.n_str = U;
-  p.acc_out = dC_hat_partial; p.dwdb = nullptr;
-  p.pdl_wait_at_end = 1;      // reads nothing the dE_hat grid writes: the two overlap
-  if (debug_skip_mask() & 8) return GE2E_OK;
-  return launch_tc_cg<TC_BWD_DC, GE2E_SOFTMAX>(cg, tmC_own, tmE_k, tmE_mn, tm_dC, p, Lc.NC, !(debug_skip_mask() & 4), st);
+  if (debug_skip_mask() & 12) return GE2E_OK;
+  return launch_tc_cg<TC_BWD, GE2E_SOFTMAX>(cg, tms, sched, p, NC, false, st);
 }
 
 }  // namespace ge2e
