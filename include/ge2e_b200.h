@@ -63,10 +63,17 @@ int ge2e_b200_path(int n_local, int n_total, int M, int D, int variant, int prec
  * events into device_buf[grid][3 roles (TMA, MMA, epilogue)][64]; NULL switches it off.
  * kernel: -1 = all, 0 = forward rows, 1 = backward rows. */
 void ge2e_b200_debug_trace(unsigned long long* device_buf, int kernel);
+/* Debug, TIMING ONLY: bitmask of kernels the library stops launching (1 prep, 2 forward rows,
+ * 4|8 backward rows, 16 finalize); results are garbage while it is non-zero.  bench.py prices each
+ * kernel in situ as (step time) - (step time without it).  Initial value: env GE2E_SKIP, else 0. */
+void ge2e_b200_debug_skip(int mask);
 /* GE2E_OK if the current CUDA device can run this library (sm_100), else GE2E_ERR_DEVICE. */
 int ge2e_b200_check_device(void);
 
-/* Scratch needed by ge2e_b200_fwd_rows / ge2e_b200_bwd_rows for this shape (may be 0). */
+/* Scratch needed by ge2e_b200_fwd_rows / ge2e_b200_bwd_rows for this shape (may be 0).
+ * The workspace must be ZERO-FILLED by the caller before its first use; every call leaves it
+ * zero-filled again (stream-K bookkeeping and grid counters are reset by the last CTA that touches
+ * them), so a buffer that is kept across calls is zeroed once.  One workspace serves one stream. */
 size_t ge2e_b200_workspace_bytes(int n_local, int n_total, int M, int D, int variant,
                                  int precision);
 

@@ -11,11 +11,17 @@ static thread_local cudaError_t g_last_cuda_error = cudaSuccess;
 void set_cuda_error(cudaError_t e) { g_last_cuda_error = e; }
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+static std::atomic<int> g_skip_mask{-1};
 int debug_skip_mask() {
-  static int m = -1;
-  if (m < 0) { const char* e = getenv("GE2E_SKIP"); m = e ? atoi(e) : 0; }
+  int m = g_skip_mask.load(std::memory_order_relaxed);
+  if (m < 0) {
+    const char* e = getenv("GE2E_SKIP");
+    m = e ? atoi(e) : 0;
+    g_skip_mask.store(m, std::memory_order_relaxed);
+  }
   return m;
 }
+void set_debug_skip_mask(int m) { g_skip_mask.store(m < 0 ? 0 : m, std::memory_order_relaxed); }
 }  // namespace ge2e
 
 using namespace ge2e;
@@ -60,6 +66,8 @@ int ge2e_b200_last_cuda_error(void) { return (int)g_last_cuda_error; }
 unsigned long long ge2e_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 void ge2e_b200_debug_trace(unsigned long long* device_buf, int kernel) { tc_set_trace(device_buf, kernel); }
+
+void ge2e_b200_debug_skip(int mask) { set_debug_skip_mask(mask); }
 
 int ge2e_b200_path(int n_local, int n_total, int M, int D, int variant, int precision) {
   if (check_enum(variant, precision) != GE2E_OK) return GE2E_ERR_ARGUMENT;
@@ -188,14 +196,9 @@ int ge2e_b200_forward(const float* E, int N, int M, int D, const float* w, const
   if (!accum) return GE2E_ERR_ARGUMENT;
   int rc = check_enum(variant, precision);
   if (rc != GE2E_OK) return rc;
-  // tensor-core path: zero the stream-K bookkeeping BEFORE prep so that the two kernels are adjacent
-  // in the stream and the second one can be launched programmatically under the first one's tail
+  // tensor-core path: prep and the rows kernel are adjacent in the stream, the second one is launched
+  // programmatically under the first one's tail
   const bool tc = precision == GE2E_TF32 && N > 0 && M >= 2 && D > 0 && tc_supported(N, N, M, D, variant);
-  if (tc) {
-    if (workspace == nullptr) return GE2E_ERR_WORKSPACE;
-    if ((rc = tc_fwd_zero_workspace(N, N, M, D, variant, workspace, workspace_bytes, (cudaStream_t)stream)) != GE2E_OK)
-      return rc;
-  }
   rc = ge2e_b200_prep(E, N, M, D, precision, e_hat, c_hat, cos_diag, accum, stream);
   if (rc != GE2E_OK) return rc;
   return fwd_rows_impl(e_hat, c_hat, cos_diag, N, N, 0, M, D, w, b, eps, variant, precision, row_stat, row_kstar,

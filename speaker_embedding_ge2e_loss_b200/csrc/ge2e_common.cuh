@@ -114,6 +114,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 // GE2E_SKIP (debug, timing only): bitmask of kernels NOT to launch -- 1 prep, 2 forward rows, 4 dE_hat,
 // 8 dC_hat, 16 finalize.  Results are garbage; scripts/stage_costs.py uses it to price each kernel in situ.
 int debug_skip_mask();
+void set_debug_skip_mask(int m);
 
 // ---- launchers implemented in ge2e_simt.cu ------------------------------------------------
 struct RowsArgs {
@@ -149,8 +150,6 @@ int simt_normalize_rows(const float* X, int rows, int D, float* Y, cudaStream_t 
 bool tc_supported(int n_local, int n_total, int M, int D, int variant);
 void tc_set_trace(unsigned long long* device_buf, int mode);
 size_t tc_workspace_bytes(int n_local, int n_total, int M, int D, int variant);
-int tc_fwd_zero_workspace(int n_local, int n_total, int M, int D, int variant, void* ws, size_t ws_bytes,
-                          cudaStream_t st);
 int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* row_aux,
                 float* loss_accum, float* per_row_out, void* ws, size_t ws_bytes, bool after_prep,
                 cudaStream_t st);

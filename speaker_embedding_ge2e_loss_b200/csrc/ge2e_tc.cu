@@ -127,6 +127,9 @@ struct TcParams {
   int maxseg;
   // BWD outputs (dE_hat / dC_hat go through the `out` tensor maps)
   float* dwdb;
+  float4* zero_base;          // BWD: dC_hat, zero-filled by the kernel itself before any partial sum lands
+  long long zero_n4;          //      (float4 count)
+  int* ctr;                   // BWD: {CTAs done zero-filling, CTAs done}: zero on entry, zero again on exit
   int pdl_wait_at_end;        // unused by the current launches (kept for stand-alone launches)
   unsigned long long* trace;  // debug: [CTA][3 roles][kTraceEvents] globaltimer stamps, or nullptr
   int dbg;                    // debug (GE2E_TC_DEBUG): 1 = no TMA for stream stages, 2 = no MMA issue,
@@ -154,6 +157,7 @@ struct SharedTail {
     alignas(16) float2 xch[kTile];        // FWD: row state of the upper column half
   };
 };
+constexpr size_t kWsHeaderBytes = 256;   // workspace: [header: BWD counters][FWD seg_done][FWD seg_part]
 constexpr size_t kSmemBytes = 1024 + kMaxSlabs * kSlabBytes + kRingBytes + sizeof(SharedTail);
 static_assert(kSmemBytes <= 232448, "dynamic shared memory over the 227 KB per-CTA limit");
 
@@ -475,6 +479,29 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
       if (CG == 1) mbar_arrive(addr); else mbar_arrive_cluster(addr);
     };
 
+    bool zero_seen = false;      // (thread ew 0 / lane 0) every CTA has finished its share of the zero-fill
+    auto wait_zero_fill = [&]() {
+      if (zero_seen) return;
+      int v;
+      do {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.ctr) : "memory");
+      } while (v < static_cast<int>(gridDim.x));
+      asm volatile("fence.proxy.async;" ::: "memory");    // the TMA reduce below is an async-proxy access
+      zero_seen = true;
+    };
+    if (kBwd) {
+      // dC_hat (and {dw, db}) collect partial sums from many CTAs: zero them here instead of with
+      // memset nodes in front of the kernel.  Every CTA clears a slice while its pipeline fills and
+      // bumps ctr[0]; nobody adds before ctr[0] == gridDim.x (all CTAs are co-resident: persistent grid).
+      const int et = tid - kEpiWarp0 * 32;
+      const long long z0 = p.zero_n4 * blockIdx.x / gridDim.x, z1 = p.zero_n4 * (blockIdx.x + 1) / gridDim.x;
+      for (long long i = z0 + et; i < z1; i += kEpiThreads) p.zero_base[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (blockIdx.x == 0 && et < 2) p.dwdb[et] = 0.f;
+      __threadfence();
+      named_bar_sync(1, kEpiThreads);
+      if (et == 0) atomicAdd(p.ctr, 1);
+    }
+
     Walk wk = make_walk();
     int kind, og, s0, s1;
     for (int sg = 0; wk.next(p, kind, og, s0, s1); ++sg) {
@@ -653,6 +680,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
             if (trow == 0) {
               const int done = atomicAdd(p.seg_done + ot, s1 - s0) + (s1 - s0);
               tail->flag = (done == st);
+              if (done == st) p.seg_done[ot] = 0;      // leave the workspace zeroed for the next call
             }
             named_bar_sync(2, kTile);
             last = tail->flag != 0;
@@ -713,6 +741,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
         if (ew == 0 && lane == 0) {
           if (tile_valid) {
             const CUtensorMap* tm_out = &tms.out[kind];
+            if (!full) wait_zero_fill();
             for (int ks = 0; ks < kslabs; ++ks) {
               if (full) tma_store_2d(tm_out, ks * kSlabCols, ot * kTile, a_smem + ks * kSlabBytes);
               else tma_reduce_add_2d(tm_out, ks * kSlabCols, ot * kTile, a_smem + ks * kSlabBytes);
@@ -744,8 +773,11 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
       if (ew == 0 && lane == 0) {
         float tw = 0.f, tb = 0.f;
         for (int i = 0; i < kEpiWarps; ++i) { tw += tail->red[i]; tb += tail->red[kEpiWarps + i]; }
+        wait_zero_fill();
         atomicAdd(p.dwdb + 0, tw);
         atomicAdd(p.dwdb + 1, tb);
+        // last CTA out restores the counters
+        if (atomicAdd(p.ctr + 1, 1) == static_cast<int>(gridDim.x) - 1) { atomicExch(p.ctr, 0); atomicExch(p.ctr + 1, 0); }
       }
     }
   }
@@ -978,22 +1010,14 @@ bool tc_supported(int n_local, int n_total, int M, int D, int variant) {
 
 size_t tc_workspace_bytes(int n_local, int n_total, int M, int D, int variant) {
   const Layout L = fwd_layout(n_local * M, n_total, D, variant);
-  return L.done_bytes + L.part_bytes;
-}
-
-int tc_fwd_zero_workspace(int n_local, int n_total, int M, int D, int variant, void* ws, size_t ws_bytes,
-                          cudaStream_t st) {
-  const Layout L = fwd_layout(n_local * M, n_total, D, variant);
-  if (ws_bytes < L.done_bytes + L.part_bytes) return GE2E_ERR_WORKSPACE;
-  if (!L.whole) GE2E_CUDA_TRY(cudaMemsetAsync(ws, 0, L.done_bytes, st));
-  return GE2E_OK;
+  return kWsHeaderBytes + L.done_bytes + L.part_bytes;
 }
 
 int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* row_aux, float* loss_accum,
                 float* per_row_out, void* ws, size_t ws_bytes, bool after_prep, cudaStream_t st) {
   const int U = a.n_local * a.M;
   const Layout L = fwd_layout(U, a.n_total, a.D, a.variant);
-  if (ws_bytes < L.done_bytes + L.part_bytes) return GE2E_ERR_WORKSPACE;
+  if (ws == nullptr || ws_bytes < kWsHeaderBytes + L.done_bytes + L.part_bytes) return GE2E_ERR_WORKSPACE;
   TmSet tms{};
   int rc = make_map_2d(&tms.own[0], a.e_hat, U, a.D, kTile);
   if (rc != GE2E_OK) return rc;
@@ -1003,12 +1027,12 @@ int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* r
   p.n_own[0] = U; p.n_str[0] = a.n_total; p.OT[0] = L.OT; p.ST[0] = L.ST; p.GP = L.GP;
   p.row_stat_out = row_stat; p.kstar_out = row_kstar; p.row_aux_out = row_aux; p.loss_accum = loss_accum;
   p.per_row_out = per_row_out;
-  p.seg_done = static_cast<int*>(ws);
-  p.seg_part = reinterpret_cast<float2*>(static_cast<uint8_t*>(ws) + L.done_bytes);
+  // the workspace is zero on entry (caller's contract) and the kernel leaves it zeroed
+  p.seg_done = reinterpret_cast<int*>(static_cast<uint8_t*>(ws) + kWsHeaderBytes);
+  p.seg_part = reinterpret_cast<float2*>(static_cast<uint8_t*>(ws) + kWsHeaderBytes + L.done_bytes);
   p.maxseg = L.maxseg;
-  // after_prep: the caller zeroed the workspace before ge2e prep and this launch directly follows the
-  // prep kernel in the stream, so it may start (barrier init, TMEM allocation) under prep's tail
-  if (!after_prep && !L.whole) GE2E_CUDA_TRY(cudaMemsetAsync(ws, 0, L.done_bytes, st));
+  // after_prep: this launch directly follows the prep kernel in the stream, so it may start (barrier
+  // init, TMEM allocation) under prep's tail
   static const BwdSched no_sched{};
   if (a.variant == GE2E_SOFTMAX)
     return launch_tc_cg<TC_FWD, GE2E_SOFTMAX>(L.CG, tms, no_sched, p, L.NC, after_prep, st);
@@ -1018,7 +1042,8 @@ int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* r
 int tc_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kstar, const float* row_aux,
                 const float* grad_out, float* dE_hat, float* dC_hat_partial, float* dwdb_accum, void* ws,
                 size_t ws_bytes, cudaStream_t st) {
-  (void)row_kstar; (void)ws; (void)ws_bytes;
+  (void)row_kstar;
+  if (ws == nullptr || ws_bytes < kWsHeaderBytes) return GE2E_ERR_WORKSPACE;
   const int U = a.n_local * a.M;
   const int cg = pick_cg(a.D);
   const int slabs = a.D / kSlabCols;
@@ -1037,15 +1062,11 @@ int tc_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kst
   const int NC = make_bwd_sched((p.OT[SEG_DE] + cg - 1) / cg, p.ST[SEG_DE], (p.OT[SEG_DC] + cg - 1) / cg, p.ST[SEG_DC],
                                 max_clusters_cg<TC_BWD, GE2E_SOFTMAX>(cg), &sched, &de_partial);
 
-  // dC_hat is always assembled from partial accumulators (TMA reduce-add): zero it, together with
-  // {dw, db} when the caller placed them right behind it
-  const size_t dc_elems = static_cast<size_t>(a.n_total) * a.D;
-  if (dwdb_accum == dC_hat_partial + dc_elems) {
-    GE2E_CUDA_TRY(cudaMemsetAsync(dC_hat_partial, 0, (dc_elems + 2) * sizeof(float), st));
-  } else {
-    GE2E_CUDA_TRY(cudaMemsetAsync(dC_hat_partial, 0, dc_elems * sizeof(float), st));
-    GE2E_CUDA_TRY(cudaMemsetAsync(dwdb_accum, 0, 2 * sizeof(float), st));
-  }
+  // dC_hat is always assembled from partial accumulators (TMA reduce-add): the kernel zero-fills it
+  // (and {dw, db}) itself; D % 32 == 0 makes the row count a whole number of float4
+  p.zero_base = reinterpret_cast<float4*>(dC_hat_partial);
+  p.zero_n4 = static_cast<long long>(a.n_total) * a.D / 4;
+  p.ctr = static_cast<int*>(ws);
   if (de_partial) GE2E_CUDA_TRY(cudaMemsetAsync(dE_hat, 0, static_cast<size_t>(U) * a.D * sizeof(float), st));
 
   TmSet tms{};

@@ -40,7 +40,9 @@ def _workspace(n_local: int, n_total: int, M: int, D: int, variant: int, precisi
     nbytes = lib().ge2e_b200_workspace_bytes(n_local, n_total, M, D, variant, precision)
     if nbytes == 0:
         return None, 0
-    return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
+    # contract of the C ABI: zero on entry; the kernels leave it zeroed, so a caller that keeps the
+    # buffer (GE2EPlan) zeroes it once
+    return torch.zeros(nbytes, dtype=torch.uint8, device=device), nbytes
 
 
 # --------------------------------------------------------------------------- single device

@@ -41,7 +41,7 @@ class GE2EPlan:
         self.dE = torch.empty((N, M, D), dtype=f32, device=dev)
         self.grad_out = torch.ones((), dtype=f32, device=dev)
         nbytes = lib().ge2e_b200_workspace_bytes(N, N, M, D, self.variant, self.precision)
-        self._ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        self._ws = torch.zeros(max(nbytes, 1), dtype=torch.uint8, device=dev)   # zero once: the kernels restore it
         self._ws_bytes = nbytes
         self.loss = self._accum[0]
         self.dw = self._scratch[N * D]
