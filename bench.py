@@ -58,6 +58,16 @@ def load_peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read + dram__bytes_write per launch of `kernel`, from the committed ncu capture."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f)["dram_bytes_per_launch"].get(kernel)
+    except Exception:
+        return None
+
+
 def make_batch(N, M, D, seed=0):
     """Unit-scale random embeddings: randn rows, L2-normalised, fp32."""
     g = torch.Generator().manual_seed(seed)
@@ -361,7 +371,9 @@ def run_ours(args):
         else:
             peak, peak_note = 148 * 128 * 2 * 1.965e9 / 1e12, "nominal fp32 FMA 148 SM x 128 lanes x 2 x 1.965 GHz (SIMT path; no measured entry)"
         roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_note,
+                    "frac": achieved / peak, "traffic": ncu_traffic(dom), "peak_source": peak_note,
+                    "traffic_note": "DRAM bytes per launch from the committed ncu --set full capture (cold L2), "
+                                    "profiles/r1_ncu_v4_tc_kernels.txt; operands are L2-resident in situ",
                     "kernel_us": insitu[dom], "kernel_us_how": "in situ: step - step without the kernel (CUDA events, "
                     "rotating inputs > L2)", "algorithmic_flops": flops,
                     "note": "algorithmic flops only: the S recomputation inside the backward (another 4 U N D) is not credited",

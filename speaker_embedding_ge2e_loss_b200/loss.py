@@ -51,6 +51,10 @@ class GE2ELoss(nn.Module):
                                      self.process_group)
         return ops.ge2e_loss(embeddings, self.w, self.b, self.eps, self.variant, self.precision)
 
+    def path_for(self, N: int, M: int, D: int) -> int:
+        """Which kernels a batch of this shape runs on: 0 = SIMT fp32, 1 = tcgen05 TF32."""
+        return _lib.lib().ge2e_b200_path(N, N, M, D, _lib.VARIANTS[self.variant], _lib.PRECISIONS[self.precision])
+
     def extra_repr(self):
         return f"variant={self.variant}, precision={self.precision}, eps={self.eps}"
 

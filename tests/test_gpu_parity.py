@@ -191,6 +191,69 @@ def test_large_n_properties(pkg, precision):
     assert abs(per.double().sum().item() - got["loss"]) <= tol * abs(got["loss"])
 
 
+# ------------------------------------------------------------------ tensor-core path: shapes and schedules
+# (N, M, D, kind): row tails (N*M and N not multiples of 128), every D the TMA slabs allow, M = 2,
+# the "whole dE groups + dC filler" schedule (1024x10, 700x9) and the flat fallback cut (2048x2: few
+# utterance tiles against many centroids)
+TC_CASES = [
+    (300, 7, 64, "clustered"), (300, 7, 96, "random"), (257, 5, 128, "clustered"), (700, 9, 256, "random"),
+    (2048, 2, 256, "clustered"), (513, 3, 32, "random"), (1024, 10, 256, "random"),
+]
+
+
+@pytest.mark.parametrize("N,M,D,kind", TC_CASES)
+def test_tensor_core_path_vs_oracle(pkg, N, M, D, kind):
+    assert pkg.lib().ge2e_b200_path(N, N, M, D, 0, 1) == 1, "shape should take the tcgen05 path"
+    E = orc.make_embeddings(N, M, D, seed=N + 3 * M + D, kind=kind)
+    ref = orc.forward_backward(E, 10.0, -5.0, 1e-6, "softmax")
+    got = run_cuda(pkg, E, 10.0, -5.0, precision="tf32")
+    check(got, ref, N * M, TF32_TOL)
+    # the fp32 SIMT path on the same batch pins the tensor-core path much tighter than 2e-3 in practice
+    exact = run_cuda(pkg, E, 10.0, -5.0, precision="fp32")
+    assert rel(got["dE"], exact["dE"]) <= 5e-4
+    assert abs(got["loss"] - exact["loss"]) <= 1e-5 * abs(exact["loss"])
+
+
+def test_tensor_core_negative_w_and_upstream_gradient(pkg):
+    # w is not clamped (s3:22 is a no-op): negative w is legal; upstream gradient g != 1
+    N, M, D = 384, 4, 128
+    E = orc.make_embeddings(N, M, D, seed=21, kind="clustered")
+    ref = orc.forward_backward(E, -3.0, 0.5, 1e-6, "softmax", g=0.25)
+    got = run_cuda(pkg, E, -3.0, 0.5, precision="tf32", g=0.25)
+    check(got, ref, N * M, TF32_TOL)
+
+
+def test_tensor_core_repeated_backward_and_reuse(pkg):
+    """The workspace is zero on entry and must be zero again on exit (stream-K bookkeeping, grid
+    counters): a second backward through the same graph and a second forward+backward on the same
+    module must reproduce the first results."""
+    dev = torch.device("cuda:0")
+    N, M, D = 640, 6, 256
+    E_np = orc.make_embeddings(N, M, D, seed=5, kind="clustered")
+    crit = pkg.GE2ELoss(None, device=dev, precision="tf32")
+    E = torch.tensor(E_np, device=dev, requires_grad=True)
+    loss = crit(E)
+    loss.backward(retain_graph=True)
+    g1 = E.grad.clone()
+    E.grad = None
+    loss.backward()
+    torch.cuda.synchronize()
+    assert rel(E.grad.cpu().numpy(), g1.cpu().numpy()) <= 5e-6
+    plan = pkg.GE2EPlan(N, M, D, "softmax", "tf32", device=dev)
+    w = torch.tensor(10.0, device=dev)
+    b = torch.tensor(-5.0, device=dev)
+    Ed = torch.tensor(E_np, device=dev)
+    outs = []
+    for _ in range(3):                    # same persistent workspace three times
+        plan.step(Ed, w, b)
+        torch.cuda.synchronize()
+        outs.append((plan.loss.item(), plan.dE.clone(), plan.dw.item()))
+    for o in outs[1:]:
+        assert abs(o[0] - outs[0][0]) <= 1e-6 * abs(outs[0][0])
+        assert rel(o[1].cpu().numpy(), outs[0][1].cpu().numpy()) <= 5e-6
+    assert rel(outs[0][1].cpu().numpy().reshape(-1), g1.cpu().numpy().reshape(-1)) <= 5e-6
+
+
 # ------------------------------------------------------------------ static helpers (s5:42-43)
 def test_static_helpers_match_oracle(pkg):
     dev = torch.device("cuda:0")
