@@ -5,11 +5,11 @@
                     [--workload cfg1|cfg2|cfg3|cfg4] [--precision tf32|fp32] [--variant softmax|contrast]
 
 One "step" = one GE2E forward + backward (grads to E, w, b) over one synthetic batch.
-  value  device-resident inputs, the fwd+bwd C-ABI calls replayed from CUDA graphs.  The inputs
-         ROTATE over a set of batches larger than the 126 MB L2 (every step reads its batch from
-         HBM), the K steps run back to back and are bracketed by ONE pair of CUDA events on the
-         launching stream.  (The same step timed alone between L2 flushes carries ~6 us of
-         event/launch floor per step; it is reported next to it as ms_per_step_l2_flushed.)
+  value  device-resident inputs, the fwd+bwd C-ABI calls of K consecutive steps captured in ONE CUDA
+         graph.  The inputs ROTATE over a set of batches larger than the 126 MB L2 (every step reads
+         its batch from HBM); the K steps are bracketed by ONE pair of CUDA events on the launching
+         stream.  (One step per graph, timed alone between L2 flushes, carries ~6-9 us of graph
+         launch / event floor per step; it is reported next to it as ms_per_step_l2_flushed.)
   e2e    the public module API (GE2ELoss(...)(E); loss.backward()) with the batch in pinned HOST
          memory: H2D copy of E and D2H read of loss/dw/db inside the timed region.
   roofline      the dominant kernel priced IN SITU: (step time) - (step time with that kernel left
@@ -195,18 +195,21 @@ def timed_steps(fn, steps, warmup, flush_buf, pre=None):
     return [a.elapsed_time(b) for a, b in evs]
 
 
-def timed_back_to_back(graphs, steps, warmup):
-    """Replays graphs[k % len] for k < steps back to back inside one CUDA-event pair; ms per step."""
-    for k in range(warmup):
-        graphs[k % len(graphs)].replay()
+def timed_back_to_back(plan, batches, w, b, steps, warmup):
+    """EXACTLY `steps` steps, rotating over `batches`, captured as ONE CUDA graph (the steps are
+    stream-ordered exactly as a training loop would enqueue them).  The graph is replayed untimed
+    until at least `warmup` steps have run (the first replay of a graph also pays its upload), then
+    once more inside one CUDA-event pair.  Returns ms per step."""
+    g = plan.capture(batches, w, b, steps=steps)
+    for _ in range(max(1, -(-warmup // steps))):
+        g.replay()
     torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for k in range(steps):
-        graphs[(warmup + k) % len(graphs)].replay()
-    b.record()
+    g.replay()
+    e.record()
     torch.cuda.synchronize()
-    return a.elapsed_time(b) / steps
+    return a.elapsed_time(e) / steps
 
 
 def insitu_costs(plan, batches, w, b, steps, warmup):
@@ -217,8 +220,7 @@ def insitu_costs(plan, batches, w, b, steps, warmup):
     try:
         for name, mask in (("full", 0), ("prep", 1), ("fwd_rows", 2), ("bwd_rows", 12), ("bwd_finalize", 16)):
             h.ge2e_b200_debug_skip(mask)
-            graphs = [plan.capture(E, w, b) for E in batches]
-            out[name] = timed_back_to_back(graphs, steps, warmup) * 1e3      # microseconds per step
+            out[name] = timed_back_to_back(plan, batches, w, b, steps, warmup) * 1e3      # microseconds per step
     finally:
         h.ge2e_b200_debug_skip(0)
     full = out.pop("full")
@@ -321,14 +323,14 @@ def run_ours(args):
         batches = [make_batch(N, M, D, seed=i).to(dev) for i in range(n_rot)]
         E = batches[0]
         plan = GE2EPlan(N, M, D, args.variant, args.precision, device=dev)
-        graphs = [plan.capture(Ei, w, b) for Ei in batches]
-        launches = plan.launches_per_step * args.steps
         sampler.start()
-        ms = [timed_back_to_back(graphs, args.steps, args.warmup)] * args.steps
+        ms = [timed_back_to_back(plan, batches, w, b, args.steps, args.warmup)] * args.steps
         clocks = sampler.finish()
-        extra["ms_per_step_l2_flushed"] = float(np.mean(timed_steps(graphs[0].replay, args.steps, args.warmup, flush)))
+        g1 = plan.capture(E, w, b)
+        launches = plan.launches_per_step * args.steps
+        extra["ms_per_step_l2_flushed"] = float(np.mean(timed_steps(g1.replay, args.steps, args.warmup, flush)))
         path = plan.path
-        graphs[0].replay()
+        g1.replay()
         loss_val = plan.loss.item()
 
         # ---- e2e: public module API, host-resident batch -------------------------------------
@@ -371,7 +373,7 @@ def run_ours(args):
         else:
             peak, peak_note = 148 * 128 * 2 * 1.965e9 / 1e12, "nominal fp32 FMA 148 SM x 128 lanes x 2 x 1.965 GHz (SIMT path; no measured entry)"
         roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": ncu_traffic(dom), "peak_source": peak_note,
+                    "frac": achieved / peak, "traffic": ncu_traffic(dom) if wl == "cfg3" else None, "peak_source": peak_note,
                     "traffic_note": "DRAM bytes per launch from the committed ncu --set full capture (cold L2), "
                                     "profiles/r1_ncu_v4_tc_kernels.txt; operands are L2-resident in situ",
                     "kernel_us": insitu[dom], "kernel_us_how": "in situ: step - step without the kernel (CUDA events, "
@@ -462,7 +464,7 @@ def run_ours(args):
                    "parallelism": "replica" if world == 1 else f"speakers sharded x{world} (all-gather c_hat, reduce-scatter dC_hat)",
                    "l2": (f"inputs larger than L2: the step rotates over {n_rot} batches ({n_rot * U * D * 4 / 1e6:.0f} MB), "
                           "no flush") if world == 1 else "flushed between timed steps (256 MiB write)",
-                   "timing": "one CUDA-event pair around K back-to-back CUDA-graph replays"
+                   "timing": "one CUDA-event pair around the K steps, captured as one CUDA graph"
                    if world == 1 else "CUDA events per step, max over ranks"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "loss": loss_val,
     }

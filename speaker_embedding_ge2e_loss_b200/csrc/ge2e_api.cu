@@ -186,7 +186,7 @@ int ge2e_b200_bwd_finalize(const float* E, const float* dE_hat, const float* dC_
                            int n_local, int M, int D, const float* w, const float* b, float eps,
                            int variant, const float* grad_out, float* dE, ge2e_stream_t stream) {
   return bwd_finalize_impl(E, dE_hat, dC_hat_local, cos_diag, row_stat, row_aux, n_local, M, D, w, b, eps,
-                           variant, grad_out, dE, false, stream);
+                           variant, grad_out, dE, true, stream);
 }
 
 int ge2e_b200_forward(const float* E, int N, int M, int D, const float* w, const float* b, float eps,
@@ -216,9 +216,8 @@ int ge2e_b200_backward(const float* E, const float* e_hat, const float* c_hat, c
                               workspace_bytes, stream);
   if (rc != GE2E_OK) return rc;
   // the finalize kernel directly follows the dC_hat tensor-core kernel: programmatic launch
-  const bool tc = precision == GE2E_TF32 && variant == GE2E_SOFTMAX && tc_supported(N, N, M, D, variant);
   return bwd_finalize_impl(E, dE_hat, dC_hat, cos_diag, row_stat, row_aux, N, M, D, w, b, eps, variant,
-                           grad_out, dE, tc, stream);
+                           grad_out, dE, true, stream);
 }
 
 int ge2e_b200_centroids(const float* E, int N, int M, int D, float* C, ge2e_stream_t stream) {

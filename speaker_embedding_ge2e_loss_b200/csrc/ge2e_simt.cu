@@ -153,6 +153,7 @@ prep_warp_kernel(const float* __restrict__ E, int n_local, int M, float* __restr
   constexpr int D = KCH * 128;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int j = blockIdx.x * kPrepWarps + wid;
+  pdl_wait();        // before touching memory: the previous step's kernels may still read what this one writes
   pdl_trigger();     // the forward tensor-core kernel may set itself up while this grid runs
   if (blockIdx.x == 0 && threadIdx.x < 4 && accum != nullptr) accum[threadIdx.x] = 0.f;
   if (j >= n_local) return;
@@ -273,6 +274,7 @@ prep_reg_kernel(const float* __restrict__ E, int n_local, int M, float* __restri
   static_assert(R <= 16, "reduce16_transposed handles 16 rows");
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int j = blockIdx.x * kPrepWarps + wid;
+  pdl_wait();        // before touching memory: the previous step's kernels may still read what this one writes
   pdl_trigger();     // the forward tensor-core kernel may set itself up while this grid runs
   if (blockIdx.x == 0 && threadIdx.x < 4 && accum != nullptr) accum[threadIdx.x] = 0.f;
   if (j >= n_local) return;
@@ -798,6 +800,7 @@ finalize_warp_kernel(const float* __restrict__ E, const float* __restrict__ dE_h
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int j = blockIdx.x * kPrepWarps + wid;
   pdl_wait();        // launched with the PDL attribute: dE_hat / dC_hat come from the preceding grids
+  pdl_trigger();     // the next step's prep may be scheduled (it waits for this grid before touching memory)
   if (j >= n_local) return;
   const float w = __ldg(wp), b = __ldg(bp), g = __ldg(gp);
   const float4* Ej = reinterpret_cast<const float4*>(E + (size_t)j * M * D) + lane;
@@ -965,6 +968,7 @@ finalize_reg_kernel(const float* __restrict__ E, const float* __restrict__ dE_ha
     for (int c = 0; c < KCH; ++c)
       v[i][c] = (active && i < M) ? __ldg(Ej + (size_t)i * (D / 4) + c * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
   pdl_wait();        // launched with the PDL attribute: dE_hat / dC_hat come from the preceding grids
+  pdl_trigger();     // the next step's prep may be scheduled (it waits for this grid before touching memory)
   if (!active) return;
   const float w = __ldg(wp), b = __ldg(bp), g = __ldg(gp);
   const float4* Gj = reinterpret_cast<const float4*>(dE_hat + (size_t)j * M * D) + lane;
@@ -1236,15 +1240,17 @@ void launch_prep_warp(const float* E, int n_local, int M, bool rnd, float* e_hat
   if (KCH <= 2 && M <= kRegRows) {
     constexpr int K2 = KCH <= 2 ? KCH : 1;    // the register-resident variant is only instantiated for D <= 256
     const dim3 g(grid), bl(kPrepWarps * 32);
-#define GE2E_PREP_REG(RR)                                                                                        \
-  (rnd ? prep_reg_kernel<K2, RR, true><<<g, bl, 0, st>>>(E, n_local, M, e_hat, c_hat, cos_diag, accum)            \
-       : prep_reg_kernel<K2, RR, false><<<g, bl, 0, st>>>(E, n_local, M, e_hat, c_hat, cos_diag, accum))
+#define GE2E_PREP_REG(RR)                                                                                          \
+  (rnd ? launch_pdl(prep_reg_kernel<K2, RR, true>, g, bl, 0, st, true, E, n_local, M, e_hat, c_hat, cos_diag, accum) \
+       : launch_pdl(prep_reg_kernel<K2, RR, false>, g, bl, 0, st, true, E, n_local, M, e_hat, c_hat, cos_diag, accum))
     if (M <= 4) GE2E_PREP_REG(4); else if (M <= 8) GE2E_PREP_REG(8); else if (M <= 12) GE2E_PREP_REG(12); else GE2E_PREP_REG(16);
 #undef GE2E_PREP_REG
     return;
   }
-  if (rnd) prep_warp_kernel<KCH, true><<<grid, kPrepWarps * 32, 0, st>>>(E, n_local, M, e_hat, c_hat, cos_diag, accum);
-  else prep_warp_kernel<KCH, false><<<grid, kPrepWarps * 32, 0, st>>>(E, n_local, M, e_hat, c_hat, cos_diag, accum);
+  if (rnd) launch_pdl(prep_warp_kernel<KCH, true>, dim3(grid), dim3(kPrepWarps * 32), 0, st, true, E, n_local, M, e_hat,
+                      c_hat, cos_diag, accum);
+  else launch_pdl(prep_warp_kernel<KCH, false>, dim3(grid), dim3(kPrepWarps * 32), 0, st, true, E, n_local, M, e_hat,
+                  c_hat, cos_diag, accum);
 }
 
 template <int KCH>

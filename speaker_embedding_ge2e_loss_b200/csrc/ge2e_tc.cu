@@ -1031,12 +1031,13 @@ int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* r
   p.seg_done = reinterpret_cast<int*>(static_cast<uint8_t*>(ws) + kWsHeaderBytes);
   p.seg_part = reinterpret_cast<float2*>(static_cast<uint8_t*>(ws) + kWsHeaderBytes + L.done_bytes);
   p.maxseg = L.maxseg;
-  // after_prep: this launch directly follows the prep kernel in the stream, so it may start (barrier
-  // init, TMEM allocation) under prep's tail
+  // programmatic dependent launch: barrier init / TMEM allocation / tensormap prefetch run under the
+  // tail of whatever kernel precedes this one in the stream; the kernel waits before touching memory
+  (void)after_prep;
   static const BwdSched no_sched{};
   if (a.variant == GE2E_SOFTMAX)
-    return launch_tc_cg<TC_FWD, GE2E_SOFTMAX>(L.CG, tms, no_sched, p, L.NC, after_prep, st);
-  return launch_tc_cg<TC_FWD, GE2E_CONTRAST>(L.CG, tms, no_sched, p, L.NC, after_prep, st);
+    return launch_tc_cg<TC_FWD, GE2E_SOFTMAX>(L.CG, tms, no_sched, p, L.NC, true, st);
+  return launch_tc_cg<TC_FWD, GE2E_CONTRAST>(L.CG, tms, no_sched, p, L.NC, true, st);
 }
 
 int tc_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kstar, const float* row_aux,
@@ -1081,7 +1082,7 @@ int tc_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kst
   if ((rc = make_map_2d(&tms.out[SEG_DC], dC_hat_partial, a.n_total, a.D, kTile)) != GE2E_OK) return rc;
 
   if (debug_skip_mask() & 12) return GE2E_OK;
-  return launch_tc_cg<TC_BWD, GE2E_SOFTMAX>(cg, tms, sched, p, NC, false, st);
+  return launch_tc_cg<TC_BWD, GE2E_SOFTMAX>(cg, tms, sched, p, NC, true, st);
 }
 
 }  // namespace ge2e

@@ -69,20 +69,23 @@ class GE2EPlan:
                                   accum_ptr, self.dE.data_ptr(), ws, self._ws_bytes, stream)
         check(rc, "ge2e_b200_backward")
 
-    def capture(self, E: torch.Tensor, w: torch.Tensor, b: torch.Tensor, backward: bool = True):
-        """Capture one step into a CUDA graph bound to these tensors; returns the graph
-        (``.replay()``).  Also records how many of the library's kernels one step launches."""
+    def capture(self, E, w: torch.Tensor, b: torch.Tensor, backward: bool = True, steps: int = 1):
+        """Capture ``steps`` consecutive steps into one CUDA graph bound to these tensors; returns the
+        graph (``.replay()``).  ``E`` is one batch or a list of batches the steps rotate over.  Also
+        records how many of the library's kernels one step launches."""
+        batches = list(E) if isinstance(E, (list, tuple)) else [E]
         with torch.cuda.device(self.device):
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                self.step(E, w, b, backward)            # warm-up: lazy func attributes, module load
+                self.step(batches[0], w, b, backward)   # warm-up: lazy func attributes, module load
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             before = lib().ge2e_b200_launch_count()
             with torch.cuda.graph(g):
-                self.step(E, w, b, backward)
-            self.launches_per_step = lib().ge2e_b200_launch_count() - before
+                for k in range(steps):
+                    self.step(batches[k % len(batches)], w, b, backward)
+            self.launches_per_step = (lib().ge2e_b200_launch_count() - before) // max(1, steps)
         self._graph = g
         return g
