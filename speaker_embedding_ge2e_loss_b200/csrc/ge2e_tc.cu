@@ -919,22 +919,71 @@ int make_bwd_sched(int OGe, int STe, int OGc, int STc, int max_cl, BwdSched* S, 
   const long long GPe = static_cast<long long>(OGe) * STe, GPc = static_cast<long long>(OGc) * STc, W = GPe + GPc;
   const int NC = static_cast<int>(std::min<long long>(max_cl, W));
   const long long T = (W + NC - 1) / NC;             // balanced share, in units
-  if (2LL * STe <= T) {
-    // whole dE_hat groups per cluster, dC_hat units fill every cluster up to the same level
+  long long max_de = 0;
+  for (int c = 0; c <= NC; ++c) {
+    S->de[c] = static_cast<int>((static_cast<long long>(c) * OGe / NC) * STe);
+    if (c > 0) max_de = std::max<long long>(max_de, S->de[c] - S->de[c - 1]);
+  }
+  if (max_de <= T + T / 8) {
+    // whole dE_hat groups per cluster (no cluster ends up more than 1/8 above the balanced share),
+    // dC_hat units fill every cluster up to the same level
     *de_partial = false;
-    for (int c = 0; c <= NC; ++c) S->de[c] = static_cast<int>((static_cast<long long>(c) * OGe / NC) * STe);
+    // a dC_hat segment costs an owner-tile load and an accumulator flush on top of its units (about 3
+    // units' worth): clusters whose level share would be smaller than that get none, the rest share it
+    constexpr long long kMinDcShare = 3;
     long long wsum = 0;
     long long wgt[kMaxClusters];
-    for (int c = 0; c < NC; ++c) {
-      wgt[c] = std::max<long long>(0, T - (S->de[c + 1] - S->de[c]));
-      wsum += wgt[c];
-    }
+    for (int pass = 0; pass < 2 && wsum == 0; ++pass)
+      for (int c = 0; c < NC; ++c) {
+        wgt[c] = std::max<long long>(0, T - (S->de[c + 1] - S->de[c]));
+        if (pass == 0 && wgt[c] < kMinDcShare) wgt[c] = 0;
+        wsum += wgt[c];
+      }
     if (wsum == 0) { for (int c = 0; c < NC; ++c) wgt[c] = 1; wsum = NC; }
+    // every cluster works on ONE dC_hat owner group (a range that straddles two groups pays a second
+    // owner-tile load and a second reduce-add flush): a cluster belongs to the group that holds the
+    // midpoint of its level share, and each group's units are then split over its clusters
+    int grp[kMaxClusters];
+    long long gsum[kMaxClusters] = {0};          // OGc <= GPc / STc; only the first OGc entries are used
     long long cum = 0;
+    for (int c = 0; c < NC; ++c) {
+      const long long mid2 = GPc * (2 * cum + wgt[c]);          // 2 * wsum * midpoint
+      grp[c] = static_cast<int>(std::min<long long>(OGc - 1, mid2 / (2 * wsum * STc)));
+      if (wgt[c] > 0 && grp[c] < kMaxClusters) gsum[grp[c]] += wgt[c];
+      cum += wgt[c];
+    }
+    bool ok = OGc <= kMaxClusters;
+    for (int g = 0; g < OGc && ok; ++g) ok = gsum[g] > 0;
+    // plain proportional cut (ranges may straddle groups) ...
+    int prop[kMaxClusters + 1];
+    cum = 0;
     for (int c = 0; c <= NC; ++c) {
-      S->dc[c] = static_cast<int>(GPc * cum / wsum);
+      prop[c] = static_cast<int>(GPc * cum / wsum);
       if (c < NC) cum += wgt[c];
     }
+    auto max_load = [&](const int* dc) {
+      long long m = 0;
+      for (int c = 0; c < NC; ++c) m = std::max<long long>(m, (S->de[c + 1] - S->de[c]) + (dc[c + 1] - dc[c]));
+      return m;
+    };
+    // ... against the group-aligned cut: take it unless alignment costs more than a straddle would
+    // (about 3 units) on the most loaded cluster
+    int alig[kMaxClusters + 1];
+    if (ok) {
+      long long gcum[kMaxClusters] = {0};
+      int pos = 0;
+      for (int c = 0; c < NC; ++c) {
+        alig[c] = pos;
+        if (wgt[c] > 0) {
+          const int g = grp[c];
+          gcum[g] += wgt[c];
+          pos = static_cast<int>(static_cast<long long>(g) * STc + STc * gcum[g] / gsum[g]);
+        }
+      }
+      alig[NC] = static_cast<int>(GPc);
+      ok = max_load(alig) <= max_load(prop) + 3;
+    }
+    for (int c = 0; c <= NC; ++c) S->dc[c] = ok ? alig[c] : prop[c];
   } else {
     // dE_hat groups too coarse: flat cut of [dC pairs | dE pairs]
     *de_partial = true;
