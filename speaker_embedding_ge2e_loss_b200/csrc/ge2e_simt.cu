@@ -991,7 +991,7 @@ finalize_reg_kernel(const float* __restrict__ E, const float* __restrict__ dE_ha
       q[i] = 0.f;
 #pragma unroll
       for (int c = 0; c < KCH; ++c) {
-        const float4 gv = (i < M) ? __ldcg(Gj + (size_t)i * (D / 4) + c * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 gv = (i < M) ? __ldg(Gj + (size_t)i * (D / 4) + c * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
         q[i] += dot4(v[i][c], gv);
       }
     }
@@ -1101,7 +1101,7 @@ finalize_reg_kernel(const float* __restrict__ E, const float* __restrict__ dE_ha
 #pragma unroll
       for (int c = 0; c < KCH; ++c) {
         const float4 e = v[i][c];
-        const float4 gv = __ldcg(Gj + (size_t)i * (D / 4) + c * 32);
+        const float4 gv = __ldg(Gj + (size_t)i * (D / 4) + c * 32);
         const float ev[4] = {e.x, e.y, e.z, e.w}, gg[4] = {gv.x, gv.y, gv.z, gv.w};
         const float sv[4] = {s[c].x, s[c].y, s[c].z, s[c].w}, sdv[4] = {sd[c].x, sd[c].y, sd[c].z, sd[c].w};
         const float bv[4] = {bc[c].x, bc[c].y, bc[c].z, bc[c].w};

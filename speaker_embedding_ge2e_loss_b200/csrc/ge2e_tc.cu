@@ -169,12 +169,12 @@ __device__ __forceinline__ int cluster_of_pair(long long gp, long long GP, int N
 // The walk over a cluster's segments, identical in every warp role.
 struct Walk {
   long long gp, end;      // remaining pair range of the current part
-  long long de0, de1;     // BWD: the dE_hat part, visited after the dC_hat part
-  int kind;               // kind of the current part
+  long long gp2, end2;    // BWD: the other part, visited second
+  int kind, kind2;        // kind of the current / of the second part (kind2 < 0: no second part left)
   __device__ __forceinline__ bool next(const TcParams& p, int& kind_out, int& og, int& s0, int& s1) {
     while (gp >= end) {
-      if (kind != SEG_DC) return false;
-      kind = SEG_DE; gp = de0; end = de1;
+      if (kind2 < 0) return false;
+      kind = kind2; gp = gp2; end = end2; kind2 = -1;
     }
     const int st = p.ST[kind];
     kind_out = kind;
@@ -254,14 +254,18 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
   auto make_walk = [&]() {
     Walk wk;
     if (!kBwd) {
-      wk.kind = SEG_DE;
+      wk.kind = SEG_DE; wk.kind2 = -1;
       wk.gp = (static_cast<long long>(cl) * p.GP) / NC;
       wk.end = (static_cast<long long>(cl + 1) * p.GP) / NC;
-      wk.de0 = wk.de1 = 0;
+      wk.gp2 = wk.end2 = 0;
+    } else if ((cl & 1) == 0) {
+      // even clusters: dC_hat part first; odd clusters: dE_hat part first.  At any time half of the
+      // chip streams utterance rows (large, may spill the L2) and half streams centroids (small)
+      wk.kind = SEG_DC; wk.gp = sched.dc[cl]; wk.end = sched.dc[cl + 1];
+      wk.kind2 = SEG_DE; wk.gp2 = sched.de[cl]; wk.end2 = sched.de[cl + 1];
     } else {
-      wk.kind = SEG_DC;
-      wk.gp = sched.dc[cl]; wk.end = sched.dc[cl + 1];
-      wk.de0 = sched.de[cl]; wk.de1 = sched.de[cl + 1];
+      wk.kind = SEG_DE; wk.gp = sched.de[cl]; wk.end = sched.de[cl + 1];
+      wk.kind2 = SEG_DC; wk.gp2 = sched.dc[cl]; wk.end2 = sched.dc[cl + 1];
     }
     return wk;
   };
@@ -924,7 +928,9 @@ int make_bwd_sched(int OGe, int STe, int OGc, int STc, int max_cl, BwdSched* S, 
     S->de[c] = static_cast<int>((static_cast<long long>(c) * OGe / NC) * STe);
     if (c > 0) max_de = std::max<long long>(max_de, S->de[c] - S->de[c - 1]);
   }
-  if (max_de <= T + T / 8) {
+  static int force_flat = -1;      // GE2E_TC_FLAT=1 (debug): always use the flat cut
+  if (force_flat < 0) { const char* e = getenv("GE2E_TC_FLAT"); force_flat = e ? atoi(e) : 0; }
+  if (max_de <= T + T / 8 && !force_flat) {
     // whole dE_hat groups per cluster (no cluster ends up more than 1/8 above the balanced share),
     // dC_hat units fill every cluster up to the same level
     *de_partial = false;
