@@ -130,7 +130,6 @@ struct TcParams {
   float4* zero_base;          // BWD: dC_hat, zero-filled by the kernel itself before any partial sum lands
   long long zero_n4;          //      (float4 count)
   int* ctr;                   // BWD: {CTAs done zero-filling, CTAs done}: zero on entry, zero again on exit
-  int pdl_wait_at_end;        // unused by the current launches (kept for stand-alone launches)
   unsigned long long* trace;  // debug: [CTA][3 roles][kTraceEvents] globaltimer stamps, or nullptr
   int dbg;                    // debug (GE2E_TC_DEBUG): 1 = no TMA for stream stages, 2 = no MMA issue,
                               //                        4 = epilogue skips the math (results are garbage)
@@ -246,9 +245,18 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
   if (CG > 1) cluster_sync_all();     // the peer's barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem = tail->tmem_base;
-  // programmatic dependent launch: everything above overlapped the stream predecessor's tail
-  pdl_trigger();
-  if (!p.pdl_wait_at_end) pdl_wait();
+  // Programmatic dependent launch: everything above overlapped the stream predecessor's tail.
+  //   FWD  reads what its predecessor (prep) wrote: wait, THEN let the successor go -- a successor that
+  //        starts early may therefore assume that everything before this kernel has completed.
+  //   BWD  its operands (e_hat, c_hat) were written two kernels back (see above), only the epilogue
+  //        needs the forward's row statistics: TMA producer and MMA warp start filling the pipeline
+  //        while the forward's slowest CTAs are still running; the epilogue warps wait (below).
+  if (!kBwd) {
+    pdl_wait();
+    pdl_trigger();
+  } else {
+    pdl_trigger();
+  }
 
   // ---- this cluster's work
   auto make_walk = [&]() {
@@ -503,6 +511,8 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
       if (blockIdx.x == 0 && et < 2) p.dwdb[et] = 0.f;
       __threadfence();
       named_bar_sync(1, kEpiThreads);
+      pdl_wait();      // row_stat / row_aux (read below) come from the forward kernel; the workspace
+                       // counters may have been zeroed by the kernel right before this one
       if (et == 0) atomicAdd(p.ctr, 1);
     }
 
@@ -787,7 +797,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
   }
 
   // ------------------------------------------------------------------------- teardown
-  if (p.pdl_wait_at_end) pdl_wait();   // this grid's completion must imply the predecessor's
+  if (kBwd && warp < kEpiWarp0) pdl_wait();   // every thread of the grid has waited by the time it completes
   tc_fence_before();
   __syncthreads();
   if (CG > 1) cluster_sync_all();     // no CTA leaves while its peer may still arrive on it / read its smem
