@@ -90,6 +90,9 @@ CASES = [
     (4, 8, 256, "random"), (64, 10, 256, "random"), (64, 10, 256, "clustered"),
     (2, 16, 256, "raw"), (33, 3, 48, "clustered"), (256, 10, 256, "random"),
     (97, 7, 130, "raw"), (5, 2, 1024, "random"), (300, 4, 64, "clustered"),
+    # utterances per speaker beyond the register-resident kernels (M > 16: streaming warp kernels;
+    # M > 32: the generic shared-memory finalize), and D = 128 / 512 on the warp-per-speaker kernels
+    (24, 20, 256, "clustered"), (12, 40, 128, "random"), (16, 13, 512, "raw"), (40, 5, 128, "clustered"),
 ]
 
 
@@ -198,6 +201,7 @@ def test_large_n_properties(pkg, precision):
 TC_CASES = [
     (300, 7, 64, "clustered"), (300, 7, 96, "random"), (257, 5, 128, "clustered"), (700, 9, 256, "random"),
     (2048, 2, 256, "clustered"), (513, 3, 32, "random"), (1024, 10, 256, "random"),
+    (256, 20, 256, "clustered"), (260, 40, 128, "random"),
 ]
 
 
