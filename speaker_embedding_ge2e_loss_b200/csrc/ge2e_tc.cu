@@ -821,8 +821,34 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   return fn;
 }
 
+// Encoding a tensor map is a driver call (~2 us); a step needs ten of them and training loops come
+// back with the same buffers (caching allocators), so the last few encodings are kept per thread.
+struct MapKey {
+  const void* base; int rows, D, box, dims;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && rows == o.rows && D == o.D && box == o.box && dims == o.dims;
+  }
+};
+constexpr int kMapCache = 32;
+struct MapCache { MapKey key[kMapCache]; CUtensorMap map[kMapCache]; int next = 0, used = 0; };
+thread_local MapCache g_maps;
+
+bool map_lookup(const MapKey& k, CUtensorMap* m) {
+  for (int i = 0; i < g_maps.used; ++i)
+    if (g_maps.key[i] == k) { *m = g_maps.map[i]; return true; }
+  return false;
+}
+void map_store(const MapKey& k, const CUtensorMap& m) {
+  g_maps.key[g_maps.next] = k;
+  g_maps.map[g_maps.next] = m;
+  g_maps.next = (g_maps.next + 1) % kMapCache;
+  g_maps.used = std::min(g_maps.used + 1, kMapCache);
+}
+
 // 2-D map over X[rows, D] fp32: box = [box_rows][32 cols], 128-byte swizzle (K-major slabs).
 int make_map_2d(CUtensorMap* m, const float* base, int rows, int D, int box_rows) {
+  const MapKey key{base, rows, D, box_rows, 2};
+  if (map_lookup(key, m)) return GE2E_OK;
   auto enc = get_encode();
   if (enc == nullptr) return GE2E_ERR_LAUNCH;
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(rows)};
@@ -832,6 +858,7 @@ int make_map_2d(CUtensorMap* m, const float* base, int rows, int D, int box_rows
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS) map_store(key, *m);
   return r == CUDA_SUCCESS ? GE2E_OK : GE2E_ERR_LAUNCH;
 }
 
@@ -839,6 +866,8 @@ int make_map_2d(CUtensorMap* m, const float* base, int rows, int D, int box_rows
 // (MN-major operand chunks for MMA2: 32 k-rows x D columns per ring stage).  32-bit MN-major
 // operands must use the 32-byte-atom flavour of the 128B swizzle (UMMA SWIZZLE_128B_BASE32B).
 int make_map_3d(CUtensorMap* m, const float* base, int rows, int D, int box_slabs) {
+  const MapKey key{base, rows, D, box_slabs, 3};
+  if (map_lookup(key, m)) return GE2E_OK;
   auto enc = get_encode();
   if (enc == nullptr) return GE2E_ERR_LAUNCH;
   cuuint64_t dims[3] = {kSlabCols, static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(D / kSlabCols)};
@@ -848,6 +877,7 @@ int make_map_3d(CUtensorMap* m, const float* base, int rows, int D, int box_slab
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS) map_store(key, *m);
   return r == CUDA_SUCCESS ? GE2E_OK : GE2E_ERR_LAUNCH;
 }
 
@@ -1015,7 +1045,13 @@ int make_bwd_sched(int OGe, int STe, int OGc, int STc, int max_cl, BwdSched* S, 
 template <int MODE, int VARIANT, int CG>
 int launch_tc(const TmSet& tms, const BwdSched& sched, const TcParams& p, int NC, bool pdl, cudaStream_t st) {
   auto kern = tc_strip_kernel<MODE, VARIANT, CG>;
-  GE2E_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  static bool attr_set[64] = {false};    // per instantiation and device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    GE2E_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
   TcParams q = p;
   q.trace = (g_trace_mode < 0 || g_trace_mode == MODE) ? g_trace : nullptr;
   {

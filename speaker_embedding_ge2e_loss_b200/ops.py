@@ -36,34 +36,69 @@ def _ptr(t: Optional[Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+_WS_CACHE: dict = {}
+
+
 def _workspace(n_local: int, n_total: int, M: int, D: int, variant: int, precision: int, device):
+    """Scratch for fwd_rows / bwd_rows.  Contract of the C ABI: zero on entry; the kernels leave it
+    zeroed again, so one buffer per (device, stream, size) is zeroed once and reused (the calls on
+    one stream are ordered; another stream gets its own buffer)."""
     nbytes = lib().ge2e_b200_workspace_bytes(n_local, n_total, M, D, variant, precision)
     if nbytes == 0:
         return None, 0
-    # contract of the C ABI: zero on entry; the kernels leave it zeroed, so a caller that keeps the
-    # buffer (GE2EPlan) zeroes it once
-    return torch.zeros(nbytes, dtype=torch.uint8, device=device), nbytes
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream, nbytes)
+    ws = _WS_CACHE.get(key)
+    if ws is None:
+        if len(_WS_CACHE) > 64:
+            _WS_CACHE.clear()
+        ws = _WS_CACHE[key] = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+    return ws, nbytes
 
 
 # --------------------------------------------------------------------------- single device
-@torch.library.custom_op("ge2e_b200::fwd", mutates_args=())
-def ge2e_fwd(E: Tensor, w: Tensor, b: Tensor, eps: float, variant: int,
-             precision: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
-    """GE2ELoss.forward (reference s3:19-30).  Returns (loss, e_hat, c_hat, cos_diag, row_stat,
-    row_kstar, row_aux); everything after loss is saved for the backward."""
+class _on_device:
+    """`with torch.cuda.device(dev)` only when dev is not already current (the context manager costs
+    more host time than the checks below)."""
+
+    def __init__(self, dev):
+        self.ctx = None if dev.index is None or dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+
+
+def _fwd_impl(E: Tensor, w: Tensor, b: Tensor, eps: float, variant: int, precision: int, packed: bool):
+    """GE2ELoss.forward (reference s3:19-30) through the C ABI.  ``packed``: the per-call intermediates
+    come out of ONE allocation (views); the custom op needs non-aliasing outputs and passes False."""
     _need_cuda(E, w, b)
     E, w, b = _f32c(E), _f32c(w), _f32c(b)
     N, M, D = E.shape
     U = N * M
     dev = E.device
-    with torch.cuda.device(dev):
-        accum = torch.empty(4, dtype=torch.float32, device=dev)
-        e_hat = torch.empty((U, D), dtype=torch.float32, device=dev)
-        c_hat = torch.empty((N, D), dtype=torch.float32, device=dev)
-        cos_diag = torch.empty(U, dtype=torch.float32, device=dev)
-        row_stat = torch.empty(U, dtype=torch.float32, device=dev)
+    with _on_device(dev):
+        if packed:
+            flat = torch.empty(U * D + N * D + 3 * U + 4, dtype=torch.float32, device=dev)
+            o = 0
+            e_hat = flat[o:o + U * D].view(U, D); o += U * D
+            c_hat = flat[o:o + N * D].view(N, D); o += N * D
+            cos_diag = flat[o:o + U]; o += U
+            row_stat = flat[o:o + U]; o += U
+            row_aux = flat[o:o + U]; o += U
+            accum = flat[o:o + 4]
+        else:
+            accum = torch.empty(4, dtype=torch.float32, device=dev)
+            e_hat = torch.empty((U, D), dtype=torch.float32, device=dev)
+            c_hat = torch.empty((N, D), dtype=torch.float32, device=dev)
+            cos_diag = torch.empty(U, dtype=torch.float32, device=dev)
+            row_stat = torch.empty(U, dtype=torch.float32, device=dev)
+            row_aux = torch.empty(U, dtype=torch.float32, device=dev)
         row_kstar = torch.empty(U if variant == _lib.CONTRAST else 1, dtype=torch.int32, device=dev)
-        row_aux = torch.empty(U, dtype=torch.float32, device=dev)
         ws, ws_bytes = _workspace(N, N, M, D, variant, precision, dev)
         rc = lib().ge2e_b200_forward(E.data_ptr(), N, M, D, w.data_ptr(), b.data_ptr(), eps, variant,
                                      precision, e_hat.data_ptr(), c_hat.data_ptr(), cos_diag.data_ptr(),
@@ -71,6 +106,40 @@ def ge2e_fwd(E: Tensor, w: Tensor, b: Tensor, eps: float, variant: int,
                                      accum.data_ptr(), _ptr(ws), ws_bytes, _stream())
     check(rc, "ge2e_b200_forward")
     return accum[0], e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux
+
+
+def _bwd_impl(grad_out, E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, eps, variant, precision):
+    """loss.backward() (s4:200) through the C ABI.  Returns (dE[N,M,D], dwdb[2])."""
+    _need_cuda(grad_out, E, w, b)
+    E, w, b = _f32c(E), _f32c(w), _f32c(b)
+    g = _f32c(grad_out)
+    N, M, D = E.shape
+    U = N * M
+    dev = E.device
+    with _on_device(dev):
+        dE = torch.empty_like(E)
+        # [dE_hat (U*D) | dC_hat (N*D) | dw | db]; `accum` = start of (dw - 1) so that accum[1]=dw, accum[2]=db
+        scratch = torch.empty(U * D + N * D + 2, dtype=torch.float32, device=dev)
+        dE_hat_ptr = scratch.data_ptr()
+        dC_ptr = dE_hat_ptr + U * D * 4
+        ws, ws_bytes = _workspace(N, N, M, D, variant, precision, dev)
+        accum_ptr = dC_ptr + (N * D - 1) * 4
+        rc = lib().ge2e_b200_backward(E.data_ptr(), e_hat.data_ptr(), c_hat.data_ptr(), cos_diag.data_ptr(),
+                                      row_stat.data_ptr(), row_kstar.data_ptr(), row_aux.data_ptr(), N, M, D,
+                                      w.data_ptr(), b.data_ptr(), eps, variant, precision, g.data_ptr(),
+                                      dE_hat_ptr, dC_ptr, accum_ptr, dE.data_ptr(),
+                                      _ptr(ws), ws_bytes, _stream())
+    check(rc, "ge2e_b200_backward")
+    return dE, scratch[U * D + N * D:]
+
+
+@torch.library.custom_op("ge2e_b200::fwd", mutates_args=())
+def ge2e_fwd(E: Tensor, w: Tensor, b: Tensor, eps: float, variant: int,
+             precision: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """GE2ELoss.forward as a torch.library op (what torch.compile / export see).  Returns (loss, e_hat,
+    c_hat, cos_diag, row_stat, row_kstar, row_aux); everything after loss is saved for the backward."""
+    out = _fwd_impl(E, w, b, eps, variant, precision, packed=False)
+    return (out[0].clone(),) + out[1:]       # accum[0] is a view of accum: op outputs must not alias
 
 
 @ge2e_fwd.register_fake
@@ -86,27 +155,9 @@ def ge2e_bwd(grad_out: Tensor, E: Tensor, w: Tensor, b: Tensor, e_hat: Tensor, c
              cos_diag: Tensor, row_stat: Tensor, row_kstar: Tensor, row_aux: Tensor, eps: float, variant: int,
              precision: int) -> Tuple[Tensor, Tensor]:
     """Backward of ge2e_b200::fwd.  Returns (dE[N,M,D], dwdb[2])."""
-    _need_cuda(grad_out, E, w, b)
-    E, w, b = _f32c(E), _f32c(w), _f32c(b)
-    g = _f32c(grad_out)
-    N, M, D = E.shape
-    U = N * M
-    dev = E.device
-    with torch.cuda.device(dev):
-        dE = torch.empty_like(E)
-        dE_hat = torch.empty((U, D), dtype=torch.float32, device=dev)
-        # dC_hat followed by {dw, db}: the library zeroes both with one memset; the layout is
-        # [dC_hat (N*D) | dw | db] and `accum` = start of (dw - 1) so that accum[1]=dw, accum[2]=db
-        scratch = torch.empty(N * D + 2, dtype=torch.float32, device=dev)
-        ws, ws_bytes = _workspace(N, N, M, D, variant, precision, dev)
-        accum_ptr = scratch.data_ptr() + (N * D - 1) * 4
-        rc = lib().ge2e_b200_backward(E.data_ptr(), e_hat.data_ptr(), c_hat.data_ptr(), cos_diag.data_ptr(),
-                                      row_stat.data_ptr(), row_kstar.data_ptr(), row_aux.data_ptr(), N, M, D,
-                                      w.data_ptr(), b.data_ptr(), eps, variant, precision, g.data_ptr(),
-                                      dE_hat.data_ptr(), scratch.data_ptr(), accum_ptr, dE.data_ptr(),
-                                      _ptr(ws), ws_bytes, _stream())
-    check(rc, "ge2e_b200_backward")
-    return dE, scratch[N * D:]
+    dE, dwdb = _bwd_impl(grad_out, E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, eps, variant,
+                         precision)
+    return dE, dwdb.clone()
 
 
 @ge2e_bwd.register_fake
@@ -132,14 +183,38 @@ def _fwd_backward(ctx, g_loss, *_unused):
 ge2e_fwd.register_autograd(_fwd_backward, setup_context=_fwd_setup)
 
 
+class _GE2EEager(torch.autograd.Function):
+    """The same two C-ABI calls as ge2e_b200::fwd / ::bwd without the torch.library dispatch layers
+    (which cost ~0.2 ms of host time per step: more than the kernels at every size up to cfg3)."""
+
+    @staticmethod
+    def forward(ctx, E, w, b, eps, variant, precision):
+        loss, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux = _fwd_impl(E, w, b, eps, variant, precision,
+                                                                               packed=True)
+        ctx.save_for_backward(E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux)
+        ctx.cfg = (eps, variant, precision)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux = ctx.saved_tensors
+        eps, variant, precision = ctx.cfg
+        dE, dwdb = _bwd_impl(g_loss, E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, eps, variant,
+                             precision)
+        return dE, dwdb[0], dwdb[1], None, None, None
+
+
 def ge2e_loss(E: Tensor, w: Tensor, b: Tensor, eps: float = 1e-6, variant: str = "softmax",
               precision: str = "fp32") -> Tensor:
-    """Functional form: differentiable in E, w, b."""
+    """Functional form: differentiable in E, w, b.  Eager calls go through a plain autograd.Function;
+    under torch.compile the registered custom ops (same kernels) are used."""
     if E.dim() != 3:
         raise ValueError(f"embeddings must be [N, M, D], got {tuple(E.shape)}")
     if E.shape[1] < 2:
         raise ValueError("GE2E needs M >= 2 utterances per speaker (the reference divides by M - 1)")
-    return ge2e_fwd(E, w, b, float(eps), _lib.VARIANTS[variant], _lib.PRECISIONS[precision])[0]
+    if torch.compiler.is_compiling():
+        return ge2e_fwd(E, w, b, float(eps), _lib.VARIANTS[variant], _lib.PRECISIONS[precision])[0]
+    return _GE2EEager.apply(E, w, b, float(eps), _lib.VARIANTS[variant], _lib.PRECISIONS[precision])
 
 
 # --------------------------------------------------------------------------- staged (plain functions)

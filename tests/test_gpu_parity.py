@@ -258,6 +258,30 @@ def test_tensor_core_repeated_backward_and_reuse(pkg):
     assert rel(outs[0][1].cpu().numpy().reshape(-1), g1.cpu().numpy().reshape(-1)) <= 5e-6
 
 
+def test_custom_op_path_matches_eager_path(pkg):
+    """The torch.library ops (what torch.compile / export trace) and the lean eager autograd.Function
+    drive the same C-ABI calls: same loss and gradients, on both kernel paths."""
+    from speaker_embedding_ge2e_loss_b200 import ops
+    dev = torch.device("cuda:0")
+    for (N, M, D, prec) in ((48, 5, 128, "fp32"), (320, 4, 256, "tf32")):
+        E_np = orc.make_embeddings(N, M, D, seed=N, kind="clustered")
+        res = []
+        for use_op in (False, True):
+            E = torch.tensor(E_np, device=dev, requires_grad=True)
+            w = torch.tensor(10.0, device=dev, requires_grad=True)
+            b = torch.tensor(-5.0, device=dev, requires_grad=True)
+            if use_op:
+                loss = torch.ops.ge2e_b200.fwd(E, w, b, 1e-6, 0, 0 if prec == "fp32" else 1)[0]
+            else:
+                loss = ops.ge2e_loss(E, w, b, 1e-6, "softmax", prec)
+            loss.backward()
+            torch.cuda.synchronize()
+            res.append((loss.item(), E.grad.cpu().numpy(), w.grad.item(), b.grad.item()))
+        assert abs(res[0][0] - res[1][0]) <= 1e-6 * abs(res[0][0])
+        assert rel(res[1][1], res[0][1]) <= 5e-6
+        assert abs(res[0][2] - res[1][2]) <= 1e-5 * max(1.0, abs(res[0][2]))
+
+
 # ------------------------------------------------------------------ static helpers (s5:42-43)
 def test_static_helpers_match_oracle(pkg):
     dev = torch.device("cuda:0")
