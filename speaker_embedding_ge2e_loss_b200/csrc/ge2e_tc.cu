@@ -131,18 +131,23 @@ struct TcParams {
   long long zero_n4;          //      (float4 count)
   int* ctr;                   // BWD: {CTAs done zero-filling, CTAs done}: zero on entry, zero again on exit
   unsigned long long* trace;  // debug: [CTA][3 roles][kTraceEvents] globaltimer stamps, or nullptr
-  int dbg;                    // debug (GE2E_TC_DEBUG): 1 = no TMA for stream stages, 2 = no MMA issue,
-                              //                        4 = epilogue skips the math (results are garbage)
+  int dbg;                    // debug (GE2E_TC_DEBUG): 1 = no TMA for stream stages, 4 = epilogue skips the
+                              //   math (results are garbage), 8 = per-stage marks in the MMA warp's trace
 };
 
 constexpr int kTraceEvents = 64;
+// DBG = false compiles every hook away: the MMA issue loop is instruction-bound (a ring stage must be
+// issued in less than the ~520 clk its MMAs run), stray branches there cost real throughput.
+template <bool DBG>
 struct Tracer {
   unsigned long long* buf;
   int n;
   __device__ __forceinline__ Tracer(unsigned long long* base, int role)
-      : buf(base ? base + (static_cast<size_t>(blockIdx.x) * 3 + role) * kTraceEvents : nullptr), n(0) {}
+      : buf(DBG && base ? base + (static_cast<size_t>(blockIdx.x) * 3 + role) * kTraceEvents : nullptr), n(0) {}
   __device__ __forceinline__ void mark() {
-    if (buf != nullptr && n < kTraceEvents) buf[n++] = globaltimer_ns();
+    if (DBG) {
+      if (buf != nullptr && n < kTraceEvents) buf[n++] = globaltimer_ns();
+    }
   }
 };
 
@@ -185,7 +190,7 @@ struct Walk {
   }
 };
 
-template <int MODE, int VARIANT, int CG>
+template <int MODE, int VARIANT, int CG, bool DBG>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSched sched, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -212,6 +217,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
   // barriers the MMA warp waits on live in the leader: address them through the cluster window
   auto lbar = [&](int i) { return (CG == 2) ? mapa(bar(i), 0) : bar(i); };
   const int kslabs = p.kslabs;
+  const int dbg = DBG ? p.dbg : 0;      // compile-time 0 in the production instantiation
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tms.own[0]);
@@ -281,7 +287,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    Tracer tr(lane == 0 ? p.trace : nullptr, 0);
+    Tracer<DBG> tr(lane == 0 ? p.trace : nullptr, 0);
     tr.mark();
     int stage = 0, phase = 0;
     auto advance = [&]() { if (++stage == kStages) { stage = 0; phase ^= 1; } };
@@ -291,7 +297,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
       mbar_wait(bar(BAR_EMPTY + stage), phase ^ 1);
       if (elect_one()) {
         const uint32_t bytes = static_cast<uint32_t>(nslab * rows_cta * 128);
-        if (p.dbg & 1) {
+        if (dbg & 1) {
           if (leader) mbar_arrive(bar(BAR_FULL + stage));
         } else {
           if (leader) mbar_expect_tx(bar(BAR_FULL + stage), bytes * CG);
@@ -313,7 +319,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
       if (elect_one()) {
         const int slabs_c = kslabs / CG;
         const uint32_t bytes = static_cast<uint32_t>(slabs_c * kMma2Rows * 128);
-        if (p.dbg & 1) {
+        if (dbg & 1) {
           if (leader) mbar_arrive(bar(BAR_FULL + stage));
         } else {
           if (leader) mbar_expect_tx(bar(BAR_FULL + stage), bytes * CG);
@@ -371,45 +377,54 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
       const uint64_t dk = smem_desc(0, 16, 1024, kLayoutSw128);                        // K-major
       const uint64_t dmn = smem_desc(0, kMma2Rows * 128, 512, kLayoutSw128Base32);     // MN-major TF32
       int stage = 0, phase = 0, sg = 0, it = 0;
-      Tracer tr(lane == 0 ? p.trace : nullptr, 1);
+      Tracer<DBG> tr(lane == 0 ? p.trace : nullptr, 1);
       tr.mark();
       auto advance = [&]() { if (++stage == kStages) { stage = 0; phase ^= 1; } };
       auto commit = [&](int b) {
         if (CG == 1) umma_commit(bar(b)); else umma_commit_2cta(bar(b), kPairMask);
       };
-      auto ss = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-        if (p.dbg & 2) return;
-        if (CG == 1) umma_tf32_ss(d, da, db, idesc, acc); else umma_tf32_ss_2cta(d, da, db, idesc, acc);
+      // A stage is issued from one asm block (umma_stage_ss / umma_stage_ts) that first probes the
+      // NEXT stage's FULL barrier: when the probe succeeded the blocking wait (~200 clk even on a
+      // completed barrier) is skipped.  The loop is instruction-bound, see ge2e_tc_ptx.cuh.
+      bool ready = false;          // FULL[stage] was seen complete by the previous stage's probe
+      uint32_t leader = 0;         // lane elected to issue (same value in every lane)
+      auto stage_wait = [&]() {
+        if (DBG && (dbg & 8)) tr.mark();     // fine trace: before / after the wait for the stage's data
+        if (!ready) mbar_wait(bar(BAR_FULL + stage), phase);
+        if (DBG && (dbg & 8)) tr.mark();
+        tc_fence_after();
       };
-      auto ts = [&](uint32_t d, uint32_t a, uint64_t db, uint32_t idesc, uint32_t acc) {
-        if (p.dbg & 2) return;
-        if (CG == 1) umma_tf32_ts(d, a, db, idesc, acc); else umma_tf32_ts_2cta(d, a, db, idesc, acc);
+      auto next_bar = [&]() { return bar(BAR_FULL + (stage + 1 == kStages ? 0 : stage + 1)); };
+      auto next_par = [&]() { return static_cast<uint32_t>(stage + 1 == kStages ? (phase ^ 1) : phase); };
+      auto stage_done = [&](uint32_t probe) {
+        __syncwarp();
+        ready = __shfl_sync(0xffffffffu, probe, leader) != 0;
+        advance();
       };
-      // MMA1 over one stage holding `nslab` K-slabs of [rows_cta x 32] starting at slab ks0
-      auto mma1_stage = [&](uint32_t d_tmem, int n, int rows_cta, int ks0, int nslab, bool first_of_seg) {
+      // MMA1 over one stage holding `nslab` (1 or 2) K-slabs of [rows_cta x 32] starting at slab ks0
+      auto mma1_stage = [&](uint32_t d_tmem, uint32_t idesc1, int rows_cta, int ks0, int nslab, bool first_of_seg) {
         if (first_of_seg) {
           for (int sl = 0; sl < nslab; ++sl) mbar_wait(bar(BAR_A_FULL + ks0 + sl), sg & 1);
         }
-        mbar_wait(bar(BAR_FULL + stage), phase);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t idesc1 = idesc_tf32(kTile * CG, n, 0, 0);
-          for (int sl = 0; sl < nslab; ++sl) {
-            const uint64_t da = dk | ((a_smem + (ks0 + sl) * kSlabBytes) >> 4);
-            const uint64_t db = dk | ((ring_smem + stage * kStageBytes + sl * rows_cta * 128) >> 4);
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)     // +32 B per K step of 8 inside the 128 B swizzled row
-              ss(d_tmem, da + 2 * k4, db + 2 * k4, idesc1, ((ks0 + sl) | k4) != 0);
-          }
-          commit(BAR_EMPTY + stage);
+        stage_wait();
+        uint32_t probe = 0;
+        if (elect_leader(leader)) {
+          const uint64_t da = dk | ((a_smem + ks0 * kSlabBytes) >> 4);
+          const uint64_t db = dk | ((ring_smem + stage * kStageBytes) >> 4);
+          const uint32_t eb = bar(BAR_EMPTY + stage);
+          if (nslab == 2)
+            probe = umma_stage_ss<CG, 2>(d_tmem, da, db, kSlabBytes >> 4, static_cast<uint32_t>(rows_cta * 128) >> 4,
+                                         idesc1, ks0 != 0, eb, next_bar(), next_par());
+          else
+            probe = umma_stage_ss<CG, 1>(d_tmem, da, db, 0, 0, idesc1, ks0 != 0, eb, next_bar(), next_par());
         }
-        __syncwarp();
-        advance();
+        stage_done(probe);
       };
+      const uint32_t idesc_unit = idesc_tf32(kTile * CG, kUnit, 0, 0);
       auto mma1_unit = [&](int iter, bool first_of_seg) {   // BWD: n = 128 into T[iter & 1]
         const uint32_t d_tmem = tmem + (iter & 1) * kUnit;
         for (int ks = 0; ks < kslabs; ks += 2)
-          mma1_stage(d_tmem, kUnit, kUnit / CG, ks, min(2, kslabs - ks), first_of_seg);
+          mma1_stage(d_tmem, idesc_unit, kUnit / CG, ks, min(2, kslabs - ks), first_of_seg);
         if (elect_one()) commit(BAR_S_FULL + (iter & 1));
         __syncwarp();
       };
@@ -417,19 +432,17 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
         const uint32_t a_tmem = tmem + (iter & 1) * kUnit;
         const uint32_t d_tmem = tmem + 2 * kUnit;
         for (int kc = 0; kc < kUnit / kMma2Rows; ++kc) {
-          mbar_wait(bar(BAR_FULL + stage), phase);
-          tc_fence_after();
-          if (elect_one()) {
+          stage_wait();
+          uint32_t probe = 0;
+          if (elect_leader(leader)) {
             // MN-major TF32 operand: 32-byte-atom 128B swizzle, chunks of 32 columns kMma2Rows*128 B
             // apart (LBO), groups of 4 k-rows 512 B apart (SBO); one MMA consumes 8 k-rows = 1024 B
             const uint64_t db = dmn | ((ring_smem + stage * kStageBytes) >> 4);
-#pragma unroll
-            for (int k2 = 0; k2 < kMma2Rows / 8; ++k2)
-              ts(d_tmem, a_tmem + kc * kMma2Rows + k2 * 8, db + 64 * k2, idesc2, !(first && kc == 0 && k2 == 0));
-            commit(BAR_EMPTY + stage);
+            static_assert(kMma2Rows == 32, "umma_stage_ts issues 4 MMAs of 8 k-rows");
+            probe = umma_stage_ts<CG>(d_tmem, a_tmem + kc * kMma2Rows, db, idesc2, !(first && kc == 0),
+                                      bar(BAR_EMPTY + stage), next_bar(), next_par());
           }
-          __syncwarp();
-          advance();
+          stage_done(probe);
         }
       };
       Walk wk = make_walk();
@@ -441,7 +454,8 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
             mbar_wait(bar(BAR_S_EMPTY + (it & 1)), ((it >> 1) & 1) ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem + (it & 1) * (kStepUnits * kUnit);
-            for (int ks = 0; ks < kslabs; ++ks) mma1_stage(d_tmem, nu * kUnit, nu * kUnit / CG, ks, 1, u == s0);
+            const uint32_t idesc_step = idesc_tf32(kTile * CG, nu * kUnit, 0, 0);
+            for (int ks = 0; ks < kslabs; ++ks) mma1_stage(d_tmem, idesc_step, nu * kUnit / CG, ks, 1, u == s0);
             if (elect_one()) commit(BAR_S_FULL + (it & 1));
             __syncwarp();
             tr.mark();   // step issued
@@ -483,7 +497,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
     const float wg = w * g;
     float dw_acc = 0.f, db_acc = 0.f, loss_acc = 0.f;
     int it = 0;
-    Tracer tr((trow == 0 && half == 0) ? p.trace : nullptr, 2);
+    Tracer<DBG> tr((trow == 0 && half == 0) ? p.trace : nullptr, 2);
     tr.mark();
     // epilogue -> MMA signals go to the leader CTA of the pair
     const uint32_t s_empty0 = lbar(BAR_S_EMPTY), g_full0 = lbar(BAR_G_FULL), acc_empty = lbar(BAR_ACC_EMPTY);
@@ -567,7 +581,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
           uint32_t v[32];
           tmem_ld32(t_addr + ch * 32, v);
           tmem_ld_wait();
-          if (p.dbg & 4) {
+          if (dbg & 4) {
             if (kBwd) tmem_st32(t_addr + ch * 32, v);
             continue;
           }
@@ -884,6 +898,12 @@ int make_map_3d(CUtensorMap* m, const float* base, int rows, int D, int box_slab
 unsigned long long* g_trace = nullptr;   // set through tc_set_trace (debug only)
 int g_trace_mode = -1;                   // -1: every kernel, else only TC_FWD / TC_BWD
 
+int debug_knobs() {
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("GE2E_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+  return dbg;
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -911,6 +931,7 @@ int pick_cg(int D) {
 // How many clusters of size CG can be co-resident (1 CTA per SM: the kernel needs ~225 KB smem).
 template <int MODE, int VARIANT, int CG>
 int max_clusters() {
+  constexpr bool DBG = false;
   static int cache = 0;
   if (cache == 0) {
     int n = 0;
@@ -923,12 +944,13 @@ int max_clusters() {
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
-      cudaFuncSetAttribute(tc_strip_kernel<MODE, VARIANT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaFuncSetAttribute(tc_strip_kernel<MODE, VARIANT, CG, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)kSmemBytes);
-      if (cudaOccupancyMaxActiveClusters(&n, tc_strip_kernel<MODE, VARIANT, CG>, &cfg) != cudaSuccess) n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, tc_strip_kernel<MODE, VARIANT, CG, DBG>, &cfg) != cudaSuccess) n = 0;
       (void)cudaGetLastError();
     }
     if (n <= 0) n = sm_count() / CG;
+    if (const char* e = getenv("GE2E_TC_MAXCL")) { const int cap = atoi(e); if (cap > 0) n = std::min(n, cap); }   // debug
     cache = std::min(n, kMaxClusters);
   }
   return cache;
@@ -1042,9 +1064,9 @@ int make_bwd_sched(int OGe, int STe, int OGc, int STc, int max_cl, BwdSched* S, 
   return NC;
 }
 
-template <int MODE, int VARIANT, int CG>
-int launch_tc(const TmSet& tms, const BwdSched& sched, const TcParams& p, int NC, bool pdl, cudaStream_t st) {
-  auto kern = tc_strip_kernel<MODE, VARIANT, CG>;
+template <int MODE, int VARIANT, int CG, bool DBG>
+int launch_tc_impl(const TmSet& tms, const BwdSched& sched, const TcParams& p, int NC, bool pdl, cudaStream_t st) {
+  auto kern = tc_strip_kernel<MODE, VARIANT, CG, DBG>;
   static bool attr_set[64] = {false};    // per instantiation and device
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1054,11 +1076,7 @@ int launch_tc(const TmSet& tms, const BwdSched& sched, const TcParams& p, int NC
   }
   TcParams q = p;
   q.trace = (g_trace_mode < 0 || g_trace_mode == MODE) ? g_trace : nullptr;
-  {
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("GE2E_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
-    q.dbg = dbg;
-  }
+  q.dbg = debug_knobs();
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(NC * CG);
   cfg.blockDim = dim3(kThreadsTc);
@@ -1073,6 +1091,13 @@ int launch_tc(const TmSet& tms, const BwdSched& sched, const TcParams& p, int NC
   GE2E_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tms, sched, q));
   GE2E_LAUNCHED();
   return GE2E_OK;
+}
+
+// the instrumented instantiation runs only while a trace buffer is set or GE2E_TC_DEBUG is non-zero
+template <int MODE, int VARIANT, int CG>
+int launch_tc(const TmSet& tms, const BwdSched& sched, const TcParams& p, int NC, bool pdl, cudaStream_t st) {
+  if (g_trace != nullptr || debug_knobs() != 0) return launch_tc_impl<MODE, VARIANT, CG, true>(tms, sched, p, NC, pdl, st);
+  return launch_tc_impl<MODE, VARIANT, CG, false>(tms, sched, p, NC, pdl, st);
 }
 
 template <int MODE, int VARIANT>

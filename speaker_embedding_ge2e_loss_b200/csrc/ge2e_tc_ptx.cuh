@@ -30,25 +30,33 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// Spin on try_wait (hardware-suspended).  A wait that never completes is a programming error in
-// the pipeline: trap after 2 s of wall time instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
+// One try_wait (hardware-suspended up to a time limit); the common case in a running pipeline.
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+// Slow path, out of line so that the hot loops stay small.  A wait that never completes is a
+// programming error in the pipeline: trap after 2 s of wall time instead of hanging the GPU.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   uint64_t t0 = 0;
-  for (uint32_t spins = 0; !done; ++spins) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (!done && (spins & 255u) == 255u) {
+  for (uint32_t spins = 0;; ++spins) {
+    if (mbar_try_wait(bar, parity)) return;
+    if ((spins & 255u) == 255u) {
       const uint64_t t = globaltimer_ns();
       if (t0 == 0) t0 = t;
       else if (t - t0 > 2000000000ull) __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 
 // ---------------------------------------------------------------- TMA
@@ -272,6 +280,98 @@ __device__ __forceinline__ void tma_load_3d_2cta(uint32_t dst, const void* tmap,
       "[%0], [%1, {%2, %3, %4}], [%5];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(z), "r"(cluster_bar)
       : "memory");
+}
+
+
+// ---------------------------------------------------------------- one ring stage per asm block
+// The MMA warp's loop is instruction-bound: a ring stage has to be issued in less than the ~520 clk
+// its MMAs run, and an mbarrier.try_wait on an already-complete barrier alone costs ~200 clk.  These
+// helpers issue, from ONE asm block, (1) a non-blocking probe of the NEXT stage's FULL barrier,
+// (2) the stage's MMAs and (3) the commit that releases the stage; the probe's latency overlaps
+// with the MMA issue and the caller skips the blocking wait when the probe already succeeded.
+// All return the probe result.  Descriptors advance by 2 (= 32 bytes >> 4) per K step of 8.
+#define GE2E_MMA_SS(CGS) "tcgen05.mma.cta_group::" CGS ".kind::tf32 [%1], a, b, %6, "
+#define GE2E_STAGE_SS_BODY(CGS, COMMIT)                                                             \
+  "{\n\t.reg .pred pn, pa, pt;\n\t.reg .b64 a, b, sa, sb;\n\t"                                       \
+  "mbarrier.test_wait.parity.shared::cta.b64 pn, [%9], %10;\n\t"                                     \
+  "setp.ne.b32 pa, %7, 0;\n\tsetp.eq.b32 pt, %7, %7;\n\t"                                            \
+  "cvt.u64.u32 sa, %4;\n\tcvt.u64.u32 sb, %5;\n\t"                                                   \
+  "mov.b64 a, %2;\n\tmov.b64 b, %3;\n\t" GE2E_MMA_SS(CGS) "pa;\n\t"                                  \
+  "add.u64 a, a, 2;\n\tadd.u64 b, b, 2;\n\t" GE2E_MMA_SS(CGS) "pt;\n\t"                              \
+  "add.u64 a, a, 2;\n\tadd.u64 b, b, 2;\n\t" GE2E_MMA_SS(CGS) "pt;\n\t"                              \
+  "add.u64 a, a, 2;\n\tadd.u64 b, b, 2;\n\t" GE2E_MMA_SS(CGS) "pt;\n\t"
+#define GE2E_STAGE_SS_SLAB2(CGS)                                                                    \
+  "add.u64 a, %2, sa;\n\tadd.u64 b, %3, sb;\n\t" GE2E_MMA_SS(CGS) "pt;\n\t"                          \
+  "add.u64 a, a, 2;\n\tadd.u64 b, b, 2;\n\t" GE2E_MMA_SS(CGS) "pt;\n\t"                              \
+  "add.u64 a, a, 2;\n\tadd.u64 b, b, 2;\n\t" GE2E_MMA_SS(CGS) "pt;\n\t"                              \
+  "add.u64 a, a, 2;\n\tadd.u64 b, b, 2;\n\t" GE2E_MMA_SS(CGS) "pt;\n\t"
+#define GE2E_COMMIT_1 "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+#define GE2E_COMMIT_2 \
+  "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%8], %11;\n\t"
+#define GE2E_STAGE_END "selp.u32 %0, 1, 0, pn;\n\t}"
+
+// NSLAB (1 or 2) K-slabs of 32 columns, both operands from shared memory (K-major, 128B swizzle):
+// 4 * NSLAB MMAs.  a_step / b_step: descriptor distance (bytes >> 4) between the two slabs.
+template <int CG, int NSLAB>
+__device__ __forceinline__ uint32_t umma_stage_ss(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t a_step,
+                                                  uint32_t b_step, uint32_t idesc, uint32_t acc_first,
+                                                  uint32_t empty_bar, uint32_t probe_bar, uint32_t probe_parity) {
+  uint32_t ready;
+  const uint16_t mask = 3;
+  if (CG == 1 && NSLAB == 1)
+    asm volatile(GE2E_STAGE_SS_BODY("1", 1) GE2E_COMMIT_1 GE2E_STAGE_END
+                 : "=r"(ready) : "r"(d_tmem), "l"(da), "l"(db), "r"(a_step), "r"(b_step), "r"(idesc), "r"(acc_first),
+                   "r"(empty_bar), "r"(probe_bar), "r"(probe_parity), "h"(mask) : "memory");
+  else if (CG == 1)
+    asm volatile(GE2E_STAGE_SS_BODY("1", 1) GE2E_STAGE_SS_SLAB2("1") GE2E_COMMIT_1 GE2E_STAGE_END
+                 : "=r"(ready) : "r"(d_tmem), "l"(da), "l"(db), "r"(a_step), "r"(b_step), "r"(idesc), "r"(acc_first),
+                   "r"(empty_bar), "r"(probe_bar), "r"(probe_parity), "h"(mask) : "memory");
+  else if (NSLAB == 1)
+    asm volatile(GE2E_STAGE_SS_BODY("2", 2) GE2E_COMMIT_2 GE2E_STAGE_END
+                 : "=r"(ready) : "r"(d_tmem), "l"(da), "l"(db), "r"(a_step), "r"(b_step), "r"(idesc), "r"(acc_first),
+                   "r"(empty_bar), "r"(probe_bar), "r"(probe_parity), "h"(mask) : "memory");
+  else
+    asm volatile(GE2E_STAGE_SS_BODY("2", 2) GE2E_STAGE_SS_SLAB2("2") GE2E_COMMIT_2 GE2E_STAGE_END
+                 : "=r"(ready) : "r"(d_tmem), "l"(da), "l"(db), "r"(a_step), "r"(b_step), "r"(idesc), "r"(acc_first),
+                   "r"(empty_bar), "r"(probe_bar), "r"(probe_parity), "h"(mask) : "memory");
+  return ready;
+}
+
+// 4 MMAs with A from tensor memory (8 columns = 8 k per MMA) and B MN-major from shared memory
+// (descriptor advances by 64 = 1024 bytes >> 4 per 8 k-rows).
+#define GE2E_MMA_TS(CGS) "tcgen05.mma.cta_group::" CGS ".kind::tf32 [%1], [ta], b, %6, "
+#define GE2E_STAGE_TS_BODY(CGS)                                                                     \
+  "{\n\t.reg .pred pn, pa, pt;\n\t.reg .b64 b;\n\t.reg .b32 ta;\n\t"                                 \
+  "mbarrier.test_wait.parity.shared::cta.b64 pn, [%9], %10;\n\t"                                     \
+  "setp.ne.b32 pa, %7, 0;\n\tsetp.eq.b32 pt, %7, %7;\n\t"                                            \
+  "mov.b32 ta, %2;\n\tmov.b64 b, %3;\n\t" GE2E_MMA_TS(CGS) "pa;\n\t"                                 \
+  "add.u32 ta, ta, 8;\n\tadd.u64 b, b, 64;\n\t" GE2E_MMA_TS(CGS) "pt;\n\t"                           \
+  "add.u32 ta, ta, 8;\n\tadd.u64 b, b, 64;\n\t" GE2E_MMA_TS(CGS) "pt;\n\t"                           \
+  "add.u32 ta, ta, 8;\n\tadd.u64 b, b, 64;\n\t" GE2E_MMA_TS(CGS) "pt;\n\t"
+template <int CG>
+__device__ __forceinline__ uint32_t umma_stage_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t idesc,
+                                                  uint32_t acc_first, uint32_t empty_bar, uint32_t probe_bar,
+                                                  uint32_t probe_parity) {
+  uint32_t ready;
+  const uint16_t mask = 3;
+  const uint32_t unused = 0;
+  if (CG == 1)
+    asm volatile(GE2E_STAGE_TS_BODY("1") GE2E_COMMIT_1 GE2E_STAGE_END
+                 : "=r"(ready) : "r"(d_tmem), "r"(a_tmem), "l"(db), "r"(unused), "r"(unused), "r"(idesc), "r"(acc_first),
+                   "r"(empty_bar), "r"(probe_bar), "r"(probe_parity), "h"(mask) : "memory");
+  else
+    asm volatile(GE2E_STAGE_TS_BODY("2") GE2E_COMMIT_2 GE2E_STAGE_END
+                 : "=r"(ready) : "r"(d_tmem), "r"(a_tmem), "l"(db), "r"(unused), "r"(unused), "r"(idesc), "r"(acc_first),
+                   "r"(empty_bar), "r"(probe_bar), "r"(probe_parity), "h"(mask) : "memory");
+  return ready;
+}
+
+// elect.sync with the leader's lane id (the same for every lane of the warp)
+__device__ __forceinline__ bool elect_leader(uint32_t& leader) {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync %1|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(pred), "=r"(leader));
+  return pred != 0;
 }
 
 // ---------------------------------------------------------------- tcgen05: TMEM <-> registers
