@@ -152,6 +152,36 @@ int ge2e_b200_backward(const float* E, const float* e_hat, const float* c_hat,
                        float* dC_hat, float* accum, float* dE, void* workspace,
                        size_t workspace_bytes, ge2e_stream_t stream);
 
+/* ---- row-indexed variants (the trainer's unperm gather) ------------- */
+
+/* The trainer shuffles the utterances before the embedder and undoes the shuffle right before the
+ * loss: `embeddings = embeddings[unperm]; embeddings.reshape(N, M, D)` (s4_train_embed_model.py:
+ * 177-192), a row gather whose autograd backward is a row scatter.  The _indexed entry points fold
+ * both into the loss: E (and dE) stay in the embedder's row order, logical row r = [speaker][utterance]
+ * lives at physical row row_index[r] (int32, device, a permutation of [0, n_local * M)).  Prep reads
+ * through the index, finalize writes dE through it; everything in between is unchanged.
+ * row_index == NULL is the plain call.                                                     */
+int ge2e_b200_prep_indexed(const float* E, const int32_t* row_index, int n_local, int M, int D,
+                           int precision, float* e_hat, float* c_hat_local, float* cos_diag,
+                           float* accum, ge2e_stream_t stream);
+int ge2e_b200_bwd_finalize_indexed(const float* E, const int32_t* row_index, const float* dE_hat,
+                                   const float* dC_hat_local, const float* cos_diag,
+                                   const float* row_stat, const float* row_aux, int n_local, int M,
+                                   int D, const float* w, const float* b, float eps, int variant,
+                                   const float* grad_out, float* dE, ge2e_stream_t stream);
+int ge2e_b200_forward_indexed(const float* E, const int32_t* row_index, int N, int M, int D,
+                              const float* w, const float* b, float eps, int variant, int precision,
+                              float* e_hat, float* c_hat, float* cos_diag, float* row_stat,
+                              int32_t* row_kstar, float* row_aux, float* accum, void* workspace,
+                              size_t workspace_bytes, ge2e_stream_t stream);
+int ge2e_b200_backward_indexed(const float* E, const int32_t* row_index, const float* e_hat,
+                               const float* c_hat, const float* cos_diag, const float* row_stat,
+                               const int32_t* row_kstar, const float* row_aux, int N, int M, int D,
+                               const float* w, const float* b, float eps, int variant, int precision,
+                               const float* grad_out, float* dE_hat, float* dC_hat, float* accum,
+                               float* dE, void* workspace, size_t workspace_bytes,
+                               ge2e_stream_t stream);
+
 /* ---- static helpers of the reference class (used by s5_eval_model.py:42-43) ----------- */
 
 /* get_centroids (s3:33-38): C[N, D] = mean over utterances. */

@@ -42,6 +42,16 @@ PROTOTYPES = {
     "ge2e_b200_backward": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _i32p, _f32p, C.c_int, C.c_int,
                                      C.c_int, _f32p, _f32p, C.c_float, C.c_int, C.c_int, _f32p, _f32p,
                                      _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, _stream]),
+    "ge2e_b200_prep_indexed": (C.c_int, [_f32p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p,
+                                         _f32p, _stream]),
+    "ge2e_b200_bwd_finalize_indexed": (C.c_int, [_f32p, _i32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int,
+                                                 C.c_int, _f32p, _f32p, C.c_float, C.c_int, _f32p, _f32p, _stream]),
+    "ge2e_b200_forward_indexed": (C.c_int, [_f32p, _i32p, C.c_int, C.c_int, C.c_int, _f32p, _f32p, C.c_float, C.c_int,
+                                            C.c_int, _f32p, _f32p, _f32p, _f32p, _i32p, _f32p, _f32p, C.c_void_p,
+                                            C.c_size_t, _stream]),
+    "ge2e_b200_backward_indexed": (C.c_int, [_f32p, _i32p, _f32p, _f32p, _f32p, _f32p, _i32p, _f32p, C.c_int, C.c_int,
+                                             C.c_int, _f32p, _f32p, C.c_float, C.c_int, C.c_int, _f32p, _f32p,
+                                             _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, _stream]),
     "ge2e_b200_centroids": (C.c_int, [_f32p, C.c_int, C.c_int, C.c_int, _f32p, _stream]),
     "ge2e_b200_utterance_centroids": (C.c_int, [_f32p, C.c_int, C.c_int, C.c_int, _f32p, _stream]),
     "ge2e_b200_normalize_rows": (C.c_int, [_f32p, C.c_int, C.c_int, _f32p, _stream]),

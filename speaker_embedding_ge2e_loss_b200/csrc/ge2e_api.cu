@@ -88,15 +88,21 @@ size_t ge2e_b200_workspace_bytes(int n_local, int n_total, int M, int D, int var
   return 0;
 }
 
-int ge2e_b200_prep(const float* E, int n_local, int M, int D, int precision, float* e_hat,
-                   float* c_hat_local, float* cos_diag, float* accum, ge2e_stream_t stream) {
+int ge2e_b200_prep_indexed(const float* E, const int32_t* row_index, int n_local, int M, int D, int precision,
+                           float* e_hat, float* c_hat_local, float* cos_diag, float* accum,
+                           ge2e_stream_t stream) {
   if (!E || !e_hat || !c_hat_local || !cos_diag) return GE2E_ERR_ARGUMENT;
   int rc = check_shape(n_local, n_local, 0, M, D);
   if (rc != GE2E_OK) return rc;
   if ((rc = check_enum(GE2E_SOFTMAX, precision)) != GE2E_OK) return rc;
   if (debug_skip_mask() & 1) return GE2E_OK;
-  return simt_prep(E, n_local, M, D, precision == GE2E_TF32, e_hat, c_hat_local, cos_diag, accum,
+  return simt_prep(E, row_index, n_local, M, D, precision == GE2E_TF32, e_hat, c_hat_local, cos_diag, accum,
                    (cudaStream_t)stream);
+}
+
+int ge2e_b200_prep(const float* E, int n_local, int M, int D, int precision, float* e_hat,
+                   float* c_hat_local, float* cos_diag, float* accum, ge2e_stream_t stream) {
+  return ge2e_b200_prep_indexed(E, nullptr, n_local, M, D, precision, e_hat, c_hat_local, cos_diag, accum, stream);
 }
 
 static int fwd_rows_impl(const float* e_hat, const float* c_hat_all, const float* cos_diag,
@@ -166,7 +172,7 @@ int ge2e_b200_bwd_rows(const float* e_hat, const float* c_hat_all, const float* 
                        (cudaStream_t)stream);
 }
 
-static int bwd_finalize_impl(const float* E, const float* dE_hat, const float* dC_hat_local,
+static int bwd_finalize_impl(const float* E, const int32_t* row_index, const float* dE_hat, const float* dC_hat_local,
                            const float* cos_diag, const float* row_stat, const float* row_aux,
                            int n_local, int M, int D, const float* w, const float* b, float eps,
                            int variant, const float* grad_out, float* dE, bool pdl, ge2e_stream_t stream) {
@@ -177,32 +183,65 @@ static int bwd_finalize_impl(const float* E, const float* dE_hat, const float* d
   if (rc != GE2E_OK) return rc;
   if ((rc = check_enum(variant, GE2E_FP32)) != GE2E_OK) return rc;
   if (debug_skip_mask() & 16) return GE2E_OK;
-  return simt_bwd_finalize(E, dE_hat, dC_hat_local, cos_diag, row_stat, row_aux, n_local, M, D, w, b, eps,
+  return simt_bwd_finalize(E, row_index, dE_hat, dC_hat_local, cos_diag, row_stat, row_aux, n_local, M, D, w, b, eps,
                            variant, grad_out, dE, pdl, (cudaStream_t)stream);
+}
+
+int ge2e_b200_bwd_finalize_indexed(const float* E, const int32_t* row_index, const float* dE_hat,
+                                   const float* dC_hat_local, const float* cos_diag, const float* row_stat,
+                                   const float* row_aux, int n_local, int M, int D, const float* w, const float* b,
+                                   float eps, int variant, const float* grad_out, float* dE,
+                                   ge2e_stream_t stream) {
+  return bwd_finalize_impl(E, row_index, dE_hat, dC_hat_local, cos_diag, row_stat, row_aux, n_local, M, D, w, b, eps,
+                           variant, grad_out, dE, true, stream);
 }
 
 int ge2e_b200_bwd_finalize(const float* E, const float* dE_hat, const float* dC_hat_local,
                            const float* cos_diag, const float* row_stat, const float* row_aux,
                            int n_local, int M, int D, const float* w, const float* b, float eps,
                            int variant, const float* grad_out, float* dE, ge2e_stream_t stream) {
-  return bwd_finalize_impl(E, dE_hat, dC_hat_local, cos_diag, row_stat, row_aux, n_local, M, D, w, b, eps,
+  return bwd_finalize_impl(E, nullptr, dE_hat, dC_hat_local, cos_diag, row_stat, row_aux, n_local, M, D, w, b, eps,
                            variant, grad_out, dE, true, stream);
 }
 
-int ge2e_b200_forward(const float* E, int N, int M, int D, const float* w, const float* b, float eps,
-                      int variant, int precision, float* e_hat, float* c_hat, float* cos_diag,
-                      float* row_stat, int32_t* row_kstar, float* row_aux, float* accum, void* workspace,
-                      size_t workspace_bytes, ge2e_stream_t stream) {
+int ge2e_b200_forward_indexed(const float* E, const int32_t* row_index, int N, int M, int D, const float* w,
+                              const float* b, float eps, int variant, int precision, float* e_hat, float* c_hat,
+                              float* cos_diag, float* row_stat, int32_t* row_kstar, float* row_aux, float* accum,
+                              void* workspace, size_t workspace_bytes, ge2e_stream_t stream) {
   if (!accum) return GE2E_ERR_ARGUMENT;
   int rc = check_enum(variant, precision);
   if (rc != GE2E_OK) return rc;
   // tensor-core path: prep and the rows kernel are adjacent in the stream, the second one is launched
   // programmatically under the first one's tail
   const bool tc = precision == GE2E_TF32 && N > 0 && M >= 2 && D > 0 && tc_supported(N, N, M, D, variant);
-  rc = ge2e_b200_prep(E, N, M, D, precision, e_hat, c_hat, cos_diag, accum, stream);
+  rc = ge2e_b200_prep_indexed(E, row_index, N, M, D, precision, e_hat, c_hat, cos_diag, accum, stream);
   if (rc != GE2E_OK) return rc;
   return fwd_rows_impl(e_hat, c_hat, cos_diag, N, N, 0, M, D, w, b, eps, variant, precision, row_stat, row_kstar,
                        row_aux, accum, nullptr, nullptr, workspace, workspace_bytes, tc, stream);
+}
+
+int ge2e_b200_forward(const float* E, int N, int M, int D, const float* w, const float* b, float eps,
+                      int variant, int precision, float* e_hat, float* c_hat, float* cos_diag,
+                      float* row_stat, int32_t* row_kstar, float* row_aux, float* accum, void* workspace,
+                      size_t workspace_bytes, ge2e_stream_t stream) {
+  return ge2e_b200_forward_indexed(E, nullptr, N, M, D, w, b, eps, variant, precision, e_hat, c_hat, cos_diag,
+                                   row_stat, row_kstar, row_aux, accum, workspace, workspace_bytes, stream);
+}
+
+int ge2e_b200_backward_indexed(const float* E, const int32_t* row_index, const float* e_hat, const float* c_hat,
+                               const float* cos_diag, const float* row_stat, const int32_t* row_kstar,
+                               const float* row_aux, int N, int M, int D, const float* w, const float* b, float eps,
+                               int variant, int precision, const float* grad_out, float* dE_hat, float* dC_hat,
+                               float* accum, float* dE, void* workspace, size_t workspace_bytes,
+                               ge2e_stream_t stream) {
+  if (!accum) return GE2E_ERR_ARGUMENT;
+  int rc = ge2e_b200_bwd_rows(e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, N, N, 0, M, D, w, b, eps,
+                              variant, precision, grad_out, dE_hat, dC_hat, accum + 1, workspace,
+                              workspace_bytes, stream);
+  if (rc != GE2E_OK) return rc;
+  // the finalize kernel directly follows the dC_hat tensor-core kernel: programmatic launch
+  return bwd_finalize_impl(E, row_index, dE_hat, dC_hat, cos_diag, row_stat, row_aux, N, M, D, w, b, eps, variant,
+                           grad_out, dE, true, stream);
 }
 
 int ge2e_b200_backward(const float* E, const float* e_hat, const float* c_hat, const float* cos_diag,
@@ -210,14 +249,9 @@ int ge2e_b200_backward(const float* E, const float* e_hat, const float* c_hat, c
                        int M, int D, const float* w, const float* b, float eps, int variant, int precision,
                        const float* grad_out, float* dE_hat, float* dC_hat, float* accum, float* dE,
                        void* workspace, size_t workspace_bytes, ge2e_stream_t stream) {
-  if (!accum) return GE2E_ERR_ARGUMENT;
-  int rc = ge2e_b200_bwd_rows(e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, N, N, 0, M, D, w, b, eps,
-                              variant, precision, grad_out, dE_hat, dC_hat, accum + 1, workspace,
-                              workspace_bytes, stream);
-  if (rc != GE2E_OK) return rc;
-  // the finalize kernel directly follows the dC_hat tensor-core kernel: programmatic launch
-  return bwd_finalize_impl(E, dE_hat, dC_hat, cos_diag, row_stat, row_aux, N, M, D, w, b, eps, variant,
-                           grad_out, dE, true, stream);
+  return ge2e_b200_backward_indexed(E, nullptr, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, N, M, D, w, b,
+                                    eps, variant, precision, grad_out, dE_hat, dC_hat, accum, dE, workspace,
+                                    workspace_bytes, stream);
 }
 
 int ge2e_b200_centroids(const float* E, int N, int M, int D, float* C, ge2e_stream_t stream) {

@@ -128,14 +128,15 @@ struct RowsArgs {
   int variant;
 };
 
-int simt_prep(const float* E, int n_local, int M, int D, bool round_tf32, float* e_hat,
+// row_index (nullable): logical row r = [speaker][utterance] lives at physical row row_index[r] of E / dE
+int simt_prep(const float* E, const int32_t* row_index, int n_local, int M, int D, bool round_tf32, float* e_hat,
               float* c_hat_local, float* cos_diag, float* accum, cudaStream_t st);
 int simt_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* row_aux,
                   float* loss_accum, float* per_row_out, float* sim_out, cudaStream_t st);
 int simt_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kstar,
                   const float* row_aux, const float* grad_out, float* dE_hat, float* dC_hat_partial,
                   float* dwdb_accum, cudaStream_t st);
-int simt_bwd_finalize(const float* E, const float* dE_hat, const float* dC_hat_local,
+int simt_bwd_finalize(const float* E, const int32_t* row_index, const float* dE_hat, const float* dC_hat_local,
                       const float* cos_diag, const float* row_stat, const float* row_aux,
                       int n_local, int M, int D,
                       const float* w, const float* b, float eps, int variant,

@@ -59,6 +59,13 @@ __device__ __forceinline__ float dot4(float4 a, float4 b) {
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
 }
 
+// Physical row of logical row r.  The optional row index folds the trainer's `embeddings[unperm]`
+// gather (s4_train_embed_model.py:189-192) into the loads of prep / finalize and the scatter of its
+// backward into finalize's stores; nullptr = rows are already in [speaker][utterance] order.
+__device__ __forceinline__ size_t phys_row(const int32_t* __restrict__ idx, size_t r) {
+  return idx != nullptr ? static_cast<size_t>(__ldg(idx + r)) : r;
+}
+
 __device__ __forceinline__ bool is_vec(const void* p, int D) {
   return ((D & 3) == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
 }
@@ -68,22 +75,23 @@ __device__ __forceinline__ bool is_vec(const void* p, int D) {
 // ------------------------------------------------------------------------------------------
 template <bool ROUND>
 __global__ void __launch_bounds__(kThreads)
-prep_kernel(const float* __restrict__ E, int M, int D, int Dp, float* __restrict__ e_hat,
-            float* __restrict__ c_hat, float* __restrict__ cos_diag, float* __restrict__ accum) {
+prep_kernel(const float* __restrict__ E, const int32_t* __restrict__ idx, int M, int D, int Dp,
+            float* __restrict__ e_hat, float* __restrict__ c_hat, float* __restrict__ cos_diag,
+            float* __restrict__ accum) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float red[kWarps];
   __shared__ float s_inv_nc;
   float* sE = smem;                    // [M][Dp]
   float* sS = smem + (size_t)M * Dp;   // [Dp] column sums
   const int j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const float* Ej = E + (size_t)j * M * D;
   const bool vec_in = is_vec(E, D);
   const bool vec_out = is_vec(e_hat, D);
   if (j == 0 && tid < 4 && accum != nullptr) accum[tid] = 0.f;
 
   for (int v = tid; v < M * (Dp >> 2); v += kThreads) {
     const int i = v / (Dp >> 2), col = (v % (Dp >> 2)) << 2;
-    *reinterpret_cast<float4*>(&sE[(size_t)i * Dp + col]) = ld4(Ej + (size_t)i * D, col, D, vec_in);
+    *reinterpret_cast<float4*>(&sE[(size_t)i * Dp + col]) =
+        ld4(E + phys_row(idx, (size_t)j * M + i) * D, col, D, vec_in);
   }
   __syncthreads();
   for (int d = tid; d < Dp; d += kThreads) {
@@ -148,8 +156,9 @@ constexpr int kRegRows = 16;   // register-resident variants hold up to this man
 
 template <int KCH, bool ROUND>
 __global__ void __launch_bounds__(kPrepWarps * 32)
-prep_warp_kernel(const float* __restrict__ E, int n_local, int M, float* __restrict__ e_hat,
-                 float* __restrict__ c_hat, float* __restrict__ cos_diag, float* __restrict__ accum) {
+prep_warp_kernel(const float* __restrict__ E, const int32_t* __restrict__ idx, int n_local, int M,
+                 float* __restrict__ e_hat, float* __restrict__ c_hat, float* __restrict__ cos_diag,
+                 float* __restrict__ accum) {
   constexpr int D = KCH * 128;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int j = blockIdx.x * kPrepWarps + wid;
@@ -157,7 +166,9 @@ prep_warp_kernel(const float* __restrict__ E, int n_local, int M, float* __restr
   pdl_trigger();     // the forward tensor-core kernel may set itself up while this grid runs
   if (blockIdx.x == 0 && threadIdx.x < 4 && accum != nullptr) accum[threadIdx.x] = 0.f;
   if (j >= n_local) return;
-  const float4* Ej = reinterpret_cast<const float4*>(E + (size_t)j * M * D) + lane;   // + i * (D/4) + c * 32
+  auto rowp = [&](int i) {      // + c * 32 float4 per 128-column chunk
+    return reinterpret_cast<const float4*>(E + phys_row(idx, (size_t)j * M + i) * D) + lane;
+  };
   float4 s[KCH];
 #pragma unroll
   for (int c = 0; c < KCH; ++c) s[c] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -167,7 +178,7 @@ prep_warp_kernel(const float* __restrict__ E, int n_local, int M, float* __restr
     for (int r = 0; r < kRowBatch; ++r)
 #pragma unroll
       for (int c = 0; c < KCH; ++c)
-        v[r][c] = (i0 + r < M) ? __ldg(Ej + (size_t)(i0 + r) * (D / 4) + c * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[r][c] = (i0 + r < M) ? __ldg(rowp(i0 + r) + c * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int r = 0; r < kRowBatch; ++r)
 #pragma unroll
@@ -199,7 +210,7 @@ prep_warp_kernel(const float* __restrict__ E, int n_local, int M, float* __restr
     for (int r = 0; r < kRowBatch; ++r)
 #pragma unroll
       for (int c = 0; c < KCH; ++c)
-        v[r][c] = (i0 + r < M) ? __ldg(Ej + (size_t)(i0 + r) * (D / 4) + c * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[r][c] = (i0 + r < M) ? __ldg(rowp(i0 + r) + c * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int r = 0; r < kRowBatch; ++r) {
       ne2[r] = 0.f; nd2[r] = 0.f; ed[r] = 0.f;
@@ -268,8 +279,9 @@ __device__ __forceinline__ float reduce16_transposed(const float (&v)[16], int l
 
 template <int KCH, int RR, bool ROUND>
 __global__ void __launch_bounds__(kPrepWarps * 32)
-prep_reg_kernel(const float* __restrict__ E, int n_local, int M, float* __restrict__ e_hat,
-                float* __restrict__ c_hat, float* __restrict__ cos_diag, float* __restrict__ accum) {
+prep_reg_kernel(const float* __restrict__ E, const int32_t* __restrict__ idx, int n_local, int M,
+                float* __restrict__ e_hat, float* __restrict__ c_hat, float* __restrict__ cos_diag,
+                float* __restrict__ accum) {
   constexpr int D = KCH * 128, R = RR;     // rows held in registers (M <= R <= 16)
   static_assert(R <= 16, "reduce16_transposed handles 16 rows");
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -278,13 +290,13 @@ prep_reg_kernel(const float* __restrict__ E, int n_local, int M, float* __restri
   pdl_trigger();     // the forward tensor-core kernel may set itself up while this grid runs
   if (blockIdx.x == 0 && threadIdx.x < 4 && accum != nullptr) accum[threadIdx.x] = 0.f;
   if (j >= n_local) return;
-  const float4* Ej = reinterpret_cast<const float4*>(E + (size_t)j * M * D) + lane;
   float4 v[R][KCH];
 #pragma unroll
-  for (int i = 0; i < R; ++i)
+  for (int i = 0; i < R; ++i) {
+    const float4* rp = (i < M) ? reinterpret_cast<const float4*>(E + phys_row(idx, (size_t)j * M + i) * D) + lane : nullptr;
 #pragma unroll
-    for (int c = 0; c < KCH; ++c)
-      v[i][c] = (i < M) ? __ldg(Ej + (size_t)i * (D / 4) + c * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < KCH; ++c) v[i][c] = (i < M) ? __ldg(rp + c * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   float4 s[KCH];
 #pragma unroll
   for (int c = 0; c < KCH; ++c) {
@@ -653,7 +665,7 @@ finalize_kernel(const float* __restrict__ E, const float* __restrict__ dE_hat,
                 const float* __restrict__ dC_hat, const float* __restrict__ cos_diag,
                 const float* __restrict__ row_stat, const float* __restrict__ row_aux, int M, int D, int Dp,
                 const float* __restrict__ wp, const float* __restrict__ bp, float eps, int variant,
-                const float* __restrict__ gp, float* __restrict__ dE) {
+                const float* __restrict__ gp, float* __restrict__ dE, const int32_t* __restrict__ idx) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float red[kWarps];
   __shared__ float s_bc[2];
@@ -663,12 +675,12 @@ finalize_kernel(const float* __restrict__ E, const float* __restrict__ dE_hat,
   float* sB = sS + Dp;                       // [Dp] dc_j / M
   const int j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const float w = __ldg(wp), b = __ldg(bp), g = __ldg(gp);
-  const float* Ej = E + (size_t)j * M * D;
   const bool vec_e = is_vec(E, D), vec_g = is_vec(dE_hat, D), vec_o = is_vec(dE, D);
 
   for (int v = tid; v < M * (Dp >> 2); v += kThreads) {
     const int i = v / (Dp >> 2), col = (v % (Dp >> 2)) << 2;
-    *reinterpret_cast<float4*>(&sE[(size_t)i * Dp + col]) = ld4(Ej + (size_t)i * D, col, D, vec_e);
+    *reinterpret_cast<float4*>(&sE[(size_t)i * Dp + col]) =
+        ld4(E + phys_row(idx, (size_t)j * M + i) * D, col, D, vec_e);
   }
   __syncthreads();
   for (int d = tid; d < Dp; d += kThreads) {
@@ -766,7 +778,6 @@ finalize_kernel(const float* __restrict__ E, const float* __restrict__ dE_hat,
     sS[d] = s;
   }
   __syncthreads();
-  float* out = dE + (size_t)j * M * D;
   for (int v = tid; v < M * (Dp >> 2); v += kThreads) {
     const int i = v / (Dp >> 2), col = (v % (Dp >> 2)) << 2;
     const float4 de = *reinterpret_cast<const float4*>(&sE[(size_t)i * Dp + col]);
@@ -778,7 +789,7 @@ finalize_kernel(const float* __restrict__ E, const float* __restrict__ dE_hat,
     o.y = de.y + bc.y + (sd.y - du.y) / m1;
     o.z = de.z + bc.z + (sd.z - du.z) / m1;
     o.w = de.w + bc.w + (sd.w - du.w) / m1;
-    st4(out + (size_t)i * D, col, D, vec_o, o);
+    st4(dE + phys_row(idx, (size_t)j * M + i) * D, col, D, vec_o, o);
   }
 }
 
@@ -795,7 +806,7 @@ finalize_warp_kernel(const float* __restrict__ E, const float* __restrict__ dE_h
                      const float* __restrict__ dC_hat, const float* __restrict__ cos_diag,
                      const float* __restrict__ row_aux, int n_local, int M,
                      const float* __restrict__ wp, const float* __restrict__ bp, float eps, int variant,
-                     const float* __restrict__ gp, float* __restrict__ dE) {
+                     const float* __restrict__ gp, float* __restrict__ dE, const int32_t* __restrict__ idx) {
   constexpr int D = KCH * 128;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int j = blockIdx.x * kPrepWarps + wid;
@@ -803,7 +814,9 @@ finalize_warp_kernel(const float* __restrict__ E, const float* __restrict__ dE_h
   pdl_trigger();     // the next step's prep may be scheduled (it waits for this grid before touching memory)
   if (j >= n_local) return;
   const float w = __ldg(wp), b = __ldg(bp), g = __ldg(gp);
-  const float4* Ej = reinterpret_cast<const float4*>(E + (size_t)j * M * D) + lane;
+  auto rowp = [&](int i) {
+    return reinterpret_cast<const float4*>(E + phys_row(idx, (size_t)j * M + i) * D) + lane;
+  };
   const float4* Gj = reinterpret_cast<const float4*>(dE_hat + (size_t)j * M * D) + lane;
   float4 s[KCH];
 #pragma unroll
@@ -814,7 +827,7 @@ finalize_warp_kernel(const float* __restrict__ E, const float* __restrict__ dE_h
     for (int r = 0; r < kRowBatch; ++r)
 #pragma unroll
       for (int c = 0; c < KCH; ++c)
-        v[r][c] = (i0 + r < M) ? __ldg(Ej + (size_t)(i0 + r) * (D / 4) + c * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[r][c] = (i0 + r < M) ? __ldg(rowp(i0 + r) + c * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int r = 0; r < kRowBatch; ++r)
 #pragma unroll
@@ -862,7 +875,7 @@ finalize_warp_kernel(const float* __restrict__ E, const float* __restrict__ dE_h
 #pragma unroll
       for (int c = 0; c < KCH; ++c) {
         const bool in = i0 + r < M;
-        v[r][c] = in ? __ldg(Ej + (size_t)(i0 + r) * (D / 4) + c * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[r][c] = in ? __ldg(rowp(i0 + r) + c * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 gv = in ? __ldg(Gj + (size_t)(i0 + r) * (D / 4) + c * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 e = v[r][c];
         const float4 d = make_float4(s[c].x - e.x, s[c].y - e.y, s[c].z - e.z, s[c].w - e.w);
@@ -915,14 +928,14 @@ finalize_warp_kernel(const float* __restrict__ E, const float* __restrict__ dE_h
     }
   }
   // pass 3: dE_i = de_i + dc_j / M + (sd - du_i) / (M - 1)
-  float4* Oj = reinterpret_cast<float4*>(dE + (size_t)j * M * D) + lane;
   for (int i = 0; i < M; ++i) {
+    float4* Oi = reinterpret_cast<float4*>(dE + phys_row(idx, (size_t)j * M + i) * D) + lane;
     const float r_ag = __shfl_sync(0xffffffffu, a_g, i), r_ae = __shfl_sync(0xffffffffu, a_e, i);
     const float r_ad = __shfl_sync(0xffffffffu, a_d, i), r_be = __shfl_sync(0xffffffffu, b_e, i);
     const float r_bd = __shfl_sync(0xffffffffu, b_d, i);
 #pragma unroll
     for (int c = 0; c < KCH; ++c) {
-      const float4 e = __ldg(Ej + (size_t)i * (D / 4) + c * 32);
+      const float4 e = __ldg(rowp(i) + c * 32);
       const float4 gv = __ldg(Gj + (size_t)i * (D / 4) + c * 32);
       const float ev[4] = {e.x, e.y, e.z, e.w}, gg[4] = {gv.x, gv.y, gv.z, gv.w};
       const float sv[4] = {s[c].x, s[c].y, s[c].z, s[c].w}, sdv[4] = {sd[c].x, sd[c].y, sd[c].z, sd[c].w};
@@ -935,7 +948,7 @@ finalize_warp_kernel(const float* __restrict__ E, const float* __restrict__ dE_h
         const float du = r_be * ev[t] + r_bd * d;
         o[t] = de + bv[t] + (sdv[t] - du) * inv_m1;
       }
-      Oj[(size_t)i * (D / 4) + c * 32] = make_float4(o[0], o[1], o[2], o[3]);
+      Oi[c * 32] = make_float4(o[0], o[1], o[2], o[3]);
     }
   }
 }
@@ -954,19 +967,21 @@ finalize_reg_kernel(const float* __restrict__ E, const float* __restrict__ dE_ha
                     const float* __restrict__ dC_hat, const float* __restrict__ cos_diag,
                     const float* __restrict__ row_aux, int n_local, int M,
                     const float* __restrict__ wp, const float* __restrict__ bp, float eps, int variant,
-                    const float* __restrict__ gp, float* __restrict__ dE) {
+                    const float* __restrict__ gp, float* __restrict__ dE, const int32_t* __restrict__ idx) {
   constexpr int D = KCH * 128, R = RR;     // rows held in registers (M <= R <= 16)
   static_assert(R <= 16, "reduce16_transposed handles 16 rows");
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int j = blockIdx.x * kPrepWarps + wid;
   const bool active = j < n_local;
   float4 v[R][KCH];
-  const float4* Ej = reinterpret_cast<const float4*>(E + (size_t)(active ? j : 0) * M * D) + lane;
+  // the row index is an input of the whole op as well (never written by the preceding grids)
 #pragma unroll
-  for (int i = 0; i < R; ++i)
+  for (int i = 0; i < R; ++i) {
+    const bool in = active && i < M;
+    const float4* rp = in ? reinterpret_cast<const float4*>(E + phys_row(idx, (size_t)j * M + i) * D) + lane : nullptr;
 #pragma unroll
-    for (int c = 0; c < KCH; ++c)
-      v[i][c] = (active && i < M) ? __ldg(Ej + (size_t)i * (D / 4) + c * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < KCH; ++c) v[i][c] = in ? __ldg(rp + c * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   pdl_wait();        // launched with the PDL attribute: dE_hat / dC_hat come from the preceding grids
   pdl_trigger();     // the next step's prep may be scheduled (it waits for this grid before touching memory)
   if (!active) return;
@@ -1091,10 +1106,10 @@ finalize_reg_kernel(const float* __restrict__ E, const float* __restrict__ dE_ha
       }
     }
   }
-  float4* Oj = reinterpret_cast<float4*>(dE + (size_t)j * M * D) + lane;
 #pragma unroll
   for (int i = 0; i < R; ++i) {
     if (i < M) {
+      float4* Oi = reinterpret_cast<float4*>(dE + phys_row(idx, (size_t)j * M + i) * D) + lane;
       const float r_ag = __shfl_sync(0xffffffffu, a_g, rev4(i)), r_ae = __shfl_sync(0xffffffffu, a_e, rev4(i));
       const float r_ad = __shfl_sync(0xffffffffu, a_d, rev4(i)), r_be = __shfl_sync(0xffffffffu, b_e, rev4(i));
       const float r_bd = __shfl_sync(0xffffffffu, b_d, rev4(i));
@@ -1113,7 +1128,7 @@ finalize_reg_kernel(const float* __restrict__ E, const float* __restrict__ dE_ha
           const float du = r_be * ev[t] + r_bd * d;
           o[t] = de + bv[t] + (sdv[t] - du) * inv_m1;
         }
-        Oj[(size_t)i * (D / 4) + c * 32] = make_float4(o[0], o[1], o[2], o[3]);
+        Oi[c * 32] = make_float4(o[0], o[1], o[2], o[3]);
       }
     }
   }
@@ -1234,49 +1249,49 @@ bool warp_path_ok(int D, std::initializer_list<const void*> ptrs) {
 }
 
 template <int KCH>
-void launch_prep_warp(const float* E, int n_local, int M, bool rnd, float* e_hat, float* c_hat, float* cos_diag,
-                      float* accum, cudaStream_t st) {
+void launch_prep_warp(const float* E, const int32_t* idx, int n_local, int M, bool rnd, float* e_hat, float* c_hat,
+                      float* cos_diag, float* accum, cudaStream_t st) {
   const int grid = (n_local + kPrepWarps - 1) / kPrepWarps;
   if (KCH <= 2 && M <= kRegRows) {
     constexpr int K2 = KCH <= 2 ? KCH : 1;    // the register-resident variant is only instantiated for D <= 256
     const dim3 g(grid), bl(kPrepWarps * 32);
 #define GE2E_PREP_REG(RR)                                                                                          \
-  (rnd ? launch_pdl(prep_reg_kernel<K2, RR, true>, g, bl, 0, st, true, E, n_local, M, e_hat, c_hat, cos_diag, accum) \
-       : launch_pdl(prep_reg_kernel<K2, RR, false>, g, bl, 0, st, true, E, n_local, M, e_hat, c_hat, cos_diag, accum))
+  (rnd ? launch_pdl(prep_reg_kernel<K2, RR, true>, g, bl, 0, st, true, E, idx, n_local, M, e_hat, c_hat, cos_diag, accum) \
+       : launch_pdl(prep_reg_kernel<K2, RR, false>, g, bl, 0, st, true, E, idx, n_local, M, e_hat, c_hat, cos_diag, accum))
     if (M <= 4) GE2E_PREP_REG(4); else if (M <= 8) GE2E_PREP_REG(8); else if (M <= 12) GE2E_PREP_REG(12); else GE2E_PREP_REG(16);
 #undef GE2E_PREP_REG
     return;
   }
-  if (rnd) launch_pdl(prep_warp_kernel<KCH, true>, dim3(grid), dim3(kPrepWarps * 32), 0, st, true, E, n_local, M, e_hat,
-                      c_hat, cos_diag, accum);
-  else launch_pdl(prep_warp_kernel<KCH, false>, dim3(grid), dim3(kPrepWarps * 32), 0, st, true, E, n_local, M, e_hat,
-                  c_hat, cos_diag, accum);
+  if (rnd) launch_pdl(prep_warp_kernel<KCH, true>, dim3(grid), dim3(kPrepWarps * 32), 0, st, true, E, idx, n_local, M,
+                      e_hat, c_hat, cos_diag, accum);
+  else launch_pdl(prep_warp_kernel<KCH, false>, dim3(grid), dim3(kPrepWarps * 32), 0, st, true, E, idx, n_local, M,
+                  e_hat, c_hat, cos_diag, accum);
 }
 
 template <int KCH>
 void launch_finalize_warp(const float* E, const float* dE_hat, const float* dC_hat, const float* cos_diag,
                           const float* row_aux, int n_local, int M, const float* w, const float* b, float eps,
-                          int variant, const float* g, float* dE, bool pdl, cudaStream_t st) {
+                          int variant, const float* g, float* dE, const int32_t* idx, bool pdl, cudaStream_t st) {
   const int grid = (n_local + kPrepWarps - 1) / kPrepWarps;
   if (KCH <= 2 && M <= kRegRows) {
     constexpr int K2 = KCH <= 2 ? KCH : 1;
 #define GE2E_FIN_REG(RR)                                                                                     \
   launch_pdl(finalize_reg_kernel<K2, RR>, dim3(grid), dim3(kPrepWarps * 32), 0, st, pdl, E, dE_hat, dC_hat, cos_diag, \
-             row_aux, n_local, M, w, b, eps, variant, g, dE)
+             row_aux, n_local, M, w, b, eps, variant, g, dE, idx)
     if (M <= 4) GE2E_FIN_REG(4); else if (M <= 8) GE2E_FIN_REG(8); else if (M <= 12) GE2E_FIN_REG(12); else GE2E_FIN_REG(16);
 #undef GE2E_FIN_REG
     return;
   }
   launch_pdl(finalize_warp_kernel<KCH>, dim3(grid), dim3(kPrepWarps * 32), 0, st, pdl, E, dE_hat, dC_hat, cos_diag,
-             row_aux, n_local, M, w, b, eps, variant, g, dE);
+             row_aux, n_local, M, w, b, eps, variant, g, dE, idx);
 }
 
-int simt_prep(const float* E, int n_local, int M, int D, bool round_tf32_, float* e_hat,
+int simt_prep(const float* E, const int32_t* row_index, int n_local, int M, int D, bool round_tf32_, float* e_hat,
               float* c_hat_local, float* cos_diag, float* accum, cudaStream_t st) {
   if (warp_path_ok(D, {E, e_hat, c_hat_local})) {
-    if (D == 128) launch_prep_warp<1>(E, n_local, M, round_tf32_, e_hat, c_hat_local, cos_diag, accum, st);
-    else if (D == 256) launch_prep_warp<2>(E, n_local, M, round_tf32_, e_hat, c_hat_local, cos_diag, accum, st);
-    else launch_prep_warp<4>(E, n_local, M, round_tf32_, e_hat, c_hat_local, cos_diag, accum, st);
+    if (D == 128) launch_prep_warp<1>(E, row_index, n_local, M, round_tf32_, e_hat, c_hat_local, cos_diag, accum, st);
+    else if (D == 256) launch_prep_warp<2>(E, row_index, n_local, M, round_tf32_, e_hat, c_hat_local, cos_diag, accum, st);
+    else launch_prep_warp<4>(E, row_index, n_local, M, round_tf32_, e_hat, c_hat_local, cos_diag, accum, st);
     GE2E_LAUNCHED();
     return GE2E_OK;
   }
@@ -1286,11 +1301,11 @@ int simt_prep(const float* E, int n_local, int M, int D, bool round_tf32_, float
   if (round_tf32_) {
     int rc = set_smem(prep_kernel<true>, smem);
     if (rc != GE2E_OK) return rc;
-    prep_kernel<true><<<n_local, kThreads, smem, st>>>(E, M, D, Dp, e_hat, c_hat_local, cos_diag, accum);
+    prep_kernel<true><<<n_local, kThreads, smem, st>>>(E, row_index, M, D, Dp, e_hat, c_hat_local, cos_diag, accum);
   } else {
     int rc = set_smem(prep_kernel<false>, smem);
     if (rc != GE2E_OK) return rc;
-    prep_kernel<false><<<n_local, kThreads, smem, st>>>(E, M, D, Dp, e_hat, c_hat_local, cos_diag, accum);
+    prep_kernel<false><<<n_local, kThreads, smem, st>>>(E, row_index, M, D, Dp, e_hat, c_hat_local, cos_diag, accum);
   }
   GE2E_LAUNCHED();
   return GE2E_OK;
@@ -1350,14 +1365,14 @@ int simt_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_k
   return dispatch_strip<MODE_BWD_DC, GE2E_SOFTMAX>(p, splits, st);
 }
 
-int simt_bwd_finalize(const float* E, const float* dE_hat, const float* dC_hat_local,
+int simt_bwd_finalize(const float* E, const int32_t* row_index, const float* dE_hat, const float* dC_hat_local,
                       const float* cos_diag, const float* row_stat, const float* row_aux, int n_local, int M,
                       int D, const float* w, const float* b, float eps, int variant,
                       const float* grad_out, float* dE, bool pdl, cudaStream_t st) {
   if (M <= 32 && warp_path_ok(D, {E, dE_hat, dC_hat_local, dE})) {
-    if (D == 128) launch_finalize_warp<1>(E, dE_hat, dC_hat_local, cos_diag, row_aux, n_local, M, w, b, eps, variant, grad_out, dE, pdl, st);
-    else if (D == 256) launch_finalize_warp<2>(E, dE_hat, dC_hat_local, cos_diag, row_aux, n_local, M, w, b, eps, variant, grad_out, dE, pdl, st);
-    else launch_finalize_warp<4>(E, dE_hat, dC_hat_local, cos_diag, row_aux, n_local, M, w, b, eps, variant, grad_out, dE, pdl, st);
+    if (D == 128) launch_finalize_warp<1>(E, dE_hat, dC_hat_local, cos_diag, row_aux, n_local, M, w, b, eps, variant, grad_out, dE, row_index, pdl, st);
+    else if (D == 256) launch_finalize_warp<2>(E, dE_hat, dC_hat_local, cos_diag, row_aux, n_local, M, w, b, eps, variant, grad_out, dE, row_index, pdl, st);
+    else launch_finalize_warp<4>(E, dE_hat, dC_hat_local, cos_diag, row_aux, n_local, M, w, b, eps, variant, grad_out, dE, row_index, pdl, st);
     GE2E_LAUNCHED();
     return GE2E_OK;
   }
@@ -1367,7 +1382,7 @@ int simt_bwd_finalize(const float* E, const float* dE_hat, const float* dC_hat_l
   int rc = set_smem(finalize_kernel, smem);
   if (rc != GE2E_OK) return rc;
   finalize_kernel<<<n_local, kThreads, smem, st>>>(E, dE_hat, dC_hat_local, cos_diag, row_stat, row_aux, M, D,
-                                                   Dp, w, b, eps, variant, grad_out, dE);
+                                                   Dp, w, b, eps, variant, grad_out, dE, row_index);
   GE2E_LAUNCHED();
   return GE2E_OK;
 }

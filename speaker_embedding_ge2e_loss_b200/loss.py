@@ -44,12 +44,17 @@ class GE2ELoss(nn.Module):
         self.w = nn.Parameter(torch.tensor(float(w)).to(self.device), requires_grad=True)
         self.b = nn.Parameter(torch.tensor(float(b)).to(self.device), requires_grad=True)
 
-    def forward(self, embeddings):
+    def forward(self, embeddings, unperm=None, speakers: int = 0):
+        """``forward(embeddings[N, M, D])`` as in the reference.  Extension: ``forward(flat[N*M, D],
+        unperm=idx, speakers=N)`` computes the loss of ``flat[idx].reshape(N, M, D)`` with the gather
+        (and the scatter of its backward) folded into the kernels (s4_train_embed_model.py:189-192)."""
         # s3:22 is a discarded torch.clamp: w is deliberately NOT clamped.
         if self.process_group is not None:
+            if unperm is not None:
+                raise ValueError("unperm is not supported together with a process_group")
             return sharded_ge2e_loss(embeddings, self.w, self.b, self.eps, self.variant, self.precision,
                                      self.process_group)
-        return ops.ge2e_loss(embeddings, self.w, self.b, self.eps, self.variant, self.precision)
+        return ops.ge2e_loss(embeddings, self.w, self.b, self.eps, self.variant, self.precision, unperm, speakers)
 
     def path_for(self, N: int, M: int, D: int) -> int:
         """Which kernels a batch of this shape runs on: 0 = SIMT fp32, 1 = tcgen05 TF32."""

@@ -73,12 +73,29 @@ class _on_device:
             self.ctx.__exit__(*a)
 
 
-def _fwd_impl(E: Tensor, w: Tensor, b: Tensor, eps: float, variant: int, precision: int, packed: bool):
+def _index_ok(row_index: Optional[Tensor], U: int, dev) -> Optional[Tensor]:
+    if row_index is None:
+        return None
+    if row_index.device != dev or row_index.numel() != U:
+        raise ValueError(f"unperm must be a device tensor with {U} entries")
+    return row_index.to(torch.int32).contiguous()
+
+
+def _fwd_impl(E: Tensor, w: Tensor, b: Tensor, eps: float, variant: int, precision: int, packed: bool,
+              row_index: Optional[Tensor] = None, speakers: int = 0):
     """GE2ELoss.forward (reference s3:19-30) through the C ABI.  ``packed``: the per-call intermediates
-    come out of ONE allocation (views); the custom op needs non-aliasing outputs and passes False."""
+    come out of ONE allocation (views); the custom op needs non-aliasing outputs and passes False.
+    ``row_index`` (with ``speakers``): E is [U, D] in the embedder's row order and logical row r lives
+    at row_index[r] (the trainer's ``embeddings[unperm]``, s4:189-192, folded into the kernels)."""
     _need_cuda(E, w, b)
     E, w, b = _f32c(E), _f32c(w), _f32c(b)
-    N, M, D = E.shape
+    if row_index is None:
+        N, M, D = E.shape
+    else:
+        U_, D = E.shape
+        N, M = speakers, U_ // max(1, speakers)
+        if speakers <= 0 or N * M != U_:
+            raise ValueError(f"{U_} rows do not split into {speakers} speakers")
     U = N * M
     dev = E.device
     with _on_device(dev):
@@ -100,21 +117,23 @@ def _fwd_impl(E: Tensor, w: Tensor, b: Tensor, eps: float, variant: int, precisi
             row_aux = torch.empty(U, dtype=torch.float32, device=dev)
         row_kstar = torch.empty(U if variant == _lib.CONTRAST else 1, dtype=torch.int32, device=dev)
         ws, ws_bytes = _workspace(N, N, M, D, variant, precision, dev)
-        rc = lib().ge2e_b200_forward(E.data_ptr(), N, M, D, w.data_ptr(), b.data_ptr(), eps, variant,
-                                     precision, e_hat.data_ptr(), c_hat.data_ptr(), cos_diag.data_ptr(),
-                                     row_stat.data_ptr(), row_kstar.data_ptr(), row_aux.data_ptr(),
-                                     accum.data_ptr(), _ptr(ws), ws_bytes, _stream())
+        rc = lib().ge2e_b200_forward_indexed(E.data_ptr(), _ptr(row_index), N, M, D, w.data_ptr(), b.data_ptr(), eps,
+                                             variant, precision, e_hat.data_ptr(), c_hat.data_ptr(),
+                                             cos_diag.data_ptr(), row_stat.data_ptr(), row_kstar.data_ptr(),
+                                             row_aux.data_ptr(), accum.data_ptr(), _ptr(ws), ws_bytes, _stream())
     check(rc, "ge2e_b200_forward")
     return accum[0], e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux
 
 
-def _bwd_impl(grad_out, E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, eps, variant, precision):
-    """loss.backward() (s4:200) through the C ABI.  Returns (dE[N,M,D], dwdb[2])."""
+def _bwd_impl(grad_out, E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, eps, variant, precision,
+              row_index: Optional[Tensor] = None):
+    """loss.backward() (s4:200) through the C ABI.  Returns (dE shaped like E, dwdb[2])."""
     _need_cuda(grad_out, E, w, b)
     E, w, b = _f32c(E), _f32c(w), _f32c(b)
     g = _f32c(grad_out)
-    N, M, D = E.shape
-    U = N * M
+    N, D = c_hat.shape
+    U = e_hat.shape[0]
+    M = U // N
     dev = E.device
     with _on_device(dev):
         dE = torch.empty_like(E)
@@ -124,11 +143,11 @@ def _bwd_impl(grad_out, E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, ro
         dC_ptr = dE_hat_ptr + U * D * 4
         ws, ws_bytes = _workspace(N, N, M, D, variant, precision, dev)
         accum_ptr = dC_ptr + (N * D - 1) * 4
-        rc = lib().ge2e_b200_backward(E.data_ptr(), e_hat.data_ptr(), c_hat.data_ptr(), cos_diag.data_ptr(),
-                                      row_stat.data_ptr(), row_kstar.data_ptr(), row_aux.data_ptr(), N, M, D,
-                                      w.data_ptr(), b.data_ptr(), eps, variant, precision, g.data_ptr(),
-                                      dE_hat_ptr, dC_ptr, accum_ptr, dE.data_ptr(),
-                                      _ptr(ws), ws_bytes, _stream())
+        rc = lib().ge2e_b200_backward_indexed(E.data_ptr(), _ptr(row_index), e_hat.data_ptr(), c_hat.data_ptr(),
+                                              cos_diag.data_ptr(), row_stat.data_ptr(), row_kstar.data_ptr(),
+                                              row_aux.data_ptr(), N, M, D, w.data_ptr(), b.data_ptr(), eps, variant,
+                                              precision, g.data_ptr(), dE_hat_ptr, dC_ptr, accum_ptr, dE.data_ptr(),
+                                              _ptr(ws), ws_bytes, _stream())
     check(rc, "ge2e_b200_backward")
     return dE, scratch[U * D + N * D:]
 
@@ -188,11 +207,12 @@ class _GE2EEager(torch.autograd.Function):
     (which cost ~0.2 ms of host time per step: more than the kernels at every size up to cfg3)."""
 
     @staticmethod
-    def forward(ctx, E, w, b, eps, variant, precision):
-        loss, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux = _fwd_impl(E, w, b, eps, variant, precision,
-                                                                               packed=True)
+    def forward(ctx, E, w, b, eps, variant, precision, row_index, speakers):
+        loss, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux = _fwd_impl(
+            E, w, b, eps, variant, precision, packed=True, row_index=row_index, speakers=speakers)
         ctx.save_for_backward(E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux)
         ctx.cfg = (eps, variant, precision)
+        ctx.row_index = row_index
         return loss
 
     @staticmethod
@@ -200,21 +220,36 @@ class _GE2EEager(torch.autograd.Function):
         E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux = ctx.saved_tensors
         eps, variant, precision = ctx.cfg
         dE, dwdb = _bwd_impl(g_loss, E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, eps, variant,
-                             precision)
-        return dE, dwdb[0], dwdb[1], None, None, None
+                             precision, row_index=ctx.row_index)
+        return dE, dwdb[0], dwdb[1], None, None, None, None, None
 
 
 def ge2e_loss(E: Tensor, w: Tensor, b: Tensor, eps: float = 1e-6, variant: str = "softmax",
-              precision: str = "fp32") -> Tensor:
+              precision: str = "fp32", unperm: Optional[Tensor] = None, speakers: int = 0) -> Tensor:
     """Functional form: differentiable in E, w, b.  Eager calls go through a plain autograd.Function;
-    under torch.compile the registered custom ops (same kernels) are used."""
+    under torch.compile the registered custom ops (same kernels) are used.
+
+    ``unperm`` (with ``speakers`` = N): E is the embedder's output [N*M, D] in shuffled row order and
+    the loss is that of ``E[unperm].reshape(N, M, D)`` (s4_train_embed_model.py:189-192); the gather and
+    the scatter of its backward happen inside the kernels, dE comes back in E's row order."""
+    if unperm is not None:
+        if E.dim() != 2:
+            raise ValueError(f"with unperm the embeddings must be [N*M, D], got {tuple(E.shape)}")
+        if speakers <= 0 or E.shape[0] % speakers != 0 or E.shape[0] // speakers < 2:
+            raise ValueError("speakers must divide the number of rows, with M >= 2 utterances per speaker")
+        if torch.compiler.is_compiling():
+            N = speakers
+            return ge2e_fwd(E[unperm].reshape(N, E.shape[0] // N, E.shape[1]), w, b, float(eps),
+                            _lib.VARIANTS[variant], _lib.PRECISIONS[precision])[0]
+        idx = _index_ok(unperm, E.shape[0], E.device)
+        return _GE2EEager.apply(E, w, b, float(eps), _lib.VARIANTS[variant], _lib.PRECISIONS[precision], idx, speakers)
     if E.dim() != 3:
         raise ValueError(f"embeddings must be [N, M, D], got {tuple(E.shape)}")
     if E.shape[1] < 2:
         raise ValueError("GE2E needs M >= 2 utterances per speaker (the reference divides by M - 1)")
     if torch.compiler.is_compiling():
         return ge2e_fwd(E, w, b, float(eps), _lib.VARIANTS[variant], _lib.PRECISIONS[precision])[0]
-    return _GE2EEager.apply(E, w, b, float(eps), _lib.VARIANTS[variant], _lib.PRECISIONS[precision])
+    return _GE2EEager.apply(E, w, b, float(eps), _lib.VARIANTS[variant], _lib.PRECISIONS[precision], None, 0)
 
 
 # --------------------------------------------------------------------------- staged (plain functions)

@@ -282,6 +282,36 @@ def test_custom_op_path_matches_eager_path(pkg):
         assert abs(res[0][2] - res[1][2]) <= 1e-5 * max(1.0, abs(res[0][2]))
 
 
+@pytest.mark.parametrize("N,M,D,precision", [(6, 5, 64, "fp32"), (64, 10, 256, "fp32"), (320, 6, 256, "tf32"),
+                                             (40, 20, 128, "fp32"), (24, 40, 96, "fp32")])
+def test_unperm_fused_matches_gather(pkg, N, M, D, precision):
+    """``crit(flat, unperm=idx, speakers=N)`` == ``crit(flat[idx].reshape(N, M, D))``
+    (s4_train_embed_model.py:177-192), including the gradient scattered back to flat's row order."""
+    dev = torch.device("cuda:0")
+    E_np = orc.make_embeddings(N, M, D, seed=N * M, kind="clustered").reshape(N * M, D)
+    rng = np.random.default_rng(1)
+    perm = rng.permutation(N * M)
+    unperm = np.argsort(perm)
+    flat_np = E_np[perm]                      # the embedder saw the rows in shuffled order
+    assert np.array_equal(flat_np[unperm], E_np)
+    idx = torch.tensor(unperm, device=dev)
+    res = []
+    for fused in (False, True):
+        crit = pkg.GE2ELoss(None, device=dev, precision=precision)
+        flat = torch.tensor(flat_np, device=dev, requires_grad=True)
+        loss = crit(flat, unperm=idx, speakers=N) if fused else crit(flat[idx].reshape(N, M, D))
+        loss.backward()
+        torch.cuda.synchronize()
+        res.append((loss.item(), flat.grad.cpu().numpy(), crit.w.grad.item()))
+    assert abs(res[0][0] - res[1][0]) <= 1e-6 * abs(res[0][0])
+    assert rel(res[1][1], res[0][1]) <= 5e-6
+    assert abs(res[0][2] - res[1][2]) <= 1e-5 * max(1.0, abs(res[0][2]))
+    ref = orc.forward_backward(E_np.reshape(N, M, D), 10.0, -5.0, 1e-6, "softmax")
+    tol = FP32_TOL if precision == "fp32" else TF32_TOL
+    assert abs(res[1][0] - ref["loss"]) <= tol * max(1.0, abs(ref["loss"]))
+    assert rel(res[1][1][unperm], ref["dE"].reshape(N * M, D)) <= tol
+
+
 # ------------------------------------------------------------------ static helpers (s5:42-43)
 def test_static_helpers_match_oracle(pkg):
     dev = torch.device("cuda:0")
