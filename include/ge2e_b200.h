@@ -67,6 +67,15 @@ void ge2e_b200_debug_trace(unsigned long long* device_buf, int kernel);
  * 4|8 backward rows, 16 finalize); results are garbage while it is non-zero.  bench.py prices each
  * kernel in situ as (step time) - (step time without it).  Initial value: env GE2E_SKIP, else 0. */
 void ge2e_b200_debug_skip(int mask);
+/* Debug, host only (no GPU needed): the work schedule of the tensor-core backward for u_local
+ * utterance rows against n_total centroids on max_clusters co-resident clusters of cta_group CTAs.
+ * Cluster c works on the pairs [de_begin[c], de_begin[c+1]) of the dE_hat list and [dc_begin[c],
+ * dc_begin[c+1]) of the dC_hat list (pair = owner group * units_per_group + stream unit).  Arrays
+ * need max_clusters + 1 entries.  units = {dE groups, units per dE group, dC groups, units per dC
+ * group}; *de_partial = 1 when dE_hat groups are cut between clusters.  Returns the cluster count. */
+int ge2e_b200_debug_bwd_schedule(int u_local, int n_total, int cta_group, int max_clusters,
+                                 int* de_begin_host, int* dc_begin_host, int* de_partial_host,
+                                 int* units_host);
 /* GE2E_OK if the current CUDA device can run this library (sm_100), else GE2E_ERR_DEVICE. */
 int ge2e_b200_check_device(void);
 

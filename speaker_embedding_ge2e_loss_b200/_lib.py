@@ -24,6 +24,8 @@ PROTOTYPES = {
     "ge2e_b200_path": (C.c_int, [C.c_int] * 6),
     "ge2e_b200_debug_trace": (None, [C.c_void_p, C.c_int]),
     "ge2e_b200_debug_skip": (None, [C.c_int]),
+    "ge2e_b200_debug_bwd_schedule": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_void_p]),
     "ge2e_b200_check_device": (C.c_int, []),
     "ge2e_b200_workspace_bytes": (C.c_size_t, [C.c_int] * 6),
     "ge2e_b200_prep": (C.c_int, [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p,

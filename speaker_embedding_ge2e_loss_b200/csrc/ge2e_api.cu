@@ -69,6 +69,13 @@ void ge2e_b200_debug_trace(unsigned long long* device_buf, int kernel) { tc_set_
 
 void ge2e_b200_debug_skip(int mask) { set_debug_skip_mask(mask); }
 
+int ge2e_b200_debug_bwd_schedule(int u_local, int n_total, int cta_group, int max_clusters, int* de_begin_host,
+                                 int* dc_begin_host, int* de_partial_host, int* units_host) {
+  if (!de_begin_host || !dc_begin_host || !de_partial_host || !units_host) return GE2E_ERR_ARGUMENT;
+  return tc_debug_bwd_schedule(u_local, n_total, cta_group, max_clusters, de_begin_host, dc_begin_host,
+                               de_partial_host, units_host);
+}
+
 int ge2e_b200_path(int n_local, int n_total, int M, int D, int variant, int precision) {
   if (check_enum(variant, precision) != GE2E_OK) return GE2E_ERR_ARGUMENT;
   return (precision == GE2E_TF32 && tc_supported(n_local, n_total, M, D, variant)) ? 1 : 0;

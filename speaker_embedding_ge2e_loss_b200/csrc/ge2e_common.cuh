@@ -150,6 +150,8 @@ int simt_normalize_rows(const float* X, int rows, int D, float* Y, cudaStream_t 
 // ---- launchers implemented in ge2e_tc.cu (tcgen05 / TMA / TMEM path) ----------------------
 bool tc_supported(int n_local, int n_total, int M, int D, int variant);
 void tc_set_trace(unsigned long long* device_buf, int mode);
+int tc_debug_bwd_schedule(int u_local, int n_total, int cg, int max_clusters, int* de_begin, int* dc_begin,
+                          int* de_partial, int* units);
 size_t tc_workspace_bytes(int n_local, int n_total, int M, int D, int variant);
 int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* row_aux,
                 float* loss_accum, float* per_row_out, void* ws, size_t ws_bytes, bool after_prep,

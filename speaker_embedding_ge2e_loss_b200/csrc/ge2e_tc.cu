@@ -1127,6 +1127,23 @@ Layout fwd_layout(int U, int n_total, int D, int variant) {
 
 void tc_set_trace(unsigned long long* device_buf, int mode) { g_trace = device_buf; g_trace_mode = mode; }
 
+// Host-only view of the backward schedule for tests: same arithmetic as tc_bwd_rows, the number of
+// co-resident clusters is an argument instead of an occupancy query.
+int tc_debug_bwd_schedule(int u_local, int n_total, int cg, int max_clusters, int* de_begin, int* dc_begin,
+                          int* de_partial, int* units) {
+  if (u_local <= 0 || n_total <= 0 || (cg != 1 && cg != 2) || max_clusters <= 0 || max_clusters > kMaxClusters)
+    return GE2E_ERR_ARGUMENT;
+  const int OTe = (u_local + kTile - 1) / kTile, STe = (n_total + kUnit - 1) / kUnit;
+  const int OTc = (n_total + kTile - 1) / kTile, STc = (u_local + kUnit - 1) / kUnit;
+  BwdSched S{};
+  bool partial = false;
+  const int NC = make_bwd_sched((OTe + cg - 1) / cg, STe, (OTc + cg - 1) / cg, STc, max_clusters, &S, &partial);
+  for (int c = 0; c <= NC; ++c) { de_begin[c] = S.de[c]; dc_begin[c] = S.dc[c]; }
+  *de_partial = partial ? 1 : 0;
+  units[0] = (OTe + cg - 1) / cg; units[1] = STe; units[2] = (OTc + cg - 1) / cg; units[3] = STc;
+  return NC;
+}
+
 bool tc_supported(int n_local, int n_total, int M, int D, int variant) {
   (void)variant;
   if (D % kSlabCols != 0 || D < kSlabCols || D > kMaxSlabs * kSlabCols) return false;

@@ -114,3 +114,33 @@ def test_product_does_not_import_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg_dir, fn)).read()
             assert "oracle" not in src, f"{fn} references oracle/"
+
+
+# ------------------------------------------------------------------ backward work schedule (host logic)
+@pytest.mark.parametrize("u_local,n_total", [(10240, 1024), (131072, 8192), (16384, 8192), (4096, 2048), (2100, 300),
+                                             (256, 8192), (300 * 7, 300), (65536, 256), (1024, 1024)])
+@pytest.mark.parametrize("cg,max_cl", [(2, 74), (1, 148), (2, 8), (1, 3)])
+def test_backward_schedule_covers_every_pair_once(pkg, u_local, n_total, cg, max_cl):
+    """Every (owner group, stream unit) pair of both contractions belongs to exactly one cluster, the
+    ranges are contiguous and monotone, dE_hat groups are whole unless the fallback cut is reported,
+    and no cluster carries much more than the level share."""
+    import ctypes as C
+    h = pkg.lib()
+    de = (C.c_int * (max_cl + 1))()
+    dc = (C.c_int * (max_cl + 1))()
+    part = C.c_int(0)
+    units = (C.c_int * 4)()
+    nc = h.ge2e_b200_debug_bwd_schedule(u_local, n_total, cg, max_cl, de, dc, C.byref(part), units)
+    assert 1 <= nc <= max_cl
+    oge, ste, ogc, stc = list(units)
+    de, dc = list(de)[:nc + 1], list(dc)[:nc + 1]
+    assert de[0] == 0 and dc[0] == 0 and de[-1] == oge * ste and dc[-1] == ogc * stc
+    assert all(b >= a for a, b in zip(de, de[1:])) and all(b >= a for a, b in zip(dc, dc[1:]))
+    if not part.value:
+        assert all(x % ste == 0 for x in de), "whole dE_hat groups expected"
+    loads = [(de[c + 1] - de[c]) + (dc[c + 1] - dc[c]) for c in range(nc)]
+    total = oge * ste + ogc * stc
+    assert sum(loads) == total
+    level = -(-total // nc)
+    # whole groups may overshoot the level share by 1/8, a dC segment shorter than 3 units is not handed out
+    assert max(loads) <= level + level // 8 + max(ste, 3) + 1, (max(loads), level)
