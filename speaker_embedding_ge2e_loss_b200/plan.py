@@ -89,3 +89,84 @@ class GE2EPlan:
             self.launches_per_step = (lib().ge2e_b200_launch_count() - before) // max(1, steps)
         self._graph = g
         return g
+
+
+class ShardedGE2EPlan:
+    """Speaker-sharded fwd+bwd (one process per GPU) with persistent buffers, the C-ABI stages and the
+    three NCCL collectives enqueued back to back so that the whole step can be captured in one CUDA
+    graph: prep -> all-gather(c_hat) -> fwd_rows -> bwd_rows -> reduce-scatter(dC_hat) ->
+    all-reduce({loss, dw, db}) -> bwd_finalize.  Upstream gradient = 1 (``loss.backward()``).
+    Results: ``.loss`` (global), ``.dE`` (this rank's rows), ``.dw`` / ``.db`` (global)."""
+
+    def __init__(self, n_local: int, n_total: int, spk_offset: int, M: int, D: int, variant: str = "softmax",
+                 precision: str = "tf32", eps: float = 1e-6, group=None, device=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group if group is not None else dist.group.WORLD
+        self.n_local, self.n_total, self.spk_offset, self.M, self.D = n_local, n_total, spk_offset, M, D
+        self.variant = _lib.VARIANTS[variant]
+        self.precision = _lib.PRECISIONS[precision]
+        self.eps = float(eps)
+        self.device = torch.device(device if device is not None else "cuda")
+        U, dev, f32 = n_local * M, self.device, torch.float32
+        self.e_hat = torch.empty((U, D), dtype=f32, device=dev)
+        self.c_hat_all = torch.empty((n_total, D), dtype=f32, device=dev)
+        self.c_hat_mine = self.c_hat_all[spk_offset:spk_offset + n_local]
+        self.cos_diag = torch.empty(U, dtype=f32, device=dev)
+        self.row_stat = torch.empty(U, dtype=f32, device=dev)
+        self.row_kstar = torch.empty(U, dtype=torch.int32, device=dev)
+        self.row_aux = torch.empty(U, dtype=f32, device=dev)
+        self.dE_hat = torch.empty((U, D), dtype=f32, device=dev)
+        self.dC_partial = torch.empty((n_total, D), dtype=f32, device=dev)
+        self.dC_local = torch.empty((n_local, D), dtype=f32, device=dev)
+        self.red = torch.empty(4, dtype=f32, device=dev)          # {loss, dw, db, -}: zeroed by prep, all-reduced
+        self.dE = torch.empty((n_local, M, D), dtype=f32, device=dev)
+        self.grad_out = torch.ones((), dtype=f32, device=dev)
+        nbytes = lib().ge2e_b200_workspace_bytes(n_local, n_total, M, D, self.variant, self.precision)
+        self._ws = torch.zeros(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        self._ws_bytes = nbytes
+        self.loss, self.dw, self.db = self.red[0], self.red[1], self.red[2]
+
+    def step(self, E_local: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> None:
+        h, dist = lib(), self.dist
+        nl, nt, off, M, D = self.n_local, self.n_total, self.spk_offset, self.M, self.D
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        ws = self._ws.data_ptr() if self._ws_bytes else None
+        check(h.ge2e_b200_prep(E_local.data_ptr(), nl, M, D, self.precision, self.e_hat.data_ptr(),
+                               self.c_hat_mine.data_ptr(), self.cos_diag.data_ptr(), self.red.data_ptr(), s),
+              "ge2e_b200_prep")
+        dist.all_gather_into_tensor(self.c_hat_all, self.c_hat_mine, group=self.group)
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        check(h.ge2e_b200_fwd_rows(self.e_hat.data_ptr(), self.c_hat_all.data_ptr(), self.cos_diag.data_ptr(), nl, nt,
+                                   off, M, D, w.data_ptr(), b.data_ptr(), self.eps, self.variant, self.precision,
+                                   self.row_stat.data_ptr(), self.row_kstar.data_ptr(), self.row_aux.data_ptr(),
+                                   self.red.data_ptr(), None, None, ws, self._ws_bytes, s), "ge2e_b200_fwd_rows")
+        check(h.ge2e_b200_bwd_rows(self.e_hat.data_ptr(), self.c_hat_all.data_ptr(), self.cos_diag.data_ptr(),
+                                   self.row_stat.data_ptr(), self.row_kstar.data_ptr(), self.row_aux.data_ptr(), nl, nt,
+                                   off, M, D, w.data_ptr(), b.data_ptr(), self.eps, self.variant, self.precision,
+                                   self.grad_out.data_ptr(), self.dE_hat.data_ptr(), self.dC_partial.data_ptr(),
+                                   self.red.data_ptr() + 4, ws, self._ws_bytes, s), "ge2e_b200_bwd_rows")
+        dist.reduce_scatter_tensor(self.dC_local, self.dC_partial, op=dist.ReduceOp.SUM, group=self.group)
+        dist.all_reduce(self.red, op=dist.ReduceOp.SUM, group=self.group)
+        check(h.ge2e_b200_bwd_finalize(E_local.data_ptr(), self.dE_hat.data_ptr(), self.dC_local.data_ptr(),
+                                       self.cos_diag.data_ptr(), self.row_stat.data_ptr(), self.row_aux.data_ptr(), nl,
+                                       M, D, w.data_ptr(), b.data_ptr(), self.eps, self.variant,
+                                       self.grad_out.data_ptr(), self.dE.data_ptr(), s), "ge2e_b200_bwd_finalize")
+
+    def capture(self, E_local, w: torch.Tensor, b: torch.Tensor, steps: int = 1):
+        """``steps`` consecutive sharded steps in one CUDA graph (NCCL collectives included).
+        ``E_local`` is one batch or a list of batches the steps rotate over."""
+        batches = list(E_local) if isinstance(E_local, (list, tuple)) else [E_local]
+        with torch.cuda.device(self.device):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self.step(batches[0], w, b)          # warm-up: communicator set-up, lazy attributes
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for k in range(steps):
+                    self.step(batches[k % len(batches)], w, b)
+        return g
