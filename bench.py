@@ -406,11 +406,59 @@ def run_ours(args):
         piped = {"value": U / (e2e_pipe_t * 1e-3), "ms_per_step_device": e2e_pipe_dev,
                  "ms_per_step_wall": e2e_pipe_wall,
                  "how": "H2D of batch k+1 on a copy stream under the fwd+bwd of batch k (double-buffered feed)"}
-        best, other, oname = (piped, serial, "serial") if e2e_pipe_t < e2e_serial_t else (serial, piped, "pipelined")
+        # the host-fed plan (public API GE2EHostFeed): same double-buffered feed, each slot's step (stages +
+        # the D2H read of loss/dw/db) is one CUDA graph, so the host issues a few stream calls per batch;
+        # every step's result is read on the host (one step behind the submit)
+        from speaker_embedding_ge2e_loss_b200 import GE2EHostFeed
+        feed = GE2EHostFeed(N, M, D, w, b, args.variant, args.precision, device=dev)
+        fhosts = [make_batch(N, M, D, seed=i).pin_memory() for i in range(3)]
+
+        def fed(steps):
+            prev, out = None, None
+            for k in range(steps):
+                t = feed.submit(fhosts[k % 3])
+                if prev is not None:
+                    out = feed.result(prev)
+                prev = t
+            return feed.result(prev)
+
+        # warm-up until the rate settles: after the host-side set-up above the GPU has idled and its clocks
+        # ramp back only gradually under this copy-dominated load (scripts/h2d_probe.py: 640 -> 195 us/step
+        # over ~250 steps on a fresh feed); steady state is what a training loop sees
+        fed(max(4, args.warmup))
+        last, fed_warm = None, max(4, args.warmup)
+        for _ in range(20):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fed(50)
+            torch.cuda.synchronize()
+            cur = time.perf_counter() - t0
+            fed_warm += 50
+            if last is not None and abs(cur - last) <= 0.03 * last:
+                break
+            last = cur
+        torch.cuda.synchronize()
+        fe0, fe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        fe0.record(feed.copy_stream)
+        fed_last = fed(args.steps)
+        fe1.record(feed.compute_stream)
+        torch.cuda.synchronize()
+        fed_wall = (time.perf_counter() - t0) * 1e3 / args.steps
+        fed_dev = fe0.elapsed_time(fe1) / args.steps
+        fed_t = max(fed_dev, fed_wall)
+        fedd = {"value": U / (fed_t * 1e-3), "ms_per_step_device": fed_dev, "ms_per_step_wall": fed_wall,
+                "how": "GE2EHostFeed: H2D of batch k+1 on a copy stream under the graph-captured fwd+bwd+result read of "
+                       "batch k; every step's loss/dw/db read on the host", "last_result": list(fed_last),
+                "warmup_steps": fed_warm,
+                "h2d_gbps": E_host.numel() * 4 / (fed_t * 1e-3) / 1e9}
+        cands = {"host_fed_plan": fedd, "module_api_pipelined": piped, "module_api_serial": serial}
+        bname = min(cands, key=lambda k: U / cands[k]["value"])
+        best = cands[bname]
         e2e = {"value": best["value"], "unit": UNIT, "h2d_bytes_per_step": E_host.numel() * 4,
                "d2h_bytes_per_step": 12, "ms_per_step_device": best["ms_per_step_device"],
-               "ms_per_step_wall": best["ms_per_step_wall"], "how": "module API (eager): " + best["how"],
-               oname: other}
+               "ms_per_step_wall": best["ms_per_step_wall"], "how": bname + ": " + best["how"]}
+        e2e.update({k: v for k, v in cands.items() if k != bname})
 
         # ---- roofline of the dominant stage ---------------------------------------------------
         st = stage_times(plan, E, w, b, flush)

@@ -145,6 +145,17 @@ int ge2e_b200_bwd_finalize(const float* E, const float* dE_hat, const float* dC_
                            int n_local, int M, int D, const float* w, const float* b, float eps,
                            int variant, const float* grad_out, float* dE, ge2e_stream_t stream);
 
+/* The trainer's post-loss tail for the two loss parameters, on the device (SURVEY 8(f) row 1;
+ * replaces `torch.nn.utils.clip_grad_norm_(self.ge2e_loss.parameters(), 1.0)` and the loss
+ * parameter group's share of `self.optimizer.step()` (plain SGD), s4_train_embed_model.py:202-203,
+ * :35-42).  clip_grad_norm_ semantics: total = sqrt(dw^2 + db^2); coef = min(1, max_norm /
+ * (total + 1e-6)); dw, db are scaled by coef IN PLACE (as the reference leaves them), then
+ * w -= lr * dw, b -= lr * db.  total_norm (nullable, device) receives the unclipped norm, the value
+ * clip_grad_norm_ returns.  All pointers are device pointers to single floats.  Enqueue it after the
+ * backward on the same stream; one one-thread kernel, launched under the previous kernel's tail. */
+int ge2e_b200_scale_bias_sgd(float* w, float* b, float* dw, float* db, float max_norm, float lr,
+                             float* total_norm, ge2e_stream_t stream);
+
 /* ---- single-device conveniences (n_local == n_total) ---------------------------------- */
 
 /* GE2ELoss.forward (s3:19-30): prep + fwd_rows.  loss = accum[0]. */

@@ -211,6 +211,13 @@ int ge2e_b200_bwd_finalize(const float* E, const float* dE_hat, const float* dC_
                            variant, grad_out, dE, true, stream);
 }
 
+int ge2e_b200_scale_bias_sgd(float* w, float* b, float* dw, float* db, float max_norm, float lr,
+                             float* total_norm, ge2e_stream_t stream) {
+  if (!w || !b || !dw || !db) return GE2E_ERR_ARGUMENT;
+  if (!(max_norm > 0.f) || !(lr >= 0.f)) return GE2E_ERR_ARGUMENT;
+  return simt_scale_bias_sgd(w, b, dw, db, max_norm, lr, total_norm, true, (cudaStream_t)stream);
+}
+
 int ge2e_b200_forward_indexed(const float* E, const int32_t* row_index, int N, int M, int D, const float* w,
                               const float* b, float eps, int variant, int precision, float* e_hat, float* c_hat,
                               float* cos_diag, float* row_stat, int32_t* row_kstar, float* row_aux, float* accum,

@@ -1387,6 +1387,32 @@ int simt_bwd_finalize(const float* E, const int32_t* row_index, const float* dE_
   return GE2E_OK;
 }
 
+// The trainer's post-loss tail for the two loss parameters (s4_train_embed_model.py:202-203):
+// clip_grad_norm_((w, b), max_norm) followed by the plain-SGD update, on the device, one thread.
+// clip_grad_norm_ semantics: total = ||(dw, db)||_2, coef = min(1, max_norm / (total + 1e-6)),
+// grads scaled in place (they stay visible to the caller), then p -= lr * grad.
+__global__ void scale_bias_sgd_kernel(float* w, float* b, float* dw, float* db, float max_norm, float lr,
+                                      float* total_norm) {
+  pdl_wait();
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float gw = *dw, gb = *db;
+  const float total = sqrtf(gw * gw + gb * gb);
+  const float coef = fminf(max_norm / (total + 1e-6f), 1.0f);
+  const float cw = gw * coef, cb = gb * coef;
+  *dw = cw;
+  *db = cb;
+  *w = *w - lr * cw;
+  *b = *b - lr * cb;
+  if (total_norm) *total_norm = total;
+}
+
+int simt_scale_bias_sgd(float* w, float* b, float* dw, float* db, float max_norm, float lr, float* total_norm,
+                        bool pdl, cudaStream_t st) {
+  launch_pdl(scale_bias_sgd_kernel, dim3(1), dim3(32), 0, st, pdl, w, b, dw, db, max_norm, lr, total_norm);
+  GE2E_LAUNCHED();
+  return GE2E_OK;
+}
+
 int simt_centroids(const float* E, int N, int M, int D, float* C, cudaStream_t st) {
   centroids_kernel<<<N, 128, 0, st>>>(E, M, D, C);
   GE2E_LAUNCHED();

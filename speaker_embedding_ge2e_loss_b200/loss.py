@@ -56,6 +56,24 @@ class GE2ELoss(nn.Module):
                                      self.process_group)
         return ops.ge2e_loss(embeddings, self.w, self.b, self.eps, self.variant, self.precision, unperm, speakers)
 
+    @torch.no_grad()
+    def clip_and_sgd_step(self, lr: float, max_norm: float = 1.0, return_norm: bool = False):
+        """The trainer's tail for the loss's own two parameters in ONE kernel launch
+        (s4_train_embed_model.py:202-203): ``clip_grad_norm_(self.parameters(), max_norm)`` followed
+        by the plain-SGD update ``p -= lr * p.grad``.  ``w.grad`` / ``b.grad`` are left clipped in
+        place, as ``clip_grad_norm_`` leaves them.  Keep ``w`` and ``b`` out of the optimiser's
+        parameter groups when using this.  Returns the unclipped norm (0-dim tensor) on request."""
+        if self.w.grad is None or self.b.grad is None:
+            raise RuntimeError("clip_and_sgd_step: call backward() first (w.grad / b.grad are None)")
+        ops._need_cuda(self.w)
+        norm = torch.empty((), dtype=torch.float32, device=self.w.device) if return_norm else None
+        with torch.cuda.device(self.w.device):
+            _lib.check(_lib.lib().ge2e_b200_scale_bias_sgd(
+                self.w.data_ptr(), self.b.data_ptr(), self.w.grad.data_ptr(), self.b.grad.data_ptr(),
+                float(max_norm), float(lr), norm.data_ptr() if return_norm else None, ops._stream()),
+                "ge2e_b200_scale_bias_sgd")
+        return norm
+
     def path_for(self, N: int, M: int, D: int) -> int:
         """Which kernels a batch of this shape runs on: 0 = SIMT fp32, 1 = tcgen05 TF32."""
         return _lib.lib().ge2e_b200_path(N, N, M, D, _lib.VARIANTS[self.variant], _lib.PRECISIONS[self.precision])

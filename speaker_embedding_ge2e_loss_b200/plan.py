@@ -16,7 +16,11 @@ from ._lib import check, lib
 
 class GE2EPlan:
     def __init__(self, N: int, M: int, D: int, variant: str = "softmax", precision: str = "fp32",
-                 eps: float = 1e-6, device=None):
+                 eps: float = 1e-6, device=None, sgd=None):
+        """``sgd=(lr, max_norm)``: every step ends with the trainer's tail for the two loss parameters
+        (clip_grad_norm_ on (w, b) + plain SGD, s4_train_embed_model.py:202-203) as one more kernel,
+        updating the ``w`` / ``b`` passed to ``step`` in place."""
+        self.sgd = None if sgd is None else (float(sgd[0]), float(sgd[1]))
         if M < 2:
             raise ValueError("GE2E needs M >= 2 utterances per speaker")
         self.N, self.M, self.D = N, M, D
@@ -68,6 +72,10 @@ class GE2EPlan:
                                   self.grad_out.data_ptr(), self.dE_hat.data_ptr(), self._scratch.data_ptr(),
                                   accum_ptr, self.dE.data_ptr(), ws, self._ws_bytes, stream)
         check(rc, "ge2e_b200_backward")
+        if self.sgd is not None:
+            rc = h.ge2e_b200_scale_bias_sgd(w.data_ptr(), b.data_ptr(), accum_ptr + 4, accum_ptr + 8, self.sgd[1],
+                                            self.sgd[0], None, stream)
+            check(rc, "ge2e_b200_scale_bias_sgd")
 
     def capture(self, E, w: torch.Tensor, b: torch.Tensor, backward: bool = True, steps: int = 1):
         """Capture ``steps`` consecutive steps into one CUDA graph bound to these tensors; returns the
@@ -170,3 +178,87 @@ class ShardedGE2EPlan:
                 for k in range(steps):
                     self.step(batches[k % len(batches)], w, b)
         return g
+
+
+class GE2EHostFeed:
+    """fwd+bwd over HOST-resident batches, pipelined: the H2D copy of batch k+1 (copy stream) runs
+    under the fwd+bwd of batch k (compute stream), and every slot's step -- the four stages plus the
+    device->host read of {loss, dw, db} into the slot's pinned result -- is one CUDA graph, so a
+    ``submit`` costs a handful of stream calls on the host.  This is the trainer's call sequence
+    (s4_train_embed_model.py:170-200: batch from the loader -> ``.to(device)`` -> loss -> backward ->
+    ``loss.to("cpu")``) with the loader's pinned batch as the input.
+
+        feed = GE2EHostFeed(N, M, D, w, b, precision="tf32")
+        t = feed.submit(E_pinned)          # returns at once
+        loss, dw, db = feed.result(t)      # waits for that slot; dE of the slot: feed.dE(t) (device)
+
+    ``depth`` slots are in flight at most; ``submit`` on a slot still in use waits on the device
+    (stream order), never on the host.  ``w`` / ``b`` are read at replay time, so in-place optimiser
+    updates between submits are seen."""
+
+    def __init__(self, N: int, M: int, D: int, w: torch.Tensor, b: torch.Tensor, variant: str = "softmax",
+                 precision: str = "fp32", eps: float = 1e-6, device=None, depth: int = 2):
+        self.device = torch.device(device if device is not None else "cuda")
+        self.N, self.M, self.D, self.depth = N, M, D, depth
+        self.w, self.b = w, b
+        dev = self.device
+        self.plans = [GE2EPlan(N, M, D, variant, precision, eps, device=dev) for _ in range(depth)]
+        self.bufs = [torch.empty((N, M, D), dtype=torch.float32, device=dev) for _ in range(depth)]
+        self.results = [torch.zeros(3, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.compute_stream = torch.cuda.Stream(device=dev)
+        self._copied = [torch.cuda.Event() for _ in range(depth)]
+        self._done = [torch.cuda.Event() for _ in range(depth)]
+        self._used = [False] * depth
+        self._k = 0
+        self._graphs = []
+        with torch.cuda.device(dev):
+            for i in range(depth):
+                p, buf, res = self.plans[i], self.bufs[i], self.results[i]
+                buf.zero_()
+                torch.cuda.synchronize()
+                with torch.cuda.stream(self.compute_stream):
+                    p.step(buf, w, b)                       # warm-up outside capture
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                before = lib().ge2e_b200_launch_count()
+                with torch.cuda.graph(g, stream=self.compute_stream):
+                    p.step(buf, w, b)
+                    res[0:1].copy_(p.loss.reshape(1), non_blocking=True)
+                    res[1:3].copy_(p._scratch[N * D:N * D + 2], non_blocking=True)
+                self.launches_per_step = lib().ge2e_b200_launch_count() - before
+                self._graphs.append(g)
+        self.path = self.plans[0].path
+
+    def submit(self, E_host: torch.Tensor) -> int:
+        if not (E_host.dtype == torch.float32 and E_host.is_contiguous() and E_host.numel() == self.N * self.M * self.D):
+            raise ValueError("GE2EHostFeed.submit: expected a contiguous fp32 batch of N*M*D values")
+        if E_host.device.type == "cpu" and not E_host.is_pinned():
+            raise ValueError("GE2EHostFeed.submit: the host batch must be in pinned memory (an unpinned copy is synchronous)")
+        i = self._k % self.depth
+        self._k += 1
+        cs, ms = self.copy_stream, self.compute_stream
+        if self._used[i]:
+            cs.wait_event(self._done[i])                 # slot's previous step has consumed its buffer
+        with torch.cuda.stream(cs):
+            self.bufs[i].copy_(E_host.view(self.N, self.M, self.D), non_blocking=True)
+            self._copied[i].record(cs)
+        ms.wait_event(self._copied[i])
+        with torch.cuda.stream(ms):
+            self._graphs[i].replay()
+            self._done[i].record(ms)
+        self._used[i] = True
+        return i
+
+    def result(self, ticket: int):
+        """(loss, dw, db) of the slot as Python floats; blocks until that slot's step has finished."""
+        self._done[ticket].synchronize()
+        r = self.results[ticket]
+        return float(r[0]), float(r[1]), float(r[2])
+
+    def dE(self, ticket: int) -> torch.Tensor:
+        """Device gradient of the slot's batch (valid once work queued after ``_done[ticket]``)."""
+        return self.plans[ticket].dE
+
+    def done_event(self, ticket: int) -> torch.cuda.Event:
+        return self._done[ticket]

@@ -63,6 +63,8 @@ def test_host_side_status_codes(pkg):
     assert h.ge2e_b200_fwd_rows(1, 1, 1, 4, 2, 0, 8, 256, 1, 1, 1e-6, 0, 0, 1, None, 1, 1, None, None, None, 0,
                                 None) == -1                                    # shard outside [0, n_total)
     assert h.ge2e_b200_calc_loss(1, 4, 8, 1e-6, 9, 1, None, None) == -3
+    assert h.ge2e_b200_scale_bias_sgd(None, 1, 1, 1, 1.0, 0.01, None, None) == -3   # null parameter pointer
+    assert h.ge2e_b200_scale_bias_sgd(1, 1, 1, 1, 0.0, 0.01, None, None) == -3      # max_norm must be > 0
     assert h.ge2e_b200_path(64, 64, 10, 256, 0, 0) == 0                        # fp32 -> SIMT kernels
     assert h.ge2e_b200_path(64, 64, 10, 256, 5, 0) < 0
 

@@ -418,3 +418,86 @@ def test_training_steps_track_reference_port(pkg):
     np.testing.assert_allclose(traj["new"][0], traj["ref"][0], rtol=2e-4)
     assert abs(traj["new"][1] - traj["ref"][1]) < 1e-4
     assert abs(traj["new"][2] - traj["ref"][2]) < 1e-4
+
+
+@pytest.mark.parametrize("N,M,D,precision,tol", [(96, 6, 256, "tf32", 2e-3), (40, 5, 128, "fp32", 1e-5)])
+def test_host_feed_matches_oracle_per_batch(pkg, N, M, D, precision, tol):
+    """GE2EHostFeed (bench.py's e2e arm): pinned host batches in, {loss, dw, db} read back per step,
+    copy of batch k+1 under the step of batch k.  Every batch's result must be that batch's oracle
+    result, in order, with more batches than slots (slot reuse) and an in-place update of w between
+    submits (w is read at replay time)."""
+    dev = torch.device("cuda:0")
+    w = torch.tensor(10.0, device=dev)
+    b = torch.tensor(-5.0, device=dev)
+    feed = pkg.GE2EHostFeed(N, M, D, w, b, "softmax", precision, device=dev)
+    batches = [orc.make_embeddings(N, M, D, seed=s, kind="clustered") for s in range(5)]
+    hosts = [torch.tensor(np.asarray(x, dtype=np.float32)).pin_memory() for x in batches]
+    tickets, got, dEs = [], [], []
+    for k, h in enumerate(hosts):
+        if k == 3:
+            torch.cuda.synchronize()
+            w.fill_(7.5)
+        t = feed.submit(h)
+        if tickets:
+            got.append(feed.result(tickets[-1]))
+        tickets.append(t)
+        feed.done_event(t).synchronize()
+        dEs.append(feed.dE(t).cpu().numpy().copy())
+    got.append(feed.result(tickets[-1]))
+    for k, x in enumerate(batches):
+        ref = orc.forward_backward(x, 10.0 if k < 3 else 7.5, -5.0, 1e-6, "softmax")
+        check(dict(loss=got[k][0], dw=got[k][1], db=got[k][2], dE=dEs[k]), ref, N * M, tol)
+    with pytest.raises(ValueError):
+        feed.submit(torch.zeros(N, M, D))            # unpinned host memory
+
+
+def test_clip_and_sgd_tail_matches_torch(pkg):
+    """SURVEY 8(f) row 1, second half: clip_grad_norm_((w, b), 1.0) + SGD step of the loss parameters
+    (s4:202-203) as one kernel, against torch's own two calls on the same gradients -- with the norm
+    above max_norm (the usual case at training sizes) and below it."""
+    dev = torch.device("cuda:0")
+    N, M, D = 16, 5, 64
+    E_np = orc.make_embeddings(N, M, D, seed=2, kind="clustered")
+    for scale, lr in ((100.0, 0.01), (1.0, 0.5)):
+        ours = pkg.GE2ELoss(None, device=dev)
+        E = torch.tensor(np.asarray(E_np, dtype=np.float32), device=dev)
+        (ours(E) * scale).backward()
+        ref_w = torch.nn.Parameter(ours.w.detach().clone())
+        ref_b = torch.nn.Parameter(ours.b.detach().clone())
+        ref_w.grad, ref_b.grad = ours.w.grad.clone(), ours.b.grad.clone()
+        ref_norm = torch.nn.utils.clip_grad_norm_([ref_w, ref_b], 1.0)
+        torch.optim.SGD([ref_w, ref_b], lr=lr).step()
+        norm = ours.clip_and_sgd_step(lr=lr, max_norm=1.0, return_norm=True)
+        torch.cuda.synchronize()
+        assert (ref_norm.item() > 1.0) == (scale == 100.0)
+        for got, ref in ((norm, ref_norm), (ours.w, ref_w), (ours.b, ref_b), (ours.w.grad, ref_w.grad),
+                         (ours.b.grad, ref_b.grad)):
+            assert abs(got.item() - ref.item()) <= 2e-6 * max(1.0, abs(ref.item())), (got.item(), ref.item())
+    with pytest.raises(RuntimeError):
+        pkg.GE2ELoss(None, device=dev).clip_and_sgd_step(lr=0.01)
+
+
+def test_plan_with_sgd_tail_tracks_manual_updates(pkg):
+    """GE2EPlan(sgd=(lr, max_norm)): three captured steps, each ending with the fused tail, against the
+    same three steps with the update applied by torch between plan steps."""
+    dev = torch.device("cuda:0")
+    N, M, D, lr = 64, 6, 256, 0.05
+    Es = [torch.tensor(np.asarray(orc.make_embeddings(N, M, D, seed=s, kind="clustered"), dtype=np.float32), device=dev)
+          for s in range(3)]
+    w = torch.tensor(10.0, device=dev); b = torch.tensor(-5.0, device=dev)
+    plan = pkg.GE2EPlan(N, M, D, "softmax", "tf32", device=dev, sgd=(lr, 1.0))
+    g = plan.capture(Es, w, b, steps=3)
+    w.fill_(10.0); b.fill_(-5.0)                         # capture's warm-up step has already moved them
+    g.replay()
+    torch.cuda.synchronize()
+    rw = torch.nn.Parameter(torch.tensor(10.0, device=dev)); rb = torch.nn.Parameter(torch.tensor(-5.0, device=dev))
+    ref = pkg.GE2EPlan(N, M, D, "softmax", "tf32", device=dev)
+    for k in range(3):
+        ref.step(Es[k], rw.data, rb.data)
+        torch.cuda.synchronize()
+        rw.grad, rb.grad = ref.dw.clone(), ref.db.clone()
+        torch.nn.utils.clip_grad_norm_([rw, rb], 1.0)
+        torch.optim.SGD([rw, rb], lr=lr).step()
+    assert abs(w.item() - rw.item()) <= 1e-5 and abs(b.item() - rb.item()) <= 1e-5, (w.item(), rw.item(), b.item(), rb.item())
+    assert abs(w.item() - 10.0) > 1e-3                   # the parameters did move
+    assert abs(plan.loss.item() - ref.loss.item()) <= 1e-5 * abs(ref.loss.item())
