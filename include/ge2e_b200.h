@@ -156,6 +156,21 @@ int ge2e_b200_bwd_finalize(const float* E, const float* dE_hat, const float* dC_
 int ge2e_b200_scale_bias_sgd(float* w, float* b, float* dw, float* db, float max_norm, float lr,
                              float* total_norm, ge2e_stream_t stream);
 
+/* EER sweep counts (s5_eval_model.py:57-89: `S_thres = S > thres`,
+ * `np.sum(S_thres[i])`, `np.sum(S_thres[i, :, i])` for 50 thresholds).  One pass over the float32
+ * similarity matrix sim[N, M, N] (device) for all T thresholds at once:
+ *   thresholds[T]  device, float32, ASCENDING (duplicates allowed), 1 <= T <= 1024
+ *   accept_all[T]  device int64: entries of sim greater than thresholds[t]
+ *   accept_own[T]  device int64: the same over the own-speaker entries sim[j, :, j]
+ *   scratch        device, ge2e_b200_threshold_counts_scratch_bytes(T) bytes (zeroed by the call)
+ * FAR / FRR / EER (s5:80-97) are a few scalar operations on these counts and stay on the host
+ * (speaker_embedding_ge2e_loss_b200/evaluation.py).  Comparisons are float32 `>` as in numpy; a NaN
+ * entry exceeds no threshold.  Integer results, bit-exact. */
+size_t ge2e_b200_threshold_counts_scratch_bytes(int T);
+int ge2e_b200_threshold_counts(const float* sim, int N, int M, const float* thresholds, int T,
+                               long long* accept_all, long long* accept_own, void* scratch,
+                               size_t scratch_bytes, ge2e_stream_t stream);
+
 /* ---- single-device conveniences (n_local == n_total) ---------------------------------- */
 
 /* GE2ELoss.forward (s3:19-30): prep + fwd_rows.  loss = accum[0]. */

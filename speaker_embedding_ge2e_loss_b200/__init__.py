@@ -4,9 +4,10 @@ Host layer only (module, torch.library op, ctypes binding of include/ge2e_b200.h
 arithmetic happens in the hand-written sm_100a kernels under ``csrc/``.
 """
 from ._lib import GE2ELibraryError, lib  # noqa: F401
+from .evaluation import EERResult, eer_sweep, evaluate_eer, threshold_counts  # noqa: F401
 from .loss import GE2ELoss  # noqa: F401
 from .ops import ge2e_loss  # noqa: F401
 from .plan import GE2EHostFeed, GE2EPlan, ShardedGE2EPlan  # noqa: F401
 from .sharded import shard_bounds, sharded_ge2e_loss  # noqa: F401
 
-__all__ = ["GE2ELoss", "GE2EPlan", "GE2EHostFeed", "ShardedGE2EPlan", "ge2e_loss", "sharded_ge2e_loss", "shard_bounds", "GE2ELibraryError", "lib"]
+__all__ = ["GE2ELoss", "GE2EPlan", "GE2EHostFeed", "ShardedGE2EPlan", "ge2e_loss", "eer_sweep", "evaluate_eer", "threshold_counts", "EERResult", "sharded_ge2e_loss", "shard_bounds", "GE2ELibraryError", "lib"]

@@ -211,6 +211,20 @@ int ge2e_b200_bwd_finalize(const float* E, const float* dE_hat, const float* dC_
                            variant, grad_out, dE, true, stream);
 }
 
+size_t ge2e_b200_threshold_counts_scratch_bytes(int T) {
+  return T < 1 ? 0 : (size_t)(2 * (T + 1) + 1) * sizeof(unsigned long long);
+}
+
+int ge2e_b200_threshold_counts(const float* sim, int N, int M, const float* thresholds, int T,
+                               long long* accept_all, long long* accept_own, void* scratch,
+                               size_t scratch_bytes, ge2e_stream_t stream) {
+  if (N < 1 || M < 1) return GE2E_ERR_SHAPE;
+  if (!sim || !thresholds || !accept_all || !accept_own || !scratch) return GE2E_ERR_ARGUMENT;
+  if (T < 1) return GE2E_ERR_SHAPE;
+  if (scratch_bytes < ge2e_b200_threshold_counts_scratch_bytes(T)) return GE2E_ERR_WORKSPACE;
+  return simt_threshold_counts(sim, N, M, thresholds, T, accept_all, accept_own, scratch, (cudaStream_t)stream);
+}
+
 int ge2e_b200_scale_bias_sgd(float* w, float* b, float* dw, float* db, float max_norm, float lr,
                              float* total_norm, ge2e_stream_t stream) {
   if (!w || !b || !dw || !db) return GE2E_ERR_ARGUMENT;

@@ -143,6 +143,8 @@ int simt_bwd_finalize(const float* E, const int32_t* row_index, const float* dE_
                       const float* grad_out, float* dE, bool pdl, cudaStream_t st);
 int simt_scale_bias_sgd(float* w, float* b, float* dw, float* db, float max_norm, float lr, float* total_norm,
                         bool pdl, cudaStream_t st);
+int simt_threshold_counts(const float* sim, int N, int M, const float* thresholds, int T, long long* accept_all,
+                          long long* accept_own, void* scratch, cudaStream_t st);
 int simt_centroids(const float* E, int N, int M, int D, float* C, cudaStream_t st);
 int simt_utterance_centroids(const float* E, int N, int M, int D, float* Uc, cudaStream_t st);
 int simt_calc_loss(const float* S, int N, int M, float eps, int variant, float* loss,

@@ -1413,6 +1413,197 @@ int simt_scale_bias_sgd(float* w, float* b, float* dw, float* db, float max_norm
   return GE2E_OK;
 }
 
+// ---- EER sweep counts (s5_eval_model.py:57-89) ------------------------------------------------
+// For every threshold t: how many entries of sim[N, M, N] exceed it, over the whole matrix and over
+// the own-speaker entries sim[j, :, j].  One pass over the matrix: each value is binned by the number
+// of (ascending) thresholds below it, bins are counted in shared-memory histograms (warp-aggregated:
+// clustered embeddings put most of a warp into the same bin), and the last block turns the histograms
+// into "accepted at threshold t" = sum of the bins above t.  Integer work, bit-exact by construction.
+// Up to kEerPrivT thresholds (the reference uses 50) every lane owns a private column of its warp's
+// histogram (bank = lane: plain conflict-free read-modify-write, no atomics); beyond that the warps of a
+// block share one histogram through warp-aggregated shared-memory atomics.
+constexpr int kEerMaxT = 1024;
+constexpr int kEerThreads = 256;
+constexpr int kEerPrivT = 64;
+constexpr int kEerPrivThreads = 128;
+
+__device__ __forceinline__ int eer_bin(float v, const float* thr, int T) {
+  int lo = 0, hi = T;                      // number of thresholds with v > thr  (NaN -> 0)
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (v > thr[mid]) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// The same count, reached from a linear guess between the first and the last threshold and two
+// verifying compares (thr[g-1] < v, !(thr[g] < v)); the guess only ever saves the search -- a wrong
+// one (unevenly spaced thresholds, a value exactly on a threshold) falls back to it.  The reference's
+// thresholds are an even grid (s5:57), for which the guess is right except on ties.
+__device__ __forceinline__ int eer_bin_guess(float v, const float* thr, int T, float lo, float inv) {
+  const float f = (v - lo) * inv;
+  const int g = (f >= 0.f) ? ((f < (float)T) ? (int)f + 1 : T) : 0;      // NaN -> 0
+  const bool ok_lo = (g == 0) || (v > thr[g - 1]);
+  const bool ok_hi = (g == T) || !(v > thr[g]);
+  if (ok_lo && ok_hi) return g;
+  return eer_bin(v, thr, T);
+}
+
+__device__ __forceinline__ void eer_count(unsigned* hist, int bin, bool on) {
+  const unsigned act = __ballot_sync(0xffffffffu, on);
+  if (!on) return;
+  const unsigned peers = __match_any_sync(act, bin);
+  if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[bin], (unsigned)__popc(peers));
+}
+
+// accepted at threshold t = values with more than t thresholds below them = sum of bins t+1 .. T
+__device__ __forceinline__ void eer_finish(unsigned long long* hist_g, int T, long long* accept_all, long long* accept_own) {
+  if (threadIdx.x < 2) {
+    const volatile unsigned long long* h = hist_g + threadIdx.x * (T + 1);
+    long long* out = threadIdx.x == 0 ? accept_all : accept_own;
+    long long run = 0;
+    for (int t = T - 1; t >= 0; --t) {
+      run += (long long)h[t + 1];
+      out[t] = run;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kEerPrivThreads)
+threshold_counts_private_kernel(const float* __restrict__ sim, long long rows, int N, int M,
+                                const float* __restrict__ thr_g, int T, unsigned long long* __restrict__ hist_g,
+                                long long* __restrict__ accept_all, long long* __restrict__ accept_own) {
+  extern __shared__ unsigned eer_smem[];
+  constexpr int kWarps = kEerPrivThreads / 32;
+  float* thr = reinterpret_cast<float*>(eer_smem);            // [T]
+  unsigned* h_own = eer_smem + T;                              // [T + 1]
+  unsigned* priv = h_own + (T + 1);                            // [kWarps][T + 1][32]
+  __shared__ bool last;
+  for (int i = threadIdx.x; i < T; i += blockDim.x) thr[i] = thr_g[i];
+  for (int i = threadIdx.x; i < (T + 1) * (1 + kWarps * 32); i += blockDim.x) h_own[i] = 0u;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned* mine = priv + (size_t)warp * (T + 1) * 32 + lane;
+  const float g_lo = thr[0];
+  const float g_span = thr[T - 1] - thr[0];
+  const float g_inv = g_span > 0.f ? (float)(T - 1) / g_span : 0.f;
+  const long long nwarps = (long long)gridDim.x * kWarps;
+  for (long long row = (long long)blockIdx.x * kWarps + warp; row < rows; row += nwarps) {
+    const int j = (int)(row / M);
+    const float* src = sim + row * N;
+    int k = lane;
+    // eight loads and searches in flight per lane (the kernel is latency-bound otherwise)
+    for (; k + 224 < N; k += 256) {
+      float v[8];
+      int bn[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = __ldg(src + k + 32 * q);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) bn[q] = eer_bin_guess(v[q], thr, T, g_lo, g_inv);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) mine[bn[q] * 32] += 1u;
+      const int dj = j - k;
+      if (dj >= 0 && dj < 256 && (dj & 31) == 0) {
+        int b = bn[0];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) b = (dj == 32 * q) ? bn[q] : b;
+        atomicAdd(&h_own[b], 1u);
+      }
+    }
+    for (; k < N; k += 32) {
+      const int b = eer_bin_guess(__ldg(src + k), thr, T, g_lo, g_inv);
+      mine[b * 32] += 1u;
+      if (k == j) atomicAdd(&h_own[b], 1u);
+    }
+  }
+  __syncthreads();
+  // fold the private columns: thread `bin` walks its row of 32 columns starting at a different bank
+  for (int bin = threadIdx.x; bin <= T; bin += blockDim.x) {
+    unsigned long long sum = 0;
+    for (int w = 0; w < kWarps; ++w)
+      for (int i = 0; i < 32; ++i) sum += priv[((size_t)w * (T + 1) + bin) * 32 + ((i + bin) & 31)];
+    if (sum) atomicAdd(&hist_g[bin], sum);
+    if (h_own[bin]) atomicAdd(&hist_g[T + 1 + bin], (unsigned long long)h_own[bin]);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&hist_g[2 * (T + 1)], 1ull) == (unsigned long long)(gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  eer_finish(hist_g, T, accept_all, accept_own);
+}
+
+__global__ void __launch_bounds__(kEerThreads)
+threshold_counts_kernel(const float* __restrict__ sim, long long total, int N, int M, const float* __restrict__ thr_g,
+                        int T, unsigned long long* __restrict__ hist_g /* [2][T+1] + ticket */,
+                        long long* __restrict__ accept_all, long long* __restrict__ accept_own) {
+  extern __shared__ unsigned eer_smem[];
+  float* thr = reinterpret_cast<float*>(eer_smem);            // [T]
+  unsigned* h_all = eer_smem + T;                              // [T + 1]
+  unsigned* h_own = h_all + (T + 1);                           // [T + 1]
+  __shared__ bool last;
+  for (int i = threadIdx.x; i < T; i += blockDim.x) thr[i] = thr_g[i];
+  for (int i = threadIdx.x; i < 2 * (T + 1); i += blockDim.x) h_all[i] = 0u;
+  __syncthreads();
+  // one warp per row sim[j, i, :] (whole warps stay in the loops together: ballot / match need every
+  // lane, so both bounds are warp-uniform); the own-speaker entry of the row is k == j
+  const int lane = threadIdx.x & 31;
+  const long long rows = total / N;
+  const long long nwarps = (long long)gridDim.x * (kEerThreads / 32);
+  for (long long row = (long long)blockIdx.x * (kEerThreads / 32) + (threadIdx.x >> 5); row < rows; row += nwarps) {
+    const int j = (int)(row / M);
+    const float* src = sim + row * N;
+    for (int k0 = 0; k0 < N; k0 += 32) {
+      const int k = k0 + lane;
+      const bool on = k < N;
+      const float v = on ? __ldg(src + k) : 0.f;
+      const int bin = on ? eer_bin(v, thr, T) : 0;
+      eer_count(h_all, bin, on);
+      eer_count(h_own, bin, on && k == j);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * (T + 1); i += blockDim.x)
+    if (h_all[i]) atomicAdd(&hist_g[i], (unsigned long long)h_all[i]);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&hist_g[2 * (T + 1)], 1ull) == (unsigned long long)(gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  eer_finish(hist_g, T, accept_all, accept_own);
+}
+
+int simt_threshold_counts(const float* sim, int N, int M, const float* thresholds, int T, long long* accept_all,
+                          long long* accept_own, void* scratch, cudaStream_t st) {
+  if (T < 1 || T > kEerMaxT) return GE2E_ERR_UNSUPPORTED;
+  const long long total = (long long)N * M * N;
+  const size_t scratch_bytes = (size_t)(2 * (T + 1) + 1) * sizeof(unsigned long long);
+  if (cudaMemsetAsync(scratch, 0, scratch_bytes, st) != cudaSuccess) return GE2E_ERR_LAUNCH;
+  const long long rows = (long long)N * M;                     // one warp per row sim[j, i, :]
+  constexpr int kSms = 148;
+  unsigned long long* hist = reinterpret_cast<unsigned long long*>(scratch);
+  if (T <= kEerPrivT) {
+    constexpr int kWarps = kEerPrivThreads / 32;
+    const size_t smem = (size_t)(T + (T + 1) * (1 + kWarps * 32)) * sizeof(unsigned);      // <= 34 KB
+    long long blocks = (rows + kWarps - 1) / kWarps;
+    const long long cap = (long long)kSms * (T <= 50 ? 8 : 6);  // resident blocks per SM by shared memory
+    if (blocks > cap) blocks = cap;
+    threshold_counts_private_kernel<<<(unsigned)blocks, kEerPrivThreads, smem, st>>>(sim, rows, N, M, thresholds, T, hist,
+                                                                                     accept_all, accept_own);
+  } else {
+    long long blocks = (rows + kEerThreads / 32 - 1) / (kEerThreads / 32);
+    const long long cap = (long long)kSms * 8;                 // 8 resident blocks of 256 threads per SM
+    if (blocks > cap) blocks = cap;
+    const size_t smem = (size_t)(T + 2 * (T + 1)) * sizeof(unsigned);
+    threshold_counts_kernel<<<(unsigned)blocks, kEerThreads, smem, st>>>(sim, total, N, M, thresholds, T, hist, accept_all,
+                                                                         accept_own);
+  }
+  GE2E_LAUNCHED();
+  return GE2E_OK;
+}
+
 int simt_centroids(const float* E, int N, int M, int D, float* C, cudaStream_t st) {
   centroids_kernel<<<N, 128, 0, st>>>(E, M, D, C);
   GE2E_LAUNCHED();
