@@ -156,6 +156,25 @@ int ge2e_b200_bwd_finalize(const float* E, const float* dE_hat, const float* dC_
 int ge2e_b200_scale_bias_sgd(float* w, float* b, float* dw, float* db, float max_norm, float lr,
                              float* total_norm, ge2e_stream_t stream);
 
+/* Model tail feeding the loss (s2_model_GE2E_loss_speach_embed.py:28-34:
+ * `x = x[:, x.size(1) - 1]; x = self.projection(x); x = x / torch.norm(x, dim=1).unsqueeze(1)`).
+ * One tcgen05 (TF32, fp32 accumulate) kernel: E = normalise_rows(X W^T + bias).
+ *   X[U, H]      device fp32, row r at X + r * x_row_stride floats (the last-frame select of the
+ *                LSTM output [U, frames, H] is x_row_stride = frames * H with X pointing at the last
+ *                frame of row 0); H % 4 == 0, x_row_stride % 4 == 0, 16-byte aligned
+ *   W[D, H]      nn.Linear weight (row-major, contiguous), D in {64, 128, 256}
+ *   bias[D]      nullable
+ *   E[U, D]      unit rows (no epsilon, as the reference: a zero row gives NaN)
+ *   inv_norm[U]  1 / ||X W^T + bias|| per row, kept for the backward (nullable)
+ * GE2E_ERR_UNSUPPORTED for other shapes / alignments. */
+int ge2e_b200_embed_tail_fwd(const float* X, long long x_row_stride, const float* W, const float* bias, int U,
+                             int H, int D, float* E, float* inv_norm, ge2e_stream_t stream);
+/* Backward of the normalisation and the bias: dY = (dE - E (E . dE)) * inv_norm (row-wise),
+ * dbias[D] = column sums of dY (nullable; zeroed by the call).  The two gradient GEMMs of the Linear
+ * (dX = dY W, dW = dY^T X) are plain library GEMMs and stay with the caller. */
+int ge2e_b200_embed_tail_bwd_rows(const float* dE, const float* E, const float* inv_norm, int U, int D, float* dY,
+                                  float* dbias, ge2e_stream_t stream);
+
 /* EER sweep counts (s5_eval_model.py:57-89: `S_thres = S > thres`,
  * `np.sum(S_thres[i])`, `np.sum(S_thres[i, :, i])` for 50 thresholds).  One pass over the float32
  * similarity matrix sim[N, M, N] (device) for all T thresholds at once:

@@ -55,6 +55,9 @@ PROTOTYPES = {
                                              C.c_int, _f32p, _f32p, C.c_float, C.c_int, C.c_int, _f32p, _f32p,
                                              _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, _stream]),
     "ge2e_b200_scale_bias_sgd": (C.c_int, [_f32p, _f32p, _f32p, _f32p, C.c_float, C.c_float, _f32p, _stream]),
+    "ge2e_b200_embed_tail_fwd": (C.c_int, [_f32p, C.c_longlong, _f32p, _f32p, C.c_int, C.c_int, C.c_int, _f32p, _f32p,
+                                           _stream]),
+    "ge2e_b200_embed_tail_bwd_rows": (C.c_int, [_f32p, _f32p, _f32p, C.c_int, C.c_int, _f32p, _f32p, _stream]),
     "ge2e_b200_threshold_counts_scratch_bytes": (C.c_size_t, [C.c_int]),
     "ge2e_b200_threshold_counts": (C.c_int, [_f32p, C.c_int, C.c_int, _f32p, C.c_int, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_size_t, _stream]),

@@ -211,6 +211,20 @@ int ge2e_b200_bwd_finalize(const float* E, const float* dE_hat, const float* dC_
                            variant, grad_out, dE, true, stream);
 }
 
+int ge2e_b200_embed_tail_fwd(const float* X, long long x_row_stride, const float* W, const float* bias, int U,
+                             int H, int D, float* E, float* inv_norm, ge2e_stream_t stream) {
+  if (U < 1 || H < 1 || D < 1) return GE2E_ERR_SHAPE;
+  if (!X || !W || !E) return GE2E_ERR_ARGUMENT;
+  return tail_fwd(X, x_row_stride, W, bias, U, H, D, E, inv_norm, (cudaStream_t)stream);
+}
+
+int ge2e_b200_embed_tail_bwd_rows(const float* dE, const float* E, const float* inv_norm, int U, int D, float* dY,
+                                  float* dbias, ge2e_stream_t stream) {
+  if (U < 1 || D < 1) return GE2E_ERR_SHAPE;
+  if (!dE || !E || !inv_norm || !dY) return GE2E_ERR_ARGUMENT;
+  return tail_bwd_rows(dE, E, inv_norm, U, D, dY, dbias, (cudaStream_t)stream);
+}
+
 size_t ge2e_b200_threshold_counts_scratch_bytes(int T) {
   return T < 1 ? 0 : (size_t)(2 * (T + 1) + 1) * sizeof(unsigned long long);
 }

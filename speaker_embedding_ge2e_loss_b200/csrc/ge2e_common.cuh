@@ -151,6 +151,13 @@ int simt_calc_loss(const float* S, int N, int M, float eps, int variant, float* 
                    float* per_row, cudaStream_t st);
 int simt_normalize_rows(const float* X, int rows, int D, float* Y, cudaStream_t st);
 
+// ---- launchers implemented in ge2e_tail.cu (model tail: Linear + L2 normalise, tcgen05) -----
+bool tail_supported(int U, int H, int D, long long x_row_stride);
+int tail_fwd(const float* X, long long x_row_stride, const float* W, const float* bias, int U, int H, int D,
+             float* E, float* inv_norm, cudaStream_t st);
+int tail_bwd_rows(const float* dE, const float* E, const float* inv_norm, int U, int D, float* dY, float* dbias,
+                  cudaStream_t st);
+
 // ---- launchers implemented in ge2e_tc.cu (tcgen05 / TMA / TMEM path) ----------------------
 bool tc_supported(int n_local, int n_total, int M, int D, int variant);
 void tc_set_trace(unsigned long long* device_buf, int mode);

@@ -1,0 +1,292 @@
+// Model tail feeding the loss: last-frame select -> Linear(H -> D) -> L2
+// normalise, reference embedding_model_GE2E/s2_model_GE2E_loss_speach_embed.py:28-34
+//     x = x[:, x.size(1) - 1];  x = self.projection(x);  x = x / torch.norm(x, dim=1).unsqueeze(1)
+//
+// Forward, one kernel: Y[128 rows x D] = X_tile[128 x H] * W[D x H]^T on tcgen05 (kind::tf32, fp32
+// accumulation in tensor memory), K streamed in 32-column slabs through a 4-stage TMA ring (X and W are
+// both K-major, 128B swizzle -- the same operand layout as the loss's E * C^T), and an epilogue that is
+// the loss's prologue: + bias, row sum of squares, scale to unit length, rows staged through shared
+// memory and written with TMA.  The last-frame select is the row stride of the X tensor map (no copy).
+// Y never reaches HBM; what is kept for the backward is E and 1 / ||y||.
+//
+//   warp 0      TMA producer           warp 1      TMEM allocation + MMA issue (one elected lane)
+//   warps 2-5   epilogue, one thread per row of the tile (TMEM lane quarter = warp % 4)
+//
+// Backward of the normalisation (+ bias gradient) is a SIMT row kernel; the two gradient GEMMs
+// (dX = dY W, dW = dY^T X) are plain library GEMMs issued by the host layer.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "ge2e_common.cuh"
+#include "ge2e_tc_ptx.cuh"
+
+namespace ge2e {
+
+namespace {
+
+using namespace ptx;
+
+constexpr int kTailRows = 128;               // rows of X per CTA
+constexpr int kTailKc = 32;                  // K columns per ring stage (one 128-byte swizzled slab)
+constexpr int kTailStages = 4;
+constexpr int kTailABytes = kTailRows * 128;             // 16 KB
+constexpr int kTailBBytes = 256 * 128;                   // 32 KB (D <= 256 rows of W)
+constexpr int kTailStageBytes = kTailABytes + kTailBBytes;
+constexpr int kTailThreads = 192;
+constexpr int kTailEpiThreads = 128;
+constexpr int kTailSmemBytes = kTailStages * kTailStageBytes + 1024 /*alignment*/ + 2048 /*tail struct*/;
+
+struct TailShared {
+  unsigned long long full[kTailStages], empty[kTailStages], acc_full;
+  uint32_t tmem_base;
+  float bias[256];
+};
+
+struct TailParams {
+  int U, H, D;
+  const float* bias;     // nullable
+  float* inv_norm;       // [U]
+};
+
+__global__ void __launch_bounds__(kTailThreads, 1)
+embed_tail_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                      const __grid_constant__ CUtensorMap tm_e, const TailParams p) {
+  extern __shared__ uint8_t tail_raw[];
+  const uint32_t raw = smem_u32(tail_raw);
+  const uint32_t ring = (raw + 1023u) & ~1023u;                       // 1024-byte aligned (swizzle atom)
+  TailShared* sh = reinterpret_cast<TailShared*>(tail_raw + (ring - raw) + kTailStages * kTailStageBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * kTailRows;
+  const int nchunks = (p.H + kTailKc - 1) / kTailKc;
+  const int D = p.D;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tm_x);
+    prefetch_tmap(&tm_w);
+    prefetch_tmap(&tm_e);
+    for (int s = 0; s < kTailStages; ++s) {
+      mbar_init(smem_u32(&sh->full[s]), 1);
+      mbar_init(smem_u32(&sh->empty[s]), 1);
+    }
+    mbar_init(smem_u32(&sh->acc_full), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<256>(smem_u32(&sh->tmem_base));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sh->tmem_base;
+  pdl_wait();          // X comes from the stream predecessor (the LSTM)
+  pdl_trigger();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      const uint32_t bytes = static_cast<uint32_t>(kTailABytes + D * 128);
+      for (int c = 0; c < nchunks; ++c) {
+        const int s = c % kTailStages;
+        mbar_wait(smem_u32(&sh->empty[s]), ((c / kTailStages) & 1) ^ 1);
+        const uint32_t fb = smem_u32(&sh->full[s]);
+        mbar_expect_tx(fb, bytes);
+        tma_load_2d(ring + s * kTailStageBytes, &tm_x, c * kTailKc, row0, fb);
+        tma_load_2d(ring + s * kTailStageBytes + kTailABytes, &tm_w, c * kTailKc, 0, fb);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issue
+    const uint32_t idesc = idesc_tf32(kTailRows, D, 0, 0);
+    const uint64_t dk = smem_desc(0, 16, 1024, kLayoutSw128);          // K-major, 8-row groups 1024 B apart
+    bool ready = false;
+    uint32_t leader = 0;
+    for (int c = 0; c < nchunks; ++c) {
+      const int s = c % kTailStages;
+      const uint32_t ph = (c / kTailStages) & 1;
+      if (!ready) mbar_wait(smem_u32(&sh->full[s]), ph);
+      tc_fence_after();
+      const int sn = (s + 1 == kTailStages) ? 0 : s + 1;
+      const uint32_t pn = (s + 1 == kTailStages) ? (ph ^ 1) : ph;
+      uint32_t probe = 0;
+      if (elect_leader(leader)) {
+        const uint64_t da = dk | ((ring + s * kTailStageBytes) >> 4);
+        const uint64_t db = dk | ((ring + s * kTailStageBytes + kTailABytes) >> 4);
+        probe = umma_stage_ss<1, 1>(tmem, da, db, 0, 0, idesc, c != 0, smem_u32(&sh->empty[s]),
+                                    smem_u32(&sh->full[sn]), pn);
+      }
+      __syncwarp();
+      ready = (c + 1 < nchunks) && __shfl_sync(0xffffffffu, probe, leader) != 0;
+    }
+    if (elect_one()) umma_commit(smem_u32(&sh->acc_full));
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue: one thread per row
+    const int q = warp & 3;                           // TMEM lane quarter this warp may read
+    const int trow = q * 32 + lane;
+    const int et = threadIdx.x - 64;                  // 0..127
+    for (int i = et; i < 256; i += kTailEpiThreads) sh->bias[i] = (p.bias != nullptr && i < D) ? p.bias[i] : 0.f;
+    named_bar_sync(1, kTailEpiThreads);
+    mbar_wait(smem_u32(&sh->acc_full), 0);
+    tc_fence_after();
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const int nslab = D / 32;
+    float ss = 0.f;
+    for (int ch = 0; ch < nslab; ++ch) {
+      uint32_t v[32];
+      tmem_ld32(tmem + lane_addr + ch * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float y = __uint_as_float(v[i]) + sh->bias[ch * 32 + i];
+        ss = fmaf(y, y, ss);
+      }
+    }
+    // x / torch.norm(x, dim=1): no epsilon in the reference (a zero row gives NaN there and here)
+    const float inv = 1.0f / sqrtf(ss);
+    if (row0 + trow < p.U && p.inv_norm != nullptr) p.inv_norm[row0 + trow] = inv;
+    // every MMA has completed (acc_full), so the ring is free: stage E in the swizzled slab layout
+    for (int ch = 0; ch < nslab; ++ch) {
+      uint32_t v[32];
+      tmem_ld32(tmem + lane_addr + ch * 32, v);
+      tmem_ld_wait();
+      const uint32_t row_smem = ring + ch * kTailABytes + trow * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = (__uint_as_float(v[4 * c + i]) + sh->bias[ch * 32 + 4 * c + i]) * inv;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_smem + ((c ^ (trow & 7)) << 4)),
+                     "r"(__float_as_uint(o[0])), "r"(__float_as_uint(o[1])), "r"(__float_as_uint(o[2])),
+                     "r"(__float_as_uint(o[3]))
+                     : "memory");
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async_smem();
+    named_bar_sync(1, kTailEpiThreads);
+    if (et == 0) {
+      for (int ch = 0; ch < nslab; ++ch) tma_store_2d(&tm_e, ch * 32, row0, ring + ch * kTailABytes);   // clips rows >= U
+      tma_store_commit();
+      tma_store_wait_read();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem);
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 tail_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+// [rows, cols] fp32 with a row stride (floats); box = [box_rows][32 cols], 128-byte swizzle
+int tail_map(CUtensorMap* m, const float* base, long long rows, int cols, long long row_stride, int box_rows) {
+  auto enc = tail_encode();
+  if (enc == nullptr) return GE2E_ERR_LAUNCH;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(row_stride) * 4};
+  cuuint32_t box[2] = {kTailKc, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? GE2E_OK : GE2E_ERR_LAUNCH;
+}
+
+// ---- backward of  e = y / ||y||  (+ the bias gradient): one warp per row ------------------------
+//   dY = (dE - e (e . dE)) / ||y||,   dbias += column sums of dY
+constexpr int kTailBwdWarps = 8;
+__global__ void __launch_bounds__(kTailBwdWarps * 32)
+embed_tail_bwd_rows_kernel(const float* __restrict__ dE, const float* __restrict__ E,
+                           const float* __restrict__ inv_norm, int U, int D, float* __restrict__ dY,
+                           float* __restrict__ dbias) {
+  __shared__ float colsum[256];
+  pdl_wait();
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) colsum[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int per_lane = D / 32;                      // D in {64, 128, 256}: 2, 4 or 8 columns per lane
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int row = blockIdx.x * kTailBwdWarps + warp; row < U; row += gridDim.x * kTailBwdWarps) {
+    const float* g = dE + (size_t)row * D;
+    const float* e = E + (size_t)row * D;
+    float gv[8], ev[8];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < per_lane) {
+        gv[i] = __ldg(g + lane + 32 * i);
+        ev[i] = __ldg(e + lane + 32 * i);
+        dot = fmaf(gv[i], ev[i], dot);
+      }
+    dot = warp_sum(dot);
+    const float inv = __ldg(inv_norm + row);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < per_lane) {
+        const float d = (gv[i] - ev[i] * dot) * inv;
+        dY[(size_t)row * D + lane + 32 * i] = d;
+        acc[i] += d;
+      }
+  }
+  if (dbias != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < per_lane) atomicAdd(&colsum[lane + 32 * i], acc[i]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < D; i += blockDim.x) atomicAdd(dbias + i, colsum[i]);
+  }
+}
+
+}  // namespace
+
+bool tail_supported(int U, int H, int D, long long x_row_stride) {
+  return U > 0 && H > 0 && H % 4 == 0 && (D == 64 || D == 128 || D == 256) && x_row_stride >= H &&
+         x_row_stride % 4 == 0;
+}
+
+int tail_fwd(const float* X, long long x_row_stride, const float* W, const float* bias, int U, int H, int D,
+             float* E, float* inv_norm, cudaStream_t st) {
+  if (!tail_supported(U, H, D, x_row_stride)) return GE2E_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(E)) & 15)
+    return GE2E_ERR_UNSUPPORTED;
+  CUtensorMap tm_x, tm_w, tm_e;
+  int rc;
+  if ((rc = tail_map(&tm_x, X, U, H, x_row_stride, kTailRows)) != GE2E_OK) return rc;
+  if ((rc = tail_map(&tm_w, W, D, H, H, D)) != GE2E_OK) return rc;
+  if ((rc = tail_map(&tm_e, E, U, D, D, kTailRows)) != GE2E_OK) return rc;
+  static thread_local int attr_dev = -1;
+  int dev = 0;
+  GE2E_CUDA_TRY(cudaGetDevice(&dev));
+  if (attr_dev != dev) {
+    GE2E_CUDA_TRY(cudaFuncSetAttribute(embed_tail_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kTailSmemBytes));
+    attr_dev = dev;
+  }
+  TailParams p{U, H, D, bias, inv_norm};
+  const int grid = (U + kTailRows - 1) / kTailRows;
+  launch_pdl(embed_tail_fwd_kernel, dim3(grid), dim3(kTailThreads), (size_t)kTailSmemBytes, st, true, tm_x, tm_w, tm_e, p);
+  GE2E_LAUNCHED();
+  return GE2E_OK;
+}
+
+int tail_bwd_rows(const float* dE, const float* E, const float* inv_norm, int U, int D, float* dY, float* dbias,
+                  cudaStream_t st) {
+  if (U <= 0 || !(D == 64 || D == 128 || D == 256)) return GE2E_ERR_UNSUPPORTED;
+  if (dbias != nullptr) GE2E_CUDA_TRY(cudaMemsetAsync(dbias, 0, sizeof(float) * D, st));
+  int grid = (U + kTailBwdWarps - 1) / kTailBwdWarps;
+  if (grid > 148 * 4) grid = 148 * 4;
+  embed_tail_bwd_rows_kernel<<<grid, kTailBwdWarps * 32, 0, st>>>(dE, E, inv_norm, U, D, dY, dbias);
+  GE2E_LAUNCHED();
+  return GE2E_OK;
+}
+
+}  // namespace ge2e

@@ -44,7 +44,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Slow path, out of line so that the hot loops stay small.  A wait that never completes is a
 // programming error in the pipeline: trap after 2 s of wall time instead of hanging the GPU.
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   uint64_t t0 = 0;
   for (uint32_t spins = 0;; ++spins) {
     if (mbar_try_wait(bar, parity)) return;
