@@ -180,7 +180,81 @@ class ShardedGE2EPlan:
         return g
 
 
-class GE2EHostFeed:
+class _HostFeed:
+    """Slot machinery shared by the host-fed plans: ``depth`` device buffers, one CUDA graph per slot
+    holding that slot's whole step plus the device->host read of its result, a copy stream for the
+    H2D transfers and a compute stream for the graphs."""
+
+    def _setup(self, shape, depth, device, make_plan, result_of):
+        self.device = torch.device(device if device is not None else "cuda")
+        self.shape, self.depth = tuple(shape), depth
+        dev = self.device
+        self.plans = [make_plan() for _ in range(depth)]
+        self.bufs = [torch.empty(self.shape, dtype=torch.float32, device=dev) for _ in range(depth)]
+        self.results = [torch.zeros(3, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.compute_stream = torch.cuda.Stream(device=dev)
+        self._copied = [torch.cuda.Event() for _ in range(depth)]
+        self._done = [torch.cuda.Event() for _ in range(depth)]
+        self._used = [False] * depth
+        self._k = 0
+        self._graphs = []
+        with torch.cuda.device(dev):
+            for i in range(depth):
+                p, buf, res = self.plans[i], self.bufs[i], self.results[i]
+                buf.normal_()
+                torch.cuda.synchronize()
+                with torch.cuda.stream(self.compute_stream):
+                    for _ in range(2):
+                        p.step(buf, self.w, self.b)         # warm-up outside capture (communicators, lazy attributes)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                before = lib().ge2e_b200_launch_count()
+                with torch.cuda.graph(g, stream=self.compute_stream):
+                    p.step(buf, self.w, self.b)
+                    for dst, src in result_of(p, res):
+                        dst.copy_(src, non_blocking=True)
+                self.launches_per_step = lib().ge2e_b200_launch_count() - before
+                self._graphs.append(g)
+
+    def submit(self, E_host: torch.Tensor) -> int:
+        n = 1
+        for d in self.shape:
+            n *= d
+        if not (E_host.dtype == torch.float32 and E_host.is_contiguous() and E_host.numel() == n):
+            raise ValueError(f"submit: expected a contiguous fp32 batch of {n} values")
+        if E_host.device.type == "cpu" and not E_host.is_pinned():
+            raise ValueError("submit: the host batch must be in pinned memory (an unpinned copy is synchronous)")
+        i = self._k % self.depth
+        self._k += 1
+        cs, ms = self.copy_stream, self.compute_stream
+        if self._used[i]:
+            cs.wait_event(self._done[i])                 # slot's previous step has consumed its buffer
+        with torch.cuda.stream(cs):
+            self.bufs[i].copy_(E_host.view(self.shape), non_blocking=True)
+            self._copied[i].record(cs)
+        ms.wait_event(self._copied[i])
+        with torch.cuda.stream(ms):
+            self._graphs[i].replay()
+            self._done[i].record(ms)
+        self._used[i] = True
+        return i
+
+    def result(self, ticket: int):
+        """(loss, dw, db) of the slot as Python floats; blocks until that slot's step has finished."""
+        self._done[ticket].synchronize()
+        r = self.results[ticket]
+        return float(r[0]), float(r[1]), float(r[2])
+
+    def dE(self, ticket: int) -> torch.Tensor:
+        """Device gradient of the slot's batch (valid for work queued after ``done_event(ticket)``)."""
+        return self.plans[ticket].dE
+
+    def done_event(self, ticket: int) -> torch.cuda.Event:
+        return self._done[ticket]
+
+
+class GE2EHostFeed(_HostFeed):
     """fwd+bwd over HOST-resident batches, pipelined: the H2D copy of batch k+1 (copy stream) runs
     under the fwd+bwd of batch k (compute stream), and every slot's step -- the four stages plus the
     device->host read of {loss, dw, db} into the slot's pinned result -- is one CUDA graph, so a
@@ -198,67 +272,26 @@ class GE2EHostFeed:
 
     def __init__(self, N: int, M: int, D: int, w: torch.Tensor, b: torch.Tensor, variant: str = "softmax",
                  precision: str = "fp32", eps: float = 1e-6, device=None, depth: int = 2):
-        self.device = torch.device(device if device is not None else "cuda")
-        self.N, self.M, self.D, self.depth = N, M, D, depth
+        self.N, self.M, self.D = N, M, D
         self.w, self.b = w, b
-        dev = self.device
-        self.plans = [GE2EPlan(N, M, D, variant, precision, eps, device=dev) for _ in range(depth)]
-        self.bufs = [torch.empty((N, M, D), dtype=torch.float32, device=dev) for _ in range(depth)]
-        self.results = [torch.zeros(3, dtype=torch.float32).pin_memory() for _ in range(depth)]
-        self.copy_stream = torch.cuda.Stream(device=dev)
-        self.compute_stream = torch.cuda.Stream(device=dev)
-        self._copied = [torch.cuda.Event() for _ in range(depth)]
-        self._done = [torch.cuda.Event() for _ in range(depth)]
-        self._used = [False] * depth
-        self._k = 0
-        self._graphs = []
-        with torch.cuda.device(dev):
-            for i in range(depth):
-                p, buf, res = self.plans[i], self.bufs[i], self.results[i]
-                buf.zero_()
-                torch.cuda.synchronize()
-                with torch.cuda.stream(self.compute_stream):
-                    p.step(buf, w, b)                       # warm-up outside capture
-                torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                before = lib().ge2e_b200_launch_count()
-                with torch.cuda.graph(g, stream=self.compute_stream):
-                    p.step(buf, w, b)
-                    res[0:1].copy_(p.loss.reshape(1), non_blocking=True)
-                    res[1:3].copy_(p._scratch[N * D:N * D + 2], non_blocking=True)
-                self.launches_per_step = lib().ge2e_b200_launch_count() - before
-                self._graphs.append(g)
+        dev = torch.device(device if device is not None else "cuda")
+        self._setup((N, M, D), depth, dev, lambda: GE2EPlan(N, M, D, variant, precision, eps, device=dev),
+                    lambda p, res: [(res[0:1], p.loss.reshape(1)), (res[1:3], p._scratch[N * D:N * D + 2])])
         self.path = self.plans[0].path
 
-    def submit(self, E_host: torch.Tensor) -> int:
-        if not (E_host.dtype == torch.float32 and E_host.is_contiguous() and E_host.numel() == self.N * self.M * self.D):
-            raise ValueError("GE2EHostFeed.submit: expected a contiguous fp32 batch of N*M*D values")
-        if E_host.device.type == "cpu" and not E_host.is_pinned():
-            raise ValueError("GE2EHostFeed.submit: the host batch must be in pinned memory (an unpinned copy is synchronous)")
-        i = self._k % self.depth
-        self._k += 1
-        cs, ms = self.copy_stream, self.compute_stream
-        if self._used[i]:
-            cs.wait_event(self._done[i])                 # slot's previous step has consumed its buffer
-        with torch.cuda.stream(cs):
-            self.bufs[i].copy_(E_host.view(self.N, self.M, self.D), non_blocking=True)
-            self._copied[i].record(cs)
-        ms.wait_event(self._copied[i])
-        with torch.cuda.stream(ms):
-            self._graphs[i].replay()
-            self._done[i].record(ms)
-        self._used[i] = True
-        return i
 
-    def result(self, ticket: int):
-        """(loss, dw, db) of the slot as Python floats; blocks until that slot's step has finished."""
-        self._done[ticket].synchronize()
-        r = self.results[ticket]
-        return float(r[0]), float(r[1]), float(r[2])
+class ShardedGE2EHostFeed(_HostFeed):
+    """``GE2EHostFeed`` for the speaker-sharded step (one process per GPU): every rank submits ITS shard
+    [n_local, M, D] from pinned host memory; a slot's graph holds the four stages, the three NCCL
+    collectives and the read-back of the global {loss, dw, db}.  Both slots' graphs run on the one
+    compute stream, so the communicator sees its collectives in the same order on every rank as long as
+    all ranks submit in lockstep (same number of submits, as a data-parallel loop does)."""
 
-    def dE(self, ticket: int) -> torch.Tensor:
-        """Device gradient of the slot's batch (valid once work queued after ``_done[ticket]``)."""
-        return self.plans[ticket].dE
-
-    def done_event(self, ticket: int) -> torch.cuda.Event:
-        return self._done[ticket]
+    def __init__(self, n_local: int, n_total: int, spk_offset: int, M: int, D: int, w: torch.Tensor, b: torch.Tensor,
+                 variant: str = "softmax", precision: str = "tf32", eps: float = 1e-6, group=None, device=None,
+                 depth: int = 2):
+        self.w, self.b = w, b
+        dev = torch.device(device if device is not None else "cuda")
+        self._setup((n_local, M, D), depth, dev,
+                    lambda: ShardedGE2EPlan(n_local, n_total, spk_offset, M, D, variant, precision, eps, group, dev),
+                    lambda p, res: [(res, p.red[0:3])])
