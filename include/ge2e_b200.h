@@ -156,6 +156,18 @@ int ge2e_b200_bwd_finalize(const float* E, const float* dE_hat, const float* dC_
 int ge2e_b200_scale_bias_sgd(float* w, float* b, float* dw, float* db, float max_norm, float lr,
                              float* total_norm, ge2e_stream_t stream);
 
+/* Batch assembly from a device-resident spectrogram bank (SURVEY 8(f) row 4;
+ * s1_dataset_loader.py:59-77 `spr_utters[utter_idx][:, clip:clip + L, :]`, the DataLoader's collate,
+ * and s4_train_embed_model.py:176-186 reshape + `mel_db_batch[perm]`): a cropped utterance is one
+ * contiguous span of its speaker's [utts, frames, mels] array, so the model's input batch is
+ *   out[r, 0:span] = bank[src_off[r] : src_off[r] + span],  r = 0 .. rows-1   (span = L * mels)
+ * with src_off[rows] (device, int64, element offsets) computed by the host from the drawn utterance
+ * indices, crop start and row permutation.  offsets_aligned != 0 promises that every offset is a
+ * multiple of 4 floats (16-byte vector path when span % 4 == 0 as well); 0 selects the scalar kernel.
+ * fp32 in, fp32 out, bit-exact copy. */
+int ge2e_b200_gather_spans(const float* bank, const long long* src_off, int rows, long long span, int offsets_aligned,
+                           float* out, ge2e_stream_t stream);
+
 /* Model tail feeding the loss (s2_model_GE2E_loss_speach_embed.py:28-34:
  * `x = x[:, x.size(1) - 1]; x = self.projection(x); x = x / torch.norm(x, dim=1).unsqueeze(1)`).
  * One tcgen05 (TF32, fp32 accumulate) kernel: E = normalise_rows(X W^T + bias).

@@ -55,6 +55,7 @@ PROTOTYPES = {
                                              C.c_int, _f32p, _f32p, C.c_float, C.c_int, C.c_int, _f32p, _f32p,
                                              _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, _stream]),
     "ge2e_b200_scale_bias_sgd": (C.c_int, [_f32p, _f32p, _f32p, _f32p, C.c_float, C.c_float, _f32p, _stream]),
+    "ge2e_b200_gather_spans": (C.c_int, [_f32p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, _f32p, _stream]),
     "ge2e_b200_embed_tail_fwd": (C.c_int, [_f32p, C.c_longlong, _f32p, _f32p, C.c_int, C.c_int, C.c_int, _f32p, _f32p,
                                            _stream]),
     "ge2e_b200_embed_tail_bwd_rows": (C.c_int, [_f32p, _f32p, _f32p, C.c_int, C.c_int, _f32p, _f32p, _stream]),

@@ -211,6 +211,15 @@ int ge2e_b200_bwd_finalize(const float* E, const float* dE_hat, const float* dC_
                            variant, grad_out, dE, true, stream);
 }
 
+int ge2e_b200_gather_spans(const float* bank, const long long* src_off, int rows, long long span, int offsets_aligned,
+                           float* out, ge2e_stream_t stream) {
+  if (rows < 1 || span < 1) return GE2E_ERR_SHAPE;
+  if (!bank || !src_off || !out) return GE2E_ERR_ARGUMENT;
+  const bool vec = offsets_aligned != 0 && span % 4 == 0 &&
+                   ((reinterpret_cast<uintptr_t>(bank) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  return simt_gather_spans(bank, src_off, rows, span, vec, out, (cudaStream_t)stream);
+}
+
 int ge2e_b200_embed_tail_fwd(const float* X, long long x_row_stride, const float* W, const float* bias, int U,
                              int H, int D, float* E, float* inv_norm, ge2e_stream_t stream) {
   if (U < 1 || H < 1 || D < 1) return GE2E_ERR_SHAPE;

@@ -145,6 +145,8 @@ int simt_scale_bias_sgd(float* w, float* b, float* dw, float* db, float max_norm
                         bool pdl, cudaStream_t st);
 int simt_threshold_counts(const float* sim, int N, int M, const float* thresholds, int T, long long* accept_all,
                           long long* accept_own, void* scratch, cudaStream_t st);
+int simt_gather_spans(const float* bank, const long long* src_off, int rows, long long span, bool vec_ok, float* out,
+                      cudaStream_t st);
 int simt_centroids(const float* E, int N, int M, int D, float* C, cudaStream_t st);
 int simt_utterance_centroids(const float* E, int N, int M, int D, float* Uc, cudaStream_t st);
 int simt_calc_loss(const float* S, int N, int M, float eps, int variant, float* loss,

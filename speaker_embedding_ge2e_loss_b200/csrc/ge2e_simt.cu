@@ -1604,6 +1604,59 @@ int simt_threshold_counts(const float* sim, int N, int M, const float* threshold
   return GE2E_OK;
 }
 
+// ---- batch assembly from a device-resident spectrogram bank (s1_dataset_loader.py:59-77) -------
+// A cropped utterance [crop_len, mels] is ONE contiguous span of the speaker's [utts, frames, mels]
+// array, so assembling the model's input batch (collate + reshape + the trainer's row permutation,
+// s4:176-186) is `rows` contiguous copies: out[r, :] = bank[src_off[r] : src_off[r] + span].
+// Pure HBM copy work: a block copies one chunk of one span, 16-byte vectors, four loads in flight per
+// thread; spans or offsets that are not 16-byte multiples take the scalar kernel.
+constexpr int kGatherThreads = 256;
+constexpr int kGatherChunk = kGatherThreads * 4 * 4;          // floats per block: 4 float4 per thread
+
+__global__ void __launch_bounds__(kGatherThreads)
+gather_spans_vec_kernel(const float* __restrict__ bank, const long long* __restrict__ src_off, long long span,
+                        int chunks, float* __restrict__ out) {
+  const int row = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+  const long long off = __ldg(src_off + row);
+  const float4* src = reinterpret_cast<const float4*>(bank + off);
+  float4* dst = reinterpret_cast<float4*>(out + (long long)row * span);
+  const long long n4 = span >> 2;
+  const long long base = (long long)chunk * (kGatherChunk / 4) + threadIdx.x;
+  float4 v[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const long long i = base + (long long)q * kGatherThreads;
+    if (i < n4) v[q] = __ldcs(src + i);                        // read once: do not keep the bank in L2
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const long long i = base + (long long)q * kGatherThreads;
+    if (i < n4) dst[i] = v[q];
+  }
+}
+
+__global__ void __launch_bounds__(kGatherThreads)
+gather_spans_scalar_kernel(const float* __restrict__ bank, const long long* __restrict__ src_off, long long span,
+                           int chunks, float* __restrict__ out) {
+  const int row = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+  const float* src = bank + __ldg(src_off + row);
+  float* dst = out + (long long)row * span;
+  const long long lo = (long long)chunk * kGatherChunk;
+  const long long hi = lo + kGatherChunk < span ? lo + kGatherChunk : span;
+  for (long long i = lo + threadIdx.x; i < hi; i += kGatherThreads) dst[i] = __ldg(src + i);
+}
+
+int simt_gather_spans(const float* bank, const long long* src_off, int rows, long long span, bool vec_ok, float* out,
+                      cudaStream_t st) {
+  const long long chunks = (span + kGatherChunk - 1) / kGatherChunk;
+  const long long blocks = chunks * rows;
+  if (blocks > 0x7fffffffLL) return GE2E_ERR_UNSUPPORTED;
+  if (vec_ok) gather_spans_vec_kernel<<<(unsigned)blocks, kGatherThreads, 0, st>>>(bank, src_off, span, (int)chunks, out);
+  else gather_spans_scalar_kernel<<<(unsigned)blocks, kGatherThreads, 0, st>>>(bank, src_off, span, (int)chunks, out);
+  GE2E_LAUNCHED();
+  return GE2E_OK;
+}
+
 int simt_centroids(const float* E, int N, int M, int D, float* C, cudaStream_t st) {
   centroids_kernel<<<N, 128, 0, st>>>(E, M, D, C);
   GE2E_LAUNCHED();
