@@ -479,7 +479,7 @@ def run_ours(args):
         roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak, "traffic": ncu_traffic(dom) if wl == "cfg3" else None, "peak_source": peak_note,
                     "traffic_note": "DRAM bytes per launch from the committed ncu --set full capture (cold L2), "
-                                    "profiles/r1_ncu_v5_tc_kernels.txt; operands are L2-resident in situ",
+                                    "profiles/r1_ncu_v6_tc_kernels.txt; operands are L2-resident in situ",
                     "kernel_us": insitu[dom], "kernel_us_how": "in situ: step - step without the kernel (CUDA events, "
                     "rotating inputs > L2)", "algorithmic_flops": flops,
                     "note": "algorithmic flops only: the S recomputation inside the backward (another 4 U N D) is not credited",
