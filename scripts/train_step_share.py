@@ -107,11 +107,12 @@ def loss_alone(crit, steps=50, warmup=10):
     return ev[0].elapsed_time(ev[1]) / steps
 
 
-print(f"N={N} M={M}  embedder: LSTM {MEL}->{HID}x{LAYERS} -> Linear {EMB}, {T} frames")
-for name, make in (("this repo, fp32", lambda: GE2ELoss(None, device=dev)),
-                   ("this repo, tf32", lambda: GE2ELoss(None, device=dev, precision="tf32")),
-                   ("eager PyTorch  ", EagerGE2E)):
-    t_step = timed(make())
-    t_loss = loss_alone(make())
-    print(f"  {name}: step {t_step:8.3f} ms   loss fwd+bwd alone {t_loss * 1e3:8.1f} us   share {t_loss / t_step * 100:5.2f} %")
-print(f"  null loss      : step {timed(NullLoss()):8.3f} ms")
+if __name__ == "__main__":
+    print(f"N={N} M={M}  embedder: LSTM {MEL}->{HID}x{LAYERS} -> Linear {EMB}, {T} frames")
+    for name, make in (("this repo, fp32", lambda: GE2ELoss(None, device=dev)),
+                       ("this repo, tf32", lambda: GE2ELoss(None, device=dev, precision="tf32")),
+                       ("eager PyTorch  ", EagerGE2E)):
+        t_step = timed(make())
+        t_loss = loss_alone(make())
+        print(f"  {name}: step {t_step:8.3f} ms   loss fwd+bwd alone {t_loss * 1e3:8.1f} us   share {t_loss / t_step * 100:5.2f} %")
+    print(f"  null loss      : step {timed(NullLoss()):8.3f} ms")
