@@ -16,6 +16,7 @@
 //   contrast_bwd     the contrast gradient has two non-zeros per row: gather/scatter kernel
 //   finalize_kernel  one CTA per speaker: diagonal term, normalisation Jacobians, fan-out
 #include <limits.h>
+#include <stdlib.h>
 
 #include <initializer_list>
 
@@ -1228,7 +1229,7 @@ template <int MODE, int VARIANT>
 int dispatch_strip(const StripParams& p, int splits, cudaStream_t st) {
   const int D = p.D;
   if (D <= 128) return launch_strip<MODE, VARIANT, 1, 4>(p, splits, st);
-  if (D <= 256) return launch_strip<MODE, VARIANT, 2, 4>(p, splits, st);
+  if (D <= 256) return launch_strip<MODE, VARIANT, 2, 4>(p, splits, st);   // R = 8 was tried: 1.65 ms vs 1.40 ms at cfg3
   if (D <= 512) return launch_strip<MODE, VARIANT, 4, 2>(p, splits, st);
   if (D <= 1024) return launch_strip<MODE, VARIANT, 8, 1>(p, splits, st);
   return GE2E_ERR_UNSUPPORTED;
