@@ -134,6 +134,7 @@ class ShardedGE2EPlan:
         self._ws = torch.zeros(max(nbytes, 1), dtype=torch.uint8, device=dev)
         self._ws_bytes = nbytes
         self.loss, self.dw, self.db = self.red[0], self.red[1], self.red[2]
+        self._side = torch.cuda.Stream(device=dev)
 
     def step(self, E_local: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> None:
         h, dist = lib(), self.dist
@@ -155,11 +156,18 @@ class ShardedGE2EPlan:
                                    self.grad_out.data_ptr(), self.dE_hat.data_ptr(), self.dC_partial.data_ptr(),
                                    self.red.data_ptr() + 4, ws, self._ws_bytes, s), "ge2e_b200_bwd_rows")
         dist.reduce_scatter_tensor(self.dC_local, self.dC_partial, op=dist.ReduceOp.SUM, group=self.group)
-        dist.all_reduce(self.red, op=dist.ReduceOp.SUM, group=self.group)
+        # {loss, dw, db} are not inputs of finalize: their all-reduce runs beside it (fork / join on a side
+        # stream; inside a capture this becomes a parallel branch of the graph)
+        cur = torch.cuda.current_stream(self.device)
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            dist.all_reduce(self.red, op=dist.ReduceOp.SUM, group=self.group)
+        s = cur.cuda_stream
         check(h.ge2e_b200_bwd_finalize(E_local.data_ptr(), self.dE_hat.data_ptr(), self.dC_local.data_ptr(),
                                        self.cos_diag.data_ptr(), self.row_stat.data_ptr(), self.row_aux.data_ptr(), nl,
                                        M, D, w.data_ptr(), b.data_ptr(), self.eps, self.variant,
                                        self.grad_out.data_ptr(), self.dE.data_ptr(), s), "ge2e_b200_bwd_finalize")
+        cur.wait_stream(self._side)
 
     def capture(self, E_local, w: torch.Tensor, b: torch.Tensor, steps: int = 1):
         """``steps`` consecutive sharded steps in one CUDA graph (NCCL collectives included).
