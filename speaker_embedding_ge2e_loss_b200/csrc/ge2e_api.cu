@@ -305,6 +305,65 @@ int ge2e_b200_backward(const float* E, const float* e_hat, const float* c_hat, c
                                     workspace_bytes, stream);
 }
 
+// ---- whole step in one call ---------------------------------------------------------------
+// 0 = never (A/B timing), 1 = where it is faster than the pipeline (default), 2 = every supported shape
+// (tests).  Initial value: env GE2E_SMALL_STEP, else 1.
+static std::atomic<int> g_small_mode{-1};
+static int small_step_mode() {
+  int m = g_small_mode.load(std::memory_order_relaxed);
+  if (m < 0) {
+    const char* e = getenv("GE2E_SMALL_STEP");
+    m = e ? atoi(e) : 1;
+    if (m < 0 || m > 2) m = 1;
+    g_small_mode.store(m, std::memory_order_relaxed);
+  }
+  return m;
+}
+void ge2e_b200_debug_small_step(int mode) { g_small_mode.store(mode < 0 || mode > 2 ? 1 : mode, std::memory_order_relaxed); }
+
+static bool use_small_step(int N, int M, int D, int variant, int precision) {
+  const int mode = small_step_mode();
+  if (mode == 0 || !(mode == 2 ? small_step_supported(N, M, D) : small_step_preferred(N, M, D))) return false;
+  return !(precision == GE2E_TF32 && tc_supported(N, N, M, D, variant));   // the tensor-core path keeps its shapes
+}
+
+size_t ge2e_b200_step_workspace_bytes(int N, int M, int D, int variant, int precision) {
+  const size_t base = ge2e_b200_workspace_bytes(N, N, M, D, variant, precision);
+  const size_t small = use_small_step(N, M, D, variant, precision) ? small_step_workspace_bytes(N, M, D) : 0;
+  return base > small ? base : small;
+}
+
+int ge2e_b200_step_launches(int N, int M, int D, int variant, int precision) {
+  if (check_enum(variant, precision) != GE2E_OK) return GE2E_ERR_ARGUMENT;
+  return use_small_step(N, M, D, variant, precision) ? 1 : 0;
+}
+
+int ge2e_b200_forward_backward(const float* E, const int32_t* row_index, int N, int M, int D, const float* w,
+                               const float* b, float eps, int variant, int precision, const float* grad_out,
+                               float* e_hat, float* c_hat, float* cos_diag, float* row_stat, int32_t* row_kstar,
+                               float* row_aux, float* accum, float* dE_hat, float* dC_hat, float* dwdb_accum,
+                               float* dE, void* workspace, size_t workspace_bytes, ge2e_stream_t stream) {
+  if (!E || !w || !b || !grad_out || !e_hat || !c_hat || !cos_diag || !row_stat || !row_aux || !accum || !dE_hat ||
+      !dC_hat || !dwdb_accum || !dE)
+    return GE2E_ERR_ARGUMENT;
+  int rc = check_shape(N, N, 0, M, D);
+  if (rc != GE2E_OK) return rc;
+  if ((rc = check_enum(variant, precision)) != GE2E_OK) return rc;
+  if (use_small_step(N, M, D, variant, precision) && debug_skip_mask() == 0) {
+    if (!workspace || workspace_bytes < small_step_workspace_bytes(N, M, D)) return GE2E_ERR_WORKSPACE;
+    if (variant == GE2E_CONTRAST && !row_kstar) return GE2E_ERR_ARGUMENT;
+    return simt_small_step(E, row_index, N, M, D, w, b, eps, variant, grad_out, e_hat, c_hat, cos_diag, row_stat,
+                           row_kstar, row_aux, nullptr, accum, dE_hat, dC_hat, dwdb_accum + 1, dE, workspace,
+                           (cudaStream_t)stream);
+  }
+  rc = ge2e_b200_forward_indexed(E, row_index, N, M, D, w, b, eps, variant, precision, e_hat, c_hat, cos_diag,
+                                 row_stat, row_kstar, row_aux, accum, workspace, workspace_bytes, stream);
+  if (rc != GE2E_OK) return rc;
+  return ge2e_b200_backward_indexed(E, row_index, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, N, M, D, w, b,
+                                    eps, variant, precision, grad_out, dE_hat, dC_hat, dwdb_accum, dE, workspace,
+                                    workspace_bytes, stream);
+}
+
 int ge2e_b200_centroids(const float* E, int N, int M, int D, float* C, ge2e_stream_t stream) {
   if (!E || !C) return GE2E_ERR_ARGUMENT;
   if (N <= 0 || M <= 0 || D <= 0) return GE2E_ERR_SHAPE;

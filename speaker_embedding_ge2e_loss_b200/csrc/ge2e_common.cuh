@@ -141,6 +141,14 @@ int simt_bwd_finalize(const float* E, const int32_t* row_index, const float* dE_
                       int n_local, int M, int D,
                       const float* w, const float* b, float eps, int variant,
                       const float* grad_out, float* dE, bool pdl, cudaStream_t st);
+// fused single-kernel fwd+bwd step for small batches (ge2e_simt.cu)
+bool small_step_supported(int N, int M, int D);
+bool small_step_preferred(int N, int M, int D);   // supported AND faster than the pipeline
+size_t small_step_workspace_bytes(int N, int M, int D);
+int simt_small_step(const float* E, const int32_t* row_index, int N, int M, int D, const float* w, const float* b,
+                    float eps, int variant, const float* grad_out, float* e_hat, float* c_hat, float* cos_diag,
+                    float* row_stat, int32_t* row_kstar, float* row_aux, float* per_row, float* loss_accum,
+                    float* dE_hat, float* dC_hat, float* dwdb, float* dE, void* workspace, cudaStream_t st);
 int simt_scale_bias_sgd(float* w, float* b, float* dw, float* db, float max_norm, float lr, float* total_norm,
                         bool pdl, cudaStream_t st);
 int simt_threshold_counts(const float* sim, int N, int M, const float* thresholds, int T, long long* accept_all,

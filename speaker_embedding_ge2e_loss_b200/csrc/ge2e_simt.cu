@@ -45,6 +45,20 @@ __device__ __forceinline__ float4 ld4(const float* __restrict__ row, int col, in
   return v;
 }
 
+// same without the read-only path: for data written earlier in the same kernel
+__device__ __forceinline__ float4 ld4_plain(const float* row, int col, int D, bool vec) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (vec) {
+    if (col < D) v = *reinterpret_cast<const float4*>(row + col);
+  } else {
+    if (col + 0 < D) v.x = row[col + 0];
+    if (col + 1 < D) v.y = row[col + 1];
+    if (col + 2 < D) v.z = row[col + 2];
+    if (col + 3 < D) v.w = row[col + 3];
+  }
+  return v;
+}
+
 __device__ __forceinline__ void st4(float* __restrict__ row, int col, int D, bool vec, float4 v) {
   if (vec) {
     if (col < D) *reinterpret_cast<float4*>(row + col) = v;
@@ -74,20 +88,19 @@ __device__ __forceinline__ bool is_vec(const void* p, int D) {
 // ------------------------------------------------------------------------------------------
 // K1: prep.  grid = n_local, block = 256, dynamic smem = (M + 1) * Dp floats.
 // ------------------------------------------------------------------------------------------
+// Body shared by prep_kernel and the fused small-batch kernel: speaker j, block of kThreads threads,
+// `smem` = (M + 1) * Dp floats.
 template <bool ROUND>
-__global__ void __launch_bounds__(kThreads)
-prep_kernel(const float* __restrict__ E, const int32_t* __restrict__ idx, int M, int D, int Dp,
-            float* __restrict__ e_hat, float* __restrict__ c_hat, float* __restrict__ cos_diag,
-            float* __restrict__ accum) {
-  extern __shared__ __align__(16) float smem[];
+__device__ __forceinline__ void prep_body(const float* __restrict__ E, const int32_t* __restrict__ idx, int j, int M,
+                                          int D, int Dp, float* __restrict__ e_hat, float* __restrict__ c_hat,
+                                          float* __restrict__ cos_diag, float* smem) {
   __shared__ float red[kWarps];
   __shared__ float s_inv_nc;
   float* sE = smem;                    // [M][Dp]
   float* sS = smem + (size_t)M * Dp;   // [Dp] column sums
-  const int j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const bool vec_in = is_vec(E, D);
   const bool vec_out = is_vec(e_hat, D);
-  if (j == 0 && tid < 4 && accum != nullptr) accum[tid] = 0.f;
 
   for (int v = tid; v < M * (Dp >> 2); v += kThreads) {
     const int i = v / (Dp >> 2), col = (v % (Dp >> 2)) << 2;
@@ -142,6 +155,16 @@ prep_kernel(const float* __restrict__ E, const int32_t* __restrict__ idx, int M,
     if (ROUND) c = round_tf32(c);
     c_hat[(size_t)j * D + d] = c;
   }
+}
+
+template <bool ROUND>
+__global__ void __launch_bounds__(kThreads)
+prep_kernel(const float* __restrict__ E, const int32_t* __restrict__ idx, int M, int D, int Dp,
+            float* __restrict__ e_hat, float* __restrict__ c_hat, float* __restrict__ cos_diag,
+            float* __restrict__ accum) {
+  extern __shared__ __align__(16) float smem[];
+  if (blockIdx.x == 0 && threadIdx.x < 4 && accum != nullptr) accum[threadIdx.x] = 0.f;
+  prep_body<ROUND>(E, idx, blockIdx.x, M, D, Dp, e_hat, c_hat, cos_diag, smem);
 }
 
 
@@ -661,21 +684,21 @@ contrast_bwd_kernel(const float* __restrict__ e_hat, const float* __restrict__ c
 // ------------------------------------------------------------------------------------------
 // K4: finalize.  grid = n_local, block = 256, dynamic smem = (2*M + 2) * Dp floats.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
-finalize_kernel(const float* __restrict__ E, const float* __restrict__ dE_hat,
-                const float* __restrict__ dC_hat, const float* __restrict__ cos_diag,
-                const float* __restrict__ row_stat, const float* __restrict__ row_aux, int M, int D, int Dp,
-                const float* __restrict__ wp, const float* __restrict__ bp, float eps, int variant,
-                const float* __restrict__ gp, float* __restrict__ dE, const int32_t* __restrict__ idx) {
-  extern __shared__ __align__(16) float smem[];
+// Body shared by finalize_kernel and the fused small-batch kernel: speaker j, block of kThreads
+// threads, `smem` = (2 M + 2) * Dp floats.  dE_hat / dC_hat are read with plain loads (the fused
+// kernel reads what its own block has just written).
+__device__ __forceinline__ void finalize_body(const float* __restrict__ E, const float* dE_hat, const float* dC_hat,
+                                              const float* cos_diag, const float* row_stat, const float* row_aux,
+                                              int j, int M, int D, int Dp, float w, float b, float g, float eps,
+                                              int variant, float* __restrict__ dE, const int32_t* __restrict__ idx,
+                                              float* smem) {
   __shared__ float red[kWarps];
   __shared__ float s_bc[2];
   float* sE = smem;                          // [M][Dp] raw embeddings -> later de (gradient through e_hat)
   float* sU = sE + (size_t)M * Dp;           // [M][Dp] du rows
   float* sS = sU + (size_t)M * Dp;           // [Dp] column sums of E, later sum_i du
   float* sB = sS + Dp;                       // [Dp] dc_j / M
-  const int j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const float w = __ldg(wp), b = __ldg(bp), g = __ldg(gp);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const bool vec_e = is_vec(E, D), vec_g = is_vec(dE_hat, D), vec_o = is_vec(dE, D);
 
   for (int v = tid; v < M * (Dp >> 2); v += kThreads) {
@@ -698,7 +721,7 @@ finalize_kernel(const float* __restrict__ E, const float* __restrict__ dE_hat,
     for (int d = tid; d < D; d += kThreads) {
       const float c = sS[d] / fm;
       n2 = fmaf(c, c, n2);
-      pr = fmaf(c, __ldg(dC_hat + (size_t)j * D + d), pr);
+      pr = fmaf(c, dC_hat[(size_t)j * D + d], pr);
     }
     const float n2t = block_sum(n2, red);
     const float prt = block_sum(pr, red);
@@ -711,7 +734,7 @@ finalize_kernel(const float* __restrict__ E, const float* __restrict__ dE_hat,
     for (int d = tid; d < Dp; d += kThreads) {
       float v = 0.f;
       if (d < D) {
-        const float dch = __ldg(dC_hat + (size_t)j * D + d);
+        const float dch = dC_hat[(size_t)j * D + d];
         const float ch = (sS[d] / fm) * inv;
         v = (ok ? (dch - ch * proj) * inv : dch * inv) / fm;
       }
@@ -728,7 +751,7 @@ finalize_kernel(const float* __restrict__ E, const float* __restrict__ dE_hat,
     for (int d = lane << 2; d < Dp; d += 128) {
       const float4 e = *reinterpret_cast<const float4*>(&sE[(size_t)i * Dp + d]);
       const float4 s = *reinterpret_cast<const float4*>(&sS[d]);
-      const float4 gv = ld4(gh, d, D, vec_g);
+      const float4 gv = ld4_plain(gh, d, D, vec_g);
       float4 u;
       u.x = (s.x - e.x) / m1; u.y = (s.y - e.y) / m1; u.z = (s.z - e.z) / m1; u.w = (s.w - e.w) / m1;
       ne2 += dot4(e, e); nu2 += dot4(u, u); eu += dot4(e, u); eg += dot4(e, gv);
@@ -739,10 +762,10 @@ finalize_kernel(const float* __restrict__ E, const float* __restrict__ dE_hat,
     const float inv_ne = 1.f / fmaxf(ne, kCosDelta), inv_nu = 1.f / fmaxf(nu, kCosDelta);
     const float cdv = eu * inv_ne * inv_nu;       // e_hat . u_hat (== cos_diag)
     // diagonal element of w*G
-    const float Sd = fmaf(w, __ldg(cos_diag + r) + eps, b);
+    const float Sd = fmaf(w, cos_diag[r] + eps, b);
     float Gd;
     if (variant == GE2E_SOFTMAX) {
-      Gd = -g * __ldg(row_aux + r);                 // g (p_jj - 1), accumulated off-diagonal in fwd
+      Gd = -g * row_aux[r];                 // g (p_jj - 1), accumulated off-diagonal in fwd
     } else {
       const float sp = 1.f / (1.f + expf(-Sd));
       Gd = -g * sp * (1.f - sp);
@@ -754,7 +777,7 @@ finalize_kernel(const float* __restrict__ E, const float* __restrict__ dE_hat,
     for (int d = lane << 2; d < Dp; d += 128) {
       const float4 e = *reinterpret_cast<const float4*>(&sE[(size_t)i * Dp + d]);
       const float4 s = *reinterpret_cast<const float4*>(&sS[d]);
-      const float4 gv = ld4(gh, d, D, vec_g);
+      const float4 gv = ld4_plain(gh, d, D, vec_g);
       float ev[4] = {e.x, e.y, e.z, e.w}, sv[4] = {s.x, s.y, s.z, s.w}, gg[4] = {gv.x, gv.y, gv.z, gv.w};
       float de[4], du[4];
 #pragma unroll
@@ -792,6 +815,17 @@ finalize_kernel(const float* __restrict__ E, const float* __restrict__ dE_hat,
     o.w = de.w + bc.w + (sd.w - du.w) / m1;
     st4(dE + phys_row(idx, (size_t)j * M + i) * D, col, D, vec_o, o);
   }
+}
+
+__global__ void __launch_bounds__(kThreads)
+finalize_kernel(const float* __restrict__ E, const float* __restrict__ dE_hat,
+                const float* __restrict__ dC_hat, const float* __restrict__ cos_diag,
+                const float* __restrict__ row_stat, const float* __restrict__ row_aux, int M, int D, int Dp,
+                const float* __restrict__ wp, const float* __restrict__ bp, float eps, int variant,
+                const float* __restrict__ gp, float* __restrict__ dE, const int32_t* __restrict__ idx) {
+  extern __shared__ __align__(16) float smem[];
+  finalize_body(E, dE_hat, dC_hat, cos_diag, row_stat, row_aux, blockIdx.x, M, D, Dp, __ldg(wp), __ldg(bp), __ldg(gp),
+                eps, variant, dE, idx, smem);
 }
 
 
@@ -1384,6 +1418,357 @@ int simt_bwd_finalize(const float* E, const int32_t* row_index, const float* dE_
   if (rc != GE2E_OK) return rc;
   finalize_kernel<<<n_local, kThreads, smem, st>>>(E, dE_hat, dC_hat_local, cos_diag, row_stat, row_aux, M, D,
                                                    Dp, w, b, eps, variant, grad_out, dE, row_index);
+  GE2E_LAUNCHED();
+  return GE2E_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Small batches (the reference's own training / test shapes: N = 64 x M = 10, N = 4 x M = 8): the
+// whole fwd+bwd step as ONE kernel.  At these sizes the five-kernel pipeline is pure launch latency
+// (cfg2: 52 us for 63 MFLOP), so one CTA per speaker runs every stage, separated by two grid-wide
+// barriers (all N <= 128 CTAs are co-resident: one per SM):
+//   1  prep_body: e_hat, c_hat_j, cos_diag of the speaker's M rows                     | barrier
+//   2  all N c_hat rows -> shared memory; cos / S of the speaker's M x N block; row softmax
+//      (or contrast arg-max), loss, dw, db; w G kept in shared memory; dE_hat rows = (wG) C_hat;
+//      this speaker's contribution (wG)^T E_hat to every centroid -> workspace [j][k][D]   | barrier
+//   3  dC_hat_j = sum over speakers of their contribution to centroid j (fixed order:
+//      deterministic); finalize_body: diagonal term, Jacobians, fan-out -> dE
+// Same arithmetic as the pipeline's kernels (shared bodies / helpers), fp32 throughout.
+// ------------------------------------------------------------------------------------------
+namespace {
+
+// Up to kSmallMaxN speakers the kernel is correct (tested to 128); it is SELECTED only up to
+// kSmallPickN: one CTA per speaker serialises the speaker's M x N block, and at N = 64 (cfg2) the single
+// kernel takes as long as the five-kernel pipeline (55 us, stage timeline: scripts/small_step_trace.py),
+// while at the reference's test shape (N = 4, M = 8) it halves the step (37 -> 18 us).
+constexpr int kSmallMaxN = 128, kSmallMaxM = 16, kSmallMaxD = 256, kSmallPickN = 16;
+constexpr size_t kSmallHeaderBytes = 256;
+
+struct SmallParams {
+  const float* E; const int32_t* idx; int M, D, Dp;
+  const float* w; const float* b; float eps;
+  const float* grad_out;            // nullable: 1
+  float* e_hat; float* c_hat; float* cos_diag; float* row_stat; int32_t* row_kstar; float* row_aux;
+  float* per_row;                   // nullable
+  float* loss_accum;                // [0] = loss (zeroed here)
+  float* dE_hat; float* dC_hat; float* dwdb; float* dE;
+  int stop;                         // debug, timing only: leave after stage `stop` (0 = run everything)
+  unsigned* ctr;                    // workspace header: {barrier arrivals, exits}; zero on entry, restored
+  float* part;                      // workspace: [N][N][D] centroid contributions
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// every CTA of the grid arrives; `target` = arrivals expected so far (monotonic counter)
+__device__ __forceinline__ void small_grid_barrier(unsigned* ctr, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    unsigned long long t0 = 0;
+    for (unsigned spins = 0; ld_acquire_u32(ctr) < target; ++spins) {
+      if ((spins & 1023u) == 1023u) {               // a missing CTA is a bug: trap instead of hanging the GPU
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t0 == 0) t0 = t;
+        else if (t - t0 > 2000000000ull) __trap();
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// 4 floats of a row that another CTA wrote earlier in this kernel: L2 load (never the L1), tail-safe
+__device__ __forceinline__ float4 ld4_cg(const float* row, int col, int D, bool vec) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (vec) { if (col < D) v = __ldcg(reinterpret_cast<const float4*>(row + col)); }
+  else {
+    if (col + 0 < D) v.x = __ldcg(row + col + 0);
+    if (col + 1 < D) v.y = __ldcg(row + col + 1);
+    if (col + 2 < D) v.z = __ldcg(row + col + 2);
+    if (col + 3 < D) v.w = __ldcg(row + col + 3);
+  }
+  return v;
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(kThreads, 1)
+small_step_kernel(const SmallParams p) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red[kWarps];
+  __shared__ float s_cd[32];
+  const int j = blockIdx.x, N = gridDim.x, M = p.M, D = p.D, Dp = p.Dp;
+  const int Np = (N + 3) & ~3;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  float* sA = smem;                                   // (2M + 2) Dp: prep_body, later finalize_body
+  float* sEh = sA + (size_t)(2 * M + 2) * Dp;         // [M][Dp] e_hat of this speaker
+  float* sC = sEh + (size_t)M * Dp;                   // [N][Dp] all c_hat
+  float* sG = sC + (size_t)N * Dp;                    // [M][Np] w * G, zero on the own-speaker column
+  float* sCos = sG + (size_t)M * Np;                  // [M][Np] cos + eps
+  pdl_wait();
+  pdl_trigger();
+  // debug (GE2E_SMALL_STOP=99, softmax only): SM clock stamps of CTA 0 into the unused row_kstar buffer
+#define GE2E_SMALL_STAMP(n) do { if (p.stop == 99 && j == 0 && tid == 0) p.row_kstar[n] = (int)clock(); } while (0)
+  GE2E_SMALL_STAMP(0);
+  const float w = __ldg(p.w), b = __ldg(p.b), eps = p.eps;
+  const float g = p.grad_out != nullptr ? __ldg(p.grad_out) : 1.f;
+  if (j == 0 && tid < 4) {
+    p.loss_accum[tid] = 0.f;                          // {loss, -, -, -} as prep does
+    if (tid < 2) p.dwdb[tid] = 0.f;
+  }
+
+  // ---- 1: this speaker's rows
+  prep_body<false>(p.E, p.idx, j, M, D, Dp, p.e_hat, p.c_hat, p.cos_diag, sA);
+  GE2E_SMALL_STAMP(1);
+  if (p.stop == 1) return;
+  do {
+  small_grid_barrier(p.ctr, (unsigned)N);
+  GE2E_SMALL_STAMP(2);
+  if (p.stop == 2) break;
+
+  // ---- 2: M x N block of the similarity matrix
+  const bool vec_c = is_vec(p.c_hat, D), vec_e = is_vec(p.e_hat, D);
+  for (int v = tid; v < N * (Dp >> 2); v += kThreads) {
+    const int k = v / (Dp >> 2), col = (v % (Dp >> 2)) << 2;
+    *reinterpret_cast<float4*>(&sC[(size_t)k * Dp + col]) = ld4_cg(p.c_hat + (size_t)k * D, col, D, vec_c);
+  }
+  for (int v = tid; v < M * (Dp >> 2); v += kThreads) {
+    const int i = v / (Dp >> 2), col = (v % (Dp >> 2)) << 2;
+    *reinterpret_cast<float4*>(&sEh[(size_t)i * Dp + col]) = ld4_plain(p.e_hat + ((size_t)j * M + i) * D, col, D, vec_e);
+  }
+  if (tid < M) s_cd[tid] = p.cos_diag[(size_t)j * M + tid];
+  __syncthreads();
+  GE2E_SMALL_STAMP(3);
+  for (int k = wid; k < N; k += kWarps) {
+    // all M dot products of centroid k at once: independent chains instead of M serial reductions
+    float dots[kSmallMaxM];
+#pragma unroll
+    for (int i = 0; i < kSmallMaxM; ++i) dots[i] = 0.f;
+    for (int d = lane << 2; d < Dp; d += 128) {
+      const float4 c = *reinterpret_cast<const float4*>(&sC[(size_t)k * Dp + d]);
+#pragma unroll
+      for (int i = 0; i < kSmallMaxM; ++i)
+        if (i < M) dots[i] += dot4(*reinterpret_cast<const float4*>(&sEh[(size_t)i * Dp + d]), c);
+    }
+    // butterfly stages interleaved over the rows (a warp_sum per row would run 16 x 5 dependent shuffles)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int i = 0; i < kSmallMaxM; ++i) dots[i] += __shfl_xor_sync(0xffffffffu, dots[i], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < kSmallMaxM; ++i)
+        if (i < M) sCos[i * Np + k] = ((k == j) ? s_cd[i] : dots[i]) + eps;         // s3:78-79
+    }
+  }
+  __syncthreads();
+  GE2E_SMALL_STAMP(4);
+  if (p.stop == 3) break;
+  float loss_part = 0.f, dw_part = 0.f, db_part = 0.f;
+  for (int i = wid; i < M; i += kWarps) {
+    const int r = j * M + i;
+    const float cd = sCos[i * Np + j];
+    const float Sd = fmaf(w, cd, b);                                                  // s3:27
+    float per, stat, aux = 0.f, dw_i = 0.f, db_i = 0.f;
+    int ks = -1;
+    if (VARIANT == GE2E_SOFTMAX) {
+      float m = -INFINITY;
+      for (int k = lane; k < N; k += 32)
+        if (k != j) m = fmaxf(m, fmaf(w, sCos[i * Np + k], b));
+      const float mx = fmaxf(warp_max(m), Sd);
+      float l = 0.f;
+      for (int k = lane; k < N; k += 32)
+        if (k != j) l += expf(fmaf(w, sCos[i * Np + k], b) - mx);
+      const float loff = warp_sum(l);
+      close_softmax_row(mx, loff, Sd, eps, stat, aux, per);                          // s3:120-121
+      float dwl = 0.f;
+      for (int k = lane; k < N; k += 32) {
+        float wg = 0.f;
+        if (k != j) {
+          const float cosv = sCos[i * Np + k];
+          const float G = g * expf(fmaf(w, cosv, b) - stat);
+          dwl = fmaf(G, cosv, dwl);
+          wg = w * G;
+        }
+        sG[i * Np + k] = wg;
+      }
+      dw_i = warp_sum(dwl) - g * aux * cd;            // own speaker: G = g (p_jj - 1) = -g aux
+      db_i = -g * eps * expf(-stat);                  // closed form
+    } else {
+      float bv = -INFINITY; int bk = INT_MAX;
+      for (int k = lane; k < N; k += 32)
+        if (k != j) {
+          const float S = fmaf(w, sCos[i * Np + k], b);
+          if (S > bv) { bv = S; bk = k; }
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+        if (ov > bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
+      }
+      const float sp = 1.f / (1.f + expf(-Sd));
+      per = 1.f - sp;
+      stat = bv;
+      const float Gp = -g * sp * (1.f - sp);
+      float Gn = 0.f, cn = 0.f;
+      if (bk != INT_MAX) {
+        ks = bk;
+        const float sn = 1.f / (1.f + expf(-bv));
+        per += sn;
+        Gn = g * sn * (1.f - sn);
+        cn = sCos[i * Np + bk];
+      }
+      for (int k = lane; k < N; k += 32) sG[i * Np + k] = (k == ks) ? w * Gn : 0.f;
+      dw_i = Gp * cd + Gn * cn;
+      db_i = Gp + Gn;
+    }
+    if (lane == 0) {
+      p.row_stat[r] = stat;
+      p.row_aux[r] = aux;
+      if (VARIANT == GE2E_CONTRAST && p.row_kstar != nullptr) p.row_kstar[r] = ks;
+      if (p.per_row != nullptr) p.per_row[r] = per;
+      loss_part += per; dw_part += dw_i; db_part += db_i;
+    }
+  }
+  {
+    const float lt = block_sum(loss_part, red);
+    const float dwt = block_sum(dw_part, red);
+    const float dbt = block_sum(db_part, red);
+    if (tid == 0) { atomicAdd(p.loss_accum, lt); atomicAdd(p.dwdb + 0, dwt); atomicAdd(p.dwdb + 1, dbt); }
+  }
+  __syncthreads();                                     // sG complete
+  GE2E_SMALL_STAMP(5);
+  if (p.stop == 4) break;
+  const bool vec_g = is_vec(p.dE_hat, D), vec_p = is_vec(p.part, D);
+  for (int i = wid; i < M; i += kWarps) {             // dE_hat rows = (wG) C_hat
+    for (int d = lane << 2; d < Dp; d += 128) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+      for (int k = 0; k < N; ++k) {
+        const float sgk = sG[i * Np + k];
+        const float4 c = *reinterpret_cast<const float4*>(&sC[(size_t)k * Dp + d]);
+        acc.x = fmaf(sgk, c.x, acc.x); acc.y = fmaf(sgk, c.y, acc.y); acc.z = fmaf(sgk, c.z, acc.z); acc.w = fmaf(sgk, c.w, acc.w);
+      }
+      st4(p.dE_hat + ((size_t)j * M + i) * D, d, D, vec_g, acc);
+    }
+  }
+  __syncthreads();
+  GE2E_SMALL_STAMP(6);
+  for (int k = wid; k < N; k += kWarps) {             // this speaker's share of dC_hat_k = (wG)^T E_hat
+    for (int d = lane << 2; d < Dp; d += 128) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+      for (int i = 0; i < M; ++i) {
+        const float sgk = sG[i * Np + k];
+        const float4 e = *reinterpret_cast<const float4*>(&sEh[(size_t)i * Dp + d]);
+        acc.x = fmaf(sgk, e.x, acc.x); acc.y = fmaf(sgk, e.y, acc.y); acc.z = fmaf(sgk, e.z, acc.z); acc.w = fmaf(sgk, e.w, acc.w);
+      }
+      st4(p.part + ((size_t)j * N + k) * D, d, D, vec_p, acc);
+    }
+  }
+  __syncthreads();
+  GE2E_SMALL_STAMP(7);
+  if (p.stop == 5) break;
+  small_grid_barrier(p.ctr, (unsigned)(2 * N));
+  GE2E_SMALL_STAMP(8);
+  if (p.stop == 6) break;
+
+  // ---- 3: centroid gradient of this speaker, then the Jacobians and the fan-out
+  // (the block's threads split the N contributions into groups so that each thread has many independent
+  // L2 loads in flight instead of a chain of N; the groups are then added in a fixed order)
+  {
+    const int ncol4 = Dp >> 2;                               // <= 64 float4 columns
+    const int ngrp = kThreads / ncol4;                       // >= 4 speaker groups
+    const int col4 = tid % ncol4, grp = tid / ncol4;
+    const int used = ngrp < N ? ngrp : N;
+    float* sP = sC;                                          // [used][Dp]: the centroids are no longer needed
+    __syncthreads();
+    if (grp < used) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int col = col4 << 2;
+      for (int j0 = grp; j0 < N; j0 += used * 8) {             // 8 L2 loads in flight, added in a fixed order
+        float4 v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int jj = j0 + q * used;
+          v[q] = (jj < N) ? ld4_cg(p.part + ((size_t)jj * N + j) * D, col, D, vec_p) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w; }
+      }
+      *reinterpret_cast<float4*>(&sP[(size_t)grp * Dp + col]) = acc;
+    }
+    __syncthreads();
+    for (int d = tid; d < D; d += kThreads) {
+      float sum = 0.f;
+      for (int q = 0; q < used; ++q) sum += sP[(size_t)q * Dp + d];
+      p.dC_hat[(size_t)j * D + d] = sum;
+    }
+  }
+  __syncthreads();
+  GE2E_SMALL_STAMP(9);
+  if (p.stop == 7) break;
+  finalize_body(p.E, p.dE_hat, p.dC_hat, p.cos_diag, p.row_stat, p.row_aux, j, M, D, Dp, w, b, g, eps, VARIANT, p.dE,
+                p.idx, sA);
+  } while (0);
+  __syncthreads();
+  GE2E_SMALL_STAMP(10);
+  // last CTA out restores the workspace header (every CTA has left both barriers by the time it exits)
+  if (tid == 0) {
+    if (atomicAdd(p.ctr + 1, 1u) == (unsigned)(N - 1)) { atomicExch(p.ctr, 0u); atomicExch(p.ctr + 1, 0u); }
+  }
+}
+
+
+size_t small_smem_bytes(int N, int M, int D) {
+  const int Dp = (D + 3) & ~3, Np = (N + 3) & ~3;
+  return ((size_t)(3 * M + 2) * Dp + (size_t)N * Dp + (size_t)2 * M * Np) * sizeof(float);
+}
+
+}  // namespace
+
+bool small_step_preferred(int N, int M, int D) { return small_step_supported(N, M, D) && N <= kSmallPickN; }
+
+bool small_step_supported(int N, int M, int D) {
+  return N >= 1 && N <= kSmallMaxN && M >= 2 && M <= kSmallMaxM && D >= 1 && D <= kSmallMaxD &&
+         small_smem_bytes(N, M, D) <= 200 * 1024;
+}
+
+size_t small_step_workspace_bytes(int N, int M, int D) {
+  return small_step_supported(N, M, D) ? kSmallHeaderBytes + (size_t)N * N * D * sizeof(float) : 0;
+}
+
+int simt_small_step(const float* E, const int32_t* row_index, int N, int M, int D, const float* w, const float* b,
+                    float eps, int variant, const float* grad_out, float* e_hat, float* c_hat, float* cos_diag,
+                    float* row_stat, int32_t* row_kstar, float* row_aux, float* per_row, float* loss_accum,
+                    float* dE_hat, float* dC_hat, float* dwdb, float* dE, void* workspace, cudaStream_t st) {
+  SmallParams p;
+  p.E = E; p.idx = row_index; p.M = M; p.D = D; p.Dp = (D + 3) & ~3;
+  p.w = w; p.b = b; p.eps = eps; p.grad_out = grad_out;
+  p.e_hat = e_hat; p.c_hat = c_hat; p.cos_diag = cos_diag; p.row_stat = row_stat; p.row_kstar = row_kstar;
+  p.row_aux = row_aux; p.per_row = per_row; p.loss_accum = loss_accum;
+  p.dE_hat = dE_hat; p.dC_hat = dC_hat; p.dwdb = dwdb; p.dE = dE;
+  static const int stop = [] { const char* e = getenv("GE2E_SMALL_STOP"); return e ? atoi(e) : 0; }();
+  p.stop = stop;
+  p.ctr = reinterpret_cast<unsigned*>(workspace);
+  p.part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kSmallHeaderBytes);
+  const size_t smem = small_smem_bytes(N, M, D);
+  if (variant == GE2E_SOFTMAX) {
+    int rc = set_smem(small_step_kernel<GE2E_SOFTMAX>, smem);
+    if (rc != GE2E_OK) return rc;
+    launch_pdl(small_step_kernel<GE2E_SOFTMAX>, dim3(N), dim3(kThreads), smem, st, true, p);
+  } else {
+    int rc = set_smem(small_step_kernel<GE2E_CONTRAST>, smem);
+    if (rc != GE2E_OK) return rc;
+    launch_pdl(small_step_kernel<GE2E_CONTRAST>, dim3(N), dim3(kThreads), smem, st, true, p);
+  }
   GE2E_LAUNCHED();
   return GE2E_OK;
 }

@@ -44,8 +44,10 @@ class GE2EPlan:
         self._accum = torch.empty(4, dtype=f32, device=dev)      # {loss, -, -, -}
         self.dE = torch.empty((N, M, D), dtype=f32, device=dev)
         self.grad_out = torch.ones((), dtype=f32, device=dev)
-        nbytes = lib().ge2e_b200_workspace_bytes(N, N, M, D, self.variant, self.precision)
+        nbytes = lib().ge2e_b200_step_workspace_bytes(N, M, D, self.variant, self.precision)
         self._ws = torch.zeros(max(nbytes, 1), dtype=torch.uint8, device=dev)   # zero once: the kernels restore it
+        # 1: the reference-sized batch runs fwd+bwd as ONE kernel (ge2e_b200_forward_backward)
+        self.single_kernel = lib().ge2e_b200_step_launches(N, M, D, self.variant, self.precision) == 1
         self._ws_bytes = nbytes
         self.loss = self._accum[0]
         self.dw = self._scratch[N * D]
@@ -58,24 +60,26 @@ class GE2EPlan:
         h, N, M, D = lib(), self.N, self.M, self.D
         stream = torch.cuda.current_stream(self.device).cuda_stream
         ws = self._ws.data_ptr() if self._ws_bytes else None
+        if backward:
+            accum_ptr = self._scratch.data_ptr() + (N * D - 1) * 4   # accum[1] = dw, accum[2] = db
+            rc = h.ge2e_b200_forward_backward(E.data_ptr(), None, N, M, D, w.data_ptr(), b.data_ptr(), self.eps,
+                                              self.variant, self.precision, self.grad_out.data_ptr(),
+                                              self.e_hat.data_ptr(), self.c_hat.data_ptr(), self.cos_diag.data_ptr(),
+                                              self.row_stat.data_ptr(), self.row_kstar.data_ptr(),
+                                              self.row_aux.data_ptr(), self._accum.data_ptr(), self.dE_hat.data_ptr(),
+                                              self._scratch.data_ptr(), accum_ptr, self.dE.data_ptr(), ws,
+                                              self._ws_bytes, stream)
+            check(rc, "ge2e_b200_forward_backward")
+            if self.sgd is not None:
+                rc = h.ge2e_b200_scale_bias_sgd(w.data_ptr(), b.data_ptr(), accum_ptr + 4, accum_ptr + 8, self.sgd[1],
+                                                self.sgd[0], None, stream)
+                check(rc, "ge2e_b200_scale_bias_sgd")
+            return
         rc = h.ge2e_b200_forward(E.data_ptr(), N, M, D, w.data_ptr(), b.data_ptr(), self.eps, self.variant,
                                  self.precision, self.e_hat.data_ptr(), self.c_hat.data_ptr(),
                                  self.cos_diag.data_ptr(), self.row_stat.data_ptr(), self.row_kstar.data_ptr(),
                                  self.row_aux.data_ptr(), self._accum.data_ptr(), ws, self._ws_bytes, stream)
         check(rc, "ge2e_b200_forward")
-        if not backward:
-            return
-        accum_ptr = self._scratch.data_ptr() + (N * D - 1) * 4   # accum[1] = dw, accum[2] = db
-        rc = h.ge2e_b200_backward(E.data_ptr(), self.e_hat.data_ptr(), self.c_hat.data_ptr(),
-                                  self.cos_diag.data_ptr(), self.row_stat.data_ptr(), self.row_kstar.data_ptr(),
-                                  self.row_aux.data_ptr(), N, M, D, w.data_ptr(), b.data_ptr(), self.eps, self.variant, self.precision,
-                                  self.grad_out.data_ptr(), self.dE_hat.data_ptr(), self._scratch.data_ptr(),
-                                  accum_ptr, self.dE.data_ptr(), ws, self._ws_bytes, stream)
-        check(rc, "ge2e_b200_backward")
-        if self.sgd is not None:
-            rc = h.ge2e_b200_scale_bias_sgd(w.data_ptr(), b.data_ptr(), accum_ptr + 4, accum_ptr + 8, self.sgd[1],
-                                            self.sgd[0], None, stream)
-            check(rc, "ge2e_b200_scale_bias_sgd")
 
     def capture(self, E, w: torch.Tensor, b: torch.Tensor, backward: bool = True, steps: int = 1):
         """Capture ``steps`` consecutive steps into one CUDA graph bound to these tensors; returns the

@@ -533,3 +533,101 @@ def test_full_size_vs_reference_formulation_on_the_gpu(pkg, N, precision, tol):
     # db is epsilon-driven and cancels catastrophically in the reference's own fp32 autograd (SURVEY 8a-bis
     # item 12): bounded, not matched
     assert abs(got["db"] - ref["db"]) <= 1e-5 * N * M
+
+
+SMALL_SHAPES = [(4, 8, 256), (64, 10, 256), (3, 2, 64), (1, 5, 32), (128, 16, 256), (7, 3, 100), (16, 6, 30), (5, 4, 7),
+                (100, 10, 128)]
+
+
+@pytest.mark.parametrize("variant", ["softmax", "contrast"])
+@pytest.mark.parametrize("N,M,D", SMALL_SHAPES)
+def test_single_kernel_step_matches_oracle(pkg, N, M, D, variant):
+    """Reference-sized batches run fwd+bwd as ONE kernel through GE2EPlan / ge2e_b200_forward_backward
+    (one CTA per speaker, grid-wide barriers).  fp32 parity bar (1e-5) against the fp64 oracle, three
+    steps on the same persistent workspace (its header must come back to zero), then an upstream
+    gradient != 1 and a negative w."""
+    dev = torch.device("cuda:0")
+    pkg.lib().ge2e_b200_debug_small_step(2)                    # every supported shape, not only N <= 16
+    try:
+        plan = pkg.GE2EPlan(N, M, D, variant, "fp32", device=dev)
+    finally:
+        pkg.lib().ge2e_b200_debug_small_step(1)
+    assert plan.single_kernel
+    pkg.lib().ge2e_b200_debug_small_step(2)
+    E_np = orc.make_embeddings(N, M, D, seed=N * 7 + M, kind="clustered")
+    E = torch.tensor(np.asarray(E_np, dtype=np.float32), device=dev)
+    for (wv, bv, gv) in ((10.0, -5.0, 1.0), (10.0, -5.0, 1.0), (-3.0, 0.5, 0.25)):
+        w = torch.tensor(wv, device=dev)
+        b = torch.tensor(bv, device=dev)
+        plan.grad_out.fill_(gv)
+        plan.step(E, w, b)
+        torch.cuda.synchronize()
+        ref = orc.forward_backward(E_np, wv, bv, 1e-6, variant, g=gv)
+        got = dict(loss=plan.loss.item(), dE=plan.dE.double().cpu().numpy(), dw=plan.dw.item(), db=plan.db.item())
+        check(got, ref, N * M, 1e-5)
+    pkg.lib().ge2e_b200_debug_small_step(1)
+    assert int(plan._ws[:256].max()) == 0                      # barrier counters restored
+    default_plan = pkg.GE2EPlan(N, M, D, variant, "fp32", device=dev)
+    assert default_plan.single_kernel == (N <= 16)             # default selection: only where it is faster
+
+
+def test_single_kernel_step_in_a_graph_and_vs_pipeline(pkg):
+    """The same step captured in a CUDA graph (4 steps over 2 batches) equals the eager module API, which
+    takes the multi-kernel pipeline; and the launch count of the plan is one kernel per step."""
+    dev = torch.device("cuda:0")
+    N, M, D = 64, 10, 256
+    Es = [torch.tensor(np.asarray(orc.make_embeddings(N, M, D, seed=s, kind="clustered"), dtype=np.float32), device=dev)
+          for s in (1, 2)]
+    w = torch.tensor(10.0, device=dev); b = torch.tensor(-5.0, device=dev)
+    pkg.lib().ge2e_b200_debug_small_step(2)
+    try:
+        plan = pkg.GE2EPlan(N, M, D, "softmax", "fp32", device=dev)
+        g = plan.capture(Es, w, b, steps=4)
+    finally:
+        pkg.lib().ge2e_b200_debug_small_step(1)
+    assert plan.launches_per_step == 1
+    g.replay(); g.replay()
+    torch.cuda.synchronize()
+    ref = run_cuda(pkg, Es[1].cpu().numpy(), 10.0, -5.0)       # last step of the graph ran on Es[1]
+    assert abs(plan.loss.item() - ref["loss"]) <= 1e-6 * abs(ref["loss"])
+    assert rel(plan.dE.double().cpu().numpy(), ref["dE"]) <= 2e-6
+    assert abs(plan.dw.item() - ref["dw"]) <= 1e-5 * max(1.0, abs(ref["dw"]))
+
+
+def test_single_kernel_step_indexed_rows(pkg):
+    """row_index (the trainer's unperm) through the single-kernel step: C ABI called directly."""
+    import ctypes as C
+    dev = torch.device("cuda:0")
+    N, M, D = 12, 5, 64
+    h = pkg.lib()
+    E_np = np.asarray(orc.make_embeddings(N, M, D, seed=9, kind="clustered"), dtype=np.float32)
+    perm = np.random.default_rng(0).permutation(N * M)
+    idx = torch.tensor(perm.astype(np.int32), device=dev)      # logical row r lives at physical row perm[r]
+    flat = torch.empty((N * M, D), device=dev)
+    flat[idx.long()] = torch.tensor(E_np.reshape(N * M, D), device=dev)
+    f32 = dict(dtype=torch.float32, device=dev)
+    U = N * M
+    e_hat, c_hat, cos_diag = torch.empty(U, D, **f32), torch.empty(N, D, **f32), torch.empty(U, **f32)
+    row_stat, row_aux, kstar = torch.empty(U, **f32), torch.empty(U, **f32), torch.empty(U, dtype=torch.int32, device=dev)
+    accum, dE_hat, scratch, dE = torch.empty(4, **f32), torch.empty(U, D, **f32), torch.empty(N * D + 2, **f32), torch.empty(U, D, **f32)
+    w = torch.tensor(10.0, device=dev); b = torch.tensor(-5.0, device=dev); gone = torch.ones((), **f32)
+    nb = h.ge2e_b200_step_workspace_bytes(N, M, D, 0, 0)
+    assert nb > 0 and h.ge2e_b200_step_launches(N, M, D, 0, 0) == 1
+    ws = torch.zeros(nb, dtype=torch.uint8, device=dev)
+    rc = h.ge2e_b200_forward_backward(flat.data_ptr(), idx.data_ptr(), N, M, D, w.data_ptr(), b.data_ptr(), 1e-6, 0, 0,
+                                      gone.data_ptr(), e_hat.data_ptr(), c_hat.data_ptr(), cos_diag.data_ptr(),
+                                      row_stat.data_ptr(), kstar.data_ptr(), row_aux.data_ptr(), accum.data_ptr(),
+                                      dE_hat.data_ptr(), scratch.data_ptr(), scratch.data_ptr() + (N * D - 1) * 4,
+                                      dE.data_ptr(), ws.data_ptr(), nb, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    ref = orc.forward_backward(E_np, 10.0, -5.0, 1e-6, "softmax")
+    got = dict(loss=accum[0].item(), dE=dE[idx.long()].double().cpu().numpy().reshape(N, M, D), dw=scratch[N * D].item(),
+               db=scratch[N * D + 1].item())
+    check(got, ref, U, 1e-5)
+    # too small a workspace is refused, not overrun
+    assert h.ge2e_b200_forward_backward(flat.data_ptr(), idx.data_ptr(), N, M, D, w.data_ptr(), b.data_ptr(), 1e-6, 0, 0,
+                                        gone.data_ptr(), e_hat.data_ptr(), c_hat.data_ptr(), cos_diag.data_ptr(),
+                                        row_stat.data_ptr(), kstar.data_ptr(), row_aux.data_ptr(), accum.data_ptr(),
+                                        dE_hat.data_ptr(), scratch.data_ptr(), scratch.data_ptr() + (N * D - 1) * 4,
+                                        dE.data_ptr(), ws.data_ptr(), 128, torch.cuda.current_stream().cuda_stream) == -4
