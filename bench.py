@@ -532,6 +532,8 @@ def run_ours(args):
             t = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = [t.item() / args.steps] * args.steps
+            splan.step(shards[0], w, b)                     # same batch as the autograd check below
+            torch.cuda.synchronize()
             extra["sharded_loss_check"] = {"graph_plan": splan.loss.item()}
             sharded_how = (f"K steps incl. NCCL collectives in one CUDA graph, shard rotating over {n_rot} batches "
                            f"({n_rot * n_local * M * D * 4 / 1e6:.0f} MB), one event pair, max over ranks")
