@@ -29,6 +29,19 @@ import torch
 from . import _lib, ops
 
 
+def span_offsets(first, frames: int, mels: int, speakers, utter_idx, clip, perm=None) -> np.ndarray:
+    """Element offset, in a bank laid out as [all utterances, frames, mels], of every output row's crop:
+    row (n, m) = utterance ``first[speakers[n]] + utter_idx[n, m]`` starting at frame ``clip[n]``; rows
+    reordered by ``perm`` (s4:186 ``mel_db_batch[perm]``).  Host only (pure index arithmetic)."""
+    first = np.asarray(first, dtype=np.int64)
+    spk = np.asarray(speakers, dtype=np.int64)
+    off = ((first[spk][:, None] + np.asarray(utter_idx, dtype=np.int64)) * frames + np.asarray(clip, dtype=np.int64)[:, None]) * mels
+    off = off.reshape(-1)
+    if perm is not None:
+        off = off[np.asarray(perm, dtype=np.int64)]
+    return np.ascontiguousarray(off)
+
+
 class SpectrogramBank:
     def __init__(self, arrays: Sequence[np.ndarray], device="cuda", names: Optional[List[str]] = None):
         if len(arrays) == 0:
@@ -84,10 +97,7 @@ class SpectrogramBank:
             raise IndexError("speaker or utterance index out of range")
         if crop_len < 1 or (clip < 0).any() or (clip + crop_len > self.frames).any():
             raise IndexError("crop outside the utterance")
-        off = ((self.first[spk][:, None] + utter_idx) * self.frames + clip[:, None]) * self.mels      # [N, M]
-        off = off.reshape(-1)
-        if perm is not None:
-            off = off[np.asarray(perm, dtype=np.int64)]
+        off = span_offsets(self.first, self.frames, self.mels, spk, utter_idx, clip, perm)
         rows, span = N * M, crop_len * self.mels
         if out is None:
             out = torch.empty((rows, crop_len, self.mels), dtype=torch.float32, device=self.device)

@@ -74,13 +74,11 @@ def threshold_counts(sim_matrix: torch.Tensor, thresholds: Sequence[float]):
     return acc_all, acc_own
 
 
-def eer_sweep(sim_matrix: torch.Tensor, thresholds: Optional[Sequence[float]] = None) -> EERResult:
-    """s5:50-97 on a device-resident similarity matrix."""
-    thresholds = default_thresholds() if thresholds is None else [float(t) for t in thresholds]
-    N, M = int(sim_matrix.shape[0]), int(sim_matrix.shape[1])
+def eer_from_counts(acc_all, acc_own, N: int, M: int, thresholds: Sequence[float]) -> EERResult:
+    """The reference's scalar arithmetic (s5:50-97) on the integer accept counts; host only."""
     if N < 2:
         raise ValueError("the reference's FAR denominator (N - 1) / M / N is zero for N = 1 (s5:80)")
-    acc_all, acc_own = threshold_counts(sim_matrix, thresholds)
+    thresholds = list(thresholds)
     diff, EER, EER_thres, EER_FAR, EER_FRR = 1, 0, 0, 0, 0
     fars, frrs = [], []
     for t, thres in enumerate(thresholds):
@@ -91,7 +89,17 @@ def eer_sweep(sim_matrix: torch.Tensor, thresholds: Optional[Sequence[float]] = 
         if diff > abs(far - frr):                                          # s5:92-97
             diff = abs(far - frr)
             EER, EER_thres, EER_FAR, EER_FRR = (far + frr) / 2, thres, far, frr
-    return EERResult(EER, EER_thres, EER_FAR, EER_FRR, thresholds, fars, frrs, acc_all, acc_own)
+    return EERResult(EER, EER_thres, EER_FAR, EER_FRR, thresholds, fars, frrs, np.asarray(acc_all), np.asarray(acc_own))
+
+
+def eer_sweep(sim_matrix: torch.Tensor, thresholds: Optional[Sequence[float]] = None) -> EERResult:
+    """s5:50-97 on a device-resident similarity matrix: counts on the GPU, scalars on the host."""
+    thresholds = default_thresholds() if thresholds is None else [float(t) for t in thresholds]
+    N, M = int(sim_matrix.shape[0]), int(sim_matrix.shape[1])
+    if N < 2:
+        raise ValueError("the reference's FAR denominator (N - 1) / M / N is zero for N = 1 (s5:80)")
+    acc_all, acc_own = threshold_counts(sim_matrix, thresholds)
+    return eer_from_counts(acc_all, acc_own, N, M, thresholds)
 
 
 def evaluate_eer(embeddings: torch.Tensor, w: float = 1.0, b: float = 0.0, hp=None,
