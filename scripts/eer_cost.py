@@ -34,19 +34,34 @@ for (N, M) in [(64, 10), (1024, 10), (2048, 16)]:
     st = torch.cuda.current_stream().cuda_stream
 
     def run(k):
+        global st
         h.ge2e_b200_threshold_counts(mats[k % n_rot].data_ptr(), N, M, th.data_ptr(), T, counts[0].data_ptr(),
                                      counts[1].data_ptr(), scratch.data_ptr(), nb, st)
     for k in range(5):
         run(k)
     torch.cuda.synchronize()
+    # 20 calls over rotating matrices captured in one CUDA graph: the eager loop is host-bound (~20 us per
+    # ctypes call + memset + launch), which would be charged to the kernel
+    steps = 20
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    gph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gph, stream=side):
+        st_keep = st
+        st = torch.cuda.current_stream().cuda_stream
+        for k in range(steps):
+            run(k)
+        st = st_keep
+    for _ in range(3):
+        gph.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    steps = 50
     e0.record()
-    for k in range(steps):
-        run(k)
+    for _ in range(5):
+        gph.replay()
     e1.record()
     torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) / steps * 1e3
+    us = e0.elapsed_time(e1) / (5 * steps) * 1e3
     nbytes = N * M * N * 4
     # host side: the reference's sequence = D2H of the matrix + numpy sweep
     t0 = time.perf_counter()

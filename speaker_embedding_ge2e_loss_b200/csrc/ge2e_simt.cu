@@ -16,6 +16,8 @@
 //   contrast_bwd     the contrast gradient has two non-zeros per row: gather/scatter kernel
 //   finalize_kernel  one CTA per speaker: diagonal term, normalisation Jacobians, fan-out
 #include <limits.h>
+
+#include <algorithm>
 #include <stdlib.h>
 
 #include <initializer_list>
@@ -1811,7 +1813,7 @@ int simt_scale_bias_sgd(float* w, float* b, float* dw, float* db, float max_norm
 constexpr int kEerMaxT = 1024;
 constexpr int kEerThreads = 256;
 constexpr int kEerPrivT = 64;
-constexpr int kEerPrivThreads = 128;
+constexpr int kEerPrivThreads = 512;   // few large blocks: the per-block fold ends in same-address global atomics
 
 __device__ __forceinline__ int eer_bin(float v, const float* thr, int T) {
   int lo = 0, hi = T;                      // number of thresholds with v > thr  (NaN -> 0)
@@ -1843,13 +1845,19 @@ __device__ __forceinline__ void eer_count(unsigned* hist, int bin, bool on) {
 }
 
 // accepted at threshold t = values with more than t thresholds below them = sum of bins t+1 .. T
-__device__ __forceinline__ void eer_finish(unsigned long long* hist_g, int T, long long* accept_all, long long* accept_own) {
+// (the whole last block fetches the two histograms into shared memory first: a single thread walking them
+// in global memory is a chain of T dependent L2 round trips, ~17 us at T = 50)
+__device__ __forceinline__ void eer_finish(unsigned long long* hist_g, int T, long long* accept_all, long long* accept_own,
+                                           unsigned long long* s_h /* shared, 2 (T + 1) entries */) {
+  const volatile unsigned long long* h = hist_g;
+  for (int i = threadIdx.x; i < 2 * (T + 1); i += blockDim.x) s_h[i] = h[i];
+  __syncthreads();
   if (threadIdx.x < 2) {
-    const volatile unsigned long long* h = hist_g + threadIdx.x * (T + 1);
+    const unsigned long long* hs = s_h + threadIdx.x * (T + 1);
     long long* out = threadIdx.x == 0 ? accept_all : accept_own;
     long long run = 0;
     for (int t = T - 1; t >= 0; --t) {
-      run += (long long)h[t + 1];
+      run += (long long)hs[t + 1];
       out[t] = run;
     }
   }
@@ -1859,7 +1867,7 @@ __global__ void __launch_bounds__(kEerPrivThreads)
 threshold_counts_private_kernel(const float* __restrict__ sim, long long rows, int N, int M,
                                 const float* __restrict__ thr_g, int T, unsigned long long* __restrict__ hist_g,
                                 long long* __restrict__ accept_all, long long* __restrict__ accept_own) {
-  extern __shared__ unsigned eer_smem[];
+  extern __shared__ __align__(16) unsigned eer_smem[];
   constexpr int kWarps = kEerPrivThreads / 32;
   float* thr = reinterpret_cast<float*>(eer_smem);            // [T]
   unsigned* h_own = eer_smem + T;                              // [T + 1]
@@ -1917,14 +1925,15 @@ threshold_counts_private_kernel(const float* __restrict__ sim, long long rows, i
   __syncthreads();
   if (!last) return;
   __threadfence();
-  eer_finish(hist_g, T, accept_all, accept_own);
+  __syncthreads();
+  eer_finish(hist_g, T, accept_all, accept_own, reinterpret_cast<unsigned long long*>(eer_smem));
 }
 
 __global__ void __launch_bounds__(kEerThreads)
 threshold_counts_kernel(const float* __restrict__ sim, long long total, int N, int M, const float* __restrict__ thr_g,
                         int T, unsigned long long* __restrict__ hist_g /* [2][T+1] + ticket */,
                         long long* __restrict__ accept_all, long long* __restrict__ accept_own) {
-  extern __shared__ unsigned eer_smem[];
+  extern __shared__ __align__(16) unsigned eer_smem[];
   float* thr = reinterpret_cast<float*>(eer_smem);            // [T]
   unsigned* h_all = eer_smem + T;                              // [T + 1]
   unsigned* h_own = h_all + (T + 1);                           // [T + 1]
@@ -1958,7 +1967,8 @@ threshold_counts_kernel(const float* __restrict__ sim, long long total, int N, i
   __syncthreads();
   if (!last) return;
   __threadfence();
-  eer_finish(hist_g, T, accept_all, accept_own);
+  __syncthreads();
+  eer_finish(hist_g, T, accept_all, accept_own, reinterpret_cast<unsigned long long*>(eer_smem));
 }
 
 int simt_threshold_counts(const float* sim, int N, int M, const float* thresholds, int T, long long* accept_all,
@@ -1972,9 +1982,11 @@ int simt_threshold_counts(const float* sim, int N, int M, const float* threshold
   unsigned long long* hist = reinterpret_cast<unsigned long long*>(scratch);
   if (T <= kEerPrivT) {
     constexpr int kWarps = kEerPrivThreads / 32;
-    const size_t smem = (size_t)(T + (T + 1) * (1 + kWarps * 32)) * sizeof(unsigned);      // <= 34 KB
+    const size_t smem = (size_t)(T + (T + 1) * (1 + kWarps * 32)) * sizeof(unsigned);      // <= 134 KB
+    int rc = set_smem(threshold_counts_private_kernel, smem);
+    if (rc != GE2E_OK) return rc;
     long long blocks = (rows + kWarps - 1) / kWarps;
-    const long long cap = (long long)kSms * (T <= 50 ? 8 : 6);  // resident blocks per SM by shared memory
+    const long long cap = (long long)kSms * (smem <= 110 * 1024 ? 2 : 1);   // resident blocks per SM by shared memory
     if (blocks > cap) blocks = cap;
     threshold_counts_private_kernel<<<(unsigned)blocks, kEerPrivThreads, smem, st>>>(sim, rows, N, M, thresholds, T, hist,
                                                                                      accept_all, accept_own);
@@ -1982,7 +1994,8 @@ int simt_threshold_counts(const float* sim, int N, int M, const float* threshold
     long long blocks = (rows + kEerThreads / 32 - 1) / (kEerThreads / 32);
     const long long cap = (long long)kSms * 8;                 // 8 resident blocks of 256 threads per SM
     if (blocks > cap) blocks = cap;
-    const size_t smem = (size_t)(T + 2 * (T + 1)) * sizeof(unsigned);
+    // the last block re-uses the dynamic shared memory for 2 (T + 1) 64-bit histogram entries
+    const size_t smem = std::max((size_t)(T + 2 * (T + 1)) * sizeof(unsigned), (size_t)2 * (T + 1) * sizeof(unsigned long long));
     threshold_counts_kernel<<<(unsigned)blocks, kEerThreads, smem, st>>>(sim, total, N, M, thresholds, T, hist, accept_all,
                                                                          accept_own);
   }
