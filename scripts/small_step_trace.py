@@ -3,6 +3,7 @@ import os
 import sys
 
 os.environ["GE2E_SMALL_STOP"] = "99"
+os.environ.setdefault("GE2E_SMALL_STEP", "2")        # trace every supported shape, not only the selected ones
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1498,7 +1498,10 @@ __device__ __forceinline__ float4 ld4_cg(const float* row, int col, int D, bool 
   return v;
 }
 
-template <int VARIANT>
+// MR = M rounded up to a multiple of 4: the cosine block's loops over the speaker's rows are fully
+// unrolled without predicates (rows M..MR-1 of the staged e_hat are zero), so the shared-memory loads of
+// all rows are issued together instead of one load -> use chain per row.
+template <int VARIANT, int MR>
 __global__ void __launch_bounds__(kThreads, 1)
 small_step_kernel(const SmallParams p) {
   extern __shared__ __align__(16) float smem[];
@@ -1508,8 +1511,8 @@ small_step_kernel(const SmallParams p) {
   const int Np = (N + 3) & ~3;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   float* sA = smem;                                   // (2M + 2) Dp: prep_body, later finalize_body
-  float* sEh = sA + (size_t)(2 * M + 2) * Dp;         // [M][Dp] e_hat of this speaker
-  float* sC = sEh + (size_t)M * Dp;                   // [N][Dp] all c_hat
+  float* sEh = sA + (size_t)(2 * M + 2) * Dp;         // [MR][Dp] e_hat of this speaker, rows >= M zero
+  float* sC = sEh + (size_t)MR * Dp;                  // [N][Dp] all c_hat
   float* sG = sC + (size_t)N * Dp;                    // [M][Np] w * G, zero on the own-speaker column
   float* sCos = sG + (size_t)M * Np;                  // [M][Np] cos + eps
   pdl_wait();
@@ -1539,33 +1542,36 @@ small_step_kernel(const SmallParams p) {
     const int k = v / (Dp >> 2), col = (v % (Dp >> 2)) << 2;
     *reinterpret_cast<float4*>(&sC[(size_t)k * Dp + col]) = ld4_cg(p.c_hat + (size_t)k * D, col, D, vec_c);
   }
-  for (int v = tid; v < M * (Dp >> 2); v += kThreads) {
+  for (int v = tid; v < MR * (Dp >> 2); v += kThreads) {
     const int i = v / (Dp >> 2), col = (v % (Dp >> 2)) << 2;
-    *reinterpret_cast<float4*>(&sEh[(size_t)i * Dp + col]) = ld4_plain(p.e_hat + ((size_t)j * M + i) * D, col, D, vec_e);
+    *reinterpret_cast<float4*>(&sEh[(size_t)i * Dp + col]) =
+        i < M ? ld4_plain(p.e_hat + ((size_t)j * M + i) * D, col, D, vec_e) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (tid < M) s_cd[tid] = p.cos_diag[(size_t)j * M + tid];
   __syncthreads();
   GE2E_SMALL_STAMP(3);
   for (int k = wid; k < N; k += kWarps) {
-    // all M dot products of centroid k at once: independent chains instead of M serial reductions
-    float dots[kSmallMaxM];
+    // all MR dot products of centroid k at once: independent chains, loads of every row issued together
+    float dots[MR];
 #pragma unroll
-    for (int i = 0; i < kSmallMaxM; ++i) dots[i] = 0.f;
+    for (int i = 0; i < MR; ++i) dots[i] = 0.f;
     for (int d = lane << 2; d < Dp; d += 128) {
       const float4 c = *reinterpret_cast<const float4*>(&sC[(size_t)k * Dp + d]);
+      float4 e[MR];
 #pragma unroll
-      for (int i = 0; i < kSmallMaxM; ++i)
-        if (i < M) dots[i] += dot4(*reinterpret_cast<const float4*>(&sEh[(size_t)i * Dp + d]), c);
+      for (int i = 0; i < MR; ++i) e[i] = *reinterpret_cast<const float4*>(&sEh[(size_t)i * Dp + d]);
+#pragma unroll
+      for (int i = 0; i < MR; ++i) dots[i] += dot4(e[i], c);
     }
-    // butterfly stages interleaved over the rows (a warp_sum per row would run 16 x 5 dependent shuffles)
+    // butterfly stages interleaved over the rows (a warp_sum per row would run MR x 5 dependent shuffles)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-      for (int i = 0; i < kSmallMaxM; ++i) dots[i] += __shfl_xor_sync(0xffffffffu, dots[i], o);
+      for (int i = 0; i < MR; ++i) dots[i] += __shfl_xor_sync(0xffffffffu, dots[i], o);
     }
     if (lane == 0) {
 #pragma unroll
-      for (int i = 0; i < kSmallMaxM; ++i)
+      for (int i = 0; i < MR; ++i)
         if (i < M) sCos[i * Np + k] = ((k == j) ? s_cd[i] : dots[i]) + eps;         // s3:78-79
     }
   }
@@ -1730,8 +1736,8 @@ small_step_kernel(const SmallParams p) {
 
 
 size_t small_smem_bytes(int N, int M, int D) {
-  const int Dp = (D + 3) & ~3, Np = (N + 3) & ~3;
-  return ((size_t)(3 * M + 2) * Dp + (size_t)N * Dp + (size_t)2 * M * Np) * sizeof(float);
+  const int Dp = (D + 3) & ~3, Np = (N + 3) & ~3, MR = (M + 3) & ~3;
+  return ((size_t)(2 * M + 2 + MR) * Dp + (size_t)N * Dp + (size_t)2 * M * Np) * sizeof(float);
 }
 
 }  // namespace
@@ -1762,15 +1768,21 @@ int simt_small_step(const float* E, const int32_t* row_index, int N, int M, int 
   p.ctr = reinterpret_cast<unsigned*>(workspace);
   p.part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kSmallHeaderBytes);
   const size_t smem = small_smem_bytes(N, M, D);
+#define GE2E_SMALL_LAUNCH(V, R)                                                                   \
+  do {                                                                                            \
+    int rc = set_smem(small_step_kernel<V, R>, smem);                                             \
+    if (rc != GE2E_OK) return rc;                                                                 \
+    launch_pdl(small_step_kernel<V, R>, dim3(N), dim3(kThreads), smem, st, true, p);              \
+  } while (0)
+  const int mr = (M + 3) & ~3;
   if (variant == GE2E_SOFTMAX) {
-    int rc = set_smem(small_step_kernel<GE2E_SOFTMAX>, smem);
-    if (rc != GE2E_OK) return rc;
-    launch_pdl(small_step_kernel<GE2E_SOFTMAX>, dim3(N), dim3(kThreads), smem, st, true, p);
+    if (mr == 4) GE2E_SMALL_LAUNCH(GE2E_SOFTMAX, 4); else if (mr == 8) GE2E_SMALL_LAUNCH(GE2E_SOFTMAX, 8);
+    else if (mr == 12) GE2E_SMALL_LAUNCH(GE2E_SOFTMAX, 12); else GE2E_SMALL_LAUNCH(GE2E_SOFTMAX, 16);
   } else {
-    int rc = set_smem(small_step_kernel<GE2E_CONTRAST>, smem);
-    if (rc != GE2E_OK) return rc;
-    launch_pdl(small_step_kernel<GE2E_CONTRAST>, dim3(N), dim3(kThreads), smem, st, true, p);
+    if (mr == 4) GE2E_SMALL_LAUNCH(GE2E_CONTRAST, 4); else if (mr == 8) GE2E_SMALL_LAUNCH(GE2E_CONTRAST, 8);
+    else if (mr == 12) GE2E_SMALL_LAUNCH(GE2E_CONTRAST, 12); else GE2E_SMALL_LAUNCH(GE2E_CONTRAST, 16);
   }
+#undef GE2E_SMALL_LAUNCH
   GE2E_LAUNCHED();
   return GE2E_OK;
 }
