@@ -160,17 +160,17 @@ int ge2e_b200_scale_bias_sgd(float* w, float* b, float* dw, float* db, float max
  * self.ge2e_loss(embeddings); loss.backward()`): ge2e_b200_forward_indexed followed by
  * ge2e_b200_backward_indexed with the same buffers (row_index nullable; accum[0] = loss;
  * dwdb_accum[1] = dw, dwdb_accum[2] = db; grad_out = device scalar, the upstream gradient).
- * Small batches -- N <= 16 speakers, M <= 16, D <= 256, e.g. the reference's test shape 4 x 8, where
- * five dependent launches are pure latency -- run as ONE kernel (the kernel itself supports N <= 128;
- * at N = 64 it is no faster than the pipeline and is not selected, see ge2e_b200_debug_small_step):
+ * Batches of the reference's own size -- N <= 64 speakers, M <= 16, D <= 256, i.e. its training
+ * (64 x 10) and test (4 x 8) shapes, where five dependent launches are mostly latency -- run as ONE
+ * kernel (the kernel itself supports N <= 128, see ge2e_b200_debug_small_step):
  * one CTA per speaker, every stage separated by grid-wide barriers (all CTAs are co-resident),
  * centroid gradients exchanged through the workspace in a fixed order (deterministic).  Those shapes
  * need ge2e_b200_step_workspace_bytes() bytes of workspace (>= ge2e_b200_workspace_bytes()); only its
  * first 256 bytes have to be zero on entry and are zero again on exit, the rest is scratch.
  * ge2e_b200_step_launches() = 1 when the single-kernel path is taken for the shape, else 0. */
 size_t ge2e_b200_step_workspace_bytes(int N, int M, int D, int variant, int precision);
-/* Debug / tests: which shapes take the single-kernel step.  0 = none, 1 = those where it beats the
- * pipeline (N <= 16; default), 2 = every shape the kernel supports (N <= 128, M <= 16, D <= 256).
+/* Debug / tests: which shapes take the single-kernel step.  0 = none, 1 = those where it was measured
+ * faster than the pipeline (N <= 64; default), 2 = every shape the kernel supports (N <= 128, M <= 16, D <= 256).
  * Initial value: env GE2E_SMALL_STEP, else 1.  Query sizes / launches AFTER setting it. */
 void ge2e_b200_debug_small_step(int mode);
 int ge2e_b200_step_launches(int N, int M, int D, int variant, int precision);

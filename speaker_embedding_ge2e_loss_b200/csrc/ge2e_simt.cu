@@ -1439,11 +1439,11 @@ int simt_bwd_finalize(const float* E, const int32_t* row_index, const float* dE_
 // ------------------------------------------------------------------------------------------
 namespace {
 
-// Up to kSmallMaxN speakers the kernel is correct (tested to 128); it is SELECTED only up to
-// kSmallPickN: one CTA per speaker serialises the speaker's M x N block, and at N = 64 (cfg2) the single
-// kernel takes as long as the five-kernel pipeline (55 us, stage timeline: scripts/small_step_trace.py),
-// while at the reference's test shape (N = 4, M = 8) it halves the step (37 -> 18 us).
-constexpr int kSmallMaxN = 128, kSmallMaxM = 16, kSmallMaxD = 256, kSmallPickN = 16;
+// Up to kSmallMaxN speakers the kernel is correct (tested to 128); it is SELECTED up to kSmallPickN:
+// one CTA per speaker serialises the speaker's M x N block, so its advantage over the five-kernel
+// pipeline shrinks with N -- 37 -> 18 us at the reference's test shape (N = 4, M = 8), 53 -> 41 us at its
+// training shape (cfg2, N = 64, M = 10; stage timeline: scripts/small_step_trace.py); not measured beyond.
+constexpr int kSmallMaxN = 128, kSmallMaxM = 16, kSmallMaxD = 256, kSmallPickN = 64;
 constexpr size_t kSmallHeaderBytes = 256;
 
 struct SmallParams {
@@ -1512,8 +1512,9 @@ small_step_kernel(const SmallParams p) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   float* sA = smem;                                   // (2M + 2) Dp: prep_body, later finalize_body
   float* sEh = sA + (size_t)(2 * M + 2) * Dp;         // [MR][Dp] e_hat of this speaker, rows >= M zero
-  float* sC = sEh + (size_t)MR * Dp;                  // [N][Dp] all c_hat
-  float* sG = sC + (size_t)N * Dp;                    // [M][Np] w * G, zero on the own-speaker column
+  const int Ds = Dp + 4;                              // row stride of sC: lanes reading different rows hit different banks
+  float* sC = sEh + (size_t)MR * Dp;                  // [N][Ds] all c_hat
+  float* sG = sC + (size_t)N * Ds;                    // [M][Np] w * G, zero on the own-speaker column
   float* sCos = sG + (size_t)M * Np;                  // [M][Np] cos + eps
   pdl_wait();
   pdl_trigger();
@@ -1540,7 +1541,7 @@ small_step_kernel(const SmallParams p) {
   const bool vec_c = is_vec(p.c_hat, D), vec_e = is_vec(p.e_hat, D);
   for (int v = tid; v < N * (Dp >> 2); v += kThreads) {
     const int k = v / (Dp >> 2), col = (v % (Dp >> 2)) << 2;
-    *reinterpret_cast<float4*>(&sC[(size_t)k * Dp + col]) = ld4_cg(p.c_hat + (size_t)k * D, col, D, vec_c);
+    *reinterpret_cast<float4*>(&sC[(size_t)k * Ds + col]) = ld4_cg(p.c_hat + (size_t)k * D, col, D, vec_c);
   }
   for (int v = tid; v < MR * (Dp >> 2); v += kThreads) {
     const int i = v / (Dp >> 2), col = (v % (Dp >> 2)) << 2;
@@ -1550,29 +1551,26 @@ small_step_kernel(const SmallParams p) {
   if (tid < M) s_cd[tid] = p.cos_diag[(size_t)j * M + tid];
   __syncthreads();
   GE2E_SMALL_STAMP(3);
-  for (int k = wid; k < N; k += kWarps) {
-    // all MR dot products of centroid k at once: independent chains, loads of every row issued together
-    float dots[MR];
-#pragma unroll
-    for (int i = 0; i < MR; ++i) dots[i] = 0.f;
-    for (int d = lane << 2; d < Dp; d += 128) {
-      const float4 c = *reinterpret_cast<const float4*>(&sC[(size_t)k * Dp + d]);
-      float4 e[MR];
-#pragma unroll
-      for (int i = 0; i < MR; ++i) e[i] = *reinterpret_cast<const float4*>(&sEh[(size_t)i * Dp + d]);
-#pragma unroll
-      for (int i = 0; i < MR; ++i) dots[i] += dot4(e[i], c);
-    }
-    // butterfly stages interleaved over the rows (a warp_sum per row would run MR x 5 dependent shuffles)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-      for (int i = 0; i < MR; ++i) dots[i] += __shfl_xor_sync(0xffffffffu, dots[i], o);
-    }
-    if (lane == 0) {
-#pragma unroll
-      for (int i = 0; i < MR; ++i)
-        if (i < M) sCos[i * Np + k] = ((k == j) ? s_cd[i] : dots[i]) + eps;         // s3:78-79
+  // lane <-> centroid (32 per pass), warp <-> pair of rows: every lane runs the whole dot product of its
+  // (row, centroid) pair, no shuffles; the two e_hat rows are broadcast loads, the centroid rows are
+  // conflict-free through the padded stride.  Rows M..MR-1 of sEh are zero (MR is even).
+  for (int i0 = 2 * wid; i0 < MR; i0 += 2 * kWarps) {
+    const float* e0 = sEh + (size_t)i0 * Dp;
+    const float* e1 = e0 + Dp;
+    for (int k0 = 0; k0 < N; k0 += 32) {
+      const int k = k0 + lane;
+      const float* c = sC + (size_t)(k < N ? k : N - 1) * Ds;
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
+      for (int d = 0; d < Dp; d += 4) {
+        const float4 cv = *reinterpret_cast<const float4*>(c + d);
+        a0 += dot4(*reinterpret_cast<const float4*>(e0 + d), cv);
+        a1 += dot4(*reinterpret_cast<const float4*>(e1 + d), cv);
+      }
+      if (k < N) {
+        if (i0 < M) sCos[i0 * Np + k] = ((k == j) ? s_cd[i0] : a0) + eps;              // s3:78-79
+        if (i0 + 1 < M) sCos[(i0 + 1) * Np + k] = ((k == j) ? s_cd[i0 + 1] : a1) + eps;
+      }
     }
   }
   __syncthreads();
@@ -1661,7 +1659,7 @@ small_step_kernel(const SmallParams p) {
 #pragma unroll 8
       for (int k = 0; k < N; ++k) {
         const float sgk = sG[i * Np + k];
-        const float4 c = *reinterpret_cast<const float4*>(&sC[(size_t)k * Dp + d]);
+        const float4 c = *reinterpret_cast<const float4*>(&sC[(size_t)k * Ds + d]);
         acc.x = fmaf(sgk, c.x, acc.x); acc.y = fmaf(sgk, c.y, acc.y); acc.z = fmaf(sgk, c.z, acc.z); acc.w = fmaf(sgk, c.w, acc.w);
       }
       st4(p.dE_hat + ((size_t)j * M + i) * D, d, D, vec_g, acc);
@@ -1737,7 +1735,7 @@ small_step_kernel(const SmallParams p) {
 
 size_t small_smem_bytes(int N, int M, int D) {
   const int Dp = (D + 3) & ~3, Np = (N + 3) & ~3, MR = (M + 3) & ~3;
-  return ((size_t)(2 * M + 2 + MR) * Dp + (size_t)N * Dp + (size_t)2 * M * Np) * sizeof(float);
+  return ((size_t)(2 * M + 2 + MR) * Dp + (size_t)N * (Dp + 4) + (size_t)2 * M * Np) * sizeof(float);
 }
 
 }  // namespace
