@@ -170,7 +170,7 @@ int ge2e_b200_scale_bias_sgd(float* w, float* b, float* dw, float* db, float max
  * ge2e_b200_step_launches() = 1 when the single-kernel path is taken for the shape, else 0. */
 size_t ge2e_b200_step_workspace_bytes(int N, int M, int D, int variant, int precision);
 /* Debug / tests: which shapes take the single-kernel step.  0 = none, 1 = those where it was measured
- * faster than the pipeline (N <= 64; default), 2 = every shape the kernel supports (N <= 128, M <= 16, D <= 256).
+ * faster than the pipeline (softmax N <= 64, contrast N <= 16; default), 2 = every shape the kernel supports (N <= 128, M <= 16, D <= 256).
  * Initial value: env GE2E_SMALL_STEP, else 1.  Query sizes / launches AFTER setting it. */
 void ge2e_b200_debug_small_step(int mode);
 int ge2e_b200_step_launches(int N, int M, int D, int variant, int precision);

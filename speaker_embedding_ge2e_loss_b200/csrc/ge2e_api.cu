@@ -323,7 +323,7 @@ void ge2e_b200_debug_small_step(int mode) { g_small_mode.store(mode < 0 || mode 
 
 static bool use_small_step(int N, int M, int D, int variant, int precision) {
   const int mode = small_step_mode();
-  if (mode == 0 || !(mode == 2 ? small_step_supported(N, M, D) : small_step_preferred(N, M, D))) return false;
+  if (mode == 0 || !(mode == 2 ? small_step_supported(N, M, D) : small_step_preferred(N, M, D, variant))) return false;
   return !(precision == GE2E_TF32 && tc_supported(N, N, M, D, variant));   // the tensor-core path keeps its shapes
 }
 

@@ -143,7 +143,7 @@ int simt_bwd_finalize(const float* E, const int32_t* row_index, const float* dE_
                       const float* grad_out, float* dE, bool pdl, cudaStream_t st);
 // fused single-kernel fwd+bwd step for small batches (ge2e_simt.cu)
 bool small_step_supported(int N, int M, int D);
-bool small_step_preferred(int N, int M, int D);   // supported AND faster than the pipeline
+bool small_step_preferred(int N, int M, int D, int variant);   // supported AND faster than the pipeline
 size_t small_step_workspace_bytes(int N, int M, int D);
 int simt_small_step(const float* E, const int32_t* row_index, int N, int M, int D, const float* w, const float* b,
                     float eps, int variant, const float* grad_out, float* e_hat, float* c_hat, float* cos_diag,

@@ -1443,7 +1443,7 @@ namespace {
 // one CTA per speaker serialises the speaker's M x N block, so its advantage over the five-kernel
 // pipeline shrinks with N -- 37 -> 18 us at the reference's test shape (N = 4, M = 8), 53 -> 41 us at its
 // training shape (cfg2, N = 64, M = 10; stage timeline: scripts/small_step_trace.py); not measured beyond.
-constexpr int kSmallMaxN = 128, kSmallMaxM = 16, kSmallMaxD = 256, kSmallPickN = 64;
+constexpr int kSmallMaxN = 128, kSmallMaxM = 16, kSmallMaxD = 256, kSmallPickN = 64, kSmallPickNContrast = 16;
 constexpr size_t kSmallHeaderBytes = 256;
 
 struct SmallParams {
@@ -1740,7 +1740,11 @@ size_t small_smem_bytes(int N, int M, int D) {
 
 }  // namespace
 
-bool small_step_preferred(int N, int M, int D) { return small_step_supported(N, M, D) && N <= kSmallPickN; }
+// (contrast: the pipeline's backward is a two-non-zeros-per-row gather / scatter, the single kernel runs the
+//  dense products; measured at cfg2: pipeline 27.6 us, single kernel 39.3 us -- so only tiny batches)
+bool small_step_preferred(int N, int M, int D, int variant) {
+  return small_step_supported(N, M, D) && N <= (variant == GE2E_CONTRAST ? kSmallPickNContrast : kSmallPickN);
+}
 
 bool small_step_supported(int N, int M, int D) {
   return N >= 1 && N <= kSmallMaxN && M >= 2 && M <= kSmallMaxM && D >= 1 && D <= kSmallMaxD &&
