@@ -49,6 +49,19 @@ def test_binding_prototypes_cover_header(pkg):
     assert sorted(_lib.PROTOTYPES) == declared_functions()
 
 
+def test_binding_prototypes_have_the_header_arity(pkg):
+    """Every ctypes prototype takes exactly as many arguments as the C declaration (a missing or extra
+    argument in the binding would silently shift every pointer after it)."""
+    from speaker_embedding_ge2e_loss_b200 import _lib
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    decls = dict(re.findall(r"\b(ge2e_b200_\w+)\s*\(([^)]*)\)", src))
+    assert set(decls) == set(_lib.PROTOTYPES)
+    for name, params in decls.items():
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert len(_lib.PROTOTYPES[name][1]) == n, f"{name}: header has {n} parameters, binding {len(_lib.PROTOTYPES[name][1])}"
+
+
 def test_host_side_status_codes(pkg):
     h = pkg.lib()
     assert h.ge2e_b200_version() >= 100
