@@ -46,7 +46,10 @@ enum ge2e_variant { GE2E_SOFTMAX = 0, GE2E_CONTRAST = 1 }; /* paper eq. (6) / eq
 
 /* GE2E_FP32: SIMT fp32 FMA everywhere (matches the reference to ~1e-6).
  * GE2E_TF32: similarity and gradient contractions on tcgen05 tensor cores with TF32
- *            operands / fp32 TMEM accumulators (stated tolerance 2e-3). */
+ *            operands / fp32 TMEM accumulators (stated tolerance 2e-3).  The softmax row sums are
+ *            taken against the fixed shift |w| + b (|cos| <= 1 bounds every logit): exact for
+ *            |w| <= 43; beyond that the smallest terms flush to zero (the reference's own
+ *            un-stabilised exp(S), s3:120, overflows beyond w + b = 88). */
 enum ge2e_precision { GE2E_FP32 = 0, GE2E_TF32 = 1 };
 
 int ge2e_b200_version(void);
@@ -59,30 +62,35 @@ unsigned long long ge2e_b200_launch_count(void);
  * GE2E_TF32 is a permission, not a demand: shapes the tensor-core path does not cover run on
  * the (more accurate) SIMT kernels.  Negative = bad variant / precision. */
 int ge2e_b200_path(int n_local, int n_total, int M, int D, int variant, int precision);
-/* Debug: while device_buf is non-NULL the tensor-core kernels stamp %globaltimer at their pipeline
- * events into device_buf[grid][3 roles (TMA, MMA, epilogue)][64]; NULL switches it off.
- * kernel: -1 = all, 0 = forward rows, 1 = backward rows. */
+/* Debug: while device_buf is non-NULL the tensor-core kernels run an instrumented instantiation that
+ * stamps %globaltimer at its pipeline events into device_buf[grid][3 roles (TMA, MMA, epilogue)][64];
+ * NULL switches it off.  kernel: -1 = all, 0 = forward-rows kernel, 1 = step kernel; | 0x100 = also one
+ * mark per ring stage in the MMA warp.  Results are unaffected. */
 void ge2e_b200_debug_trace(unsigned long long* device_buf, int kernel);
-/* Debug, TIMING ONLY: bitmask of kernels the library stops launching (1 prep, 2 forward rows,
- * 4|8 backward rows, 16 finalize); results are garbage while it is non-zero.  bench.py prices each
- * kernel in situ as (step time) - (step time without it).  Initial value: env GE2E_SKIP, else 0. */
-void ge2e_b200_debug_skip(int mask);
-/* Debug, host only (no GPU needed): the work schedule of the tensor-core backward for u_local
+/* Measurement: while device_buf is non-NULL every CTA of the tensor-core step kernel writes %globaltimer
+ * at its start and at its end into device_buf[CTA]{start, end} (two stores per CTA; the production
+ * kernel, results unaffected).  max(end) - min(start) is the kernel's duration inside a running step,
+ * which CUDA events cannot bracket inside a captured graph. */
+void ge2e_b200_debug_stamps(unsigned long long* device_buf);
+/* Debug, host only (no GPU needed): the work schedule of the tensor-core step kernel for u_local
  * utterance rows against n_total centroids on max_clusters co-resident clusters of cta_group CTAs.
- * Cluster c works on the pairs [de_begin[c], de_begin[c+1]) of the dE_hat list and [dc_begin[c],
- * dc_begin[c+1]) of the dC_hat list (pair = owner group * units_per_group + stream unit).  Arrays
- * need max_clusters + 1 entries.  units = {dE groups, units per dE group, dC groups, units per dC
- * group}; *de_partial = 1 when dE_hat groups are cut between clusters.  Returns the cluster count. */
-int ge2e_b200_debug_bwd_schedule(int u_local, int n_total, int cta_group, int max_clusters,
-                                 int* de_begin_host, int* dc_begin_host, int* de_partial_host,
-                                 int* units_host);
+ * Cluster c works on the pairs [de_begin[c], de_begin[c+1]) of the dE_hat list (pass 1) and [dc_begin[c],
+ * dc_begin[c+1]) of the dC_hat list (pass 2) (pair = owner group * units_per_group + stream unit).
+ * Arrays need max_clusters + 1 entries.  units = {dE groups, units per dE group, dC groups, units per dC
+ * group}; partial = {dE_hat groups are cut between clusters, dC_hat groups are cut}.  Returns the
+ * cluster count. */
+int ge2e_b200_debug_step_schedule(int u_local, int n_total, int cta_group, int max_clusters,
+                                  int* de_begin_host, int* dc_begin_host, int* partial_host,
+                                  int* units_host);
 /* GE2E_OK if the current CUDA device can run this library (sm_100), else GE2E_ERR_DEVICE. */
 int ge2e_b200_check_device(void);
 
-/* Scratch needed by ge2e_b200_fwd_rows / ge2e_b200_bwd_rows for this shape (may be 0).
- * The workspace must be ZERO-FILLED by the caller before its first use; every call leaves it
- * zero-filled again (stream-K bookkeeping and grid counters are reset by the last CTA that touches
- * them), so a buffer that is kept across calls is zeroed once.  One workspace serves one stream. */
+/* Scratch needed by ge2e_b200_fwd_rows / ge2e_b200_bwd_rows / ge2e_b200_step_rows for this shape (may
+ * be 0; 16-byte aligned).  The workspace must be ZERO-FILLED by the caller before its first use; every
+ * call leaves its bookkeeping zero-filled again (stream-K state and grid counters are reset by the last
+ * CTA that touches them; the rest is scratch), so a buffer that is kept across calls is zeroed once.
+ * One workspace serves one stream.  After a call that FAILED on the device (trap, launch error) zero it
+ * again before reuse. */
 size_t ge2e_b200_workspace_bytes(int n_local, int n_total, int M, int D, int variant,
                                  int precision);
 
@@ -113,23 +121,37 @@ int ge2e_b200_prep(const float* E, int n_local, int M, int D, int precision, flo
  *                      loses all digits on well-separated speakers); may be NULL for contrast
  *   loss_accum         += sum of the local rows' losses (zeroed by ge2e_b200_prep)
  *   per_row_out        optional [U_local] per-embedding loss (s3:121)
- *   sim_out            optional [U_local, n_total] cos + eps (what get_cos_sim returns)   */
+ *   sim_out            optional [U_local, n_total] cos + eps (what get_cos_sim returns)
+ *   dE_hat, row_scale  optional, both or neither: "a backward will follow".  Where the softmax loss
+ *                      runs on tensor cores (ge2e_b200_path() == 1) the forward is then the rows pass
+ *                      of the step kernel: S is computed once, P = exp(S - (|w| + b)) feeds the row
+ *                      sums AND, from tensor memory, the contraction P . C_hat, so the forward leaves
+ *                        dE_hat[U_local, D]  UN-NORMALISED off-diagonal gradient rows
+ *                        row_scale[U_local]  w exp(|w| + b - lse_r): the true row is
+ *                                            g * row_scale[r] * dE_hat[r]   (applied by bwd_finalize)
+ *                      and ge2e_b200_bwd_rows has only the centroid pass left.  On every other path the
+ *                      two pointers are ignored (nothing is written).                                 */
 int ge2e_b200_fwd_rows(const float* e_hat, const float* c_hat_all, const float* cos_diag,
                        int n_local, int n_total, int spk_offset, int M, int D,
                        const float* w, const float* b, float eps, int variant, int precision,
                        float* row_stat, int32_t* row_kstar, float* row_aux, float* loss_accum,
-                       float* per_row_out, float* sim_out, void* workspace,
-                       size_t workspace_bytes, ge2e_stream_t stream);
+                       float* per_row_out, float* sim_out, float* dE_hat, float* row_scale,
+                       void* workspace, size_t workspace_bytes, ge2e_stream_t stream);
 
 /* Stage 3: gradient wrt the normalised operands, S recomputed on the fly (never stored).
  * Replaces the autograd graph of s3:57-79 / s3:114-127.
  *   dE_hat[U_local, D]         sum_{k != j} w G_rk c_hat_k          (off-diagonal part)
  *   dC_hat_partial[n_total, D] sum_{local r, k != j(r)} w G_rk e_hat_r  (zeroed inside;
  *                              reduce-scatter it across ranks when sharded)
- *   dwdb_accum[2]              += {dw, db} of the local rows (zeroed by ge2e_b200_prep as
- *                              accum+1)                                                  */
+ *   dwdb_accum[2]              = {dw, db} of the local rows (zeroed inside, then accumulated)
+ *   row_scale                  the forward's row_scale when ge2e_b200_fwd_rows was given dE_hat /
+ *                              row_scale on the tensor-core softmax path: dE_hat is then left as the
+ *                              forward wrote it and only dC_hat_partial, dw, db are produced.  NULL:
+ *                              dE_hat is computed here (on the SIMT kernels where the tensor-core
+ *                              forward did not prepare it).                                        */
 int ge2e_b200_bwd_rows(const float* e_hat, const float* c_hat_all, const float* cos_diag,
                        const float* row_stat, const int32_t* row_kstar, const float* row_aux,
+                       const float* row_scale,
                        int n_local, int n_total, int spk_offset, int M, int D, const float* w,
                        const float* b, float eps, int variant, int precision,
                        const float* grad_out, float* dE_hat, float* dC_hat_partial,
@@ -139,11 +161,30 @@ int ge2e_b200_bwd_rows(const float* e_hat, const float* c_hat_all, const float* 
 /* Stage 4 (per rank, local speakers): diagonal (leave-one-out) term, the three
  * normalisation Jacobians and the centroid fan-out.
  *   dC_hat_local[n_local, D]  this rank's rows of the (reduced) dC_hat
+ *   row_scale                 NULL, or the forward's row_scale (dE_hat rows are un-normalised, see
+ *                             ge2e_b200_fwd_rows): row r of dE_hat counts g * row_scale[r] times
  *   dE[U_local, D]            gradient wrt the raw embeddings                            */
 int ge2e_b200_bwd_finalize(const float* E, const float* dE_hat, const float* dC_hat_local,
                            const float* cos_diag, const float* row_stat, const float* row_aux,
-                           int n_local, int M, int D, const float* w, const float* b, float eps,
-                           int variant, const float* grad_out, float* dE, ge2e_stream_t stream);
+                           const float* row_scale, int n_local, int M, int D, const float* w,
+                           const float* b, float eps, int variant, const float* grad_out, float* dE,
+                           ge2e_stream_t stream);
+
+/* Stages 2 + 3 in one call, for a step whose forward and backward are issued together (a captured
+ * training step; the sharded step between its all-gather and its reduce-scatter):
+ * ge2e_b200_fwd_rows followed by ge2e_b200_bwd_rows with the same buffers.  Where the softmax loss runs
+ * on tensor cores this is ONE persistent kernel: rows pass (loss, row statistics, un-normalised dE_hat),
+ * a grid-wide barrier, centroid pass (dC_hat_partial, dw, db): 8 U N D issued flops for 6 U N D
+ * algorithmic, S never stored.
+ *   accum[4]   {loss, dw, db, -}: += (zeroed by ge2e_b200_prep, which must precede this call)
+ *   row_scale  [U_local] out: pass it to ge2e_b200_bwd_finalize when ge2e_b200_path() == 1 and the
+ *              variant is softmax, NULL otherwise                                              */
+int ge2e_b200_step_rows(const float* e_hat, const float* c_hat_all, const float* cos_diag, int n_local,
+                        int n_total, int spk_offset, int M, int D, const float* w, const float* b,
+                        float eps, int variant, int precision, const float* grad_out, float* row_stat,
+                        int32_t* row_kstar, float* row_aux, float* row_scale, float* accum,
+                        float* dE_hat, float* dC_hat_partial, void* workspace, size_t workspace_bytes,
+                        ge2e_stream_t stream);
 
 /* The trainer's post-loss tail for the two loss parameters, on the device (SURVEY 8(f) row 1;
  * replaces `torch.nn.utils.clip_grad_norm_(self.ge2e_loss.parameters(), 1.0)` and the loss
@@ -157,9 +198,9 @@ int ge2e_b200_scale_bias_sgd(float* w, float* b, float* dw, float* db, float max
                              float* total_norm, ge2e_stream_t stream);
 
 /* The whole step of the trainer in one call (s4_train_embed_model.py:196 + :200: `loss =
- * self.ge2e_loss(embeddings); loss.backward()`): ge2e_b200_forward_indexed followed by
- * ge2e_b200_backward_indexed with the same buffers (row_index nullable; accum[0] = loss;
- * dwdb_accum[1] = dw, dwdb_accum[2] = db; grad_out = device scalar, the upstream gradient).
+ * self.ge2e_loss(embeddings); loss.backward()`): ge2e_b200_prep_indexed, ge2e_b200_step_rows and
+ * ge2e_b200_bwd_finalize_indexed with the same buffers (row_index nullable; accum[0] = loss,
+ * accum[1] = dw, accum[2] = db; grad_out = device scalar, the upstream gradient).
  * Batches of the reference's own size -- N <= 64 speakers, M <= 16, D <= 256, i.e. its training
  * (64 x 10) and test (4 x 8) shapes, where five dependent launches are mostly latency -- run as ONE
  * kernel (the kernel itself supports N <= 128, see ge2e_b200_debug_small_step):
@@ -171,13 +212,13 @@ int ge2e_b200_scale_bias_sgd(float* w, float* b, float* dw, float* db, float max
 size_t ge2e_b200_step_workspace_bytes(int N, int M, int D, int variant, int precision);
 /* Debug / tests: which shapes take the single-kernel step.  0 = none, 1 = those where it was measured
  * faster than the pipeline (softmax N <= 64, contrast N <= 16; default), 2 = every shape the kernel supports (N <= 128, M <= 16, D <= 256).
- * Initial value: env GE2E_SMALL_STEP, else 1.  Query sizes / launches AFTER setting it. */
+ * Initial value 1.  Query sizes / launches AFTER setting it. */
 void ge2e_b200_debug_small_step(int mode);
 int ge2e_b200_step_launches(int N, int M, int D, int variant, int precision);
 int ge2e_b200_forward_backward(const float* E, const int32_t* row_index, int N, int M, int D, const float* w,
                                const float* b, float eps, int variant, int precision, const float* grad_out,
                                float* e_hat, float* c_hat, float* cos_diag, float* row_stat, int32_t* row_kstar,
-                               float* row_aux, float* accum, float* dE_hat, float* dC_hat, float* dwdb_accum,
+                               float* row_aux, float* row_scale, float* accum, float* dE_hat, float* dC_hat,
                                float* dE, void* workspace, size_t workspace_bytes, ge2e_stream_t stream);
 
 /* Batch assembly from a device-resident spectrogram bank (SURVEY 8(f) row 4;
@@ -228,18 +269,22 @@ int ge2e_b200_threshold_counts(const float* sim, int N, int M, const float* thre
 
 /* ---- single-device conveniences (n_local == n_total) ---------------------------------- */
 
-/* GE2ELoss.forward (s3:19-30): prep + fwd_rows.  loss = accum[0]. */
+/* GE2ELoss.forward (s3:19-30): prep + fwd_rows.  loss = accum[0].  dE_hat / row_scale: NULL for a
+ * forward that no backward follows, else buffers [N*M, D] / [N*M] to hand to ge2e_b200_backward (see
+ * ge2e_b200_fwd_rows). */
 int ge2e_b200_forward(const float* E, int N, int M, int D, const float* w, const float* b,
                       float eps, int variant, int precision, float* e_hat, float* c_hat,
                       float* cos_diag, float* row_stat, int32_t* row_kstar, float* row_aux,
-                      float* accum, void* workspace, size_t workspace_bytes, ge2e_stream_t stream);
+                      float* accum, float* dE_hat, float* row_scale, void* workspace,
+                      size_t workspace_bytes, ge2e_stream_t stream);
 
-/* loss.backward() (s4:200): bwd_rows + bwd_finalize.  dw = accum[1], db = accum[2]. */
+/* loss.backward() (s4:200): bwd_rows + bwd_finalize.  dw = accum[1], db = accum[2].  dE_hat /
+ * row_scale: the buffers the forward was given (row_scale NULL if it was given none). */
 int ge2e_b200_backward(const float* E, const float* e_hat, const float* c_hat,
                        const float* cos_diag, const float* row_stat, const int32_t* row_kstar,
-                       const float* row_aux, int N, int M, int D, const float* w, const float* b, float eps,
-                       int variant, int precision, const float* grad_out, float* dE_hat,
-                       float* dC_hat, float* accum, float* dE, void* workspace,
+                       const float* row_aux, const float* row_scale, int N, int M, int D, const float* w,
+                       const float* b, float eps, int variant, int precision, const float* grad_out,
+                       float* dE_hat, float* dC_hat, float* accum, float* dE, void* workspace,
                        size_t workspace_bytes, ge2e_stream_t stream);
 
 /* ---- row-indexed variants (the trainer's unperm gather) ------------- */
@@ -256,17 +301,19 @@ int ge2e_b200_prep_indexed(const float* E, const int32_t* row_index, int n_local
                            float* accum, ge2e_stream_t stream);
 int ge2e_b200_bwd_finalize_indexed(const float* E, const int32_t* row_index, const float* dE_hat,
                                    const float* dC_hat_local, const float* cos_diag,
-                                   const float* row_stat, const float* row_aux, int n_local, int M,
-                                   int D, const float* w, const float* b, float eps, int variant,
-                                   const float* grad_out, float* dE, ge2e_stream_t stream);
+                                   const float* row_stat, const float* row_aux, const float* row_scale,
+                                   int n_local, int M, int D, const float* w, const float* b, float eps,
+                                   int variant, const float* grad_out, float* dE, ge2e_stream_t stream);
 int ge2e_b200_forward_indexed(const float* E, const int32_t* row_index, int N, int M, int D,
                               const float* w, const float* b, float eps, int variant, int precision,
                               float* e_hat, float* c_hat, float* cos_diag, float* row_stat,
-                              int32_t* row_kstar, float* row_aux, float* accum, void* workspace,
-                              size_t workspace_bytes, ge2e_stream_t stream);
+                              int32_t* row_kstar, float* row_aux, float* accum, float* dE_hat,
+                              float* row_scale, void* workspace, size_t workspace_bytes,
+                              ge2e_stream_t stream);
 int ge2e_b200_backward_indexed(const float* E, const int32_t* row_index, const float* e_hat,
                                const float* c_hat, const float* cos_diag, const float* row_stat,
-                               const int32_t* row_kstar, const float* row_aux, int N, int M, int D,
+                               const int32_t* row_kstar, const float* row_aux, const float* row_scale,
+                               int N, int M, int D,
                                const float* w, const float* b, float eps, int variant, int precision,
                                const float* grad_out, float* dE_hat, float* dC_hat, float* accum,
                                float* dE, void* workspace, size_t workspace_bytes,

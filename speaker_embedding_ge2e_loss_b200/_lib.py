@@ -23,36 +23,40 @@ PROTOTYPES = {
     "ge2e_b200_launch_count": (C.c_ulonglong, []),
     "ge2e_b200_path": (C.c_int, [C.c_int] * 6),
     "ge2e_b200_debug_trace": (None, [C.c_void_p, C.c_int]),
-    "ge2e_b200_debug_skip": (None, [C.c_int]),
-    "ge2e_b200_debug_bwd_schedule": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
-                                               C.c_void_p, C.c_void_p]),
+    "ge2e_b200_debug_stamps": (None, [C.c_void_p]),
+    "ge2e_b200_debug_step_schedule": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_void_p]),
     "ge2e_b200_check_device": (C.c_int, []),
     "ge2e_b200_workspace_bytes": (C.c_size_t, [C.c_int] * 6),
     "ge2e_b200_prep": (C.c_int, [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p,
                                  _stream]),
     "ge2e_b200_fwd_rows": (C.c_int, [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      _f32p, _f32p, C.c_float, C.c_int, C.c_int, _f32p, _i32p, _f32p, _f32p,
-                                     _f32p, _f32p, C.c_void_p, C.c_size_t, _stream]),
-    "ge2e_b200_bwd_rows": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _i32p, _f32p, C.c_int, C.c_int, C.c_int,
+                                     _f32p, _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, _stream]),
+    "ge2e_b200_bwd_rows": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _i32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_int, _f32p, _f32p, C.c_float, C.c_int, C.c_int,
                                      _f32p, _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, _stream]),
-    "ge2e_b200_bwd_finalize": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int,
+    "ge2e_b200_bwd_finalize": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int,
                                          _f32p, _f32p, C.c_float, C.c_int, _f32p, _f32p, _stream]),
+    "ge2e_b200_step_rows": (C.c_int, [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p,
+                                      C.c_float, C.c_int, C.c_int, _f32p, _f32p, _i32p, _f32p, _f32p, _f32p, _f32p,
+                                      _f32p, C.c_void_p, C.c_size_t, _stream]),
     "ge2e_b200_forward": (C.c_int, [_f32p, C.c_int, C.c_int, C.c_int, _f32p, _f32p, C.c_float, C.c_int,
-                                    C.c_int, _f32p, _f32p, _f32p, _f32p, _i32p, _f32p, _f32p, C.c_void_p,
+                                    C.c_int, _f32p, _f32p, _f32p, _f32p, _i32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p,
                                     C.c_size_t, _stream]),
-    "ge2e_b200_backward": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _i32p, _f32p, C.c_int, C.c_int,
+    "ge2e_b200_backward": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _i32p, _f32p, _f32p, C.c_int, C.c_int,
                                      C.c_int, _f32p, _f32p, C.c_float, C.c_int, C.c_int, _f32p, _f32p,
                                      _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, _stream]),
     "ge2e_b200_prep_indexed": (C.c_int, [_f32p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p,
                                          _f32p, _stream]),
-    "ge2e_b200_bwd_finalize_indexed": (C.c_int, [_f32p, _i32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int,
-                                                 C.c_int, _f32p, _f32p, C.c_float, C.c_int, _f32p, _f32p, _stream]),
+    "ge2e_b200_bwd_finalize_indexed": (C.c_int, [_f32p, _i32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int,
+                                                 C.c_int, C.c_int, _f32p, _f32p, C.c_float, C.c_int, _f32p, _f32p,
+                                                 _stream]),
     "ge2e_b200_forward_indexed": (C.c_int, [_f32p, _i32p, C.c_int, C.c_int, C.c_int, _f32p, _f32p, C.c_float, C.c_int,
-                                            C.c_int, _f32p, _f32p, _f32p, _f32p, _i32p, _f32p, _f32p, C.c_void_p,
-                                            C.c_size_t, _stream]),
-    "ge2e_b200_backward_indexed": (C.c_int, [_f32p, _i32p, _f32p, _f32p, _f32p, _f32p, _i32p, _f32p, C.c_int, C.c_int,
-                                             C.c_int, _f32p, _f32p, C.c_float, C.c_int, C.c_int, _f32p, _f32p,
+                                            C.c_int, _f32p, _f32p, _f32p, _f32p, _i32p, _f32p, _f32p, _f32p, _f32p,
+                                            C.c_void_p, C.c_size_t, _stream]),
+    "ge2e_b200_backward_indexed": (C.c_int, [_f32p, _i32p, _f32p, _f32p, _f32p, _f32p, _i32p, _f32p, _f32p, C.c_int,
+                                             C.c_int, C.c_int, _f32p, _f32p, C.c_float, C.c_int, C.c_int, _f32p, _f32p,
                                              _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, _stream]),
     "ge2e_b200_scale_bias_sgd": (C.c_int, [_f32p, _f32p, _f32p, _f32p, C.c_float, C.c_float, _f32p, _stream]),
     "ge2e_b200_debug_small_step": (None, [C.c_int]),

@@ -11,17 +11,6 @@ static thread_local cudaError_t g_last_cuda_error = cudaSuccess;
 void set_cuda_error(cudaError_t e) { g_last_cuda_error = e; }
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
-static std::atomic<int> g_skip_mask{-1};
-int debug_skip_mask() {
-  int m = g_skip_mask.load(std::memory_order_relaxed);
-  if (m < 0) {
-    const char* e = getenv("GE2E_SKIP");
-    m = e ? atoi(e) : 0;
-    g_skip_mask.store(m, std::memory_order_relaxed);
-  }
-  return m;
-}
-void set_debug_skip_mask(int m) { g_skip_mask.store(m < 0 ? 0 : m, std::memory_order_relaxed); }
 }  // namespace ge2e
 
 using namespace ge2e;
@@ -67,13 +56,13 @@ unsigned long long ge2e_b200_launch_count(void) { return g_launches.load(std::me
 
 void ge2e_b200_debug_trace(unsigned long long* device_buf, int kernel) { tc_set_trace(device_buf, kernel); }
 
-void ge2e_b200_debug_skip(int mask) { set_debug_skip_mask(mask); }
+void ge2e_b200_debug_stamps(unsigned long long* device_buf) { tc_set_stamps(device_buf); }
 
-int ge2e_b200_debug_bwd_schedule(int u_local, int n_total, int cta_group, int max_clusters, int* de_begin_host,
-                                 int* dc_begin_host, int* de_partial_host, int* units_host) {
-  if (!de_begin_host || !dc_begin_host || !de_partial_host || !units_host) return GE2E_ERR_ARGUMENT;
-  return tc_debug_bwd_schedule(u_local, n_total, cta_group, max_clusters, de_begin_host, dc_begin_host,
-                               de_partial_host, units_host);
+int ge2e_b200_debug_step_schedule(int u_local, int n_total, int cta_group, int max_clusters, int* de_begin_host,
+                                  int* dc_begin_host, int* partial_host, int* units_host) {
+  if (!de_begin_host || !dc_begin_host || !partial_host || !units_host) return GE2E_ERR_ARGUMENT;
+  return tc_debug_step_schedule(u_local, n_total, cta_group, max_clusters, de_begin_host, dc_begin_host,
+                                partial_host, units_host);
 }
 
 int ge2e_b200_path(int n_local, int n_total, int M, int D, int variant, int precision) {
@@ -102,7 +91,6 @@ int ge2e_b200_prep_indexed(const float* E, const int32_t* row_index, int n_local
   int rc = check_shape(n_local, n_local, 0, M, D);
   if (rc != GE2E_OK) return rc;
   if ((rc = check_enum(GE2E_SOFTMAX, precision)) != GE2E_OK) return rc;
-  if (debug_skip_mask() & 1) return GE2E_OK;
   return simt_prep(E, row_index, n_local, M, D, precision == GE2E_TF32, e_hat, c_hat_local, cos_diag, accum,
                    (cudaStream_t)stream);
 }
@@ -116,8 +104,8 @@ static int fwd_rows_impl(const float* e_hat, const float* c_hat_all, const float
                        int n_local, int n_total, int spk_offset, int M, int D, const float* w,
                        const float* b, float eps, int variant, int precision, float* row_stat,
                        int32_t* row_kstar, float* row_aux, float* loss_accum, float* per_row_out,
-                       float* sim_out, void* workspace, size_t workspace_bytes, bool after_prep,
-                       ge2e_stream_t stream) {
+                       float* sim_out, float* dE_hat, float* row_scale, void* workspace, size_t workspace_bytes,
+                       bool after_prep, ge2e_stream_t stream) {
   if (!e_hat || !c_hat_all || !cos_diag || !w || !b || !row_stat || !loss_accum)
     return GE2E_ERR_ARGUMENT;
   int rc = check_shape(n_local, n_total, spk_offset, M, D);
@@ -126,13 +114,16 @@ static int fwd_rows_impl(const float* e_hat, const float* c_hat_all, const float
   if (variant == GE2E_CONTRAST && !row_kstar) return GE2E_ERR_ARGUMENT;
   if (variant == GE2E_SOFTMAX && !row_aux) return GE2E_ERR_ARGUMENT;
   RowsArgs a{e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, b, eps, variant};
-  if (debug_skip_mask() & 2) return GE2E_OK;
   if (precision == GE2E_TF32 && tc_supported(n_local, n_total, M, D, variant)) {
     // the tensor-core path never materialises S: sim_out is an fp32-path feature
     if (sim_out != nullptr) return GE2E_ERR_UNSUPPORTED;
     if (workspace_bytes < tc_workspace_bytes(n_local, n_total, M, D, variant) ||
         (workspace == nullptr && tc_workspace_bytes(n_local, n_total, M, D, variant) > 0))
       return GE2E_ERR_WORKSPACE;
+    // softmax with a backward to follow: the rows pass of the step kernel (loss + un-normalised dE_hat)
+    if (variant == GE2E_SOFTMAX && dE_hat != nullptr && row_scale != nullptr)
+      return tc_step(a, 1, nullptr, nullptr, nullptr, row_stat, row_aux, row_scale, loss_accum, per_row_out, dE_hat,
+                     nullptr, nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
     return tc_fwd_rows(a, row_stat, row_kstar, row_aux, loss_accum, per_row_out, workspace, workspace_bytes,
                        after_prep, (cudaStream_t)stream);
   }
@@ -144,16 +135,17 @@ int ge2e_b200_fwd_rows(const float* e_hat, const float* c_hat_all, const float* 
                        int n_local, int n_total, int spk_offset, int M, int D, const float* w,
                        const float* b, float eps, int variant, int precision, float* row_stat,
                        int32_t* row_kstar, float* row_aux, float* loss_accum, float* per_row_out,
-                       float* sim_out, void* workspace, size_t workspace_bytes, ge2e_stream_t stream) {
+                       float* sim_out, float* dE_hat, float* row_scale, void* workspace, size_t workspace_bytes,
+                       ge2e_stream_t stream) {
   return fwd_rows_impl(e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, b, eps, variant,
-                       precision, row_stat, row_kstar, row_aux, loss_accum, per_row_out, sim_out, workspace,
-                       workspace_bytes, false, stream);
+                       precision, row_stat, row_kstar, row_aux, loss_accum, per_row_out, sim_out, dE_hat, row_scale,
+                       workspace, workspace_bytes, false, stream);
 }
 
 int ge2e_b200_bwd_rows(const float* e_hat, const float* c_hat_all, const float* cos_diag,
                        const float* row_stat, const int32_t* row_kstar, const float* row_aux,
-                       int n_local, int n_total, int spk_offset, int M, int D, const float* w,
-                       const float* b, float eps,
+                       const float* row_scale, int n_local, int n_total, int spk_offset, int M, int D,
+                       const float* w, const float* b, float eps,
                        int variant, int precision, const float* grad_out, float* dE_hat,
                        float* dC_hat_partial, float* dwdb_accum, void* workspace,
                        size_t workspace_bytes, ge2e_stream_t stream) {
@@ -167,13 +159,15 @@ int ge2e_b200_bwd_rows(const float* e_hat, const float* c_hat_all, const float* 
   if (variant == GE2E_SOFTMAX && !row_aux) return GE2E_ERR_ARGUMENT;
   RowsArgs a{e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, b, eps, variant};
   // the contrast gradient is a 2-nonzeros-per-row gather/scatter: no contraction to put on
-  // tensor cores, so both precisions share the SIMT kernel.
-  if (precision == GE2E_TF32 && variant == GE2E_SOFTMAX && tc_supported(n_local, n_total, M, D, variant)) {
+  // tensor cores, so both precisions share the SIMT kernel.  Softmax on tensor cores: the forward's rows
+  // pass already left the un-normalised dE_hat (row_scale says so); only the centroid pass remains.
+  if (precision == GE2E_TF32 && variant == GE2E_SOFTMAX && row_scale != nullptr &&
+      tc_supported(n_local, n_total, M, D, variant)) {
     if (workspace_bytes < tc_workspace_bytes(n_local, n_total, M, D, variant) ||
         (workspace == nullptr && tc_workspace_bytes(n_local, n_total, M, D, variant) > 0))
       return GE2E_ERR_WORKSPACE;
-    return tc_bwd_rows(a, row_stat, row_kstar, row_aux, grad_out, dE_hat, dC_hat_partial, dwdb_accum,
-                       workspace, workspace_bytes, (cudaStream_t)stream);
+    return tc_step(a, 2, grad_out, row_stat, row_aux, nullptr, nullptr, nullptr, nullptr, nullptr, dE_hat,
+                   dC_hat_partial, dwdb_accum, workspace, workspace_bytes, (cudaStream_t)stream);
   }
   return simt_bwd_rows(a, row_stat, row_kstar, row_aux, grad_out, dE_hat, dC_hat_partial, dwdb_accum,
                        (cudaStream_t)stream);
@@ -181,7 +175,7 @@ int ge2e_b200_bwd_rows(const float* e_hat, const float* c_hat_all, const float* 
 
 static int bwd_finalize_impl(const float* E, const int32_t* row_index, const float* dE_hat, const float* dC_hat_local,
                            const float* cos_diag, const float* row_stat, const float* row_aux,
-                           int n_local, int M, int D, const float* w, const float* b, float eps,
+                           const float* row_scale, int n_local, int M, int D, const float* w, const float* b, float eps,
                            int variant, const float* grad_out, float* dE, bool pdl, ge2e_stream_t stream) {
   if (!E || !dE_hat || !dC_hat_local || !cos_diag || !row_stat || !w || !b || !grad_out || !dE)
     return GE2E_ERR_ARGUMENT;
@@ -189,26 +183,25 @@ static int bwd_finalize_impl(const float* E, const int32_t* row_index, const flo
   int rc = check_shape(n_local, n_local, 0, M, D);
   if (rc != GE2E_OK) return rc;
   if ((rc = check_enum(variant, GE2E_FP32)) != GE2E_OK) return rc;
-  if (debug_skip_mask() & 16) return GE2E_OK;
-  return simt_bwd_finalize(E, row_index, dE_hat, dC_hat_local, cos_diag, row_stat, row_aux, n_local, M, D, w, b, eps,
-                           variant, grad_out, dE, pdl, (cudaStream_t)stream);
+  return simt_bwd_finalize(E, row_index, dE_hat, dC_hat_local, cos_diag, row_stat, row_aux, row_scale, n_local, M, D, w,
+                           b, eps, variant, grad_out, dE, pdl, (cudaStream_t)stream);
 }
 
 int ge2e_b200_bwd_finalize_indexed(const float* E, const int32_t* row_index, const float* dE_hat,
                                    const float* dC_hat_local, const float* cos_diag, const float* row_stat,
-                                   const float* row_aux, int n_local, int M, int D, const float* w, const float* b,
-                                   float eps, int variant, const float* grad_out, float* dE,
-                                   ge2e_stream_t stream) {
-  return bwd_finalize_impl(E, row_index, dE_hat, dC_hat_local, cos_diag, row_stat, row_aux, n_local, M, D, w, b, eps,
-                           variant, grad_out, dE, true, stream);
+                                   const float* row_aux, const float* row_scale, int n_local, int M, int D,
+                                   const float* w, const float* b, float eps, int variant, const float* grad_out,
+                                   float* dE, ge2e_stream_t stream) {
+  return bwd_finalize_impl(E, row_index, dE_hat, dC_hat_local, cos_diag, row_stat, row_aux, row_scale, n_local, M, D, w,
+                           b, eps, variant, grad_out, dE, true, stream);
 }
 
 int ge2e_b200_bwd_finalize(const float* E, const float* dE_hat, const float* dC_hat_local,
                            const float* cos_diag, const float* row_stat, const float* row_aux,
-                           int n_local, int M, int D, const float* w, const float* b, float eps,
-                           int variant, const float* grad_out, float* dE, ge2e_stream_t stream) {
-  return bwd_finalize_impl(E, nullptr, dE_hat, dC_hat_local, cos_diag, row_stat, row_aux, n_local, M, D, w, b, eps,
-                           variant, grad_out, dE, true, stream);
+                           const float* row_scale, int n_local, int M, int D, const float* w, const float* b,
+                           float eps, int variant, const float* grad_out, float* dE, ge2e_stream_t stream) {
+  return bwd_finalize_impl(E, nullptr, dE_hat, dC_hat_local, cos_diag, row_stat, row_aux, row_scale, n_local, M, D, w,
+                           b, eps, variant, grad_out, dE, true, stream);
 }
 
 int ge2e_b200_gather_spans(const float* bank, const long long* src_off, int rows, long long span, int offsets_aligned,
@@ -255,10 +248,18 @@ int ge2e_b200_scale_bias_sgd(float* w, float* b, float* dw, float* db, float max
   return simt_scale_bias_sgd(w, b, dw, db, max_norm, lr, total_norm, true, (cudaStream_t)stream);
 }
 
+// true when (shape, variant, precision) runs the softmax step on tensor cores: there the forward's rows pass
+// leaves an UN-NORMALISED dE_hat plus row_scale, and the backward is the centroid pass alone
+static bool tc_softmax_step(int n_local, int n_total, int M, int D, int variant, int precision) {
+  return precision == GE2E_TF32 && variant == GE2E_SOFTMAX && n_local > 0 && n_total > 0 && M >= 2 && D > 0 &&
+         tc_supported(n_local, n_total, M, D, variant);
+}
+
 int ge2e_b200_forward_indexed(const float* E, const int32_t* row_index, int N, int M, int D, const float* w,
                               const float* b, float eps, int variant, int precision, float* e_hat, float* c_hat,
                               float* cos_diag, float* row_stat, int32_t* row_kstar, float* row_aux, float* accum,
-                              void* workspace, size_t workspace_bytes, ge2e_stream_t stream) {
+                              float* dE_hat, float* row_scale, void* workspace, size_t workspace_bytes,
+                              ge2e_stream_t stream) {
   if (!accum) return GE2E_ERR_ARGUMENT;
   int rc = check_enum(variant, precision);
   if (rc != GE2E_OK) return rc;
@@ -268,57 +269,78 @@ int ge2e_b200_forward_indexed(const float* E, const int32_t* row_index, int N, i
   rc = ge2e_b200_prep_indexed(E, row_index, N, M, D, precision, e_hat, c_hat, cos_diag, accum, stream);
   if (rc != GE2E_OK) return rc;
   return fwd_rows_impl(e_hat, c_hat, cos_diag, N, N, 0, M, D, w, b, eps, variant, precision, row_stat, row_kstar,
-                       row_aux, accum, nullptr, nullptr, workspace, workspace_bytes, tc, stream);
+                       row_aux, accum, nullptr, nullptr, dE_hat, row_scale, workspace, workspace_bytes, tc, stream);
 }
 
 int ge2e_b200_forward(const float* E, int N, int M, int D, const float* w, const float* b, float eps,
                       int variant, int precision, float* e_hat, float* c_hat, float* cos_diag,
-                      float* row_stat, int32_t* row_kstar, float* row_aux, float* accum, void* workspace,
-                      size_t workspace_bytes, ge2e_stream_t stream) {
+                      float* row_stat, int32_t* row_kstar, float* row_aux, float* accum, float* dE_hat,
+                      float* row_scale, void* workspace, size_t workspace_bytes, ge2e_stream_t stream) {
   return ge2e_b200_forward_indexed(E, nullptr, N, M, D, w, b, eps, variant, precision, e_hat, c_hat, cos_diag,
-                                   row_stat, row_kstar, row_aux, accum, workspace, workspace_bytes, stream);
+                                   row_stat, row_kstar, row_aux, accum, dE_hat, row_scale, workspace, workspace_bytes,
+                                   stream);
 }
 
 int ge2e_b200_backward_indexed(const float* E, const int32_t* row_index, const float* e_hat, const float* c_hat,
                                const float* cos_diag, const float* row_stat, const int32_t* row_kstar,
-                               const float* row_aux, int N, int M, int D, const float* w, const float* b, float eps,
-                               int variant, int precision, const float* grad_out, float* dE_hat, float* dC_hat,
-                               float* accum, float* dE, void* workspace, size_t workspace_bytes,
-                               ge2e_stream_t stream) {
+                               const float* row_aux, const float* row_scale, int N, int M, int D, const float* w,
+                               const float* b, float eps, int variant, int precision, const float* grad_out,
+                               float* dE_hat, float* dC_hat, float* accum, float* dE, void* workspace,
+                               size_t workspace_bytes, ge2e_stream_t stream) {
   if (!accum) return GE2E_ERR_ARGUMENT;
-  int rc = ge2e_b200_bwd_rows(e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, N, N, 0, M, D, w, b, eps,
+  // row_scale is meaningful only where the forward produced it
+  const float* scale = tc_softmax_step(N, N, M, D, variant, precision) ? row_scale : nullptr;
+  int rc = ge2e_b200_bwd_rows(e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, scale, N, N, 0, M, D, w, b, eps,
                               variant, precision, grad_out, dE_hat, dC_hat, accum + 1, workspace,
                               workspace_bytes, stream);
   if (rc != GE2E_OK) return rc;
   // the finalize kernel directly follows the dC_hat tensor-core kernel: programmatic launch
-  return bwd_finalize_impl(E, row_index, dE_hat, dC_hat, cos_diag, row_stat, row_aux, N, M, D, w, b, eps, variant,
+  return bwd_finalize_impl(E, row_index, dE_hat, dC_hat, cos_diag, row_stat, row_aux, scale, N, M, D, w, b, eps, variant,
                            grad_out, dE, true, stream);
 }
 
 int ge2e_b200_backward(const float* E, const float* e_hat, const float* c_hat, const float* cos_diag,
-                       const float* row_stat, const int32_t* row_kstar, const float* row_aux, int N,
-                       int M, int D, const float* w, const float* b, float eps, int variant, int precision,
+                       const float* row_stat, const int32_t* row_kstar, const float* row_aux, const float* row_scale,
+                       int N, int M, int D, const float* w, const float* b, float eps, int variant, int precision,
                        const float* grad_out, float* dE_hat, float* dC_hat, float* accum, float* dE,
                        void* workspace, size_t workspace_bytes, ge2e_stream_t stream) {
-  return ge2e_b200_backward_indexed(E, nullptr, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, N, M, D, w, b,
-                                    eps, variant, precision, grad_out, dE_hat, dC_hat, accum, dE, workspace,
+  return ge2e_b200_backward_indexed(E, nullptr, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, row_scale, N, M,
+                                    D, w, b, eps, variant, precision, grad_out, dE_hat, dC_hat, accum, dE, workspace,
                                     workspace_bytes, stream);
 }
 
-// ---- whole step in one call ---------------------------------------------------------------
-// 0 = never (A/B timing), 1 = where it is faster than the pipeline (default), 2 = every supported shape
-// (tests).  Initial value: env GE2E_SMALL_STEP, else 1.
-static std::atomic<int> g_small_mode{-1};
-static int small_step_mode() {
-  int m = g_small_mode.load(std::memory_order_relaxed);
-  if (m < 0) {
-    const char* e = getenv("GE2E_SMALL_STEP");
-    m = e ? atoi(e) : 1;
-    if (m < 0 || m > 2) m = 1;
-    g_small_mode.store(m, std::memory_order_relaxed);
+// ---- forward rows + backward rows in one call (what a captured step issues) -----------------
+int ge2e_b200_step_rows(const float* e_hat, const float* c_hat_all, const float* cos_diag, int n_local, int n_total,
+                        int spk_offset, int M, int D, const float* w, const float* b, float eps, int variant,
+                        int precision, const float* grad_out, float* row_stat, int32_t* row_kstar, float* row_aux,
+                        float* row_scale, float* accum, float* dE_hat, float* dC_hat_partial, void* workspace,
+                        size_t workspace_bytes, ge2e_stream_t stream) {
+  if (!e_hat || !c_hat_all || !cos_diag || !w || !b || !grad_out || !row_stat || !row_aux || !row_scale || !accum ||
+      !dE_hat || !dC_hat_partial)
+    return GE2E_ERR_ARGUMENT;
+  int rc = check_shape(n_local, n_total, spk_offset, M, D);
+  if (rc != GE2E_OK) return rc;
+  if ((rc = check_enum(variant, precision)) != GE2E_OK) return rc;
+  if (variant == GE2E_CONTRAST && !row_kstar) return GE2E_ERR_ARGUMENT;
+  if (tc_softmax_step(n_local, n_total, M, D, variant, precision)) {
+    // ONE launch: rows pass, grid-wide barrier, centroid pass ({loss, dw, db} += into accum: zeroed by prep)
+    RowsArgs a{e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, b, eps, variant};
+    return tc_step(a, 3, grad_out, nullptr, nullptr, row_stat, row_aux, row_scale, accum, nullptr, dE_hat,
+                   dC_hat_partial, accum + 1, workspace, workspace_bytes, (cudaStream_t)stream);
   }
-  return m;
+  rc = fwd_rows_impl(e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, b, eps, variant, precision,
+                     row_stat, row_kstar, row_aux, accum, nullptr, nullptr, nullptr, nullptr, workspace, workspace_bytes,
+                     true, stream);
+  if (rc != GE2E_OK) return rc;
+  return ge2e_b200_bwd_rows(e_hat, c_hat_all, cos_diag, row_stat, row_kstar, row_aux, nullptr, n_local, n_total,
+                            spk_offset, M, D, w, b, eps, variant, precision, grad_out, dE_hat, dC_hat_partial, accum + 1,
+                            workspace, workspace_bytes, stream);
 }
+
+// ---- whole step in one call ---------------------------------------------------------------
+// 0 = never (A/B timing), 1 = where it is faster than the pipeline (default), 2 = every supported shape (tests)
+static std::atomic<int> g_small_mode{1};
+static int small_step_mode() { return g_small_mode.load(std::memory_order_relaxed); }
 void ge2e_b200_debug_small_step(int mode) { g_small_mode.store(mode < 0 || mode > 2 ? 1 : mode, std::memory_order_relaxed); }
 
 static bool use_small_step(int N, int M, int D, int variant, int precision) {
@@ -341,27 +363,30 @@ int ge2e_b200_step_launches(int N, int M, int D, int variant, int precision) {
 int ge2e_b200_forward_backward(const float* E, const int32_t* row_index, int N, int M, int D, const float* w,
                                const float* b, float eps, int variant, int precision, const float* grad_out,
                                float* e_hat, float* c_hat, float* cos_diag, float* row_stat, int32_t* row_kstar,
-                               float* row_aux, float* accum, float* dE_hat, float* dC_hat, float* dwdb_accum,
+                               float* row_aux, float* row_scale, float* accum, float* dE_hat, float* dC_hat,
                                float* dE, void* workspace, size_t workspace_bytes, ge2e_stream_t stream) {
-  if (!E || !w || !b || !grad_out || !e_hat || !c_hat || !cos_diag || !row_stat || !row_aux || !accum || !dE_hat ||
-      !dC_hat || !dwdb_accum || !dE)
+  if (!E || !w || !b || !grad_out || !e_hat || !c_hat || !cos_diag || !row_stat || !row_aux || !row_scale || !accum ||
+      !dE_hat || !dC_hat || !dE)
     return GE2E_ERR_ARGUMENT;
   int rc = check_shape(N, N, 0, M, D);
   if (rc != GE2E_OK) return rc;
   if ((rc = check_enum(variant, precision)) != GE2E_OK) return rc;
-  if (use_small_step(N, M, D, variant, precision) && debug_skip_mask() == 0) {
+  if (use_small_step(N, M, D, variant, precision)) {
     if (!workspace || workspace_bytes < small_step_workspace_bytes(N, M, D)) return GE2E_ERR_WORKSPACE;
     if (variant == GE2E_CONTRAST && !row_kstar) return GE2E_ERR_ARGUMENT;
     return simt_small_step(E, row_index, N, M, D, w, b, eps, variant, grad_out, e_hat, c_hat, cos_diag, row_stat,
-                           row_kstar, row_aux, nullptr, accum, dE_hat, dC_hat, dwdb_accum + 1, dE, workspace,
+                           row_kstar, row_aux, nullptr, accum, dE_hat, dC_hat, accum + 1, dE, workspace,
                            (cudaStream_t)stream);
   }
-  rc = ge2e_b200_forward_indexed(E, row_index, N, M, D, w, b, eps, variant, precision, e_hat, c_hat, cos_diag,
-                                 row_stat, row_kstar, row_aux, accum, workspace, workspace_bytes, stream);
+  // prep (zeroes accum) -> rows: every kernel is launched programmatically under its predecessor's tail
+  rc = ge2e_b200_prep_indexed(E, row_index, N, M, D, precision, e_hat, c_hat, cos_diag, accum, stream);
   if (rc != GE2E_OK) return rc;
-  return ge2e_b200_backward_indexed(E, row_index, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, N, M, D, w, b,
-                                    eps, variant, precision, grad_out, dE_hat, dC_hat, dwdb_accum, dE, workspace,
-                                    workspace_bytes, stream);
+  rc = ge2e_b200_step_rows(e_hat, c_hat, cos_diag, N, N, 0, M, D, w, b, eps, variant, precision, grad_out, row_stat,
+                           row_kstar, row_aux, row_scale, accum, dE_hat, dC_hat, workspace, workspace_bytes, stream);
+  if (rc != GE2E_OK) return rc;
+  const float* scale = tc_softmax_step(N, N, M, D, variant, precision) ? row_scale : nullptr;
+  return bwd_finalize_impl(E, row_index, dE_hat, dC_hat, cos_diag, row_stat, row_aux, scale, N, M, D, w, b, eps, variant,
+                           grad_out, dE, true, stream);
 }
 
 int ge2e_b200_centroids(const float* E, int N, int M, int D, float* C, ge2e_stream_t stream) {

@@ -111,11 +111,6 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-// GE2E_SKIP (debug, timing only): bitmask of kernels NOT to launch -- 1 prep, 2 forward rows, 4 dE_hat,
-// 8 dC_hat, 16 finalize.  Results are garbage; scripts/stage_costs.py uses it to price each kernel in situ.
-int debug_skip_mask();
-void set_debug_skip_mask(int m);
-
 // ---- launchers implemented in ge2e_simt.cu ------------------------------------------------
 struct RowsArgs {
   const float* e_hat;      // [U_local, D]
@@ -138,6 +133,7 @@ int simt_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_k
                   float* dwdb_accum, cudaStream_t st);
 int simt_bwd_finalize(const float* E, const int32_t* row_index, const float* dE_hat, const float* dC_hat_local,
                       const float* cos_diag, const float* row_stat, const float* row_aux,
+                      const float* row_scale /* nullable: dE_hat row r is g * row_scale[r] * dE_hat[r] */,
                       int n_local, int M, int D,
                       const float* w, const float* b, float eps, int variant,
                       const float* grad_out, float* dE, bool pdl, cudaStream_t st);
@@ -171,14 +167,17 @@ int tail_bwd_rows(const float* dE, const float* E, const float* inv_norm, int U,
 // ---- launchers implemented in ge2e_tc.cu (tcgen05 / TMA / TMEM path) ----------------------
 bool tc_supported(int n_local, int n_total, int M, int D, int variant);
 void tc_set_trace(unsigned long long* device_buf, int mode);
-int tc_debug_bwd_schedule(int u_local, int n_total, int cg, int max_clusters, int* de_begin, int* dc_begin,
-                          int* de_partial, int* units);
+void tc_set_stamps(unsigned long long* device_buf);
+int tc_debug_step_schedule(int u_local, int n_total, int cg, int max_clusters, int* de_begin, int* dc_begin,
+                           int* partial, int* units);
 size_t tc_workspace_bytes(int n_local, int n_total, int M, int D, int variant);
 int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* row_aux,
                 float* loss_accum, float* per_row_out, void* ws, size_t ws_bytes, bool after_prep,
                 cudaStream_t st);
-int tc_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kstar,
-                const float* row_aux, const float* grad_out, float* dE_hat, float* dC_hat_partial, float* dwdb_accum,
-                void* ws, size_t ws_bytes, cudaStream_t st);
+// softmax step on tensor cores; phases: 1 = rows pass (loss, row statistics, un-normalised dE_hat + row_scale),
+// 2 = centroid pass (dC_hat_partial, {dw, db}), 3 = both in one launch
+int tc_step(const RowsArgs& a, int phases, const float* grad_out, const float* row_stat_in, const float* row_aux_in,
+            float* row_stat, float* row_aux, float* row_scale, float* loss_accum, float* per_row_out, float* dE_hat,
+            float* dC_hat_partial, float* dwdb_accum, void* ws, size_t ws_bytes, cudaStream_t st);
 
 }  // namespace ge2e

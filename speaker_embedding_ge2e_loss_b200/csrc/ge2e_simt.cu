@@ -691,7 +691,8 @@ contrast_bwd_kernel(const float* __restrict__ e_hat, const float* __restrict__ c
 // kernel reads what its own block has just written).
 __device__ __forceinline__ void finalize_body(const float* __restrict__ E, const float* dE_hat, const float* dC_hat,
                                               const float* cos_diag, const float* row_stat, const float* row_aux,
-                                              int j, int M, int D, int Dp, float w, float b, float g, float eps,
+                                              const float* row_scale, int j, int M, int D, int Dp, float w, float b,
+                                              float g, float eps,
                                               int variant, float* __restrict__ dE, const int32_t* __restrict__ idx,
                                               float* smem) {
   __shared__ float red[kWarps];
@@ -750,6 +751,8 @@ __device__ __forceinline__ void finalize_body(const float* __restrict__ E, const
     const int r = j * M + i;
     float ne2 = 0.f, nu2 = 0.f, eu = 0.f, eg = 0.f;
     const float* gh = dE_hat + (size_t)r * D;
+    // tensor-core softmax path: dE_hat holds un-normalised rows, the true row is g * row_scale[r] times it
+    const float gsc = row_scale != nullptr ? g * row_scale[r] : 1.f;
     for (int d = lane << 2; d < Dp; d += 128) {
       const float4 e = *reinterpret_cast<const float4*>(&sE[(size_t)i * Dp + d]);
       const float4 s = *reinterpret_cast<const float4*>(&sS[d]);
@@ -758,7 +761,7 @@ __device__ __forceinline__ void finalize_body(const float* __restrict__ E, const
       u.x = (s.x - e.x) / m1; u.y = (s.y - e.y) / m1; u.z = (s.z - e.z) / m1; u.w = (s.w - e.w) / m1;
       ne2 += dot4(e, e); nu2 += dot4(u, u); eu += dot4(e, u); eg += dot4(e, gv);
     }
-    ne2 = warp_sum(ne2); nu2 = warp_sum(nu2); eu = warp_sum(eu); eg = warp_sum(eg);
+    ne2 = warp_sum(ne2); nu2 = warp_sum(nu2); eu = warp_sum(eu); eg = warp_sum(eg) * gsc;
     const float ne = sqrtf(ne2), nu = sqrtf(nu2);
     const bool ok_e = ne >= kCosDelta, ok_u = nu >= kCosDelta;
     const float inv_ne = 1.f / fmaxf(ne, kCosDelta), inv_nu = 1.f / fmaxf(nu, kCosDelta);
@@ -786,7 +789,7 @@ __device__ __forceinline__ void finalize_body(const float* __restrict__ E, const
       for (int t = 0; t < 4; ++t) {
         const float eh = ev[t] * inv_ne;
         const float uh = ((sv[t] - ev[t]) / m1) * inv_nu;
-        const float deh = gg[t] + dd * uh;
+        const float deh = gg[t] * gsc + dd * uh;
         const float duh = dd * eh;
         de[t] = ok_e ? (deh - eh * proj_e) * inv_ne : deh * inv_ne;
         du[t] = ok_u ? (duh - uh * proj_u) * inv_nu : duh * inv_nu;
@@ -822,11 +825,12 @@ __device__ __forceinline__ void finalize_body(const float* __restrict__ E, const
 __global__ void __launch_bounds__(kThreads)
 finalize_kernel(const float* __restrict__ E, const float* __restrict__ dE_hat,
                 const float* __restrict__ dC_hat, const float* __restrict__ cos_diag,
-                const float* __restrict__ row_stat, const float* __restrict__ row_aux, int M, int D, int Dp,
+                const float* __restrict__ row_stat, const float* __restrict__ row_aux,
+                const float* __restrict__ row_scale, int M, int D, int Dp,
                 const float* __restrict__ wp, const float* __restrict__ bp, float eps, int variant,
                 const float* __restrict__ gp, float* __restrict__ dE, const int32_t* __restrict__ idx) {
   extern __shared__ __align__(16) float smem[];
-  finalize_body(E, dE_hat, dC_hat, cos_diag, row_stat, row_aux, blockIdx.x, M, D, Dp, __ldg(wp), __ldg(bp), __ldg(gp),
+  finalize_body(E, dE_hat, dC_hat, cos_diag, row_stat, row_aux, row_scale, blockIdx.x, M, D, Dp, __ldg(wp), __ldg(bp), __ldg(gp),
                 eps, variant, dE, idx, smem);
 }
 
@@ -841,7 +845,7 @@ template <int KCH>
 __global__ void __launch_bounds__(kPrepWarps * 32)
 finalize_warp_kernel(const float* __restrict__ E, const float* __restrict__ dE_hat,
                      const float* __restrict__ dC_hat, const float* __restrict__ cos_diag,
-                     const float* __restrict__ row_aux, int n_local, int M,
+                     const float* __restrict__ row_aux, const float* __restrict__ row_scale, int n_local, int M,
                      const float* __restrict__ wp, const float* __restrict__ bp, float eps, int variant,
                      const float* __restrict__ gp, float* __restrict__ dE, const int32_t* __restrict__ idx) {
   constexpr int D = KCH * 128;
@@ -944,12 +948,13 @@ finalize_warp_kernel(const float* __restrict__ E, const float* __restrict__ dE_h
           Gd = -g * sp * (1.f - sp);
         }
         const float dd = w * Gd;
-        const float proj_e = eg[r] * inv_ne + dd * cdv;             // e_hat . d e_hat
+        const float gsc = row_scale != nullptr ? g * __ldcg(row_scale + row) : 1.f;   // un-normalised dE_hat rows
+        const float proj_e = eg[r] * gsc * inv_ne + dd * cdv;       // e_hat . d e_hat
         const float proj_u = dd * cdv;                              // u_hat . d u_hat
         // d e_hat = gv + dd u_hat, d u_hat = dd e_hat; Jacobians of the two normalisations:
         //   de = (deh - e_hat proj_e) / |e|  ->  gv inv_ne + d (dd inv_nu inv_m1 inv_ne) - e (proj_e inv_ne^2)
         //   du = (duh - u_hat proj_u) / |u|  ->  e (dd inv_ne inv_nu) - d (proj_u inv_nu^2 inv_m1)
-        const float r_ag = inv_ne;
+        const float r_ag = inv_ne * gsc;
         const float r_ad = dd * inv_nu * inv_m1 * inv_ne;
         const float r_ae = ok_e ? -proj_e * inv_ne * inv_ne : 0.f;
         const float r_be = dd * inv_ne * inv_nu;
@@ -1002,7 +1007,7 @@ template <int KCH, int RR>
 __global__ void __launch_bounds__(kPrepWarps * 32)
 finalize_reg_kernel(const float* __restrict__ E, const float* __restrict__ dE_hat,
                     const float* __restrict__ dC_hat, const float* __restrict__ cos_diag,
-                    const float* __restrict__ row_aux, int n_local, int M,
+                    const float* __restrict__ row_aux, const float* __restrict__ row_scale, int n_local, int M,
                     const float* __restrict__ wp, const float* __restrict__ bp, float eps, int variant,
                     const float* __restrict__ gp, float* __restrict__ dE, const int32_t* __restrict__ idx) {
   constexpr int D = KCH * 128, R = RR;     // rows held in registers (M <= R <= 16)
@@ -1120,9 +1125,10 @@ finalize_reg_kernel(const float* __restrict__ E, const float* __restrict__ dE_ha
       Gd = -g * sp * (1.f - sp);
     }
     const float dd = w * Gd;
-    const float proj_e = t_eg * inv_ne + dd * cdv;                // e_hat . d e_hat
+    const float gsc = row_scale != nullptr ? g * __ldcg(row_scale + row) : 1.f;   // un-normalised dE_hat rows
+    const float proj_e = t_eg * gsc * inv_ne + dd * cdv;          // e_hat . d e_hat
     const float proj_u = dd * cdv;                                // u_hat . d u_hat
-    a_g = inv_ne;
+    a_g = inv_ne * gsc;
     a_d = dd * inv_nu * inv_m1 * inv_ne;
     a_e = ok_e ? -proj_e * inv_ne * inv_ne : 0.f;
     b_e = dd * inv_ne * inv_nu;
@@ -1307,20 +1313,21 @@ void launch_prep_warp(const float* E, const int32_t* idx, int n_local, int M, bo
 
 template <int KCH>
 void launch_finalize_warp(const float* E, const float* dE_hat, const float* dC_hat, const float* cos_diag,
-                          const float* row_aux, int n_local, int M, const float* w, const float* b, float eps,
+                          const float* row_aux, const float* row_scale, int n_local, int M, const float* w,
+                          const float* b, float eps,
                           int variant, const float* g, float* dE, const int32_t* idx, bool pdl, cudaStream_t st) {
   const int grid = (n_local + kPrepWarps - 1) / kPrepWarps;
   if (KCH <= 2 && M <= kRegRows) {
     constexpr int K2 = KCH <= 2 ? KCH : 1;
 #define GE2E_FIN_REG(RR)                                                                                     \
   launch_pdl(finalize_reg_kernel<K2, RR>, dim3(grid), dim3(kPrepWarps * 32), 0, st, pdl, E, dE_hat, dC_hat, cos_diag, \
-             row_aux, n_local, M, w, b, eps, variant, g, dE, idx)
+             row_aux, row_scale, n_local, M, w, b, eps, variant, g, dE, idx)
     if (M <= 4) GE2E_FIN_REG(4); else if (M <= 8) GE2E_FIN_REG(8); else if (M <= 12) GE2E_FIN_REG(12); else GE2E_FIN_REG(16);
 #undef GE2E_FIN_REG
     return;
   }
   launch_pdl(finalize_warp_kernel<KCH>, dim3(grid), dim3(kPrepWarps * 32), 0, st, pdl, E, dE_hat, dC_hat, cos_diag,
-             row_aux, n_local, M, w, b, eps, variant, g, dE, idx);
+             row_aux, row_scale, n_local, M, w, b, eps, variant, g, dE, idx);
 }
 
 int simt_prep(const float* E, const int32_t* row_index, int n_local, int M, int D, bool round_tf32_, float* e_hat,
@@ -1403,13 +1410,13 @@ int simt_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_k
 }
 
 int simt_bwd_finalize(const float* E, const int32_t* row_index, const float* dE_hat, const float* dC_hat_local,
-                      const float* cos_diag, const float* row_stat, const float* row_aux, int n_local, int M,
-                      int D, const float* w, const float* b, float eps, int variant,
+                      const float* cos_diag, const float* row_stat, const float* row_aux, const float* row_scale,
+                      int n_local, int M, int D, const float* w, const float* b, float eps, int variant,
                       const float* grad_out, float* dE, bool pdl, cudaStream_t st) {
   if (M <= 32 && warp_path_ok(D, {E, dE_hat, dC_hat_local, dE})) {
-    if (D == 128) launch_finalize_warp<1>(E, dE_hat, dC_hat_local, cos_diag, row_aux, n_local, M, w, b, eps, variant, grad_out, dE, row_index, pdl, st);
-    else if (D == 256) launch_finalize_warp<2>(E, dE_hat, dC_hat_local, cos_diag, row_aux, n_local, M, w, b, eps, variant, grad_out, dE, row_index, pdl, st);
-    else launch_finalize_warp<4>(E, dE_hat, dC_hat_local, cos_diag, row_aux, n_local, M, w, b, eps, variant, grad_out, dE, row_index, pdl, st);
+    if (D == 128) launch_finalize_warp<1>(E, dE_hat, dC_hat_local, cos_diag, row_aux, row_scale, n_local, M, w, b, eps, variant, grad_out, dE, row_index, pdl, st);
+    else if (D == 256) launch_finalize_warp<2>(E, dE_hat, dC_hat_local, cos_diag, row_aux, row_scale, n_local, M, w, b, eps, variant, grad_out, dE, row_index, pdl, st);
+    else launch_finalize_warp<4>(E, dE_hat, dC_hat_local, cos_diag, row_aux, row_scale, n_local, M, w, b, eps, variant, grad_out, dE, row_index, pdl, st);
     GE2E_LAUNCHED();
     return GE2E_OK;
   }
@@ -1418,7 +1425,7 @@ int simt_bwd_finalize(const float* E, const int32_t* row_index, const float* dE_
   if (smem > 200 * 1024) return GE2E_ERR_UNSUPPORTED;
   int rc = set_smem(finalize_kernel, smem);
   if (rc != GE2E_OK) return rc;
-  finalize_kernel<<<n_local, kThreads, smem, st>>>(E, dE_hat, dC_hat_local, cos_diag, row_stat, row_aux, M, D,
+  finalize_kernel<<<n_local, kThreads, smem, st>>>(E, dE_hat, dC_hat_local, cos_diag, row_stat, row_aux, row_scale, M, D,
                                                    Dp, w, b, eps, variant, grad_out, dE, row_index);
   GE2E_LAUNCHED();
   return GE2E_OK;
@@ -1721,7 +1728,7 @@ small_step_kernel(const SmallParams p) {
   __syncthreads();
   GE2E_SMALL_STAMP(9);
   if (p.stop == 7) break;
-  finalize_body(p.E, p.dE_hat, p.dC_hat, p.cos_diag, p.row_stat, p.row_aux, j, M, D, Dp, w, b, g, eps, VARIANT, p.dE,
+  finalize_body(p.E, p.dE_hat, p.dC_hat, p.cos_diag, p.row_stat, p.row_aux, nullptr, j, M, D, Dp, w, b, g, eps, VARIANT, p.dE,
                 p.idx, sA);
   } while (0);
   __syncthreads();
@@ -1765,8 +1772,12 @@ int simt_small_step(const float* E, const int32_t* row_index, int N, int M, int 
   p.e_hat = e_hat; p.c_hat = c_hat; p.cos_diag = cos_diag; p.row_stat = row_stat; p.row_kstar = row_kstar;
   p.row_aux = row_aux; p.per_row = per_row; p.loss_accum = loss_accum;
   p.dE_hat = dE_hat; p.dC_hat = dC_hat; p.dwdb = dwdb; p.dE = dE;
+#ifdef GE2E_DEBUG_BUILD      // scripts/small_step_trace.py builds its own library with -DGE2E_DEBUG_BUILD
   static const int stop = [] { const char* e = getenv("GE2E_SMALL_STOP"); return e ? atoi(e) : 0; }();
   p.stop = stop;
+#else
+  p.stop = 0;
+#endif
   p.ctr = reinterpret_cast<unsigned*>(workspace);
   p.part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kSmallHeaderBytes);
   const size_t smem = small_smem_bytes(N, M, D);

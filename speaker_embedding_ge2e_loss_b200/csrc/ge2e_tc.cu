@@ -1,7 +1,8 @@
 // tcgen05 / TMA / TMEM path of the GE2E loss (TF32 operands, fp32 accumulators in tensor memory).
 //
-// One warp-specialised persistent kernel, two instantiations: the forward rows and the whole
-// backward contraction (the tensor-core twin of ge2e_simt.cu's strip kernel).  An "owner" operand
+// One warp-specialised persistent kernel, two instantiations: the forward rows alone (contrast loss,
+// forward-only calls) and the whole softmax step -- forward rows fused with the dE_hat contraction,
+// then the dC_hat contraction (the tensor-core twin of ge2e_simt.cu's strip kernel).  An "owner" operand
 // tile X[128, D] stays resident in shared memory, a "stream" operand Y is pulled through a TMA
 // ring one work unit (128 rows) at a time:
 //
@@ -9,12 +10,18 @@
 //   FWD    epilogue: online log-sum-exp (softmax) / running arg-max (contrast) over T's columns;
 //          S = w (cos + eps) + b is never written anywhere (reference s3:64-79, s3:27, s3:114-127)
 //          n = 256 (two units per step) whenever two units are left in the CTA's range
-//   BWD    epilogue: G = w g (softmax(S) - onehot) with the leave-one-out diagonal masked,
-//          rounded to TF32 and written back over T in TMEM (n = 128);
-//   MMA2   Acc[128 x D] += G . Y_unit            (A from TMEM, B MN-major from smem)  -> TMEM
-//            DE segments: X = E_hat rows, Y = C_hat     -> dE_hat = (wG) C_hat
-//            DC segments: X = C_hat rows, Y = E_hat     -> dC_hat = (wG)^T E_hat
+//   STEP   two passes over S (n = 128), S computed ONCE per pass and never stored:
+//          pass 1 (DE segments: X = E_hat rows, Y = C_hat): epilogue P = exp2(S log2e - m) with the
+//            leave-one-out diagonal masked, m = |w| + b a FIXED shift (|cos| <= 1 bounds every logit,
+//            so partial sums from different clusters simply add); the row sums give the log-sum-exp
+//            (the forward's row loss) and P, rounded to TF32, is written back over T in TMEM;
+//            MMA2  Acc[128 x D] += P . Y_unit  (A from TMEM, B MN-major from smem) -> un-normalised
+//            dE_hat rows: the true row is g w exp(m - lse_r) times it (row_scale, applied by finalize)
+//          -- grid-wide barrier: every row sum is complete --
+//          pass 2 (DC segments: X = C_hat rows, Y = E_hat): epilogue G = w g softmax(S) with the own
+//            speaker's rows masked, written back over T; MMA2 Acc += G . Y_unit -> dC_hat = (wG)^T E_hat
 //          the accumulator leaves through shared memory and a TMA store / TMA reduce-add.
+//          Issued contraction work: 8 U N D (algorithmic 6: S is recomputed once, for pass 2).
 //
 // CG = 2 runs every MMA on a CTA pair (tcgen05 cta_group::2, UMMA M = 256): the two CTAs of a
 // cluster own two consecutive owner tiles and each fetches HALF of every stream operand, which
@@ -27,12 +34,11 @@
 //   FWD   the flat pair list is cut into equal contiguous ranges over the clusters (stream-K); a
 //         cluster whose range covers only part of an owner group publishes (max, sum) per row and
 //         the last cluster to finish that tile merges.
-//   BWD   both contractions in ONE launch.  dE_hat owner groups are short (n_total / 128 units):
-//         a cluster takes WHOLE groups (plain store, no zero-fill of dE_hat), and the long dC_hat
-//         groups are the divisible filler that balances the clusters; their partial accumulators
-//         are added into the zeroed dC_hat at the L2 (cp.reduce.async.bulk).  Shapes whose dE_hat
-//         groups are too coarse for that fall back to a flat cut of [dC pairs | dE pairs].
-//         The per-cluster ranges are computed on the host (make_bwd_sched) and passed by value.
+//   STEP  both passes in ONE launch, each cut evenly over the clusters: whole owner groups where
+//         that balances (plain store), else a flat cut whose partial accumulators are added into the
+//         zero-filled output at the L2 (cp.reduce.async.bulk).  The per-cluster ranges are computed on
+//         the host (make_step_sched) and passed by value.  The TMA and MMA warps run straight from
+//         pass 1 into pass 2 (their operands are inputs); only the epilogue waits at the barrier.
 //
 // Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
 // warps 4-11 = epilogue (TMEM lane quarter = warp % 4, column half = (warp - 4) / 4: two threads
@@ -71,7 +77,8 @@ constexpr int kMaxClusters = 160;     // >= SM count / cluster size
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
-enum { TC_FWD = 0, TC_BWD = 1 };
+enum { TC_FWD = 0, TC_STEP = 1 };
+enum { PASS_ROWS = 1, PASS_CENTROIDS = 2 };   // TcParams::phases
 enum { SEG_DE = 0, SEG_DC = 1 };      // index into the per-segment-kind arrays (FWD uses index 0)
 
 // barrier indices inside the shared barrier array
@@ -97,8 +104,8 @@ struct TmSet {
   CUtensorMap out[2];    // accumulator output box [128 rows][32 cols], 128B swizzle
 };
 
-// BWD: pair range [begin[c], begin[c + 1]) of cluster c in the dE_hat / dC_hat pair lists
-struct BwdSched {
+// STEP: pair range [begin[c], begin[c + 1]) of cluster c in the dE_hat (pass 1) / dC_hat (pass 2) pair lists
+struct StepSched {
   int de[kMaxClusters + 1];
   int dc[kMaxClusters + 1];
 };
@@ -110,9 +117,12 @@ struct TcParams {
   int OT[2], ST[2];           // owner tiles, stream units
   long long GP;               // FWD: owner groups * ST (group, stream unit) pairs
   const float* cos_diag;      // [U_local]
-  const float* row_stat;      // BWD: lse per local utterance row
-  const float* row_aux;       // BWD: q = 1 - p_jj per local utterance row
-  float* row_aux_out;         // FWD softmax
+  const float* row_stat;      // STEP, pass 2 alone: lse per local utterance row (written by an earlier launch)
+  const float* row_aux;       // STEP, pass 2 alone: q = 1 - p_jj per local utterance row
+  float* row_aux_out;         // FWD softmax / STEP pass 1
+  int phases;                 // STEP: PASS_ROWS | PASS_CENTROIDS
+  float* rowsum;              // STEP: [U_local] off-diagonal sums of P (workspace; zero-filled by the kernel)
+  float* row_scale_out;       // STEP pass 1: w exp(m - lse_r), the factor of the un-normalised dE_hat rows
   const float* w;
   const float* b;
   const float* grad_out;
@@ -127,12 +137,14 @@ struct TcParams {
   int maxseg;
   // BWD outputs (dE_hat / dC_hat go through the `out` tensor maps)
   float* dwdb;
-  float4* zero_base;          // BWD: dC_hat, zero-filled by the kernel itself before any partial sum lands
-  long long zero_n4;          //      (float4 count)
-  int* ctr;                   // BWD: {CTAs done zero-filling, CTAs done}: zero on entry, zero again on exit
+  float4* zero_base;          // STEP: dC_hat, zero-filled by the kernel itself before any partial sum lands
+  long long zero_n4;          //      (float4 count; 0 = nothing to clear)
+  float4* zero2_base;         // STEP: dE_hat when some owner group is cut between clusters
+  long long zero2_n4;
+  int* ctr;                   // STEP: {CTAs done zero-filling, CTAs done, CTAs done with pass 1}: zero on entry and exit
+  unsigned long long* stamps; // STEP, nullable: [CTA]{start, end} globaltimer stamps (in-situ kernel time)
   unsigned long long* trace;  // debug: [CTA][3 roles][kTraceEvents] globaltimer stamps, or nullptr
-  int dbg;                    // debug (GE2E_TC_DEBUG): 1 = no TMA for stream stages, 4 = epilogue skips the
-                              //   math (results are garbage), 8 = per-stage marks in the MMA warp's trace
+  int dbg;                    // debug instantiation only: 8 = per-stage marks in the MMA warp's trace
 };
 
 constexpr int kTraceEvents = 64;
@@ -155,7 +167,10 @@ struct SharedTail {
   uint64_t bars[BAR_COUNT];
   uint32_t tmem_base;
   int flag;
-  float red[2 * kEpiWarps];
+  union {
+    float red[2 * kEpiWarps];
+    float red3[3 * kEpiWarps];
+  };
   union {                                 // 1 KB either way: the budget above the ring is ~2 KB
     alignas(16) float lse_s[2][kUnit];    // DC segments: lse (log2 domain) of the current stream rows
     alignas(16) float2 xch[kTile];        // FWD: row state of the upper column half
@@ -192,7 +207,7 @@ struct Walk {
 
 template <int MODE, int VARIANT, int CG, bool DBG>
 __global__ void __launch_bounds__(kThreadsTc, 1)
-tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSched sched, const TcParams p) {
+tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepSched sched, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr bool kBwd = (MODE != TC_FWD);
   constexpr int kStageBytes = 32768 / CG;
@@ -251,18 +266,12 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
   if (CG > 1) cluster_sync_all();     // the peer's barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem = tail->tmem_base;
-  // Programmatic dependent launch: everything above overlapped the stream predecessor's tail.
-  //   FWD  reads what its predecessor (prep) wrote: wait, THEN let the successor go -- a successor that
-  //        starts early may therefore assume that everything before this kernel has completed.
-  //   BWD  its operands (e_hat, c_hat) were written two kernels back (see above), only the epilogue
-  //        needs the forward's row statistics: TMA producer and MMA warp start filling the pipeline
-  //        while the forward's slowest CTAs are still running; the epilogue warps wait (below).
-  if (!kBwd) {
-    pdl_wait();
-    pdl_trigger();
-  } else {
-    pdl_trigger();
-  }
+  // Programmatic dependent launch: everything above overlapped the stream predecessor's tail.  Both
+  // instantiations read what their predecessor (prep) wrote: wait, THEN let the successor go -- a
+  // successor that starts early may therefore assume that everything before this kernel has completed.
+  pdl_wait();
+  pdl_trigger();
+  if (kBwd && p.stamps != nullptr && tid == 0) p.stamps[2 * blockIdx.x] = globaltimer_ns();
 
   // ---- this cluster's work
   auto make_walk = [&]() {
@@ -272,12 +281,8 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
       wk.gp = (static_cast<long long>(cl) * p.GP) / NC;
       wk.end = (static_cast<long long>(cl + 1) * p.GP) / NC;
       wk.gp2 = wk.end2 = 0;
-    } else if ((cl & 1) == 0) {
-      // even clusters: dC_hat part first; odd clusters: dE_hat part first.  At any time half of the
-      // chip streams utterance rows (large, may spill the L2) and half streams centroids (small)
-      wk.kind = SEG_DC; wk.gp = sched.dc[cl]; wk.end = sched.dc[cl + 1];
-      wk.kind2 = SEG_DE; wk.gp2 = sched.de[cl]; wk.end2 = sched.de[cl + 1];
     } else {
+      // pass 1 (dE_hat segments), then pass 2 (dC_hat segments); a pass that is not in p.phases has empty ranges
       wk.kind = SEG_DE; wk.gp = sched.de[cl]; wk.end = sched.de[cl + 1];
       wk.kind2 = SEG_DC; wk.gp2 = sched.dc[cl]; wk.end2 = sched.dc[cl + 1];
     }
@@ -297,18 +302,14 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
       mbar_wait(bar(BAR_EMPTY + stage), phase ^ 1);
       if (elect_one()) {
         const uint32_t bytes = static_cast<uint32_t>(nslab * rows_cta * 128);
-        if (dbg & 1) {
-          if (leader) mbar_arrive(bar(BAR_FULL + stage));
-        } else {
-          if (leader) mbar_expect_tx(bar(BAR_FULL + stage), bytes * CG);
-          const uint32_t full = lbar(BAR_FULL + stage);
-          uint32_t dst = ring_smem + stage * kStageBytes;
-          for (int sl = 0; sl < nslab; ++sl)
-            for (int r = 0; r < rows_cta; r += kBoxRows, dst += kBoxRows * 128) {
-              if (CG == 1) tma_load_2d(dst, tm, (ks0 + sl) * kSlabCols, row0 + r, full);
-              else tma_load_2d_2cta(dst, tm, (ks0 + sl) * kSlabCols, row0 + cr * rows_cta + r, full);
-            }
-        }
+        if (leader) mbar_expect_tx(bar(BAR_FULL + stage), bytes * CG);
+        const uint32_t full = lbar(BAR_FULL + stage);
+        uint32_t dst = ring_smem + stage * kStageBytes;
+        for (int sl = 0; sl < nslab; ++sl)
+          for (int r = 0; r < rows_cta; r += kBoxRows, dst += kBoxRows * 128) {
+            if (CG == 1) tma_load_2d(dst, tm, (ks0 + sl) * kSlabCols, row0 + r, full);
+            else tma_load_2d_2cta(dst, tm, (ks0 + sl) * kSlabCols, row0 + cr * rows_cta + r, full);
+          }
       }
       __syncwarp();
       advance();
@@ -319,15 +320,11 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
       if (elect_one()) {
         const int slabs_c = kslabs / CG;
         const uint32_t bytes = static_cast<uint32_t>(slabs_c * kMma2Rows * 128);
-        if (dbg & 1) {
-          if (leader) mbar_arrive(bar(BAR_FULL + stage));
-        } else {
-          if (leader) mbar_expect_tx(bar(BAR_FULL + stage), bytes * CG);
-          const uint32_t full = lbar(BAR_FULL + stage);
-          const uint32_t dst = ring_smem + stage * kStageBytes;
-          if (CG == 1) tma_load_3d(dst, tm, 0, row0, 0, full);
-          else tma_load_3d_2cta(dst, tm, 0, row0, cr * slabs_c, full);
-        }
+        if (leader) mbar_expect_tx(bar(BAR_FULL + stage), bytes * CG);
+        const uint32_t full = lbar(BAR_FULL + stage);
+        const uint32_t dst = ring_smem + stage * kStageBytes;
+        if (CG == 1) tma_load_3d(dst, tm, 0, row0, 0, full);
+        else tma_load_3d_2cta(dst, tm, 0, row0, cr * slabs_c, full);
       }
       __syncwarp();
       advance();
@@ -487,14 +484,21 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
   } else if (warp >= kEpiWarp0) {
     // ===================================================================== epilogue
     const int ew = warp - kEpiWarp0;
+    const int et = tid - kEpiWarp0 * 32;             // thread index among the epilogue threads
     const int quarter = ew & 3, half = ew >> 2;      // TMEM lanes [32 q, 32 q + 32); column half h
     const int trow = quarter * 32 + lane;            // row inside the owner tile
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const float w = __ldg(p.w), b = __ldg(p.b), eps = p.eps;
     const float w2 = w * kLog2e, b2 = fmaf(w, eps, b) * kLog2e;   // log2-domain affine: S*log2e
     const float bb = fmaf(w, eps, b);
-    const float g = kBwd ? __ldg(p.grad_out) : 1.f;
+    const float g = (kBwd && p.grad_out != nullptr) ? __ldg(p.grad_out) : 1.f;
     const float wg = w * g;
+    // STEP, pass 1: every logit is bounded by |w| + (w eps + b) because |cos| <= 1, so the exponentials are
+    // taken against that FIXED shift (log2 domain: m2) instead of a running row maximum: P <= 1, partial row
+    // sums and partial accumulators of different clusters simply add, nothing is ever rescaled.  The
+    // smallest P is 2^(-2 |w| log2e), a normal fp32 number for |w| <= 43 (the reference's own exp(S) is
+    // un-stabilised, s3:120, and overflows beyond w + b = 88).
+    const float m2 = b2 + fabsf(w2), mx = m2 * kLn2, c0 = -fabsf(w2);
     float dw_acc = 0.f, db_acc = 0.f, loss_acc = 0.f;
     int it = 0;
     Tracer<DBG> tr((trow == 0 && half == 0) ? p.trace : nullptr, 2);
@@ -504,36 +508,86 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
     auto arrive_leader = [&](uint32_t addr) {
       if (CG == 1) mbar_arrive(addr); else mbar_arrive_cluster(addr);
     };
-
-    bool zero_seen = false;      // (thread ew 0 / lane 0) every CTA has finished its share of the zero-fill
+    // spin until *ctr >= target (all CTAs of the persistent grid are co-resident); a counter that never
+    // gets there is a bug: trap after 2 s instead of hanging the GPU
+    auto spin_until = [&](const int* ctr, int target) {
+      unsigned long long t0 = 0;
+      for (unsigned spins = 0;; ++spins) {
+        int v;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        if (v >= target) break;
+        if ((spins & 1023u) == 1023u) {
+          const unsigned long long t = globaltimer_ns();
+          if (t0 == 0) t0 = t;
+          else if (t - t0 > 2000000000ull) __trap();
+        }
+      }
+    };
+    bool zero_seen = false;      // (thread et 0) every CTA has finished its share of the zero-fill
     auto wait_zero_fill = [&]() {
       if (zero_seen) return;
-      int v;
-      do {
-        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.ctr) : "memory");
-      } while (v < static_cast<int>(gridDim.x));
+      spin_until(p.ctr, static_cast<int>(gridDim.x));
       asm volatile("fence.proxy.async;" ::: "memory");    // the TMA reduce below is an async-proxy access
       zero_seen = true;
     };
     if (kBwd) {
-      // dC_hat (and {dw, db}) collect partial sums from many CTAs: zero them here instead of with
-      // memset nodes in front of the kernel.  Every CTA clears a slice while its pipeline fills and
-      // bumps ctr[0]; nobody adds before ctr[0] == gridDim.x (all CTAs are co-resident: persistent grid).
-      const int et = tid - kEpiWarp0 * 32;
-      const long long z0 = p.zero_n4 * blockIdx.x / gridDim.x, z1 = p.zero_n4 * (blockIdx.x + 1) / gridDim.x;
-      for (long long i = z0 + et; i < z1; i += kEpiThreads) p.zero_base[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (blockIdx.x == 0 && et < 2) p.dwdb[et] = 0.f;
+      // Outputs that collect partial sums from many CTAs (dC_hat; dE_hat when its owner groups are cut; the
+      // row sums) are zeroed here instead of with memset nodes in front of the kernel: every CTA clears a
+      // slice while its pipeline fills and bumps ctr[0]; nobody adds before ctr[0] == gridDim.x.
+      auto zfill = [&](float4* base, long long n4) {
+        const long long z0 = n4 * blockIdx.x / gridDim.x, z1 = n4 * (blockIdx.x + 1) / gridDim.x;
+        for (long long i = z0 + et; i < z1; i += kEpiThreads) base[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      if (p.zero_n4 > 0) zfill(p.zero_base, p.zero_n4);
+      if (p.zero2_n4 > 0) zfill(p.zero2_base, p.zero2_n4);
+      if (p.phases & PASS_ROWS) zfill(reinterpret_cast<float4*>(p.rowsum), (p.n_own[SEG_DE] + 3) / 4);
       __threadfence();
       named_bar_sync(1, kEpiThreads);
-      pdl_wait();      // row_stat / row_aux (read below) come from the forward kernel; the workspace
-                       // counters may have been zeroed by the kernel right before this one
       if (et == 0) atomicAdd(p.ctr, 1);
     }
+
+    // STEP: between the passes.  Grid-wide barrier (every row sum complete), then each CTA closes a slice
+    // of the rows: log-sum-exp, row loss, q = 1 - p_jj, the factor of the un-normalised dE_hat row; the
+    // diagonal terms of dw and the closed-form db ride along.
+    auto close_rows = [&]() {
+      if (p.phases & PASS_ROWS) {
+        __threadfence();
+        named_bar_sync(1, kEpiThreads);
+        if (et == 0) {
+          atomicAdd(p.ctr + 2, 1);
+          spin_until(p.ctr + 2, static_cast<int>(gridDim.x));
+        }
+        named_bar_sync(1, kEpiThreads);
+      }
+      const int U = p.n_own[SEG_DE];
+      for (int r = blockIdx.x * kEpiThreads + et; r < U; r += gridDim.x * kEpiThreads) {
+        const float cdv = __ldg(p.cos_diag + r);
+        float stat, q;
+        if (p.phases & PASS_ROWS) {
+          float per;
+          close_softmax_row(mx, __ldcg(p.rowsum + r), fmaf(w, cdv + eps, b), eps, stat, q, per);   // s3:120-121
+          p.row_stat_out[r] = stat;
+          p.row_aux_out[r] = q;
+          p.row_scale_out[r] = w * expf(mx - stat);
+          if (p.per_row_out != nullptr) p.per_row_out[r] = per;
+          loss_acc += per;
+        } else {
+          stat = __ldg(p.row_stat + r);
+          q = __ldg(p.row_aux + r);
+        }
+        if (p.phases & PASS_CENTROIDS) {
+          dw_acc = fmaf(-q, cdv + eps, dw_acc);     // diagonal element G_jj = -g q (uses cos_diag)
+          db_acc -= eps * expf(-stat);              // item 12: db = -g sum eps / (sum exp + eps)
+        }
+      }
+    };
+    bool closed = false;
 
     Walk wk = make_walk();
     int kind, og, s0, s1;
     for (int sg = 0; wk.next(p, kind, og, s0, s1); ++sg) {
       const bool is_dc = kBwd && kind == SEG_DC;       // CTA-uniform
+      if (kBwd && is_dc && !closed) { close_rows(); closed = true; }
       const int n_str = p.n_str[kind];
       const int ot = og * CG + cr;
       const bool tile_valid = ot < p.OT[kind];         // CTA-uniform
@@ -541,13 +595,12 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
       const bool ovalid = orow < p.n_own[kind];
       // per-owner-row metadata
       int jg = -1;            // FWD / DE: global speaker of this utterance row
-      float cd = 0.f, lse2 = INFINITY, qd = 0.f;
+      float cd = 0.f;
       int dlo = 0, dhi = 0;   // DC: local utterance rows [dlo, dhi) belong to this centroid
       if (!is_dc) {
         if (ovalid) {
           jg = p.spk_offset + orow / p.M;
-          cd = __ldg(p.cos_diag + orow);
-          if (kBwd) { lse2 = __ldg(p.row_stat + orow) * kLog2e; qd = __ldg(p.row_aux + orow); }
+          if (!kBwd) cd = __ldg(p.cos_diag + orow);
         }
       } else {
         const int jl = orow - p.spk_offset;
@@ -556,19 +609,40 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
       // FWD softmax running state, log2 domain, OFF-diagonal columns only: the running max starts at
       // the diagonal logit (known from cos_diag) and the diagonal term joins when the row is closed
       const float xd2 = fmaf(cd, w2, b2);
-      float m2 = xd2, lsum = 0.f;
+      float m2r = xd2, lsum = 0.f;
       float best = -INFINITY; int bestk = INT_MAX;   // FWD contrast
+      float rs_acc = 0.f;                            // STEP pass 1: this thread's share of the row sum
+      float dw_seg = 0.f;                            // STEP pass 2: sum p (cos + eps) of this centroid row
+      // STEP pass 2: lse (log2 domain) of stream row ur from its raw inputs -- the row sum of pass 1 when both
+      // passes run in this launch (row_stat was written by other CTAs after the barrier), else row_stat
+      auto lse2_of = [&](bool valid, float raw, float cdv) -> float {
+        if (!valid) return INFINITY;
+        if (!(p.phases & PASS_ROWS)) return raw * kLog2e;
+        float stat, q, per;
+        close_softmax_row(mx, raw, fmaf(w, cdv + eps, b), eps, stat, q, per);
+        return stat * kLog2e;
+      };
+      auto lse2_raw = [&](int ur, float& raw, float& cdv) -> bool {
+        if (ur >= n_str) return false;
+        if (p.phases & PASS_ROWS) { raw = __ldcg(p.rowsum + ur); cdv = __ldg(p.cos_diag + ur); }
+        else { raw = __ldg(p.row_stat + ur); cdv = 0.f; }
+        return true;
+      };
+      if (is_dc && half == 0) {
+        float raw = 0.f, cdv = 0.f;
+        const bool v0 = lse2_raw(s0 * kUnit + trow, raw, cdv);
+        tail->lse_s[it & 1][trow] = lse2_of(v0, raw, cdv);
+      }
 
       for (int u = s0; u < s1; u += kStepUnits, ++it) {
         const int nu = min(kStepUnits, s1 - u);
         const int buf = it & 1;
+        float nraw = 0.f, ncd = 0.f;
+        bool nvalid = false;
         if (is_dc) {
-          // stage the lse of the 128 stream rows (utterances) of this unit
-          if (half == 0) {
-            const int ur = u * kUnit + trow;
-            tail->lse_s[buf][trow] = (ur < n_str) ? __ldg(p.row_stat + ur) * kLog2e : INFINITY;
-          }
-          named_bar_sync(1, kEpiThreads);
+          named_bar_sync(1, kEpiThreads);      // lse_s[buf] staged (by the previous unit, or above)
+          // the next unit's raw inputs travel while this unit is processed
+          if (half == 0 && u + 1 < s1) nvalid = lse2_raw((u + 1) * kUnit + trow, nraw, ncd);
         }
         mbar_wait(bar(BAR_S_FULL + buf), (it >> 1) & 1);
         tc_fence_after();
@@ -577,18 +651,14 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
         const int nch = nu * (kUnit / 32) / 2;       // 32-column chunks per column half
 #pragma unroll 1
         for (int ch = half * nch; ch < (half + 1) * nch; ++ch) {
-          const int c0 = u * kUnit + ch * 32;        // first stream row (column of T) of this chunk
+          const int cc = u * kUnit + ch * 32;        // first stream row (column of T) of this chunk
           uint32_t v[32];
           tmem_ld32(t_addr + ch * 32, v);
           tmem_ld_wait();
-          if (dbg & 4) {
-            if (kBwd) tmem_st32(t_addr + ch * 32, v);
-            continue;
-          }
           if (!kBwd) {
-            if (c0 < n_str) {
-              const bool tailc = c0 + 32 > n_str;
-              const bool diagc = static_cast<unsigned>(jg - c0) < 32u;
+            if (cc < n_str) {
+              const bool tailc = cc + 32 > n_str;
+              const bool diagc = static_cast<unsigned>(jg - cc) < 32u;
               if (VARIANT == GE2E_SOFTMAX) {
                 float x[32];
 #pragma unroll
@@ -596,51 +666,43 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
                 if (__any_sync(0xffffffffu, tailc || diagc)) {
 #pragma unroll
                   for (int i = 0; i < 32; ++i)   // own-speaker column (s3:78) and padding leave the sum
-                    if (c0 + i == jg || c0 + i >= n_str) x[i] = -INFINITY;
+                    if (cc + i == jg || cc + i >= n_str) x[i] = -INFINITY;
                 }
                 float cm = x[0];
 #pragma unroll
                 for (int i = 1; i < 32; ++i) cm = fmaxf(cm, x[i]);
-                const float mn = fmaxf(m2, cm);
-                float s = 0.f;
+                const float mn = fmaxf(m2r, cm);
+                float sacc = 0.f;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) s += ex2(x[i] - mn);
-                lsum = fmaf(lsum, ex2(m2 - mn), s);
-                m2 = mn;
+                for (int i = 0; i < 32; ++i) sacc += ex2(x[i] - mn);
+                lsum = fmaf(lsum, ex2(m2r - mn), sacc);
+                m2r = mn;
               } else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                  float s = fmaf(__uint_as_float(v[i]), w, bb);
-                  if (c0 + i == jg || c0 + i >= n_str) s = -INFINITY;
-                  if (s > best) { best = s; bestk = c0 + i; }
+                  float sv = fmaf(__uint_as_float(v[i]), w, bb);
+                  if (cc + i == jg || cc + i >= n_str) sv = -INFINITY;
+                  if (sv > best) { best = sv; bestk = cc + i; }
                 }
               }
             }
           } else {
-            // ---- backward: G tile, written back over T
             uint32_t gq[32];
             if (!is_dc) {
-              const bool special = (c0 + 32 > n_str) || (static_cast<unsigned>(jg - c0) < 32u);
+              // ---- pass 1: P tile (fixed shift), written back over T; row sums on the side
+              const bool special = (cc + 32 > n_str) || (static_cast<unsigned>(jg - cc) < 32u);
               const bool any_special = __any_sync(0xffffffffu, special);
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                const float dot = __uint_as_float(v[i]);
-                float pr = ex2(fmaf(dot, w2, b2) - lse2);        // softmax prob (0 for padded rows)
-                if (any_special) {
-                  if (c0 + i >= n_str) pr = 0.f;
-                  if (c0 + i == jg) {
-                    // diagonal: p_jj - 1 = -q (saved by the forward), uses cos_diag, contributes to
-                    // dw but not to the contraction
-                    dw_acc = fmaf(-qd, cd + eps, dw_acc);
-                    pr = 0.f;
-                  }
-                }
-                dw_acc = fmaf(pr, dot + eps, dw_acc);
-                gq[i] = __float_as_uint(round_tf32(wg * pr));
+                float pr = ex2(fmaf(__uint_as_float(v[i]), w2, c0));
+                if (any_special && (cc + i >= n_str || cc + i == jg)) pr = 0.f;   // padding / own speaker (s3:78)
+                rs_acc += pr;
+                gq[i] = __float_as_uint(round_tf32(pr));
               }
             } else {
+              // ---- pass 2: G tile = w g softmax(S), own speaker's rows masked, written back over T
               const float4* ls4 = reinterpret_cast<const float4*>(&tail->lse_s[buf][ch * 32]);
-              const bool special = (c0 < dhi) && (c0 + 32 > dlo);
+              const bool special = (cc < dhi) && (cc + 32 > dlo);
               const bool any_special = __any_sync(0xffffffffu, special);
 #pragma unroll
               for (int i4 = 0; i4 < 8; ++i4) {
@@ -649,8 +711,10 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                   const int i = i4 * 4 + q;
-                  float pr = ex2(fmaf(__uint_as_float(v[i]), w2, b2) - ls[q]);   // lse = +inf past the end
-                  if (any_special && c0 + i >= dlo && c0 + i < dhi) pr = 0.f;    // own speaker's rows
+                  const float dot = __uint_as_float(v[i]);
+                  float pr = ex2(fmaf(dot, w2, b2) - ls[q]);                     // lse = +inf past the end
+                  if (any_special && cc + i >= dlo && cc + i < dhi) pr = 0.f;    // own speaker's rows
+                  dw_seg = fmaf(pr, dot + eps, dw_seg);
                   gq[i] = __float_as_uint(round_tf32(wg * pr));
                 }
               }
@@ -664,6 +728,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
           __syncwarp();
           if (lane == 0) arrive_leader(s_empty0 + 8u * buf);
         } else {
+          if (is_dc && half == 0 && u + 1 < s1) tail->lse_s[buf ^ 1][trow] = lse2_of(nvalid, nraw, ncd);
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
@@ -676,7 +741,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
       if (!kBwd) {
         // fold the two column halves of every row (upper half hands its state over through smem)
         float2 mine;
-        if (VARIANT == GE2E_SOFTMAX) mine = make_float2(m2, lsum);
+        if (VARIANT == GE2E_SOFTMAX) mine = make_float2(m2r, lsum);
         else mine = make_float2(best, __int_as_float(bestk));
         if (half == 1) tail->xch[trow] = mine;
         named_bar_sync(1, kEpiThreads);
@@ -685,9 +750,9 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
         if (half == 0 && tile_valid) {     // tile_valid is CTA-uniform: barrier 2 below stays consistent
           auto fold = [&](float2 q) {
             if (VARIANT == GE2E_SOFTMAX) {
-              const float mn = fmaxf(m2, q.x);
-              lsum = lsum * ex2(m2 - mn) + q.y * ex2(q.x - mn);
-              m2 = mn;
+              const float mn = fmaxf(m2r, q.x);
+              lsum = lsum * ex2(m2r - mn) + q.y * ex2(q.x - mn);
+              m2r = mn;
             } else {
               const int qk = __float_as_int(q.y);
               if (q.x > best || (q.x == best && qk < bestk)) { best = q.x; bestk = qk; }
@@ -700,7 +765,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
           bool last = full;
           if (!full) {
             float2 part;
-            if (VARIANT == GE2E_SOFTMAX) part = make_float2(m2, lsum);
+            if (VARIANT == GE2E_SOFTMAX) part = make_float2(m2r, lsum);
             else part = make_float2(best, __int_as_float(bestk));
             p.seg_part[(static_cast<size_t>(ot) * p.maxseg + (cl - first_cl)) * kTile + trow] = part;
             __threadfence();
@@ -716,7 +781,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
               __threadfence();
               const int last_cl = cluster_of_pair(static_cast<long long>(og) * st + st - 1, p.GP, NC);
               const int nseg = last_cl - first_cl + 1;
-              m2 = xd2; lsum = 0.f; best = -INFINITY; bestk = INT_MAX;
+              m2r = xd2; lsum = 0.f; best = -INFINITY; bestk = INT_MAX;
               for (int sgi = 0; sgi < nseg; ++sgi)
                 fold(__ldcg(&p.seg_part[(static_cast<size_t>(ot) * p.maxseg + sgi) * kTile + trow]));
             }
@@ -726,7 +791,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
             float per, stat, aux = 0.f;
             int ks = -1;
             if (VARIANT == GE2E_SOFTMAX) {
-              close_softmax_row(m2 * kLn2, lsum, Sd, eps, stat, aux, per);   // s3:120-121
+              close_softmax_row(m2r * kLn2, lsum, Sd, eps, stat, aux, per);   // s3:120-121
             } else {
               per = 1.f - 1.f / (1.f + expf(-Sd));
               stat = best;
@@ -741,7 +806,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
         }
       } else {
         // drain the accumulator [128 x D] of this segment (columns split between the two halves)
-        if (!is_dc && ovalid && s0 == 0 && half == 0) db_acc -= g * eps * ex2(-lse2);   // item 12
+        if (is_dc && ovalid) dw_acc += dw_seg;
         mbar_wait(bar(BAR_ACC_FULL), sg & 1);
         tc_fence_after();
         // TMEM -> registers -> owner area of shared memory (free: every MMA of the segment has
@@ -765,11 +830,12 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
         __syncwarp();
         if (lane == 0) arrive_leader(acc_empty);
         fence_proxy_async_smem();
+        if (et == 0 && (!full || !is_dc)) wait_zero_fill();   // partial sums and row sums land in zeroed memory
         named_bar_sync(1, kEpiThreads);
-        if (ew == 0 && lane == 0) {
+        if (!is_dc && ovalid) atomicAdd(p.rowsum + orow, rs_acc);
+        if (et == 0) {
           if (tile_valid) {
             const CUtensorMap* tm_out = &tms.out[kind];
-            if (!full) wait_zero_fill();
             for (int ks = 0; ks < kslabs; ++ks) {
               if (full) tma_store_2d(tm_out, ks * kSlabCols, ot * kTile, a_smem + ks * kSlabBytes);
               else tma_reduce_add_2d(tm_out, ks * kSlabCols, ot * kTile, a_smem + ks * kSlabBytes);
@@ -782,6 +848,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
       }
       tr.mark();   // segment flushed
     }
+    if (kBwd && !closed) close_rows();     // no pass-2 segment in this cluster (or pass 1 alone)
 
     // ------------------------------------------------------------ scalar reductions (once per CTA)
     if (!kBwd) {
@@ -794,24 +861,28 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ BwdSc
         atomicAdd(p.loss_accum, t);
       }
     } else {
+      loss_acc = warp_sum(loss_acc);
       dw_acc = warp_sum(dw_acc) * g;
-      db_acc = warp_sum(db_acc);
-      if (lane == 0) { tail->red[ew] = dw_acc; tail->red[kEpiWarps + ew] = db_acc; }
+      db_acc = warp_sum(db_acc) * g;
+      if (lane == 0) { tail->red3[ew] = loss_acc; tail->red3[kEpiWarps + ew] = dw_acc; tail->red3[2 * kEpiWarps + ew] = db_acc; }
       named_bar_sync(1, kEpiThreads);
-      if (ew == 0 && lane == 0) {
-        float tw = 0.f, tb = 0.f;
-        for (int i = 0; i < kEpiWarps; ++i) { tw += tail->red[i]; tb += tail->red[kEpiWarps + i]; }
-        wait_zero_fill();
-        atomicAdd(p.dwdb + 0, tw);
-        atomicAdd(p.dwdb + 1, tb);
+      if (et == 0) {
+        float tl = 0.f, tw = 0.f, tb = 0.f;
+        for (int i = 0; i < kEpiWarps; ++i) {
+          tl += tail->red3[i]; tw += tail->red3[kEpiWarps + i]; tb += tail->red3[2 * kEpiWarps + i];
+        }
+        if (p.phases & PASS_ROWS) atomicAdd(p.loss_accum, tl);
+        if (p.phases & PASS_CENTROIDS) { atomicAdd(p.dwdb + 0, tw); atomicAdd(p.dwdb + 1, tb); }
+        if (p.stamps != nullptr) p.stamps[2 * blockIdx.x + 1] = globaltimer_ns();
         // last CTA out restores the counters
-        if (atomicAdd(p.ctr + 1, 1) == static_cast<int>(gridDim.x) - 1) { atomicExch(p.ctr, 0); atomicExch(p.ctr + 1, 0); }
+        if (atomicAdd(p.ctr + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+          atomicExch(p.ctr, 0); atomicExch(p.ctr + 1, 0); atomicExch(p.ctr + 2, 0);
+        }
       }
     }
   }
 
   // ------------------------------------------------------------------------- teardown
-  if (kBwd && warp < kEpiWarp0) pdl_wait();   // every thread of the grid has waited by the time it completes
   tc_fence_before();
   __syncthreads();
   if (CG > 1) cluster_sync_all();     // no CTA leaves while its peer may still arrive on it / read its smem
@@ -896,64 +967,61 @@ int make_map_3d(CUtensorMap* m, const float* base, int rows, int D, int box_slab
 }
 
 unsigned long long* g_trace = nullptr;   // set through tc_set_trace (debug only)
-int g_trace_mode = -1;                   // -1: every kernel, else only TC_FWD / TC_BWD
+int g_trace_mode = -1;                   // -1: every kernel, else only TC_FWD / TC_STEP
+int g_trace_fine = 0;                    // 8: per-stage marks in the MMA warp's trace
+unsigned long long* g_stamps = nullptr;  // set through tc_set_stamps: per-CTA {start, end} of the step kernel
 
-int debug_knobs() {
-  static int dbg = -1;
-  if (dbg < 0) { const char* e = getenv("GE2E_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
-  return dbg;
+// SM count and co-resident cluster count are properties of the CURRENT device: cached per device
+constexpr int kMaxDevices = 64;
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
 }
 
 int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices) return 148;
+  if (n[dev] == 0) {
+    cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (n[dev] <= 0) n[dev] = 148;
   }
-  return n;
+  return n[dev];
 }
 
 // CTA-pair mode (cta_group::2) needs an even number of 32-column chunks of D so that an MMA2 stage
-// splits evenly between the two CTAs.  GE2E_TC_CG = 1 | 2 overrides.
-int pick_cg(int D) {
-  static int env = -1;
-  if (env < 0) {
-    const char* s = getenv("GE2E_TC_CG");
-    env = s ? atoi(s) : 0;
-  }
-  int cg = (env == 1 || env == 2) ? env : 2;
-  if ((D / kSlabCols) % 2 != 0) cg = 1;
-  return cg;
-}
+// splits evenly between the two CTAs.
+int pick_cg(int D) { return ((D / kSlabCols) % 2 != 0) ? 1 : 2; }
 
 // How many clusters of size CG can be co-resident (1 CTA per SM: the kernel needs ~225 KB smem).
+// The step kernel's grid barrier relies on this number: every CTA of its grid must be resident.
 template <int MODE, int VARIANT, int CG>
 int max_clusters() {
   constexpr bool DBG = false;
-  static int cache = 0;
-  if (cache == 0) {
-    int n = 0;
-    if (CG > 1) {
-      cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(sm_count() / CG * CG);
-      cfg.blockDim = dim3(kThreadsTc);
-      cfg.dynamicSmemBytes = kSmemBytes;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      cfg.attrs = at; cfg.numAttrs = 1;
-      cudaFuncSetAttribute(tc_strip_kernel<MODE, VARIANT, CG, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)kSmemBytes);
-      if (cudaOccupancyMaxActiveClusters(&n, tc_strip_kernel<MODE, VARIANT, CG, DBG>, &cfg) != cudaSuccess) n = 0;
-      (void)cudaGetLastError();
-    }
-    if (n <= 0) n = sm_count() / CG;
-    if (const char* e = getenv("GE2E_TC_MAXCL")) { const int cap = atoi(e); if (cap > 0) n = std::min(n, cap); }   // debug
-    cache = std::min(n, kMaxClusters);
+  static int cache[kMaxDevices] = {0};
+  const int dev = current_device();
+  const bool cacheable = dev >= 0 && dev < kMaxDevices;
+  if (cacheable && cache[dev] != 0) return cache[dev];
+  int n = 0;
+  {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(sm_count() / CG * CG);
+    cfg.blockDim = dim3(kThreadsTc);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaFuncSetAttribute(tc_strip_kernel<MODE, VARIANT, CG, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)kSmemBytes);
+    if (cudaOccupancyMaxActiveClusters(&n, tc_strip_kernel<MODE, VARIANT, CG, DBG>, &cfg) != cudaSuccess) n = 0;
+    (void)cudaGetLastError();
   }
-  return cache;
+  if (n <= 0) return 0;        // not cached: the caller reports GE2E_ERR_LAUNCH
+  n = std::min(n, kMaxClusters);
+  if (cacheable) cache[dev] = n;
+  return n;
 }
 
 struct Layout {
@@ -970,7 +1038,7 @@ Layout make_layout(int n_own, int n_str, int cg, int max_cl) {
   L.CG = cg;
   L.OG = (L.OT + L.CG - 1) / L.CG;
   L.GP = static_cast<long long>(L.OG) * L.ST;
-  L.NC = static_cast<int>(std::min<long long>(max_cl, L.GP));
+  L.NC = static_cast<int>(std::min<long long>(std::max(max_cl, 1), L.GP));
   const long long per = L.GP / L.NC;                 // >= 1
   L.maxseg = static_cast<int>(std::min<long long>(L.ST, L.ST / per + 2));
   L.done_bytes = (static_cast<size_t>(L.OT) * sizeof(int) + 255) & ~static_cast<size_t>(255);
@@ -979,104 +1047,45 @@ Layout make_layout(int n_own, int n_str, int cg, int max_cl) {
   return L;
 }
 
-// Backward schedule (see the header comment).  Returns the number of clusters; *de_partial tells the
-// caller whether some dE_hat owner group is cut between clusters (then dE_hat must be zero-filled).
-int make_bwd_sched(int OGe, int STe, int OGc, int STc, int max_cl, BwdSched* S, bool* de_partial) {
-  const long long GPe = static_cast<long long>(OGe) * STe, GPc = static_cast<long long>(OGc) * STc, W = GPe + GPc;
-  const int NC = static_cast<int>(std::min<long long>(max_cl, W));
-  const long long T = (W + NC - 1) / NC;             // balanced share, in units
-  long long max_de = 0;
-  for (int c = 0; c <= NC; ++c) {
-    S->de[c] = static_cast<int>((static_cast<long long>(c) * OGe / NC) * STe);
-    if (c > 0) max_de = std::max<long long>(max_de, S->de[c] - S->de[c - 1]);
-  }
-  static int force_flat = -1;      // GE2E_TC_FLAT=1 (debug): always use the flat cut
-  if (force_flat < 0) { const char* e = getenv("GE2E_TC_FLAT"); force_flat = e ? atoi(e) : 0; }
-  if (max_de <= T + T / 8 && !force_flat) {
-    // whole dE_hat groups per cluster (no cluster ends up more than 1/8 above the balanced share),
-    // dC_hat units fill every cluster up to the same level
-    *de_partial = false;
-    // a dC_hat segment costs an owner-tile load and an accumulator flush on top of its units (about 3
-    // units' worth): clusters whose level share would be smaller than that get none, the rest share it
-    constexpr long long kMinDcShare = 3;
-    long long wsum = 0;
-    long long wgt[kMaxClusters];
-    for (int pass = 0; pass < 2 && wsum == 0; ++pass)
-      for (int c = 0; c < NC; ++c) {
-        wgt[c] = std::max<long long>(0, T - (S->de[c + 1] - S->de[c]));
-        if (pass == 0 && wgt[c] < kMinDcShare) wgt[c] = 0;
-        wsum += wgt[c];
-      }
-    if (wsum == 0) { for (int c = 0; c < NC; ++c) wgt[c] = 1; wsum = NC; }
-    // every cluster works on ONE dC_hat owner group (a range that straddles two groups pays a second
-    // owner-tile load and a second reduce-add flush): a cluster belongs to the group that holds the
-    // midpoint of its level share, and each group's units are then split over its clusters
-    int grp[kMaxClusters];
-    long long gsum[kMaxClusters] = {0};          // OGc <= GPc / STc; only the first OGc entries are used
-    long long cum = 0;
-    for (int c = 0; c < NC; ++c) {
-      const long long mid2 = GPc * (2 * cum + wgt[c]);          // 2 * wsum * midpoint
-      grp[c] = static_cast<int>(std::min<long long>(OGc - 1, mid2 / (2 * wsum * STc)));
-      if (wgt[c] > 0 && grp[c] < kMaxClusters) gsum[grp[c]] += wgt[c];
-      cum += wgt[c];
+// Schedule of the step kernel (see the header comment): each pass is cut evenly over the clusters.
+// A pass whose owner groups can be dealt out whole without leaving any cluster more than 1/8 above the
+// level share keeps them whole (plain stores, one owner load per group); otherwise the flat pair list
+// is cut into equal contiguous ranges and the partial accumulators are reduce-added.  Returns the number
+// of clusters; *de_partial / *dc_partial tell the caller whether the outputs need a zero-fill.
+int make_step_sched(int OGe, int STe, int OGc, int STc, int phases, int max_cl, StepSched* S, bool* de_partial,
+                    bool* dc_partial) {
+  const long long GPe = (phases & PASS_ROWS) ? static_cast<long long>(OGe) * STe : 0;
+  const long long GPc = (phases & PASS_CENTROIDS) ? static_cast<long long>(OGc) * STc : 0;
+  const int NC = static_cast<int>(std::max<long long>(1, std::min<long long>(max_cl, std::max(GPe, GPc))));
+  auto cut = [&](long long GP, int OG, int ST, int* out) -> bool {     // returns "some group is cut"
+    if (GP == 0) { for (int c = 0; c <= NC; ++c) out[c] = 0; return false; }
+    const long long level = (GP + NC - 1) / NC;
+    const long long whole_max = static_cast<long long>((OG + NC - 1) / NC) * ST;   // most loaded cluster, whole groups
+    if (whole_max <= level + level / 8) {
+      for (int c = 0; c <= NC; ++c) out[c] = static_cast<int>((static_cast<long long>(c) * OG / NC) * ST);
+      return false;
     }
-    bool ok = OGc <= kMaxClusters;
-    for (int g = 0; g < OGc && ok; ++g) ok = gsum[g] > 0;
-    // plain proportional cut (ranges may straddle groups) ...
-    int prop[kMaxClusters + 1];
-    cum = 0;
-    for (int c = 0; c <= NC; ++c) {
-      prop[c] = static_cast<int>(GPc * cum / wsum);
-      if (c < NC) cum += wgt[c];
-    }
-    auto max_load = [&](const int* dc) {
-      long long m = 0;
-      for (int c = 0; c < NC; ++c) m = std::max<long long>(m, (S->de[c + 1] - S->de[c]) + (dc[c + 1] - dc[c]));
-      return m;
-    };
-    // ... against the group-aligned cut: take it unless alignment costs more than a straddle would
-    // (about 3 units) on the most loaded cluster
-    int alig[kMaxClusters + 1];
-    if (ok) {
-      long long gcum[kMaxClusters] = {0};
-      int pos = 0;
-      for (int c = 0; c < NC; ++c) {
-        alig[c] = pos;
-        if (wgt[c] > 0) {
-          const int g = grp[c];
-          gcum[g] += wgt[c];
-          pos = static_cast<int>(static_cast<long long>(g) * STc + STc * gcum[g] / gsum[g]);
-        }
-      }
-      alig[NC] = static_cast<int>(GPc);
-      ok = max_load(alig) <= max_load(prop) + 3;
-    }
-    for (int c = 0; c <= NC; ++c) S->dc[c] = ok ? alig[c] : prop[c];
-  } else {
-    // dE_hat groups too coarse: flat cut of [dC pairs | dE pairs]
-    *de_partial = true;
-    for (int c = 0; c <= NC; ++c) {
-      const long long lo = static_cast<long long>(c) * W / NC;
-      S->dc[c] = static_cast<int>(std::min(lo, GPc));
-      S->de[c] = static_cast<int>(std::max<long long>(0, lo - GPc));
-    }
-  }
+    for (int c = 0; c <= NC; ++c) out[c] = static_cast<int>(static_cast<long long>(c) * GP / NC);
+    return true;
+  };
+  *de_partial = cut(GPe, OGe, STe, S->de);
+  *dc_partial = cut(GPc, OGc, STc, S->dc);
   return NC;
 }
 
 template <int MODE, int VARIANT, int CG, bool DBG>
-int launch_tc_impl(const TmSet& tms, const BwdSched& sched, const TcParams& p, int NC, bool pdl, cudaStream_t st) {
+int launch_tc_impl(const TmSet& tms, const StepSched& sched, const TcParams& p, int NC, bool pdl, cudaStream_t st) {
   auto kern = tc_strip_kernel<MODE, VARIANT, CG, DBG>;
-  static bool attr_set[64] = {false};    // per instantiation and device
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+  static bool attr_set[kMaxDevices] = {false};    // per instantiation and device
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices || !attr_set[dev]) {
     GE2E_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    if (dev >= 0 && dev < kMaxDevices) attr_set[dev] = true;
   }
   TcParams q = p;
   q.trace = (g_trace_mode < 0 || g_trace_mode == MODE) ? g_trace : nullptr;
-  q.dbg = debug_knobs();
+  q.dbg = g_trace_fine;
+  q.stamps = (MODE == TC_STEP) ? g_stamps : nullptr;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(NC * CG);
   cfg.blockDim = dim3(kThreadsTc);
@@ -1093,10 +1102,10 @@ int launch_tc_impl(const TmSet& tms, const BwdSched& sched, const TcParams& p, i
   return GE2E_OK;
 }
 
-// the instrumented instantiation runs only while a trace buffer is set or GE2E_TC_DEBUG is non-zero
+// the instrumented instantiation runs only while a trace buffer is set (ge2e_b200_debug_trace)
 template <int MODE, int VARIANT, int CG>
-int launch_tc(const TmSet& tms, const BwdSched& sched, const TcParams& p, int NC, bool pdl, cudaStream_t st) {
-  if (g_trace != nullptr || debug_knobs() != 0) return launch_tc_impl<MODE, VARIANT, CG, true>(tms, sched, p, NC, pdl, st);
+int launch_tc(const TmSet& tms, const StepSched& sched, const TcParams& p, int NC, bool pdl, cudaStream_t st) {
+  if (g_trace != nullptr) return launch_tc_impl<MODE, VARIANT, CG, true>(tms, sched, p, NC, pdl, st);
   return launch_tc_impl<MODE, VARIANT, CG, false>(tms, sched, p, NC, pdl, st);
 }
 
@@ -1105,7 +1114,7 @@ int max_clusters_cg(int cg) {
   return cg == 2 ? max_clusters<MODE, VARIANT, 2>() : max_clusters<MODE, VARIANT, 1>();
 }
 template <int MODE, int VARIANT>
-int launch_tc_cg(int cg, const TmSet& tms, const BwdSched& sched, const TcParams& p, int NC, bool pdl,
+int launch_tc_cg(int cg, const TmSet& tms, const StepSched& sched, const TcParams& p, int NC, bool pdl,
                  cudaStream_t st) {
   return cg == 2 ? launch_tc<MODE, VARIANT, 2>(tms, sched, p, NC, pdl, st)
                  : launch_tc<MODE, VARIANT, 1>(tms, sched, p, NC, pdl, st);
@@ -1120,26 +1129,34 @@ Layout fwd_layout(int U, int n_total, int D, int variant) {
   const int cg = pick_cg(D);
   const int mc = (variant == GE2E_SOFTMAX) ? max_clusters_cg<TC_FWD, GE2E_SOFTMAX>(cg)
                                            : max_clusters_cg<TC_FWD, GE2E_CONTRAST>(cg);
-  return make_layout(U, n_total, cg, mc);
+  return make_layout(U, n_total, cg, mc > 0 ? mc : sm_count() / cg);
 }
+
+size_t rowsum_bytes(int U) { return (static_cast<size_t>((U + 3) & ~3) * sizeof(float) + 255) & ~static_cast<size_t>(255); }
 
 }  // namespace
 
-void tc_set_trace(unsigned long long* device_buf, int mode) { g_trace = device_buf; g_trace_mode = mode; }
+void tc_set_trace(unsigned long long* device_buf, int mode) {
+  g_trace = device_buf;
+  g_trace_fine = (mode >= 0 && (mode & 0x100)) ? 8 : 0;
+  g_trace_mode = mode < 0 ? -1 : (mode & 0xff);
+}
+void tc_set_stamps(unsigned long long* device_buf) { g_stamps = device_buf; }
 
-// Host-only view of the backward schedule for tests: same arithmetic as tc_bwd_rows, the number of
+// Host-only view of the step schedule for tests: same arithmetic as tc_step, the number of
 // co-resident clusters is an argument instead of an occupancy query.
-int tc_debug_bwd_schedule(int u_local, int n_total, int cg, int max_clusters, int* de_begin, int* dc_begin,
-                          int* de_partial, int* units) {
+int tc_debug_step_schedule(int u_local, int n_total, int cg, int max_clusters, int* de_begin, int* dc_begin,
+                           int* partial, int* units) {
   if (u_local <= 0 || n_total <= 0 || (cg != 1 && cg != 2) || max_clusters <= 0 || max_clusters > kMaxClusters)
     return GE2E_ERR_ARGUMENT;
   const int OTe = (u_local + kTile - 1) / kTile, STe = (n_total + kUnit - 1) / kUnit;
   const int OTc = (n_total + kTile - 1) / kTile, STc = (u_local + kUnit - 1) / kUnit;
-  BwdSched S{};
-  bool partial = false;
-  const int NC = make_bwd_sched((OTe + cg - 1) / cg, STe, (OTc + cg - 1) / cg, STc, max_clusters, &S, &partial);
+  StepSched S{};
+  bool dep = false, dcp = false;
+  const int NC = make_step_sched((OTe + cg - 1) / cg, STe, (OTc + cg - 1) / cg, STc, PASS_ROWS | PASS_CENTROIDS,
+                                 max_clusters, &S, &dep, &dcp);
   for (int c = 0; c <= NC; ++c) { de_begin[c] = S.de[c]; dc_begin[c] = S.dc[c]; }
-  *de_partial = partial ? 1 : 0;
+  partial[0] = dep ? 1 : 0; partial[1] = dcp ? 1 : 0;
   units[0] = (OTe + cg - 1) / cg; units[1] = STe; units[2] = (OTc + cg - 1) / cg; units[3] = STc;
   return NC;
 }
@@ -1151,9 +1168,10 @@ bool tc_supported(int n_local, int n_total, int M, int D, int variant) {
   return get_encode() != nullptr;
 }
 
+// workspace: [header 256 B: step counters][FWD seg_done][FWD seg_part][STEP row sums]
 size_t tc_workspace_bytes(int n_local, int n_total, int M, int D, int variant) {
   const Layout L = fwd_layout(n_local * M, n_total, D, variant);
-  return kWsHeaderBytes + L.done_bytes + L.part_bytes;
+  return kWsHeaderBytes + L.done_bytes + L.part_bytes + rowsum_bytes(n_local * M);
 }
 
 int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* row_aux, float* loss_accum,
@@ -1177,41 +1195,57 @@ int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* r
   // programmatic dependent launch: barrier init / TMEM allocation / tensormap prefetch run under the
   // tail of whatever kernel precedes this one in the stream; the kernel waits before touching memory
   (void)after_prep;
-  static const BwdSched no_sched{};
+  static const StepSched no_sched{};
   if (a.variant == GE2E_SOFTMAX)
     return launch_tc_cg<TC_FWD, GE2E_SOFTMAX>(L.CG, tms, no_sched, p, L.NC, true, st);
   return launch_tc_cg<TC_FWD, GE2E_CONTRAST>(L.CG, tms, no_sched, p, L.NC, true, st);
 }
 
-int tc_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kstar, const float* row_aux,
-                const float* grad_out, float* dE_hat, float* dC_hat_partial, float* dwdb_accum, void* ws,
-                size_t ws_bytes, cudaStream_t st) {
-  (void)row_kstar;
-  if (ws == nullptr || ws_bytes < kWsHeaderBytes) return GE2E_ERR_WORKSPACE;
+// The softmax step on tensor cores.  phases = PASS_ROWS: forward rows + un-normalised dE_hat (+ row_scale);
+// PASS_CENTROIDS: dC_hat_partial, {dw, db} from the row statistics of an earlier PASS_ROWS launch;
+// both: one launch with a grid-wide barrier between the passes.
+int tc_step(const RowsArgs& a, int phases, const float* grad_out, const float* row_stat_in, const float* row_aux_in,
+            float* row_stat, float* row_aux, float* row_scale, float* loss_accum, float* per_row_out, float* dE_hat,
+            float* dC_hat_partial, float* dwdb_accum, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int U = a.n_local * a.M;
+  if (ws == nullptr || ws_bytes < tc_workspace_bytes(a.n_local, a.n_total, a.M, a.D, a.variant)) return GE2E_ERR_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(ws) & 15) != 0) return GE2E_ERR_WORKSPACE;
   const int cg = pick_cg(a.D);
   const int slabs = a.D / kSlabCols;
+  const int max_cl = max_clusters_cg<TC_STEP, GE2E_SOFTMAX>(cg);
+  if (max_cl <= 0) return GE2E_ERR_LAUNCH;     // the grid barrier needs a known co-resident cluster count
   // segment kind DE: owner = utterance tiles, stream = centroids; DC: owner = centroid tiles, stream = utterances
   TcParams p{};
   fill_common(p, a);
-  p.row_stat = row_stat; p.row_aux = row_aux; p.grad_out = grad_out; p.dwdb = dwdb_accum;
+  p.phases = phases;
+  p.row_stat = row_stat_in; p.row_aux = row_aux_in; p.grad_out = grad_out; p.dwdb = dwdb_accum;
+  p.row_stat_out = row_stat; p.row_aux_out = row_aux; p.row_scale_out = row_scale; p.loss_accum = loss_accum;
+  p.per_row_out = per_row_out;
   p.n_own[SEG_DE] = U; p.n_str[SEG_DE] = a.n_total;
   p.n_own[SEG_DC] = a.n_total; p.n_str[SEG_DC] = U;
   for (int k = 0; k < 2; ++k) {
     p.OT[k] = (p.n_own[k] + kTile - 1) / kTile;
     p.ST[k] = (p.n_str[k] + kUnit - 1) / kUnit;
   }
-  BwdSched sched{};
-  bool de_partial = false;
-  const int NC = make_bwd_sched((p.OT[SEG_DE] + cg - 1) / cg, p.ST[SEG_DE], (p.OT[SEG_DC] + cg - 1) / cg, p.ST[SEG_DC],
-                                max_clusters_cg<TC_BWD, GE2E_SOFTMAX>(cg), &sched, &de_partial);
-
-  // dC_hat is always assembled from partial accumulators (TMA reduce-add): the kernel zero-fills it
-  // (and {dw, db}) itself; D % 32 == 0 makes the row count a whole number of float4
-  p.zero_base = reinterpret_cast<float4*>(dC_hat_partial);
-  p.zero_n4 = static_cast<long long>(a.n_total) * a.D / 4;
+  StepSched sched{};
+  bool de_partial = false, dc_partial = false;
+  const int NC = make_step_sched((p.OT[SEG_DE] + cg - 1) / cg, p.ST[SEG_DE], (p.OT[SEG_DC] + cg - 1) / cg, p.ST[SEG_DC],
+                                 phases, max_cl, &sched, &de_partial, &dc_partial);
+  // outputs assembled from partial accumulators (TMA reduce-add) are zero-filled by the kernel itself;
+  // D % 32 == 0 makes every row a whole number of float4
+  if ((phases & PASS_CENTROIDS) && dc_partial) {
+    p.zero_base = reinterpret_cast<float4*>(dC_hat_partial);
+    p.zero_n4 = static_cast<long long>(a.n_total) * a.D / 4;
+  }
+  if ((phases & PASS_ROWS) && de_partial) {
+    p.zero2_base = reinterpret_cast<float4*>(dE_hat);
+    p.zero2_n4 = static_cast<long long>(U) * a.D / 4;
+  }
   p.ctr = static_cast<int*>(ws);
-  if (de_partial) GE2E_CUDA_TRY(cudaMemsetAsync(dE_hat, 0, static_cast<size_t>(U) * a.D * sizeof(float), st));
+  const Layout L = fwd_layout(U, a.n_total, a.D, a.variant);
+  p.rowsum = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + kWsHeaderBytes + L.done_bytes + L.part_bytes);
+  // {dw, db} accumulate: zeroed by prep when the passes run in one step; a lone backward clears them here
+  if (phases == PASS_CENTROIDS) GE2E_CUDA_TRY(cudaMemsetAsync(dwdb_accum, 0, 2 * sizeof(float), st));
 
   TmSet tms{};
   int rc;
@@ -1222,10 +1256,9 @@ int tc_bwd_rows(const RowsArgs& a, const float* row_stat, const int32_t* row_kst
   if ((rc = make_map_2d(&tms.own[SEG_DC], a.c_hat_all, a.n_total, a.D, kTile)) != GE2E_OK) return rc;
   if ((rc = make_map_2d(&tms.strk[SEG_DC], a.e_hat, U, a.D, kBoxRows)) != GE2E_OK) return rc;
   if ((rc = make_map_3d(&tms.strmn[SEG_DC], a.e_hat, U, a.D, slabs / cg)) != GE2E_OK) return rc;
-  if ((rc = make_map_2d(&tms.out[SEG_DC], dC_hat_partial, a.n_total, a.D, kTile)) != GE2E_OK) return rc;
-
-  if (debug_skip_mask() & 12) return GE2E_OK;
-  return launch_tc_cg<TC_BWD, GE2E_SOFTMAX>(cg, tms, sched, p, NC, true, st);
+  if ((rc = make_map_2d(&tms.out[SEG_DC], dC_hat_partial != nullptr ? dC_hat_partial : dE_hat, a.n_total, a.D, kTile)) != GE2E_OK)
+    return rc;
+  return launch_tc_cg<TC_STEP, GE2E_SOFTMAX>(cg, tms, sched, p, NC, phases != PASS_CENTROIDS, st);
 }
 
 }  // namespace ge2e

@@ -135,8 +135,8 @@ class GE2ELoss(nn.Module):
                                                                ops._stream()), "ge2e_b200_normalize_rows")
         one = torch.ones((), dtype=torch.float32, device=dev)
         zero = torch.zeros((), dtype=torch.float32, device=dev)
-        _, _, _, _, sim = ops.fwd_rows(e_hat, c_hat, cos_diag, N, N, 0, M, D, one, zero, eps, _lib.SOFTMAX,
-                                    _lib.FP32, accum, sim=True)
+        sim = ops.fwd_rows(e_hat, c_hat, cos_diag, N, N, 0, M, D, one, zero, eps, _lib.SOFTMAX,
+                           _lib.FP32, accum, sim=True)[4]
         return sim.view(N, M, N)
 
     @staticmethod

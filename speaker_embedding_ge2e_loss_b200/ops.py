@@ -32,8 +32,30 @@ def _f32c(t: Tensor) -> Tensor:
     return t.contiguous()
 
 
+def _same_f32c(*ts: Optional[Tensor]) -> None:
+    """The staged ops hand raw pointers to fp32 kernels: a half-precision or strided tensor (autocast, a
+    slice) would be read and written out of bounds, so refuse it instead of copying (outputs alias)."""
+    for t in ts:
+        if t is None:
+            continue
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise TypeError(f"expected a contiguous float32 CUDA tensor, got {t.dtype}, "
+                            f"contiguous={t.is_contiguous()}")
+        if not t.is_cuda:
+            raise RuntimeError("speaker_embedding_ge2e_loss_b200 runs on CUDA (sm_100a) tensors only; "
+                               "there is no CPU fallback")
+
+
 def _ptr(t: Optional[Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
+
+
+def _check(rc: int, what: str) -> None:
+    """check() for calls that used a cached workspace: a failed call may have left its counters dirty,
+    so the cache is dropped and the next call starts from a freshly zeroed buffer."""
+    if rc != 0:
+        _WS_CACHE.clear()
+    check(rc, what)
 
 
 _WS_CACHE: dict = {}
@@ -46,6 +68,10 @@ def _workspace(n_local: int, n_total: int, M: int, D: int, variant: int, precisi
     nbytes = lib().ge2e_b200_workspace_bytes(n_local, n_total, M, D, variant, precision)
     if nbytes == 0:
         return None, 0
+    if torch.cuda.is_current_stream_capturing():
+        # inside a capture torch.zeros is only recorded: a cached buffer would be handed to later eager
+        # calls without ever having been cleared, and it would pin memory of the graph's private pool
+        return torch.zeros(nbytes, dtype=torch.uint8, device=device), nbytes
     key = (device.index if device.index is not None else torch.cuda.current_device(),
            torch.cuda.current_stream(device).cuda_stream, nbytes)
     ws = _WS_CACHE.get(key)
@@ -81,12 +107,21 @@ def _index_ok(row_index: Optional[Tensor], U: int, dev) -> Optional[Tensor]:
     return row_index.to(torch.int32).contiguous()
 
 
+def _tc_softmax(N: int, M: int, D: int, variant: int, precision: int) -> bool:
+    """True where the softmax loss runs on tensor cores: the forward then also leaves the un-normalised
+    dE_hat rows + row_scale (include/ge2e_b200.h, ge2e_b200_fwd_rows) and the backward is one pass."""
+    return variant == _lib.SOFTMAX and lib().ge2e_b200_path(N, N, M, D, variant, precision) == 1
+
+
 def _fwd_impl(E: Tensor, w: Tensor, b: Tensor, eps: float, variant: int, precision: int, packed: bool,
-              row_index: Optional[Tensor] = None, speakers: int = 0):
+              row_index: Optional[Tensor] = None, speakers: int = 0, want_grad: bool = True):
     """GE2ELoss.forward (reference s3:19-30) through the C ABI.  ``packed``: the per-call intermediates
     come out of ONE allocation (views); the custom op needs non-aliasing outputs and passes False.
     ``row_index`` (with ``speakers``): E is [U, D] in the embedder's row order and logical row r lives
-    at row_index[r] (the trainer's ``embeddings[unperm]``, s4:189-192, folded into the kernels)."""
+    at row_index[r] (the trainer's ``embeddings[unperm]``, s4:189-192, folded into the kernels).
+    ``want_grad``: a backward will follow (tensor-core softmax path: the forward prepares dE_hat).
+    Returns (loss, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, dE_hat, row_scale); the last two
+    are 1-element placeholders where the path does not use them."""
     _need_cuda(E, w, b)
     E, w, b = _f32c(E), _f32c(w), _f32c(b)
     if row_index is None:
@@ -99,14 +134,18 @@ def _fwd_impl(E: Tensor, w: Tensor, b: Tensor, eps: float, variant: int, precisi
     U = N * M
     dev = E.device
     with _on_device(dev):
+        fused = want_grad and _tc_softmax(N, M, D, variant, precision)
+        nh, ns = (U * D, U) if fused else (1, 1)
         if packed:
-            flat = torch.empty(U * D + N * D + 3 * U + 4, dtype=torch.float32, device=dev)
+            flat = torch.empty(U * D + N * D + 3 * U + 4 + nh + ns, dtype=torch.float32, device=dev)
             o = 0
             e_hat = flat[o:o + U * D].view(U, D); o += U * D
             c_hat = flat[o:o + N * D].view(N, D); o += N * D
+            dE_hat = flat[o:o + nh]; o += nh          # 16-byte aligned: U * D and N * D are multiples of 4 here
             cos_diag = flat[o:o + U]; o += U
             row_stat = flat[o:o + U]; o += U
             row_aux = flat[o:o + U]; o += U
+            row_scale = flat[o:o + ns]; o += ns
             accum = flat[o:o + 4]
         else:
             accum = torch.empty(4, dtype=torch.float32, device=dev)
@@ -115,19 +154,26 @@ def _fwd_impl(E: Tensor, w: Tensor, b: Tensor, eps: float, variant: int, precisi
             cos_diag = torch.empty(U, dtype=torch.float32, device=dev)
             row_stat = torch.empty(U, dtype=torch.float32, device=dev)
             row_aux = torch.empty(U, dtype=torch.float32, device=dev)
+            dE_hat = torch.empty(nh, dtype=torch.float32, device=dev)
+            row_scale = torch.empty(ns, dtype=torch.float32, device=dev)
+        if fused:
+            dE_hat = dE_hat.view(U, D)
         row_kstar = torch.empty(U if variant == _lib.CONTRAST else 1, dtype=torch.int32, device=dev)
         ws, ws_bytes = _workspace(N, N, M, D, variant, precision, dev)
         rc = lib().ge2e_b200_forward_indexed(E.data_ptr(), _ptr(row_index), N, M, D, w.data_ptr(), b.data_ptr(), eps,
                                              variant, precision, e_hat.data_ptr(), c_hat.data_ptr(),
                                              cos_diag.data_ptr(), row_stat.data_ptr(), row_kstar.data_ptr(),
-                                             row_aux.data_ptr(), accum.data_ptr(), _ptr(ws), ws_bytes, _stream())
-    check(rc, "ge2e_b200_forward")
-    return accum[0], e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux
+                                             row_aux.data_ptr(), accum.data_ptr(),
+                                             dE_hat.data_ptr() if fused else None,
+                                             row_scale.data_ptr() if fused else None, _ptr(ws), ws_bytes, _stream())
+    _check(rc, "ge2e_b200_forward")
+    return accum[0], e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, dE_hat, row_scale
 
 
-def _bwd_impl(grad_out, E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, eps, variant, precision,
-              row_index: Optional[Tensor] = None):
-    """loss.backward() (s4:200) through the C ABI.  Returns (dE shaped like E, dwdb[2])."""
+def _bwd_impl(grad_out, E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, dE_hat, row_scale, eps,
+              variant, precision, row_index: Optional[Tensor] = None):
+    """loss.backward() (s4:200) through the C ABI.  ``dE_hat`` / ``row_scale``: what the forward prepared
+    (1-element placeholders where the path does not use them).  Returns (dE shaped like E, dwdb[2])."""
     _need_cuda(grad_out, E, w, b)
     E, w, b = _f32c(E), _f32c(w), _f32c(b)
     g = _f32c(grad_out)
@@ -137,26 +183,28 @@ def _bwd_impl(grad_out, E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, ro
     dev = E.device
     with _on_device(dev):
         dE = torch.empty_like(E)
-        # [dE_hat (U*D) | dC_hat (N*D) | dw | db]; `accum` = start of (dw - 1) so that accum[1]=dw, accum[2]=db
-        scratch = torch.empty(U * D + N * D + 2, dtype=torch.float32, device=dev)
-        dE_hat_ptr = scratch.data_ptr()
-        dC_ptr = dE_hat_ptr + U * D * 4
+        fused = dE_hat.numel() == U * D and _tc_softmax(N, M, D, variant, precision)
+        # [accum (4: -, dw, db, -) | dC_hat (N*D) | dE_hat (U*D) unless the forward prepared it]
+        scratch = torch.empty(4 + N * D + (0 if fused else U * D), dtype=torch.float32, device=dev)
+        dC_ptr = scratch.data_ptr() + 16
+        dE_hat_ptr = dE_hat.data_ptr() if fused else dC_ptr + N * D * 4
         ws, ws_bytes = _workspace(N, N, M, D, variant, precision, dev)
-        accum_ptr = dC_ptr + (N * D - 1) * 4
         rc = lib().ge2e_b200_backward_indexed(E.data_ptr(), _ptr(row_index), e_hat.data_ptr(), c_hat.data_ptr(),
                                               cos_diag.data_ptr(), row_stat.data_ptr(), row_kstar.data_ptr(),
-                                              row_aux.data_ptr(), N, M, D, w.data_ptr(), b.data_ptr(), eps, variant,
-                                              precision, g.data_ptr(), dE_hat_ptr, dC_ptr, accum_ptr, dE.data_ptr(),
-                                              _ptr(ws), ws_bytes, _stream())
-    check(rc, "ge2e_b200_backward")
-    return dE, scratch[U * D + N * D:]
+                                              row_aux.data_ptr(), row_scale.data_ptr() if fused else None, N, M, D,
+                                              w.data_ptr(), b.data_ptr(), eps, variant, precision, g.data_ptr(),
+                                              dE_hat_ptr, dC_ptr, scratch.data_ptr(), dE.data_ptr(), _ptr(ws), ws_bytes,
+                                              _stream())
+    _check(rc, "ge2e_b200_backward")
+    return dE, scratch[1:3]
 
 
 @torch.library.custom_op("ge2e_b200::fwd", mutates_args=())
 def ge2e_fwd(E: Tensor, w: Tensor, b: Tensor, eps: float, variant: int,
-             precision: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+             precision: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     """GE2ELoss.forward as a torch.library op (what torch.compile / export see).  Returns (loss, e_hat,
-    c_hat, cos_diag, row_stat, row_kstar, row_aux); everything after loss is saved for the backward."""
+    c_hat, cos_diag, row_stat, row_kstar, row_aux, dE_hat, row_scale); everything after loss is saved for
+    the backward."""
     out = _fwd_impl(E, w, b, eps, variant, precision, packed=False)
     return (out[0].clone(),) + out[1:]       # accum[0] is a view of accum: op outputs must not alias
 
@@ -165,37 +213,40 @@ def ge2e_fwd(E: Tensor, w: Tensor, b: Tensor, eps: float, variant: int,
 def _(E, w, b, eps, variant, precision):
     N, M, D = E.shape
     U = N * M
+    fused = _tc_softmax(N, M, D, variant, precision)
     return (E.new_empty(()), E.new_empty((U, D)), E.new_empty((N, D)), E.new_empty(U), E.new_empty(U),
-            E.new_empty(U if variant == _lib.CONTRAST else 1, dtype=torch.int32), E.new_empty(U))
+            E.new_empty(U if variant == _lib.CONTRAST else 1, dtype=torch.int32), E.new_empty(U),
+            E.new_empty((U, D) if fused else (1,)), E.new_empty(U if fused else 1))
 
 
 @torch.library.custom_op("ge2e_b200::bwd", mutates_args=())
 def ge2e_bwd(grad_out: Tensor, E: Tensor, w: Tensor, b: Tensor, e_hat: Tensor, c_hat: Tensor,
-             cos_diag: Tensor, row_stat: Tensor, row_kstar: Tensor, row_aux: Tensor, eps: float, variant: int,
-             precision: int) -> Tuple[Tensor, Tensor]:
+             cos_diag: Tensor, row_stat: Tensor, row_kstar: Tensor, row_aux: Tensor, dE_hat: Tensor,
+             row_scale: Tensor, eps: float, variant: int, precision: int) -> Tuple[Tensor, Tensor]:
     """Backward of ge2e_b200::fwd.  Returns (dE[N,M,D], dwdb[2])."""
-    dE, dwdb = _bwd_impl(grad_out, E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, eps, variant,
-                         precision)
+    dE, dwdb = _bwd_impl(grad_out, E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, dE_hat, row_scale,
+                         eps, variant, precision)
     return dE, dwdb.clone()
 
 
 @ge2e_bwd.register_fake
-def _(grad_out, E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, eps, variant, precision):
+def _(grad_out, E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, dE_hat, row_scale, eps, variant,
+      precision):
     return torch.empty_like(E), E.new_empty(2)
 
 
 def _fwd_setup(ctx, inputs, output):
     E, w, b, eps, variant, precision = inputs
-    _, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux = output
-    ctx.save_for_backward(E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux)
+    _, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, dE_hat, row_scale = output
+    ctx.save_for_backward(E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, dE_hat, row_scale)
     ctx.cfg = (eps, variant, precision)
 
 
 def _fwd_backward(ctx, g_loss, *_unused):
-    E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux = ctx.saved_tensors
+    E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, dE_hat, row_scale = ctx.saved_tensors
     eps, variant, precision = ctx.cfg
-    dE, dwdb = ge2e_bwd(g_loss, E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, eps, variant,
-                        precision)
+    dE, dwdb = ge2e_bwd(g_loss, E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, dE_hat, row_scale, eps,
+                        variant, precision)
     return dE, dwdb[0], dwdb[1], None, None, None
 
 
@@ -208,19 +259,21 @@ class _GE2EEager(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, E, w, b, eps, variant, precision, row_index, speakers):
-        loss, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux = _fwd_impl(
-            E, w, b, eps, variant, precision, packed=True, row_index=row_index, speakers=speakers)
-        ctx.save_for_backward(E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux)
+        want_grad = any(ctx.needs_input_grad[:3])
+        loss, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, dE_hat, row_scale = _fwd_impl(
+            E, w, b, eps, variant, precision, packed=True, row_index=row_index, speakers=speakers,
+            want_grad=want_grad)
+        ctx.save_for_backward(E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, dE_hat, row_scale)
         ctx.cfg = (eps, variant, precision)
         ctx.row_index = row_index
         return loss
 
     @staticmethod
     def backward(ctx, g_loss):
-        E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux = ctx.saved_tensors
+        E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, dE_hat, row_scale = ctx.saved_tensors
         eps, variant, precision = ctx.cfg
-        dE, dwdb = _bwd_impl(g_loss, E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, eps, variant,
-                             precision, row_index=ctx.row_index)
+        dE, dwdb = _bwd_impl(g_loss, E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, dE_hat, row_scale,
+                             eps, variant, precision, row_index=ctx.row_index)
         return dE, dwdb[0], dwdb[1], None, None, None, None, None
 
 
@@ -257,6 +310,8 @@ def prep(E: Tensor, c_hat_local_out: Tensor, precision: int):
     """Stage 1 on the local speakers; writes c_hat into ``c_hat_local_out`` (a slice of the
     all-gather buffer).  Returns (e_hat, cos_diag, accum)."""
     _need_cuda(E, c_hat_local_out)
+    E = _f32c(E)
+    _same_f32c(c_hat_local_out)
     n, M, D = E.shape
     dev = E.device
     e_hat = torch.empty((n * M, D), dtype=torch.float32, device=dev)
@@ -270,9 +325,17 @@ def prep(E: Tensor, c_hat_local_out: Tensor, precision: int):
 
 
 def fwd_rows(e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, b, eps, variant, precision,
-             accum, per_row: bool = False, sim: bool = False):
+             accum, per_row: bool = False, sim: bool = False, want_grad: bool = False):
+    """Returns (row_stat, row_kstar, row_aux, per_row, sim, dE_hat, row_scale); the last two are None
+    unless ``want_grad`` and the softmax loss runs on tensor cores for this shape (the forward then
+    prepares the un-normalised dE_hat: hand both to bwd_rows / bwd_finalize)."""
+    _same_f32c(e_hat, c_hat_all, cos_diag, w, b, accum)
     dev = e_hat.device
     U = n_local * M
+    fused = (want_grad and variant == _lib.SOFTMAX and not sim
+             and lib().ge2e_b200_path(n_local, n_total, M, D, variant, precision) == 1)
+    dE_hat = torch.empty((U, D), dtype=torch.float32, device=dev) if fused else None
+    row_scale = torch.empty(U, dtype=torch.float32, device=dev) if fused else None
     row_stat = torch.empty(U, dtype=torch.float32, device=dev)
     row_kstar = torch.empty(U if variant == _lib.CONTRAST else 1, dtype=torch.int32, device=dev)
     row_aux = torch.empty(U, dtype=torch.float32, device=dev)
@@ -283,35 +346,44 @@ def fwd_rows(e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, 
         rc = lib().ge2e_b200_fwd_rows(e_hat.data_ptr(), c_hat_all.data_ptr(), cos_diag.data_ptr(), n_local,
                                       n_total, spk_offset, M, D, w.data_ptr(), b.data_ptr(), eps, variant,
                                       precision, row_stat.data_ptr(), row_kstar.data_ptr(), row_aux.data_ptr(),
-                                      accum.data_ptr(), _ptr(per), _ptr(sim_out), _ptr(ws), ws_bytes, _stream())
-    check(rc, "ge2e_b200_fwd_rows")
-    return row_stat, row_kstar, row_aux, per, sim_out
+                                      accum.data_ptr(), _ptr(per), _ptr(sim_out), _ptr(dE_hat), _ptr(row_scale),
+                                      _ptr(ws), ws_bytes, _stream())
+    _check(rc, "ge2e_b200_fwd_rows")
+    return row_stat, row_kstar, row_aux, per, sim_out, dE_hat, row_scale
 
 
 def bwd_rows(e_hat, c_hat_all, cos_diag, row_stat, row_kstar, row_aux, n_local, n_total, spk_offset, M, D, w, b,
-             eps, variant, precision, grad_out):
-    """Returns (dE_hat[U_local, D], dC_hat_partial[n_total, D], dwdb[2])."""
+             eps, variant, precision, grad_out, dE_hat=None, row_scale=None):
+    """Returns (dE_hat[U_local, D], dC_hat_partial[n_total, D], dwdb[2]).  ``dE_hat`` / ``row_scale``: what
+    fwd_rows(want_grad=True) returned (None: dE_hat is computed here)."""
+    _same_f32c(e_hat, c_hat_all, cos_diag, row_stat, row_aux, w, b, grad_out, dE_hat, row_scale)
     dev = e_hat.device
-    dE_hat = torch.empty((n_local * M, D), dtype=torch.float32, device=dev)
+    if dE_hat is None or row_scale is None:
+        dE_hat, row_scale = torch.empty((n_local * M, D), dtype=torch.float32, device=dev), None
     scratch = torch.empty(n_total * D + 2, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         ws, ws_bytes = _workspace(n_local, n_total, M, D, variant, precision, dev)
         rc = lib().ge2e_b200_bwd_rows(e_hat.data_ptr(), c_hat_all.data_ptr(), cos_diag.data_ptr(),
-                                      row_stat.data_ptr(), row_kstar.data_ptr(), row_aux.data_ptr(), n_local,
+                                      row_stat.data_ptr(), row_kstar.data_ptr(), row_aux.data_ptr(),
+                                      _ptr(row_scale), n_local,
                                       n_total, spk_offset, M, D, w.data_ptr(), b.data_ptr(), eps, variant, precision,
                                       grad_out.data_ptr(), dE_hat.data_ptr(), scratch.data_ptr(),
                                       scratch.data_ptr() + n_total * D * 4, _ptr(ws), ws_bytes, _stream())
-    check(rc, "ge2e_b200_bwd_rows")
+    _check(rc, "ge2e_b200_bwd_rows")
     return dE_hat, scratch[:n_total * D].view(n_total, D), scratch[n_total * D:]
 
 
-def bwd_finalize(E, dE_hat, dC_hat_local, cos_diag, row_stat, row_aux, w, b, eps, variant, grad_out):
+def bwd_finalize(E, dE_hat, dC_hat_local, cos_diag, row_stat, row_aux, w, b, eps, variant, grad_out,
+                 row_scale=None):
+    E = _f32c(E)
+    _same_f32c(dE_hat, dC_hat_local, cos_diag, row_stat, row_aux, w, b, grad_out, row_scale)
+    _need_cuda(E)
     n, M, D = E.shape
     dE = torch.empty_like(E)
     with torch.cuda.device(E.device):
         rc = lib().ge2e_b200_bwd_finalize(E.data_ptr(), dE_hat.data_ptr(), dC_hat_local.data_ptr(),
-                                          cos_diag.data_ptr(), row_stat.data_ptr(), row_aux.data_ptr(), n, M, D,
-                                          w.data_ptr(),
+                                          cos_diag.data_ptr(), row_stat.data_ptr(), row_aux.data_ptr(),
+                                          _ptr(row_scale), n, M, D, w.data_ptr(),
                                           b.data_ptr(), eps, variant, grad_out.data_ptr(), dE.data_ptr(),
                                           _stream())
     check(rc, "ge2e_b200_bwd_finalize")

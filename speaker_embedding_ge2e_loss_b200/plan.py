@@ -39,9 +39,9 @@ class GE2EPlan:
         self.row_kstar = torch.empty(U, dtype=torch.int32, device=dev)
         self.row_aux = torch.empty(U, dtype=f32, device=dev)
         self.dE_hat = torch.empty((U, D), dtype=f32, device=dev)
-        # [dC_hat (N*D) | dw | db] so that the library zeroes all of it with one memset
-        self._scratch = torch.empty(N * D + 2, dtype=f32, device=dev)
-        self._accum = torch.empty(4, dtype=f32, device=dev)      # {loss, -, -, -}
+        self.row_scale = torch.empty(U, dtype=f32, device=dev)   # tensor-core softmax path: factor of the dE_hat rows
+        self.dC_hat = torch.empty((N, D), dtype=f32, device=dev)
+        self._accum = torch.empty(4, dtype=f32, device=dev)      # {loss, dw, db, -}: zeroed by prep every step
         self.dE = torch.empty((N, M, D), dtype=f32, device=dev)
         self.grad_out = torch.ones((), dtype=f32, device=dev)
         nbytes = lib().ge2e_b200_step_workspace_bytes(N, M, D, self.variant, self.precision)
@@ -49,9 +49,7 @@ class GE2EPlan:
         # 1: the reference-sized batch runs fwd+bwd as ONE kernel (ge2e_b200_forward_backward)
         self.single_kernel = lib().ge2e_b200_step_launches(N, M, D, self.variant, self.precision) == 1
         self._ws_bytes = nbytes
-        self.loss = self._accum[0]
-        self.dw = self._scratch[N * D]
-        self.db = self._scratch[N * D + 1]
+        self.loss, self.dw, self.db = self._accum[0], self._accum[1], self._accum[2]
         self._graph = None
 
     def step(self, E: torch.Tensor, w: torch.Tensor, b: torch.Tensor, backward: bool = True) -> None:
@@ -61,13 +59,13 @@ class GE2EPlan:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         ws = self._ws.data_ptr() if self._ws_bytes else None
         if backward:
-            accum_ptr = self._scratch.data_ptr() + (N * D - 1) * 4   # accum[1] = dw, accum[2] = db
+            accum_ptr = self._accum.data_ptr()
             rc = h.ge2e_b200_forward_backward(E.data_ptr(), None, N, M, D, w.data_ptr(), b.data_ptr(), self.eps,
                                               self.variant, self.precision, self.grad_out.data_ptr(),
                                               self.e_hat.data_ptr(), self.c_hat.data_ptr(), self.cos_diag.data_ptr(),
                                               self.row_stat.data_ptr(), self.row_kstar.data_ptr(),
-                                              self.row_aux.data_ptr(), self._accum.data_ptr(), self.dE_hat.data_ptr(),
-                                              self._scratch.data_ptr(), accum_ptr, self.dE.data_ptr(), ws,
+                                              self.row_aux.data_ptr(), self.row_scale.data_ptr(), accum_ptr,
+                                              self.dE_hat.data_ptr(), self.dC_hat.data_ptr(), self.dE.data_ptr(), ws,
                                               self._ws_bytes, stream)
             check(rc, "ge2e_b200_forward_backward")
             if self.sgd is not None:
@@ -78,7 +76,8 @@ class GE2EPlan:
         rc = h.ge2e_b200_forward(E.data_ptr(), N, M, D, w.data_ptr(), b.data_ptr(), self.eps, self.variant,
                                  self.precision, self.e_hat.data_ptr(), self.c_hat.data_ptr(),
                                  self.cos_diag.data_ptr(), self.row_stat.data_ptr(), self.row_kstar.data_ptr(),
-                                 self.row_aux.data_ptr(), self._accum.data_ptr(), ws, self._ws_bytes, stream)
+                                 self.row_aux.data_ptr(), self._accum.data_ptr(), None, None, ws, self._ws_bytes,
+                                 stream)
         check(rc, "ge2e_b200_forward")
 
     def capture(self, E, w: torch.Tensor, b: torch.Tensor, backward: bool = True, steps: int = 1):
@@ -106,8 +105,8 @@ class GE2EPlan:
 class ShardedGE2EPlan:
     """Speaker-sharded fwd+bwd (one process per GPU) with persistent buffers, the C-ABI stages and the
     three NCCL collectives enqueued back to back so that the whole step can be captured in one CUDA
-    graph: prep -> all-gather(c_hat) -> fwd_rows -> bwd_rows -> reduce-scatter(dC_hat) ->
-    all-reduce({loss, dw, db}) -> bwd_finalize.  Upstream gradient = 1 (``loss.backward()``).
+    graph: prep -> all-gather(c_hat) -> step_rows (forward rows + backward rows: ONE tensor-core kernel for
+    the softmax loss) -> reduce-scatter(dC_hat) -> all-reduce({loss, dw, db}) || bwd_finalize.  Upstream gradient = 1 (``loss.backward()``).
     Results: ``.loss`` (global), ``.dE`` (this rank's rows), ``.dw`` / ``.db`` (global)."""
 
     def __init__(self, n_local: int, n_total: int, spk_offset: int, M: int, D: int, variant: str = "softmax",
@@ -129,6 +128,10 @@ class ShardedGE2EPlan:
         self.row_kstar = torch.empty(U, dtype=torch.int32, device=dev)
         self.row_aux = torch.empty(U, dtype=f32, device=dev)
         self.dE_hat = torch.empty((U, D), dtype=f32, device=dev)
+        self.row_scale = torch.empty(U, dtype=f32, device=dev)
+        self.path = lib().ge2e_b200_path(n_local, n_total, M, D, self.variant, self.precision)
+        # finalize applies row_scale only where the forward produced it (softmax on tensor cores)
+        self._scaled = self.path == 1 and self.variant == _lib.SOFTMAX
         self.dC_partial = torch.empty((n_total, D), dtype=f32, device=dev)
         self.dC_local = torch.empty((n_local, D), dtype=f32, device=dev)
         self.red = torch.empty(4, dtype=f32, device=dev)          # {loss, dw, db, -}: zeroed by prep, all-reduced
@@ -150,15 +153,12 @@ class ShardedGE2EPlan:
               "ge2e_b200_prep")
         dist.all_gather_into_tensor(self.c_hat_all, self.c_hat_mine, group=self.group)
         s = torch.cuda.current_stream(self.device).cuda_stream
-        check(h.ge2e_b200_fwd_rows(self.e_hat.data_ptr(), self.c_hat_all.data_ptr(), self.cos_diag.data_ptr(), nl, nt,
-                                   off, M, D, w.data_ptr(), b.data_ptr(), self.eps, self.variant, self.precision,
-                                   self.row_stat.data_ptr(), self.row_kstar.data_ptr(), self.row_aux.data_ptr(),
-                                   self.red.data_ptr(), None, None, ws, self._ws_bytes, s), "ge2e_b200_fwd_rows")
-        check(h.ge2e_b200_bwd_rows(self.e_hat.data_ptr(), self.c_hat_all.data_ptr(), self.cos_diag.data_ptr(),
-                                   self.row_stat.data_ptr(), self.row_kstar.data_ptr(), self.row_aux.data_ptr(), nl, nt,
-                                   off, M, D, w.data_ptr(), b.data_ptr(), self.eps, self.variant, self.precision,
-                                   self.grad_out.data_ptr(), self.dE_hat.data_ptr(), self.dC_partial.data_ptr(),
-                                   self.red.data_ptr() + 4, ws, self._ws_bytes, s), "ge2e_b200_bwd_rows")
+        check(h.ge2e_b200_step_rows(self.e_hat.data_ptr(), self.c_hat_all.data_ptr(), self.cos_diag.data_ptr(), nl, nt,
+                                    off, M, D, w.data_ptr(), b.data_ptr(), self.eps, self.variant, self.precision,
+                                    self.grad_out.data_ptr(), self.row_stat.data_ptr(), self.row_kstar.data_ptr(),
+                                    self.row_aux.data_ptr(), self.row_scale.data_ptr(), self.red.data_ptr(),
+                                    self.dE_hat.data_ptr(), self.dC_partial.data_ptr(), ws, self._ws_bytes, s),
+              "ge2e_b200_step_rows")
         dist.reduce_scatter_tensor(self.dC_local, self.dC_partial, op=dist.ReduceOp.SUM, group=self.group)
         # {loss, dw, db} are not inputs of finalize: their all-reduce runs beside it (fork / join on a side
         # stream; inside a capture this becomes a parallel branch of the graph)
@@ -168,7 +168,8 @@ class ShardedGE2EPlan:
             dist.all_reduce(self.red, op=dist.ReduceOp.SUM, group=self.group)
         s = cur.cuda_stream
         check(h.ge2e_b200_bwd_finalize(E_local.data_ptr(), self.dE_hat.data_ptr(), self.dC_local.data_ptr(),
-                                       self.cos_diag.data_ptr(), self.row_stat.data_ptr(), self.row_aux.data_ptr(), nl,
+                                       self.cos_diag.data_ptr(), self.row_stat.data_ptr(), self.row_aux.data_ptr(),
+                                       self.row_scale.data_ptr() if self._scaled else None, nl,
                                        M, D, w.data_ptr(), b.data_ptr(), self.eps, self.variant,
                                        self.grad_out.data_ptr(), self.dE.data_ptr(), s), "ge2e_b200_bwd_finalize")
         cur.wait_stream(self._side)
@@ -288,7 +289,7 @@ class GE2EHostFeed(_HostFeed):
         self.w, self.b = w, b
         dev = torch.device(device if device is not None else "cuda")
         self._setup((N, M, D), depth, dev, lambda: GE2EPlan(N, M, D, variant, precision, eps, device=dev),
-                    lambda p, res: [(res[0:1], p.loss.reshape(1)), (res[1:3], p._scratch[N * D:N * D + 2])])
+                    lambda p, res: [(res, p._accum[0:3])])
         self.path = self.plans[0].path
 
 

@@ -74,27 +74,32 @@ class ShardedGE2EFunction(torch.autograd.Function):
         e_hat, cos_diag, accum = stages.prep(E_local, mine, precision)
         # all-gather of the normalised centroids (8.4 MB at N=8192, D=256)
         dist.all_gather_into_tensor(c_hat_all, mine if _inplace_ok(group) else mine.clone(), group=group)
-        row_stat, row_kstar, row_aux, _, _ = stages.fwd_rows(e_hat, c_hat_all, cos_diag, n_local, n_total,
-                                                             spk_offset, M, D, w, b, eps, variant, precision, accum)
+        # want_grad: where the softmax loss runs on tensor cores the forward also leaves the un-normalised
+        # dE_hat rows + row_scale (None on every other path) and the backward is the centroid pass alone
+        row_stat, row_kstar, row_aux, _, _, dE_hat, row_scale = stages.fwd_rows(
+            e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, b, eps, variant, precision, accum,
+            want_grad=any(ctx.needs_input_grad[:3]))
         loss = accum[0].clone()
         dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
-        ctx.save_for_backward(E_local, w, b, e_hat, c_hat_all, cos_diag, row_stat, row_kstar, row_aux)
+        ctx.save_for_backward(E_local, w, b, e_hat, c_hat_all, cos_diag, row_stat, row_kstar, row_aux, dE_hat,
+                              row_scale)
         ctx.cfg = (eps, variant, precision, group, stages, n_local, n_total, spk_offset, M, D)
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        E_local, w, b, e_hat, c_hat_all, cos_diag, row_stat, row_kstar, row_aux = ctx.saved_tensors
+        E_local, w, b, e_hat, c_hat_all, cos_diag, row_stat, row_kstar, row_aux, dE_hat, row_scale = ctx.saved_tensors
         eps, variant, precision, group, stages, n_local, n_total, spk_offset, M, D = ctx.cfg
         g = g.contiguous()
         dE_hat, dC_partial, dwdb = stages.bwd_rows(e_hat, c_hat_all, cos_diag, row_stat, row_kstar, row_aux,
                                                    n_local, n_total, spk_offset, M, D, w, b, eps, variant,
-                                                   precision, g)
+                                                   precision, g, dE_hat=dE_hat, row_scale=row_scale)
         dC_local = torch.empty((n_local, D), dtype=dC_partial.dtype, device=dC_partial.device)
         dist.reduce_scatter_tensor(dC_local, dC_partial.contiguous(), op=dist.ReduceOp.SUM, group=group)
         dwdb = dwdb.clone()
         dist.all_reduce(dwdb, op=dist.ReduceOp.SUM, group=group)
-        dE = stages.bwd_finalize(E_local, dE_hat, dC_local, cos_diag, row_stat, row_aux, w, b, eps, variant, g)
+        dE = stages.bwd_finalize(E_local, dE_hat, dC_local, cos_diag, row_stat, row_aux, w, b, eps, variant, g,
+                                 row_scale=row_scale)
         return dE, dwdb[0], dwdb[1], None, None, None, None, None
 
 

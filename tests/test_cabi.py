@@ -70,11 +70,13 @@ def test_host_side_status_codes(pkg):
         assert h.ge2e_b200_strerror(code) not in (b"ok", b"unknown ge2e status")
     # argument checking happens before any CUDA call: safe without a GPU
     assert h.ge2e_b200_forward(None, 4, 8, 256, None, None, 1e-6, 0, 0, None, None, None, None, None, None, None,
-                               None, 0, None) == -3
+                               None, None, None, 0, None) == -3
     assert h.ge2e_b200_prep(1, 4, 1, 256, 0, 1, 1, 1, 1, None) == -1          # M < 2
     assert h.ge2e_b200_prep(1, 4, 8, 256, 7, 1, 1, 1, 1, None) == -3          # unknown precision
-    assert h.ge2e_b200_fwd_rows(1, 1, 1, 4, 2, 0, 8, 256, 1, 1, 1e-6, 0, 0, 1, None, 1, 1, None, None, None, 0,
-                                None) == -1                                    # shard outside [0, n_total)
+    assert h.ge2e_b200_fwd_rows(1, 1, 1, 4, 2, 0, 8, 256, 1, 1, 1e-6, 0, 0, 1, None, 1, 1, None, None, None, None,
+                                None, 0, None) == -1                           # shard outside [0, n_total)
+    assert h.ge2e_b200_step_rows(1, 1, 1, 4, 4, 0, 8, 256, 1, 1, 1e-6, 0, 1, 1, 1, None, 1, None, 1, 1, 1, None, 0,
+                                 None) == -3                                   # row_scale is required
     assert h.ge2e_b200_calc_loss(1, 4, 8, 1e-6, 9, 1, None, None) == -3
     assert h.ge2e_b200_scale_bias_sgd(None, 1, 1, 1, 1.0, 0.01, None, None) == -3   # null parameter pointer
     assert h.ge2e_b200_scale_bias_sgd(1, 1, 1, 1, 0.0, 0.01, None, None) == -3      # max_norm must be > 0
@@ -131,31 +133,32 @@ def test_product_does_not_import_oracle():
             assert "oracle" not in src, f"{fn} references oracle/"
 
 
-# ------------------------------------------------------------------ backward work schedule (host logic)
+# ------------------------------------------------------------------ step-kernel work schedule (host logic)
 @pytest.mark.parametrize("u_local,n_total", [(10240, 1024), (131072, 8192), (16384, 8192), (4096, 2048), (2100, 300),
                                              (256, 8192), (300 * 7, 300), (65536, 256), (1024, 1024)])
 @pytest.mark.parametrize("cg,max_cl", [(2, 74), (1, 148), (2, 8), (1, 3)])
-def test_backward_schedule_covers_every_pair_once(pkg, u_local, n_total, cg, max_cl):
-    """Every (owner group, stream unit) pair of both contractions belongs to exactly one cluster, the
-    ranges are contiguous and monotone, dE_hat groups are whole unless the fallback cut is reported,
-    and no cluster carries much more than the level share."""
+def test_step_schedule_covers_every_pair_once(pkg, u_local, n_total, cg, max_cl):
+    """Every (owner group, stream unit) pair of both passes belongs to exactly one cluster, the ranges are
+    contiguous and monotone, owner groups are whole unless a cut is reported, and in EACH pass (a grid-wide
+    barrier separates them) no cluster carries more than 1/8 above the level share."""
     import ctypes as C
     h = pkg.lib()
     de = (C.c_int * (max_cl + 1))()
     dc = (C.c_int * (max_cl + 1))()
-    part = C.c_int(0)
+    part = (C.c_int * 2)()
     units = (C.c_int * 4)()
-    nc = h.ge2e_b200_debug_bwd_schedule(u_local, n_total, cg, max_cl, de, dc, C.byref(part), units)
+    nc = h.ge2e_b200_debug_step_schedule(u_local, n_total, cg, max_cl, de, dc, part, units)
     assert 1 <= nc <= max_cl
     oge, ste, ogc, stc = list(units)
     de, dc = list(de)[:nc + 1], list(dc)[:nc + 1]
     assert de[0] == 0 and dc[0] == 0 and de[-1] == oge * ste and dc[-1] == ogc * stc
     assert all(b >= a for a, b in zip(de, de[1:])) and all(b >= a for a, b in zip(dc, dc[1:]))
-    if not part.value:
+    if not part[0]:
         assert all(x % ste == 0 for x in de), "whole dE_hat groups expected"
-    loads = [(de[c + 1] - de[c]) + (dc[c + 1] - dc[c]) for c in range(nc)]
-    total = oge * ste + ogc * stc
-    assert sum(loads) == total
-    level = -(-total // nc)
-    # whole groups may overshoot the level share by 1/8, a dC segment shorter than 3 units is not handed out
-    assert max(loads) <= level + level // 8 + max(ste, 3) + 1, (max(loads), level)
+    if not part[1]:
+        assert all(x % stc == 0 for x in dc), "whole dC_hat groups expected"
+    for begin, total in ((de, oge * ste), (dc, ogc * stc)):
+        loads = [begin[c + 1] - begin[c] for c in range(nc)]
+        assert sum(loads) == total
+        level = -(-total // nc)
+        assert max(loads) <= level + level // 8, (max(loads), level)

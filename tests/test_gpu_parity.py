@@ -609,25 +609,26 @@ def test_single_kernel_step_indexed_rows(pkg):
     U = N * M
     e_hat, c_hat, cos_diag = torch.empty(U, D, **f32), torch.empty(N, D, **f32), torch.empty(U, **f32)
     row_stat, row_aux, kstar = torch.empty(U, **f32), torch.empty(U, **f32), torch.empty(U, dtype=torch.int32, device=dev)
-    accum, dE_hat, scratch, dE = torch.empty(4, **f32), torch.empty(U, D, **f32), torch.empty(N * D + 2, **f32), torch.empty(U, D, **f32)
+    accum, dE_hat, scratch, dE = torch.empty(4, **f32), torch.empty(U, D, **f32), torch.empty(N * D, **f32), torch.empty(U, D, **f32)
+    row_scale = torch.empty(U, **f32)
     w = torch.tensor(10.0, device=dev); b = torch.tensor(-5.0, device=dev); gone = torch.ones((), **f32)
     nb = h.ge2e_b200_step_workspace_bytes(N, M, D, 0, 0)
     assert nb > 0 and h.ge2e_b200_step_launches(N, M, D, 0, 0) == 1
     ws = torch.zeros(nb, dtype=torch.uint8, device=dev)
     rc = h.ge2e_b200_forward_backward(flat.data_ptr(), idx.data_ptr(), N, M, D, w.data_ptr(), b.data_ptr(), 1e-6, 0, 0,
                                       gone.data_ptr(), e_hat.data_ptr(), c_hat.data_ptr(), cos_diag.data_ptr(),
-                                      row_stat.data_ptr(), kstar.data_ptr(), row_aux.data_ptr(), accum.data_ptr(),
-                                      dE_hat.data_ptr(), scratch.data_ptr(), scratch.data_ptr() + (N * D - 1) * 4,
+                                      row_stat.data_ptr(), kstar.data_ptr(), row_aux.data_ptr(), row_scale.data_ptr(),
+                                      accum.data_ptr(), dE_hat.data_ptr(), scratch.data_ptr(),
                                       dE.data_ptr(), ws.data_ptr(), nb, torch.cuda.current_stream().cuda_stream)
     assert rc == 0
     torch.cuda.synchronize()
     ref = orc.forward_backward(E_np, 10.0, -5.0, 1e-6, "softmax")
-    got = dict(loss=accum[0].item(), dE=dE[idx.long()].double().cpu().numpy().reshape(N, M, D), dw=scratch[N * D].item(),
-               db=scratch[N * D + 1].item())
+    got = dict(loss=accum[0].item(), dE=dE[idx.long()].double().cpu().numpy().reshape(N, M, D), dw=accum[1].item(),
+               db=accum[2].item())
     check(got, ref, U, 1e-5)
     # too small a workspace is refused, not overrun
     assert h.ge2e_b200_forward_backward(flat.data_ptr(), idx.data_ptr(), N, M, D, w.data_ptr(), b.data_ptr(), 1e-6, 0, 0,
                                         gone.data_ptr(), e_hat.data_ptr(), c_hat.data_ptr(), cos_diag.data_ptr(),
-                                        row_stat.data_ptr(), kstar.data_ptr(), row_aux.data_ptr(), accum.data_ptr(),
-                                        dE_hat.data_ptr(), scratch.data_ptr(), scratch.data_ptr() + (N * D - 1) * 4,
+                                        row_stat.data_ptr(), kstar.data_ptr(), row_aux.data_ptr(), row_scale.data_ptr(),
+                                        accum.data_ptr(), dE_hat.data_ptr(), scratch.data_ptr(),
                                         dE.data_ptr(), ws.data_ptr(), 128, torch.cuda.current_stream().cuda_stream) == -4

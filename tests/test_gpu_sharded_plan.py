@@ -25,7 +25,8 @@ CHILD = textwrap.dedent("""
         return ((a - r).abs().max() / r.abs().max().clamp_min(1e-12)).item()
     for (N, M, D, variant, precision, tol) in [(64, 10, 256, "softmax", "tf32", 2e-3),
                                                 (64, 10, 256, "contrast", "tf32", 2e-3),
-                                                (48, 8, 128, "softmax", "fp32", 1e-5)]:
+                                                (48, 8, 128, "softmax", "fp32", 1e-5),
+                                                (512, 4, 256, "softmax", "tf32", 2e-3)]:    # tcgen05 step kernel
         g = torch.Generator().manual_seed(N + M)
         Es = [torch.nn.functional.normalize(torch.randn(N, M, D, generator=g), dim=-1).to(dev) for _ in range(2)]
         w = torch.tensor(10.0, device=dev); b = torch.tensor(-5.0, device=dev)

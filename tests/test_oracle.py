@@ -126,3 +126,25 @@ def test_oracle_gradient_is_consistent_with_finite_differences():
         db = 0.7 * (orc.forward(E, 4.0, -1.0 + h, 1e-6, variant)[0] -
                     orc.forward(E, 4.0, -1.0 - h, 1e-6, variant)[0]) / (2 * h)
         assert abs(dw - r["dw"]) < 1e-6 and abs(db - r["db"]) < 1e-6
+
+
+# ------------------------------------------------------------------ chunked torch restatement (large-N checker)
+@pytest.mark.parametrize("N,M,D,kind,variant,wbg", [
+    (64, 10, 64, "clustered", "softmax", (10.0, -5.0, 1.0)), (33, 3, 48, "raw", "softmax", (-3.0, 0.5, 0.25)),
+    (40, 5, 32, "random", "contrast", (10.0, -5.0, 1.0)), (7, 2, 16, "clustered", "contrast", (4.0, -1.0, -0.7)),
+])
+def test_torch_oracle_matches_numpy_oracle(N, M, D, kind, variant, wbg):
+    """oracle/ge2e_oracle_torch.py (what the GPU tests evaluate in float64 at configs 3 / 4) is the numpy
+    oracle row chunk by row chunk: identical to 1e-12 whatever the chunk size."""
+    import torch
+    from oracle import ge2e_oracle_torch as orct
+    w, b, g = wbg
+    E = orc.make_embeddings(N, M, D, seed=N + D, kind=kind)
+    ref = orc.forward_backward(E, w, b, 1e-6, variant, g=g)
+    for chunk in (N * M, 37):
+        got = orct.forward_backward(torch.tensor(E), w, b, 1e-6, variant, g=g, chunk=chunk)
+        assert abs(got["loss"] - ref["loss"]) <= 1e-12 * max(1.0, abs(ref["loss"]))
+        assert np.linalg.norm(got["dE"].numpy() - ref["dE"]) <= 1e-12 * np.linalg.norm(ref["dE"])
+        assert abs(got["dw"] - ref["dw"]) <= 1e-12 * max(1.0, abs(ref["dw"]))
+        assert abs(got["db"] - ref["db"]) <= 1e-12 * max(1.0, abs(ref["db"]))
+        assert np.allclose(got["per"].numpy(), ref["per"], rtol=1e-12, atol=1e-14)

@@ -20,7 +20,9 @@ DELTA = 1e-8
 
 
 class TorchStages:
-    """CPU stand-in for ops.prep / fwd_rows / bwd_rows / bwd_finalize (same signatures)."""
+    """CPU stand-in for ops.prep / fwd_rows / bwd_rows / bwd_finalize (same signatures).  ``fused``: emulate
+    the tensor-core softmax contract (the forward leaves un-normalised dE_hat rows + row_scale)."""
+    fused = False
 
     @staticmethod
     def _unit(x):
@@ -49,26 +51,35 @@ class TorchStages:
 
     @staticmethod
     def fwd_rows(e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, b, eps, variant, precision,
-                 accum, per_row=False, sim=False):
+                 accum, per_row=False, sim=False, want_grad=False):
         S, _, rows, spk = TorchStages._S(e_hat, c_hat_all, cos_diag, n_local, spk_offset, M, w, b, eps)
         aux = torch.zeros_like(cos_diag)
+        dE_hat = row_scale = None
         if variant == 0:
             Z = torch.exp(S).sum(1) + eps
             stat = torch.log(Z)
             per = stat - S[rows, spk]
             aux = (Z - torch.exp(S[rows, spk])) / Z          # q = 1 - p_jj
             kstar = torch.zeros(1, dtype=torch.int32)
+            if want_grad and TorchStages.fused:
+                # contract of the tensor-core rows pass (include/ge2e_b200.h, ge2e_b200_fwd_rows): P against
+                # the fixed shift |w| + (w eps + b), own-speaker column excluded; un-normalised rows + scale
+                m = w.abs() + (w * eps + b)
+                P = torch.exp(S - m)
+                P[rows, spk] = 0
+                dE_hat = P @ c_hat_all
+                row_scale = w * torch.exp(m - stat)
         else:
             Sm = S.clone()
             Sm[rows, spk] = -float("inf")
             stat, kstar = Sm.max(dim=1)
             per = 1 - torch.sigmoid(S[rows, spk]) + torch.sigmoid(stat)
         accum[0] += per.sum()
-        return stat, kstar, aux, per, None
+        return stat, kstar, aux, per, None, dE_hat, row_scale
 
     @staticmethod
     def bwd_rows(e_hat, c_hat_all, cos_diag, row_stat, row_kstar, row_aux, n_local, n_total, spk_offset, M, D, w,
-                 b, eps, variant, precision, grad_out):
+                 b, eps, variant, precision, grad_out, dE_hat=None, row_scale=None):
         S, cos, rows, spk = TorchStages._S(e_hat, c_hat_all, cos_diag, n_local, spk_offset, M, w, b, eps)
         if variant == 0:
             G = torch.exp(S - row_stat[:, None])
@@ -83,11 +94,16 @@ class TorchStages:
         dwdb = torch.stack([(G * cos).sum(), G.sum()])
         Goff = (w * G).clone()
         Goff[rows, spk] = 0
+        if row_scale is not None:                      # the forward prepared dE_hat: centroid pass only
+            return dE_hat, Goff.T @ e_hat, dwdb
         return Goff @ c_hat_all, Goff.T @ e_hat, dwdb
 
     @staticmethod
-    def bwd_finalize(E, dE_hat, dC_hat_local, cos_diag, row_stat, row_aux, w, b, eps, variant, grad_out):
+    def bwd_finalize(E, dE_hat, dC_hat_local, cos_diag, row_stat, row_aux, w, b, eps, variant, grad_out,
+                     row_scale=None):
         n, M, D = E.shape
+        if row_scale is not None:
+            dE_hat = dE_hat * (grad_out * row_scale)[:, None]
         Ef = E.reshape(n * M, D)
         s = E.sum(dim=1, keepdim=True)
         u = ((s - E) / (M - 1)).reshape(n * M, D)
@@ -117,7 +133,8 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, N, M, D, variant, q):
+def _worker(rank, world, port, N, M, D, variant, q, fused=False):
+    TorchStages.fused = fused
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -136,14 +153,15 @@ def _worker(rank, world, port, N, M, D, variant, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,variant", [(2, "softmax"), (2, "contrast"), (4, "softmax")])
-def test_sharded_equals_single_process_oracle(world, variant):
+@pytest.mark.parametrize("world,variant,fused", [(2, "softmax", False), (2, "softmax", True), (2, "contrast", False),
+                                                 (4, "softmax", True)])
+def test_sharded_equals_single_process_oracle(world, variant, fused):
     from oracle import ge2e_oracle as orc
     N, M, D = 8, 3, 16
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, N, M, D, variant, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, N, M, D, variant, q, fused)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted((q.get(timeout=120) for _ in range(world)), key=lambda t: t[0])
