@@ -92,8 +92,8 @@ enum {
   BAR_G_FULL = BAR_S_EMPTY + 2,         // [2] BWD: G written back to TMEM             (leader)
   BAR_ACC_FULL = BAR_G_FULL + 2,        // BWD: accumulator complete for this segment  (every CTA)
   BAR_ACC_EMPTY,                        // BWD: accumulator drained                    (leader)
-  BAR_A_FREE,                           // BWD: accumulator flush no longer reads the owner area
-  BAR_COUNT
+  BAR_A_FREE,                           // [slabs] STEP: the flush's TMA store has read owner slab k (own CTA)
+  BAR_COUNT = BAR_A_FREE + kMaxSlabs
 };
 
 // tensor maps of one launch; index = segment kind (FWD: [SEG_DE] only)
@@ -254,7 +254,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
     }
     mbar_init(bar(BAR_ACC_FULL), 1);
     mbar_init(bar(BAR_ACC_EMPTY), kEpiArrivals);
-    mbar_init(bar(BAR_A_FREE), 1);
+    for (int i = 0; i < kMaxSlabs; ++i) mbar_init(bar(BAR_A_FREE + i), 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -336,19 +336,19 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
       const CUtensorMap* tm_k = &tms.strk[kind];
       const CUtensorMap* tm_mn = &tms.strmn[kind];
       const int ot = og * CG + cr;      // may be >= OT in the last group: TMA zero-fills, nothing is stored
-      if (sg > 0) {
-        mbar_wait(bar(BAR_A_EMPTY), (sg - 1) & 1);
-        if (kBwd) mbar_wait(bar(BAR_A_FREE), (sg - 1) & 1);   // the accumulator flush stages through the owner area
-      }
+      if (sg > 0) mbar_wait(bar(BAR_A_EMPTY), (sg - 1) & 1);      // every MMA1 of the previous segment has completed
       tr.mark();   // owner tile issue
-      if (elect_one()) {
-        for (int ks = 0; ks < kslabs; ++ks) {
+      for (int ks = 0; ks < kslabs; ++ks) {
+        // STEP: the previous segment's accumulator leaves through the owner area, slab by slab; slab ks is
+        // free again once the TMA store that took it out has read it
+        if (kBwd && sg > 0) mbar_wait(bar(BAR_A_FREE + ks), (sg - 1) & 1);
+        if (elect_one()) {
           if (leader) mbar_expect_tx(bar(BAR_A_FULL + ks), kSlabBytes * CG);
           if (CG == 1) tma_load_2d(a_smem + ks * kSlabBytes, tm_own, ks * kSlabCols, ot * kTile, bar(BAR_A_FULL + ks));
           else tma_load_2d_2cta(a_smem + ks * kSlabBytes, tm_own, ks * kSlabCols, ot * kTile, lbar(BAR_A_FULL + ks));
         }
+        __syncwarp();
       }
-      __syncwarp();
       if (!kBwd) {
         for (int u = s0; u < s1; u += kStepUnits) {
           const int nu = min(kStepUnits, s1 - u);
@@ -549,16 +549,21 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
     // STEP: between the passes.  Grid-wide barrier (every row sum complete), then each CTA closes a slice
     // of the rows: log-sum-exp, row loss, q = 1 - p_jj, the factor of the un-normalised dE_hat row; the
     // diagonal terms of dw and the closed-form db ride along.
+    bool arrived = false;        // this CTA's row sums are out and counted at the grid barrier
+    auto arrive_pass1 = [&]() {
+      __threadfence();
+      named_bar_sync(1, kEpiThreads);
+      if (et == 0) atomicAdd(p.ctr + 2, 1);
+      arrived = true;
+      tr.mark();   // arrived at the grid barrier
+    };
     auto close_rows = [&]() {
       if (p.phases & PASS_ROWS) {
-        __threadfence();
-        named_bar_sync(1, kEpiThreads);
-        if (et == 0) {
-          atomicAdd(p.ctr + 2, 1);
-          spin_until(p.ctr + 2, static_cast<int>(gridDim.x));
-        }
+        if (!arrived) arrive_pass1();      // a cluster without pass-1 work
+        if (et == 0) spin_until(p.ctr + 2, static_cast<int>(gridDim.x));
         named_bar_sync(1, kEpiThreads);
       }
+      tr.mark();   // grid barrier passed
       const int U = p.n_own[SEG_DE];
       for (int r = blockIdx.x * kEpiThreads + et; r < U; r += gridDim.x * kEpiThreads) {
         const float cdv = __ldg(p.cos_diag + r);
@@ -580,6 +585,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
           db_acc -= eps * expf(-stat);              // item 12: db = -g sum eps / (sum exp + eps)
         }
       }
+      tr.mark();   // rows closed
     };
     bool closed = false;
 
@@ -805,11 +811,22 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
           }
         }
       } else {
+        // pass 1: the row sums are final once the last tile has been consumed -- they do not wait for the
+        // accumulator; after the cluster's last pass-1 segment the CTA arrives at the grid barrier BEFORE
+        // it flushes, so the flush runs under the barrier's skew instead of in front of it
+        if (!is_dc) {
+          if (et == 0) wait_zero_fill();
+          named_bar_sync(1, kEpiThreads);
+          if (ovalid) atomicAdd(p.rowsum + orow, rs_acc);
+          if (wk.kind == SEG_DE && wk.gp >= wk.end) arrive_pass1();
+        } else if (ovalid) {
+          dw_acc += dw_seg;
+        }
         // drain the accumulator [128 x D] of this segment (columns split between the two halves)
-        if (is_dc && ovalid) dw_acc += dw_seg;
         mbar_wait(bar(BAR_ACC_FULL), sg & 1);
         tc_fence_after();
-        // TMEM -> registers -> owner area of shared memory (free: every MMA of the segment has
+        tr.mark();   // accumulator complete
+        // TMEM -> registers -> owner area of shared memory (free: every MMA1 of the segment has
         // completed) in the 128B-swizzled slab layout -> one TMA store per 32-column slab.  A range
         // that covers the whole owner group stores, a partial range adds into the zeroed output
         // (cp.reduce.async.bulk: the fp32 add happens at the L2).  Rows past n_own are clipped.
@@ -829,21 +846,25 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
         tc_fence_before();
         __syncwarp();
         if (lane == 0) arrive_leader(acc_empty);
+        tr.mark();   // accumulator drained into shared memory
         fence_proxy_async_smem();
-        if (et == 0 && (!full || !is_dc)) wait_zero_fill();   // partial sums and row sums land in zeroed memory
         named_bar_sync(1, kEpiThreads);
-        if (!is_dc && ovalid) atomicAdd(p.rowsum + orow, rs_acc);
         if (et == 0) {
+          // one bulk group per slab: slab k goes back to the TMA warp (next owner tile) as soon as ITS store
+          // has read it, so the reload of the owner area interleaves with the flush instead of following it
           if (tile_valid) {
             const CUtensorMap* tm_out = &tms.out[kind];
+            if (!full) wait_zero_fill();
             for (int ks = 0; ks < kslabs; ++ks) {
               if (full) tma_store_2d(tm_out, ks * kSlabCols, ot * kTile, a_smem + ks * kSlabBytes);
               else tma_reduce_add_2d(tm_out, ks * kSlabCols, ot * kTile, a_smem + ks * kSlabBytes);
+              tma_store_commit();
             }
-            tma_store_commit();
-            tma_store_wait_read();
           }
-          mbar_arrive(bar(BAR_A_FREE));
+          for (int ks = 0; ks < kslabs; ++ks) {
+            if (tile_valid) tma_store_wait_read_pending(kslabs - 1 - ks);
+            mbar_arrive(bar(BAR_A_FREE + ks));
+          }
         }
       }
       tr.mark();   // segment flushed
@@ -1047,29 +1068,75 @@ Layout make_layout(int n_own, int n_str, int cg, int max_cl) {
   return L;
 }
 
-// Schedule of the step kernel (see the header comment): each pass is cut evenly over the clusters.
-// A pass whose owner groups can be dealt out whole without leaving any cluster more than 1/8 above the
-// level share keeps them whole (plain stores, one owner load per group); otherwise the flat pair list
-// is cut into equal contiguous ranges and the partial accumulators are reduce-added.  Returns the number
-// of clusters; *de_partial / *dc_partial tell the caller whether the outputs need a zero-fill.
+// Schedule of the step kernel (see the header comment).  A pass is `OG` owner groups of `ST` stream units;
+// cluster c works on the contiguous pair range [out[c], out[c + 1]).  Changing owner group inside a range
+// (a "straddle") costs an accumulator flush, an owner-tile load and a pipeline refill -- about kStraddle
+// units of work (measured: 8-9 us against 2.7 us per unit at config 3) -- so three cuts compete on the load
+// of the busiest cluster:
+//   whole     whole groups per cluster (plain stores, nothing to zero-fill)
+//   assigned  OG <= clusters: every cluster belongs to ONE group, whose units are split over its clusters
+//   flat      equal contiguous ranges of the flat pair list; ranges straddle groups
+// `delay[c]` (units, nullable) is how much later than the others cluster c can start this pass (pass 2: a
+// cluster that finishes pass 1 last flushes AFTER the grid barrier instead of under it); the assigned and
+// flat cuts hand such a cluster correspondingly fewer units.  Returns true when some group is cut.
+constexpr int kStraddle = 3;
+bool cut_pass(long long GP, int OG, int ST, int NC, const double* delay, int* out) {
+  if (GP == 0) { for (int c = 0; c <= NC; ++c) out[c] = 0; return false; }
+  const long long level = (GP + NC - 1) / NC;
+  const long long cost_whole = static_cast<long long>((OG + NC - 1) / NC) * ST;
+  const long long cost_flat = level + ((GP % NC == 0 && level % ST == 0) ? 0 : kStraddle);
+  long long cost_assigned = LLONG_MAX;
+  if (OG <= NC) {
+    const int n_min = NC / OG;                          // clusters of the least served group
+    cost_assigned = (ST + n_min - 1) / n_min;
+  }
+  // split `units` pairs starting at pair `base` over clusters [c0, c1) in proportion to K - delay[c]
+  auto split = [&](int c0, int c1, long long base, long long units) {
+    const int n = c1 - c0;
+    double dsum = 0;
+    for (int c = c0; c < c1; ++c) dsum += delay ? delay[c] : 0.0;
+    const double K = (static_cast<double>(units) + dsum) / n;
+    double wsum = 0, cum = 0;
+    for (int c = c0; c < c1; ++c) wsum += std::max(0.25, K - (delay ? delay[c] : 0.0));
+    for (int c = c0; c < c1; ++c) {
+      out[c] = static_cast<int>(base + static_cast<long long>(units * (cum / wsum) + 0.5));
+      cum += std::max(0.25, K - (delay ? delay[c] : 0.0));
+    }
+  };
+  if (cost_assigned <= cost_whole && cost_assigned <= cost_flat && OG < NC) {
+    for (int g = 0; g < OG; ++g) {
+      const int c0 = static_cast<int>(static_cast<long long>(g) * NC / OG);
+      const int c1 = static_cast<int>(static_cast<long long>(g + 1) * NC / OG);
+      split(c0, c1, static_cast<long long>(g) * ST, ST);
+    }
+    out[NC] = static_cast<int>(GP);
+    return NC > OG;
+  }
+  if (cost_whole <= cost_flat) {
+    for (int c = 0; c <= NC; ++c) out[c] = static_cast<int>((static_cast<long long>(c) * OG / NC) * ST);
+    return false;
+  }
+  split(0, NC, 0, GP);
+  out[NC] = static_cast<int>(GP);
+  return true;
+}
+
 int make_step_sched(int OGe, int STe, int OGc, int STc, int phases, int max_cl, StepSched* S, bool* de_partial,
                     bool* dc_partial) {
   const long long GPe = (phases & PASS_ROWS) ? static_cast<long long>(OGe) * STe : 0;
   const long long GPc = (phases & PASS_CENTROIDS) ? static_cast<long long>(OGc) * STc : 0;
   const int NC = static_cast<int>(std::max<long long>(1, std::min<long long>(max_cl, std::max(GPe, GPc))));
-  auto cut = [&](long long GP, int OG, int ST, int* out) -> bool {     // returns "some group is cut"
-    if (GP == 0) { for (int c = 0; c <= NC; ++c) out[c] = 0; return false; }
-    const long long level = (GP + NC - 1) / NC;
-    const long long whole_max = static_cast<long long>((OG + NC - 1) / NC) * ST;   // most loaded cluster, whole groups
-    if (whole_max <= level + level / 8) {
-      for (int c = 0; c <= NC; ++c) out[c] = static_cast<int>((static_cast<long long>(c) * OG / NC) * ST);
-      return false;
-    }
-    for (int c = 0; c <= NC; ++c) out[c] = static_cast<int>(static_cast<long long>(c) * GP / NC);
-    return true;
-  };
-  *de_partial = cut(GPe, OGe, STe, S->de);
-  *dc_partial = cut(GPc, OGc, STc, S->dc);
+  *de_partial = cut_pass(GPe, OGe, STe, NC, nullptr, S->de);
+  // pass 2 starts at the grid barrier, i.e. when the busiest cluster of pass 1 is done; whoever finishes
+  // pass 1 within ~kStraddle units of that moment still has its own flush in front of it
+  double delay[kMaxClusters];
+  long long busiest = 0;
+  for (int c = 0; c < NC; ++c) busiest = std::max<long long>(busiest, S->de[c + 1] - S->de[c]);
+  for (int c = 0; c < NC; ++c) {
+    const long long load = S->de[c + 1] - S->de[c];
+    delay[c] = (GPe > 0 && load > 0) ? std::max<double>(0.0, kStraddle - static_cast<double>(busiest - load)) : 0.0;
+  }
+  *dc_partial = cut_pass(GPc, OGc, STc, NC, (phases == (PASS_ROWS | PASS_CENTROIDS)) ? delay : nullptr, S->dc);
   return NC;
 }
 

@@ -113,6 +113,20 @@ __device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, int x, int y
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed bulk stores of this thread have finished READING shared memory
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all but the `pending` most recent bulk groups of this thread have finished reading shared memory
+// (groups complete in commit order; the count is an immediate operand)
+__device__ __forceinline__ void tma_store_wait_read_pending(int pending) {
+  switch (pending) {
+    case 0: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); break;
+    case 4: asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory"); break;
+    case 5: asm volatile("cp.async.bulk.wait_group.read 5;" ::: "memory"); break;
+    case 6: asm volatile("cp.async.bulk.wait_group.read 6;" ::: "memory"); break;
+    default: asm volatile("cp.async.bulk.wait_group.read 7;" ::: "memory"); break;
+  }
+}
 
 // ---------------------------------------------------------------- clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() {
