@@ -5,21 +5,25 @@
                     [--workload cfg1|cfg2|cfg3|cfg4] [--precision tf32|fp32] [--variant softmax|contrast]
 
 One "step" = one GE2E forward + backward (grads to E, w, b) over one synthetic batch.
-  value  device-resident inputs, the fwd+bwd C-ABI calls of K consecutive steps captured in ONE CUDA
-         graph.  The inputs ROTATE over a set of batches larger than the 126 MB L2 (every step reads
-         its batch from HBM); the K steps are bracketed by ONE pair of CUDA events on the launching
-         stream.  (One step per graph, timed alone between L2 flushes, carries ~6-9 us of graph
-         launch / event floor per step; it is reported next to it as ms_per_step_l2_flushed.)
-  e2e    the public module API (GE2ELoss(...)(E); loss.backward()) with the batch in pinned HOST
-         memory: H2D copy of E and D2H read of loss/dw/db inside the timed region.
-  roofline      the dominant kernel priced IN SITU: (step time) - (step time with that kernel left
-                out, ge2e_b200_debug_skip), same rotating-input event timing; the kernel timed alone
-                between L2 flushes is reported next to it.
-  cpu_baseline  the torch-CPU port of the reference's expanded algorithm (oracle/ge2e_ref_port.py)
-                on a bounded row sample of the same batch, all host threads.
-N=1 runs cfg3 (the config the metric is quoted on).  N>1 runs cfg4 (N=8192, M=16) speaker-sharded
-over the ranks (strong scaling: total work fixed); rank 0 also times cfg4 unsharded on its own GPU
-so the line carries its own 1-GPU denominator.
+  value  device-resident inputs, the C-ABI calls of K consecutive steps captured in ONE CUDA graph
+         (GE2EPlan.capture).  The inputs ROTATE over a set of batches larger than the 126 MB L2 (every step
+         reads its batch from HBM); a replay of the K steps is bracketed by ONE pair of CUDA events on the
+         launching stream; the reported time is the MEDIAN of 7 such replays (all listed in `replays_ms`).
+  e2e    the same metric with the batch in pinned HOST memory: H2D copy of E and D2H read of loss / dw / db
+         inside the timed region, through the public API (GE2EHostFeed, and the GE2ELoss module serially
+         and double-buffered; the fastest is the headline, all three are listed with the API they use).
+  roofline      the dominant kernel (the tensor-core step kernel: forward rows + both gradient
+                contractions) priced IN SITU: every CTA stamps %globaltimer at its start and end
+                (ge2e_b200_debug_stamps), max(end) - min(start) over the last step of a replay is the
+                kernel's duration inside the running graph; algorithmic flops 6 U N D.
+  fp32_path     cfg3 through the default precision of GE2ELoss(hp) ("fp32": SIMT FMA kernels), same timing.
+  cpu_baseline  the reference's own GE2ELoss (baseline/_ref, unmodified) where its O(N^2 M D) expansion fits
+                the host (cfg1, cfg2), else the torch-CPU port of it (oracle/ge2e_ref_port.py) on a bounded
+                row sample of the same batch; all host threads.
+N=1 runs cfg3 (the config the metric is quoted on).  N>1 runs cfg4 (N=8192, M=16) speaker-sharded over the
+ranks (strong scaling: total work fixed); every rank checks its shard of the result against the single-GPU
+plan on the same batch (parity_check, non-zero exit on failure) and rank 0 times cfg4 unsharded on its own
+GPU so the line carries its own 1-GPU denominator (scaling_efficiency_same_workload).
 """
 from __future__ import annotations
 
@@ -124,16 +128,65 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def real_reference_class():
+    """The reference's own GE2ELoss from baseline/_ref (scripts/install_reference.py), or None."""
+    if not os.path.isfile(os.path.join(REF_DIR, "embedding_model_GE2E", "s3_loss_function_GE2E.py")):
+        return None
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    try:
+        from embedding_model_GE2E.s3_loss_function_GE2E import GE2ELoss as RefLoss
+        from utils.dict_to_dot import GetDictWithDotNotation
+    except Exception:
+        return None
+    hp = GetDictWithDotNotation({"general": {"device": torch.device("cpu"), "small_err": 1e-6}})
+    return lambda: RefLoss(hp)
+
+
 def cpu_reference_sample(N, M, D, seed, target_rows):
-    """Time the reference-algorithm port on a bounded row sample; returns (utt/s, dict)."""
-    from oracle import ge2e_ref_port as port
+    """Time the reference on the host cores: its own class on the whole batch where the O(N^2 M D)
+    expansion fits (kind "reference"), else the port of it on a bounded row sample (kind "port").
+    Returns (utt/s, dict)."""
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    E = make_batch(N, M, D, seed).numpy()
     U = N * M
+    make = real_reference_class() if (target_rows >= U and U * N * D * 4 <= 2 << 30) else None
+    if make is not None:
+        crit = make()
+        E = make_batch(N, M, D, seed).requires_grad_(True)
+        best = None
+        for it in range(3):
+            E.grad = crit.w.grad = crit.b.grad = None
+            t0 = time.perf_counter()
+            loss = crit(E)
+            loss.backward()
+            dt = time.perf_counter() - t0
+            best = dt if best is None or it > 0 and dt < best else best      # iteration 0 warms the allocator
+        return U / best, dict(cores=threads, rows=U, seconds=best, kind="reference", loss=float(loss.detach()))
+    from oracle import ge2e_ref_port as port
+    E = make_batch(N, M, D, seed).numpy()
     rows = None if target_rows >= U else list(range(0, U, max(1, U // target_rows)))[:target_rows]
     sec, n_rows, _ = port.time_fwd_bwd(E, rows=rows, iters=1, warmup=0, threads=threads)
-    return n_rows / sec, dict(cores=threads, rows=n_rows, seconds=sec)
+    return n_rows / sec, dict(cores=threads, rows=n_rows, seconds=sec, kind="port")
+
+
+def config_of(wl, N, M, D, variant):
+    """The `config` object: identical keys and values in both arms (the driver compares them)."""
+    return {"workload": f"{wl}: N={N} M={M} D={D} {variant} GE2E fwd+bwd", "N": N, "M": M, "D": D, "variant": variant}
+
+
+def cpu_sample_text(info, N, M):
+    U = N * M
+    if info["kind"] == "reference":
+        return (f"the whole batch ({U} utterances), best of 2 timed iterations after 1 warm-up, {info['seconds']:.3f} s "
+                f"each: the reference's own GE2ELoss (baseline/_ref/embedding_model_GE2E/s3_loss_function_GE2E.py, "
+                f"unmodified) forward + backward on the host")
+    return (f"{info['rows']} of {U} utterance rows against all {N} centroids, 1 iteration, {info['seconds']:.2f} s "
+            f"(torch-CPU port of the reference's expanded algorithm, bit-checked against the real class; the full "
+            f"batch needs {4 * U * N * 256 / 1e9:.0f} GB per expanded tensor and does not fit host RAM)")
 
 
 def sample_rows_for(N, M, D):
@@ -161,11 +214,9 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic unit-norm random embeddings",
-        "config": {"workload": f"{wl}: N={N} M={M} D={D} softmax GE2E fwd+bwd", "N": N, "M": M, "D": D},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": "port",
-                         "sample": f"{info['rows']} of {N * M} utterance rows against all {N} centroids per step "
-                                   f"(the reference's O(N^2 M D) expansion of the full batch does not fit host RAM); "
-                                   f"torch-CPU port of s3_loss_function_GE2E.py, bit-checked against the real class"},
+        "config": config_of(wl, N, M, D, args.variant),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
+                         "sample": cpu_sample_text(info, N, M) + " (per step)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -195,63 +246,76 @@ def timed_steps(fn, steps, warmup, flush_buf, pre=None):
     return [a.elapsed_time(b) for a, b in evs]
 
 
-def timed_back_to_back(plan, batches, w, b, steps, warmup):
+def timed_back_to_back(plan, batches, w, b, steps, warmup, reps=7):
     """EXACTLY `steps` steps, rotating over `batches`, captured as ONE CUDA graph (the steps are
     stream-ordered exactly as a training loop would enqueue them).  The graph is replayed untimed
     until at least `warmup` steps have run (the first replay of a graph also pays its upload), then
-    once more inside one CUDA-event pair.  Returns ms per step."""
+    `reps` times, each inside one CUDA-event pair.  Returns (median ms per step, [ms per step of each replay])."""
     g = plan.capture(batches, w, b, steps=steps)
     for _ in range(max(1, -(-warmup // steps))):
         g.replay()
     torch.cuda.synchronize()
-    a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    g.replay()
-    e.record()
-    torch.cuda.synchronize()
-    return a.elapsed_time(e) / steps
+    out = []
+    for _ in range(reps):
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        g.replay()
+        e.record()
+        torch.cuda.synchronize()
+        out.append(a.elapsed_time(e) / steps)
+    return float(np.median(out)), out
 
 
-def insitu_costs(plan, batches, w, b, steps, warmup):
-    """Per-kernel cost inside the step: full step minus the step captured without that kernel."""
+def step_kernel_in_situ(plan, batches, w, b, steps, warmup, reps=5):
+    """Duration of the tensor-core step kernel INSIDE the running graph: every CTA of the kernel stamps
+    %globaltimer at its start and end (production kernel, two stores per CTA); after a replay the buffer
+    holds the stamps of the replay's last step.  Returns the median over `reps` replays in microseconds,
+    or None when the plan does not run the step kernel."""
     from speaker_embedding_ge2e_loss_b200 import lib
     h = lib()
-    out = {}
+    stamps = torch.zeros(2 * 512, dtype=torch.int64, device=batches[0].device)
+    h.ge2e_b200_debug_stamps(stamps.data_ptr())
     try:
-        for name, mask in (("full", 0), ("prep", 1), ("fwd_rows", 2), ("bwd_rows", 12), ("bwd_finalize", 16)):
-            h.ge2e_b200_debug_skip(mask)
-            out[name] = timed_back_to_back(plan, batches, w, b, steps, warmup) * 1e3      # microseconds per step
+        g = plan.capture(batches, w, b, steps=steps)
+        for _ in range(max(1, -(-warmup // steps))):
+            g.replay()
+        vals = []
+        for _ in range(reps):
+            stamps.zero_()
+            g.replay()
+            torch.cuda.synchronize()
+            st = stamps.cpu().numpy().reshape(-1, 2)
+            st = st[(st[:, 0] > 0) & (st[:, 1] > 0)]
+            if len(st) == 0:
+                return None
+            vals.append(float(st[:, 1].max() - st[:, 0].min()) / 1e3)
     finally:
-        h.ge2e_b200_debug_skip(0)
-    full = out.pop("full")
-    return {k: full - v for k, v in out.items()}, full
+        h.ge2e_b200_debug_stamps(None)
+    return float(np.median(vals))
 
 
 def stage_times(plan, E, w, b, flush_buf, reps=20):
-    """CUDA-event time of each C-ABI stage (prep | fwd_rows | bwd_rows | bwd_finalize) alone."""
+    """CUDA-event time of each C-ABI stage (prep | step_rows | bwd_finalize) alone, L2 flushed before each."""
     from speaker_embedding_ge2e_loss_b200 import lib
     h = lib()
     N, M, D = plan.N, plan.M, plan.D
     s = torch.cuda.current_stream().cuda_stream
     ws = plan._ws.data_ptr() if plan._ws_bytes else None
     acc = plan._accum.data_ptr()
-    scr = plan._scratch.data_ptr()
+    scaled = plan.path == 1 and plan.variant == 0
     calls = {
         "prep": lambda: h.ge2e_b200_prep(E.data_ptr(), N, M, D, plan.precision, plan.e_hat.data_ptr(),
                                          plan.c_hat.data_ptr(), plan.cos_diag.data_ptr(), acc, s),
-        "fwd_rows": lambda: h.ge2e_b200_fwd_rows(plan.e_hat.data_ptr(), plan.c_hat.data_ptr(), plan.cos_diag.data_ptr(),
-                                                 N, N, 0, M, D, w.data_ptr(), b.data_ptr(), plan.eps, plan.variant,
-                                                 plan.precision, plan.row_stat.data_ptr(), plan.row_kstar.data_ptr(),
-                                                 plan.row_aux.data_ptr(), acc, None, None, ws, plan._ws_bytes, s),
-        "bwd_rows": lambda: h.ge2e_b200_bwd_rows(plan.e_hat.data_ptr(), plan.c_hat.data_ptr(), plan.cos_diag.data_ptr(),
-                                                 plan.row_stat.data_ptr(), plan.row_kstar.data_ptr(),
-                                                 plan.row_aux.data_ptr(), N, N, 0, M, D,
-                                                 w.data_ptr(), b.data_ptr(), plan.eps, plan.variant, plan.precision,
-                                                 plan.grad_out.data_ptr(), plan.dE_hat.data_ptr(), scr,
-                                                 scr + N * D * 4, ws, plan._ws_bytes, s),
-        "bwd_finalize": lambda: h.ge2e_b200_bwd_finalize(E.data_ptr(), plan.dE_hat.data_ptr(), scr,
+        "step_rows": lambda: h.ge2e_b200_step_rows(plan.e_hat.data_ptr(), plan.c_hat.data_ptr(), plan.cos_diag.data_ptr(),
+                                                   N, N, 0, M, D, w.data_ptr(), b.data_ptr(), plan.eps, plan.variant,
+                                                   plan.precision, plan.grad_out.data_ptr(), plan.row_stat.data_ptr(),
+                                                   plan.row_kstar.data_ptr(), plan.row_aux.data_ptr(),
+                                                   plan.row_scale.data_ptr(), acc, plan.dE_hat.data_ptr(),
+                                                   plan.dC_hat.data_ptr(), ws, plan._ws_bytes, s),
+        "bwd_finalize": lambda: h.ge2e_b200_bwd_finalize(E.data_ptr(), plan.dE_hat.data_ptr(), plan.dC_hat.data_ptr(),
                                                          plan.cos_diag.data_ptr(), plan.row_stat.data_ptr(),
-                                                         plan.row_aux.data_ptr(), N, M, D,
+                                                         plan.row_aux.data_ptr(),
+                                                         plan.row_scale.data_ptr() if scaled else None, N, M, D,
                                                          w.data_ptr(), b.data_ptr(), plan.eps, plan.variant,
                                                          plan.grad_out.data_ptr(), plan.dE.data_ptr(), s),
     }
@@ -261,8 +325,31 @@ def stage_times(plan, E, w, b, flush_buf, reps=20):
             rc = fn()
             assert rc == 0, (name, rc)
         ms = timed_steps(run, reps, 3, flush_buf)
-        out[name] = float(np.mean(ms)) * 1e3      # microseconds
+        out[name] = float(np.median(ms)) * 1e3      # microseconds
     return out
+
+
+def wait_for_clocks(sampler_index, seconds=3.0):
+    """Spin a small kernel until NVML reports the SM clock within 5 % of its maximum (or `seconds` pass): a
+    GPU that idled during host-side set-up ramps its clocks only gradually under a copy-dominated load."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hd = pynvml.nvmlDeviceGetHandleByIndex(sampler_index)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(hd, pynvml.NVML_CLOCK_SM)
+    except Exception:
+        return None
+    x = torch.randn(4096, 4096, device="cuda")
+    t0 = time.perf_counter()
+    mhz = 0
+    while time.perf_counter() - t0 < seconds:
+        for _ in range(20):
+            x = torch.mm(x, x).clamp_(-1, 1)
+        torch.cuda.synchronize()
+        mhz = pynvml.nvmlDeviceGetClockInfo(hd, pynvml.NVML_CLOCK_SM)
+        if mhz >= 0.95 * mx:
+            break
+    return {"sm_mhz": mhz, "sm_max_mhz": mx, "waited_s": round(time.perf_counter() - t0, 3)}
 
 
 def measure_tf32_peak():
@@ -324,11 +411,13 @@ def run_ours(args):
         E = batches[0]
         plan = GE2EPlan(N, M, D, args.variant, args.precision, device=dev)
         sampler.start()
-        ms = [timed_back_to_back(plan, batches, w, b, args.steps, args.warmup)] * args.steps
+        ms_med, replays = timed_back_to_back(plan, batches, w, b, args.steps, args.warmup)
+        ms = [ms_med] * args.steps
         clocks = sampler.finish()
+        extra["replays_ms"] = [round(x, 6) for x in replays]
         g1 = plan.capture(E, w, b)
         launches = plan.launches_per_step * args.steps
-        extra["ms_per_step_l2_flushed"] = float(np.mean(timed_steps(g1.replay, args.steps, args.warmup, flush)))
+        extra["ms_per_step_l2_flushed"] = float(np.median(timed_steps(g1.replay, args.steps, args.warmup, flush)))
         path = plan.path
         g1.replay()
         loss_val = plan.loss.item()
@@ -422,21 +511,14 @@ def run_ours(args):
                 prev = t
             return feed.result(prev)
 
-        # warm-up until the rate settles: after the host-side set-up above the GPU has idled and its clocks
-        # ramp back only gradually under this copy-dominated load (scripts/h2d_probe.py: 640 -> 195 us/step
-        # over ~250 steps on a fresh feed); steady state is what a training loop sees
+        # warm-up: after the host-side set-up above the GPU has idled and its clocks ramp back only gradually
+        # under this copy-dominated load (scripts/h2d_probe.py: 640 -> 195 us/step over ~250 steps on a fresh
+        # feed).  Bring the SM clock back to its maximum with a compute kernel (NVML reading, not a rate
+        # heuristic), then run a fixed 200 feed steps; steady state is what a training loop sees
         fed(max(4, args.warmup))
-        last, fed_warm = None, max(4, args.warmup)
-        for _ in range(20):
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            fed(50)
-            torch.cuda.synchronize()
-            cur = time.perf_counter() - t0
-            fed_warm += 50
-            if last is not None and abs(cur - last) <= 0.03 * last:
-                break
-            last = cur
+        fed_clock = wait_for_clocks(local_rank)
+        fed(200)
+        fed_warm = max(4, args.warmup) + 200
         torch.cuda.synchronize()
         fe0, fe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
@@ -450,47 +532,73 @@ def run_ours(args):
         fedd = {"value": U / (fed_t * 1e-3), "ms_per_step_device": fed_dev, "ms_per_step_wall": fed_wall,
                 "how": "GE2EHostFeed: H2D of batch k+1 on a copy stream under the graph-captured fwd+bwd+result read of "
                        "batch k; every step's loss/dw/db read on the host", "last_result": list(fed_last),
-                "warmup_steps": fed_warm,
+                "warmup_steps": fed_warm, "clock_before_warmup": fed_clock,
                 "h2d_gbps": E_host.numel() * 4 / (fed_t * 1e-3) / 1e9}
         cands = {"host_fed_plan": fedd, "module_api_pipelined": piped, "module_api_serial": serial}
         bname = min(cands, key=lambda k: U / cands[k]["value"])
         best = cands[bname]
+        apis = {"host_fed_plan": "GE2EHostFeed.submit / .result (graph-captured step per slot)",
+                "module_api_pipelined": "GE2ELoss(hp)(E); loss.backward() (the call s4_train_embed_model.py:196-200 "
+                                        "makes), batches double-buffered by the caller",
+                "module_api_serial": "GE2ELoss(hp)(E); loss.backward() (the call s4_train_embed_model.py:196-200 makes)"}
+        for k in cands:
+            cands[k]["api"] = apis[k]
         e2e = {"value": best["value"], "unit": UNIT, "h2d_bytes_per_step": E_host.numel() * 4,
                "d2h_bytes_per_step": 12, "ms_per_step_device": best["ms_per_step_device"],
-               "ms_per_step_wall": best["ms_per_step_wall"], "how": bname + ": " + best["how"]}
+               "ms_per_step_wall": best["ms_per_step_wall"], "how": bname + ": " + best["how"], "api": apis[bname]}
         e2e.update({k: v for k, v in cands.items() if k != bname})
 
-        # ---- roofline of the dominant stage ---------------------------------------------------
+        # ---- roofline of the dominant kernel --------------------------------------------------
         st = stage_times(plan, E, w, b, flush)
-        insitu, full_us = insitu_costs(plan, batches, w, b, max(10, args.steps), max(3, args.warmup))
         tf32_peak = measure_tf32_peak()
         extra["stage_us_alone_l2_flushed"] = st
-        extra["stage_us_in_situ"] = insitu
         extra["tf32_cublas_tflops_measured_here"] = tf32_peak
-        dom = max(("fwd_rows", "bwd_rows"), key=lambda k: insitu[k])
-        flops = {"fwd_rows": 2.0 * U * N * D, "bwd_rows": 4.0 * U * N * D}[dom]
-        if getattr(plan, "single_kernel", False):
-            # reference-sized batch: the whole step IS one kernel (the stage prices above are the pipeline's,
-            # which the debug skip masks fall back to); score the step itself
-            dom, flops = "small_step_kernel (whole fwd+bwd step)", 6.0 * U * N * D
-            insitu = dict(insitu)
-            insitu[dom] = float(np.mean(ms)) * 1e3
-            extra["stage_us_in_situ_note"] = "pipeline kernels (GE2E_SMALL_STEP=0 equivalent); the timed step is the single kernel"
-        achieved = flops / (insitu[dom] * 1e-6) / 1e12
+        step_us = ms_med * 1e3
+        flops = 6.0 * U * N * D
+        kern_us = step_kernel_in_situ(plan, batches, w, b, max(10, args.steps), max(3, args.warmup)) if path == 1 else None
+        if kern_us is not None:
+            dom, how = "tc_strip_kernel<STEP> (forward rows + dE_hat pass, grid barrier, dC_hat pass)", \
+                "in situ: max(CTA end) - min(CTA start) of the kernel's %globaltimer stamps in the last step of a graph replay"
+            extra["step_us_outside_the_step_kernel"] = step_us - kern_us
+        elif getattr(plan, "single_kernel", False):
+            dom, kern_us, how = "small_step_kernel (whole fwd+bwd step)", step_us, "the step is this one kernel: step time"
+        else:
+            # SIMT pipeline (fp32 path, contrast backward): the rows kernels dominate; priced alone, L2 flushed
+            dom, kern_us, how = "strip_kernel x3 (ge2e_b200_step_rows)", min(st["step_rows"], step_us), \
+                "C-ABI stage timed alone between L2 flushes (CUDA events), capped by the step time"
+        achieved = flops / (kern_us * 1e-6) / 1e12
         if path == 1:
-            # a ~75 us step is a burst; the multi-millisecond cfg4 step runs under the power cap
+            # a < 0.1 ms step is a burst; the multi-millisecond cfg4 step runs under the power cap
             key = "bf16_tflops" if wl != "cfg4" else "bf16_tflops_sustained"
             peak, peak_note = peaks[key] / 2, f"MEASURED_PEAKS {key}/2 (TF32 runs at half the bf16 rate), {peaks['source']}"
         else:
             peak, peak_note = 148 * 128 * 2 * 1.965e9 / 1e12, "nominal fp32 FMA 148 SM x 128 lanes x 2 x 1.965 GHz (SIMT path; no measured entry)"
         roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": ncu_traffic(dom) if wl == "cfg3" else None, "peak_source": peak_note,
-                    "traffic_note": "DRAM bytes per launch from the committed ncu --set full capture (cold L2), "
-                                    "profiles/r1_ncu_v6_tc_kernels.txt; operands are L2-resident in situ",
-                    "kernel_us": insitu[dom], "kernel_us_how": "in situ: step - step without the kernel (CUDA events, "
-                    "rotating inputs > L2)", "algorithmic_flops": flops,
-                    "note": "algorithmic flops only: the S recomputation inside the backward (another 4 U N D) is not credited",
-                    "step_frac": (6.0 * U * N * D / (float(np.mean(ms)) * 1e-3) / 1e12) / peak}
+                    "frac": achieved / peak, "traffic": ncu_traffic("step") if (wl == "cfg3" and path == 1) else None,
+                    "peak_source": peak_note,
+                    "traffic_note": "DRAM bytes per launch from the committed ncu --set full capture (cold L2), see "
+                                    "profiles/ncu_traffic.json; operands are L2-resident in situ",
+                    "kernel_us": kern_us, "kernel_us_how": how, "algorithmic_flops": flops,
+                    "issued_flops": 8.0 * U * N * D if path == 1 else None,
+                    "note": "algorithmic flops only (6 U N D: S, dE_hat, dC_hat); the second computation of S "
+                            "for the dC_hat pass (another 2 U N D) is not credited",
+                    "step_frac": (flops / (step_us * 1e-6) / 1e12) / peak}
+
+        # ---- the default precision of the drop-in module on the same workload ----------------
+        if wl == "cfg3" and args.precision == "tf32" and args.variant == "softmax":
+            plan32 = GE2EPlan(N, M, D, args.variant, "fp32", device=dev)
+            k32 = max(3, min(args.steps, 10))
+            ms32, rep32 = timed_back_to_back(plan32, batches, w, b, k32, 3, reps=3)
+            fma_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+            extra["fp32_path"] = {"ms_per_step": ms32, "value": U / (ms32 * 1e-3), "unit": UNIT, "steps": k32,
+                                  "replays_ms": [round(x, 5) for x in rep32], "path": "simt-fp32",
+                                  "frac_vs_fp32_fma_roof": (flops / (ms32 * 1e-3) / 1e12) / fma_peak,
+                                  "frac_vs_tf32_roof_div3": (flops / (ms32 * 1e-3) / 1e12) / (peaks["bf16_tflops"] / 2 / 3),
+                                  "loss": float(plan32.loss.item()),
+                                  "note": "GE2ELoss(hp) defaults to precision='fp32' (reference arithmetic, 1e-5 parity): "
+                                          "this line; precision='tf32' (or hp.general.ge2e_precision) selects the "
+                                          "tensor-core path of the headline"}
+            del plan32
     else:
         from speaker_embedding_ge2e_loss_b200.sharded import sharded_ge2e_loss
         off, n_local = shard_bounds(N, world, rank)
@@ -539,9 +647,30 @@ def run_ours(args):
             t = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = [t.item() / args.steps] * args.steps
-            splan.step(shards[0], w, b)                     # same batch as the autograd check below
+            splan.step(shards[0], w, b)                     # same batch as the checks below
             torch.cuda.synchronize()
             extra["sharded_loss_check"] = {"graph_plan": splan.loss.item()}
+            # ---- parity: every rank runs the WHOLE batch through the single-GPU plan on its own GPU and
+            # compares its shard of dE and the global loss / dw / db; the worst rank decides
+            tol = 2e-3 if args.precision == "tf32" else 1e-5
+            E1 = E_full.to(dev)
+            plan1 = GE2EPlan(N, M, D, args.variant, args.precision, device=dev)
+            plan1.step(E1, w, b)
+            torch.cuda.synchronize()
+            ref_dE = plan1.dE[off:off + n_local].double()
+            errs = torch.tensor([
+                ((splan.dE.double() - ref_dE).norm() / ref_dE.norm().clamp_min(1e-30)).item(),
+                abs(splan.loss.item() - plan1.loss.item()) / max(1.0, abs(plan1.loss.item())),
+                abs(splan.dw.item() - plan1.dw.item()) / max(1.0, abs(plan1.dw.item())),
+                abs(splan.db.item() - plan1.db.item()) / (1e-5 * U / tol),       # db: absolute 1e-5 * U
+            ], device=dev, dtype=torch.float64)
+            dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+            parity = {"dE_rel": errs[0].item(), "loss": errs[1].item(), "dw": errs[2].item(),
+                      "db_abs": errs[3].item() * (1e-5 * U / tol), "tol": tol, "ok": bool((errs <= tol).all().item()),
+                      "against": "GE2EPlan on the whole batch on each rank's own GPU (max over ranks); the plan itself "
+                                 "is checked against the float64 oracle at this size in tests/test_gpu_step.py"}
+            extra["parity_check"] = parity
+            del E1, plan1
             sharded_how = (f"K steps incl. NCCL collectives in one CUDA graph, shard rotating over {n_rot} batches "
                            f"({n_rot * n_local * M * D * 4 / 1e6:.0f} MB), one event pair, max over ranks")
         launches = int(lib().ge2e_b200_launch_count() - launches_before)
@@ -631,12 +760,18 @@ def run_ours(args):
             E1 = E_full.to(dev)
             plan1 = GE2EPlan(N, M, D, args.variant, args.precision, device=dev)
             g1 = plan1.capture(E1, w, b)
-            ms1 = timed_steps(g1.replay, max(3, args.steps // 2), 3, flush)
-            extra["single_gpu_same_workload"] = {"value": U / (float(np.mean(ms1)) * 1e-3), "unit": UNIT,
-                                                 "ms_per_step": float(np.mean(ms1))}
-            del E1, plan1
+            ms1 = float(np.median(timed_steps(g1.replay, max(5, args.steps // 2), 3, flush)))
+            extra["single_gpu_same_workload"] = {"value": U / (ms1 * 1e-3), "unit": UNIT, "ms_per_step": ms1}
+            extra["scaling_efficiency_same_workload"] = ms1 / (world * ms[0])
+            del E1, plan1, g1
         dist.barrier()
 
+    if world > 1:
+        g = splan = feed = shards = fhosts = step = e2e_step = fed = fed_timed = None   # drop the graphs that hold NCCL nodes
+    if world > 1 and not extra.get("parity_check", {"ok": True})["ok"]:
+        if rank == 0:
+            print(json.dumps({"error": "sharded result does not match the single-GPU plan", **extra["parity_check"]}))
+        _leave(world, code=3)
     if rank != 0:
         _leave(world)
         return
@@ -650,35 +785,50 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
         "dtype": "tf32" if path == 1 else "f32", "data": "synthetic unit-norm random embeddings",
-        "config": {"workload": f"{wl}: N={N} M={M} D={D} {args.variant} GE2E fwd+bwd", "N": N, "M": M, "D": D,
-                   "variant": args.variant, "precision": args.precision,
-                   "path": "tcgen05-tf32" if path == 1 else "simt-fp32",
-                   "parallelism": "replica" if world == 1 else f"speakers sharded x{world} (all-gather c_hat, reduce-scatter dC_hat)",
-                   "l2": (f"inputs larger than L2: the step rotates over {n_rot} batches ({n_rot * U * D * 4 / 1e6:.0f} MB), "
-                          "no flush") if world == 1 else sharded_how,
-                   "timing": "one CUDA-event pair around the K steps, captured as one CUDA graph"
-                   if world == 1 else sharded_how},
+        "config": config_of(wl, N, M, D, args.variant),
+        "run": {"precision": args.precision, "path": "tcgen05-tf32" if path == 1 else "simt-fp32",
+                "parallelism": "replica" if world == 1 else f"speakers sharded x{world} (all-gather c_hat, reduce-scatter dC_hat)",
+                "l2": (f"inputs larger than L2: the step rotates over {n_rot} batches ({n_rot * U * D * 4 / 1e6:.0f} MB), "
+                       "no flush") if world == 1 else sharded_how,
+                "timing": "median of 7 replays of the K steps captured as one CUDA graph, one CUDA-event pair per replay"
+                if world == 1 else sharded_how},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "loss": loss_val,
     }
     if cpu_val is not None:
-        line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": cpu_info["cores"], "kind": "port",
-                                "sample": f"{cpu_info['rows']} of {U} utterance rows against all {N} centroids, "
-                                          f"1 iteration, {cpu_info['seconds']:.2f} s (torch-CPU port of the reference's "
-                                          f"expanded algorithm; the full batch does not fit host RAM at this N)"}
+        line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": cpu_info["cores"], "kind": cpu_info["kind"],
+                                "sample": cpu_sample_text(cpu_info, N, M)}
     line.update(extra)
     print(json.dumps(line))
     _leave(world)
 
 
-def _leave(world):
-    """End a multi-rank run without tearing the NCCL communicator down: destroying a communicator whose
-    collectives live inside an instantiated CUDA graph blocks (seen on 2 GPUs: both ranks printed and then sat
-    in destroy_process_group until the outer timeout).  All results are out by now, so flush and exit 0."""
-    if world > 1:
-        torch.cuda.synchronize()
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+def _leave(world, code=0):
+    """End a multi-rank run.  The instantiated CUDA graphs that hold NCCL collectives are destroyed FIRST
+    (garbage-collect every plan / feed / graph object, synchronise); only then is the communicator torn down.
+    Destroying it while such a graph was alive blocked both ranks in round 1.  The teardown runs under a
+    watchdog: all results are out by now, so a communicator that still refuses to die within 20 s does not
+    turn a finished measurement into a failure."""
+    if world <= 1:
+        if code:
+            sys.exit(code)
+        return
+    import gc
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    gc.collect()
+    torch.cuda.synchronize()
+    killer = threading.Timer(20.0, lambda: os._exit(code))
+    killer.daemon = True
+    killer.start()
+    try:
+        dist.destroy_process_group()
+    except Exception:
+        pass
+    killer.cancel()
+    sys.stdout.flush()
+    os._exit(code)
 
 
 def main():

@@ -551,9 +551,8 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
     // diagonal terms of dw and the closed-form db ride along.
     bool arrived = false;        // this CTA's row sums are out and counted at the grid barrier
     auto arrive_pass1 = [&]() {
-      __threadfence();
-      named_bar_sync(1, kEpiThreads);
-      if (et == 0) atomicAdd(p.ctr + 2, 1);
+      named_bar_sync(1, kEpiThreads);      // every thread's row-sum atomics have returned
+      if (et == 0) { __threadfence(); atomicAdd(p.ctr + 2, 1); }
       arrived = true;
       tr.mark();   // arrived at the grid barrier
     };
@@ -817,7 +816,12 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
         if (!is_dc) {
           if (et == 0) wait_zero_fill();
           named_bar_sync(1, kEpiThreads);
-          if (ovalid) atomicAdd(p.rowsum + orow, rs_acc);
+          // value-returning atomics: when the old value is back the add has been performed at the L2, so
+          // the barrier arrival below needs no device-wide fence behind 256 outstanding reductions
+          if (ovalid) {
+            const float old = atomicAdd(p.rowsum + orow, rs_acc);
+            asm volatile("" ::"f"(old));
+          }
           if (wk.kind == SEG_DE && wk.gp >= wk.end) arrive_pass1();
         } else if (ovalid) {
           dw_acc += dw_seg;

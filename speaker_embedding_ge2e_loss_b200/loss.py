@@ -27,9 +27,14 @@ def _hp_get(hp, name, default):
 
 
 class GE2ELoss(nn.Module):
-    def __init__(self, hp=None, *, w: float = 10.0, b: float = -5.0, variant: str = "softmax",
-                 precision: str = "fp32", eps=None, device=None, process_group=None):
+    def __init__(self, hp=None, *, w: float = 10.0, b: float = -5.0, variant=None,
+                 precision=None, eps=None, device=None, process_group=None):
         super().__init__()
+        # the reference's trainer constructs GE2ELoss(hp) with no keywords (s4_train_embed_model.py:33):
+        # the two opt-in extensions can therefore also come from hp.general (ge2e_variant / ge2e_precision);
+        # absent both, the defaults reproduce the reference (softmax, fp32 arithmetic)
+        variant = variant if variant is not None else _hp_get(hp, "ge2e_variant", "softmax")
+        precision = precision if precision is not None else _hp_get(hp, "ge2e_precision", "fp32")
         if variant not in _lib.VARIANTS:
             raise ValueError(f"variant must be one of {sorted(_lib.VARIANTS)}")
         if precision not in _lib.PRECISIONS:
