@@ -1753,9 +1753,20 @@ bool small_step_preferred(int N, int M, int D, int variant) {
   return small_step_supported(N, M, D) && N <= (variant == GE2E_CONTRAST ? kSmallPickNContrast : kSmallPickN);
 }
 
+// The kernel's grid barriers need all N CTAs co-resident.  Counting one CTA per SM of the CURRENT device is
+// conservative (small shapes would fit several) and also holds on a MIG slice, whose SM count is what the
+// attribute reports; a device with fewer SMs than speakers takes the multi-kernel pipeline instead.
+static int device_sm_count() {
+  static int n[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (n[dev] == 0 && cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n[dev] = 0;
+  return n[dev];
+}
+
 bool small_step_supported(int N, int M, int D) {
   return N >= 1 && N <= kSmallMaxN && M >= 2 && M <= kSmallMaxM && D >= 1 && D <= kSmallMaxD &&
-         small_smem_bytes(N, M, D) <= 200 * 1024;
+         small_smem_bytes(N, M, D) <= 200 * 1024 && N <= device_sm_count();
 }
 
 size_t small_step_workspace_bytes(int N, int M, int D) {

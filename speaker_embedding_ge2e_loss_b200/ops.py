@@ -253,28 +253,173 @@ def _fwd_backward(ctx, g_loss, *_unused):
 ge2e_fwd.register_autograd(_fwd_backward, setup_context=_fwd_setup)
 
 
+# --------------------------------------------------------------------------- eager module path
+# What `loss = crit(E); loss.backward()` (s4_train_embed_model.py:196-200) costs on the host matters as much
+# as the kernels at the reference's batch sizes, so the eager path keeps one _EagerPlan per (device, shape,
+# variant, precision): kernel path and workspace size queried once, the intermediates of a step (e_hat,
+# c_hat, row statistics, dE_hat, dC_hat: one allocation) taken from a small pool and handed back when the
+# autograd node that uses them dies, their pointers pre-bound.  Per step only what ESCAPES to the caller is
+# allocated: the 4-float accumulator behind the loss tensor, the one behind dw / db, and dE.
+_RAW_STREAM = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
+def _raw_stream(dev_index: int) -> int:
+    if _RAW_STREAM is not None:
+        return _RAW_STREAM(dev_index)
+    return torch.cuda.current_stream(dev_index).cuda_stream
+
+
+class _StepBufs:
+    __slots__ = ("flat", "kstar", "e_hat", "c_hat", "cos_diag", "row_stat", "row_aux", "dE_hat", "row_scale", "dC_hat",
+                 "fwd_ptrs", "plan", "pooled", "__weakref__")
+
+    def __init__(self, plan, pooled: bool):
+        N, M, D, U = plan.N, plan.M, plan.D, plan.U
+        dev = plan.device
+        nh, ns = (U * D, U) if plan.fused else (0, 0)
+        flat = torch.empty(2 * U * D + 2 * N * D + 3 * U + ns, dtype=torch.float32, device=dev)
+        o = 0
+
+        def take(n):
+            nonlocal o
+            v = flat[o:o + n]
+            o += n
+            return v
+        self.flat = flat
+        self.e_hat = take(U * D)
+        self.c_hat = take(N * D)
+        self.dE_hat = take(U * D)              # forward (tensor-core softmax) or backward scratch
+        self.dC_hat = take(N * D)
+        self.cos_diag, self.row_stat, self.row_aux = take(U), take(U), take(U)
+        self.row_scale = take(ns) if ns else None
+        self.kstar = torch.empty(U if plan.variant == _lib.CONTRAST else 1, dtype=torch.int32, device=dev)
+        self.plan, self.pooled = plan, pooled
+        self.fwd_ptrs = (self.e_hat.data_ptr(), self.c_hat.data_ptr(), self.cos_diag.data_ptr(), self.row_stat.data_ptr(),
+                         self.kstar.data_ptr(), self.row_aux.data_ptr())
+
+
+class _EagerPlan:
+    __slots__ = ("N", "M", "D", "U", "variant", "precision", "device", "dev_index", "path", "fused", "ws_bytes", "free")
+
+    def __init__(self, dev, N, M, D, variant, precision):
+        self.N, self.M, self.D, self.U = N, M, D, N * M
+        self.variant, self.precision, self.device = variant, precision, dev
+        self.dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+        h = lib()
+        self.path = h.ge2e_b200_path(N, N, M, D, variant, precision)
+        self.fused = variant == _lib.SOFTMAX and self.path == 1
+        self.ws_bytes = h.ge2e_b200_workspace_bytes(N, N, M, D, variant, precision)
+        self.free = []
+
+    def take(self) -> _StepBufs:
+        if torch.cuda.is_current_stream_capturing():
+            return _StepBufs(self, pooled=False)      # memory of a capture belongs to the graph's pool: never recycled
+        return self.free.pop() if self.free else _StepBufs(self, pooled=True)
+
+    def give(self, bufs: _StepBufs) -> None:
+        if bufs.pooled and len(self.free) < 4:
+            self.free.append(bufs)
+
+    def workspace(self, stream: int):
+        if self.ws_bytes == 0:
+            return None
+        if torch.cuda.is_current_stream_capturing():
+            return torch.zeros(self.ws_bytes, dtype=torch.uint8, device=self.device)
+        key = (self.dev_index, stream, self.ws_bytes)
+        ws = _WS_CACHE.get(key)
+        if ws is None:
+            if len(_WS_CACHE) > 64:
+                _WS_CACHE.clear()
+            ws = _WS_CACHE[key] = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=self.device)
+        return ws
+
+
+_EAGER_PLANS: dict = {}
+
+
+def _eager_plan(dev, N, M, D, variant, precision) -> _EagerPlan:
+    key = (dev.index, N, M, D, variant, precision)
+    plan = _EAGER_PLANS.get(key)
+    if plan is None:
+        if len(_EAGER_PLANS) > 32:
+            _EAGER_PLANS.clear()
+        plan = _EAGER_PLANS[key] = _EagerPlan(dev, N, M, D, variant, precision)
+    return plan
+
+
+class _Lease:
+    """Returns the step's buffers to the pool when the autograd node (ctx) that holds it is collected --
+    i.e. when no backward through this forward can happen any more."""
+    __slots__ = ("bufs",)
+
+    def __init__(self, bufs):
+        self.bufs = bufs
+
+    def __del__(self):
+        b = self.bufs
+        if b is not None:
+            b.plan.give(b)
+
+
 class _GE2EEager(torch.autograd.Function):
-    """The same two C-ABI calls as ge2e_b200::fwd / ::bwd without the torch.library dispatch layers
+    """ge2e_b200_forward_indexed / ge2e_b200_backward_indexed without the torch.library dispatch layers
     (which cost ~0.2 ms of host time per step: more than the kernels at every size up to cfg3)."""
 
     @staticmethod
     def forward(ctx, E, w, b, eps, variant, precision, row_index, speakers):
-        want_grad = any(ctx.needs_input_grad[:3])
-        loss, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, dE_hat, row_scale = _fwd_impl(
-            E, w, b, eps, variant, precision, packed=True, row_index=row_index, speakers=speakers,
-            want_grad=want_grad)
-        ctx.save_for_backward(E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, dE_hat, row_scale)
-        ctx.cfg = (eps, variant, precision)
-        ctx.row_index = row_index
-        return loss
+        if not (E.is_cuda and w.is_cuda and b.is_cuda):
+            raise RuntimeError("speaker_embedding_ge2e_loss_b200 runs on CUDA (sm_100a) tensors only; "
+                               "there is no CPU fallback")
+        if E.dtype != torch.float32 or w.dtype != torch.float32 or b.dtype != torch.float32:
+            raise TypeError(f"expected float32, got {E.dtype}")
+        if not E.is_contiguous():
+            E = E.contiguous()
+        if row_index is None:
+            N, M, D = E.shape
+        else:
+            U_, D = E.shape
+            N, M = speakers, U_ // max(1, speakers)
+            if speakers <= 0 or N * M != U_:
+                raise ValueError(f"{U_} rows do not split into {speakers} speakers")
+        dev = E.device
+        plan = _eager_plan(dev, N, M, D, variant, precision)
+        want_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        with _on_device(dev):
+            bufs = plan.take()
+            accum = torch.empty(4, dtype=torch.float32, device=dev)     # escapes as the loss tensor: never pooled
+            stream = _raw_stream(plan.dev_index)
+            ws = plan.workspace(stream)
+            fused = plan.fused and want_grad
+            rc = lib().ge2e_b200_forward_indexed(
+                E.data_ptr(), _ptr(row_index), N, M, D, w.data_ptr(), b.data_ptr(), eps, variant, precision,
+                *bufs.fwd_ptrs, accum.data_ptr(), bufs.dE_hat.data_ptr() if fused else None,
+                bufs.row_scale.data_ptr() if fused else None, _ptr(ws), plan.ws_bytes, stream)
+        _check(rc, "ge2e_b200_forward")
+        ctx.save_for_backward(E, w, b)
+        ctx.lease = _Lease(bufs)
+        ctx.cfg = (eps, variant, precision, plan, fused, row_index, N, M, D)
+        return accum[0]
 
     @staticmethod
     def backward(ctx, g_loss):
-        E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, dE_hat, row_scale = ctx.saved_tensors
-        eps, variant, precision = ctx.cfg
-        dE, dwdb = _bwd_impl(g_loss, E, w, b, e_hat, c_hat, cos_diag, row_stat, row_kstar, row_aux, dE_hat, row_scale,
-                             eps, variant, precision, row_index=ctx.row_index)
-        return dE, dwdb[0], dwdb[1], None, None, None, None, None
+        E, w, b = ctx.saved_tensors
+        eps, variant, precision, plan, fused, row_index, N, M, D = ctx.cfg
+        bufs = ctx.lease.bufs
+        g = g_loss if (g_loss.dtype == torch.float32 and g_loss.is_cuda) else g_loss.to(E.device, torch.float32)
+        dev = E.device
+        with _on_device(dev):
+            dE = torch.empty_like(E)
+            accum = torch.empty(4, dtype=torch.float32, device=dev)     # escapes as dw / db: never pooled
+            stream = _raw_stream(plan.dev_index)
+            ws = plan.workspace(stream)
+            rc = lib().ge2e_b200_backward_indexed(
+                E.data_ptr(), _ptr(row_index), bufs.e_hat.data_ptr(), bufs.c_hat.data_ptr(), bufs.cos_diag.data_ptr(),
+                bufs.row_stat.data_ptr(), bufs.kstar.data_ptr(), bufs.row_aux.data_ptr(),
+                bufs.row_scale.data_ptr() if fused else None, N, M, D, w.data_ptr(), b.data_ptr(), eps, variant,
+                precision, g.data_ptr(), bufs.dE_hat.data_ptr(), bufs.dC_hat.data_ptr(), accum.data_ptr(), dE.data_ptr(),
+                _ptr(ws), plan.ws_bytes, stream)
+        _check(rc, "ge2e_b200_backward")
+        return dE, accum[1], accum[2], None, None, None, None, None
 
 
 def ge2e_loss(E: Tensor, w: Tensor, b: Tensor, eps: float = 1e-6, variant: str = "softmax",
