@@ -186,6 +186,34 @@ int ge2e_b200_step_rows(const float* e_hat, const float* c_hat_all, const float*
                         float* dE_hat, float* dC_hat_partial, void* workspace, size_t workspace_bytes,
                         ge2e_stream_t stream);
 
+/* ---- speaker-sharded step over PEER MEMORY (one NVLink / NVSwitch domain, <= 8 ranks) ----------
+ * The two exchange steps of the sharded loss without collective kernels: the ranks map each
+ * other's buffers (CUDA peer access / symmetric memory; the Python layer uses
+ * torch.distributed._symmetric_memory) and the kernels store / add across NVLink themselves.
+ *   all-gather of c_hat      ge2e_b200_peer_publish: this rank's slice c_hat_mine[n_local, D] (the rows prep
+ *                            just wrote into its own c_hat_all) is stored into the same slice of every peer's
+ *                            c_hat_all -- peer_slices_host[r] = peer r's c_hat_all + spk_offset * D, a HOST
+ *                            array of n_peers device pointers (the other ranks) -- and dC_local_zero[n_local, D],
+ *                            this rank's rows of the centroid gradient, is cleared;
+ *   -- cross-rank barrier (caller: e.g. the symmetric-memory handle's barrier) --
+ *   reduce-scatter of dC_hat ge2e_b200_step_rows_peers: ge2e_b200_step_rows whose centroid pass reduce-adds
+ *                            every accumulator tile straight into the OWNER rank's rows (TMA
+ *                            cp.reduce.async.bulk into peer memory: the fp32 add happens at the owner's L2)
+ *                            -- dC_owner_host[r] = rank r's dC_local[n_total / n_ranks, D], a HOST array of
+ *                            n_ranks device pointers, this rank's own included -- instead of into a
+ *                            full-height partial that a reduce-scatter sums afterwards;
+ *   -- cross-rank barrier --, then ge2e_b200_bwd_finalize on dC_local as usual.
+ * Tensor-core softmax shapes with (n_total / n_ranks) % 128 == 0 only (GE2E_ERR_UNSUPPORTED otherwise: use
+ * ge2e_b200_step_rows + a reduce-scatter).  The 3-float {loss, dw, db} all-reduce stays with the caller. */
+int ge2e_b200_peer_publish(const float* c_hat_mine, float* const* peer_slices_host, int n_peers, int n_local,
+                           int D, float* dC_local_zero, ge2e_stream_t stream);
+int ge2e_b200_step_rows_peers(const float* e_hat, const float* c_hat_all, const float* cos_diag, int n_local,
+                              int n_total, int spk_offset, int M, int D, const float* w, const float* b,
+                              float eps, int variant, int precision, const float* grad_out, float* row_stat,
+                              int32_t* row_kstar, float* row_aux, float* row_scale, float* accum,
+                              float* dE_hat, float* const* dC_owner_host, int n_ranks, void* workspace,
+                              size_t workspace_bytes, ge2e_stream_t stream);
+
 /* The trainer's post-loss tail for the two loss parameters, on the device (SURVEY 8(f) row 1;
  * replaces `torch.nn.utils.clip_grad_norm_(self.ge2e_loss.parameters(), 1.0)` and the loss
  * parameter group's share of `self.optimizer.step()` (plain SGD), s4_train_embed_model.py:202-203,

@@ -337,6 +337,39 @@ int ge2e_b200_step_rows(const float* e_hat, const float* c_hat_all, const float*
                             workspace, workspace_bytes, stream);
 }
 
+// ---- speaker-sharded step over peer memory (one NVSwitch domain) ---------------------------
+int ge2e_b200_peer_publish(const float* c_hat_mine, float* const* peer_slices_host, int n_peers, int n_local, int D,
+                           float* dC_local_zero, ge2e_stream_t stream) {
+  if (!c_hat_mine || !peer_slices_host || !dC_local_zero) return GE2E_ERR_ARGUMENT;
+  if (n_peers < 0 || n_peers > GE2E_MAX_PEERS || n_local <= 0 || D <= 0 || D % 4 != 0) return GE2E_ERR_SHAPE;
+  for (int r = 0; r < n_peers; ++r)
+    if (!peer_slices_host[r] || (reinterpret_cast<uintptr_t>(peer_slices_host[r]) & 15) != 0) return GE2E_ERR_ARGUMENT;
+  if (((reinterpret_cast<uintptr_t>(c_hat_mine) | reinterpret_cast<uintptr_t>(dC_local_zero)) & 15) != 0)
+    return GE2E_ERR_ARGUMENT;
+  return simt_peer_publish(c_hat_mine, peer_slices_host, n_peers, (long long)n_local * D, dC_local_zero,
+                           (long long)n_local * D, (cudaStream_t)stream);
+}
+
+int ge2e_b200_step_rows_peers(const float* e_hat, const float* c_hat_all, const float* cos_diag, int n_local, int n_total,
+                              int spk_offset, int M, int D, const float* w, const float* b, float eps, int variant,
+                              int precision, const float* grad_out, float* row_stat, int32_t* row_kstar, float* row_aux,
+                              float* row_scale, float* accum, float* dE_hat, float* const* dC_owner_host, int n_ranks,
+                              void* workspace, size_t workspace_bytes, ge2e_stream_t stream) {
+  (void)row_kstar;
+  if (!e_hat || !c_hat_all || !cos_diag || !w || !b || !grad_out || !row_stat || !row_aux || !row_scale || !accum ||
+      !dE_hat || !dC_owner_host)
+    return GE2E_ERR_ARGUMENT;
+  int rc = check_shape(n_local, n_total, spk_offset, M, D);
+  if (rc != GE2E_OK) return rc;
+  if ((rc = check_enum(variant, precision)) != GE2E_OK) return rc;
+  if (n_ranks < 2 || n_ranks > GE2E_MAX_PEERS || n_local * n_ranks != n_total) return GE2E_ERR_SHAPE;
+  // only the tensor-core softmax step flushes through peer memory; everything else keeps the reduce-scatter
+  if (!tc_softmax_step(n_local, n_total, M, D, variant, precision)) return GE2E_ERR_UNSUPPORTED;
+  RowsArgs a{e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, b, eps, variant};
+  return tc_step(a, 3, grad_out, nullptr, nullptr, row_stat, row_aux, row_scale, accum, nullptr, dE_hat, nullptr,
+                 accum + 1, workspace, workspace_bytes, (cudaStream_t)stream, dC_owner_host, n_ranks);
+}
+
 // ---- whole step in one call ---------------------------------------------------------------
 // 0 = never (A/B timing), 1 = where it is faster than the pipeline (default), 2 = every supported shape (tests)
 static std::atomic<int> g_small_mode{1};

@@ -13,6 +13,7 @@
 namespace ge2e {
 
 constexpr float kCosDelta = 1e-8f;  // F.cosine_similarity eps (s3:57, s3:70)
+#define GE2E_MAX_PEERS 8             // ranks of one NVSwitch domain served by the peer-memory entry points
 constexpr int kWarp = 32;
 
 // thread-local record of the last CUDA failure, exposed through the C ABI
@@ -176,8 +177,13 @@ int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* r
                 cudaStream_t st);
 // softmax step on tensor cores; phases: 1 = rows pass (loss, row statistics, un-normalised dE_hat + row_scale),
 // 2 = centroid pass (dC_hat_partial, {dw, db}), 3 = both in one launch
+// dC_owner (nullable, HOST array of n_ranks device pointers): speaker-sharded over peer memory -- pass 2 adds its
+// accumulators straight into the owner rank's dC_local[n_total / n_ranks, D] (see ge2e_b200_step_rows_peers)
 int tc_step(const RowsArgs& a, int phases, const float* grad_out, const float* row_stat_in, const float* row_aux_in,
             float* row_stat, float* row_aux, float* row_scale, float* loss_accum, float* per_row_out, float* dE_hat,
-            float* dC_hat_partial, float* dwdb_accum, void* ws, size_t ws_bytes, cudaStream_t st);
+            float* dC_hat_partial, float* dwdb_accum, void* ws, size_t ws_bytes, cudaStream_t st,
+            float* const* dC_owner = nullptr, int n_ranks = 0);
+int simt_peer_publish(const float* src, float* const* dst, int n_dst, long long n_floats, float* zero, long long zero_floats,
+                      cudaStream_t st);
 
 }  // namespace ge2e

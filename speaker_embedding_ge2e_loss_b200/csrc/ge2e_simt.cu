@@ -2092,6 +2092,43 @@ int simt_gather_spans(const float* bank, const long long* src_off, int rows, lon
   return GE2E_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Speaker-sharded step over peer memory (NVLink / NVSwitch): the all-gather of the normalised centroids as
+// plain stores.  Every rank copies ITS slice of c_hat (1 MB at config 4 on 8 ranks) into the same slice of
+// every peer's c_hat_all and clears its own dC_local, which the peers' step kernels then add into.
+// ------------------------------------------------------------------------------------------
+namespace {
+struct PeerDst { float4* p[GE2E_MAX_PEERS]; };
+
+__global__ void __launch_bounds__(256)
+peer_publish_kernel(const float4* __restrict__ src, PeerDst dst, int n_dst, long long n4, float4* __restrict__ zero,
+                    long long zero_n4) {
+  pdl_wait();        // src is written by the preceding kernel (prep)
+  pdl_trigger();
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = src[i];
+#pragma unroll
+    for (int r = 0; r < GE2E_MAX_PEERS; ++r)
+      if (r < n_dst) dst.p[r][i] = v;
+  }
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < zero_n4; i += stride)
+    zero[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+}  // namespace
+
+int simt_peer_publish(const float* src, float* const* dst, int n_dst, long long n_floats, float* zero, long long zero_floats,
+                      cudaStream_t st) {
+  PeerDst d{};
+  for (int r = 0; r < n_dst; ++r) d.p[r] = reinterpret_cast<float4*>(dst[r]);
+  const long long n4 = n_floats / 4, z4 = zero_floats / 4;
+  const int grid = static_cast<int>(std::min<long long>(148 * 2, std::max<long long>(1, (std::max(n4, z4) + 255) / 256)));
+  GE2E_CUDA_TRY(launch_pdl(peer_publish_kernel, dim3(grid), dim3(256), 0, st, true, reinterpret_cast<const float4*>(src), d,
+                           n_dst, n4, reinterpret_cast<float4*>(zero), z4));
+  GE2E_LAUNCHED();
+  return GE2E_OK;
+}
+
 int simt_centroids(const float* E, int N, int M, int D, float* C, cudaStream_t st) {
   centroids_kernel<<<N, 128, 0, st>>>(E, M, D, C);
   GE2E_LAUNCHED();

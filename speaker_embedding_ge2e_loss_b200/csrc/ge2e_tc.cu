@@ -74,6 +74,7 @@ constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreadsTc = (kEpiWarp0 + kEpiWarps) * 32;
 constexpr int kMaxClusters = 160;     // >= SM count / cluster size
+constexpr int kMaxPeers = GE2E_MAX_PEERS;   // ranks of one NVSwitch domain (fused reduce-scatter)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -102,6 +103,10 @@ struct TmSet {
   CUtensorMap strk[2];   // stream, K-major    box [64 rows][32 cols], 128B swizzle
   CUtensorMap strmn[2];  // stream, MN-major   box [D/32/CG][32 rows][32 cols], 32B-atom 128B swizzle
   CUtensorMap out[2];    // accumulator output box [128 rows][32 cols], 128B swizzle
+  // STEP, speaker-sharded over peer memory: dC_hat rows [r * peer_rows, (r + 1) * peer_rows) live in rank r's
+  // dC_local (mapped into this process, NVLink): pass 2 reduce-adds its accumulators THERE instead of into a
+  // full-height local partial that a reduce-scatter would have to sum afterwards
+  CUtensorMap out_peer[kMaxPeers];
 };
 
 // STEP: pair range [begin[c], begin[c + 1]) of cluster c in the dE_hat (pass 1) / dC_hat (pass 2) pair lists
@@ -142,6 +147,7 @@ struct TcParams {
   float4* zero2_base;         // STEP: dE_hat when some owner group is cut between clusters
   long long zero2_n4;
   int* ctr;                   // STEP: {CTAs done zero-filling, CTAs done, CTAs done with pass 1}: zero on entry and exit
+  int peer_rows;              // STEP: > 0: centroid rows per rank, pass 2 flushes through tms.out_peer (see TmSet)
   unsigned long long* stamps; // STEP, nullable: [CTA]{start, end} globaltimer stamps (in-situ kernel time)
   unsigned long long* trace;  // debug: [CTA][3 roles][kTraceEvents] globaltimer stamps, or nullptr
   int dbg;                    // debug instantiation only: 8 = per-stage marks in the MMA warp's trace
@@ -858,10 +864,21 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
           // has read it, so the reload of the owner area interleaves with the flush instead of following it
           if (tile_valid) {
             const CUtensorMap* tm_out = &tms.out[kind];
-            if (!full) wait_zero_fill();
+            int row0 = ot * kTile;
+            bool store = full;
+            if (is_dc && p.peer_rows > 0) {
+              // the owner rank zero-filled its rows before the cross-rank barrier in front of this kernel;
+              // every rank adds (fp32 add at the owner's L2 -- over NVLink for the other ranks)
+              const int r = row0 / p.peer_rows;
+              tm_out = &tms.out_peer[r];
+              row0 -= r * p.peer_rows;
+              store = false;
+            } else if (!full) {
+              wait_zero_fill();
+            }
             for (int ks = 0; ks < kslabs; ++ks) {
-              if (full) tma_store_2d(tm_out, ks * kSlabCols, ot * kTile, a_smem + ks * kSlabBytes);
-              else tma_reduce_add_2d(tm_out, ks * kSlabCols, ot * kTile, a_smem + ks * kSlabBytes);
+              if (store) tma_store_2d(tm_out, ks * kSlabCols, row0, a_smem + ks * kSlabBytes);
+              else tma_reduce_add_2d(tm_out, ks * kSlabCols, row0, a_smem + ks * kSlabBytes);
               tma_store_commit();
             }
           }
@@ -1277,8 +1294,13 @@ int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* r
 // both: one launch with a grid-wide barrier between the passes.
 int tc_step(const RowsArgs& a, int phases, const float* grad_out, const float* row_stat_in, const float* row_aux_in,
             float* row_stat, float* row_aux, float* row_scale, float* loss_accum, float* per_row_out, float* dE_hat,
-            float* dC_hat_partial, float* dwdb_accum, void* ws, size_t ws_bytes, cudaStream_t st) {
+            float* dC_hat_partial, float* dwdb_accum, void* ws, size_t ws_bytes, cudaStream_t st,
+            float* const* dC_owner, int n_ranks) {
   const int U = a.n_local * a.M;
+  const bool peers = dC_owner != nullptr && n_ranks > 1;
+  if (peers && (n_ranks > kMaxPeers || a.n_total % n_ranks != 0 || (a.n_total / n_ranks) % kTile != 0 ||
+                !(phases & PASS_CENTROIDS)))
+    return GE2E_ERR_UNSUPPORTED;
   if (ws == nullptr || ws_bytes < tc_workspace_bytes(a.n_local, a.n_total, a.M, a.D, a.variant)) return GE2E_ERR_WORKSPACE;
   if ((reinterpret_cast<uintptr_t>(ws) & 15) != 0) return GE2E_ERR_WORKSPACE;
   const int cg = pick_cg(a.D);
@@ -1304,7 +1326,7 @@ int tc_step(const RowsArgs& a, int phases, const float* grad_out, const float* r
                                  phases, max_cl, &sched, &de_partial, &dc_partial);
   // outputs assembled from partial accumulators (TMA reduce-add) are zero-filled by the kernel itself;
   // D % 32 == 0 makes every row a whole number of float4
-  if ((phases & PASS_CENTROIDS) && dc_partial) {
+  if ((phases & PASS_CENTROIDS) && dc_partial && !peers) {
     p.zero_base = reinterpret_cast<float4*>(dC_hat_partial);
     p.zero_n4 = static_cast<long long>(a.n_total) * a.D / 4;
   }
@@ -1329,6 +1351,13 @@ int tc_step(const RowsArgs& a, int phases, const float* grad_out, const float* r
   if ((rc = make_map_3d(&tms.strmn[SEG_DC], a.e_hat, U, a.D, slabs / cg)) != GE2E_OK) return rc;
   if ((rc = make_map_2d(&tms.out[SEG_DC], dC_hat_partial != nullptr ? dC_hat_partial : dE_hat, a.n_total, a.D, kTile)) != GE2E_OK)
     return rc;
+  if (peers) {
+    p.peer_rows = a.n_total / n_ranks;
+    for (int r = 0; r < n_ranks; ++r) {
+      if (dC_owner[r] == nullptr || (reinterpret_cast<uintptr_t>(dC_owner[r]) & 15) != 0) return GE2E_ERR_ARGUMENT;
+      if ((rc = make_map_2d(&tms.out_peer[r], dC_owner[r], p.peer_rows, a.D, kTile)) != GE2E_OK) return rc;
+    }
+  }
   return launch_tc_cg<TC_STEP, GE2E_SOFTMAX>(cg, tms, sched, p, NC, phases != PASS_CENTROIDS, st);
 }
 

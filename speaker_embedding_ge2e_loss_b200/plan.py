@@ -110,7 +110,16 @@ class ShardedGE2EPlan:
     Results: ``.loss`` (global), ``.dE`` (this rank's rows), ``.dw`` / ``.db`` (global)."""
 
     def __init__(self, n_local: int, n_total: int, spk_offset: int, M: int, D: int, variant: str = "softmax",
-                 precision: str = "tf32", eps: float = 1e-6, group=None, device=None):
+                 precision: str = "tf32", eps: float = 1e-6, group=None, device=None, peer_memory="auto"):
+        """``peer_memory``: "auto" (default) / True / False.  Where the softmax loss runs on tensor cores and the
+        ranks of ``group`` can map each other's memory (one NVLink / NVSwitch domain, <= 8 ranks, n_local a
+        multiple of 128), the two exchange steps are done by the kernels themselves over peer memory
+        (``torch.distributed._symmetric_memory`` buffers): the all-gather of ``c_hat`` is a store of this rank's
+        slice into every peer (``ge2e_b200_peer_publish``), the reduce-scatter of ``dC_hat`` is the step
+        kernel's centroid pass adding its accumulator tiles straight into the owner rank's rows
+        (``ge2e_b200_step_rows_peers``); two cross-rank barriers replace the two NCCL collectives.  Otherwise
+        (or with ``peer_memory=False``) the step uses all_gather_into_tensor / reduce_scatter_tensor.
+        All ranks must construct the plan collectively (the buffers are rendezvoused)."""
         import torch.distributed as dist
         self.dist = dist
         self.group = group if group is not None else dist.group.WORLD
@@ -121,7 +130,7 @@ class ShardedGE2EPlan:
         self.device = torch.device(device if device is not None else "cuda")
         U, dev, f32 = n_local * M, self.device, torch.float32
         self.e_hat = torch.empty((U, D), dtype=f32, device=dev)
-        self.c_hat_all = torch.empty((n_total, D), dtype=f32, device=dev)
+        self.c_hat_all = torch.empty((n_total, D), dtype=f32, device=dev)      # (replaced below in peer-memory mode)
         self.c_hat_mine = self.c_hat_all[spk_offset:spk_offset + n_local]
         self.cos_diag = torch.empty(U, dtype=f32, device=dev)
         self.row_stat = torch.empty(U, dtype=f32, device=dev)
@@ -132,8 +141,22 @@ class ShardedGE2EPlan:
         self.path = lib().ge2e_b200_path(n_local, n_total, M, D, self.variant, self.precision)
         # finalize applies row_scale only where the forward produced it (softmax on tensor cores)
         self._scaled = self.path == 1 and self.variant == _lib.SOFTMAX
-        self.dC_partial = torch.empty((n_total, D), dtype=f32, device=dev)
-        self.dC_local = torch.empty((n_local, D), dtype=f32, device=dev)
+        self.peer, self.peer_error = False, None
+        world = dist.get_world_size(self.group)
+        if peer_memory and world > 1:
+            ok = self._scaled and world <= 8 and n_local % 128 == 0 and n_local * world == n_total
+            if ok:
+                try:
+                    self._setup_peer_memory(world, dist.get_rank(self.group))
+                except Exception as e:          # no peer mapping on this system: the NCCL path is always there
+                    self.peer_error = repr(e)
+                    if peer_memory is True:
+                        raise
+            elif peer_memory is True:
+                raise ValueError("peer_memory=True needs the tensor-core softmax path, <= 8 ranks and n_local % 128 == 0")
+        if not self.peer:
+            self.dC_partial = torch.empty((n_total, D), dtype=f32, device=dev)
+            self.dC_local = torch.empty((n_local, D), dtype=f32, device=dev)
         self.red = torch.empty(4, dtype=f32, device=dev)          # {loss, dw, db, -}: zeroed by prep, all-reduced
         self.dE = torch.empty((n_local, M, D), dtype=f32, device=dev)
         self.grad_out = torch.ones((), dtype=f32, device=dev)
@@ -143,7 +166,63 @@ class ShardedGE2EPlan:
         self.loss, self.dw, self.db = self.red[0], self.red[1], self.red[2]
         self._side = torch.cuda.Stream(device=dev)
 
+    def _setup_peer_memory(self, world: int, rank: int) -> None:
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        f32, dev = torch.float32, self.device
+        gname = self.group.group_name
+        c_all = symm.empty((self.n_total, self.D), dtype=f32, device=dev)
+        hc = symm.rendezvous(c_all, gname)
+        dC = symm.empty((self.n_local, self.D), dtype=f32, device=dev)
+        hd = symm.rendezvous(dC, gname)
+        ptr_c, ptr_d = list(hc.buffer_ptrs), list(hd.buffer_ptrs)
+        if len(ptr_c) != world or len(ptr_d) != world:
+            raise RuntimeError("symmetric-memory rendezvous returned a different world size")
+        off_bytes = self.spk_offset * self.D * 4
+        peers = [ptr_c[r] + off_bytes for r in range(world) if r != rank]       # MY slice in every peer's c_hat_all
+        self._peer_slices = (C.c_void_p * len(peers))(*peers)
+        self._dC_owner = (C.c_void_p * world)(*ptr_d)                            # every rank's dC_local, mine included
+        self._n_peers, self._world = len(peers), world
+        self._hc, self._hd = hc, hd
+        self.c_hat_all = c_all
+        self.c_hat_mine = c_all[self.spk_offset:self.spk_offset + self.n_local]
+        self.dC_local, self.dC_partial = dC, None
+        self.peer = True
+
+    def _step_peer(self, E_local, w, b) -> None:
+        """prep -> publish c_hat slice to the peers, clear my dC rows -> barrier -> step kernel (centroid pass adds
+        into the owners' rows over NVLink) -> barrier -> all-reduce {loss, dw, db} || finalize."""
+        h, dist = lib(), self.dist
+        nl, nt, off, M, D = self.n_local, self.n_total, self.spk_offset, self.M, self.D
+        cur = torch.cuda.current_stream(self.device)
+        s = cur.cuda_stream
+        ws = self._ws.data_ptr() if self._ws_bytes else None
+        check(h.ge2e_b200_prep(E_local.data_ptr(), nl, M, D, self.precision, self.e_hat.data_ptr(),
+                               self.c_hat_mine.data_ptr(), self.cos_diag.data_ptr(), self.red.data_ptr(), s),
+              "ge2e_b200_prep")
+        check(h.ge2e_b200_peer_publish(self.c_hat_mine.data_ptr(), self._peer_slices, self._n_peers, nl, D,
+                                       self.dC_local.data_ptr(), s), "ge2e_b200_peer_publish")
+        self._hc.barrier(channel=0)          # every slice of c_hat_all has landed, every dC_local is cleared
+        check(h.ge2e_b200_step_rows_peers(self.e_hat.data_ptr(), self.c_hat_all.data_ptr(), self.cos_diag.data_ptr(), nl,
+                                          nt, off, M, D, w.data_ptr(), b.data_ptr(), self.eps, self.variant,
+                                          self.precision, self.grad_out.data_ptr(), self.row_stat.data_ptr(),
+                                          self.row_kstar.data_ptr(), self.row_aux.data_ptr(), self.row_scale.data_ptr(),
+                                          self.red.data_ptr(), self.dE_hat.data_ptr(), self._dC_owner, self._world, ws,
+                                          self._ws_bytes, s), "ge2e_b200_step_rows_peers")
+        self._hd.barrier(channel=0)          # every rank's contributions to my dC rows have landed
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            dist.all_reduce(self.red, op=dist.ReduceOp.SUM, group=self.group)
+        check(h.ge2e_b200_bwd_finalize(E_local.data_ptr(), self.dE_hat.data_ptr(), self.dC_local.data_ptr(),
+                                       self.cos_diag.data_ptr(), self.row_stat.data_ptr(), self.row_aux.data_ptr(),
+                                       self.row_scale.data_ptr(), nl, M, D, w.data_ptr(), b.data_ptr(), self.eps,
+                                       self.variant, self.grad_out.data_ptr(), self.dE.data_ptr(), s),
+              "ge2e_b200_bwd_finalize")
+        cur.wait_stream(self._side)
+
     def step(self, E_local: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> None:
+        if self.peer:
+            return self._step_peer(E_local, w, b)
         h, dist = lib(), self.dist
         nl, nt, off, M, D = self.n_local, self.n_total, self.spk_offset, self.M, self.D
         s = torch.cuda.current_stream(self.device).cuda_stream
