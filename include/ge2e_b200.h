@@ -190,11 +190,13 @@ int ge2e_b200_step_rows(const float* e_hat, const float* c_hat_all, const float*
  * The two exchange steps of the sharded loss without collective kernels: the ranks map each
  * other's buffers (CUDA peer access / symmetric memory; the Python layer uses
  * torch.distributed._symmetric_memory) and the kernels store / add across NVLink themselves.
- *   all-gather of c_hat      ge2e_b200_peer_publish: this rank's slice c_hat_mine[n_local, D] (the rows prep
- *                            just wrote into its own c_hat_all) is stored into the same slice of every peer's
- *                            c_hat_all -- peer_slices_host[r] = peer r's c_hat_all + spk_offset * D, a HOST
- *                            array of n_peers device pointers (the other ranks) -- and dC_local_zero[n_local, D],
- *                            this rank's rows of the centroid gradient, is cleared;
+ *   all-gather of c_hat      ge2e_b200_peer_publish: src[n_floats] -- this rank's slice of c_hat, the rows prep
+ *                            just wrote into its own c_hat_all -- is stored to dst_host[0 .. n_dst) (a HOST
+ *                            array of device pointers: the same slice of every PEER's c_hat_all), or, with
+ *                            multicast != 0 and n_dst == 1, to ONE multicast address of the NVSwitch domain
+ *                            (multimem.st: one store leaves the GPU, the switch replicates it to every rank);
+ *                            zero[zero_floats] (nullable: this rank's dC_local) is cleared.  The same call
+ *                            publishes a rank's {loss, dw, db} partials into the peers' scalar tables;
  *   -- cross-rank barrier (caller: e.g. the symmetric-memory handle's barrier) --
  *   reduce-scatter of dC_hat ge2e_b200_step_rows_peers: ge2e_b200_step_rows whose centroid pass reduce-adds
  *                            every accumulator tile straight into the OWNER rank's rows (TMA
@@ -204,9 +206,10 @@ int ge2e_b200_step_rows(const float* e_hat, const float* c_hat_all, const float*
  *                            full-height partial that a reduce-scatter sums afterwards;
  *   -- cross-rank barrier --, then ge2e_b200_bwd_finalize on dC_local as usual.
  * Tensor-core softmax shapes with (n_total / n_ranks) % 128 == 0 only (GE2E_ERR_UNSUPPORTED otherwise: use
- * ge2e_b200_step_rows + a reduce-scatter).  The 3-float {loss, dw, db} all-reduce stays with the caller. */
-int ge2e_b200_peer_publish(const float* c_hat_mine, float* const* peer_slices_host, int n_peers, int n_local,
-                           int D, float* dC_local_zero, ge2e_stream_t stream);
+ * ge2e_b200_step_rows + a reduce-scatter).  The {loss, dw, db} partials of accum[] are exchanged by the
+ * caller (ShardedGE2EPlan publishes them into a [ranks, 4] table in front of the second barrier). */
+int ge2e_b200_peer_publish(const float* src, float* const* dst_host, int n_dst, int multicast,
+                           long long n_floats, float* zero, long long zero_floats, ge2e_stream_t stream);
 int ge2e_b200_step_rows_peers(const float* e_hat, const float* c_hat_all, const float* cos_diag, int n_local,
                               int n_total, int spk_offset, int M, int D, const float* w, const float* b,
                               float eps, int variant, int precision, const float* grad_out, float* row_stat,

@@ -42,15 +42,15 @@ def main():
     p = ShardedGE2EPlan(nl, N, off, M, D, "softmax", "tf32", device=dev, peer_memory=False if a.no_peer else "auto")
     h = lib()
     ws = p._ws.data_ptr() if p._ws_bytes else None
-    names = (["prep", "peer_publish", "barrier", "step_rows_peers", "barrier2", "all_reduce", "bwd_finalize"] if p.peer
+    names = (["prep", "peer_publish", "barrier", "step_rows_peers", "scalars+barrier2", "sum_scalars", "bwd_finalize"] if p.peer
              else ["prep", "all_gather", "step_rows", "reduce_scatter", "all_reduce", "bwd_finalize"])
 
     def stages_peer():
         s = torch.cuda.current_stream(dev).cuda_stream
         yield lambda: check(h.ge2e_b200_prep(E.data_ptr(), nl, M, D, p.precision, p.e_hat.data_ptr(),
                                              p.c_hat_mine.data_ptr(), p.cos_diag.data_ptr(), p.red.data_ptr(), s), "prep")
-        yield lambda: check(h.ge2e_b200_peer_publish(p.c_hat_mine.data_ptr(), p._peer_slices, p._n_peers, nl, D,
-                                                     p.dC_local.data_ptr(), s), "publish")
+        yield lambda: check(h.ge2e_b200_peer_publish(p.c_hat_mine.data_ptr(), p._peer_slices, p._n_peers, p._mcast, nl * D,
+                                                     p.dC_local.data_ptr(), nl * D, s), "publish")
         yield lambda: p._hc.barrier(channel=0)
         yield lambda: check(h.ge2e_b200_step_rows_peers(p.e_hat.data_ptr(), p.c_hat_all.data_ptr(), p.cos_diag.data_ptr(),
                                                         nl, N, off, M, D, w.data_ptr(), b.data_ptr(), p.eps, p.variant,
@@ -58,8 +58,9 @@ def main():
                                                         p.row_kstar.data_ptr(), p.row_aux.data_ptr(),
                                                         p.row_scale.data_ptr(), p.red.data_ptr(), p.dE_hat.data_ptr(),
                                                         p._dC_owner, p._world, ws, p._ws_bytes, s), "step_rows_peers")
-        yield lambda: p._hd.barrier(channel=0)
-        yield lambda: dist.all_reduce(p.red, op=dist.ReduceOp.SUM)
+        yield lambda: (check(h.ge2e_b200_peer_publish(p.red.data_ptr(), p._red_rows, p._world, 0, 4, None, 0, s), "scalars"),
+                       p._hd.barrier(channel=0))
+        yield lambda: torch.sum(p.red_all, dim=0, out=p.red_sum)
         yield lambda: check(h.ge2e_b200_bwd_finalize(E.data_ptr(), p.dE_hat.data_ptr(), p.dC_local.data_ptr(),
                                                      p.cos_diag.data_ptr(), p.row_stat.data_ptr(), p.row_aux.data_ptr(),
                                                      p.row_scale.data_ptr(), nl, M, D, w.data_ptr(), b.data_ptr(), p.eps,
@@ -122,7 +123,7 @@ def main():
     dist.all_reduce(tg, op=dist.ReduceOp.MAX)
     if rank == 0:
         out = {"shape": [N, M, D], "world": world, "peer_memory": p.peer, "peer_error": p.peer_error,
-               "stage_us_eager_max_over_ranks": dict(zip(names, [round(v, 1) for v in med.tolist()])),
+               "multicast": bool(getattr(p, "_mcast", 0)), "stage_us_eager_max_over_ranks": dict(zip(names, [round(v, 1) for v in med.tolist()])),
                "sum_of_stages_us": round(float(med.sum()), 1), "graph_step_us_max_over_ranks": round(tg.item(), 1)}
         print(json.dumps(out), flush=True)
     del gr

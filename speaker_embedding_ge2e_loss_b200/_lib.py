@@ -41,7 +41,8 @@ PROTOTYPES = {
     "ge2e_b200_step_rows": (C.c_int, [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p,
                                       C.c_float, C.c_int, C.c_int, _f32p, _f32p, _i32p, _f32p, _f32p, _f32p, _f32p,
                                       _f32p, C.c_void_p, C.c_size_t, _stream]),
-    "ge2e_b200_peer_publish": (C.c_int, [_f32p, C.c_void_p, C.c_int, C.c_int, C.c_int, _f32p, _stream]),
+    "ge2e_b200_peer_publish": (C.c_int, [_f32p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, _f32p, C.c_longlong,
+                                         _stream]),
     "ge2e_b200_step_rows_peers": (C.c_int, [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p,
                                             _f32p, C.c_float, C.c_int, C.c_int, _f32p, _f32p, _i32p, _f32p, _f32p,
                                             _f32p, _f32p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, _stream]),

@@ -338,16 +338,17 @@ int ge2e_b200_step_rows(const float* e_hat, const float* c_hat_all, const float*
 }
 
 // ---- speaker-sharded step over peer memory (one NVSwitch domain) ---------------------------
-int ge2e_b200_peer_publish(const float* c_hat_mine, float* const* peer_slices_host, int n_peers, int n_local, int D,
-                           float* dC_local_zero, ge2e_stream_t stream) {
-  if (!c_hat_mine || !peer_slices_host || !dC_local_zero) return GE2E_ERR_ARGUMENT;
-  if (n_peers < 0 || n_peers > GE2E_MAX_PEERS || n_local <= 0 || D <= 0 || D % 4 != 0) return GE2E_ERR_SHAPE;
-  for (int r = 0; r < n_peers; ++r)
-    if (!peer_slices_host[r] || (reinterpret_cast<uintptr_t>(peer_slices_host[r]) & 15) != 0) return GE2E_ERR_ARGUMENT;
-  if (((reinterpret_cast<uintptr_t>(c_hat_mine) | reinterpret_cast<uintptr_t>(dC_local_zero)) & 15) != 0)
+int ge2e_b200_peer_publish(const float* src, float* const* dst_host, int n_dst, int multicast, long long n_floats,
+                           float* zero, long long zero_floats, ge2e_stream_t stream) {
+  if (!src || !dst_host) return GE2E_ERR_ARGUMENT;
+  if (n_dst < 1 || n_dst > GE2E_MAX_PEERS || n_floats < 0 || n_floats % 4 != 0 || zero_floats < 0 || zero_floats % 4 != 0 ||
+      (multicast && n_dst != 1))
+    return GE2E_ERR_SHAPE;
+  for (int r = 0; r < n_dst; ++r)
+    if (!dst_host[r] || (reinterpret_cast<uintptr_t>(dst_host[r]) & 15) != 0) return GE2E_ERR_ARGUMENT;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) != 0 || (zero_floats > 0 && (!zero || (reinterpret_cast<uintptr_t>(zero) & 15) != 0)))
     return GE2E_ERR_ARGUMENT;
-  return simt_peer_publish(c_hat_mine, peer_slices_host, n_peers, (long long)n_local * D, dC_local_zero,
-                           (long long)n_local * D, (cudaStream_t)stream);
+  return simt_peer_publish(src, dst_host, n_dst, multicast != 0, n_floats, zero, zero_floats, (cudaStream_t)stream);
 }
 
 int ge2e_b200_step_rows_peers(const float* e_hat, const float* c_hat_all, const float* cos_diag, int n_local, int n_total,

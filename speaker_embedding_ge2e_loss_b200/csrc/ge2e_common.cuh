@@ -183,7 +183,7 @@ int tc_step(const RowsArgs& a, int phases, const float* grad_out, const float* r
             float* row_stat, float* row_aux, float* row_scale, float* loss_accum, float* per_row_out, float* dE_hat,
             float* dC_hat_partial, float* dwdb_accum, void* ws, size_t ws_bytes, cudaStream_t st,
             float* const* dC_owner = nullptr, int n_ranks = 0);
-int simt_peer_publish(const float* src, float* const* dst, int n_dst, long long n_floats, float* zero, long long zero_floats,
-                      cudaStream_t st);
+int simt_peer_publish(const float* src, float* const* dst, int n_dst, bool multicast, long long n_floats, float* zero,
+                      long long zero_floats, cudaStream_t st);
 
 }  // namespace ge2e

@@ -2100,31 +2100,44 @@ int simt_gather_spans(const float* bank, const long long* src_off, int rows, lon
 namespace {
 struct PeerDst { float4* p[GE2E_MAX_PEERS]; };
 
+template <bool MULTICAST>
 __global__ void __launch_bounds__(256)
 peer_publish_kernel(const float4* __restrict__ src, PeerDst dst, int n_dst, long long n4, float4* __restrict__ zero,
                     long long zero_n4) {
-  pdl_wait();        // src is written by the preceding kernel (prep)
+  pdl_wait();        // src is written by the preceding kernel
   pdl_trigger();
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 v = src[i];
+    if (MULTICAST) {
+      // dst.p[0] is a multicast address of the NVSwitch domain: ONE store leaves this GPU, the switch
+      // replicates it into every rank's copy of the buffer (this rank's own included)
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst.p[0] + i), "f"(v.x),
+                   "f"(v.y), "f"(v.z), "f"(v.w)
+                   : "memory");
+    } else {
 #pragma unroll
-    for (int r = 0; r < GE2E_MAX_PEERS; ++r)
-      if (r < n_dst) dst.p[r][i] = v;
+      for (int r = 0; r < GE2E_MAX_PEERS; ++r)
+        if (r < n_dst) dst.p[r][i] = v;
+    }
   }
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < zero_n4; i += stride)
     zero[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 }  // namespace
 
-int simt_peer_publish(const float* src, float* const* dst, int n_dst, long long n_floats, float* zero, long long zero_floats,
-                      cudaStream_t st) {
+int simt_peer_publish(const float* src, float* const* dst, int n_dst, bool multicast, long long n_floats, float* zero,
+                      long long zero_floats, cudaStream_t st) {
   PeerDst d{};
   for (int r = 0; r < n_dst; ++r) d.p[r] = reinterpret_cast<float4*>(dst[r]);
   const long long n4 = n_floats / 4, z4 = zero_floats / 4;
   const int grid = static_cast<int>(std::min<long long>(148 * 2, std::max<long long>(1, (std::max(n4, z4) + 255) / 256)));
-  GE2E_CUDA_TRY(launch_pdl(peer_publish_kernel, dim3(grid), dim3(256), 0, st, true, reinterpret_cast<const float4*>(src), d,
-                           n_dst, n4, reinterpret_cast<float4*>(zero), z4));
+  if (multicast)
+    GE2E_CUDA_TRY(launch_pdl(peer_publish_kernel<true>, dim3(grid), dim3(256), 0, st, true,
+                             reinterpret_cast<const float4*>(src), d, n_dst, n4, reinterpret_cast<float4*>(zero), z4));
+  else
+    GE2E_CUDA_TRY(launch_pdl(peer_publish_kernel<false>, dim3(grid), dim3(256), 0, st, true,
+                             reinterpret_cast<const float4*>(src), d, n_dst, n4, reinterpret_cast<float4*>(zero), z4));
   GE2E_LAUNCHED();
   return GE2E_OK;
 }

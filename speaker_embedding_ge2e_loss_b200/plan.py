@@ -157,13 +157,15 @@ class ShardedGE2EPlan:
         if not self.peer:
             self.dC_partial = torch.empty((n_total, D), dtype=f32, device=dev)
             self.dC_local = torch.empty((n_local, D), dtype=f32, device=dev)
-        self.red = torch.empty(4, dtype=f32, device=dev)          # {loss, dw, db, -}: zeroed by prep, all-reduced
+        self.red = torch.empty(4, dtype=f32, device=dev)          # {loss, dw, db, -}: zeroed by prep; this rank's partials
         self.dE = torch.empty((n_local, M, D), dtype=f32, device=dev)
         self.grad_out = torch.ones((), dtype=f32, device=dev)
         nbytes = lib().ge2e_b200_workspace_bytes(n_local, n_total, M, D, self.variant, self.precision)
         self._ws = torch.zeros(max(nbytes, 1), dtype=torch.uint8, device=dev)
         self._ws_bytes = nbytes
-        self.loss, self.dw, self.db = self.red[0], self.red[1], self.red[2]
+        # global {loss, dw, db, -} after a step: `red` all-reduced in place (NCCL), or the sum of the ranks' rows
+        self.results = self.red_sum if self.peer else self.red
+        self.loss, self.dw, self.db = self.results[0], self.results[1], self.results[2]
         self._side = torch.cuda.Stream(device=dev)
 
     def _setup_peer_memory(self, world: int, rank: int) -> None:
@@ -179,10 +181,26 @@ class ShardedGE2EPlan:
         if len(ptr_c) != world or len(ptr_d) != world:
             raise RuntimeError("symmetric-memory rendezvous returned a different world size")
         off_bytes = self.spk_offset * self.D * 4
-        peers = [ptr_c[r] + off_bytes for r in range(world) if r != rank]       # MY slice in every peer's c_hat_all
-        self._peer_slices = (C.c_void_p * len(peers))(*peers)
+        try:
+            mc = int(hc.multicast_ptr)
+        except Exception:
+            mc = 0
+        if mc:
+            # NVSwitch multicast: one store per element leaves this GPU, the switch writes every rank's copy
+            self._peer_slices, self._n_peers, self._mcast = (C.c_void_p * 1)(mc + off_bytes), 1, 1
+        else:
+            peers = [ptr_c[r] + off_bytes for r in range(world) if r != rank]   # MY slice in every peer's c_hat_all
+            self._peer_slices, self._n_peers, self._mcast = (C.c_void_p * len(peers))(*peers), len(peers), 0
         self._dC_owner = (C.c_void_p * world)(*ptr_d)                            # every rank's dC_local, mine included
-        self._n_peers, self._world = len(peers), world
+        self._world = world
+        # {loss, dw, db} of every rank: a [world, 4] table replicated on every rank; rank r stores its row into
+        # every copy in front of the second barrier, every rank sums the rows itself (no all-reduce kernel)
+        red_all = symm.empty((world, 4), dtype=f32, device=dev)
+        hr = symm.rendezvous(red_all, gname)
+        rows = [p + rank * 16 for p in hr.buffer_ptrs]
+        self._red_rows = (C.c_void_p * world)(*rows)
+        self.red_all, self._hr = red_all, hr
+        self.red_sum = torch.zeros(4, dtype=f32, device=dev)
         self._hc, self._hd = hc, hd
         self.c_hat_all = c_all
         self.c_hat_mine = c_all[self.spk_offset:self.spk_offset + self.n_local]
@@ -200,8 +218,8 @@ class ShardedGE2EPlan:
         check(h.ge2e_b200_prep(E_local.data_ptr(), nl, M, D, self.precision, self.e_hat.data_ptr(),
                                self.c_hat_mine.data_ptr(), self.cos_diag.data_ptr(), self.red.data_ptr(), s),
               "ge2e_b200_prep")
-        check(h.ge2e_b200_peer_publish(self.c_hat_mine.data_ptr(), self._peer_slices, self._n_peers, nl, D,
-                                       self.dC_local.data_ptr(), s), "ge2e_b200_peer_publish")
+        check(h.ge2e_b200_peer_publish(self.c_hat_mine.data_ptr(), self._peer_slices, self._n_peers, self._mcast, nl * D,
+                                       self.dC_local.data_ptr(), nl * D, s), "ge2e_b200_peer_publish")
         self._hc.barrier(channel=0)          # every slice of c_hat_all has landed, every dC_local is cleared
         check(h.ge2e_b200_step_rows_peers(self.e_hat.data_ptr(), self.c_hat_all.data_ptr(), self.cos_diag.data_ptr(), nl,
                                           nt, off, M, D, w.data_ptr(), b.data_ptr(), self.eps, self.variant,
@@ -209,16 +227,15 @@ class ShardedGE2EPlan:
                                           self.row_kstar.data_ptr(), self.row_aux.data_ptr(), self.row_scale.data_ptr(),
                                           self.red.data_ptr(), self.dE_hat.data_ptr(), self._dC_owner, self._world, ws,
                                           self._ws_bytes, s), "ge2e_b200_step_rows_peers")
-        self._hd.barrier(channel=0)          # every rank's contributions to my dC rows have landed
-        self._side.wait_stream(cur)
-        with torch.cuda.stream(self._side):
-            dist.all_reduce(self.red, op=dist.ReduceOp.SUM, group=self.group)
+        check(h.ge2e_b200_peer_publish(self.red.data_ptr(), self._red_rows, self._world, 0, 4, None, 0, s),
+              "ge2e_b200_peer_publish")   # my {loss, dw, db} into row `rank` of every rank's table
+        self._hd.barrier(channel=0)          # every rank's contributions to my dC rows (and its scalars) have landed
         check(h.ge2e_b200_bwd_finalize(E_local.data_ptr(), self.dE_hat.data_ptr(), self.dC_local.data_ptr(),
                                        self.cos_diag.data_ptr(), self.row_stat.data_ptr(), self.row_aux.data_ptr(),
                                        self.row_scale.data_ptr(), nl, M, D, w.data_ptr(), b.data_ptr(), self.eps,
                                        self.variant, self.grad_out.data_ptr(), self.dE.data_ptr(), s),
               "ge2e_b200_bwd_finalize")
-        cur.wait_stream(self._side)
+        torch.sum(self.red_all, dim=0, out=self.red_sum)
 
     def step(self, E_local: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> None:
         if self.peer:
@@ -386,4 +403,4 @@ class ShardedGE2EHostFeed(_HostFeed):
         dev = torch.device(device if device is not None else "cuda")
         self._setup((n_local, M, D), depth, dev,
                     lambda: ShardedGE2EPlan(n_local, n_total, spk_offset, M, D, variant, precision, eps, group, dev),
-                    lambda p, res: [(res, p.red[0:3])])
+                    lambda p, res: [(res, p.results[0:3])])
