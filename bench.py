@@ -671,8 +671,13 @@ def run_ours(args):
                                  "is checked against the float64 oracle at this size in tests/test_gpu_step.py"}
             extra["parity_check"] = parity
             del E1, plan1
-            sharded_how = (f"K steps incl. NCCL collectives in one CUDA graph, shard rotating over {n_rot} batches "
-                           f"({n_rot * n_local * M * D * 4 / 1e6:.0f} MB), one event pair, max over ranks")
+            exchange = ("peer memory over NVLink (multicast publish of c_hat, step kernel reduce-adds dC_hat into the owner "
+                        "rank, symmetric-memory barriers; no NCCL kernel in the step)" if splan.peer
+                        else "NCCL all-gather / reduce-scatter / all-reduce")
+            extra["exchange"] = {"peer_memory": bool(splan.peer), "multicast": bool(getattr(splan, "_mcast", 0)),
+                                 "peer_error": splan.peer_error, "how": exchange}
+            sharded_how = (f"K steps incl. the exchange steps ({exchange}) in one CUDA graph, shard rotating over {n_rot} "
+                           f"batches ({n_rot * n_local * M * D * 4 / 1e6:.0f} MB), one event pair, max over ranks")
         launches = int(lib().ge2e_b200_launch_count() - launches_before)
         path = lib().ge2e_b200_path(n_local, N, M, D, 0 if args.variant == "softmax" else 1,
                                     1 if args.precision == "tf32" else 0)
