@@ -50,7 +50,15 @@ enum ge2e_variant { GE2E_SOFTMAX = 0, GE2E_CONTRAST = 1 }; /* paper eq. (6) / eq
  *            taken against the fixed shift |w| + b (|cos| <= 1 bounds every logit): exact for
  *            |w| <= 43; beyond that the smallest terms flush to zero (the reference's own
  *            un-stabilised exp(S), s3:120, overflows beyond w + b = 88). */
-enum ge2e_precision { GE2E_FP32 = 0, GE2E_TF32 = 1 };
+/* GE2E_FP32_SPLIT: fp32-class accuracy on the tensor cores (reference arithmetic is fp32, s3:57,70).  Every
+ *            operand travels as two fp16 planes hi = fp16(x), lo = fp16(x - hi) -- e_hat / c_hat then hold
+ *            [2][rows][D] halves in the same bytes as [rows][D] floats -- and every product is the three
+ *            kind::f16 MMAs hi.hi + hi.lo + lo.hi with fp32 accumulation (error ~2^-22 per term).  The
+ *            softmax probabilities are normalised by a forward launch before the step kernel cuts them into
+ *            planes.  Softmax variant, D = 128 or 256, shapes of the tensor-core path only; unlike GE2E_TF32
+ *            this is a demand: an uncovered (shape, variant) returns GE2E_ERR_UNSUPPORTED -- ask
+ *            ge2e_b200_path() first and fall back to GE2E_FP32. */
+enum ge2e_precision { GE2E_FP32 = 0, GE2E_TF32 = 1, GE2E_FP32_SPLIT = 2 };
 
 int ge2e_b200_version(void);
 const char* ge2e_b200_strerror(int status);
@@ -58,7 +66,8 @@ const char* ge2e_b200_strerror(int status);
 int ge2e_b200_last_cuda_error(void);
 /* Number of kernels this library has launched (host-side count, all threads). */
 unsigned long long ge2e_b200_launch_count(void);
-/* Which kernels a (shape, variant, precision) uses: 0 = SIMT fp32 FMA, 1 = tcgen05 TF32.
+/* Which kernels a (shape, variant, precision) uses: 0 = SIMT fp32 FMA, 1 = tcgen05 TF32, 2 = tcgen05 split
+ * fp16 planes (GE2E_FP32_SPLIT; GE2E_ERR_UNSUPPORTED when the shape / variant is not covered).
  * GE2E_TF32 is a permission, not a demand: shapes the tensor-core path does not cover run on
  * the (more accurate) SIMT kernels.  Negative = bad variant / precision. */
 int ge2e_b200_path(int n_local, int n_total, int M, int D, int variant, int precision);

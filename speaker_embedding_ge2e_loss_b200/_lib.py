@@ -11,9 +11,22 @@ _i32p = C.c_void_p
 _stream = C.c_void_p
 
 SOFTMAX, CONTRAST = 0, 1
-FP32, TF32 = 0, 1
+FP32, TF32, FP32_SPLIT = 0, 1, 2
 VARIANTS = {"softmax": SOFTMAX, "contrast": CONTRAST}
-PRECISIONS = {"fp32": FP32, "tf32": TF32}
+# "fp32" (the default, the reference's arithmetic) means fp32-class results: on the tensor cores through the
+# split-fp16 operand mode where the shape is covered (resolve_precision), else the SIMT fp32 FMA kernels.
+# "fp32_simt" / "fp32_split" pin one of the two.
+PRECISIONS = {"fp32": FP32, "tf32": TF32, "fp32_simt": FP32, "fp32_split": FP32_SPLIT}
+
+
+def resolve_precision(name: str, n_local: int, n_total: int, M: int, D: int, variant: int) -> int:
+    """Precision code handed to the C ABI for a (shape, variant): "fp32" picks GE2E_FP32_SPLIT where
+    ge2e_b200_path() covers it (single-device calls only: the planes do not travel through the collectives)."""
+    if name not in PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
+    if name == "fp32" and n_local == n_total and lib().ge2e_b200_path(n_local, n_total, M, D, variant, FP32_SPLIT) == 2:
+        return FP32_SPLIT
+    return PRECISIONS[name]
 
 # name -> (restype, argtypes); kept in the order of include/ge2e_b200.h
 PROTOTYPES = {

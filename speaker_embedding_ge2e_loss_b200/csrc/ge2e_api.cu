@@ -27,8 +27,18 @@ int check_shape(int n_local, int n_total, int spk_offset, int M, int D) {
 
 int check_enum(int variant, int precision) {
   if (variant != GE2E_SOFTMAX && variant != GE2E_CONTRAST) return GE2E_ERR_ARGUMENT;
-  if (precision != GE2E_FP32 && precision != GE2E_TF32) return GE2E_ERR_ARGUMENT;
+  if (precision != GE2E_FP32 && precision != GE2E_TF32 && precision != GE2E_FP32_SPLIT) return GE2E_ERR_ARGUMENT;
   return GE2E_OK;
+}
+
+// (shape, variant, precision) runs on the tensor-core kernels.  GE2E_TF32 is a permission (uncovered shapes run
+// on the SIMT kernels, same operand layout); GE2E_FP32_SPLIT is a demand, because its operand layout (two fp16
+// planes) is only understood by the tensor-core kernels: callers check ge2e_b200_path() first.
+bool on_tc(int n_local, int n_total, int M, int D, int variant, int precision) {
+  if (n_local <= 0 || n_total <= 0 || M < 2 || D <= 0) return false;
+  if (precision == GE2E_TF32) return tc_supported(n_local, n_total, M, D, variant);
+  if (precision == GE2E_FP32_SPLIT) return tc_split_supported(n_local, n_total, M, D, variant);
+  return false;
 }
 
 }  // namespace
@@ -67,7 +77,8 @@ int ge2e_b200_debug_step_schedule(int u_local, int n_total, int cta_group, int m
 
 int ge2e_b200_path(int n_local, int n_total, int M, int D, int variant, int precision) {
   if (check_enum(variant, precision) != GE2E_OK) return GE2E_ERR_ARGUMENT;
-  return (precision == GE2E_TF32 && tc_supported(n_local, n_total, M, D, variant)) ? 1 : 0;
+  if (precision == GE2E_FP32_SPLIT) return on_tc(n_local, n_total, M, D, variant, precision) ? 2 : GE2E_ERR_UNSUPPORTED;
+  return on_tc(n_local, n_total, M, D, variant, precision) ? 1 : 0;
 }
 
 int ge2e_b200_check_device(void) {
@@ -79,8 +90,7 @@ int ge2e_b200_check_device(void) {
 }
 
 size_t ge2e_b200_workspace_bytes(int n_local, int n_total, int M, int D, int variant, int precision) {
-  if (precision == GE2E_TF32 && tc_supported(n_local, n_total, M, D, variant))
-    return tc_workspace_bytes(n_local, n_total, M, D, variant);
+  if (on_tc(n_local, n_total, M, D, variant, precision)) return tc_workspace_bytes(n_local, n_total, M, D, variant);
   return 0;
 }
 
@@ -91,8 +101,7 @@ int ge2e_b200_prep_indexed(const float* E, const int32_t* row_index, int n_local
   int rc = check_shape(n_local, n_local, 0, M, D);
   if (rc != GE2E_OK) return rc;
   if ((rc = check_enum(GE2E_SOFTMAX, precision)) != GE2E_OK) return rc;
-  return simt_prep(E, row_index, n_local, M, D, precision == GE2E_TF32, e_hat, c_hat_local, cos_diag, accum,
-                   (cudaStream_t)stream);
+  return simt_prep(E, row_index, n_local, M, D, precision, e_hat, c_hat_local, cos_diag, accum, (cudaStream_t)stream);
 }
 
 int ge2e_b200_prep(const float* E, int n_local, int M, int D, int precision, float* e_hat,
@@ -114,12 +123,22 @@ static int fwd_rows_impl(const float* e_hat, const float* c_hat_all, const float
   if (variant == GE2E_CONTRAST && !row_kstar) return GE2E_ERR_ARGUMENT;
   if (variant == GE2E_SOFTMAX && !row_aux) return GE2E_ERR_ARGUMENT;
   RowsArgs a{e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, b, eps, variant};
-  if (precision == GE2E_TF32 && tc_supported(n_local, n_total, M, D, variant)) {
+  if (precision == GE2E_FP32_SPLIT && !on_tc(n_local, n_total, M, D, variant, precision)) return GE2E_ERR_UNSUPPORTED;
+  if (on_tc(n_local, n_total, M, D, variant, precision)) {
     // the tensor-core path never materialises S: sim_out is an fp32-path feature
     if (sim_out != nullptr) return GE2E_ERR_UNSUPPORTED;
     if (workspace_bytes < tc_workspace_bytes(n_local, n_total, M, D, variant) ||
         (workspace == nullptr && tc_workspace_bytes(n_local, n_total, M, D, variant) > 0))
       return GE2E_ERR_WORKSPACE;
+    if (precision == GE2E_FP32_SPLIT) {
+      // the forward kernel closes the rows; with a backward to follow, the rows pass of the step kernel then
+      // forms dE_hat from probabilities that are already normalised (see ge2e_tc.cu, PREC_SPLIT)
+      rc = tc_fwd_rows(a, row_stat, row_kstar, row_aux, loss_accum, per_row_out, workspace, workspace_bytes, after_prep,
+                       (cudaStream_t)stream, true);
+      if (rc != GE2E_OK || dE_hat == nullptr || row_scale == nullptr) return rc;
+      return tc_step(a, 1, nullptr, row_stat, row_aux, nullptr, nullptr, row_scale, nullptr, nullptr, dE_hat, nullptr,
+                     nullptr, workspace, workspace_bytes, (cudaStream_t)stream, nullptr, 0, true);
+    }
     // softmax with a backward to follow: the rows pass of the step kernel (loss + un-normalised dE_hat)
     if (variant == GE2E_SOFTMAX && dE_hat != nullptr && row_scale != nullptr)
       return tc_step(a, 1, nullptr, nullptr, nullptr, row_stat, row_aux, row_scale, loss_accum, per_row_out, dE_hat,
@@ -161,13 +180,15 @@ int ge2e_b200_bwd_rows(const float* e_hat, const float* c_hat_all, const float* 
   // the contrast gradient is a 2-nonzeros-per-row gather/scatter: no contraction to put on
   // tensor cores, so both precisions share the SIMT kernel.  Softmax on tensor cores: the forward's rows
   // pass already left the un-normalised dE_hat (row_scale says so); only the centroid pass remains.
-  if (precision == GE2E_TF32 && variant == GE2E_SOFTMAX && row_scale != nullptr &&
-      tc_supported(n_local, n_total, M, D, variant)) {
+  if (precision == GE2E_FP32_SPLIT && (!on_tc(n_local, n_total, M, D, variant, precision) || row_scale == nullptr))
+    return GE2E_ERR_UNSUPPORTED;
+  if (variant == GE2E_SOFTMAX && row_scale != nullptr && on_tc(n_local, n_total, M, D, variant, precision)) {
     if (workspace_bytes < tc_workspace_bytes(n_local, n_total, M, D, variant) ||
         (workspace == nullptr && tc_workspace_bytes(n_local, n_total, M, D, variant) > 0))
       return GE2E_ERR_WORKSPACE;
     return tc_step(a, 2, grad_out, row_stat, row_aux, nullptr, nullptr, nullptr, nullptr, nullptr, dE_hat,
-                   dC_hat_partial, dwdb_accum, workspace, workspace_bytes, (cudaStream_t)stream);
+                   dC_hat_partial, dwdb_accum, workspace, workspace_bytes, (cudaStream_t)stream, nullptr, 0,
+                   precision == GE2E_FP32_SPLIT);
   }
   return simt_bwd_rows(a, row_stat, row_kstar, row_aux, grad_out, dE_hat, dC_hat_partial, dwdb_accum,
                        (cudaStream_t)stream);
@@ -251,8 +272,7 @@ int ge2e_b200_scale_bias_sgd(float* w, float* b, float* dw, float* db, float max
 // true when (shape, variant, precision) runs the softmax step on tensor cores: there the forward's rows pass
 // leaves an UN-NORMALISED dE_hat plus row_scale, and the backward is the centroid pass alone
 static bool tc_softmax_step(int n_local, int n_total, int M, int D, int variant, int precision) {
-  return precision == GE2E_TF32 && variant == GE2E_SOFTMAX && n_local > 0 && n_total > 0 && M >= 2 && D > 0 &&
-         tc_supported(n_local, n_total, M, D, variant);
+  return variant == GE2E_SOFTMAX && on_tc(n_local, n_total, M, D, variant, precision);
 }
 
 int ge2e_b200_forward_indexed(const float* E, const int32_t* row_index, int N, int M, int D, const float* w,
@@ -265,7 +285,7 @@ int ge2e_b200_forward_indexed(const float* E, const int32_t* row_index, int N, i
   if (rc != GE2E_OK) return rc;
   // tensor-core path: prep and the rows kernel are adjacent in the stream, the second one is launched
   // programmatically under the first one's tail
-  const bool tc = precision == GE2E_TF32 && N > 0 && M >= 2 && D > 0 && tc_supported(N, N, M, D, variant);
+  const bool tc = on_tc(N, N, M, D, variant, precision);
   rc = ge2e_b200_prep_indexed(E, row_index, N, M, D, precision, e_hat, c_hat, cos_diag, accum, stream);
   if (rc != GE2E_OK) return rc;
   return fwd_rows_impl(e_hat, c_hat, cos_diag, N, N, 0, M, D, w, b, eps, variant, precision, row_stat, row_kstar,
@@ -325,9 +345,18 @@ int ge2e_b200_step_rows(const float* e_hat, const float* c_hat_all, const float*
   if (tc_softmax_step(n_local, n_total, M, D, variant, precision)) {
     // ONE launch: rows pass, grid-wide barrier, centroid pass ({loss, dw, db} += into accum: zeroed by prep)
     RowsArgs a{e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, b, eps, variant};
+    if (precision == GE2E_FP32_SPLIT) {
+      // two launches: the forward kernel closes the rows (loss, lse, q), the step kernel runs both passes on them
+      rc = tc_fwd_rows(a, row_stat, row_kstar, row_aux, accum, nullptr, workspace, workspace_bytes, true,
+                       (cudaStream_t)stream, true);
+      if (rc != GE2E_OK) return rc;
+      return tc_step(a, 3, grad_out, row_stat, row_aux, nullptr, nullptr, row_scale, nullptr, nullptr, dE_hat,
+                     dC_hat_partial, accum + 1, workspace, workspace_bytes, (cudaStream_t)stream, nullptr, 0, true);
+    }
     return tc_step(a, 3, grad_out, nullptr, nullptr, row_stat, row_aux, row_scale, accum, nullptr, dE_hat,
                    dC_hat_partial, accum + 1, workspace, workspace_bytes, (cudaStream_t)stream);
   }
+  if (precision == GE2E_FP32_SPLIT) return GE2E_ERR_UNSUPPORTED;
   rc = fwd_rows_impl(e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, b, eps, variant, precision,
                      row_stat, row_kstar, row_aux, accum, nullptr, nullptr, nullptr, nullptr, workspace, workspace_bytes,
                      true, stream);
@@ -365,7 +394,7 @@ int ge2e_b200_step_rows_peers(const float* e_hat, const float* c_hat_all, const 
   if ((rc = check_enum(variant, precision)) != GE2E_OK) return rc;
   if (n_ranks < 2 || n_ranks > GE2E_MAX_PEERS || n_local * n_ranks != n_total) return GE2E_ERR_SHAPE;
   // only the tensor-core softmax step flushes through peer memory; everything else keeps the reduce-scatter
-  if (!tc_softmax_step(n_local, n_total, M, D, variant, precision)) return GE2E_ERR_UNSUPPORTED;
+  if (precision != GE2E_TF32 || !tc_softmax_step(n_local, n_total, M, D, variant, precision)) return GE2E_ERR_UNSUPPORTED;
   RowsArgs a{e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, b, eps, variant};
   return tc_step(a, 3, grad_out, nullptr, nullptr, row_stat, row_aux, row_scale, accum, nullptr, dE_hat, nullptr,
                  accum + 1, workspace, workspace_bytes, (cudaStream_t)stream, dC_owner_host, n_ranks);
@@ -380,7 +409,7 @@ void ge2e_b200_debug_small_step(int mode) { g_small_mode.store(mode < 0 || mode 
 static bool use_small_step(int N, int M, int D, int variant, int precision) {
   const int mode = small_step_mode();
   if (mode == 0 || !(mode == 2 ? small_step_supported(N, M, D) : small_step_preferred(N, M, D, variant))) return false;
-  return !(precision == GE2E_TF32 && tc_supported(N, N, M, D, variant));   // the tensor-core path keeps its shapes
+  return !on_tc(N, N, M, D, variant, precision);   // the tensor-core path keeps its shapes
 }
 
 size_t ge2e_b200_step_workspace_bytes(int N, int M, int D, int variant, int precision) {

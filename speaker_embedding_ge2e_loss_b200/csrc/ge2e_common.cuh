@@ -125,7 +125,9 @@ struct RowsArgs {
 };
 
 // row_index (nullable): logical row r = [speaker][utterance] lives at physical row row_index[r] of E / dE
-int simt_prep(const float* E, const int32_t* row_index, int n_local, int M, int D, bool round_tf32, float* e_hat,
+// prec: 0 = fp32 operands as they are, 1 = rounded to TF32, 2 = two fp16 planes [2][rows][D] (hi, lo) in the
+// same allocation (D = 128 / 256 / 512 only)
+int simt_prep(const float* E, const int32_t* row_index, int n_local, int M, int D, int prec, float* e_hat,
               float* c_hat_local, float* cos_diag, float* accum, cudaStream_t st);
 int simt_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* row_aux,
                   float* loss_accum, float* per_row_out, float* sim_out, cudaStream_t st);
@@ -167,6 +169,8 @@ int tail_bwd_rows(const float* dE, const float* E, const float* inv_norm, int U,
 
 // ---- launchers implemented in ge2e_tc.cu (tcgen05 / TMA / TMEM path) ----------------------
 bool tc_supported(int n_local, int n_total, int M, int D, int variant);
+// fp32-class precision on tensor cores (operands as two fp16 planes, see ge2e_tc.cu): softmax, D = 128 / 256
+bool tc_split_supported(int n_local, int n_total, int M, int D, int variant);
 void tc_set_trace(unsigned long long* device_buf, int mode);
 void tc_set_stamps(unsigned long long* device_buf);
 int tc_debug_step_schedule(int u_local, int n_total, int cg, int max_clusters, int* de_begin, int* dc_begin,
@@ -174,7 +178,7 @@ int tc_debug_step_schedule(int u_local, int n_total, int cg, int max_clusters, i
 size_t tc_workspace_bytes(int n_local, int n_total, int M, int D, int variant);
 int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* row_aux,
                 float* loss_accum, float* per_row_out, void* ws, size_t ws_bytes, bool after_prep,
-                cudaStream_t st);
+                cudaStream_t st, bool split = false);
 // softmax step on tensor cores; phases: 1 = rows pass (loss, row statistics, un-normalised dE_hat + row_scale),
 // 2 = centroid pass (dC_hat_partial, {dw, db}), 3 = both in one launch
 // dC_owner (nullable, HOST array of n_ranks device pointers): speaker-sharded over peer memory -- pass 2 adds its
@@ -182,7 +186,7 @@ int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* r
 int tc_step(const RowsArgs& a, int phases, const float* grad_out, const float* row_stat_in, const float* row_aux_in,
             float* row_stat, float* row_aux, float* row_scale, float* loss_accum, float* per_row_out, float* dE_hat,
             float* dC_hat_partial, float* dwdb_accum, void* ws, size_t ws_bytes, cudaStream_t st,
-            float* const* dC_owner = nullptr, int n_ranks = 0);
+            float* const* dC_owner = nullptr, int n_ranks = 0, bool split = false);
 int simt_peer_publish(const float* src, float* const* dst, int n_dst, bool multicast, long long n_floats, float* zero,
                       long long zero_floats, cudaStream_t st);
 

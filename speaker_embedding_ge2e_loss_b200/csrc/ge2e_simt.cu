@@ -15,6 +15,7 @@
 //                    (reference s3:64-79, s3:27, s3:114-127 and their autograd)
 //   contrast_bwd     the contrast gradient has two non-zeros per row: gather/scatter kernel
 //   finalize_kernel  one CTA per speaker: diagonal term, normalisation Jacobians, fan-out
+#include <cuda_fp16.h>
 #include <limits.h>
 
 #include <algorithm>
@@ -176,11 +177,32 @@ prep_kernel(const float* __restrict__ E, const int32_t* __restrict__ idx, int M,
 // re-reads them (L1 hits) for the norms / leave-one-out cosine (s3:57) and writes e_hat.
 // Requires D = 128 KCH, 16-byte aligned rows.  grid = ceil(n_local / 4), block = 128.
 // ------------------------------------------------------------------------------------------
+// Operand precision of the normalised rows (PREC): 0 = fp32 as they are, 1 = rounded to TF32, 2 = two fp16 planes
+// hi = fp16(x), lo = fp16(x - hi) laid out [2][rows][D] in the same allocation (the tensor-core path's fp32-class
+// mode: hi.hi + hi.lo + lo.hi reproduces the fp32 product to ~2^-22).  put4 stores columns [col, col + 4) of `row`.
+template <int PREC>
+__device__ __forceinline__ void put4(float* base, size_t row, int D, int col, size_t plane_elems, float4 v) {
+  if (PREC == 2) {
+    __half* h = reinterpret_cast<__half*>(base);
+    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+    uint2 hi, lo;
+    hi.x = *reinterpret_cast<const uint32_t*>(&h0); hi.y = *reinterpret_cast<const uint32_t*>(&h1);
+    lo.x = *reinterpret_cast<const uint32_t*>(&l0); lo.y = *reinterpret_cast<const uint32_t*>(&l1);
+    *reinterpret_cast<uint2*>(h + row * D + col) = hi;
+    *reinterpret_cast<uint2*>(h + plane_elems + row * D + col) = lo;
+  } else {
+    if (PREC == 1) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+    *reinterpret_cast<float4*>(base + row * D + col) = v;
+  }
+}
+
 constexpr int kPrepWarps = 4;
 constexpr int kRowBatch = 4;   // rows in flight per lane (KCH float4 loads each)
 constexpr int kRegRows = 16;   // register-resident variants hold up to this many rows per speaker
 
-template <int KCH, bool ROUND>
+template <int KCH, int PREC>
 __global__ void __launch_bounds__(kPrepWarps * 32)
 prep_warp_kernel(const float* __restrict__ E, const int32_t* __restrict__ idx, int n_local, int M,
                  float* __restrict__ e_hat, float* __restrict__ c_hat, float* __restrict__ cos_diag,
@@ -219,15 +241,11 @@ prep_warp_kernel(const float* __restrict__ E, const int32_t* __restrict__ idx, i
   for (int c = 0; c < KCH; ++c) ss += dot4(s[c], s[c]);
   ss = warp_sum(ss);
   const float sc = inv_m / fmaxf(sqrtf(ss) * inv_m, kCosDelta);
-  float4* Cj = reinterpret_cast<float4*>(c_hat + (size_t)j * D) + lane;
 #pragma unroll
-  for (int c = 0; c < KCH; ++c) {
-    float4 o = make_float4(s[c].x * sc, s[c].y * sc, s[c].z * sc, s[c].w * sc);
-    if (ROUND) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-    Cj[c * 32] = o;
-  }
+  for (int c = 0; c < KCH; ++c)
+    put4<PREC>(c_hat, j, D, 4 * lane + 128 * c, (size_t)n_local * D,
+               make_float4(s[c].x * sc, s[c].y * sc, s[c].z * sc, s[c].w * sc));
   // rows: |e|, |u| and e.u with u = (s - e) / (M - 1)   (s3:105-111, s3:57)
-  float4* Oj = reinterpret_cast<float4*>(e_hat + (size_t)j * M * D) + lane;
   float my_cos = 0.f;
   for (int i0 = 0; i0 < M; i0 += kRowBatch) {
     float4 v[kRowBatch][KCH];
@@ -265,8 +283,7 @@ prep_warp_kernel(const float* __restrict__ E, const int32_t* __restrict__ idx, i
         for (int c = 0; c < KCH; ++c) {
           float4 e = v[r][c];
           e.x *= inv_ne; e.y *= inv_ne; e.z *= inv_ne; e.w *= inv_ne;
-          if (ROUND) { e.x = round_tf32(e.x); e.y = round_tf32(e.y); e.z = round_tf32(e.z); e.w = round_tf32(e.w); }
-          Oj[(size_t)(i0 + r) * (D / 4) + c * 32] = e;
+          put4<PREC>(e_hat, (size_t)j * M + i0 + r, D, 4 * lane + 128 * c, (size_t)n_local * M * D, e);
         }
       }
     }
@@ -303,7 +320,7 @@ __device__ __forceinline__ float reduce16_transposed(const float (&v)[16], int l
   return e + __shfl_xor_sync(0xffffffffu, e, 16);
 }
 
-template <int KCH, int RR, bool ROUND>
+template <int KCH, int RR, int PREC>
 __global__ void __launch_bounds__(kPrepWarps * 32)
 prep_reg_kernel(const float* __restrict__ E, const int32_t* __restrict__ idx, int n_local, int M,
                 float* __restrict__ e_hat, float* __restrict__ c_hat, float* __restrict__ cos_diag,
@@ -336,13 +353,10 @@ prep_reg_kernel(const float* __restrict__ E, const int32_t* __restrict__ idx, in
   for (int c = 0; c < KCH; ++c) ss += dot4(s[c], s[c]);
   ss = warp_sum(ss);
   const float sc = inv_m / fmaxf(sqrtf(ss) * inv_m, kCosDelta);       // s3:37 + normalisation
-  float4* Cj = reinterpret_cast<float4*>(c_hat + (size_t)j * D) + lane;
 #pragma unroll
-  for (int c = 0; c < KCH; ++c) {
-    float4 o = make_float4(s[c].x * sc, s[c].y * sc, s[c].z * sc, s[c].w * sc);
-    if (ROUND) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-    Cj[c * 32] = o;
-  }
+  for (int c = 0; c < KCH; ++c)
+    put4<PREC>(c_hat, j, D, 4 * lane + 128 * c, (size_t)n_local * D,
+               make_float4(s[c].x * sc, s[c].y * sc, s[c].z * sc, s[c].w * sc));
   // |e|^2, |s - e|^2, e.(s - e) of every row (u = (s - e) / (M - 1): s3:105-111)
   float ne2[16], nd2[16], ed[16];
 #pragma unroll
@@ -363,7 +377,6 @@ prep_reg_kernel(const float* __restrict__ E, const int32_t* __restrict__ idx, in
   const float inv_ne = 1.f / fmaxf(sqrtf(t_ne2), kCosDelta);
   const float inv_nu = 1.f / fmaxf(sqrtf(t_nd2) * inv_m1, kCosDelta);
   if (lane < 16 && my_row < M) cos_diag[(size_t)j * M + my_row] = (t_ed * inv_m1) * inv_ne * inv_nu;   // s3:57
-  float4* Oj = reinterpret_cast<float4*>(e_hat + (size_t)j * M * D) + lane;
 #pragma unroll
   for (int i = 0; i < R; ++i) {
     if (i < M) {      // warp-uniform
@@ -372,8 +385,7 @@ prep_reg_kernel(const float* __restrict__ E, const int32_t* __restrict__ idx, in
       for (int c = 0; c < KCH; ++c) {
         float4 e = v[i][c];
         e.x *= k; e.y *= k; e.z *= k; e.w *= k;
-        if (ROUND) { e.x = round_tf32(e.x); e.y = round_tf32(e.y); e.z = round_tf32(e.z); e.w = round_tf32(e.w); }
-        Oj[(size_t)i * (D / 4) + c * 32] = e;
+        put4<PREC>(e_hat, (size_t)j * M + i, D, 4 * lane + 128 * c, (size_t)n_local * M * D, e);
       }
     }
   }
@@ -1292,22 +1304,25 @@ bool warp_path_ok(int D, std::initializer_list<const void*> ptrs) {
 }
 
 template <int KCH>
-void launch_prep_warp(const float* E, const int32_t* idx, int n_local, int M, bool rnd, float* e_hat, float* c_hat,
+void launch_prep_warp(const float* E, const int32_t* idx, int n_local, int M, int prec, float* e_hat, float* c_hat,
                       float* cos_diag, float* accum, cudaStream_t st) {
   const int grid = (n_local + kPrepWarps - 1) / kPrepWarps;
   if (KCH <= 2 && M <= kRegRows) {
     constexpr int K2 = KCH <= 2 ? KCH : 1;    // the register-resident variant is only instantiated for D <= 256
     const dim3 g(grid), bl(kPrepWarps * 32);
 #define GE2E_PREP_REG(RR)                                                                                          \
-  (rnd ? launch_pdl(prep_reg_kernel<K2, RR, true>, g, bl, 0, st, true, E, idx, n_local, M, e_hat, c_hat, cos_diag, accum) \
-       : launch_pdl(prep_reg_kernel<K2, RR, false>, g, bl, 0, st, true, E, idx, n_local, M, e_hat, c_hat, cos_diag, accum))
+  (prec == 2 ? launch_pdl(prep_reg_kernel<K2, RR, 2>, g, bl, 0, st, true, E, idx, n_local, M, e_hat, c_hat, cos_diag, accum) \
+   : prec == 1 ? launch_pdl(prep_reg_kernel<K2, RR, 1>, g, bl, 0, st, true, E, idx, n_local, M, e_hat, c_hat, cos_diag, accum) \
+               : launch_pdl(prep_reg_kernel<K2, RR, 0>, g, bl, 0, st, true, E, idx, n_local, M, e_hat, c_hat, cos_diag, accum))
     if (M <= 4) GE2E_PREP_REG(4); else if (M <= 8) GE2E_PREP_REG(8); else if (M <= 12) GE2E_PREP_REG(12); else GE2E_PREP_REG(16);
 #undef GE2E_PREP_REG
     return;
   }
-  if (rnd) launch_pdl(prep_warp_kernel<KCH, true>, dim3(grid), dim3(kPrepWarps * 32), 0, st, true, E, idx, n_local, M,
-                      e_hat, c_hat, cos_diag, accum);
-  else launch_pdl(prep_warp_kernel<KCH, false>, dim3(grid), dim3(kPrepWarps * 32), 0, st, true, E, idx, n_local, M,
+  if (prec == 2) launch_pdl(prep_warp_kernel<KCH, 2>, dim3(grid), dim3(kPrepWarps * 32), 0, st, true, E, idx, n_local, M,
+                            e_hat, c_hat, cos_diag, accum);
+  else if (prec == 1) launch_pdl(prep_warp_kernel<KCH, 1>, dim3(grid), dim3(kPrepWarps * 32), 0, st, true, E, idx, n_local,
+                                 M, e_hat, c_hat, cos_diag, accum);
+  else launch_pdl(prep_warp_kernel<KCH, 0>, dim3(grid), dim3(kPrepWarps * 32), 0, st, true, E, idx, n_local, M,
                   e_hat, c_hat, cos_diag, accum);
 }
 
@@ -1330,15 +1345,17 @@ void launch_finalize_warp(const float* E, const float* dE_hat, const float* dC_h
              row_aux, row_scale, n_local, M, w, b, eps, variant, g, dE, idx);
 }
 
-int simt_prep(const float* E, const int32_t* row_index, int n_local, int M, int D, bool round_tf32_, float* e_hat,
+int simt_prep(const float* E, const int32_t* row_index, int n_local, int M, int D, int prec, float* e_hat,
               float* c_hat_local, float* cos_diag, float* accum, cudaStream_t st) {
+  const bool round_tf32_ = prec == 1;
   if (warp_path_ok(D, {E, e_hat, c_hat_local})) {
-    if (D == 128) launch_prep_warp<1>(E, row_index, n_local, M, round_tf32_, e_hat, c_hat_local, cos_diag, accum, st);
-    else if (D == 256) launch_prep_warp<2>(E, row_index, n_local, M, round_tf32_, e_hat, c_hat_local, cos_diag, accum, st);
-    else launch_prep_warp<4>(E, row_index, n_local, M, round_tf32_, e_hat, c_hat_local, cos_diag, accum, st);
+    if (D == 128) launch_prep_warp<1>(E, row_index, n_local, M, prec, e_hat, c_hat_local, cos_diag, accum, st);
+    else if (D == 256) launch_prep_warp<2>(E, row_index, n_local, M, prec, e_hat, c_hat_local, cos_diag, accum, st);
+    else launch_prep_warp<4>(E, row_index, n_local, M, prec, e_hat, c_hat_local, cos_diag, accum, st);
     GE2E_LAUNCHED();
     return GE2E_OK;
   }
+  if (prec == 2) return GE2E_ERR_UNSUPPORTED;     // the fp16 planes are written by the warp kernels only
   const int Dp = (D + 3) & ~3;
   const size_t smem = (size_t)(M + 1) * Dp * sizeof(float);
   if (smem > 200 * 1024) return GE2E_ERR_UNSUPPORTED;

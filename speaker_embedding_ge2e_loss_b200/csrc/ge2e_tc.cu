@@ -45,6 +45,7 @@
 // share a tile row).  Producer and MMA warps run their loops with all 32 lanes and issue through
 // elect.sync: what looks like a detail is a 2.5x difference in MMA issue rate (see the probe).
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cudaTypedefs.h>
 #include <limits.h>
 #include <stdlib.h>
@@ -79,6 +80,19 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
 enum { TC_FWD = 0, TC_STEP = 1 };
+// operand precision: TF32 (one rounded fp32 plane) or SPLIT (fp32-class: every operand as two fp16 planes
+// hi = fp16(x), lo = fp16(x - hi); a product is the three kind::f16 MMAs hi.hi + hi.lo + lo.hi)
+enum { PREC_TF32 = 0, PREC_SPLIT = 1 };
+// The probability planes carry p * 2^(14 + k): 2^14 keeps p <= 1 inside fp16, and k >= 0 lifts what is known to
+// be small -- pass 1: k_r from q_r = 1 - p_jj >= every off-diagonal probability of utterance row r (per owner
+// row, undone by row_scale); pass 2: k from the largest q of the whole batch (undone in the accumulator flush).
+// Without the lift a confident batch (all off-diagonal p ~ 1e-8) would sit in the fp16 subnormals.
+constexpr int kSplitLift = 14;
+constexpr int kSplitMaxExtra = 96;
+__device__ __forceinline__ int split_extra_lift(float q) {      // largest k in [0, 96] with q * 2^k <= 1
+  if (!(q > 0.f)) return kSplitMaxExtra;
+  return max(0, min(kSplitMaxExtra, -ilogbf(q) - 1));
+}
 enum { PASS_ROWS = 1, PASS_CENTROIDS = 2 };   // TcParams::phases
 enum { SEG_DE = 0, SEG_DC = 1 };      // index into the per-segment-kind arrays (FWD uses index 0)
 
@@ -211,11 +225,21 @@ struct Walk {
   }
 };
 
-template <int MODE, int VARIANT, int CG, bool DBG>
+// two fp32 values -> packed fp16 pair of their leading parts and of the remainders
+__device__ __forceinline__ void split_pack(float p0, float p1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(p0, p1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+template <int MODE, int VARIANT, int CG, int PREC, bool DBG>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepSched sched, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr bool kBwd = (MODE != TC_FWD);
+  constexpr bool kSplit = (PREC == PREC_SPLIT);
   constexpr int kStageBytes = 32768 / CG;
   constexpr int kStages = 3 * CG;
   constexpr uint16_t kPairMask = (CG == 2) ? 3 : 1;
@@ -238,6 +262,8 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
   // barriers the MMA warp waits on live in the leader: address them through the cluster window
   auto lbar = [&](int i) { return (CG == 2) ? mapa(bar(i), 0) : bar(i); };
   const int kslabs = p.kslabs;
+  // SPLIT: slab s of an operand tile is [rows x 64 fp16] = chunk s % hs of plane s / hs (hi plane first)
+  const int hs = kslabs >> 1;
   const int dbg = DBG ? p.dbg : 0;      // compile-time 0 in the production instantiation
 
   if (warp == 0 && lane == 0) {
@@ -313,8 +339,14 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
         uint32_t dst = ring_smem + stage * kStageBytes;
         for (int sl = 0; sl < nslab; ++sl)
           for (int r = 0; r < rows_cta; r += kBoxRows, dst += kBoxRows * 128) {
-            if (CG == 1) tma_load_2d(dst, tm, (ks0 + sl) * kSlabCols, row0 + r, full);
-            else tma_load_2d_2cta(dst, tm, (ks0 + sl) * kSlabCols, row0 + cr * rows_cta + r, full);
+            const int s = ks0 + sl;
+            if (kSplit) {
+              if (CG == 1) tma_load_3d(dst, tm, (s % hs) * 64, row0 + r, s / hs, full);
+              else tma_load_3d_2cta(dst, tm, (s % hs) * 64, row0 + cr * rows_cta + r, s / hs, full);
+            } else {
+              if (CG == 1) tma_load_2d(dst, tm, s * kSlabCols, row0 + r, full);
+              else tma_load_2d_2cta(dst, tm, s * kSlabCols, row0 + cr * rows_cta + r, full);
+            }
           }
       }
       __syncwarp();
@@ -329,8 +361,13 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
         if (leader) mbar_expect_tx(bar(BAR_FULL + stage), bytes * CG);
         const uint32_t full = lbar(BAR_FULL + stage);
         const uint32_t dst = ring_smem + stage * kStageBytes;
-        if (CG == 1) tma_load_3d(dst, tm, 0, row0, 0, full);
-        else tma_load_3d_2cta(dst, tm, 0, row0, cr * slabs_c, full);
+        if (kSplit) {        // [plane][chunk][32 rows][64 fp16]: this CTA's chunks of both planes in one box
+          if (CG == 1) tma_load_4d(dst, tm, 0, row0, 0, 0, full);
+          else tma_load_4d_2cta(dst, tm, 0, row0, cr * (hs / CG), 0, full);
+        } else {
+          if (CG == 1) tma_load_3d(dst, tm, 0, row0, 0, full);
+          else tma_load_3d_2cta(dst, tm, 0, row0, cr * slabs_c, full);
+        }
       }
       __syncwarp();
       advance();
@@ -344,14 +381,22 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
       const int ot = og * CG + cr;      // may be >= OT in the last group: TMA zero-fills, nothing is stored
       if (sg > 0) mbar_wait(bar(BAR_A_EMPTY), (sg - 1) & 1);      // every MMA1 of the previous segment has completed
       tr.mark();   // owner tile issue
-      for (int ks = 0; ks < kslabs; ++ks) {
+      for (int i = 0; i < kslabs; ++i) {
+        // SPLIT: chunk c of the hi plane is first used together with chunk c of the lo plane
+        const int ks = kSplit ? (i & 1) * hs + (i >> 1) : i;
         // STEP: the previous segment's accumulator leaves through the owner area, slab by slab; slab ks is
         // free again once the TMA store that took it out has read it
         if (kBwd && sg > 0) mbar_wait(bar(BAR_A_FREE + ks), (sg - 1) & 1);
         if (elect_one()) {
           if (leader) mbar_expect_tx(bar(BAR_A_FULL + ks), kSlabBytes * CG);
-          if (CG == 1) tma_load_2d(a_smem + ks * kSlabBytes, tm_own, ks * kSlabCols, ot * kTile, bar(BAR_A_FULL + ks));
-          else tma_load_2d_2cta(a_smem + ks * kSlabBytes, tm_own, ks * kSlabCols, ot * kTile, lbar(BAR_A_FULL + ks));
+          const uint32_t dst = a_smem + ks * kSlabBytes;
+          if (kSplit) {
+            if (CG == 1) tma_load_3d(dst, tm_own, (ks % hs) * 64, ot * kTile, ks / hs, bar(BAR_A_FULL + ks));
+            else tma_load_3d_2cta(dst, tm_own, (ks % hs) * 64, ot * kTile, ks / hs, lbar(BAR_A_FULL + ks));
+          } else {
+            if (CG == 1) tma_load_2d(dst, tm_own, ks * kSlabCols, ot * kTile, bar(BAR_A_FULL + ks));
+            else tma_load_2d_2cta(dst, tm_own, ks * kSlabCols, ot * kTile, lbar(BAR_A_FULL + ks));
+          }
         }
         __syncwarp();
       }
@@ -375,10 +420,12 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
   } else if (warp == 1) {
     // ===================================================================== MMA issuer (leader CTA)
     if (leader) {
-      const uint32_t idesc2 = idesc_tf32(kTile * CG, p.D, 0, 1);
+      const uint32_t idesc2 = kSplit ? idesc_f16(kTile * CG, p.D, 0, 1) : idesc_tf32(kTile * CG, p.D, 0, 1);
       // descriptor templates: only the 14-bit start-address field changes per MMA
       const uint64_t dk = smem_desc(0, 16, 1024, kLayoutSw128);                        // K-major
-      const uint64_t dmn = smem_desc(0, kMma2Rows * 128, 512, kLayoutSw128Base32);     // MN-major TF32
+      // MN-major: TF32 needs the 32-byte-atom swizzle (4-row groups), fp16 the plain 128B swizzle (8-row groups)
+      const uint64_t dmn = kSplit ? smem_desc(0, kMma2Rows * 128, 1024, kLayoutSw128)
+                                  : smem_desc(0, kMma2Rows * 128, 512, kLayoutSw128Base32);
       int stage = 0, phase = 0, sg = 0, it = 0;
       Tracer<DBG> tr(lane == 0 ? p.trace : nullptr, 1);
       tr.mark();
@@ -406,6 +453,31 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
       };
       // MMA1 over one stage holding `nslab` (1 or 2) K-slabs of [rows_cta x 32] starting at slab ks0
       auto mma1_stage = [&](uint32_t d_tmem, uint32_t idesc1, int rows_cta, int ks0, int nslab, bool first_of_seg) {
+        if (kSplit) {
+          // stream slab s = (plane, chunk c): a hi slab meets the owner's hi AND lo chunk c (8 MMAs), a lo slab
+          // the owner's hi chunk (4 MMAs); lo.lo is below fp32 resolution and is not formed
+          if (first_of_seg) {
+            for (int sl = 0; sl < nslab; ++sl) {
+              const int s = ks0 + sl, c = s % hs;
+              mbar_wait(bar(BAR_A_FULL + c), sg & 1);
+              if (s < hs) mbar_wait(bar(BAR_A_FULL + hs + c), sg & 1);
+            }
+          }
+          stage_wait();
+          uint32_t probe = 0;
+          if (elect_leader(leader)) {
+            probe = mbar_test(next_bar(), next_par());
+            for (int sl = 0; sl < nslab; ++sl) {
+              const int s = ks0 + sl, c = s % hs;
+              const uint64_t db = dk | ((ring_smem + stage * kStageBytes + sl * rows_cta * 128) >> 4);
+              umma_f16_ss4<CG>(d_tmem, dk | ((a_smem + c * kSlabBytes) >> 4), db, idesc1, s != 0);
+              if (s < hs) umma_f16_ss4<CG>(d_tmem, dk | ((a_smem + (hs + c) * kSlabBytes) >> 4), db, idesc1, 1);
+            }
+            commit(BAR_EMPTY + stage);
+          }
+          stage_done(probe);
+          return;
+        }
         if (first_of_seg) {
           for (int sl = 0; sl < nslab; ++sl) mbar_wait(bar(BAR_A_FULL + ks0 + sl), sg & 1);
         }
@@ -423,7 +495,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
         }
         stage_done(probe);
       };
-      const uint32_t idesc_unit = idesc_tf32(kTile * CG, kUnit, 0, 0);
+      const uint32_t idesc_unit = kSplit ? idesc_f16(kTile * CG, kUnit, 0, 0) : idesc_tf32(kTile * CG, kUnit, 0, 0);
       auto mma1_unit = [&](int iter, bool first_of_seg) {   // BWD: n = 128 into T[iter & 1]
         const uint32_t d_tmem = tmem + (iter & 1) * kUnit;
         for (int ks = 0; ks < kslabs; ks += 2)
@@ -437,6 +509,23 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
         for (int kc = 0; kc < kUnit / kMma2Rows; ++kc) {
           stage_wait();
           uint32_t probe = 0;
+          if (kSplit) {
+            if (elect_leader(leader)) {
+              probe = mbar_test(next_bar(), next_par());
+              // P / G planes in T (see the epilogue): column half h = kc / 2 holds [hi 32 cols | lo 32 cols] of
+              // its 64 stream rows; the stage's 32 rows start 16 columns into the plane when kc is odd
+              const uint32_t a_hi = a_tmem + 64 * (kc >> 1) + 16 * (kc & 1), a_lo = a_hi + 32;
+              const uint32_t sb = ring_smem + stage * kStageBytes;
+              const uint64_t db_hi = dmn | (sb >> 4);
+              const uint64_t db_lo = dmn | ((sb + (hs / CG) * kMma2Rows * 128) >> 4);
+              umma_f16_ts2<CG>(d_tmem, a_hi, db_hi, idesc2, !(first && kc == 0));
+              umma_f16_ts2<CG>(d_tmem, a_hi, db_lo, idesc2, 1);
+              umma_f16_ts2<CG>(d_tmem, a_lo, db_hi, idesc2, 1);
+              commit(BAR_EMPTY + stage);
+            }
+            stage_done(probe);
+            continue;
+          }
           if (elect_leader(leader)) {
             // MN-major TF32 operand: 32-byte-atom 128B swizzle, chunks of 32 columns kMma2Rows*128 B
             // apart (LBO), groups of 4 k-rows 512 B apart (SBO); one MMA consumes 8 k-rows = 1024 B
@@ -457,7 +546,8 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
             mbar_wait(bar(BAR_S_EMPTY + (it & 1)), ((it >> 1) & 1) ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem + (it & 1) * (kStepUnits * kUnit);
-            const uint32_t idesc_step = idesc_tf32(kTile * CG, nu * kUnit, 0, 0);
+            const uint32_t idesc_step = kSplit ? idesc_f16(kTile * CG, nu * kUnit, 0, 0)
+                                               : idesc_tf32(kTile * CG, nu * kUnit, 0, 0);
             for (int ks = 0; ks < kslabs; ++ks) mma1_stage(d_tmem, idesc_step, nu * kUnit / CG, ks, 1, u == s0);
             if (elect_one()) commit(BAR_S_FULL + (it & 1));
             __syncwarp();
@@ -507,6 +597,10 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
     const float m2 = b2 + fabsf(w2), mx = m2 * kLn2, c0 = -fabsf(w2);
     float dw_acc = 0.f, db_acc = 0.f, loss_acc = 0.f;
     int it = 0;
+    // STEP: the rows are closed in this launch (TF32: pass 1 produces the row sums) or were closed by the
+    // forward kernel in front of it (SPLIT: the probabilities must be normalised BEFORE they are cut into
+    // fp16 planes, so the log-sum-exp has to be known when pass 1 starts)
+    const bool close_here = kBwd && !kSplit && (p.phases & PASS_ROWS);
     Tracer<DBG> tr((trow == 0 && half == 0) ? p.trace : nullptr, 2);
     tr.mark();
     // epilogue -> MMA signals go to the leader CTA of the pair
@@ -546,7 +640,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
       };
       if (p.zero_n4 > 0) zfill(p.zero_base, p.zero_n4);
       if (p.zero2_n4 > 0) zfill(p.zero2_base, p.zero2_n4);
-      if (p.phases & PASS_ROWS) zfill(reinterpret_cast<float4*>(p.rowsum), (p.n_own[SEG_DE] + 3) / 4);
+      if (close_here) zfill(reinterpret_cast<float4*>(p.rowsum), (p.n_own[SEG_DE] + 3) / 4);
       __threadfence();
       named_bar_sync(1, kEpiThreads);
       if (et == 0) atomicAdd(p.ctr, 1);
@@ -555,6 +649,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
     // STEP: between the passes.  Grid-wide barrier (every row sum complete), then each CTA closes a slice
     // of the rows: log-sum-exp, row loss, q = 1 - p_jj, the factor of the un-normalised dE_hat row; the
     // diagonal terms of dw and the closed-form db ride along.
+    int lift2 = kSplitLift;      // SPLIT pass 2: exponent of the probability planes (set by close_rows)
     bool arrived = false;        // this CTA's row sums are out and counted at the grid barrier
     auto arrive_pass1 = [&]() {
       named_bar_sync(1, kEpiThreads);      // every thread's row-sum atomics have returned
@@ -563,17 +658,29 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
       tr.mark();   // arrived at the grid barrier
     };
     auto close_rows = [&]() {
-      if (p.phases & PASS_ROWS) {
+      if (close_here) {
         if (!arrived) arrive_pass1();      // a cluster without pass-1 work
         if (et == 0) spin_until(p.ctr + 2, static_cast<int>(gridDim.x));
         named_bar_sync(1, kEpiThreads);
       }
       tr.mark();   // grid barrier passed
       const int U = p.n_own[SEG_DE];
+      if (kSplit && (p.phases & PASS_CENTROIDS)) {
+        // pass 2's lift: every CTA takes the maximum of q over ALL rows (U floats out of the L2)
+        float qm = 0.f;
+        for (int r = et; r < U; r += kEpiThreads) qm = fmaxf(qm, __ldg(p.row_aux + r));
+        qm = warp_max(qm);
+        if (lane == 0) tail->red[ew] = qm;
+        named_bar_sync(1, kEpiThreads);
+        qm = tail->red[0];
+        for (int i = 1; i < kEpiWarps; ++i) qm = fmaxf(qm, tail->red[i]);
+        lift2 = kSplitLift + split_extra_lift(qm);
+        named_bar_sync(1, kEpiThreads);      // red is reused by the scalar reductions
+      }
       for (int r = blockIdx.x * kEpiThreads + et; r < U; r += gridDim.x * kEpiThreads) {
         const float cdv = __ldg(p.cos_diag + r);
         float stat, q;
-        if (p.phases & PASS_ROWS) {
+        if (close_here) {
           float per;
           close_softmax_row(mx, __ldcg(p.rowsum + r), fmaf(w, cdv + eps, b), eps, stat, q, per);   // s3:120-121
           p.row_stat_out[r] = stat;
@@ -584,6 +691,8 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
         } else {
           stat = __ldg(p.row_stat + r);
           q = __ldg(p.row_aux + r);
+          if (kSplit && (p.phases & PASS_ROWS))      // dE_hat row r was formed from p * 2^(14 + k_r)
+            p.row_scale_out[r] = w * exp2f(static_cast<float>(-(kSplitLift + split_extra_lift(q))));
         }
         if (p.phases & PASS_CENTROIDS) {
           dw_acc = fmaf(-q, cdv + eps, dw_acc);     // diagonal element G_jj = -g q (uses cos_diag)
@@ -628,17 +737,23 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
       // passes run in this launch (row_stat was written by other CTAs after the barrier), else row_stat
       auto lse2_of = [&](bool valid, float raw, float cdv) -> float {
         if (!valid) return INFINITY;
-        if (!(p.phases & PASS_ROWS)) return raw * kLog2e;
+        if (!close_here) return raw * kLog2e;
         float stat, q, per;
         close_softmax_row(mx, raw, fmaf(w, cdv + eps, b), eps, stat, q, per);
         return stat * kLog2e;
       };
       auto lse2_raw = [&](int ur, float& raw, float& cdv) -> bool {
         if (ur >= n_str) return false;
-        if (p.phases & PASS_ROWS) { raw = __ldcg(p.rowsum + ur); cdv = __ldg(p.cos_diag + ur); }
+        if (close_here) { raw = __ldcg(p.rowsum + ur); cdv = __ldg(p.cos_diag + ur); }
         else { raw = __ldg(p.row_stat + ur); cdv = 0.f; }
         return true;
       };
+      // SPLIT pass 1: exponent offset of this owner row, P * 2^14 = exp2(S w2 + c0r); a row past the end gives 0
+      float c0r = 0.f;
+      if (kBwd && kSplit && !is_dc)
+        c0r = ovalid ? (b2 + static_cast<float>(kSplitLift + split_extra_lift(__ldg(p.row_aux + orow)))) -
+                           __ldg(p.row_stat + orow) * kLog2e
+                     : -INFINITY;
       if (is_dc && half == 0) {
         float raw = 0.f, cdv = 0.f;
         const bool v0 = lse2_raw(s0 * kUnit + trow, raw, cdv);
@@ -660,6 +775,57 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
         tr.mark();   // T tile ready
         const uint32_t t_addr = tmem + lane_addr + buf * (kStepUnits * kUnit);
         const int nch = nu * (kUnit / 32) / 2;       // 32-column chunks per column half
+        if (kBwd && kSplit) {
+          // This thread's 64 columns of T become [hi plane: 32 cells | lo plane: 32 cells] of packed fp16 pairs
+          // IN PLACE, so all 64 are read before the first cell is written.
+          const uint32_t tb = t_addr + half * 64;
+          uint32_t v0[32], v1[32];
+          tmem_ld32(tb, v0);
+          tmem_ld32(tb + 32, v1);
+          tmem_ld_wait();
+          auto plane_chunk = [&](const uint32_t (&v)[32], int c2) {
+            const int ch = half * 2 + c2;
+            const int cc = u * kUnit + ch * 32;
+            uint32_t hi[16], lo[16];
+            if (!is_dc) {
+              const bool special = (cc + 32 > n_str) || (static_cast<unsigned>(jg - cc) < 32u);
+              const bool any_special = __any_sync(0xffffffffu, special);
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                float p0 = ex2(fmaf(__uint_as_float(v[i]), w2, c0r));
+                float p1 = ex2(fmaf(__uint_as_float(v[i + 1]), w2, c0r));
+                if (any_special) {     // padding / own speaker (s3:78)
+                  if (cc + i >= n_str || cc + i == jg) p0 = 0.f;
+                  if (cc + i + 1 >= n_str || cc + i + 1 == jg) p1 = 0.f;
+                }
+                split_pack(p0, p1, hi[i >> 1], lo[i >> 1]);
+              }
+            } else {
+              const float* ls = &tail->lse_s[buf][ch * 32];
+              const bool special = (cc < dhi) && (cc + 32 > dlo);
+              const bool any_special = __any_sync(0xffffffffu, special);
+              const float b2s = b2 + static_cast<float>(lift2);
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const float2 l2 = *reinterpret_cast<const float2*>(ls + i);
+                const float d0 = __uint_as_float(v[i]), d1 = __uint_as_float(v[i + 1]);
+                float p0 = ex2(fmaf(d0, w2, b2s) - l2.x);       // lse = +inf past the end
+                float p1 = ex2(fmaf(d1, w2, b2s) - l2.y);
+                if (any_special) {     // own speaker's rows
+                  if (cc + i >= dlo && cc + i < dhi) p0 = 0.f;
+                  if (cc + i + 1 >= dlo && cc + i + 1 < dhi) p1 = 0.f;
+                }
+                dw_seg = fmaf(p0, d0 + eps, dw_seg);
+                dw_seg = fmaf(p1, d1 + eps, dw_seg);
+                split_pack(p0, p1, hi[i >> 1], lo[i >> 1]);
+              }
+            }
+            tmem_st16(tb + 16 * c2, hi);
+            tmem_st16(tb + 32 + 16 * c2, lo);
+          };
+          plane_chunk(v0, 0);
+          plane_chunk(v1, 1);
+        } else
 #pragma unroll 1
         for (int ch = half * nch; ch < (half + 1) * nch; ++ch) {
           const int cc = u * kUnit + ch * 32;        // first stream row (column of T) of this chunk
@@ -819,7 +985,9 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
         // pass 1: the row sums are final once the last tile has been consumed -- they do not wait for the
         // accumulator; after the cluster's last pass-1 segment the CTA arrives at the grid barrier BEFORE
         // it flushes, so the flush runs under the barrier's skew instead of in front of it
-        if (!is_dc) {
+        if (!is_dc && !close_here) {
+          // SPLIT (or a lone pass 1 never happens without close_here in TF32): nothing to publish
+        } else if (!is_dc) {
           if (et == 0) wait_zero_fill();
           named_bar_sync(1, kEpiThreads);
           // value-returning atomics: when the old value is back the add has been performed at the L2, so
@@ -830,7 +998,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
           }
           if (wk.kind == SEG_DE && wk.gp >= wk.end) arrive_pass1();
         } else if (ovalid) {
-          dw_acc += dw_seg;
+          dw_acc += kSplit ? dw_seg * exp2f(static_cast<float>(-lift2)) : dw_seg;
         }
         // drain the accumulator [128 x D] of this segment (columns split between the two halves)
         mbar_wait(bar(BAR_ACC_FULL), sg & 1);
@@ -846,6 +1014,11 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
           uint32_t v[32];
           tmem_ld32(tmem + lane_addr + 2 * kUnit + ch * 32, v);
           tmem_ld_wait();
+          if (kSplit && is_dc) {       // the G planes carried p * 2^lift2: dC_hat = w g 2^-lift2 (.)
+            const float fs = wg * exp2f(static_cast<float>(-lift2));
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * fs);
+          }
           const uint32_t row_smem = a_smem + ch * kSlabBytes + trow * 128;
 #pragma unroll
           for (int c = 0; c < 8; ++c)
@@ -913,7 +1086,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
         for (int i = 0; i < kEpiWarps; ++i) {
           tl += tail->red3[i]; tw += tail->red3[kEpiWarps + i]; tb += tail->red3[2 * kEpiWarps + i];
         }
-        if (p.phases & PASS_ROWS) atomicAdd(p.loss_accum, tl);
+        if (close_here) atomicAdd(p.loss_accum, tl);
         if (p.phases & PASS_CENTROIDS) { atomicAdd(p.dwdb + 0, tw); atomicAdd(p.dwdb + 1, tb); }
         if (p.stamps != nullptr) p.stamps[2 * blockIdx.x + 1] = globaltimer_ns();
         // last CTA out restores the counters
@@ -1008,6 +1181,41 @@ int make_map_3d(CUtensorMap* m, const float* base, int rows, int D, int box_slab
   return r == CUDA_SUCCESS ? GE2E_OK : GE2E_ERR_LAUNCH;
 }
 
+// SPLIT operands: X as two fp16 planes [2][rows][D] (hi, lo).
+// 3-D map {D, rows, plane}: box = [1][box_rows][64 cols] = one K-major slab of one plane, 128-byte swizzle.
+int make_map_h3(CUtensorMap* m, const void* base, int rows, int D, int box_rows) {
+  const MapKey key{base, rows, D, box_rows, 13};
+  if (map_lookup(key, m)) return GE2E_OK;
+  auto enc = get_encode();
+  if (enc == nullptr) return GE2E_ERR_LAUNCH;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(rows), 2};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(D) * 2, static_cast<cuuint64_t>(rows) * D * 2};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS) map_store(key, *m);
+  return r == CUDA_SUCCESS ? GE2E_OK : GE2E_ERR_LAUNCH;
+}
+// 4-D map {64, rows, D/64, plane}: box = [2 planes][box_chunks][32 rows][64 cols] (MN-major operand of MMA2:
+// 32 k-rows x this CTA's columns, both planes, per ring stage); fp16 MN-major takes the plain 128B swizzle.
+int make_map_h4(CUtensorMap* m, const void* base, int rows, int D, int box_chunks) {
+  const MapKey key{base, rows, D, box_chunks, 14};
+  if (map_lookup(key, m)) return GE2E_OK;
+  auto enc = get_encode();
+  if (enc == nullptr) return GE2E_ERR_LAUNCH;
+  cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(D / 64), 2};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(D) * 2, 128, static_cast<cuuint64_t>(rows) * D * 2};
+  cuuint32_t box[4] = {64, kMma2Rows, static_cast<cuuint32_t>(box_chunks), 2};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS) map_store(key, *m);
+  return r == CUDA_SUCCESS ? GE2E_OK : GE2E_ERR_LAUNCH;
+}
+
 unsigned long long* g_trace = nullptr;   // set through tc_set_trace (debug only)
 int g_trace_mode = -1;                   // -1: every kernel, else only TC_FWD / TC_STEP
 int g_trace_fine = 0;                    // 8: per-stage marks in the MMA warp's trace
@@ -1055,9 +1263,10 @@ int max_clusters() {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaFuncSetAttribute(tc_strip_kernel<MODE, VARIANT, CG, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    // same block size, shared memory and cluster shape in every precision: the TF32 instantiation answers for all
+    cudaFuncSetAttribute(tc_strip_kernel<MODE, VARIANT, CG, PREC_TF32, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)kSmemBytes);
-    if (cudaOccupancyMaxActiveClusters(&n, tc_strip_kernel<MODE, VARIANT, CG, DBG>, &cfg) != cudaSuccess) n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, tc_strip_kernel<MODE, VARIANT, CG, PREC_TF32, DBG>, &cfg) != cudaSuccess) n = 0;
     (void)cudaGetLastError();
   }
   if (n <= 0) return 0;        // not cached: the caller reports GE2E_ERR_LAUNCH
@@ -1161,9 +1370,9 @@ int make_step_sched(int OGe, int STe, int OGc, int STc, int phases, int max_cl, 
   return NC;
 }
 
-template <int MODE, int VARIANT, int CG, bool DBG>
+template <int MODE, int VARIANT, int CG, int PREC, bool DBG>
 int launch_tc_impl(const TmSet& tms, const StepSched& sched, const TcParams& p, int NC, bool pdl, cudaStream_t st) {
-  auto kern = tc_strip_kernel<MODE, VARIANT, CG, DBG>;
+  auto kern = tc_strip_kernel<MODE, VARIANT, CG, PREC, DBG>;
   static bool attr_set[kMaxDevices] = {false};    // per instantiation and device
   const int dev = current_device();
   if (dev < 0 || dev >= kMaxDevices || !attr_set[dev]) {
@@ -1193,8 +1402,13 @@ int launch_tc_impl(const TmSet& tms, const StepSched& sched, const TcParams& p, 
 // the instrumented instantiation runs only while a trace buffer is set (ge2e_b200_debug_trace)
 template <int MODE, int VARIANT, int CG>
 int launch_tc(const TmSet& tms, const StepSched& sched, const TcParams& p, int NC, bool pdl, cudaStream_t st) {
-  if (g_trace != nullptr) return launch_tc_impl<MODE, VARIANT, CG, true>(tms, sched, p, NC, pdl, st);
-  return launch_tc_impl<MODE, VARIANT, CG, false>(tms, sched, p, NC, pdl, st);
+  if (g_trace != nullptr) return launch_tc_impl<MODE, VARIANT, CG, PREC_TF32, true>(tms, sched, p, NC, pdl, st);
+  return launch_tc_impl<MODE, VARIANT, CG, PREC_TF32, false>(tms, sched, p, NC, pdl, st);
+}
+// split precision: softmax, CTA pairs (D = 128 or 256), no instrumented twin
+template <int MODE>
+int launch_tc_split(const TmSet& tms, const StepSched& sched, const TcParams& p, int NC, bool pdl, cudaStream_t st) {
+  return launch_tc_impl<MODE, GE2E_SOFTMAX, 2, PREC_SPLIT, false>(tms, sched, p, NC, pdl, st);
 }
 
 template <int MODE, int VARIANT>
@@ -1256,6 +1470,12 @@ bool tc_supported(int n_local, int n_total, int M, int D, int variant) {
   return get_encode() != nullptr;
 }
 
+bool tc_split_supported(int n_local, int n_total, int M, int D, int variant) {
+  // softmax only (the contrast backward is a SIMT gather over fp32 operands); D = 128 / 256: prep's warp
+  // kernels write the planes, and the MMA2 stage must split evenly over the CTA pair
+  return variant == GE2E_SOFTMAX && (D == 128 || D == 256) && tc_supported(n_local, n_total, M, D, variant);
+}
+
 // workspace: [header 256 B: step counters][FWD seg_done][FWD seg_part][STEP row sums]
 size_t tc_workspace_bytes(int n_local, int n_total, int M, int D, int variant) {
   const Layout L = fwd_layout(n_local * M, n_total, D, variant);
@@ -1263,14 +1483,20 @@ size_t tc_workspace_bytes(int n_local, int n_total, int M, int D, int variant) {
 }
 
 int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* row_aux, float* loss_accum,
-                float* per_row_out, void* ws, size_t ws_bytes, bool after_prep, cudaStream_t st) {
+                float* per_row_out, void* ws, size_t ws_bytes, bool after_prep, cudaStream_t st, bool split) {
   const int U = a.n_local * a.M;
+  if (split && !tc_split_supported(a.n_local, a.n_total, a.M, a.D, a.variant)) return GE2E_ERR_UNSUPPORTED;
   const Layout L = fwd_layout(U, a.n_total, a.D, a.variant);
   if (ws == nullptr || ws_bytes < kWsHeaderBytes + L.done_bytes + L.part_bytes) return GE2E_ERR_WORKSPACE;
   TmSet tms{};
-  int rc = make_map_2d(&tms.own[0], a.e_hat, U, a.D, kTile);
-  if (rc != GE2E_OK) return rc;
-  if ((rc = make_map_2d(&tms.strk[0], a.c_hat_all, a.n_total, a.D, kBoxRows)) != GE2E_OK) return rc;
+  int rc;
+  if (split) {
+    if ((rc = make_map_h3(&tms.own[0], a.e_hat, U, a.D, kTile)) != GE2E_OK) return rc;
+    if ((rc = make_map_h3(&tms.strk[0], a.c_hat_all, a.n_total, a.D, kBoxRows)) != GE2E_OK) return rc;
+  } else {
+    if ((rc = make_map_2d(&tms.own[0], a.e_hat, U, a.D, kTile)) != GE2E_OK) return rc;
+    if ((rc = make_map_2d(&tms.strk[0], a.c_hat_all, a.n_total, a.D, kBoxRows)) != GE2E_OK) return rc;
+  }
   TcParams p{};
   fill_common(p, a);
   p.n_own[0] = U; p.n_str[0] = a.n_total; p.OT[0] = L.OT; p.ST[0] = L.ST; p.GP = L.GP;
@@ -1284,6 +1510,7 @@ int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* r
   // tail of whatever kernel precedes this one in the stream; the kernel waits before touching memory
   (void)after_prep;
   static const StepSched no_sched{};
+  if (split) return launch_tc_split<TC_FWD>(tms, no_sched, p, L.NC, true, st);
   if (a.variant == GE2E_SOFTMAX)
     return launch_tc_cg<TC_FWD, GE2E_SOFTMAX>(L.CG, tms, no_sched, p, L.NC, true, st);
   return launch_tc_cg<TC_FWD, GE2E_CONTRAST>(L.CG, tms, no_sched, p, L.NC, true, st);
@@ -1295,9 +1522,13 @@ int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* r
 int tc_step(const RowsArgs& a, int phases, const float* grad_out, const float* row_stat_in, const float* row_aux_in,
             float* row_stat, float* row_aux, float* row_scale, float* loss_accum, float* per_row_out, float* dE_hat,
             float* dC_hat_partial, float* dwdb_accum, void* ws, size_t ws_bytes, cudaStream_t st,
-            float* const* dC_owner, int n_ranks) {
+            float* const* dC_owner, int n_ranks, bool split) {
   const int U = a.n_local * a.M;
   const bool peers = dC_owner != nullptr && n_ranks > 1;
+  // SPLIT: the rows were closed by tc_fwd_rows(split) -- pass 1 and pass 2 both read row_stat_in / row_aux_in
+  if (split && (!tc_split_supported(a.n_local, a.n_total, a.M, a.D, a.variant) || peers || row_stat_in == nullptr ||
+                row_aux_in == nullptr))
+    return GE2E_ERR_UNSUPPORTED;
   if (peers && (n_ranks > kMaxPeers || a.n_total % n_ranks != 0 || (a.n_total / n_ranks) % kTile != 0 ||
                 !(phases & PASS_CENTROIDS)))
     return GE2E_ERR_UNSUPPORTED;
@@ -1342,13 +1573,23 @@ int tc_step(const RowsArgs& a, int phases, const float* grad_out, const float* r
 
   TmSet tms{};
   int rc;
-  if ((rc = make_map_2d(&tms.own[SEG_DE], a.e_hat, U, a.D, kTile)) != GE2E_OK) return rc;
-  if ((rc = make_map_2d(&tms.strk[SEG_DE], a.c_hat_all, a.n_total, a.D, kBoxRows)) != GE2E_OK) return rc;
-  if ((rc = make_map_3d(&tms.strmn[SEG_DE], a.c_hat_all, a.n_total, a.D, slabs / cg)) != GE2E_OK) return rc;
+  if (split) {
+    const int chunks_c = a.D / 64 / cg;
+    if ((rc = make_map_h3(&tms.own[SEG_DE], a.e_hat, U, a.D, kTile)) != GE2E_OK) return rc;
+    if ((rc = make_map_h3(&tms.strk[SEG_DE], a.c_hat_all, a.n_total, a.D, kBoxRows)) != GE2E_OK) return rc;
+    if ((rc = make_map_h4(&tms.strmn[SEG_DE], a.c_hat_all, a.n_total, a.D, chunks_c)) != GE2E_OK) return rc;
+    if ((rc = make_map_h3(&tms.own[SEG_DC], a.c_hat_all, a.n_total, a.D, kTile)) != GE2E_OK) return rc;
+    if ((rc = make_map_h3(&tms.strk[SEG_DC], a.e_hat, U, a.D, kBoxRows)) != GE2E_OK) return rc;
+    if ((rc = make_map_h4(&tms.strmn[SEG_DC], a.e_hat, U, a.D, chunks_c)) != GE2E_OK) return rc;
+  } else {
+    if ((rc = make_map_2d(&tms.own[SEG_DE], a.e_hat, U, a.D, kTile)) != GE2E_OK) return rc;
+    if ((rc = make_map_2d(&tms.strk[SEG_DE], a.c_hat_all, a.n_total, a.D, kBoxRows)) != GE2E_OK) return rc;
+    if ((rc = make_map_3d(&tms.strmn[SEG_DE], a.c_hat_all, a.n_total, a.D, slabs / cg)) != GE2E_OK) return rc;
+    if ((rc = make_map_2d(&tms.own[SEG_DC], a.c_hat_all, a.n_total, a.D, kTile)) != GE2E_OK) return rc;
+    if ((rc = make_map_2d(&tms.strk[SEG_DC], a.e_hat, U, a.D, kBoxRows)) != GE2E_OK) return rc;
+    if ((rc = make_map_3d(&tms.strmn[SEG_DC], a.e_hat, U, a.D, slabs / cg)) != GE2E_OK) return rc;
+  }
   if ((rc = make_map_2d(&tms.out[SEG_DE], dE_hat, U, a.D, kTile)) != GE2E_OK) return rc;
-  if ((rc = make_map_2d(&tms.own[SEG_DC], a.c_hat_all, a.n_total, a.D, kTile)) != GE2E_OK) return rc;
-  if ((rc = make_map_2d(&tms.strk[SEG_DC], a.e_hat, U, a.D, kBoxRows)) != GE2E_OK) return rc;
-  if ((rc = make_map_3d(&tms.strmn[SEG_DC], a.e_hat, U, a.D, slabs / cg)) != GE2E_OK) return rc;
   if ((rc = make_map_2d(&tms.out[SEG_DC], dC_hat_partial != nullptr ? dC_hat_partial : dE_hat, a.n_total, a.D, kTile)) != GE2E_OK)
     return rc;
   if (peers) {
@@ -1358,6 +1599,7 @@ int tc_step(const RowsArgs& a, int phases, const float* grad_out, const float* r
       if ((rc = make_map_2d(&tms.out_peer[r], dC_owner[r], p.peer_rows, a.D, kTile)) != GE2E_OK) return rc;
     }
   }
+  if (split) return launch_tc_split<TC_STEP>(tms, sched, p, NC, phases != PASS_CENTROIDS, st);
   return launch_tc_cg<TC_STEP, GE2E_SOFTMAX>(cg, tms, sched, p, NC, phases != PASS_CENTROIDS, st);
 }
 

@@ -76,6 +76,13 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int 
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int x, int y, int z, int w, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(z), "r"(w), "r"(bar)
+      : "memory");
+}
+
 // multicast variants: the box lands at the same CTA-relative offset in every CTA of `mask` and
 // completes tx bytes on the mbarrier at the same offset in each of them
 __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const void* tmap, int x, int y, uint32_t bar,
@@ -295,7 +302,14 @@ __device__ __forceinline__ void tma_load_3d_2cta(uint32_t dst, const void* tmap,
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(z), "r"(cluster_bar)
       : "memory");
 }
-
+__device__ __forceinline__ void tma_load_4d_2cta(uint32_t dst, const void* tmap, int x, int y, int z, int w,
+                                                 uint32_t cluster_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(z), "r"(w), "r"(cluster_bar)
+      : "memory");
+}
 
 // ---------------------------------------------------------------- one ring stage per asm block
 // The MMA warp's loop is instruction-bound: a ring stage has to be issued in less than the ~520 clk
@@ -380,6 +394,58 @@ __device__ __forceinline__ uint32_t umma_stage_ts(uint32_t d_tmem, uint32_t a_tm
   return ready;
 }
 
+// ---------------------------------------------------------------- kind::f16 (split-precision path)
+// fp32 operands travel as two fp16 planes (hi = fp16(x), lo = fp16(x - hi)); a product is three MMAs
+// (hi hi, hi lo, lo hi) into the same fp32 accumulator.  Same byte geometry as the TF32 path: a K step is
+// 16 elements = 32 bytes (descriptor + 2), an MN-major K step is 16 rows = 2048 bytes (descriptor + 128),
+// an A operand in tensor memory takes 8 columns per K step (two fp16 per 32-bit cell).
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (static_cast<uint32_t>(a_mn_major) << 15) | (static_cast<uint32_t>(b_mn_major) << 16) |
+         (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+// non-blocking probe of an mbarrier phase
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done;
+}
+#define GE2E_MMA_F16_SS(CGS) "tcgen05.mma.cta_group::" CGS ".kind::f16 [%0], a, b, %3, "
+#define GE2E_F16_SS4(CGS)                                                                           \
+  "{\n\t.reg .pred pa, pt;\n\t.reg .b64 a, b;\n\t"                                               \
+  "setp.ne.b32 pa, %4, 0;\n\tsetp.eq.b32 pt, %4, %4;\n\t"                                         \
+  "mov.b64 a, %1;\n\tmov.b64 b, %2;\n\t" GE2E_MMA_F16_SS(CGS) "pa;\n\t"                          \
+  "add.u64 a, a, 2;\n\tadd.u64 b, b, 2;\n\t" GE2E_MMA_F16_SS(CGS) "pt;\n\t"                      \
+  "add.u64 a, a, 2;\n\tadd.u64 b, b, 2;\n\t" GE2E_MMA_F16_SS(CGS) "pt;\n\t"                      \
+  "add.u64 a, a, 2;\n\tadd.u64 b, b, 2;\n\t" GE2E_MMA_F16_SS(CGS) "pt;\n\t}"
+// 4 MMAs over one [rows x 64 fp16] K-major slab pair (K = 64): D (+)= A_slab . B_slab^T
+template <int CG>
+__device__ __forceinline__ void umma_f16_ss4(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc,
+                                             uint32_t acc_first) {
+  if (CG == 1)
+    asm volatile(GE2E_F16_SS4("1") ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc_first) : "memory");
+  else
+    asm volatile(GE2E_F16_SS4("2") ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc_first) : "memory");
+}
+// 2 MMAs (32 k-rows): A from tensor memory (16 columns), B MN-major from shared memory
+#define GE2E_MMA_F16_TS(CGS) "tcgen05.mma.cta_group::" CGS ".kind::f16 [%0], [ta], b, %3, "
+#define GE2E_F16_TS2(CGS)                                                                           \
+  "{\n\t.reg .pred pa, pt;\n\t.reg .b64 b;\n\t.reg .b32 ta;\n\t"                                \
+  "setp.ne.b32 pa, %4, 0;\n\tsetp.eq.b32 pt, %4, %4;\n\t"                                         \
+  "mov.b32 ta, %1;\n\tmov.b64 b, %2;\n\t" GE2E_MMA_F16_TS(CGS) "pa;\n\t"                         \
+  "add.u32 ta, ta, 8;\n\tadd.u64 b, b, 128;\n\t" GE2E_MMA_F16_TS(CGS) "pt;\n\t}"
+template <int CG>
+__device__ __forceinline__ void umma_f16_ts2(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t idesc,
+                                             uint32_t acc_first) {
+  if (CG == 1)
+    asm volatile(GE2E_F16_TS2("1") ::"r"(d_tmem), "r"(a_tmem), "l"(db), "r"(idesc), "r"(acc_first) : "memory");
+  else
+    asm volatile(GE2E_F16_TS2("2") ::"r"(d_tmem), "r"(a_tmem), "l"(db), "r"(idesc), "r"(acc_first) : "memory");
+}
+
 // elect.sync with the leader's lane id (the same for every lane of the warp)
 __device__ __forceinline__ bool elect_leader(uint32_t& leader) {
   uint32_t pred;
@@ -412,6 +478,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
         "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
         "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }

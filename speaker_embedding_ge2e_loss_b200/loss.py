@@ -81,7 +81,8 @@ class GE2ELoss(nn.Module):
 
     def path_for(self, N: int, M: int, D: int) -> int:
         """Which kernels a batch of this shape runs on: 0 = SIMT fp32, 1 = tcgen05 TF32."""
-        return _lib.lib().ge2e_b200_path(N, N, M, D, _lib.VARIANTS[self.variant], _lib.PRECISIONS[self.precision])
+        v = _lib.VARIANTS[self.variant]
+        return _lib.lib().ge2e_b200_path(N, N, M, D, v, _lib.resolve_precision(self.precision, N, N, M, D, v))
 
     def extra_repr(self):
         return f"variant={self.variant}, precision={self.precision}, eps={self.eps}"

@@ -110,7 +110,7 @@ def _index_ok(row_index: Optional[Tensor], U: int, dev) -> Optional[Tensor]:
 def _tc_softmax(N: int, M: int, D: int, variant: int, precision: int) -> bool:
     """True where the softmax loss runs on tensor cores: the forward then also leaves the un-normalised
     dE_hat rows + row_scale (include/ge2e_b200.h, ge2e_b200_fwd_rows) and the backward is one pass."""
-    return variant == _lib.SOFTMAX and lib().ge2e_b200_path(N, N, M, D, variant, precision) == 1
+    return variant == _lib.SOFTMAX and lib().ge2e_b200_path(N, N, M, D, variant, precision) in (1, 2)
 
 
 def _fwd_impl(E: Tensor, w: Tensor, b: Tensor, eps: float, variant: int, precision: int, packed: bool,
@@ -307,7 +307,7 @@ class _EagerPlan:
         self.dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
         h = lib()
         self.path = h.ge2e_b200_path(N, N, M, D, variant, precision)
-        self.fused = variant == _lib.SOFTMAX and self.path == 1
+        self.fused = variant == _lib.SOFTMAX and self.path in (1, 2)
         self.ws_bytes = h.ge2e_b200_workspace_bytes(N, N, M, D, variant, precision)
         self.free = []
 
@@ -435,19 +435,21 @@ def ge2e_loss(E: Tensor, w: Tensor, b: Tensor, eps: float = 1e-6, variant: str =
             raise ValueError(f"with unperm the embeddings must be [N*M, D], got {tuple(E.shape)}")
         if speakers <= 0 or E.shape[0] % speakers != 0 or E.shape[0] // speakers < 2:
             raise ValueError("speakers must divide the number of rows, with M >= 2 utterances per speaker")
+        N, vcode = speakers, _lib.VARIANTS[variant]
+        pcode = _lib.resolve_precision(precision, N, N, E.shape[0] // N, E.shape[1], vcode)
         if torch.compiler.is_compiling():
-            N = speakers
-            return ge2e_fwd(E[unperm].reshape(N, E.shape[0] // N, E.shape[1]), w, b, float(eps),
-                            _lib.VARIANTS[variant], _lib.PRECISIONS[precision])[0]
+            return ge2e_fwd(E[unperm].reshape(N, E.shape[0] // N, E.shape[1]), w, b, float(eps), vcode, pcode)[0]
         idx = _index_ok(unperm, E.shape[0], E.device)
-        return _GE2EEager.apply(E, w, b, float(eps), _lib.VARIANTS[variant], _lib.PRECISIONS[precision], idx, speakers)
+        return _GE2EEager.apply(E, w, b, float(eps), vcode, pcode, idx, speakers)
     if E.dim() != 3:
         raise ValueError(f"embeddings must be [N, M, D], got {tuple(E.shape)}")
     if E.shape[1] < 2:
         raise ValueError("GE2E needs M >= 2 utterances per speaker (the reference divides by M - 1)")
+    vcode = _lib.VARIANTS[variant]
+    pcode = _lib.resolve_precision(precision, E.shape[0], E.shape[0], E.shape[1], E.shape[2], vcode)
     if torch.compiler.is_compiling():
-        return ge2e_fwd(E, w, b, float(eps), _lib.VARIANTS[variant], _lib.PRECISIONS[precision])[0]
-    return _GE2EEager.apply(E, w, b, float(eps), _lib.VARIANTS[variant], _lib.PRECISIONS[precision], None, 0)
+        return ge2e_fwd(E, w, b, float(eps), vcode, pcode)[0]
+    return _GE2EEager.apply(E, w, b, float(eps), vcode, pcode, None, 0)
 
 
 # --------------------------------------------------------------------------- staged (plain functions)

@@ -25,13 +25,15 @@ class GE2EPlan:
             raise ValueError("GE2E needs M >= 2 utterances per speaker")
         self.N, self.M, self.D = N, M, D
         self.variant = _lib.VARIANTS[variant]
-        self.precision = _lib.PRECISIONS[precision]
         self.eps = float(eps)
         self.device = torch.device(device if device is not None else "cuda")
         if self.device.type != "cuda":
             raise RuntimeError("speaker_embedding_ge2e_loss_b200 runs on CUDA (sm_100a) only; no CPU fallback")
+        with torch.cuda.device(self.device):
+            self.precision = _lib.resolve_precision(precision, N, N, M, D, self.variant)
         U, dev, f32 = N * M, self.device, torch.float32
-        self.path = lib().ge2e_b200_path(N, N, M, D, self.variant, self.precision)  # 0 SIMT, 1 tcgen05
+        # 0 SIMT fp32, 1 tcgen05 TF32, 2 tcgen05 split fp16 planes (fp32-class)
+        self.path = lib().ge2e_b200_path(N, N, M, D, self.variant, self.precision)
         self.e_hat = torch.empty((U, D), dtype=f32, device=dev)
         self.c_hat = torch.empty((N, D), dtype=f32, device=dev)
         self.cos_diag = torch.empty(U, dtype=f32, device=dev)
