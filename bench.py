@@ -16,7 +16,8 @@ One "step" = one GE2E forward + backward (grads to E, w, b) over one synthetic b
                 contractions) priced IN SITU: every CTA stamps %globaltimer at its start and end
                 (ge2e_b200_debug_stamps), max(end) - min(start) over the last step of a replay is the
                 kernel's duration inside the running graph; algorithmic flops 6 U N D.
-  fp32_path     cfg3 through the default precision of GE2ELoss(hp) ("fp32": SIMT FMA kernels), same timing.
+  fp32_path     cfg3 through the default precision of GE2ELoss(hp) ("fp32": fp32-class results; at this shape the
+                tensor cores with operands split into two fp16 planes), same timing; the SIMT FMA kernels beside it.
   cpu_baseline  the reference's own GE2ELoss (baseline/_ref, unmodified) where its O(N^2 M D) expansion fits
                 the host (cfg1, cfg2), else the torch-CPU port of it (oracle/ge2e_ref_port.py) on a bounded
                 row sample of the same batch; all host threads.
@@ -302,7 +303,7 @@ def stage_times(plan, E, w, b, flush_buf, reps=20):
     s = torch.cuda.current_stream().cuda_stream
     ws = plan._ws.data_ptr() if plan._ws_bytes else None
     acc = plan._accum.data_ptr()
-    scaled = plan.path == 1 and plan.variant == 0
+    scaled = plan.path in (1, 2) and plan.variant == 0
     calls = {
         "prep": lambda: h.ge2e_b200_prep(E.data_ptr(), N, M, D, plan.precision, plan.e_hat.data_ptr(),
                                          plan.c_hat.data_ptr(), plan.cos_diag.data_ptr(), acc, s),
@@ -555,8 +556,12 @@ def run_ours(args):
         extra["tf32_cublas_tflops_measured_here"] = tf32_peak
         step_us = ms_med * 1e3
         flops = 6.0 * U * N * D
-        kern_us = step_kernel_in_situ(plan, batches, w, b, max(10, args.steps), max(3, args.warmup)) if path == 1 else None
-        if kern_us is not None:
+        kern_us = step_kernel_in_situ(plan, batches, w, b, max(10, args.steps), max(3, args.warmup)) if path in (1, 2) else None
+        if kern_us is not None and path == 2:
+            dom, how = "tc_strip_kernel<STEP, split fp16 planes> (dE_hat pass + dC_hat pass; the rows were closed by the forward kernel before it)", \
+                "in situ: max(CTA end) - min(CTA start) of the kernel's %globaltimer stamps in the last step of a graph replay"
+            extra["step_us_outside_the_step_kernel"] = step_us - kern_us
+        elif kern_us is not None:
             dom, how = "tc_strip_kernel<STEP> (forward rows + dE_hat pass, grid barrier, dC_hat pass)", \
                 "in situ: max(CTA end) - min(CTA start) of the kernel's %globaltimer stamps in the last step of a graph replay"
             extra["step_us_outside_the_step_kernel"] = step_us - kern_us
@@ -571,6 +576,10 @@ def run_ours(args):
             # a < 0.1 ms step is a burst; the multi-millisecond cfg4 step runs under the power cap
             key = "bf16_tflops" if wl != "cfg4" else "bf16_tflops_sustained"
             peak, peak_note = peaks[key] / 2, f"MEASURED_PEAKS {key}/2 (TF32 runs at half the bf16 rate), {peaks['source']}"
+        elif path == 2:
+            key = "bf16_tflops" if wl != "cfg4" else "bf16_tflops_sustained"
+            peak, peak_note = peaks[key] / 3, (f"MEASURED_PEAKS {key}/3: an fp32-class product is three fp16 MMAs "
+                                               f"(hi.hi + hi.lo + lo.hi) at the bf16 rate, {peaks['source']}")
         else:
             peak, peak_note = 148 * 128 * 2 * 1.965e9 / 1e12, "nominal fp32 FMA 148 SM x 128 lanes x 2 x 1.965 GHz (SIMT path; no measured entry)"
         roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -579,9 +588,12 @@ def run_ours(args):
                     "traffic_note": "DRAM bytes per launch from the committed ncu --set full capture (cold L2), see "
                                     "profiles/ncu_traffic.json; operands are L2-resident in situ",
                     "kernel_us": kern_us, "kernel_us_how": how, "algorithmic_flops": flops,
-                    "issued_flops": 8.0 * U * N * D if path == 1 else None,
-                    "note": "algorithmic flops only (6 U N D: S, dE_hat, dC_hat); the second computation of S "
-                            "for the dC_hat pass (another 2 U N D) is not credited",
+                    "issued_flops": 8.0 * U * N * D if path == 1 else (8.0 * U * N * D * 3 if path == 2 else None),
+                    "note": ("algorithmic flops only (6 U N D: S, dE_hat, dC_hat); the second computation of S "
+                             "for the dC_hat pass (another 2 U N D) is not credited") if path != 2 else
+                            ("algorithmic flops only (6 U N D) against this ONE kernel, which issues 8 U N D x 3 fp16 MMAs; "
+                             "the forward kernel in front of it (S once more, 2 U N D x 3) is outside kernel_us and inside "
+                             "step_frac"),
                     "step_frac": (flops / (step_us * 1e-6) / 1e12) / peak}
 
         # ---- the default precision of the drop-in module on the same workload ----------------
@@ -590,15 +602,24 @@ def run_ours(args):
             k32 = max(3, min(args.steps, 10))
             ms32, rep32 = timed_back_to_back(plan32, batches, w, b, k32, 3, reps=3)
             fma_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+            names = {0: "simt-fp32", 1: "tcgen05-tf32", 2: "tcgen05 split fp16 planes (3 MMAs per product)"}
             extra["fp32_path"] = {"ms_per_step": ms32, "value": U / (ms32 * 1e-3), "unit": UNIT, "steps": k32,
-                                  "replays_ms": [round(x, 5) for x in rep32], "path": "simt-fp32",
+                                  "replays_ms": [round(x, 5) for x in rep32], "path": names[plan32.path],
+                                  "launches_per_step": 4 if plan32.path == 2 else None,
                                   "frac_vs_fp32_fma_roof": (flops / (ms32 * 1e-3) / 1e12) / fma_peak,
                                   "frac_vs_tf32_roof_div3": (flops / (ms32 * 1e-3) / 1e12) / (peaks["bf16_tflops"] / 2 / 3),
+                                  "frac_vs_f16_roof_div3": (flops / (ms32 * 1e-3) / 1e12) / (peaks["bf16_tflops"] / 3),
                                   "loss": float(plan32.loss.item()),
-                                  "note": "GE2ELoss(hp) defaults to precision='fp32' (reference arithmetic, 1e-5 parity): "
-                                          "this line; precision='tf32' (or hp.general.ge2e_precision) selects the "
-                                          "tensor-core path of the headline"}
+                                  "note": "GE2ELoss(hp) defaults to precision='fp32' (reference arithmetic, 1e-5 parity, "
+                                          "tests/test_gpu_split.py): this line.  At this shape it runs on the tensor cores with "
+                                          "every operand split into two fp16 planes (GE2E_FP32_SPLIT); precision='tf32' (or "
+                                          "hp.general.ge2e_precision) selects the TF32 path of the headline, 'fp32_simt' the "
+                                          "fp32 FMA kernels"}
             del plan32
+            plan_simt = GE2EPlan(N, M, D, args.variant, "fp32_simt", device=dev)
+            ms_s, _ = timed_back_to_back(plan_simt, batches, w, b, 3, 2, reps=3)
+            extra["fp32_path"]["simt_fp32_ms_per_step"] = ms_s
+            del plan_simt
     else:
         from speaker_embedding_ge2e_loss_b200.sharded import sharded_ge2e_loss
         off, n_local = shard_bounds(N, world, rank)
@@ -789,9 +810,11 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
-        "dtype": "tf32" if path == 1 else "f32", "data": "synthetic unit-norm random embeddings",
+        "dtype": "tf32" if path == 1 else ("f16x2-split (fp32-class)" if path == 2 else "f32"),
+        "data": "synthetic unit-norm random embeddings",
         "config": config_of(wl, N, M, D, args.variant),
-        "run": {"precision": args.precision, "path": "tcgen05-tf32" if path == 1 else "simt-fp32",
+        "run": {"precision": args.precision,
+                "path": {1: "tcgen05-tf32", 2: "tcgen05 split fp16 planes"}.get(path, "simt-fp32"),
                 "parallelism": "replica" if world == 1 else f"speakers sharded x{world} (all-gather c_hat, reduce-scatter dC_hat)",
                 "l2": (f"inputs larger than L2: the step rotates over {n_rot} batches ({n_rot * U * D * 4 / 1e6:.0f} MB), "
                        "no flush") if world == 1 else sharded_how,
@@ -843,7 +866,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32", "fp32_simt", "fp32_split"])
     ap.add_argument("--variant", default="softmax", choices=["softmax", "contrast"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

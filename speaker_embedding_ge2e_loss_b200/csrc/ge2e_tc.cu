@@ -225,6 +225,33 @@ struct Walk {
   }
 };
 
+// close_softmax_row (ge2e_common.cuh, reference s3:119-121) from LOG2-domain state: m2 >= every S_k log2e (the
+// running maximum, or the fixed shift), loff = sum_{k != j} exp2(S_k log2e - m2), xd2 = the diagonal logit formed
+// by the SAME affine map (w log2e, b log2e) as the off-diagonal ones -- the constant roundings of that map then
+// cancel in q = 1 - p_j, which a natural-domain diagonal term against a log2-domain sum would not (measured at
+// w = 30: -5e-6 relative in q).  Sd = the natural-domain diagonal logit for the large-q row loss.
+// lse2 = log-sum-exp in the log2 domain, z = sum_k exp2(S_k log2e - m2) + eps 2^-m2 (only where m2 > -115).
+struct RowClose { float stat, q, per, lse2, z; };
+__device__ __forceinline__ RowClose close_softmax_row_log2(float m2, float loff, float xd2, float Sd, float eps) {
+  RowClose r;
+  if (m2 > -115.f) {      // -80 log2e
+    const float em = eps * exp2f(-m2);
+    r.z = loff + exp2f(xd2 - m2) + em;
+    r.lse2 = m2 + log2f(r.z);
+    r.stat = r.lse2 * kLn2;
+    r.q = (loff + em) / r.z;
+  } else {                // every logit below -80: eps dominates
+    const float s = exp2f(m2);
+    const float Z = eps + (loff + exp2f(xd2 - m2)) * s;
+    r.stat = logf(Z);
+    r.lse2 = r.stat * kLog2e;
+    r.q = (eps + loff * s) / Z;
+    r.z = Z / s;
+  }
+  r.per = (r.q < 0.5f) ? -log1pf(-r.q) : r.stat - Sd;
+  return r;
+}
+
 // two fp32 values -> packed fp16 pair of their leading parts and of the remainders
 __device__ __forceinline__ void split_pack(float p0, float p1, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(p0, p1);
@@ -594,7 +621,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
     // sums and partial accumulators of different clusters simply add, nothing is ever rescaled.  The
     // smallest P is 2^(-2 |w| log2e), a normal fp32 number for |w| <= 43 (the reference's own exp(S) is
     // un-stabilised, s3:120, and overflows beyond w + b = 88).
-    const float m2 = b2 + fabsf(w2), mx = m2 * kLn2, c0 = -fabsf(w2);
+    const float m2 = b2 + fabsf(w2), c0 = -fabsf(w2);
     float dw_acc = 0.f, db_acc = 0.f, loss_acc = 0.f;
     int it = 0;
     // STEP: the rows are closed in this launch (TF32: pass 1 produces the row sums) or were closed by the
@@ -681,13 +708,14 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
         const float cdv = __ldg(p.cos_diag + r);
         float stat, q;
         if (close_here) {
-          float per;
-          close_softmax_row(mx, __ldcg(p.rowsum + r), fmaf(w, cdv + eps, b), eps, stat, q, per);   // s3:120-121
+          const RowClose rc = close_softmax_row_log2(m2, __ldcg(p.rowsum + r), fmaf(cdv, w2, b2),
+                                                     fmaf(w, cdv + eps, b), eps);      // s3:120-121
+          stat = rc.stat; q = rc.q;
           p.row_stat_out[r] = stat;
           p.row_aux_out[r] = q;
-          p.row_scale_out[r] = w * expf(mx - stat);
-          if (p.per_row_out != nullptr) p.per_row_out[r] = per;
-          loss_acc += per;
+          p.row_scale_out[r] = w / rc.z;      // = w exp(m - lse_r)
+          if (p.per_row_out != nullptr) p.per_row_out[r] = rc.per;
+          loss_acc += rc.per;
         } else {
           stat = __ldg(p.row_stat + r);
           q = __ldg(p.row_aux + r);
@@ -738,9 +766,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
       auto lse2_of = [&](bool valid, float raw, float cdv) -> float {
         if (!valid) return INFINITY;
         if (!close_here) return raw * kLog2e;
-        float stat, q, per;
-        close_softmax_row(mx, raw, fmaf(w, cdv + eps, b), eps, stat, q, per);
-        return stat * kLog2e;
+        return close_softmax_row_log2(m2, raw, fmaf(cdv, w2, b2), fmaf(w, cdv + eps, b), eps).lse2;
       };
       auto lse2_raw = [&](int ur, float& raw, float& cdv) -> bool {
         if (ur >= n_str) return false;
@@ -968,7 +994,8 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
             float per, stat, aux = 0.f;
             int ks = -1;
             if (VARIANT == GE2E_SOFTMAX) {
-              close_softmax_row(m2r * kLn2, lsum, Sd, eps, stat, aux, per);   // s3:120-121
+              const RowClose rc = close_softmax_row_log2(m2r, lsum, xd2, Sd, eps);   // s3:120-121
+              stat = rc.stat; aux = rc.q; per = rc.per;
             } else {
               per = 1.f - 1.f / (1.f + expf(-Sd));
               stat = best;

@@ -480,7 +480,7 @@ def fwd_rows(e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, 
     dev = e_hat.device
     U = n_local * M
     fused = (want_grad and variant == _lib.SOFTMAX and not sim
-             and lib().ge2e_b200_path(n_local, n_total, M, D, variant, precision) == 1)
+             and lib().ge2e_b200_path(n_local, n_total, M, D, variant, precision) in (1, 2))
     dE_hat = torch.empty((U, D), dtype=torch.float32, device=dev) if fused else None
     row_scale = torch.empty(U, dtype=torch.float32, device=dev) if fused else None
     row_stat = torch.empty(U, dtype=torch.float32, device=dev)
