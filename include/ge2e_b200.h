@@ -287,10 +287,21 @@ int ge2e_b200_gather_spans(const float* bank, const long long* src_off, int rows
 int ge2e_b200_embed_tail_fwd(const float* X, long long x_row_stride, const float* W, const float* bias, int U,
                              int H, int D, float* E, float* inv_norm, ge2e_stream_t stream);
 /* Backward of the normalisation and the bias: dY = (dE - E (E . dE)) * inv_norm (row-wise),
- * dbias[D] = column sums of dY (nullable; zeroed by the call).  The two gradient GEMMs of the Linear
- * (dX = dY W, dW = dY^T X) are plain library GEMMs and stay with the caller. */
+ * dbias[D] = column sums of dY (nullable; zeroed by the call). */
 int ge2e_b200_embed_tail_bwd_rows(const float* dE, const float* E, const float* inv_norm, int U, int D, float* dY,
                                   float* dbias, ge2e_stream_t stream);
+/* The two gradient GEMMs of the Linear layer (what autograd runs under s2_model_GE2E_loss_speach_embed.py:31),
+ * on tcgen05 with TF32 operands / fp32 accumulation like the forward:
+ *   dX[U, H] = dY[U, D] W[D, H]       rows dx_row_stride floats apart: the gradient of the last-frame select is
+ *                                     written straight into the last frame of a zeroed [U, frames, H] tensor
+ *   dW[D, H] = dY^T X[U, H]           X rows x_row_stride apart (as in the forward); the sum over U is split over
+ *                                     CTAs and added at the L2 (dW is zeroed by the call)
+ * dX or dW may be NULL (that product is skipped).  Needs H % 32 == 0, D in {64, 128, 256}, strides % 4 == 0,
+ * 16-byte aligned pointers: ..._supported() returns 1 where this holds, GE2E_ERR_UNSUPPORTED otherwise (the host
+ * layer then issues plain library GEMMs). */
+int ge2e_b200_embed_tail_bwd_gemms_supported(int U, int H, int D, long long x_row_stride, long long dx_row_stride);
+int ge2e_b200_embed_tail_bwd_gemms(const float* dY, const float* W, const float* X, long long x_row_stride, int U,
+                                   int H, int D, float* dX, long long dx_row_stride, float* dW, ge2e_stream_t stream);
 
 /* EER sweep counts (s5_eval_model.py:57-89: `S_thres = S > thres`,
  * `np.sum(S_thres[i])`, `np.sum(S_thres[i, :, i])` for 50 thresholds).  One pass over the float32

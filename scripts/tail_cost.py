@@ -64,6 +64,30 @@ for (U, frames, H, D) in [(640, 160, 768, 256), (10240, 1, 768, 256), (131072, 1
     res["roofline"] = {"tensor_TFLOPs": flops / t / 1e12, "tensor_peak": tf32, "tensor_frac": flops / t / 1e12 / tf32,
                        "hbm_GBps": nbytes / t / 1e9, "hbm_peak": hbm, "hbm_frac": nbytes / t / 1e9 / hbm,
                        "bound": "hbm" if nbytes / hbm / 1e9 > flops / tf32 / 1e12 else "tensor"}
+    # the two gradient GEMMs of the Linear layer (dX = dY W, dW = dY^T X): one tcgen05 kernel each vs library GEMMs
+    dY = torch.randn(U, D, device=dev)
+    dX = torch.empty(U, H, device=dev)
+    dW = torch.empty(D, H, device=dev)
+
+    def ours_gemms():
+        rc = h.ge2e_b200_embed_tail_bwd_gemms(dY.data_ptr(), W.data_ptr(), x.data_ptr(), x.stride(0), U, H, D,
+                                              dX.data_ptr(), H, dW.data_ptr(), st)
+        assert rc == 0, rc
+
+    def lib_gemms():
+        torch.matmul(dY, W, out=dX)
+        torch.matmul(dY.t(), x, out=dW)
+
+    res["ours_bwd_gemms_us"] = timed(ours_gemms)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    res["torch_fp32_bwd_gemms_us"] = timed(lib_gemms)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    res["torch_tf32_bwd_gemms_us"] = timed(lib_gemms)
+    gf = 4.0 * U * H * D
+    gb = 4.0 * (2 * U * D + 2 * D * H + 2 * U * H)
+    tg = res["ours_bwd_gemms_us"] * 1e-6
+    res["bwd_gemms_roofline"] = {"tensor_frac": gf / tg / 1e12 / tf32, "hbm_frac": gb / tg / 1e9 / hbm,
+                                 "bound": "hbm" if gb / hbm / 1e9 > gf / tf32 / 1e12 else "tensor"}
     # forward + backward through the public module vs the same three lines under autograd
     tail = pkg.ProjectionL2Norm(H, D).to(dev)
     dE = torch.randn(U, D, device=dev)

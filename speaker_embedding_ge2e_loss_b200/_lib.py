@@ -87,6 +87,9 @@ PROTOTYPES = {
     "ge2e_b200_embed_tail_fwd": (C.c_int, [_f32p, C.c_longlong, _f32p, _f32p, C.c_int, C.c_int, C.c_int, _f32p, _f32p,
                                            _stream]),
     "ge2e_b200_embed_tail_bwd_rows": (C.c_int, [_f32p, _f32p, _f32p, C.c_int, C.c_int, _f32p, _f32p, _stream]),
+    "ge2e_b200_embed_tail_bwd_gemms_supported": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_longlong]),
+    "ge2e_b200_embed_tail_bwd_gemms": (C.c_int, [_f32p, _f32p, _f32p, C.c_longlong, C.c_int, C.c_int, C.c_int,
+                                                 _f32p, C.c_longlong, _f32p, _stream]),
     "ge2e_b200_threshold_counts_scratch_bytes": (C.c_size_t, [C.c_int]),
     "ge2e_b200_threshold_counts": (C.c_int, [_f32p, C.c_int, C.c_int, _f32p, C.c_int, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_size_t, _stream]),

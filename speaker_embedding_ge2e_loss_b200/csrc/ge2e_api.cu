@@ -248,6 +248,17 @@ int ge2e_b200_embed_tail_bwd_rows(const float* dE, const float* E, const float* 
   return tail_bwd_rows(dE, E, inv_norm, U, D, dY, dbias, (cudaStream_t)stream);
 }
 
+int ge2e_b200_embed_tail_bwd_gemms_supported(int U, int H, int D, long long x_row_stride, long long dx_row_stride) {
+  return tail_bwd_gemms_supported(U, H, D, x_row_stride, dx_row_stride) ? 1 : 0;
+}
+
+int ge2e_b200_embed_tail_bwd_gemms(const float* dY, const float* W, const float* X, long long x_row_stride, int U,
+                                   int H, int D, float* dX, long long dx_row_stride, float* dW, ge2e_stream_t stream) {
+  if (U < 1 || H < 1 || D < 1) return GE2E_ERR_SHAPE;
+  if (!dY || (!dX && !dW) || (dX && !W) || (dW && !X)) return GE2E_ERR_ARGUMENT;
+  return tail_bwd_gemms(dY, W, X, x_row_stride, U, H, D, dX, dx_row_stride, dW, (cudaStream_t)stream);
+}
+
 size_t ge2e_b200_threshold_counts_scratch_bytes(int T) {
   return T < 1 ? 0 : (size_t)(2 * (T + 1) + 1) * sizeof(unsigned long long);
 }

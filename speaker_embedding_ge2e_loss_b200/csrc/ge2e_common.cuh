@@ -166,6 +166,10 @@ int tail_fwd(const float* X, long long x_row_stride, const float* W, const float
              float* E, float* inv_norm, cudaStream_t st);
 int tail_bwd_rows(const float* dE, const float* E, const float* inv_norm, int U, int D, float* dY, float* dbias,
                   cudaStream_t st);
+// gradient GEMMs of the Linear layer on tcgen05: dX = dY W (row stride dx_row_stride), dW = dY^T X; either may be null
+bool tail_bwd_gemms_supported(int U, int H, int D, long long x_row_stride, long long dx_row_stride);
+int tail_bwd_gemms(const float* dY, const float* W, const float* X, long long x_row_stride, int U, int H, int D,
+                   float* dX, long long dx_row_stride, float* dW, cudaStream_t st);
 
 // ---- launchers implemented in ge2e_tc.cu (tcgen05 / TMA / TMEM path) ----------------------
 bool tc_supported(int n_local, int n_total, int M, int D, int variant);

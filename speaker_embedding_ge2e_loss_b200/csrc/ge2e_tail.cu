@@ -12,10 +12,14 @@
 //   warp 0      TMA producer           warp 1      TMEM allocation + MMA issue (one elected lane)
 //   warps 2-5   epilogue, one thread per row of the tile (TMEM lane quarter = warp % 4)
 //
-// Backward of the normalisation (+ bias gradient) is a SIMT row kernel; the two gradient GEMMs
-// (dX = dY W, dW = dY^T X) are plain library GEMMs issued by the host layer.
+// Backward of the normalisation (+ bias gradient) is a SIMT row kernel; the two gradient GEMMs of the Linear
+// layer (dX = dY W, dW = dY^T X -- what autograd runs under s2:31) are one more tcgen05 kernel, tail_gemm_kernel:
+// C[128 x 256 tile] (+)= A B with B (and for dW also A) taken MN-major straight from the row-major tensors, K
+// streamed through a TMA ring, K split over CTAs for dW (partial tiles added at the L2 with TMA reduce-add).
 #include <cuda.h>
 #include <cudaTypedefs.h>
+
+#include <algorithm>
 
 #include "ge2e_common.cuh"
 #include "ge2e_tc_ptx.cuh"
@@ -246,7 +250,209 @@ embed_tail_bwd_rows_kernel(const float* __restrict__ dE, const float* __restrict
   }
 }
 
+// ---- gradient GEMMs of the Linear layer ---------------------------------------------------------
+//   dX[U x H] = dY[U x D] W[D x H]          A = dY rows, K-major (K = D);   B = W,  K x N row-major = MN-major
+//   dW[D x H] = dY^T[D x U] X[U x H]        A = dY,      K x M row-major = MN-major (K = U);  B = X, MN-major
+// One CTA per (128-row M tile, 256-column N tile, K range); TF32 operands, fp32 accumulation in 256 TMEM
+// columns; ring stage = 32 k: A 16 KB + B 32 KB.  MN-major TF32 operands use the 32-byte-atom 128B swizzle
+// (ge2e_tc_ptx.cuh): chunks of 32 columns 4096 B apart (LBO), groups of 4 k-rows 512 B apart (SBO), one MMA
+// (k = 8) consumes 1024 B.  warp 0 = TMA, warp 1 = MMA + TMEM, warps 2-5 = epilogue (a row each).
+constexpr int kGemmStages = 4;
+constexpr int kGemmK = 32;                        // k per ring stage
+constexpr int kGemmN = 256;
+constexpr int kGemmABytes = 128 * kGemmK * 4;     // 16 KB
+constexpr int kGemmBBytes = kGemmN * kGemmK * 4;  // 32 KB
+constexpr int kGemmStageBytes = kGemmABytes + kGemmBBytes;
+constexpr int kGemmSmemBytes = kGemmStages * kGemmStageBytes + 1024 + 256;
+
+struct GemmShared {
+  unsigned long long full[kGemmStages], empty[kGemmStages], acc_full;
+  uint32_t tmem_base;
+};
+
+struct GemmParams {
+  int k_total;       // K
+  int k_per_cta;     // multiple of kGemmK; blockIdx.z covers [z * k_per_cta, min(K, (z + 1) * k_per_cta))
+  int a_mn;          // A is MN-major (K x M row-major)
+  int reduce;        // add into C (K split) instead of storing
+  int n_slabs;       // 32-column slabs of C in this launch's N tiles that exist at all (for the last tile: clipped by TMA)
+};
+
+__global__ void __launch_bounds__(kTailThreads, 1)
+tail_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                 const __grid_constant__ CUtensorMap tm_c, const GemmParams p) {
+  extern __shared__ uint8_t gemm_raw[];
+  const uint32_t raw = smem_u32(gemm_raw);
+  const uint32_t ring = (raw + 1023u) & ~1023u;
+  GemmShared* sh = reinterpret_cast<GemmShared*>(gemm_raw + (ring - raw) + kGemmStages * kGemmStageBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * kGemmN, m0 = blockIdx.y * 128;
+  const int k0 = blockIdx.z * p.k_per_cta;
+  const int k1 = min(p.k_total, k0 + p.k_per_cta);
+  const int nst = (k1 - k0 + kGemmK - 1) / kGemmK;      // >= 1 by construction of the grid
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tm_a); prefetch_tmap(&tm_b); prefetch_tmap(&tm_c);
+    for (int s = 0; s < kGemmStages; ++s) {
+      mbar_init(smem_u32(&sh->full[s]), 1);
+      mbar_init(smem_u32(&sh->empty[s]), 1);
+    }
+    mbar_init(smem_u32(&sh->acc_full), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<256>(smem_u32(&sh->tmem_base));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sh->tmem_base;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int c = 0; c < nst; ++c) {
+        const int s = c % kGemmStages;
+        mbar_wait(smem_u32(&sh->empty[s]), ((c / kGemmStages) & 1) ^ 1);
+        const uint32_t fb = smem_u32(&sh->full[s]);
+        mbar_expect_tx(fb, kGemmStageBytes);          // out-of-range parts of a box are zero-filled and counted
+        const uint32_t sa = ring + s * kGemmStageBytes, sb = sa + kGemmABytes;
+        const int k = k0 + c * kGemmK;
+        if (p.a_mn) tma_load_3d(sa, &tm_a, 0, k, m0 / 32, fb);       // [4 chunks of 32 m][32 k][32]
+        else tma_load_2d(sa, &tm_a, k, m0, fb);                      // [128 m][32 k]
+        tma_load_3d(sb, &tm_b, 0, k, n0 / 32, fb);                   // [8 chunks of 32 n][32 k][32]
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    const uint32_t idesc = idesc_tf32(128, kGemmN, p.a_mn, 1);
+    const uint64_t dk = smem_desc(0, 16, 1024, kLayoutSw128);
+    const uint64_t dmn = smem_desc(0, kGemmK * 128, 512, kLayoutSw128Base32);
+    const uint64_t da0 = p.a_mn ? dmn : dk;
+    const uint32_t a_step = p.a_mn ? 64u : 2u;          // descriptor units (16 B) per k = 8
+    for (int c = 0; c < nst; ++c) {
+      const int s = c % kGemmStages;
+      mbar_wait(smem_u32(&sh->full[s]), (c / kGemmStages) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = ring + s * kGemmStageBytes, sb = sa + kGemmABytes;
+        uint64_t da = da0 | (sa >> 4), db = dmn | (sb >> 4);
+#pragma unroll
+        for (int j = 0; j < kGemmK / 8; ++j) {
+          umma_tf32_ss(tmem, da, db, idesc, (c | j) != 0);
+          da += a_step; db += 64;
+        }
+        umma_commit(smem_u32(&sh->empty[s]));
+      }
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(smem_u32(&sh->acc_full));
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int trow = q * 32 + lane;
+    const int et = threadIdx.x - 64;
+    mbar_wait(smem_u32(&sh->acc_full), 0);
+    tc_fence_after();
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    // every MMA has completed, so every load has landed and been consumed: the ring is free to stage C
+    for (int ch = 0; ch < p.n_slabs; ++ch) {
+      uint32_t v[32];
+      tmem_ld32(tmem + lane_addr + ch * 32, v);
+      tmem_ld_wait();
+      const uint32_t row_smem = ring + ch * kTailABytes + trow * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_smem + ((c ^ (trow & 7)) << 4)),
+                     "r"(v[4 * c]), "r"(v[4 * c + 1]), "r"(v[4 * c + 2]), "r"(v[4 * c + 3])
+                     : "memory");
+    }
+    tc_fence_before();
+    fence_proxy_async_smem();
+    named_bar_sync(1, kTailEpiThreads);
+    if (et == 0) {
+      for (int ch = 0; ch < p.n_slabs; ++ch) {          // rows / columns past the end of C are clipped
+        if (p.reduce) tma_reduce_add_2d(&tm_c, n0 + ch * 32, m0, ring + ch * kTailABytes);
+        else tma_store_2d(&tm_c, n0 + ch * 32, m0, ring + ch * kTailABytes);
+      }
+      tma_store_commit();
+      tma_store_wait_read();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem);
+}
+
+// [rows, cols] fp32 with a row stride, viewed as [cols / 32][rows][32]: box = [box_chunks][32 rows][32 cols],
+// 32-byte-atom 128B swizzle -- an MN-major TF32 operand block of 32 k-rows (cols % 32 == 0)
+int tail_map_mn(CUtensorMap* m, const float* base, long long rows, int cols, long long row_stride, int box_chunks) {
+  auto enc = tail_encode();
+  if (enc == nullptr) return GE2E_ERR_LAUNCH;
+  cuuint64_t dims[3] = {32, static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(cols / 32)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(row_stride) * 4, 128};
+  cuuint32_t box[3] = {32, kGemmK, static_cast<cuuint32_t>(box_chunks)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? GE2E_OK : GE2E_ERR_LAUNCH;
+}
+
+int launch_tail_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, int m_tiles,
+                     int n_tiles, int k_splits, cudaStream_t st) {
+  static thread_local int attr_dev = -1;
+  int dev = 0;
+  GE2E_CUDA_TRY(cudaGetDevice(&dev));
+  if (attr_dev != dev) {
+    GE2E_CUDA_TRY(cudaFuncSetAttribute(tail_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+    attr_dev = dev;
+  }
+  tail_gemm_kernel<<<dim3(n_tiles, m_tiles, k_splits), kTailThreads, kGemmSmemBytes, st>>>(ta, tb, tc, p);
+  GE2E_LAUNCHED();
+  return GE2E_OK;
+}
+
 }  // namespace
+
+bool tail_bwd_gemms_supported(int U, int H, int D, long long x_row_stride, long long dx_row_stride) {
+  return U > 0 && H >= 32 && H % 32 == 0 && (D == 64 || D == 128 || D == 256) && x_row_stride >= H &&
+         x_row_stride % 4 == 0 && dx_row_stride >= H && dx_row_stride % 4 == 0;
+}
+
+int tail_bwd_gemms(const float* dY, const float* W, const float* X, long long x_row_stride, int U, int H, int D,
+                   float* dX, long long dx_row_stride, float* dW, cudaStream_t st) {
+  if (!tail_bwd_gemms_supported(U, H, D, x_row_stride, dx_row_stride)) return GE2E_ERR_UNSUPPORTED;
+  const int n_tiles = (H + kGemmN - 1) / kGemmN;
+  const int n_slabs = std::min(kGemmN, H) / 32;     // H < 256: fewer slabs; a clipped last tile stores nothing past H
+  int rc;
+  if (dX != nullptr) {
+    if ((reinterpret_cast<uintptr_t>(dY) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(dX)) & 15)
+      return GE2E_ERR_UNSUPPORTED;
+    CUtensorMap ta, tb, tc;
+    if ((rc = tail_map(&ta, dY, U, D, D, 128)) != GE2E_OK) return rc;                   // K-major A: [128 m][32 k]
+    if ((rc = tail_map_mn(&tb, W, D, H, H, kGemmN / 32)) != GE2E_OK) return rc;         // W[k = d][n = h]
+    if ((rc = tail_map(&tc, dX, U, H, dx_row_stride, 128)) != GE2E_OK) return rc;
+    GemmParams p{D, D, 0, 0, n_slabs};
+    if ((rc = launch_tail_gemm(ta, tb, tc, p, (U + 127) / 128, n_tiles, 1, st)) != GE2E_OK) return rc;
+  }
+  if (dW != nullptr) {
+    if (X == nullptr) return GE2E_ERR_ARGUMENT;
+    if ((reinterpret_cast<uintptr_t>(dY) | reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(dW)) & 15)
+      return GE2E_ERR_UNSUPPORTED;
+    CUtensorMap ta, tb, tc;
+    if ((rc = tail_map_mn(&ta, dY, U, D, D, 4)) != GE2E_OK) return rc;                   // dY[k = u][m = d]
+    if ((rc = tail_map_mn(&tb, X, U, H, x_row_stride, kGemmN / 32)) != GE2E_OK) return rc;   // X[k = u][n = h]
+    if ((rc = tail_map(&tc, dW, D, H, H, 128)) != GE2E_OK) return rc;
+    const int m_tiles = (D + 127) / 128;
+    // K = U split so that the grid covers the SMs about once; a split is a whole number of ring stages
+    const int stages = (U + kGemmK - 1) / kGemmK;
+    int want = std::max(1, 148 / (m_tiles * n_tiles));
+    int per = (stages + want - 1) / want;                       // stages per CTA
+    const int splits = (stages + per - 1) / per;
+    GemmParams p{U, per * kGemmK, 1, splits > 1 ? 1 : 0, n_slabs};
+    if (splits > 1) GE2E_CUDA_TRY(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)D * H, st));
+    if ((rc = launch_tail_gemm(ta, tb, tc, p, m_tiles, n_tiles, splits, st)) != GE2E_OK) return rc;
+  }
+  return GE2E_OK;
+}
 
 bool tail_supported(int U, int H, int D, long long x_row_stride) {
   return U > 0 && H > 0 && H % 4 == 0 && (D == 64 || D == 128 || D == 256) && x_row_stride >= H &&

@@ -6,7 +6,10 @@ the row norm.  ``ProjectionL2Norm`` holds the same ``projection`` sub-module (st
 ``projection.weight`` / ``projection.bias``, so the reference's checkpoints load) and runs the three
 lines as ONE tcgen05 kernel (``ge2e_b200_embed_tail_fwd``): the last-frame select is the row stride
 of the TMA tensor map, the normalisation is the GEMM's epilogue, and the un-normalised projection
-never reaches HBM.  TF32 tensor cores, fp32 accumulation.  CUDA (sm_100a) only; no fallback.
+never reaches HBM.  TF32 tensor cores, fp32 accumulation.  CUDA (sm_100a) only; no fallback.  The backward is
+the row Jacobian of the normalisation (``ge2e_b200_embed_tail_bwd_rows``) followed by the two gradient GEMMs of
+the Linear layer, dX = dY W and dW = dY^T X, as one more tcgen05 kernel (``ge2e_b200_embed_tail_bwd_gemms``; hidden
+sizes that are not a multiple of 32 take library GEMMs instead).
 
     tail = ProjectionL2Norm(768, 256).to("cuda")
     out, _ = lstm(mel)                      # [U, frames, 768]
@@ -69,15 +72,27 @@ class _ProjectNormalize(torch.autograd.Function):
                                                                 None if dbias is None else dbias.data_ptr(),
                                                                 ops._stream()), "ge2e_b200_embed_tail_bwd_rows")
         dX = dW = None
-        if ctx.needs_input_grad[0]:
-            dx_last = dY @ w                                        # library GEMM
-            if len(ctx.x_shape) == 3:                               # gradient of the last-frame select
-                dX = torch.zeros(ctx.x_shape, dtype=torch.float32, device=E.device)
-                dX[:, ctx.x_shape[1] - 1] = dx_last
-            else:
-                dX = dx_last
-        if ctx.needs_input_grad[1]:
-            dW = dY.t() @ xv                                        # library GEMM
+        H = xv.shape[1]
+        want_x, want_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if want_x:                                                  # gradient of the last-frame select: zeros elsewhere
+            dX = (torch.zeros if len(ctx.x_shape) == 3 else torch.empty)(ctx.x_shape, dtype=torch.float32, device=E.device)
+            dx_last = dX[:, ctx.x_shape[1] - 1] if len(ctx.x_shape) == 3 else dX
+        if want_w:
+            dW = torch.empty((D, H), dtype=torch.float32, device=E.device)
+        h = _lib.lib()
+        dxs = dx_last.stride(0) if want_x else H
+        if (want_x or want_w) and h.ge2e_b200_embed_tail_bwd_gemms_supported(U, H, D, xv.stride(0), dxs) == 1:
+            # dX = dY W and dW = dY^T X on tcgen05 (dX lands in the last frame through the row stride)
+            with torch.cuda.device(E.device):
+                _lib.check(h.ge2e_b200_embed_tail_bwd_gemms(dY.data_ptr(), w.data_ptr(), xv.data_ptr(), xv.stride(0), U, H, D,
+                                                            dx_last.data_ptr() if want_x else None, dxs,
+                                                            dW.data_ptr() if want_w else None, ops._stream()),
+                           "ge2e_b200_embed_tail_bwd_gemms")
+        else:                                                       # H % 32 != 0: plain library GEMMs
+            if want_x:
+                dx_last.copy_(dY @ w)
+            if want_w:
+                torch.matmul(dY.t(), xv, out=dW)
         return dX, dW, dbias
 
 

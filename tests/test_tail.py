@@ -120,6 +120,28 @@ def test_gpu_module_matches_reference_lines_and_loads_state_dict():
 
 
 @pytest.mark.gpu
+def test_gpu_backward_gemms_run_on_our_kernels():
+    """dX = dY W and dW = dY^T X are launches of this library (tcgen05 kernel), not library GEMMs, wherever the
+    hidden size is a multiple of 32 (the reference's 768): forward 1 launch, backward 3 (rows, dX, dW)."""
+    import speaker_embedding_ge2e_loss_b200 as pkg
+    dev = torch.device("cuda:0")
+    h = pkg.lib()
+    assert h.ge2e_b200_embed_tail_bwd_gemms_supported(10240, 768, 256, 768, 768) == 1
+    assert h.ge2e_b200_embed_tail_bwd_gemms_supported(640, 768, 256, 160 * 768, 160 * 768) == 1     # last-frame strides
+    assert h.ge2e_b200_embed_tail_bwd_gemms_supported(100, 36, 64, 36, 36) == 0
+    tail = pkg.ProjectionL2Norm(768, 256).to(dev)
+    out = torch.randn(300, 3, 768, device=dev, requires_grad=True)
+    n0 = h.ge2e_b200_launch_count()
+    E = tail(out)
+    n1 = h.ge2e_b200_launch_count()
+    E.sum().backward()
+    torch.cuda.synchronize()
+    n2 = h.ge2e_b200_launch_count()
+    assert n1 - n0 == 1 and n2 - n1 == 3, (n1 - n0, n2 - n1)
+    assert float(out.grad[:, :-1].abs().max()) == 0.0 and float(out.grad[:, -1].abs().max()) > 0
+
+
+@pytest.mark.gpu
 def test_gpu_unsupported_shapes_raise():
     import speaker_embedding_ge2e_loss_b200 as pkg
     dev = torch.device("cuda:0")
