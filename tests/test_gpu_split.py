@@ -115,7 +115,7 @@ def test_split_scalars(pkg, w, b, g):
     assert abs(got["loss"] - ref["loss"]) <= FP32_TOL * max(1.0, abs(ref["loss"]))
     # At w = 30 every rounding of a cosine is worth 43 in the exponent and the gradient is what is left of a
     # cancellation (confident rows): measured here 9.5e-6 for this path against 1.3e-6 for the SIMT fp32 kernels
-    # (a -3e-6 relative bias of the off-diagonal mass q, see DESIGN.md 3.5) -- 2e-5 is the bar at this scale,
+    # (a -3e-6 relative bias of the off-diagonal mass q, see DESIGN.md 3.4) -- 2e-5 is the bar at this scale,
     # 1e-5 everywhere else (w = 10 is the reference's initial value: 8e-7 against 6e-7).
     tol = FP32_TOL if abs(w) <= 10.0 else 2 * FP32_TOL
     assert trel(simt["dE"].reshape(-1), ref["dE"].reshape(-1)) <= FP32_TOL
