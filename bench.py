@@ -700,8 +700,9 @@ def run_ours(args):
             sharded_how = (f"K steps incl. the exchange steps ({exchange}) in one CUDA graph, shard rotating over {n_rot} "
                            f"batches ({n_rot * n_local * M * D * 4 / 1e6:.0f} MB), one event pair, max over ranks")
         launches = int(lib().ge2e_b200_launch_count() - launches_before)
-        path = lib().ge2e_b200_path(n_local, N, M, D, 0 if args.variant == "softmax" else 1,
-                                    1 if args.precision == "tf32" else 0)
+        from speaker_embedding_ge2e_loss_b200 import _lib as _l
+        vcode = 0 if args.variant == "softmax" else 1
+        path = lib().ge2e_b200_path(n_local, N, M, D, vcode, _l.resolve_precision(args.precision, n_local, N, M, D, vcode))
         loss_val = step().item()
         e2e = None
         roofline = None
@@ -776,11 +777,14 @@ def run_ours(args):
                        "warmup_steps": fed_warm, "last_result": fedd["last_result"], "module_api_eager": eager}
             else:
                 e2e["host_fed_plan"] = fedd
-        peak = peaks["bf16_tflops_sustained"] / 2 if path == 1 else 148 * 128 * 2 * 1.965e9 / 1e12   # long steps: sustained
+        # long steps: sustained rates.  TF32 = half the bf16 rate; an fp32-class product = three fp16 MMAs
+        peak = (peaks["bf16_tflops_sustained"] / 2 if path == 1 else
+                peaks["bf16_tflops_sustained"] / 3 if path == 2 else 148 * 128 * 2 * 1.965e9 / 1e12)
         ach = 6.0 * U * N * D / (ms[0] * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": "whole sharded step, all ranks", "achieved": ach,
                     "peak": peak * world, "unit": "TFLOP/s", "frac": ach / (peak * world), "traffic": None,
-                    "peak_source": "MEASURED_PEAKS bf16_tflops_sustained/2 per GPU (millisecond-long steps run under the power cap)"}
+                    "peak_source": "MEASURED_PEAKS bf16_tflops_sustained / 2 (TF32) or / 3 (split fp16 planes) per GPU "
+                                   "(millisecond-long steps run under the power cap)"}
         if rank == 0:
             # 1-GPU denominator for strong scaling: the same cfg on this rank's GPU alone
             E1 = E_full.to(dev)

@@ -52,7 +52,8 @@ enum ge2e_variant { GE2E_SOFTMAX = 0, GE2E_CONTRAST = 1 }; /* paper eq. (6) / eq
  *            un-stabilised exp(S), s3:120, overflows beyond w + b = 88). */
 /* GE2E_FP32_SPLIT: fp32-class accuracy on the tensor cores (reference arithmetic is fp32, s3:57,70).  Every
  *            operand travels as two fp16 planes hi = fp16(x), lo = fp16(x - hi) -- e_hat / c_hat then hold
- *            [2][rows][D] halves in the same bytes as [rows][D] floats -- and every product is the three
+ *            [rows][2][D] halves in the same bytes as [rows][D] floats (a row's hi plane, then its lo plane: whatever
+ *            moves rows -- the all-gather of c_hat, a peer publish -- moves both) -- and every product is the three
  *            kind::f16 MMAs hi.hi + hi.lo + lo.hi with fp32 accumulation (error ~2^-22 per term).  The
  *            softmax probabilities are normalised by a forward launch before the step kernel cuts them into
  *            planes.  Softmax variant, D = 128 or 256, shapes of the tensor-core path only; unlike GE2E_TF32

@@ -21,10 +21,10 @@ PRECISIONS = {"fp32": FP32, "tf32": TF32, "fp32_simt": FP32, "fp32_split": FP32_
 
 def resolve_precision(name: str, n_local: int, n_total: int, M: int, D: int, variant: int) -> int:
     """Precision code handed to the C ABI for a (shape, variant): "fp32" picks GE2E_FP32_SPLIT where
-    ge2e_b200_path() covers it (single-device calls only: the planes do not travel through the collectives)."""
+    ge2e_b200_path() covers it (speaker shards included: a centroid row carries both of its planes)."""
     if name not in PRECISIONS:
         raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
-    if name == "fp32" and n_local == n_total and lib().ge2e_b200_path(n_local, n_total, M, D, variant, FP32_SPLIT) == 2:
+    if name == "fp32" and lib().ge2e_b200_path(n_local, n_total, M, D, variant, FP32_SPLIT) == 2:
         return FP32_SPLIT
     return PRECISIONS[name]
 

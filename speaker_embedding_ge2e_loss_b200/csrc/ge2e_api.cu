@@ -396,7 +396,6 @@ int ge2e_b200_step_rows_peers(const float* e_hat, const float* c_hat_all, const 
                               int precision, const float* grad_out, float* row_stat, int32_t* row_kstar, float* row_aux,
                               float* row_scale, float* accum, float* dE_hat, float* const* dC_owner_host, int n_ranks,
                               void* workspace, size_t workspace_bytes, ge2e_stream_t stream) {
-  (void)row_kstar;
   if (!e_hat || !c_hat_all || !cos_diag || !w || !b || !grad_out || !row_stat || !row_aux || !row_scale || !accum ||
       !dE_hat || !dC_owner_host)
     return GE2E_ERR_ARGUMENT;
@@ -405,8 +404,15 @@ int ge2e_b200_step_rows_peers(const float* e_hat, const float* c_hat_all, const 
   if ((rc = check_enum(variant, precision)) != GE2E_OK) return rc;
   if (n_ranks < 2 || n_ranks > GE2E_MAX_PEERS || n_local * n_ranks != n_total) return GE2E_ERR_SHAPE;
   // only the tensor-core softmax step flushes through peer memory; everything else keeps the reduce-scatter
-  if (precision != GE2E_TF32 || !tc_softmax_step(n_local, n_total, M, D, variant, precision)) return GE2E_ERR_UNSUPPORTED;
+  if (!tc_softmax_step(n_local, n_total, M, D, variant, precision)) return GE2E_ERR_UNSUPPORTED;
   RowsArgs a{e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, b, eps, variant};
+  if (precision == GE2E_FP32_SPLIT) {
+    rc = tc_fwd_rows(a, row_stat, row_kstar, row_aux, accum, nullptr, workspace, workspace_bytes, true,
+                     (cudaStream_t)stream, true);
+    if (rc != GE2E_OK) return rc;
+    return tc_step(a, 3, grad_out, row_stat, row_aux, nullptr, nullptr, row_scale, nullptr, nullptr, dE_hat, nullptr,
+                   accum + 1, workspace, workspace_bytes, (cudaStream_t)stream, dC_owner_host, n_ranks, true);
+  }
   return tc_step(a, 3, grad_out, nullptr, nullptr, row_stat, row_aux, row_scale, accum, nullptr, dE_hat, nullptr,
                  accum + 1, workspace, workspace_bytes, (cudaStream_t)stream, dC_owner_host, n_ranks);
 }

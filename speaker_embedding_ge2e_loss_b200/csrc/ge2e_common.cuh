@@ -125,7 +125,7 @@ struct RowsArgs {
 };
 
 // row_index (nullable): logical row r = [speaker][utterance] lives at physical row row_index[r] of E / dE
-// prec: 0 = fp32 operands as they are, 1 = rounded to TF32, 2 = two fp16 planes [2][rows][D] (hi, lo) in the
+// prec: 0 = fp32 operands as they are, 1 = rounded to TF32, 2 = two fp16 planes [rows][2][D] (hi, lo) in the
 // same allocation (D = 128 / 256 / 512 only)
 int simt_prep(const float* E, const int32_t* row_index, int n_local, int M, int D, int prec, float* e_hat,
               float* c_hat_local, float* cos_diag, float* accum, cudaStream_t st);

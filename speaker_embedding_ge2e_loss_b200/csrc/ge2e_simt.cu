@@ -178,10 +178,11 @@ prep_kernel(const float* __restrict__ E, const int32_t* __restrict__ idx, int M,
 // Requires D = 128 KCH, 16-byte aligned rows.  grid = ceil(n_local / 4), block = 128.
 // ------------------------------------------------------------------------------------------
 // Operand precision of the normalised rows (PREC): 0 = fp32 as they are, 1 = rounded to TF32, 2 = two fp16 planes
-// hi = fp16(x), lo = fp16(x - hi) laid out [2][rows][D] in the same allocation (the tensor-core path's fp32-class
+// hi = fp16(x), lo = fp16(x - hi), laid out [rows][2][D] -- a row's hi plane then its lo plane in the bytes of the
+// fp32 row, so whatever moves rows (all-gather, peer publish) moves both planes (the tensor-core path's fp32-class
 // mode: hi.hi + hi.lo + lo.hi reproduces the fp32 product to ~2^-22).  put4 stores columns [col, col + 4) of `row`.
 template <int PREC>
-__device__ __forceinline__ void put4(float* base, size_t row, int D, int col, size_t plane_elems, float4 v) {
+__device__ __forceinline__ void put4(float* base, size_t row, int D, int col, float4 v) {
   if (PREC == 2) {
     __half* h = reinterpret_cast<__half*>(base);
     const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
@@ -190,8 +191,8 @@ __device__ __forceinline__ void put4(float* base, size_t row, int D, int col, si
     uint2 hi, lo;
     hi.x = *reinterpret_cast<const uint32_t*>(&h0); hi.y = *reinterpret_cast<const uint32_t*>(&h1);
     lo.x = *reinterpret_cast<const uint32_t*>(&l0); lo.y = *reinterpret_cast<const uint32_t*>(&l1);
-    *reinterpret_cast<uint2*>(h + row * D + col) = hi;
-    *reinterpret_cast<uint2*>(h + plane_elems + row * D + col) = lo;
+    *reinterpret_cast<uint2*>(h + row * 2 * D + col) = hi;
+    *reinterpret_cast<uint2*>(h + row * 2 * D + D + col) = lo;
   } else {
     if (PREC == 1) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
     *reinterpret_cast<float4*>(base + row * D + col) = v;
@@ -243,7 +244,7 @@ prep_warp_kernel(const float* __restrict__ E, const int32_t* __restrict__ idx, i
   const float sc = inv_m / fmaxf(sqrtf(ss) * inv_m, kCosDelta);
 #pragma unroll
   for (int c = 0; c < KCH; ++c)
-    put4<PREC>(c_hat, j, D, 4 * lane + 128 * c, (size_t)n_local * D,
+    put4<PREC>(c_hat, j, D, 4 * lane + 128 * c,
                make_float4(s[c].x * sc, s[c].y * sc, s[c].z * sc, s[c].w * sc));
   // rows: |e|, |u| and e.u with u = (s - e) / (M - 1)   (s3:105-111, s3:57)
   float my_cos = 0.f;
@@ -283,7 +284,7 @@ prep_warp_kernel(const float* __restrict__ E, const int32_t* __restrict__ idx, i
         for (int c = 0; c < KCH; ++c) {
           float4 e = v[r][c];
           e.x *= inv_ne; e.y *= inv_ne; e.z *= inv_ne; e.w *= inv_ne;
-          put4<PREC>(e_hat, (size_t)j * M + i0 + r, D, 4 * lane + 128 * c, (size_t)n_local * M * D, e);
+          put4<PREC>(e_hat, (size_t)j * M + i0 + r, D, 4 * lane + 128 * c, e);
         }
       }
     }
@@ -355,7 +356,7 @@ prep_reg_kernel(const float* __restrict__ E, const int32_t* __restrict__ idx, in
   const float sc = inv_m / fmaxf(sqrtf(ss) * inv_m, kCosDelta);       // s3:37 + normalisation
 #pragma unroll
   for (int c = 0; c < KCH; ++c)
-    put4<PREC>(c_hat, j, D, 4 * lane + 128 * c, (size_t)n_local * D,
+    put4<PREC>(c_hat, j, D, 4 * lane + 128 * c,
                make_float4(s[c].x * sc, s[c].y * sc, s[c].z * sc, s[c].w * sc));
   // |e|^2, |s - e|^2, e.(s - e) of every row (u = (s - e) / (M - 1): s3:105-111)
   float ne2[16], nd2[16], ed[16];
@@ -385,7 +386,7 @@ prep_reg_kernel(const float* __restrict__ E, const int32_t* __restrict__ idx, in
       for (int c = 0; c < KCH; ++c) {
         float4 e = v[i][c];
         e.x *= k; e.y *= k; e.z *= k; e.w *= k;
-        put4<PREC>(e_hat, (size_t)j * M + i, D, 4 * lane + 128 * c, (size_t)n_local * M * D, e);
+        put4<PREC>(e_hat, (size_t)j * M + i, D, 4 * lane + 128 * c, e);
       }
     }
   }

@@ -1208,7 +1208,7 @@ int make_map_3d(CUtensorMap* m, const float* base, int rows, int D, int box_slab
   return r == CUDA_SUCCESS ? GE2E_OK : GE2E_ERR_LAUNCH;
 }
 
-// SPLIT operands: X as two fp16 planes [2][rows][D] (hi, lo).
+// SPLIT operands: X as fp16 planes [rows][2][D] (a row's hi plane, then its lo plane, in the bytes of the fp32 row).
 // 3-D map {D, rows, plane}: box = [1][box_rows][64 cols] = one K-major slab of one plane, 128-byte swizzle.
 int make_map_h3(CUtensorMap* m, const void* base, int rows, int D, int box_rows) {
   const MapKey key{base, rows, D, box_rows, 13};
@@ -1216,7 +1216,7 @@ int make_map_h3(CUtensorMap* m, const void* base, int rows, int D, int box_rows)
   auto enc = get_encode();
   if (enc == nullptr) return GE2E_ERR_LAUNCH;
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(rows), 2};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(D) * 2, static_cast<cuuint64_t>(rows) * D * 2};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(D) * 4, static_cast<cuuint64_t>(D) * 2};
   cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
@@ -1233,7 +1233,7 @@ int make_map_h4(CUtensorMap* m, const void* base, int rows, int D, int box_chunk
   auto enc = get_encode();
   if (enc == nullptr) return GE2E_ERR_LAUNCH;
   cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(D / 64), 2};
-  cuuint64_t strides[3] = {static_cast<cuuint64_t>(D) * 2, 128, static_cast<cuuint64_t>(rows) * D * 2};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(D) * 4, 128, static_cast<cuuint64_t>(D) * 2};
   cuuint32_t box[4] = {64, kMma2Rows, static_cast<cuuint32_t>(box_chunks), 2};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
@@ -1553,7 +1553,7 @@ int tc_step(const RowsArgs& a, int phases, const float* grad_out, const float* r
   const int U = a.n_local * a.M;
   const bool peers = dC_owner != nullptr && n_ranks > 1;
   // SPLIT: the rows were closed by tc_fwd_rows(split) -- pass 1 and pass 2 both read row_stat_in / row_aux_in
-  if (split && (!tc_split_supported(a.n_local, a.n_total, a.M, a.D, a.variant) || peers || row_stat_in == nullptr ||
+  if (split && (!tc_split_supported(a.n_local, a.n_total, a.M, a.D, a.variant) || row_stat_in == nullptr ||
                 row_aux_in == nullptr))
     return GE2E_ERR_UNSUPPORTED;
   if (peers && (n_ranks > kMaxPeers || a.n_total % n_ranks != 0 || (a.n_total / n_ranks) % kTile != 0 ||

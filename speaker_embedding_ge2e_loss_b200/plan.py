@@ -127,9 +127,10 @@ class ShardedGE2EPlan:
         self.group = group if group is not None else dist.group.WORLD
         self.n_local, self.n_total, self.spk_offset, self.M, self.D = n_local, n_total, spk_offset, M, D
         self.variant = _lib.VARIANTS[variant]
-        self.precision = _lib.PRECISIONS[precision]
         self.eps = float(eps)
         self.device = torch.device(device if device is not None else "cuda")
+        with torch.cuda.device(self.device):
+            self.precision = _lib.resolve_precision(precision, n_local, n_total, M, D, self.variant)
         U, dev, f32 = n_local * M, self.device, torch.float32
         self.e_hat = torch.empty((U, D), dtype=f32, device=dev)
         self.c_hat_all = torch.empty((n_total, D), dtype=f32, device=dev)      # (replaced below in peer-memory mode)
@@ -142,7 +143,7 @@ class ShardedGE2EPlan:
         self.row_scale = torch.empty(U, dtype=f32, device=dev)
         self.path = lib().ge2e_b200_path(n_local, n_total, M, D, self.variant, self.precision)
         # finalize applies row_scale only where the forward produced it (softmax on tensor cores)
-        self._scaled = self.path == 1 and self.variant == _lib.SOFTMAX
+        self._scaled = self.path in (1, 2) and self.variant == _lib.SOFTMAX
         self.peer, self.peer_error = False, None
         world = dist.get_world_size(self.group)
         if peer_memory and world > 1:

@@ -110,5 +110,11 @@ def sharded_ge2e_loss(E_local, w, b, eps=1e-6, variant="softmax", precision="fp3
     if E_local.dim() != 3 or E_local.shape[1] < 2:
         raise ValueError(f"embeddings must be [n_local, M>=2, D], got {tuple(E_local.shape)}")
     group = group if group is not None else dist.group.WORLD
-    return ShardedGE2EFunction.apply(E_local, w, b, float(eps), _lib.VARIANTS[variant],
-                                     _lib.PRECISIONS[precision], group, stages or CudaStages)
+    vcode = _lib.VARIANTS[variant]
+    if E_local.is_cuda:
+        n_local, M, D = E_local.shape
+        with torch.cuda.device(E_local.device):
+            pcode = _lib.resolve_precision(precision, n_local, n_local * dist.get_world_size(group), M, D, vcode)
+    else:       # host-side emulation of the stages (tests): no tensor-core path to resolve to
+        pcode = _lib.PRECISIONS[precision]
+    return ShardedGE2EFunction.apply(E_local, w, b, float(eps), vcode, pcode, group, stages or CudaStages)

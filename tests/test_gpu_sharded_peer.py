@@ -40,6 +40,20 @@ CHILD = textwrap.dedent("""
             assert rel(p.dE, ref.dE[off:off + nl]) <= 2e-5, (k, rel(p.dE, ref.dE[off:off + nl]))
             assert abs(p.loss.item() - ref.loss.item()) <= 1e-5 * abs(ref.loss.item())
             assert abs(p.dw.item() - ref.dw.item()) <= 1e-4 * max(1.0, abs(ref.dw.item()))
+    # the default precision (fp32-class on the tensor cores: centroid rows carry their hi / lo fp16 planes
+    # through the publish / the all-gather)
+    ref32 = GE2EPlan(N, M, D, "softmax", "fp32", device=dev)
+    peer32 = ShardedGE2EPlan(nl, N, off, M, D, "softmax", "fp32", device=dev, peer_memory=True)
+    nccl32 = ShardedGE2EPlan(nl, N, off, M, D, "softmax", "fp32", device=dev, peer_memory=False)
+    assert ref32.precision == 2 and peer32.precision == 2 and peer32.peer and not nccl32.peer
+    for k in (1, 0):
+        shard = E_all[k][off:off + nl].contiguous()
+        ref32.step(E_all[k], w, b); peer32.step(shard, w, b); nccl32.step(shard, w, b)
+        torch.cuda.synchronize()
+        for p in (peer32, nccl32):
+            assert rel(p.dE, ref32.dE[off:off + nl]) <= 5e-6, (k, rel(p.dE, ref32.dE[off:off + nl]))
+            assert abs(p.loss.item() - ref32.loss.item()) <= 2e-6 * abs(ref32.loss.item())
+            assert abs(p.dw.item() - ref32.dw.item()) <= 1e-5 * max(1.0, abs(ref32.dw.item()))
     shards = [E_all[k][off:off + nl].contiguous() for k in range(2)]
     graph = peer.capture(shards, w, b, steps=4)          # steps 0..3 on shards 0, 1, 0, 1
     for _ in range(3):

@@ -66,7 +66,7 @@ def test_which_shapes_take_the_split_path(pkg):
     from speaker_embedding_ge2e_loss_b200 import _lib
     assert _lib.resolve_precision("fp32", 1024, 1024, 10, 256, 0) == _lib.FP32_SPLIT
     assert _lib.resolve_precision("fp32", 64, 64, 10, 256, 0) == _lib.FP32
-    assert _lib.resolve_precision("fp32", 128, 1024, 10, 256, 0) == _lib.FP32     # a shard: planes do not travel
+    assert _lib.resolve_precision("fp32", 128, 1024, 10, 256, 0) == _lib.FP32_SPLIT    # a speaker shard
     assert _lib.resolve_precision("fp32_simt", 1024, 1024, 10, 256, 0) == _lib.FP32
     assert _lib.resolve_precision("tf32", 1024, 1024, 10, 256, 0) == _lib.TF32
 

@@ -208,7 +208,7 @@ def run_shards(pkg, E, w, b, R, precision, one_launch, variant=0):
                                        dC_part.data_ptr(), ws.data_ptr() if nb else None, nb,
                                        torch.cuda.current_stream().cuda_stream)
             assert rc == 0, h.ge2e_b200_strerror(rc)
-            if not (h.ge2e_b200_path(nl, N, M, D, variant, prec) == 1 and variant == 0):
+            if not (h.ge2e_b200_path(nl, N, M, D, variant, prec) in (1, 2) and variant == 0):
                 s["row_scale"] = None
             torch.cuda.synchronize()
             assert not ws[:256].any(), "the workspace's counters must be zero again after the call"
@@ -238,12 +238,17 @@ def run_shards(pkg, E, w, b, R, precision, one_launch, variant=0):
     (64, 10, 256, 2, "fp32", FP32_TOL), (512, 4, 256, 4, "fp32", FP32_TOL), (96, 5, 64, 3, "fp32", FP32_TOL),
     (512, 4, 256, 2, "tf32", TF32_TOL), (1024, 10, 256, 8, "tf32", TF32_TOL), (768, 3, 128, 3, "tf32", TF32_TOL),
     (2048, 8, 256, 8, "tf32", TF32_TOL),
+    # fp32-class on the tensor cores: a centroid row carries its hi and lo fp16 planes through the "all-gather"
+    (1024, 10, 256, 8, "fp32_split", FP32_TOL), (768, 3, 128, 3, "fp32_split", FP32_TOL),
+    (2048, 8, 256, 2, "fp32_split", FP32_TOL),
 ])
 @pytest.mark.parametrize("one_launch", [False, True])
 def test_speaker_shards_on_one_gpu_vs_oracle(pkg, N, M, D, R, precision, tol, one_launch):
     E = torch.tensor(orc.make_embeddings(N, M, D, seed=N + R, kind="clustered"), device=DEV)
     if precision == "tf32":
         assert pkg.lib().ge2e_b200_path(N // R, N, M, D, 0, 1) == 1, "the shard should take the tcgen05 path"
+    if precision == "fp32_split":
+        assert pkg.lib().ge2e_b200_path(N // R, N, M, D, 0, 2) == 2, "the shard should take the split tcgen05 path"
     ref = orct.forward_backward(E, 10.0, -5.0, 1e-6, "softmax")
     got = run_shards(pkg, E, 10.0, -5.0, R, precision, one_launch)
     check_dev(got, ref, N * M, tol)
