@@ -24,6 +24,7 @@
 #include <initializer_list>
 
 #include "ge2e_common.cuh"
+#include "ge2e_tc_ptx.cuh"
 
 namespace ge2e {
 
@@ -702,6 +703,8 @@ contrast_bwd_kernel(const float* __restrict__ e_hat, const float* __restrict__ c
 // Body shared by finalize_kernel and the fused small-batch kernel: speaker j, block of kThreads
 // threads, `smem` = (2 M + 2) * Dp floats.  dE_hat / dC_hat are read with plain loads (the fused
 // kernel reads what its own block has just written).
+// REUSE_E: sE already holds the speaker's raw rows (prep_body staged them at the same place earlier in this kernel).
+template <bool REUSE_E = false>
 __device__ __forceinline__ void finalize_body(const float* __restrict__ E, const float* dE_hat, const float* dC_hat,
                                               const float* cos_diag, const float* row_stat, const float* row_aux,
                                               const float* row_scale, int j, int M, int D, int Dp, float w, float b,
@@ -717,12 +720,14 @@ __device__ __forceinline__ void finalize_body(const float* __restrict__ E, const
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const bool vec_e = is_vec(E, D), vec_g = is_vec(dE_hat, D), vec_o = is_vec(dE, D);
 
-  for (int v = tid; v < M * (Dp >> 2); v += kThreads) {
-    const int i = v / (Dp >> 2), col = (v % (Dp >> 2)) << 2;
-    *reinterpret_cast<float4*>(&sE[(size_t)i * Dp + col]) =
-        ld4(E + phys_row(idx, (size_t)j * M + i) * D, col, D, vec_e);
+  if (!REUSE_E) {
+    for (int v = tid; v < M * (Dp >> 2); v += kThreads) {
+      const int i = v / (Dp >> 2), col = (v % (Dp >> 2)) << 2;
+      *reinterpret_cast<float4*>(&sE[(size_t)i * Dp + col]) =
+          ld4(E + phys_row(idx, (size_t)j * M + i) * D, col, D, vec_e);
+    }
+    __syncthreads();
   }
-  __syncthreads();
   for (int d = tid; d < Dp; d += kThreads) {
     float s = 0.f;
     for (int i = 0; i < M; ++i) s += sE[(size_t)i * Dp + d];
@@ -737,7 +742,7 @@ __device__ __forceinline__ void finalize_body(const float* __restrict__ E, const
     for (int d = tid; d < D; d += kThreads) {
       const float c = sS[d] / fm;
       n2 = fmaf(c, c, n2);
-      pr = fmaf(c, dC_hat[(size_t)j * D + d], pr);
+      pr = fmaf(c, REUSE_E ? __ldcg(dC_hat + (size_t)j * D + d) : dC_hat[(size_t)j * D + d], pr);
     }
     const float n2t = block_sum(n2, red);
     const float prt = block_sum(pr, red);
@@ -750,7 +755,7 @@ __device__ __forceinline__ void finalize_body(const float* __restrict__ E, const
     for (int d = tid; d < Dp; d += kThreads) {
       float v = 0.f;
       if (d < D) {
-        const float dch = dC_hat[(size_t)j * D + d];
+        const float dch = REUSE_E ? __ldcg(dC_hat + (size_t)j * D + d) : dC_hat[(size_t)j * D + d];
         const float ch = (sS[d] / fm) * inv;
         v = (ok ? (dch - ch * proj) * inv : dch * inv) / fm;
       }
@@ -1494,8 +1499,8 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 __device__ __forceinline__ void small_grid_barrier(unsigned* ctr, unsigned target) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(ctr, 1u);
+    // release: the block's writes (ordered before this thread by the bar.sync) become visible with the arrival
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
     unsigned long long t0 = 0;
     for (unsigned spins = 0; ld_acquire_u32(ctr) < target; ++spins) {
       if ((spins & 1023u) == 1023u) {               // a missing CTA is a bug: trap instead of hanging the GPU
@@ -1505,7 +1510,6 @@ __device__ __forceinline__ void small_grid_barrier(unsigned* ctr, unsigned targe
         else if (t - t0 > 2000000000ull) __trap();
       }
     }
-    __threadfence();
   }
   __syncthreads();
 }
@@ -1530,8 +1534,10 @@ template <int VARIANT, int MR>
 __global__ void __launch_bounds__(kThreads, 1)
 small_step_kernel(const SmallParams p) {
   extern __shared__ __align__(16) float smem[];
-  __shared__ float red[kWarps];
+  __shared__ float red[3 * kWarps];
   __shared__ float s_cd[32];
+  __shared__ __align__(8) unsigned long long s_bar;   // bulk-copy completion (stage 2 operands)
+  constexpr int R4 = MR / 4;                          // rows per thread where the block splits into 4 row groups
   const int j = blockIdx.x, N = gridDim.x, M = p.M, D = p.D, Dp = p.Dp;
   const int Np = (N + 3) & ~3;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -1539,8 +1545,10 @@ small_step_kernel(const SmallParams p) {
   float* sEh = sA + (size_t)(2 * M + 2) * Dp;         // [MR][Dp] e_hat of this speaker, rows >= M zero
   const int Ds = Dp + 4;                              // row stride of sC: lanes reading different rows hit different banks
   float* sC = sEh + (size_t)MR * Dp;                  // [N][Ds] all c_hat
-  float* sG = sC + (size_t)N * Ds;                    // [M][Np] w * G, zero on the own-speaker column
-  float* sCos = sG + (size_t)M * Np;                  // [M][Np] cos + eps
+  float* sG = sC + (size_t)N * Ds;                    // [MR][Np] w * G, zero on the own-speaker column (rows >= M unused)
+  float* sCos = sG + (size_t)MR * Np;                 // [MR][Np] cos + eps
+  float* sRed = sCos + (size_t)MR * Np;               // [kWarps][MR][32] partial dot products of the cosine block
+  if (tid == 0) { ptx::mbar_init(ptx::smem_u32(&s_bar), 1); ptx::fence_mbar_init(); }
   pdl_wait();
   pdl_trigger();
   // debug (GE2E_SMALL_STOP=99, softmax only): SM clock stamps of CTA 0 into the unused row_kstar buffer
@@ -1552,50 +1560,102 @@ small_step_kernel(const SmallParams p) {
     p.loss_accum[tid] = 0.f;                          // {loss, -, -, -} as prep does
     if (tid < 2) p.dwdb[tid] = 0.f;
   }
+  // 16-byte rows: the centroid gradient is assembled at the L2 -- every CTA adds its [N][D] share with ONE bulk
+  // reduce-add, into rows their owners cleared before the first grid barrier (otherwise: workspace + gather)
+  const bool dc_at_l2 = (Dp == D) && is_vec(p.dC_hat, D);
+  if (dc_at_l2)
+    for (int d = tid; d < D; d += kThreads) p.dC_hat[(size_t)j * D + d] = 0.f;
 
   // ---- 1: this speaker's rows
   prep_body<false>(p.E, p.idx, j, M, D, Dp, p.e_hat, p.c_hat, p.cos_diag, sA);
   GE2E_SMALL_STAMP(1);
   if (p.stop == 1) return;
   do {
+  // e_hat / c_hat rows come back through bulk copies (async proxy): order this thread's global writes before them
+  asm volatile("fence.proxy.async;" ::: "memory");
   small_grid_barrier(p.ctr, (unsigned)N);
   GE2E_SMALL_STAMP(2);
   if (p.stop == 2) break;
 
   // ---- 2: M x N block of the similarity matrix
   const bool vec_c = is_vec(p.c_hat, D), vec_e = is_vec(p.e_hat, D);
-  for (int v = tid; v < N * (Dp >> 2); v += kThreads) {
-    const int k = v / (Dp >> 2), col = (v % (Dp >> 2)) << 2;
-    *reinterpret_cast<float4*>(&sC[(size_t)k * Ds + col]) = ld4_cg(p.c_hat + (size_t)k * D, col, D, vec_c);
+  for (int v = tid; v < (MR - M) * Np; v += kThreads) sG[M * Np + v] = 0.f;    // padding rows of w G: read, never NaN
+  if (vec_c && vec_e) {
+    // whole rows are 16-byte multiples: one bulk copy per centroid row (the padded row stride keeps 16-byte
+    // alignment) and one for the speaker's M contiguous e_hat rows, all counted on one mbarrier
+    const uint32_t bar = ptx::smem_u32(&s_bar);
+    if (wid == 0) {
+      asm volatile("fence.proxy.async;" ::: "memory");     // what the grid barrier acquired -> async proxy
+      if (lane == 0) ptx::mbar_expect_tx(bar, static_cast<uint32_t>((N + M) * D * sizeof(float)));
+      __syncwarp();
+      for (int k = lane; k < N; k += 32)
+        ptx::bulk_load_1d(ptx::smem_u32(sC + (size_t)k * Ds), p.c_hat + (size_t)k * D, D * sizeof(float), bar);
+      if (lane == 0)
+        ptx::bulk_load_1d(ptx::smem_u32(sEh), p.e_hat + (size_t)j * M * D, M * D * sizeof(float), bar);
+    }
+    for (int v = tid; v < (MR - M) * Dp; v += kThreads) sEh[(size_t)M * Dp + v] = 0.f;
+    if (tid < M) s_cd[tid] = p.cos_diag[(size_t)j * M + tid];
+    ptx::mbar_wait(bar, 0);
+  } else {
+    for (int v = tid; v < N * (Dp >> 2); v += kThreads) {
+      const int k = v / (Dp >> 2), col = (v % (Dp >> 2)) << 2;
+      *reinterpret_cast<float4*>(&sC[(size_t)k * Ds + col]) = ld4_cg(p.c_hat + (size_t)k * D, col, D, vec_c);
+    }
+    for (int v = tid; v < MR * (Dp >> 2); v += kThreads) {
+      const int i = v / (Dp >> 2), col = (v % (Dp >> 2)) << 2;
+      *reinterpret_cast<float4*>(&sEh[(size_t)i * Dp + col]) =
+          i < M ? ld4_plain(p.e_hat + ((size_t)j * M + i) * D, col, D, vec_e) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (tid < M) s_cd[tid] = p.cos_diag[(size_t)j * M + tid];
   }
-  for (int v = tid; v < MR * (Dp >> 2); v += kThreads) {
-    const int i = v / (Dp >> 2), col = (v % (Dp >> 2)) << 2;
-    *reinterpret_cast<float4*>(&sEh[(size_t)i * Dp + col]) =
-        i < M ? ld4_plain(p.e_hat + ((size_t)j * M + i) * D, col, D, vec_e) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  if (tid < M) s_cd[tid] = p.cos_diag[(size_t)j * M + tid];
   __syncthreads();
   GE2E_SMALL_STAMP(3);
-  // lane <-> centroid (32 per pass), warp <-> pair of rows: every lane runs the whole dot product of its
-  // (row, centroid) pair, no shuffles; the two e_hat rows are broadcast loads, the centroid rows are
-  // conflict-free through the padded stride.  Rows M..MR-1 of sEh are zero (MR is even).
-  for (int i0 = 2 * wid; i0 < MR; i0 += 2 * kWarps) {
-    const float* e0 = sEh + (size_t)i0 * Dp;
-    const float* e1 = e0 + Dp;
-    for (int k0 = 0; k0 < N; k0 += 32) {
-      const int k = k0 + lane;
+  // thread <-> (centroid kk of KT per pass, column phase dq of DQ = 256 / KT): a thread takes float4 columns dq,
+  // dq + DQ, ... of its centroid against ALL the speaker's rows (the centroid row is read once per block, the
+  // e_hat columns are warp-wide broadcasts where a warp shares dq), then the DQ partial dot products of every
+  // (row, centroid) are added: by shuffles inside a warp (KT < 32), through shared memory across warps, in a fixed
+  // order.  Rows M..MR-1 of sEh are zero.  KT: the smallest power of two >= N, between 4 and 64.
+  {
+    int lkt = 2;
+    while ((1 << lkt) < N && lkt < 6) ++lkt;
+    const int KT = 1 << lkt, DQ = kThreads >> lkt;
+    const int kk = tid & (KT - 1), dq = tid >> lkt;
+    const int KW = KT < 32 ? KT : 32;                 // distinct centroids inside one warp
+    const int ncol4 = Dp >> 2;
+    for (int k0 = 0; k0 < N; k0 += KT) {
+      const int k = k0 + kk;
       const float* c = sC + (size_t)(k < N ? k : N - 1) * Ds;
-      float a0 = 0.f, a1 = 0.f;
-#pragma unroll 8
-      for (int d = 0; d < Dp; d += 4) {
-        const float4 cv = *reinterpret_cast<const float4*>(c + d);
-        a0 += dot4(*reinterpret_cast<const float4*>(e0 + d), cv);
-        a1 += dot4(*reinterpret_cast<const float4*>(e1 + d), cv);
+      float acc[MR];
+#pragma unroll
+      for (int i = 0; i < MR; ++i) acc[i] = 0.f;
+#pragma unroll 2
+      for (int c4 = dq; c4 < ncol4; c4 += DQ) {
+        const float4 cv = *reinterpret_cast<const float4*>(c + (c4 << 2));
+#pragma unroll
+        for (int i = 0; i < MR; ++i)
+          acc[i] += dot4(*reinterpret_cast<const float4*>(sEh + (size_t)i * Dp + (c4 << 2)), cv);
       }
-      if (k < N) {
-        if (i0 < M) sCos[i0 * Np + k] = ((k == j) ? s_cd[i0] : a0) + eps;              // s3:78-79
-        if (i0 + 1 < M) sCos[(i0 + 1) * Np + k] = ((k == j) ? s_cd[i0 + 1] : a1) + eps;
+      for (int o = KT; o < 32; o <<= 1) {
+#pragma unroll
+        for (int i = 0; i < MR; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
       }
+      if (lane < KW) {
+#pragma unroll
+        for (int i = 0; i < MR; ++i) sRed[(wid * MR + i) * 32 + lane] = acc[i];
+      }
+      __syncthreads();
+      // (row i, centroid kk): the warps that hold it are wid = (kk >> 5) + q * wpk, q < nw
+      const int wpk = KT > 32 ? KT >> 5 : 1;          // warps that share one dq phase
+      const int nw = kWarps / wpk;
+      for (int v = tid; v < M * KT; v += kThreads) {
+        const int i = v >> lkt, kq = v & (KT - 1), kg = k0 + kq;
+        if (kg < N) {
+          float t = 0.f;
+          for (int q = 0; q < nw; ++q) t += sRed[(((kq >> 5) + q * wpk) * MR + i) * 32 + (kq & 31)];
+          sCos[i * Np + kg] = ((kg == j) ? s_cd[i] : t) + eps;                          // s3:78-79
+        }
+      }
+      if (k0 + KT < N) __syncthreads();               // sRed is rewritten by the next pass
     }
   }
   __syncthreads();
@@ -1609,25 +1669,32 @@ small_step_kernel(const SmallParams p) {
     float per, stat, aux = 0.f, dw_i = 0.f, db_i = 0.f;
     int ks = -1;
     if (VARIANT == GE2E_SOFTMAX) {
+      // the row's N <= 128 logits stay in registers (4 per lane): one pass for the maximum, one exponential each
+      constexpr int kPer = kSmallMaxN / 32;
+      float cosv[kPer], ex[kPer];
       float m = -INFINITY;
-      for (int k = lane; k < N; k += 32)
-        if (k != j) m = fmaxf(m, fmaf(w, sCos[i * Np + k], b));
+#pragma unroll
+      for (int q = 0; q < kPer; ++q) {
+        const int k = lane + 32 * q;
+        const bool on = k < N && k != j;
+        cosv[q] = on ? sCos[i * Np + k] : 0.f;
+        ex[q] = on ? fmaf(w, cosv[q], b) : -INFINITY;
+        m = fmaxf(m, ex[q]);
+      }
       const float mx = fmaxf(warp_max(m), Sd);
       float l = 0.f;
-      for (int k = lane; k < N; k += 32)
-        if (k != j) l += expf(fmaf(w, sCos[i * Np + k], b) - mx);
+#pragma unroll
+      for (int q = 0; q < kPer; ++q) { ex[q] = expf(ex[q] - mx); l += ex[q]; }      // exp(-inf) = 0 off the row
       const float loff = warp_sum(l);
       close_softmax_row(mx, loff, Sd, eps, stat, aux, per);                          // s3:120-121
+      const float sc = g * expf(mx - stat);             // G_k = g exp(S_k - stat) = sc exp(S_k - mx)
       float dwl = 0.f;
-      for (int k = lane; k < N; k += 32) {
-        float wg = 0.f;
-        if (k != j) {
-          const float cosv = sCos[i * Np + k];
-          const float G = g * expf(fmaf(w, cosv, b) - stat);
-          dwl = fmaf(G, cosv, dwl);
-          wg = w * G;
-        }
-        sG[i * Np + k] = wg;
+#pragma unroll
+      for (int q = 0; q < kPer; ++q) {
+        const int k = lane + 32 * q;
+        const float G = sc * ex[q];
+        dwl = fmaf(G, cosv[q], dwl);
+        if (k < N) sG[i * Np + k] = w * G;              // zero on the own-speaker column
       }
       dw_i = warp_sum(dwl) - g * aux * cd;            // own speaker: G = g (p_jj - 1) = -g aux
       db_i = -g * eps * expf(-stat);                  // closed form
@@ -1668,53 +1735,114 @@ small_step_kernel(const SmallParams p) {
       loss_part += per; dw_part += dw_i; db_part += db_i;
     }
   }
-  {
-    const float lt = block_sum(loss_part, red);
-    const float dwt = block_sum(dw_part, red);
-    const float dbt = block_sum(db_part, red);
-    if (tid == 0) { atomicAdd(p.loss_accum, lt); atomicAdd(p.dwdb + 0, dwt); atomicAdd(p.dwdb + 1, dbt); }
+  // lane 0 of every warp holds its rows' {loss, dw, db}: one round through shared memory
+  if (lane == 0) { red[wid] = loss_part; red[kWarps + wid] = dw_part; red[2 * kWarps + wid] = db_part; }
+  __syncthreads();                                     // sG complete, partial sums staged
+  if (tid < 3) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < kWarps; ++q) t += red[tid * kWarps + q];
+    atomicAdd(tid == 0 ? p.loss_accum : p.dwdb + (tid - 1), t);
   }
-  __syncthreads();                                     // sG complete
   GE2E_SMALL_STAMP(5);
   if (p.stop == 4) break;
   const bool vec_g = is_vec(p.dE_hat, D), vec_p = is_vec(p.part, D);
-  for (int i = wid; i < M; i += kWarps) {             // dE_hat rows = (wG) C_hat
-    for (int d = lane << 2; d < Dp; d += 128) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-      for (int k = 0; k < N; ++k) {
-        const float sgk = sG[i * Np + k];
+  {
+    // thread <-> (float4 column c4 of 64, group of 4): dE_hat rows rg, rg + 4, ... = (wG) C_hat, then this speaker's
+    // share (wG)^T E_hat of centroids kg, kg + 4, ...; a warp shares its group, so the w G entries are broadcasts
+    const int d = (tid & 63) << 2, grp = tid >> 6;
+    if (d < Dp) {
+      float4 acc[R4];
+#pragma unroll
+      for (int q = 0; q < R4; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      // four centroids per step: the four w G entries of a row come as ONE broadcast 16-byte load (rows >= M are
+      // zero; columns N..Np-1 of w G are never written, so the tail runs entry by entry)
+      auto fma_row = [&](float4& a, float sgk, const float4& c) {
+        a.x = fmaf(sgk, c.x, a.x); a.y = fmaf(sgk, c.y, a.y); a.z = fmaf(sgk, c.z, a.z); a.w = fmaf(sgk, c.w, a.w);
+      };
+      int k = 0;
+      for (; k + 4 <= N; k += 4) {
+        const float4 c0 = *reinterpret_cast<const float4*>(&sC[(size_t)(k + 0) * Ds + d]);
+        const float4 c1 = *reinterpret_cast<const float4*>(&sC[(size_t)(k + 1) * Ds + d]);
+        const float4 c2 = *reinterpret_cast<const float4*>(&sC[(size_t)(k + 2) * Ds + d]);
+        const float4 c3 = *reinterpret_cast<const float4*>(&sC[(size_t)(k + 3) * Ds + d]);
+#pragma unroll
+        for (int q = 0; q < R4; ++q) {
+          const float4 sg = *reinterpret_cast<const float4*>(&sG[(grp + 4 * q) * Np + k]);
+          fma_row(acc[q], sg.x, c0); fma_row(acc[q], sg.y, c1); fma_row(acc[q], sg.z, c2); fma_row(acc[q], sg.w, c3);
+        }
+      }
+      for (; k < N; ++k) {
         const float4 c = *reinterpret_cast<const float4*>(&sC[(size_t)k * Ds + d]);
-        acc.x = fmaf(sgk, c.x, acc.x); acc.y = fmaf(sgk, c.y, acc.y); acc.z = fmaf(sgk, c.z, acc.z); acc.w = fmaf(sgk, c.w, acc.w);
+#pragma unroll
+        for (int q = 0; q < R4; ++q) fma_row(acc[q], sG[(grp + 4 * q) * Np + k], c);
       }
-      st4(p.dE_hat + ((size_t)j * M + i) * D, d, D, vec_g, acc);
+#pragma unroll
+      for (int q = 0; q < R4; ++q) {
+        const int i = grp + 4 * q;
+        if (i < M) st4(p.dE_hat + ((size_t)j * M + i) * D, d, D, vec_g, acc[q]);
+      }
+    }
+    __syncthreads();                                   // the centroids are no longer needed: sC becomes the share tile
+    GE2E_SMALL_STAMP(6);
+    float* sP = sC;                                    // [N][Dp], contiguous (source of the bulk reduce-add)
+    if (d < Dp) {
+      float4 e[MR];
+#pragma unroll
+      for (int i = 0; i < MR; ++i) e[i] = *reinterpret_cast<const float4*>(&sEh[(size_t)i * Dp + d]);
+      auto put_share = [&](int k, const float4& a) {
+        if (dc_at_l2) *reinterpret_cast<float4*>(&sP[(size_t)k * Dp + d]) = a;
+        else st4(p.part + ((size_t)j * N + k) * D, d, D, vec_p, a);
+      };
+      // centroids 4 grp + 16 t .. + 3: a row's four w G entries are one broadcast 16-byte load (rows >= M: w G and
+      // e_hat are both zero -- no branch in the chain); the columns N..Np-1 of w G are never written: tail by entry
+      int kb = 4 * grp;
+      for (; kb + 4 <= N; kb += 16) {
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+#pragma unroll
+        for (int i = 0; i < MR; ++i) {
+          const float4 sg = *reinterpret_cast<const float4*>(&sG[i * Np + kb]);
+          a0.x = fmaf(sg.x, e[i].x, a0.x); a0.y = fmaf(sg.x, e[i].y, a0.y); a0.z = fmaf(sg.x, e[i].z, a0.z); a0.w = fmaf(sg.x, e[i].w, a0.w);
+          a1.x = fmaf(sg.y, e[i].x, a1.x); a1.y = fmaf(sg.y, e[i].y, a1.y); a1.z = fmaf(sg.y, e[i].z, a1.z); a1.w = fmaf(sg.y, e[i].w, a1.w);
+          a2.x = fmaf(sg.z, e[i].x, a2.x); a2.y = fmaf(sg.z, e[i].y, a2.y); a2.z = fmaf(sg.z, e[i].z, a2.z); a2.w = fmaf(sg.z, e[i].w, a2.w);
+          a3.x = fmaf(sg.w, e[i].x, a3.x); a3.y = fmaf(sg.w, e[i].y, a3.y); a3.z = fmaf(sg.w, e[i].z, a3.z); a3.w = fmaf(sg.w, e[i].w, a3.w);
+        }
+        put_share(kb, a0); put_share(kb + 1, a1); put_share(kb + 2, a2); put_share(kb + 3, a3);
+      }
+      for (int k = kb; k < N && k < kb + 4; ++k) {      // at most one group holds the N % 4 trailing centroids
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < MR; ++i) {
+          const float sgk = sG[i * Np + k];
+          a.x = fmaf(sgk, e[i].x, a.x); a.y = fmaf(sgk, e[i].y, a.y); a.z = fmaf(sgk, e[i].z, a.z); a.w = fmaf(sgk, e[i].w, a.w);
+        }
+        put_share(k, a);
+      }
+    }
+    if (dc_at_l2) {
+      ptx::fence_proxy_async_smem();                   // this thread's tile entries -> async proxy
+      __syncthreads();
+      GE2E_SMALL_STAMP(7);
+      if (tid == 0) {
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                     ::"l"(p.dC_hat), "r"(ptx::smem_u32(sP)), "r"(static_cast<uint32_t>((size_t)N * D * sizeof(float)))
+                     : "memory");
+        ptx::tma_store_commit();
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // performed: the barrier arrival below publishes it
+      }
     }
   }
   __syncthreads();
-  GE2E_SMALL_STAMP(6);
-  for (int k = wid; k < N; k += kWarps) {             // this speaker's share of dC_hat_k = (wG)^T E_hat
-    for (int d = lane << 2; d < Dp; d += 128) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-      for (int i = 0; i < M; ++i) {
-        const float sgk = sG[i * Np + k];
-        const float4 e = *reinterpret_cast<const float4*>(&sEh[(size_t)i * Dp + d]);
-        acc.x = fmaf(sgk, e.x, acc.x); acc.y = fmaf(sgk, e.y, acc.y); acc.z = fmaf(sgk, e.z, acc.z); acc.w = fmaf(sgk, e.w, acc.w);
-      }
-      st4(p.part + ((size_t)j * N + k) * D, d, D, vec_p, acc);
-    }
-  }
-  __syncthreads();
-  GE2E_SMALL_STAMP(7);
+  if (!dc_at_l2) GE2E_SMALL_STAMP(7);
   if (p.stop == 5) break;
   small_grid_barrier(p.ctr, (unsigned)(2 * N));
   GE2E_SMALL_STAMP(8);
   if (p.stop == 6) break;
 
   // ---- 3: centroid gradient of this speaker, then the Jacobians and the fan-out
-  // (the block's threads split the N contributions into groups so that each thread has many independent
-  // L2 loads in flight instead of a chain of N; the groups are then added in a fixed order)
-  {
+  // (unaligned rows only: the block's threads split the N contributions into groups so that each thread has many
+  // independent L2 loads in flight instead of a chain of N; the groups are then added in a fixed order)
+  if (!dc_at_l2) {
     const int ncol4 = Dp >> 2;                               // <= 64 float4 columns
     const int ngrp = kThreads / ncol4;                       // >= 4 speaker groups
     const int col4 = tid % ncol4, grp = tid / ncol4;
@@ -1746,8 +1874,8 @@ small_step_kernel(const SmallParams p) {
   __syncthreads();
   GE2E_SMALL_STAMP(9);
   if (p.stop == 7) break;
-  finalize_body(p.E, p.dE_hat, p.dC_hat, p.cos_diag, p.row_stat, p.row_aux, nullptr, j, M, D, Dp, w, b, g, eps, VARIANT, p.dE,
-                p.idx, sA);
+  finalize_body<true>(p.E, p.dE_hat, p.dC_hat, p.cos_diag, p.row_stat, p.row_aux, nullptr, j, M, D, Dp, w, b, g, eps, VARIANT,
+                      p.dE, p.idx, sA);      // sA still holds the raw rows prep_body staged
   } while (0);
   __syncthreads();
   GE2E_SMALL_STAMP(10);
@@ -1760,7 +1888,8 @@ small_step_kernel(const SmallParams p) {
 
 size_t small_smem_bytes(int N, int M, int D) {
   const int Dp = (D + 3) & ~3, Np = (N + 3) & ~3, MR = (M + 3) & ~3;
-  return ((size_t)(2 * M + 2 + MR) * Dp + (size_t)N * (Dp + 4) + (size_t)2 * M * Np) * sizeof(float);
+  return ((size_t)(2 * M + 2 + MR) * Dp + (size_t)N * (Dp + 4) + (size_t)2 * MR * Np + (size_t)kWarps * MR * 32) *
+         sizeof(float);
 }
 
 }  // namespace
@@ -1784,7 +1913,7 @@ static int device_sm_count() {
 
 bool small_step_supported(int N, int M, int D) {
   return N >= 1 && N <= kSmallMaxN && M >= 2 && M <= kSmallMaxM && D >= 1 && D <= kSmallMaxD &&
-         small_smem_bytes(N, M, D) <= 200 * 1024 && N <= device_sm_count();
+         small_smem_bytes(N, M, D) <= 225 * 1024 && N <= device_sm_count();
 }
 
 size_t small_step_workspace_bytes(int N, int M, int D) {

@@ -83,6 +83,13 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int 
       : "memory");
 }
 
+// plain 1-D bulk copy global -> shared (16-byte aligned, size a multiple of 16), bytes counted on `bar`
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
 // multicast variants: the box lands at the same CTA-relative offset in every CTA of `mask` and
 // completes tx bytes on the mbarrier at the same offset in each of them
 __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const void* tmap, int x, int y, uint32_t bar,
