@@ -1537,6 +1537,8 @@ small_step_kernel(const SmallParams p) {
   __shared__ float red[3 * kWarps];
   __shared__ float s_cd[32];
   __shared__ __align__(8) unsigned long long s_bar;   // bulk-copy completion (stage 2 operands)
+  __shared__ float s_ine[16], s_inu[16], s_aux[16];   // fast path: 1/|e|, 1/|u|, 1 - p_jj per row of the speaker
+  __shared__ int s_ok[16];                            // fast path: bit 0 |e| >= delta, bit 1 |u| >= delta
   constexpr int R4 = MR / 4;                          // rows per thread where the block splits into 4 row groups
   const int j = blockIdx.x, N = gridDim.x, M = p.M, D = p.D, Dp = p.Dp;
   const int Np = (N + 3) & ~3;
@@ -1567,7 +1569,83 @@ small_step_kernel(const SmallParams p) {
     for (int d = tid; d < D; d += kThreads) p.dC_hat[(size_t)j * D + d] = 0.f;
 
   // ---- 1: this speaker's rows
-  prep_body<false>(p.E, p.idx, j, M, D, Dp, p.e_hat, p.c_hat, p.cos_diag, sA);
+  // Fast path (whole 16-byte rows of a multiple of 64 columns -- D = 64 / 128 / 192 / 256): the stage bodies shared
+  // with the pipeline's kernels (prep_body / finalize_body: a warp per row, M rows in two rounds, every operand
+  // through global memory) are replaced by forms that keep the speaker's state in shared memory from here to the
+  // last store: a HALF-warp per row (all M <= 16 rows at once), per-row norms computed once, e_hat rows written
+  // straight into the stage-2 operand tile, dE_hat rows handed to the Jacobians in shared memory.
+  const bool fast = (Dp == D) && (D % 64 == 0) && is_vec(p.E, D) && is_vec(p.e_hat, D) && is_vec(p.c_hat, D) &&
+                    is_vec(p.dE_hat, D) && is_vec(p.dC_hat, D) && is_vec(p.dE, D);
+  float* fE = sA;                                     // [M][Dp] raw rows, later d e (gradient through e_hat)
+  float* fS = fE + (size_t)M * Dp;                    // [Dp] column sums of the raw rows, later of d u
+  float* fU = fS + Dp;                                // [M][Dp] dE_hat rows, later d u
+  float* fB = fU + (size_t)M * Dp;                    // [Dp] dC_hat row, then d c / M
+  const int ncol4 = Dp >> 2;
+  const int hw = tid >> 4, hl = tid & 15;             // half-warp <-> row
+  const float fm = (float)M, inv_m1 = 1.f / (float)(M - 1);
+  float c_norm2 = 0.f, c_mine = 0.f;                  // fast path: |c_j|^2 (every thread), c_j[tid]
+  if (fast) {
+    for (int i = wid; i < M; i += kWarps) {
+      const float4* src = reinterpret_cast<const float4*>(p.E + phys_row(p.idx, (size_t)j * M + i) * D);
+      float4* dst = reinterpret_cast<float4*>(fE + (size_t)i * Dp);
+      for (int c4 = lane; c4 < ncol4; c4 += 32) dst[c4] = __ldg(src + c4);
+    }
+    for (int v = tid; v < (MR - M) * Dp; v += kThreads) sEh[(size_t)M * Dp + v] = 0.f;
+    __syncthreads();
+    float cpart = 0.f;
+    for (int d = tid; d < Dp; d += kThreads) {
+      float sum = 0.f;
+      for (int i = 0; i < M; ++i) sum += fE[(size_t)i * Dp + d];                 // s3:105
+      fS[d] = sum;
+      const float c = sum / fm;                                                  // s3:37
+      cpart = fmaf(c, c, cpart);
+    }
+    cpart = warp_sum(cpart);
+    if (lane == 0) red[wid] = cpart;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kWarps; ++q) c_norm2 += red[q];
+    const float inv_nc = 1.f / fmaxf(sqrtf(c_norm2), kCosDelta);
+    if (tid < D) {                                     // D <= 256 = block size: one centroid entry per thread
+      c_mine = fS[tid] / fm;
+      p.c_hat[(size_t)j * D + tid] = c_mine * inv_nc;
+    }
+    // rows: |e|, |u| and e.u with u = (s - e) / (M - 1)   (s3:105-111, s3:57)
+    const bool act = hw < M;
+    float ne2 = 0.f, nd2 = 0.f, ed = 0.f;
+    if (act)
+      for (int c4 = hl; c4 < ncol4; c4 += 16) {
+        const float4 e = reinterpret_cast<const float4*>(fE + (size_t)hw * Dp)[c4];
+        const float4 sv = reinterpret_cast<const float4*>(fS)[c4];
+        const float4 dv = make_float4(sv.x - e.x, sv.y - e.y, sv.z - e.z, sv.w - e.w);
+        ne2 += dot4(e, e); nd2 += dot4(dv, dv); ed += dot4(e, dv);
+      }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      ne2 += __shfl_xor_sync(0xffffffffu, ne2, o);
+      nd2 += __shfl_xor_sync(0xffffffffu, nd2, o);
+      ed += __shfl_xor_sync(0xffffffffu, ed, o);
+    }
+    if (act) {
+      const float ne = sqrtf(ne2), nu = sqrtf(nd2) * inv_m1;
+      const float inv_ne = 1.f / fmaxf(ne, kCosDelta), inv_nu = 1.f / fmaxf(nu, kCosDelta);
+      const float cosd = (ed * inv_m1) * inv_ne * inv_nu;
+      float4* gdst = reinterpret_cast<float4*>(p.e_hat + ((size_t)j * M + hw) * D);
+      for (int c4 = hl; c4 < ncol4; c4 += 16) {
+        float4 e = reinterpret_cast<const float4*>(fE + (size_t)hw * Dp)[c4];
+        e.x *= inv_ne; e.y *= inv_ne; e.z *= inv_ne; e.w *= inv_ne;
+        reinterpret_cast<float4*>(sEh + (size_t)hw * Dp)[c4] = e;
+        gdst[c4] = e;
+      }
+      if (hl == 0) {
+        s_cd[hw] = cosd; p.cos_diag[(size_t)j * M + hw] = cosd;
+        s_ine[hw] = inv_ne; s_inu[hw] = inv_nu;
+        s_ok[hw] = (ne >= kCosDelta ? 1 : 0) | (nu >= kCosDelta ? 2 : 0);
+      }
+    }
+  } else {
+    prep_body<false>(p.E, p.idx, j, M, D, Dp, p.e_hat, p.c_hat, p.cos_diag, sA);
+  }
   GE2E_SMALL_STAMP(1);
   if (p.stop == 1) return;
   do {
@@ -1580,7 +1658,18 @@ small_step_kernel(const SmallParams p) {
   // ---- 2: M x N block of the similarity matrix
   const bool vec_c = is_vec(p.c_hat, D), vec_e = is_vec(p.e_hat, D);
   for (int v = tid; v < (MR - M) * Np; v += kThreads) sG[M * Np + v] = 0.f;    // padding rows of w G: read, never NaN
-  if (vec_c && vec_e) {
+  if (fast) {
+    // 16 bytes per cp.async, all of a thread's copies in flight together (a warp takes rows wid, wid + 8, ...):
+    // one L2 round trip for the whole centroid matrix; stage 1 left e_hat in sEh and the cosines in s_cd
+    for (int k = wid; k < N; k += kWarps) {
+      const float4* src = reinterpret_cast<const float4*>(p.c_hat + (size_t)k * D);
+      const uint32_t dst = ptx::smem_u32(sC + (size_t)k * Ds);
+      for (int c4 = lane; c4 < ncol4; c4 += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (c4 << 4)), "l"(src + c4) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else if (vec_c && vec_e) {
     // whole rows are 16-byte multiples: one bulk copy per centroid row (the padded row stride keeps 16-byte
     // alignment) and one for the speaker's M contiguous e_hat rows, all counted on one mbarrier
     const uint32_t bar = ptx::smem_u32(&s_bar);
@@ -1730,6 +1819,7 @@ small_step_kernel(const SmallParams p) {
     if (lane == 0) {
       p.row_stat[r] = stat;
       p.row_aux[r] = aux;
+      s_aux[i] = aux;
       if (VARIANT == GE2E_CONTRAST && p.row_kstar != nullptr) p.row_kstar[r] = ks;
       if (p.per_row != nullptr) p.per_row[r] = per;
       loss_part += per; dw_part += dw_i; db_part += db_i;
@@ -1780,7 +1870,10 @@ small_step_kernel(const SmallParams p) {
 #pragma unroll
       for (int q = 0; q < R4; ++q) {
         const int i = grp + 4 * q;
-        if (i < M) st4(p.dE_hat + ((size_t)j * M + i) * D, d, D, vec_g, acc[q]);
+        if (i < M) {
+          st4(p.dE_hat + ((size_t)j * M + i) * D, d, D, vec_g, acc[q]);
+          if (fast) *reinterpret_cast<float4*>(fU + (size_t)i * Dp + d) = acc[q];     // for the Jacobians (stage 3)
+        }
       }
     }
     __syncthreads();                                   // the centroids are no longer needed: sC becomes the share tile
@@ -1828,8 +1921,60 @@ small_step_kernel(const SmallParams p) {
                      ::"l"(p.dC_hat), "r"(ptx::smem_u32(sP)), "r"(static_cast<uint32_t>((size_t)N * D * sizeof(float)))
                      : "memory");
         ptx::tma_store_commit();
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // performed: the barrier arrival below publishes it
       }
+      if (fast) {
+        // While the adds travel: everything of stage 3 that does not need the centroid gradient -- the two
+        // normalisation Jacobians of e_hat and u_hat (same arithmetic as finalize_body) and the column sums of d u
+        const bool act = hw < M;
+        float eg = 0.f;
+        if (act)
+          for (int c4 = hl; c4 < ncol4; c4 += 16)
+            eg += dot4(reinterpret_cast<const float4*>(fE + (size_t)hw * Dp)[c4],
+                       reinterpret_cast<const float4*>(fU + (size_t)hw * Dp)[c4]);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) eg += __shfl_xor_sync(0xffffffffu, eg, o);
+        if (act) {
+          const float inv_ne = s_ine[hw], inv_nu = s_inu[hw], cdv = s_cd[hw];
+          const bool ok_e = (s_ok[hw] & 1) != 0, ok_u = (s_ok[hw] & 2) != 0;
+          float Gd;                                      // diagonal element of G
+          if (VARIANT == GE2E_SOFTMAX) {
+            Gd = -g * s_aux[hw];                         // g (p_jj - 1), accumulated off-diagonal in stage 2
+          } else {
+            const float sp = 1.f / (1.f + expf(-fmaf(w, cdv + eps, b)));
+            Gd = -g * sp * (1.f - sp);
+          }
+          const float dd = w * Gd;
+          const float proj_e = eg * inv_ne + dd * cdv;   // e_hat . d e_hat
+          const float proj_u = dd * cdv;                 // u_hat . d u_hat
+          for (int c4 = hl; c4 < ncol4; c4 += 16) {
+            const float4 e = reinterpret_cast<const float4*>(fE + (size_t)hw * Dp)[c4];
+            const float4 sv = reinterpret_cast<const float4*>(fS)[c4];
+            const float4 gv = reinterpret_cast<const float4*>(fU + (size_t)hw * Dp)[c4];
+            const float ev[4] = {e.x, e.y, e.z, e.w}, ss[4] = {sv.x, sv.y, sv.z, sv.w}, gg[4] = {gv.x, gv.y, gv.z, gv.w};
+            float de[4], du[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float eh = ev[t] * inv_ne;
+              const float uh = ((ss[t] - ev[t]) * inv_m1) * inv_nu;
+              const float deh = gg[t] + dd * uh;
+              const float duh = dd * eh;
+              de[t] = ok_e ? (deh - eh * proj_e) * inv_ne : deh * inv_ne;
+              du[t] = ok_u ? (duh - uh * proj_u) * inv_nu : duh * inv_nu;
+            }
+            // each slot is read and then overwritten by the same lane
+            reinterpret_cast<float4*>(fU + (size_t)hw * Dp)[c4] = make_float4(du[0], du[1], du[2], du[3]);
+            reinterpret_cast<float4*>(fE + (size_t)hw * Dp)[c4] = make_float4(de[0], de[1], de[2], de[3]);
+          }
+        }
+        __syncthreads();          // d e, d u complete; the sums of the raw rows are no longer needed (c_mine)
+        for (int d = tid; d < Dp; d += kThreads) {
+          float sum = 0.f;
+          for (int i = 0; i < M; ++i) sum += fU[(size_t)i * Dp + d];
+          fS[d] = sum;
+        }
+      }
+      // performed (not just read): the barrier arrival below publishes this CTA's adds
+      if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   }
   __syncthreads();
@@ -1874,8 +2019,41 @@ small_step_kernel(const SmallParams p) {
   __syncthreads();
   GE2E_SMALL_STAMP(9);
   if (p.stop == 7) break;
-  finalize_body<true>(p.E, p.dE_hat, p.dC_hat, p.cos_diag, p.row_stat, p.row_aux, nullptr, j, M, D, Dp, w, b, g, eps, VARIANT,
-                      p.dE, p.idx, sA);      // sA still holds the raw rows prep_body staged
+  if (fast) {
+    // centroid Jacobian: d c = (dC_hat - c_hat (c_hat . dC_hat)) / |c|   (or dC_hat / delta), kept as d c / M
+    const float dch = tid < D ? __ldcg(p.dC_hat + (size_t)j * D + tid) : 0.f;      // assembled at the L2 by all CTAs
+    float prp = warp_sum(c_mine * dch);
+    if (lane == 0) red[wid] = prp;
+    __syncthreads();
+    float pr = 0.f;
+#pragma unroll
+    for (int q = 0; q < kWarps; ++q) pr += red[q];
+    if (tid < D) {
+      const float nc = sqrtf(c_norm2);
+      const float inv = 1.f / fmaxf(nc, kCosDelta);
+      const float proj = pr * inv;                   // c_hat . dC_hat
+      fB[tid] = (nc >= kCosDelta ? (dch - (c_mine * inv) * proj) * inv : dch * inv) / fm;
+    }
+    __syncthreads();
+    for (int i = wid; i < M; i += kWarps) {           // fan-out of d c and of the leave-one-out centroids (s3:105-111)
+      float4* dst = reinterpret_cast<float4*>(p.dE + phys_row(p.idx, (size_t)j * M + i) * D);
+      for (int c4 = lane; c4 < ncol4; c4 += 32) {
+        const float4 de = reinterpret_cast<const float4*>(fE + (size_t)i * Dp)[c4];
+        const float4 du = reinterpret_cast<const float4*>(fU + (size_t)i * Dp)[c4];
+        const float4 sd = reinterpret_cast<const float4*>(fS)[c4];
+        const float4 bc = reinterpret_cast<const float4*>(fB)[c4];
+        float4 o;
+        o.x = de.x + bc.x + (sd.x - du.x) * inv_m1;
+        o.y = de.y + bc.y + (sd.y - du.y) * inv_m1;
+        o.z = de.z + bc.z + (sd.z - du.z) * inv_m1;
+        o.w = de.w + bc.w + (sd.w - du.w) * inv_m1;
+        dst[c4] = o;
+      }
+    }
+  } else {
+    finalize_body<true>(p.E, p.dE_hat, p.dC_hat, p.cos_diag, p.row_stat, p.row_aux, nullptr, j, M, D, Dp, w, b, g, eps,
+                        VARIANT, p.dE, p.idx, sA);      // sA still holds the raw rows prep_body staged
+  }
   } while (0);
   __syncthreads();
   GE2E_SMALL_STAMP(10);
