@@ -1485,6 +1485,7 @@ struct SmallParams {
   float* loss_accum;                // [0] = loss (zeroed here)
   float* dE_hat; float* dC_hat; float* dwdb; float* dE;
   int stop;                         // debug, timing only: leave after stage `stop` (0 = run everything)
+  int cluster;                      // the grid is ONE thread-block cluster (N <= 8): hardware barriers
   unsigned* ctr;                    // workspace header: {barrier arrivals, exits}; zero on entry, restored
   float* part;                      // workspace: [N][N][D] centroid contributions
 };
@@ -1651,7 +1652,9 @@ small_step_kernel(const SmallParams p) {
   do {
   // e_hat / c_hat rows come back through bulk copies (async proxy): order this thread's global writes before them
   asm volatile("fence.proxy.async;" ::: "memory");
-  small_grid_barrier(p.ctr, (unsigned)N);
+  // up to 8 speakers the whole grid is one thread-block cluster: barrier.cluster (release / acquire at cluster
+  // scope) instead of an arrival counter polled through the L2
+  if (p.cluster) { __syncthreads(); ptx::cluster_sync_all(); } else small_grid_barrier(p.ctr, (unsigned)N);
   GE2E_SMALL_STAMP(2);
   if (p.stop == 2) break;
 
@@ -1980,7 +1983,7 @@ small_step_kernel(const SmallParams p) {
   __syncthreads();
   if (!dc_at_l2) GE2E_SMALL_STAMP(7);
   if (p.stop == 5) break;
-  small_grid_barrier(p.ctr, (unsigned)(2 * N));
+  if (p.cluster) { __syncthreads(); ptx::cluster_sync_all(); } else small_grid_barrier(p.ctr, (unsigned)(2 * N));
   GE2E_SMALL_STAMP(8);
   if (p.stop == 6) break;
 
@@ -2058,7 +2061,7 @@ small_step_kernel(const SmallParams p) {
   __syncthreads();
   GE2E_SMALL_STAMP(10);
   // last CTA out restores the workspace header (every CTA has left both barriers by the time it exits)
-  if (tid == 0) {
+  if (tid == 0 && !p.cluster) {
     if (atomicAdd(p.ctr + 1, 1u) == (unsigned)(N - 1)) { atomicExch(p.ctr, 0u); atomicExch(p.ctr + 1, 0u); }
   }
 }
@@ -2117,11 +2120,21 @@ int simt_small_step(const float* E, const int32_t* row_index, int N, int M, int 
   p.ctr = reinterpret_cast<unsigned*>(workspace);
   p.part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kSmallHeaderBytes);
   const size_t smem = small_smem_bytes(N, M, D);
+  // N <= 8 (the portable cluster size): the N CTAs form one cluster
+  p.cluster = N <= 8 ? 1 : 0;
 #define GE2E_SMALL_LAUNCH(V, R)                                                                   \
   do {                                                                                            \
     int rc = set_smem(small_step_kernel<V, R>, smem);                                             \
     if (rc != GE2E_OK) return rc;                                                                 \
-    launch_pdl(small_step_kernel<V, R>, dim3(N), dim3(kThreads), smem, st, true, p);              \
+    cudaLaunchConfig_t cfg{};                                                                     \
+    cfg.gridDim = dim3(N); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st; \
+    cudaLaunchAttribute at[2];                                                                    \
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                \
+    at[0].val.programmaticStreamSerializationAllowed = 1;                                         \
+    at[1].id = cudaLaunchAttributeClusterDimension;                                               \
+    at[1].val.clusterDim.x = N; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;           \
+    cfg.attrs = at; cfg.numAttrs = p.cluster ? 2 : 1;                                             \
+    GE2E_CUDA_TRY(cudaLaunchKernelEx(&cfg, small_step_kernel<V, R>, p));                          \
   } while (0)
   const int mr = (M + 3) & ~3;
   if (variant == GE2E_SOFTMAX) {
