@@ -245,14 +245,15 @@ int ge2e_b200_scale_bias_sgd(float* w, float* b, float* dw, float* db, float max
  * Batches of the reference's own size -- N <= 64 speakers, M <= 16, D <= 256, i.e. its training
  * (64 x 10) and test (4 x 8) shapes, where five dependent launches are mostly latency -- run as ONE
  * kernel (the kernel itself supports N <= 128, see ge2e_b200_debug_small_step):
- * one CTA per speaker, every stage separated by grid-wide barriers (all CTAs are co-resident),
- * centroid gradients exchanged through the workspace in a fixed order (deterministic).  Those shapes
+ * one CTA per speaker, every stage separated by grid-wide barriers (all CTAs are co-resident; up to 8 speakers
+ * the grid is one thread-block cluster), centroid gradients added at the L2 (one bulk reduce-add per CTA; rows
+ * that are not whole 16-byte multiples go through the workspace in a fixed order instead).  Those shapes
  * need ge2e_b200_step_workspace_bytes() bytes of workspace (>= ge2e_b200_workspace_bytes()); only its
  * first 256 bytes have to be zero on entry and are zero again on exit, the rest is scratch.
  * ge2e_b200_step_launches() = 1 when the single-kernel path is taken for the shape, else 0. */
 size_t ge2e_b200_step_workspace_bytes(int N, int M, int D, int variant, int precision);
 /* Debug / tests: which shapes take the single-kernel step.  0 = none, 1 = those where it was measured
- * faster than the pipeline (softmax N <= 64, contrast N <= 16; default), 2 = every shape the kernel supports (N <= 128, M <= 16, D <= 256).
+ * faster than the pipeline (N <= 64; default), 2 = every shape the kernel supports (N <= 128, M <= 16, D <= 256).
  * Initial value 1.  Query sizes / launches AFTER setting it. */
 void ge2e_b200_debug_small_step(int mode);
 int ge2e_b200_step_launches(int N, int M, int D, int variant, int precision);

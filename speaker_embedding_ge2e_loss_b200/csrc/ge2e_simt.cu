@@ -1471,9 +1471,10 @@ namespace {
 
 // Up to kSmallMaxN speakers the kernel is correct (tested to 128); it is SELECTED up to kSmallPickN:
 // one CTA per speaker serialises the speaker's M x N block, so its advantage over the five-kernel
-// pipeline shrinks with N -- 37 -> 18 us at the reference's test shape (N = 4, M = 8), 53 -> 41 us at its
-// training shape (cfg2, N = 64, M = 10; stage timeline: scripts/small_step_trace.py); not measured beyond.
-constexpr int kSmallMaxN = 128, kSmallMaxM = 16, kSmallMaxD = 256, kSmallPickN = 64, kSmallPickNContrast = 16;
+// pipeline shrinks with N -- 37 -> 9.1 us at the reference's test shape (N = 4, M = 8), 53 -> 19.9 us at its
+// training shape (cfg2, N = 64, M = 10; contrast: 30.8 -> 19.7 us; stage timeline: scripts/small_step_trace.py);
+// not measured beyond.
+constexpr int kSmallMaxN = 128, kSmallMaxM = 16, kSmallMaxD = 256, kSmallPickN = 64, kSmallPickNContrast = 64;
 constexpr size_t kSmallHeaderBytes = 256;
 
 struct SmallParams {
@@ -2075,8 +2076,8 @@ size_t small_smem_bytes(int N, int M, int D) {
 
 }  // namespace
 
-// (contrast: the pipeline's backward is a two-non-zeros-per-row gather / scatter, the single kernel runs the
-//  dense products; measured at cfg2: pipeline 27.6 us, single kernel 39.3 us -- so only tiny batches)
+// (contrast: the pipeline's backward is a two-non-zeros-per-row gather / scatter while the single kernel runs the
+//  dense products; since the round-2 rewrite of the stages the single kernel still wins at cfg2: 19.7 vs 30.8 us)
 bool small_step_preferred(int N, int M, int D, int variant) {
   return small_step_supported(N, M, D) && N <= (variant == GE2E_CONTRAST ? kSmallPickNContrast : kSmallPickN);
 }
