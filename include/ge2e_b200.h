@@ -242,7 +242,7 @@ int ge2e_b200_scale_bias_sgd(float* w, float* b, float* dw, float* db, float max
  * self.ge2e_loss(embeddings); loss.backward()`): ge2e_b200_prep_indexed, ge2e_b200_step_rows and
  * ge2e_b200_bwd_finalize_indexed with the same buffers (row_index nullable; accum[0] = loss,
  * accum[1] = dw, accum[2] = db; grad_out = device scalar, the upstream gradient).
- * Batches of the reference's own size -- N <= 64 speakers, M <= 16, D <= 256, i.e. its training
+ * Batches of the reference's own size -- N <= 128 speakers, M <= 16, D <= 256, i.e. its training
  * (64 x 10) and test (4 x 8) shapes, where five dependent launches are mostly latency -- run as ONE
  * kernel (the kernel itself supports N <= 128, see ge2e_b200_debug_small_step):
  * one CTA per speaker, every stage separated by grid-wide barriers (all CTAs are co-resident; up to 8 speakers
@@ -253,7 +253,7 @@ int ge2e_b200_scale_bias_sgd(float* w, float* b, float* dw, float* db, float max
  * ge2e_b200_step_launches() = 1 when the single-kernel path is taken for the shape, else 0. */
 size_t ge2e_b200_step_workspace_bytes(int N, int M, int D, int variant, int precision);
 /* Debug / tests: which shapes take the single-kernel step.  0 = none, 1 = those where it was measured
- * faster than the pipeline (N <= 64; default), 2 = every shape the kernel supports (N <= 128, M <= 16, D <= 256).
+ * faster than the pipeline (all of them since round 2: N <= 128; default), 2 = every shape the kernel supports (N <= 128, M <= 16, D <= 256).
  * Initial value 1.  Query sizes / launches AFTER setting it. */
 void ge2e_b200_debug_small_step(int mode);
 int ge2e_b200_step_launches(int N, int M, int D, int variant, int precision);

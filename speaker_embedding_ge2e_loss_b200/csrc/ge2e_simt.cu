@@ -1472,9 +1472,9 @@ namespace {
 // Up to kSmallMaxN speakers the kernel is correct (tested to 128); it is SELECTED up to kSmallPickN:
 // one CTA per speaker serialises the speaker's M x N block, so its advantage over the five-kernel
 // pipeline shrinks with N -- 37 -> 9.1 us at the reference's test shape (N = 4, M = 8), 53 -> 19.9 us at its
-// training shape (cfg2, N = 64, M = 10; contrast: 30.8 -> 19.7 us; stage timeline: scripts/small_step_trace.py);
-// not measured beyond.
-constexpr int kSmallMaxN = 128, kSmallMaxM = 16, kSmallMaxD = 256, kSmallPickN = 64, kSmallPickNContrast = 64;
+// training shape (cfg2, N = 64, M = 10; contrast: 30.8 -> 19.7 us; stage timeline: scripts/small_step_trace.py),
+// 86 -> 32 us at N = 128, M = 10 (contrast 42 -> 32): selected wherever it is supported.
+constexpr int kSmallMaxN = 128, kSmallMaxM = 16, kSmallMaxD = 256, kSmallPickN = 128, kSmallPickNContrast = 128;
 constexpr size_t kSmallHeaderBytes = 256;
 
 struct SmallParams {

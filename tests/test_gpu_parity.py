@@ -568,7 +568,7 @@ def test_single_kernel_step_matches_oracle(pkg, N, M, D, variant):
     pkg.lib().ge2e_b200_debug_small_step(1)
     assert int(plan._ws[:256].max()) == 0                      # barrier counters restored
     default_plan = pkg.GE2EPlan(N, M, D, variant, "fp32", device=dev)
-    assert default_plan.single_kernel == (N <= 64)             # where it was measured faster (both variants)
+    assert default_plan.single_kernel                          # measured faster than the pipeline up to N = 128
 
 
 def test_single_kernel_step_in_a_graph_and_vs_pipeline(pkg):
