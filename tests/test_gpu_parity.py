@@ -536,7 +536,9 @@ def test_full_size_vs_reference_formulation_on_the_gpu(pkg, N, precision, tol):
 
 
 SMALL_SHAPES = [(4, 8, 256), (64, 10, 256), (3, 2, 64), (1, 5, 32), (128, 16, 256), (7, 3, 100), (16, 6, 30), (5, 4, 7),
-                (100, 10, 128)]
+                (100, 10, 128),
+                # fast path (D % 64 == 0) with odd M, every cluster size up to 8, D = 192, N just past the cluster limit
+                (6, 16, 192), (2, 3, 128), (8, 13, 256), (9, 5, 64), (33, 7, 64), (1, 2, 256)]
 
 
 @pytest.mark.parametrize("variant", ["softmax", "contrast"])
