@@ -257,6 +257,11 @@ size_t ge2e_b200_step_workspace_bytes(int N, int M, int D, int variant, int prec
  * Initial value 1.  Query sizes / launches AFTER setting it. */
 void ge2e_b200_debug_small_step(int mode);
 int ge2e_b200_step_launches(int N, int M, int D, int variant, int precision);
+/* The step's gradients for another upstream gradient: the loss is linear in it, so a step that ran with
+ * grad_out = 1 (what an eager `loss = crit(E)` does when it computes the whole step in its forward) is finished by
+ * dE_out[n] = g * dE_in[n], dwdb_out[2] = g * dwdb_in[2] -- one launch (`loss.backward()`, s4:200). */
+int ge2e_b200_scale_grads(const float* dE_in, float* dE_out, long long n, const float* dwdb_in, float* dwdb_out,
+                          const float* grad_out, ge2e_stream_t stream);
 int ge2e_b200_forward_backward(const float* E, const int32_t* row_index, int N, int M, int D, const float* w,
                                const float* b, float eps, int variant, int precision, const float* grad_out,
                                float* e_hat, float* c_hat, float* cos_diag, float* row_stat, int32_t* row_kstar,

@@ -80,6 +80,7 @@ PROTOTYPES = {
     "ge2e_b200_debug_small_step": (None, [C.c_int]),
     "ge2e_b200_step_workspace_bytes": (C.c_size_t, [C.c_int] * 5),
     "ge2e_b200_step_launches": (C.c_int, [C.c_int] * 5),
+    "ge2e_b200_scale_grads": (C.c_int, [_f32p, _f32p, C.c_longlong, _f32p, _f32p, _f32p, _stream]),
     "ge2e_b200_forward_backward": (C.c_int, [_f32p, _i32p, C.c_int, C.c_int, C.c_int, _f32p, _f32p, C.c_float, C.c_int,
                                              C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _i32p, _f32p, _f32p, _f32p,
                                              _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, _stream]),

@@ -469,6 +469,13 @@ int ge2e_b200_forward_backward(const float* E, const int32_t* row_index, int N, 
                            grad_out, dE, true, stream);
 }
 
+int ge2e_b200_scale_grads(const float* dE_in, float* dE_out, long long n, const float* dwdb_in, float* dwdb_out,
+                          const float* grad_out, ge2e_stream_t stream) {
+  if (!dE_in || !dE_out || !dwdb_in || !dwdb_out || !grad_out) return GE2E_ERR_ARGUMENT;
+  if (n < 1) return GE2E_ERR_SHAPE;
+  return simt_scale_grads(dE_in, dE_out, n, dwdb_in, dwdb_out, grad_out, (cudaStream_t)stream);
+}
+
 int ge2e_b200_centroids(const float* E, int N, int M, int D, float* C, ge2e_stream_t stream) {
   if (!E || !C) return GE2E_ERR_ARGUMENT;
   if (N <= 0 || M <= 0 || D <= 0) return GE2E_ERR_SHAPE;

@@ -148,6 +148,8 @@ int simt_small_step(const float* E, const int32_t* row_index, int N, int M, int 
                     float eps, int variant, const float* grad_out, float* e_hat, float* c_hat, float* cos_diag,
                     float* row_stat, int32_t* row_kstar, float* row_aux, float* per_row, float* loss_accum,
                     float* dE_hat, float* dC_hat, float* dwdb, float* dE, void* workspace, cudaStream_t st);
+int simt_scale_grads(const float* in, float* out, long long n, const float* dwdb_in, float* dwdb_out, const float* g,
+                     cudaStream_t st);
 int simt_scale_bias_sgd(float* w, float* b, float* dw, float* db, float max_norm, float lr, float* total_norm,
                         bool pdl, cudaStream_t st);
 int simt_threshold_counts(const float* sim, int N, int M, const float* thresholds, int T, long long* accept_all,

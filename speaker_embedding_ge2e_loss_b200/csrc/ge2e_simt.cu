@@ -2169,6 +2169,38 @@ __global__ void scale_bias_sgd_kernel(float* w, float* b, float* dw, float* db, 
   if (total_norm) *total_norm = total;
 }
 
+// Gradients of a step that ran with upstream gradient 1, scaled by the real one (the loss is linear in it):
+// out = g * in, {dw, db}_out = g * {dw, db}_in.  One launch; the eager module path's backward.
+__global__ void __launch_bounds__(256)
+scale_grads_kernel(const float* __restrict__ in, float* __restrict__ out, long long n, const float* __restrict__ dwdb_in,
+                   float* __restrict__ dwdb_out, const float* __restrict__ gp) {
+  pdl_wait();
+  const float g = __ldg(gp);
+  if (blockIdx.x == 0 && threadIdx.x < 2) dwdb_out[threadIdx.x] = g * dwdb_in[threadIdx.x];
+  const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    const float4* i4 = reinterpret_cast<const float4*>(in);
+    float4* o4 = reinterpret_cast<float4*>(out);
+    for (long long i = t0; i < (n >> 2); i += stride) {
+      float4 v = __ldcs(i4 + i);
+      v.x *= g; v.y *= g; v.z *= g; v.w *= g;
+      __stcs(o4 + i, v);
+    }
+  } else {
+    for (long long i = t0; i < n; i += stride) out[i] = g * in[i];
+  }
+}
+
+int simt_scale_grads(const float* in, float* out, long long n, const float* dwdb_in, float* dwdb_out, const float* g,
+                     cudaStream_t st) {
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  launch_pdl(scale_grads_kernel, dim3((unsigned)blocks), dim3(256), 0, st, true, in, out, n, dwdb_in, dwdb_out, g);
+  GE2E_LAUNCHED();
+  return GE2E_OK;
+}
+
 int simt_scale_bias_sgd(float* w, float* b, float* dw, float* db, float max_norm, float lr, float* total_norm,
                         bool pdl, cudaStream_t st) {
   launch_pdl(scale_bias_sgd_kernel, dim3(1), dim3(32), 0, st, pdl, w, b, dw, db, max_norm, lr, total_norm);

@@ -271,12 +271,12 @@ def _raw_stream(dev_index: int) -> int:
 
 class _StepBufs:
     __slots__ = ("flat", "kstar", "e_hat", "c_hat", "cos_diag", "row_stat", "row_aux", "dE_hat", "row_scale", "dC_hat",
-                 "fwd_ptrs", "plan", "pooled", "__weakref__")
+                 "fwd_ptrs", "step_ptrs", "plan", "pooled", "__weakref__")
 
     def __init__(self, plan, pooled: bool):
         N, M, D, U = plan.N, plan.M, plan.D, plan.U
         dev = plan.device
-        nh, ns = (U * D, U) if plan.fused else (0, 0)
+        ns = U                                  # row_scale: used by the tensor-core softmax paths, required by the ABI
         flat = torch.empty(2 * U * D + 2 * N * D + 3 * U + ns, dtype=torch.float32, device=dev)
         o = 0
 
@@ -291,15 +291,17 @@ class _StepBufs:
         self.dE_hat = take(U * D)              # forward (tensor-core softmax) or backward scratch
         self.dC_hat = take(N * D)
         self.cos_diag, self.row_stat, self.row_aux = take(U), take(U), take(U)
-        self.row_scale = take(ns) if ns else None
+        self.row_scale = take(ns)
         self.kstar = torch.empty(U if plan.variant == _lib.CONTRAST else 1, dtype=torch.int32, device=dev)
         self.plan, self.pooled = plan, pooled
         self.fwd_ptrs = (self.e_hat.data_ptr(), self.c_hat.data_ptr(), self.cos_diag.data_ptr(), self.row_stat.data_ptr(),
                          self.kstar.data_ptr(), self.row_aux.data_ptr())
+        self.step_ptrs = (*self.fwd_ptrs, self.row_scale.data_ptr())
 
 
 class _EagerPlan:
-    __slots__ = ("N", "M", "D", "U", "variant", "precision", "device", "dev_index", "path", "fused", "ws_bytes", "free")
+    __slots__ = ("N", "M", "D", "U", "variant", "precision", "device", "dev_index", "path", "fused", "ws_bytes", "free",
+                 "one", "free_on")
 
     def __init__(self, dev, N, M, D, variant, precision):
         self.N, self.M, self.D, self.U = N, M, D, N * M
@@ -308,8 +310,12 @@ class _EagerPlan:
         h = lib()
         self.path = h.ge2e_b200_path(N, N, M, D, variant, precision)
         self.fused = variant == _lib.SOFTMAX and self.path in (1, 2)
-        self.ws_bytes = h.ge2e_b200_workspace_bytes(N, N, M, D, variant, precision)
+        # the whole-step entry point (single-kernel step for reference-sized batches) may need more than the stages
+        self.ws_bytes = max(h.ge2e_b200_workspace_bytes(N, N, M, D, variant, precision),
+                            h.ge2e_b200_step_workspace_bytes(N, M, D, variant, precision))
         self.free = []
+        self.free_on = {}
+        self.one = torch.ones((), dtype=torch.float32, device=dev)      # upstream gradient of the step run in forward
 
     def take(self) -> _StepBufs:
         if torch.cuda.is_current_stream_capturing():
@@ -319,6 +325,22 @@ class _EagerPlan:
     def give(self, bufs: _StepBufs) -> None:
         if bufs.pooled and len(self.free) < 4:
             self.free.append(bufs)
+
+    def take_on(self, stream: int) -> _StepBufs:
+        """Scratch for a step whose every use is enqueued on `stream` before this returns to the caller: handed
+        back at once (give_on) and reused by the next step on the SAME stream, where stream order protects it."""
+        if torch.cuda.is_current_stream_capturing():
+            return _StepBufs(self, pooled=False)
+        q = self.free_on.get(stream)
+        return q.pop() if q else _StepBufs(self, pooled=True)
+
+    def give_on(self, bufs: _StepBufs, stream: int) -> None:
+        if bufs.pooled:
+            if len(self.free_on) > 8:
+                self.free_on.clear()
+            q = self.free_on.setdefault(stream, [])
+            if len(q) < 2:
+                q.append(bufs)
 
     def workspace(self, stream: int):
         if self.ws_bytes == 0:
@@ -384,12 +406,33 @@ class _GE2EEager(torch.autograd.Function):
         dev = E.device
         plan = _eager_plan(dev, N, M, D, variant, precision)
         want_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        if want_grad:
+            # A loss somebody will differentiate (s4:196 + s4:200): the WHOLE step now, with upstream gradient 1 --
+            # one C call: one kernel for reference-sized batches, prep + ONE persistent step kernel + finalize on
+            # the tensor-core paths (instead of a forward and a backward that each cross the grid) -- and backward
+            # only scales by the real upstream gradient.  A forward under grad mode that is never differentiated
+            # (s4:103) pays for gradients it does not use; wrap it in torch.no_grad() to get the forward kernels.
+            with _on_device(dev):
+                stream = _raw_stream(plan.dev_index)
+                bufs = plan.take_on(stream)
+                accum = torch.empty(4, dtype=torch.float32, device=dev)     # escapes as the loss tensor: never pooled
+                dE = torch.empty_like(E)
+                ws = plan.workspace(stream)
+                rc = lib().ge2e_b200_forward_backward(
+                    E.data_ptr(), _ptr(row_index), N, M, D, w.data_ptr(), b.data_ptr(), eps, variant, precision,
+                    plan.one.data_ptr(), *bufs.step_ptrs, accum.data_ptr(), bufs.dE_hat.data_ptr(), bufs.dC_hat.data_ptr(),
+                    dE.data_ptr(), _ptr(ws), plan.ws_bytes, stream)
+            _check(rc, "ge2e_b200_forward_backward")
+            plan.give_on(bufs, stream)  # the next step on this stream may overwrite them: stream order
+            ctx.lease = None
+            ctx.cfg = (plan, dE, accum)
+            return accum[0]
         with _on_device(dev):
             bufs = plan.take()
             accum = torch.empty(4, dtype=torch.float32, device=dev)     # escapes as the loss tensor: never pooled
             stream = _raw_stream(plan.dev_index)
             ws = plan.workspace(stream)
-            fused = plan.fused and want_grad
+            fused = False
             rc = lib().ge2e_b200_forward_indexed(
                 E.data_ptr(), _ptr(row_index), N, M, D, w.data_ptr(), b.data_ptr(), eps, variant, precision,
                 *bufs.fwd_ptrs, accum.data_ptr(), bufs.dE_hat.data_ptr() if fused else None,
@@ -402,6 +445,17 @@ class _GE2EEager(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_loss):
+        if len(ctx.cfg) == 3:           # the step ran in forward with upstream gradient 1: scale by the real one
+            plan, dE1, acc1 = ctx.cfg
+            dev = dE1.device
+            g = g_loss if (g_loss.dtype == torch.float32 and g_loss.is_cuda) else g_loss.to(dev, torch.float32)
+            with _on_device(dev):
+                dE = torch.empty_like(dE1)
+                dwdb = torch.empty(2, dtype=torch.float32, device=dev)      # escapes as dw / db
+                rc = lib().ge2e_b200_scale_grads(dE1.data_ptr(), dE.data_ptr(), dE1.numel(), acc1.data_ptr() + 4,
+                                                 dwdb.data_ptr(), g.data_ptr(), _raw_stream(plan.dev_index))
+            _check(rc, "ge2e_b200_scale_grads")
+            return dE, dwdb[0], dwdb[1], None, None, None, None, None
         E, w, b = ctx.saved_tensors
         eps, variant, precision, plan, fused, row_index, N, M, D = ctx.cfg
         bufs = ctx.lease.bufs
