@@ -1493,7 +1493,9 @@ int tc_debug_step_schedule(int u_local, int n_total, int cg, int max_clusters, i
 bool tc_supported(int n_local, int n_total, int M, int D, int variant) {
   (void)variant;
   if (D % kSlabCols != 0 || D < kSlabCols || D > kMaxSlabs * kSlabCols) return false;
-  if (n_total < 256 || static_cast<long long>(n_local) * M < 256) return false;
+  // up to 128 speakers the single-kernel SIMT step is faster (32 us at N = 128, M = 10 against 57 / 40 us here);
+  // from 129 on these kernels win (N = 129..255: 57 us split / 40 us TF32 against 94..152 us on the SIMT pipeline)
+  if (n_total < 129 || static_cast<long long>(n_local) * M < 256) return false;
   return get_encode() != nullptr;
 }
 

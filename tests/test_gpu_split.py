@@ -63,6 +63,7 @@ def test_which_shapes_take_the_split_path(pkg):
     assert h.ge2e_b200_path(1024, 1024, 10, 256, 1, 2) < 0           # contrast: SIMT backward reads fp32 operands
     assert h.ge2e_b200_path(1024, 1024, 10, 192, 0, 2) < 0           # D = 128 / 256 only
     assert h.ge2e_b200_path(64, 64, 10, 256, 0, 2) < 0               # reference-sized batches stay on the SIMT step
+    assert h.ge2e_b200_path(128, 128, 10, 256, 0, 2) < 0 and h.ge2e_b200_path(129, 129, 10, 256, 0, 2) == 2
     from speaker_embedding_ge2e_loss_b200 import _lib
     assert _lib.resolve_precision("fp32", 1024, 1024, 10, 256, 0) == _lib.FP32_SPLIT
     assert _lib.resolve_precision("fp32", 64, 64, 10, 256, 0) == _lib.FP32
@@ -78,6 +79,8 @@ CASES = [
     (700, 9, 256, "random"),
     (2048, 2, 128, "clustered"),       # M = 2: the leave-one-out centroid is the other utterance
     (256, 20, 256, "clustered"),
+    (129, 10, 256, "clustered"),       # first speaker count past the single-kernel step: two stream units, one nearly empty
+    (200, 3, 128, "random"),
 ]
 
 

@@ -83,7 +83,7 @@ def test_torch_oracle_on_device_matches_numpy_oracle(variant):
 STEP_CASES = [
     (300, 7, 64, "clustered"), (257, 5, 128, "clustered"), (700, 9, 256, "random"), (2048, 2, 256, "clustered"),
     (513, 3, 32, "random"), (1024, 10, 256, "clustered"), (256, 20, 256, "clustered"), (260, 40, 128, "random"),
-    (4096, 1 + 1, 96, "random"),
+    (4096, 1 + 1, 96, "random"), (129, 10, 256, "clustered"), (200, 5, 64, "random"),
 ]
 
 
