@@ -305,7 +305,7 @@ def stage_times(plan, E, w, b, flush_buf, reps=20):
     s = torch.cuda.current_stream().cuda_stream
     ws = plan._ws.data_ptr() if plan._ws_bytes else None
     acc = plan._accum.data_ptr()
-    scaled = plan.path in (1, 2) and plan.variant == 0
+    scaled = plan.path in (1, 2, 3) and plan.variant == 0
     calls = {
         "prep": lambda: h.ge2e_b200_prep(E.data_ptr(), N, M, D, plan.precision, plan.e_hat.data_ptr(),
                                          plan.c_hat.data_ptr(), plan.cos_diag.data_ptr(), acc, s),
@@ -560,7 +560,7 @@ def run_ours(args):
         flops = 6.0 * U * N * D
         kern_all = []
         kern_us = step_kernel_in_situ(plan, batches, w, b, max(10, args.steps), max(3, args.warmup),
-                                      all_out=kern_all) if path in (1, 2) else None
+                                      all_out=kern_all) if path in (1, 2, 3) else None
         if kern_us is not None and path == 2:
             dom, how = "tc_strip_kernel<STEP, split fp16 planes> (dE_hat pass + dC_hat pass; the rows were closed by the forward kernel before it)", \
                 "in situ: max(CTA end) - min(CTA start) of the kernel's %globaltimer stamps in the last step of a graph replay"
@@ -584,6 +584,9 @@ def run_ours(args):
             key = "bf16_tflops" if wl != "cfg4" else "bf16_tflops_sustained"
             peak, peak_note = peaks[key] / 3, (f"MEASURED_PEAKS {key}/3: an fp32-class product is three fp16 MMAs "
                                                f"(hi.hi + hi.lo + lo.hi) at the bf16 rate, {peaks['source']}")
+        elif path == 3:
+            key = "bf16_tflops" if wl != "cfg4" else "bf16_tflops_sustained"
+            peak, peak_note = peaks[key], f"MEASURED_PEAKS {key} (fp16 operands run at the bf16 rate), {peaks['source']}"
         else:
             peak, peak_note = 148 * 128 * 2 * 1.965e9 / 1e12, "nominal fp32 FMA 148 SM x 128 lanes x 2 x 1.965 GHz (SIMT path; no measured entry)"
         roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -819,11 +822,11 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
-        "dtype": "tf32" if path == 1 else ("f16x2-split (fp32-class)" if path == 2 else "f32"),
+        "dtype": {1: "tf32", 2: "f16x2-split (fp32-class)", 3: "f16"}.get(path, "f32"),
         "data": "synthetic unit-norm random embeddings",
         "config": config_of(wl, N, M, D, args.variant),
         "run": {"precision": args.precision,
-                "path": {1: "tcgen05-tf32", 2: "tcgen05 split fp16 planes"}.get(path, "simt-fp32"),
+                "path": {1: "tcgen05-tf32", 2: "tcgen05 split fp16 planes", 3: "tcgen05 fp16 operands"}.get(path, "simt-fp32"),
                 "parallelism": "replica" if world == 1 else f"speakers sharded x{world} (all-gather c_hat, reduce-scatter dC_hat)",
                 "l2": (f"inputs larger than L2: the step rotates over {n_rot} batches ({n_rot * U * D * 4 / 1e6:.0f} MB), "
                        "no flush") if world == 1 else sharded_how,
@@ -875,7 +878,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32", "fp32_simt", "fp32_split"])
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32", "fp32_simt", "fp32_split", "f16"])
     ap.add_argument("--variant", default="softmax", choices=["softmax", "contrast"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -59,7 +59,11 @@ enum ge2e_variant { GE2E_SOFTMAX = 0, GE2E_CONTRAST = 1 }; /* paper eq. (6) / eq
  *            planes.  Softmax variant, D = 128 or 256, shapes of the tensor-core path only; unlike GE2E_TF32
  *            this is a demand: an uncovered (shape, variant) returns GE2E_ERR_UNSUPPORTED -- ask
  *            ge2e_b200_path() first and fall back to GE2E_FP32. */
-enum ge2e_precision { GE2E_FP32 = 0, GE2E_TF32 = 1, GE2E_FP32_SPLIT = 2 };
+/* GE2E_F16:  the hi plane of GE2E_FP32_SPLIT alone: fp16 operands carry the same 11-bit mantissa as TF32 (the
+ *            stated tolerance stays 2e-3) at twice its MMA rate, one MMA per product; same kernels, same
+ *            row-closing order and the same shape rules as GE2E_FP32_SPLIT (a demand, too).  It pays where the MMAs
+ *            dominate (config 4 and its shards); at config 3 the extra forward launch costs more than it saves. */
+enum ge2e_precision { GE2E_FP32 = 0, GE2E_TF32 = 1, GE2E_FP32_SPLIT = 2, GE2E_F16 = 3 };
 
 int ge2e_b200_version(void);
 const char* ge2e_b200_strerror(int status);
@@ -68,7 +72,8 @@ int ge2e_b200_last_cuda_error(void);
 /* Number of kernels this library has launched (host-side count, all threads). */
 unsigned long long ge2e_b200_launch_count(void);
 /* Which kernels a (shape, variant, precision) uses: 0 = SIMT fp32 FMA, 1 = tcgen05 TF32, 2 = tcgen05 split
- * fp16 planes (GE2E_FP32_SPLIT; GE2E_ERR_UNSUPPORTED when the shape / variant is not covered).
+ * fp16 planes (GE2E_FP32_SPLIT), 3 = tcgen05 one fp16 plane (GE2E_F16); the last two answer
+ * GE2E_ERR_UNSUPPORTED when the shape / variant is not covered.
  * GE2E_TF32 is a permission, not a demand: shapes the tensor-core path does not cover run on
  * the (more accurate) SIMT kernels.  Negative = bad variant / precision. */
 int ge2e_b200_path(int n_local, int n_total, int M, int D, int variant, int precision);

@@ -11,12 +11,14 @@ _i32p = C.c_void_p
 _stream = C.c_void_p
 
 SOFTMAX, CONTRAST = 0, 1
-FP32, TF32, FP32_SPLIT = 0, 1, 2
+FP32, TF32, FP32_SPLIT, F16 = 0, 1, 2, 3
 VARIANTS = {"softmax": SOFTMAX, "contrast": CONTRAST}
 # "fp32" (the default, the reference's arithmetic) means fp32-class results: on the tensor cores through the
 # split-fp16 operand mode where the shape is covered (resolve_precision), else the SIMT fp32 FMA kernels.
 # "fp32_simt" / "fp32_split" pin one of the two.
-PRECISIONS = {"fp32": FP32, "tf32": TF32, "fp32_simt": FP32, "fp32_split": FP32_SPLIT}
+# "f16": the 2e-3 tolerance class with fp16 operands instead of TF32 (same 11-bit mantissa, twice the MMA rate:
+# GE2E_F16).  Opt-in: it wins only where the MMAs dominate (config 4 on one GPU: 1.12x).
+PRECISIONS = {"fp32": FP32, "tf32": TF32, "fp32_simt": FP32, "fp32_split": FP32_SPLIT, "tf32_mma": TF32, "f16": F16}
 
 
 def resolve_precision(name: str, n_local: int, n_total: int, M: int, D: int, variant: int) -> int:
@@ -26,6 +28,8 @@ def resolve_precision(name: str, n_local: int, n_total: int, M: int, D: int, var
         raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
     if name == "fp32" and lib().ge2e_b200_path(n_local, n_total, M, D, variant, FP32_SPLIT) == 2:
         return FP32_SPLIT
+    if name == "f16" and lib().ge2e_b200_path(n_local, n_total, M, D, variant, F16) != 3:
+        return TF32           # shapes the fp16-operand kernels do not cover: the TF32 permission
     return PRECISIONS[name]
 
 # name -> (restype, argtypes); kept in the order of include/ge2e_b200.h

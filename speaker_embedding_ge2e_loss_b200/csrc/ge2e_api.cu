@@ -27,17 +27,23 @@ int check_shape(int n_local, int n_total, int spk_offset, int M, int D) {
 
 int check_enum(int variant, int precision) {
   if (variant != GE2E_SOFTMAX && variant != GE2E_CONTRAST) return GE2E_ERR_ARGUMENT;
-  if (precision != GE2E_FP32 && precision != GE2E_TF32 && precision != GE2E_FP32_SPLIT) return GE2E_ERR_ARGUMENT;
+  if (precision != GE2E_FP32 && precision != GE2E_TF32 && precision != GE2E_FP32_SPLIT && precision != GE2E_F16)
+    return GE2E_ERR_ARGUMENT;
   return GE2E_OK;
 }
 
 // (shape, variant, precision) runs on the tensor-core kernels.  GE2E_TF32 is a permission (uncovered shapes run
 // on the SIMT kernels, same operand layout); GE2E_FP32_SPLIT is a demand, because its operand layout (two fp16
 // planes) is only understood by the tensor-core kernels: callers check ge2e_b200_path() first.
+// fp16 operand planes (a demand, see above): GE2E_FP32_SPLIT (two planes, fp32-class) and GE2E_F16 (one plane)
+bool is_planes(int precision) { return precision == GE2E_FP32_SPLIT || precision == GE2E_F16; }
+// operand precision code of the tensor-core launchers (ge2e_common.cuh): 0 TF32, 1 split planes, 2 one plane
+int tc_prec(int precision) { return precision == GE2E_FP32_SPLIT ? 1 : (precision == GE2E_F16 ? 2 : 0); }
+
 bool on_tc(int n_local, int n_total, int M, int D, int variant, int precision) {
   if (n_local <= 0 || n_total <= 0 || M < 2 || D <= 0) return false;
   if (precision == GE2E_TF32) return tc_supported(n_local, n_total, M, D, variant);
-  if (precision == GE2E_FP32_SPLIT) return tc_split_supported(n_local, n_total, M, D, variant);
+  if (is_planes(precision)) return tc_split_supported(n_local, n_total, M, D, variant);
   return false;
 }
 
@@ -77,7 +83,7 @@ int ge2e_b200_debug_step_schedule(int u_local, int n_total, int cta_group, int m
 
 int ge2e_b200_path(int n_local, int n_total, int M, int D, int variant, int precision) {
   if (check_enum(variant, precision) != GE2E_OK) return GE2E_ERR_ARGUMENT;
-  if (precision == GE2E_FP32_SPLIT) return on_tc(n_local, n_total, M, D, variant, precision) ? 2 : GE2E_ERR_UNSUPPORTED;
+  if (is_planes(precision)) return on_tc(n_local, n_total, M, D, variant, precision) ? precision : GE2E_ERR_UNSUPPORTED;
   return on_tc(n_local, n_total, M, D, variant, precision) ? 1 : 0;
 }
 
@@ -123,21 +129,21 @@ static int fwd_rows_impl(const float* e_hat, const float* c_hat_all, const float
   if (variant == GE2E_CONTRAST && !row_kstar) return GE2E_ERR_ARGUMENT;
   if (variant == GE2E_SOFTMAX && !row_aux) return GE2E_ERR_ARGUMENT;
   RowsArgs a{e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, b, eps, variant};
-  if (precision == GE2E_FP32_SPLIT && !on_tc(n_local, n_total, M, D, variant, precision)) return GE2E_ERR_UNSUPPORTED;
+  if (is_planes(precision) && !on_tc(n_local, n_total, M, D, variant, precision)) return GE2E_ERR_UNSUPPORTED;
   if (on_tc(n_local, n_total, M, D, variant, precision)) {
     // the tensor-core path never materialises S: sim_out is an fp32-path feature
     if (sim_out != nullptr) return GE2E_ERR_UNSUPPORTED;
     if (workspace_bytes < tc_workspace_bytes(n_local, n_total, M, D, variant) ||
         (workspace == nullptr && tc_workspace_bytes(n_local, n_total, M, D, variant) > 0))
       return GE2E_ERR_WORKSPACE;
-    if (precision == GE2E_FP32_SPLIT) {
+    if (is_planes(precision)) {
       // the forward kernel closes the rows; with a backward to follow, the rows pass of the step kernel then
       // forms dE_hat from probabilities that are already normalised (see ge2e_tc.cu, PREC_SPLIT)
       rc = tc_fwd_rows(a, row_stat, row_kstar, row_aux, loss_accum, per_row_out, workspace, workspace_bytes, after_prep,
-                       (cudaStream_t)stream, true);
+                       (cudaStream_t)stream, tc_prec(precision));
       if (rc != GE2E_OK || dE_hat == nullptr || row_scale == nullptr) return rc;
       return tc_step(a, 1, nullptr, row_stat, row_aux, nullptr, nullptr, row_scale, nullptr, nullptr, dE_hat, nullptr,
-                     nullptr, workspace, workspace_bytes, (cudaStream_t)stream, nullptr, 0, true);
+                     nullptr, workspace, workspace_bytes, (cudaStream_t)stream, nullptr, 0, tc_prec(precision));
     }
     // softmax with a backward to follow: the rows pass of the step kernel (loss + un-normalised dE_hat)
     if (variant == GE2E_SOFTMAX && dE_hat != nullptr && row_scale != nullptr)
@@ -180,7 +186,7 @@ int ge2e_b200_bwd_rows(const float* e_hat, const float* c_hat_all, const float* 
   // the contrast gradient is a 2-nonzeros-per-row gather/scatter: no contraction to put on
   // tensor cores, so both precisions share the SIMT kernel.  Softmax on tensor cores: the forward's rows
   // pass already left the un-normalised dE_hat (row_scale says so); only the centroid pass remains.
-  if (precision == GE2E_FP32_SPLIT && (!on_tc(n_local, n_total, M, D, variant, precision) || row_scale == nullptr))
+  if (is_planes(precision) && (!on_tc(n_local, n_total, M, D, variant, precision) || row_scale == nullptr))
     return GE2E_ERR_UNSUPPORTED;
   if (variant == GE2E_SOFTMAX && row_scale != nullptr && on_tc(n_local, n_total, M, D, variant, precision)) {
     if (workspace_bytes < tc_workspace_bytes(n_local, n_total, M, D, variant) ||
@@ -188,7 +194,7 @@ int ge2e_b200_bwd_rows(const float* e_hat, const float* c_hat_all, const float* 
       return GE2E_ERR_WORKSPACE;
     return tc_step(a, 2, grad_out, row_stat, row_aux, nullptr, nullptr, nullptr, nullptr, nullptr, dE_hat,
                    dC_hat_partial, dwdb_accum, workspace, workspace_bytes, (cudaStream_t)stream, nullptr, 0,
-                   precision == GE2E_FP32_SPLIT);
+                   tc_prec(precision));
   }
   return simt_bwd_rows(a, row_stat, row_kstar, row_aux, grad_out, dE_hat, dC_hat_partial, dwdb_accum,
                        (cudaStream_t)stream);
@@ -356,18 +362,18 @@ int ge2e_b200_step_rows(const float* e_hat, const float* c_hat_all, const float*
   if (tc_softmax_step(n_local, n_total, M, D, variant, precision)) {
     // ONE launch: rows pass, grid-wide barrier, centroid pass ({loss, dw, db} += into accum: zeroed by prep)
     RowsArgs a{e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, b, eps, variant};
-    if (precision == GE2E_FP32_SPLIT) {
+    if (is_planes(precision)) {
       // two launches: the forward kernel closes the rows (loss, lse, q), the step kernel runs both passes on them
       rc = tc_fwd_rows(a, row_stat, row_kstar, row_aux, accum, nullptr, workspace, workspace_bytes, true,
-                       (cudaStream_t)stream, true);
+                       (cudaStream_t)stream, tc_prec(precision));
       if (rc != GE2E_OK) return rc;
       return tc_step(a, 3, grad_out, row_stat, row_aux, nullptr, nullptr, row_scale, nullptr, nullptr, dE_hat,
-                     dC_hat_partial, accum + 1, workspace, workspace_bytes, (cudaStream_t)stream, nullptr, 0, true);
+                     dC_hat_partial, accum + 1, workspace, workspace_bytes, (cudaStream_t)stream, nullptr, 0, tc_prec(precision));
     }
     return tc_step(a, 3, grad_out, nullptr, nullptr, row_stat, row_aux, row_scale, accum, nullptr, dE_hat,
                    dC_hat_partial, accum + 1, workspace, workspace_bytes, (cudaStream_t)stream);
   }
-  if (precision == GE2E_FP32_SPLIT) return GE2E_ERR_UNSUPPORTED;
+  if (is_planes(precision)) return GE2E_ERR_UNSUPPORTED;
   rc = fwd_rows_impl(e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, b, eps, variant, precision,
                      row_stat, row_kstar, row_aux, accum, nullptr, nullptr, nullptr, nullptr, workspace, workspace_bytes,
                      true, stream);
@@ -406,12 +412,12 @@ int ge2e_b200_step_rows_peers(const float* e_hat, const float* c_hat_all, const 
   // only the tensor-core softmax step flushes through peer memory; everything else keeps the reduce-scatter
   if (!tc_softmax_step(n_local, n_total, M, D, variant, precision)) return GE2E_ERR_UNSUPPORTED;
   RowsArgs a{e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, b, eps, variant};
-  if (precision == GE2E_FP32_SPLIT) {
+  if (is_planes(precision)) {
     rc = tc_fwd_rows(a, row_stat, row_kstar, row_aux, accum, nullptr, workspace, workspace_bytes, true,
-                     (cudaStream_t)stream, true);
+                     (cudaStream_t)stream, tc_prec(precision));
     if (rc != GE2E_OK) return rc;
     return tc_step(a, 3, grad_out, row_stat, row_aux, nullptr, nullptr, row_scale, nullptr, nullptr, dE_hat, nullptr,
-                   accum + 1, workspace, workspace_bytes, (cudaStream_t)stream, dC_owner_host, n_ranks, true);
+                   accum + 1, workspace, workspace_bytes, (cudaStream_t)stream, dC_owner_host, n_ranks, tc_prec(precision));
   }
   return tc_step(a, 3, grad_out, nullptr, nullptr, row_stat, row_aux, row_scale, accum, nullptr, dE_hat, nullptr,
                  accum + 1, workspace, workspace_bytes, (cudaStream_t)stream, dC_owner_host, n_ranks);

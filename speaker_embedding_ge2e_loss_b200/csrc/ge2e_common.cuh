@@ -125,7 +125,7 @@ struct RowsArgs {
 };
 
 // row_index (nullable): logical row r = [speaker][utterance] lives at physical row row_index[r] of E / dE
-// prec: 0 = fp32 operands as they are, 1 = rounded to TF32, 2 = two fp16 planes [rows][2][D] (hi, lo) in the
+// prec: 0 = fp32 operands as they are, 1 = rounded to TF32, 3 = the hi plane of 2 alone, 2 = two fp16 planes [rows][2][D] (hi, lo) in the
 // same allocation (D = 128 / 256 / 512 only)
 int simt_prep(const float* E, const int32_t* row_index, int n_local, int M, int D, int prec, float* e_hat,
               float* c_hat_local, float* cos_diag, float* accum, cudaStream_t st);
@@ -184,7 +184,7 @@ int tc_debug_step_schedule(int u_local, int n_total, int cg, int max_clusters, i
 size_t tc_workspace_bytes(int n_local, int n_total, int M, int D, int variant);
 int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* row_aux,
                 float* loss_accum, float* per_row_out, void* ws, size_t ws_bytes, bool after_prep,
-                cudaStream_t st, bool split = false);
+                cudaStream_t st, int prec = 0 /* 0 TF32, 1 split fp16 planes, 2 one fp16 plane */);
 // softmax step on tensor cores; phases: 1 = rows pass (loss, row statistics, un-normalised dE_hat + row_scale),
 // 2 = centroid pass (dC_hat_partial, {dw, db}), 3 = both in one launch
 // dC_owner (nullable, HOST array of n_ranks device pointers): speaker-sharded over peer memory -- pass 2 adds its
@@ -192,7 +192,7 @@ int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* r
 int tc_step(const RowsArgs& a, int phases, const float* grad_out, const float* row_stat_in, const float* row_aux_in,
             float* row_stat, float* row_aux, float* row_scale, float* loss_accum, float* per_row_out, float* dE_hat,
             float* dC_hat_partial, float* dwdb_accum, void* ws, size_t ws_bytes, cudaStream_t st,
-            float* const* dC_owner = nullptr, int n_ranks = 0, bool split = false);
+            float* const* dC_owner = nullptr, int n_ranks = 0, int prec = 0);
 int simt_peer_publish(const float* src, float* const* dst, int n_dst, bool multicast, long long n_floats, float* zero,
                       long long zero_floats, cudaStream_t st);
 

@@ -184,7 +184,13 @@ prep_kernel(const float* __restrict__ E, const int32_t* __restrict__ idx, int M,
 // mode: hi.hi + hi.lo + lo.hi reproduces the fp32 product to ~2^-22).  put4 stores columns [col, col + 4) of `row`.
 template <int PREC>
 __device__ __forceinline__ void put4(float* base, size_t row, int D, int col, float4 v) {
-  if (PREC == 2) {
+  if (PREC == 3) {          // the hi plane alone (fp16 operands of the TF32-tolerance class)
+    __half* h = reinterpret_cast<__half*>(base);
+    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    uint2 hi;
+    hi.x = *reinterpret_cast<const uint32_t*>(&h0); hi.y = *reinterpret_cast<const uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(h + row * 2 * D + col) = hi;
+  } else if (PREC == 2) {
     __half* h = reinterpret_cast<__half*>(base);
     const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
     const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
@@ -1317,14 +1323,17 @@ void launch_prep_warp(const float* E, const int32_t* idx, int n_local, int M, in
     constexpr int K2 = KCH <= 2 ? KCH : 1;    // the register-resident variant is only instantiated for D <= 256
     const dim3 g(grid), bl(kPrepWarps * 32);
 #define GE2E_PREP_REG(RR)                                                                                          \
-  (prec == 2 ? launch_pdl(prep_reg_kernel<K2, RR, 2>, g, bl, 0, st, true, E, idx, n_local, M, e_hat, c_hat, cos_diag, accum) \
+  (prec == 3 ? launch_pdl(prep_reg_kernel<K2, RR, 3>, g, bl, 0, st, true, E, idx, n_local, M, e_hat, c_hat, cos_diag, accum) \
+   : prec == 2 ? launch_pdl(prep_reg_kernel<K2, RR, 2>, g, bl, 0, st, true, E, idx, n_local, M, e_hat, c_hat, cos_diag, accum) \
    : prec == 1 ? launch_pdl(prep_reg_kernel<K2, RR, 1>, g, bl, 0, st, true, E, idx, n_local, M, e_hat, c_hat, cos_diag, accum) \
                : launch_pdl(prep_reg_kernel<K2, RR, 0>, g, bl, 0, st, true, E, idx, n_local, M, e_hat, c_hat, cos_diag, accum))
     if (M <= 4) GE2E_PREP_REG(4); else if (M <= 8) GE2E_PREP_REG(8); else if (M <= 12) GE2E_PREP_REG(12); else GE2E_PREP_REG(16);
 #undef GE2E_PREP_REG
     return;
   }
-  if (prec == 2) launch_pdl(prep_warp_kernel<KCH, 2>, dim3(grid), dim3(kPrepWarps * 32), 0, st, true, E, idx, n_local, M,
+  if (prec == 3) launch_pdl(prep_warp_kernel<KCH, 3>, dim3(grid), dim3(kPrepWarps * 32), 0, st, true, E, idx, n_local, M,
+                            e_hat, c_hat, cos_diag, accum);
+  else if (prec == 2) launch_pdl(prep_warp_kernel<KCH, 2>, dim3(grid), dim3(kPrepWarps * 32), 0, st, true, E, idx, n_local, M,
                             e_hat, c_hat, cos_diag, accum);
   else if (prec == 1) launch_pdl(prep_warp_kernel<KCH, 1>, dim3(grid), dim3(kPrepWarps * 32), 0, st, true, E, idx, n_local,
                                  M, e_hat, c_hat, cos_diag, accum);
@@ -1361,7 +1370,7 @@ int simt_prep(const float* E, const int32_t* row_index, int n_local, int M, int 
     GE2E_LAUNCHED();
     return GE2E_OK;
   }
-  if (prec == 2) return GE2E_ERR_UNSUPPORTED;     // the fp16 planes are written by the warp kernels only
+  if (prec >= 2) return GE2E_ERR_UNSUPPORTED;     // the fp16 planes are written by the warp kernels only
   const int Dp = (D + 3) & ~3;
   const size_t smem = (size_t)(M + 1) * Dp * sizeof(float);
   if (smem > 200 * 1024) return GE2E_ERR_UNSUPPORTED;

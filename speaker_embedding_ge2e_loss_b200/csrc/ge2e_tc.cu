@@ -82,7 +82,9 @@ constexpr float kLn2 = 0.6931471805599453f;
 enum { TC_FWD = 0, TC_STEP = 1 };
 // operand precision: TF32 (one rounded fp32 plane) or SPLIT (fp32-class: every operand as two fp16 planes
 // hi = fp16(x), lo = fp16(x - hi); a product is the three kind::f16 MMAs hi.hi + hi.lo + lo.hi)
-enum { PREC_TF32 = 0, PREC_SPLIT = 1 };
+// F16: ONE fp16 plane (hi only): 11-bit mantissas as TF32, twice its MMA rate -- the TF32-tolerance class for the
+// shapes where the MMAs dominate (same kernels and row-closing order as SPLIT, one MMA per product)
+enum { PREC_TF32 = 0, PREC_SPLIT = 1, PREC_F16 = 2 };
 // The probability planes carry p * 2^(14 + k): 2^14 keeps p <= 1 inside fp16, and k >= 0 lifts what is known to
 // be small -- pass 1: k_r from q_r = 1 - p_jj >= every off-diagonal probability of utterance row r (per owner
 // row, undone by row_scale); pass 2: k from the largest q of the whole batch (undone in the accumulator flush).
@@ -130,7 +132,8 @@ struct StepSched {
 };
 
 struct TcParams {
-  int D, kslabs;
+  int D, kslabs;              // kslabs = D / 32: 32-column fp32 slabs of an accumulator tile (and of a TF32 operand tile)
+  int oslabs;                 // 128-byte slabs of an OPERAND tile: D / 32 (TF32), 2 D / 64 (SPLIT), D / 64 (F16)
   int M, spk_offset;
   int n_own[2], n_str[2];     // rows of the owner / stream matrix per segment kind
   int OT[2], ST[2];           // owner tiles, stream units
@@ -266,7 +269,12 @@ __global__ void __launch_bounds__(kThreadsTc, 1)
 tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepSched sched, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr bool kBwd = (MODE != TC_FWD);
-  constexpr bool kSplit = (PREC == PREC_SPLIT);
+  constexpr bool kSplit = (PREC != PREC_TF32);      // fp16 operand planes, rows closed by the forward kernel
+  constexpr int kPlanes = (PREC == PREC_SPLIT) ? 2 : 1;
+  // stream rows (K of MMA2) per ring stage: a stage is 16 KB per CTA of a pair either way -- 32 rows of fp32 or of
+  // two fp16 planes, 64 rows of ONE fp16 plane (with 32 the stages would be half empty and the ring would hold
+  // barely one unit of look-ahead: the F16 kernel ran load-latency-bound)
+  constexpr int kM2 = (PREC == PREC_F16) ? 64 : kMma2Rows;
   constexpr int kStageBytes = 32768 / CG;
   constexpr int kStages = 3 * CG;
   constexpr uint16_t kPairMask = (CG == 2) ? 3 : 1;
@@ -288,9 +296,9 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
   const bool leader = (cr == 0);
   // barriers the MMA warp waits on live in the leader: address them through the cluster window
   auto lbar = [&](int i) { return (CG == 2) ? mapa(bar(i), 0) : bar(i); };
-  const int kslabs = p.kslabs;
-  // SPLIT: slab s of an operand tile is [rows x 64 fp16] = chunk s % hs of plane s / hs (hi plane first)
-  const int hs = kslabs >> 1;
+  const int kslabs = p.kslabs, oslabs = p.oslabs;
+  // fp16 planes: slab s of an operand tile is [rows x 64 fp16] = chunk s % hs of plane s / hs (hi plane first)
+  const int hs = p.D >> 6;
   const int dbg = DBG ? p.dbg : 0;      // compile-time 0 in the production instantiation
 
   if (warp == 0 && lane == 0) {
@@ -383,8 +391,8 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
     auto load_mn = [&](const CUtensorMap* tm, int row0) {
       mbar_wait(bar(BAR_EMPTY + stage), phase ^ 1);
       if (elect_one()) {
-        const int slabs_c = kslabs / CG;
-        const uint32_t bytes = static_cast<uint32_t>(slabs_c * kMma2Rows * 128);
+        const int slabs_c = oslabs / CG;
+        const uint32_t bytes = static_cast<uint32_t>(slabs_c * kM2 * 128);
         if (leader) mbar_expect_tx(bar(BAR_FULL + stage), bytes * CG);
         const uint32_t full = lbar(BAR_FULL + stage);
         const uint32_t dst = ring_smem + stage * kStageBytes;
@@ -408,9 +416,9 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
       const int ot = og * CG + cr;      // may be >= OT in the last group: TMA zero-fills, nothing is stored
       if (sg > 0) mbar_wait(bar(BAR_A_EMPTY), (sg - 1) & 1);      // every MMA1 of the previous segment has completed
       tr.mark();   // owner tile issue
-      for (int i = 0; i < kslabs; ++i) {
+      for (int i = 0; i < oslabs; ++i) {
         // SPLIT: chunk c of the hi plane is first used together with chunk c of the lo plane
-        const int ks = kSplit ? (i & 1) * hs + (i >> 1) : i;
+        const int ks = (kPlanes == 2) ? (i & 1) * hs + (i >> 1) : i;
         // STEP: the previous segment's accumulator leaves through the owner area, slab by slab; slab ks is
         // free again once the TMA store that took it out has read it
         if (kBwd && sg > 0) mbar_wait(bar(BAR_A_FREE + ks), (sg - 1) & 1);
@@ -430,16 +438,16 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
       if (!kBwd) {
         for (int u = s0; u < s1; u += kStepUnits) {
           const int nu = min(kStepUnits, s1 - u);
-          for (int ks = 0; ks < kslabs; ++ks) load_k(tm_k, u * kUnit, nu * kUnit / CG, ks, 1);
+          for (int ks = 0; ks < oslabs; ++ks) load_k(tm_k, u * kUnit, nu * kUnit / CG, ks, 1);
         }
       } else {
         auto load_mma1_unit = [&](int u) {       // stages of two slabs, n = 128
-          for (int ks = 0; ks < kslabs; ks += 2) load_k(tm_k, u * kUnit, kUnit / CG, ks, min(2, kslabs - ks));
+          for (int ks = 0; ks < oslabs; ks += 2) load_k(tm_k, u * kUnit, kUnit / CG, ks, min(2, oslabs - ks));
         };
         load_mma1_unit(s0);
         for (int u = s0; u < s1; ++u) {
           if (u + 1 < s1) load_mma1_unit(u + 1);
-          for (int kc = 0; kc < kUnit / kMma2Rows; ++kc) load_mn(tm_mn, u * kUnit + kc * kMma2Rows);
+          for (int kc = 0; kc < kUnit / kM2; ++kc) load_mn(tm_mn, u * kUnit + kc * kM2);
         }
       }
       tr.mark();   // all loads of the segment issued
@@ -451,7 +459,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
       // descriptor templates: only the 14-bit start-address field changes per MMA
       const uint64_t dk = smem_desc(0, 16, 1024, kLayoutSw128);                        // K-major
       // MN-major: TF32 needs the 32-byte-atom swizzle (4-row groups), fp16 the plain 128B swizzle (8-row groups)
-      const uint64_t dmn = kSplit ? smem_desc(0, kMma2Rows * 128, 1024, kLayoutSw128)
+      const uint64_t dmn = kSplit ? smem_desc(0, kM2 * 128, 1024, kLayoutSw128)
                                   : smem_desc(0, kMma2Rows * 128, 512, kLayoutSw128Base32);
       int stage = 0, phase = 0, sg = 0, it = 0;
       Tracer<DBG> tr(lane == 0 ? p.trace : nullptr, 1);
@@ -487,7 +495,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
             for (int sl = 0; sl < nslab; ++sl) {
               const int s = ks0 + sl, c = s % hs;
               mbar_wait(bar(BAR_A_FULL + c), sg & 1);
-              if (s < hs) mbar_wait(bar(BAR_A_FULL + hs + c), sg & 1);
+              if (kPlanes == 2 && s < hs) mbar_wait(bar(BAR_A_FULL + hs + c), sg & 1);
             }
           }
           stage_wait();
@@ -498,7 +506,8 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
               const int s = ks0 + sl, c = s % hs;
               const uint64_t db = dk | ((ring_smem + stage * kStageBytes + sl * rows_cta * 128) >> 4);
               umma_f16_ss4<CG>(d_tmem, dk | ((a_smem + c * kSlabBytes) >> 4), db, idesc1, s != 0);
-              if (s < hs) umma_f16_ss4<CG>(d_tmem, dk | ((a_smem + (hs + c) * kSlabBytes) >> 4), db, idesc1, 1);
+              if (kPlanes == 2 && s < hs)
+                umma_f16_ss4<CG>(d_tmem, dk | ((a_smem + (hs + c) * kSlabBytes) >> 4), db, idesc1, 1);
             }
             commit(BAR_EMPTY + stage);
           }
@@ -525,17 +534,30 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
       const uint32_t idesc_unit = kSplit ? idesc_f16(kTile * CG, kUnit, 0, 0) : idesc_tf32(kTile * CG, kUnit, 0, 0);
       auto mma1_unit = [&](int iter, bool first_of_seg) {   // BWD: n = 128 into T[iter & 1]
         const uint32_t d_tmem = tmem + (iter & 1) * kUnit;
-        for (int ks = 0; ks < kslabs; ks += 2)
-          mma1_stage(d_tmem, idesc_unit, kUnit / CG, ks, min(2, kslabs - ks), first_of_seg);
+        for (int ks = 0; ks < oslabs; ks += 2)
+          mma1_stage(d_tmem, idesc_unit, kUnit / CG, ks, min(2, oslabs - ks), first_of_seg);
         if (elect_one()) commit(BAR_S_FULL + (iter & 1));
         __syncwarp();
       };
       auto mma2_unit = [&](int iter, bool first) {
         const uint32_t a_tmem = tmem + (iter & 1) * kUnit;
         const uint32_t d_tmem = tmem + 2 * kUnit;
-        for (int kc = 0; kc < kUnit / kMma2Rows; ++kc) {
+        for (int kc = 0; kc < kUnit / kM2; ++kc) {
           stage_wait();
           uint32_t probe = 0;
+          if (PREC == PREC_F16) {
+            if (elect_leader(leader)) {
+              probe = mbar_test(next_bar(), next_par());
+              // the stage's 64 stream rows are column half kc of T: 32 cells of packed fp16 pairs = 4 K steps
+              const uint32_t a_hi = a_tmem + 64 * kc;
+              const uint64_t db_hi = dmn | ((ring_smem + stage * kStageBytes) >> 4);
+              umma_f16_ts2<CG>(d_tmem, a_hi, db_hi, idesc2, !(first && kc == 0));
+              umma_f16_ts2<CG>(d_tmem, a_hi + 16, db_hi + 256, idesc2, 1);      // rows 32..63: 4096 bytes further
+              commit(BAR_EMPTY + stage);
+            }
+            stage_done(probe);
+            continue;
+          }
           if (kSplit) {
             if (elect_leader(leader)) {
               probe = mbar_test(next_bar(), next_par());
@@ -546,8 +568,10 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
               const uint64_t db_hi = dmn | (sb >> 4);
               const uint64_t db_lo = dmn | ((sb + (hs / CG) * kMma2Rows * 128) >> 4);
               umma_f16_ts2<CG>(d_tmem, a_hi, db_hi, idesc2, !(first && kc == 0));
-              umma_f16_ts2<CG>(d_tmem, a_hi, db_lo, idesc2, 1);
-              umma_f16_ts2<CG>(d_tmem, a_lo, db_hi, idesc2, 1);
+              if (kPlanes == 2) {
+                umma_f16_ts2<CG>(d_tmem, a_hi, db_lo, idesc2, 1);
+                umma_f16_ts2<CG>(d_tmem, a_lo, db_hi, idesc2, 1);
+              }
               commit(BAR_EMPTY + stage);
             }
             stage_done(probe);
@@ -575,7 +599,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
             const uint32_t d_tmem = tmem + (it & 1) * (kStepUnits * kUnit);
             const uint32_t idesc_step = kSplit ? idesc_f16(kTile * CG, nu * kUnit, 0, 0)
                                                : idesc_tf32(kTile * CG, nu * kUnit, 0, 0);
-            for (int ks = 0; ks < kslabs; ++ks) mma1_stage(d_tmem, idesc_step, nu * kUnit / CG, ks, 1, u == s0);
+            for (int ks = 0; ks < oslabs; ++ks) mma1_stage(d_tmem, idesc_step, nu * kUnit / CG, ks, 1, u == s0);
             if (elect_one()) commit(BAR_S_FULL + (it & 1));
             __syncwarp();
             tr.mark();   // step issued
@@ -847,7 +871,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
               }
             }
             tmem_st16(tb + 16 * c2, hi);
-            tmem_st16(tb + 32 + 16 * c2, lo);
+            if (kPlanes == 2) tmem_st16(tb + 32 + 16 * c2, lo);
           };
           plane_chunk(v0, 0);
           plane_chunk(v1, 1);
@@ -1211,7 +1235,7 @@ int make_map_3d(CUtensorMap* m, const float* base, int rows, int D, int box_slab
 // SPLIT operands: X as fp16 planes [rows][2][D] (a row's hi plane, then its lo plane, in the bytes of the fp32 row).
 // 3-D map {D, rows, plane}: box = [1][box_rows][64 cols] = one K-major slab of one plane, 128-byte swizzle.
 int make_map_h3(CUtensorMap* m, const void* base, int rows, int D, int box_rows) {
-  const MapKey key{base, rows, D, box_rows, 13};
+  const MapKey key{base, rows, D, box_rows, 15};
   if (map_lookup(key, m)) return GE2E_OK;
   auto enc = get_encode();
   if (enc == nullptr) return GE2E_ERR_LAUNCH;
@@ -1227,14 +1251,16 @@ int make_map_h3(CUtensorMap* m, const void* base, int rows, int D, int box_rows)
 }
 // 4-D map {64, rows, D/64, plane}: box = [2 planes][box_chunks][32 rows][64 cols] (MN-major operand of MMA2:
 // 32 k-rows x this CTA's columns, both planes, per ring stage); fp16 MN-major takes the plain 128B swizzle.
-int make_map_h4(CUtensorMap* m, const void* base, int rows, int D, int box_chunks) {
-  const MapKey key{base, rows, D, box_chunks, 14};
+int make_map_h4(CUtensorMap* m, const void* base, int rows, int D, int box_chunks, int planes) {
+  const int box_rows = planes == 1 ? 64 : kMma2Rows;      // see kM2 in the kernel
+  const MapKey key{base, rows, D, box_chunks, 12 + planes};
   if (map_lookup(key, m)) return GE2E_OK;
   auto enc = get_encode();
   if (enc == nullptr) return GE2E_ERR_LAUNCH;
   cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(D / 64), 2};
   cuuint64_t strides[3] = {static_cast<cuuint64_t>(D) * 4, 128, static_cast<cuuint64_t>(D) * 2};
-  cuuint32_t box[4] = {64, kMma2Rows, static_cast<cuuint32_t>(box_chunks), 2};
+  cuuint32_t box[4] = {64, static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(box_chunks),
+                       static_cast<cuuint32_t>(planes)};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1432,9 +1458,14 @@ int launch_tc(const TmSet& tms, const StepSched& sched, const TcParams& p, int N
   if (g_trace != nullptr) return launch_tc_impl<MODE, VARIANT, CG, PREC_TF32, true>(tms, sched, p, NC, pdl, st);
   return launch_tc_impl<MODE, VARIANT, CG, PREC_TF32, false>(tms, sched, p, NC, pdl, st);
 }
-// split precision: softmax, CTA pairs (D = 128 or 256), no instrumented twin
+// fp16 operand planes (prec = PREC_SPLIT / PREC_F16): softmax, CTA pairs (D = 128 or 256), no instrumented twin
 template <int MODE>
-int launch_tc_split(const TmSet& tms, const StepSched& sched, const TcParams& p, int NC, bool pdl, cudaStream_t st) {
+int launch_tc_split(int prec, const TmSet& tms, const StepSched& sched, const TcParams& p, int NC, bool pdl, cudaStream_t st) {
+  if (prec == PREC_F16) {
+    if (MODE == TC_STEP && g_trace != nullptr)      // instrumented twin of the step kernel (ge2e_b200_debug_trace)
+      return launch_tc_impl<MODE, GE2E_SOFTMAX, 2, PREC_F16, true>(tms, sched, p, NC, pdl, st);
+    return launch_tc_impl<MODE, GE2E_SOFTMAX, 2, PREC_F16, false>(tms, sched, p, NC, pdl, st);
+  }
   return launch_tc_impl<MODE, GE2E_SOFTMAX, 2, PREC_SPLIT, false>(tms, sched, p, NC, pdl, st);
 }
 
@@ -1450,7 +1481,7 @@ int launch_tc_cg(int cg, const TmSet& tms, const StepSched& sched, const TcParam
 }
 
 void fill_common(TcParams& p, const RowsArgs& a) {
-  p.D = a.D; p.kslabs = a.D / kSlabCols; p.M = a.M; p.spk_offset = a.spk_offset;
+  p.D = a.D; p.kslabs = a.D / kSlabCols; p.oslabs = p.kslabs; p.M = a.M; p.spk_offset = a.spk_offset;
   p.cos_diag = a.cos_diag; p.w = a.w; p.b = a.b; p.eps = a.eps;
 }
 
@@ -1512,8 +1543,9 @@ size_t tc_workspace_bytes(int n_local, int n_total, int M, int D, int variant) {
 }
 
 int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* row_aux, float* loss_accum,
-                float* per_row_out, void* ws, size_t ws_bytes, bool after_prep, cudaStream_t st, bool split) {
+                float* per_row_out, void* ws, size_t ws_bytes, bool after_prep, cudaStream_t st, int prec) {
   const int U = a.n_local * a.M;
+  const bool split = prec != PREC_TF32;         // fp16 operand planes
   if (split && !tc_split_supported(a.n_local, a.n_total, a.M, a.D, a.variant)) return GE2E_ERR_UNSUPPORTED;
   const Layout L = fwd_layout(U, a.n_total, a.D, a.variant);
   if (ws == nullptr || ws_bytes < kWsHeaderBytes + L.done_bytes + L.part_bytes) return GE2E_ERR_WORKSPACE;
@@ -1528,6 +1560,7 @@ int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* r
   }
   TcParams p{};
   fill_common(p, a);
+  if (split) p.oslabs = (prec == PREC_SPLIT ? 2 : 1) * (a.D / 64);
   p.n_own[0] = U; p.n_str[0] = a.n_total; p.OT[0] = L.OT; p.ST[0] = L.ST; p.GP = L.GP;
   p.row_stat_out = row_stat; p.kstar_out = row_kstar; p.row_aux_out = row_aux; p.loss_accum = loss_accum;
   p.per_row_out = per_row_out;
@@ -1539,7 +1572,7 @@ int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* r
   // tail of whatever kernel precedes this one in the stream; the kernel waits before touching memory
   (void)after_prep;
   static const StepSched no_sched{};
-  if (split) return launch_tc_split<TC_FWD>(tms, no_sched, p, L.NC, true, st);
+  if (split) return launch_tc_split<TC_FWD>(prec, tms, no_sched, p, L.NC, true, st);
   if (a.variant == GE2E_SOFTMAX)
     return launch_tc_cg<TC_FWD, GE2E_SOFTMAX>(L.CG, tms, no_sched, p, L.NC, true, st);
   return launch_tc_cg<TC_FWD, GE2E_CONTRAST>(L.CG, tms, no_sched, p, L.NC, true, st);
@@ -1551,9 +1584,10 @@ int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* r
 int tc_step(const RowsArgs& a, int phases, const float* grad_out, const float* row_stat_in, const float* row_aux_in,
             float* row_stat, float* row_aux, float* row_scale, float* loss_accum, float* per_row_out, float* dE_hat,
             float* dC_hat_partial, float* dwdb_accum, void* ws, size_t ws_bytes, cudaStream_t st,
-            float* const* dC_owner, int n_ranks, bool split) {
+            float* const* dC_owner, int n_ranks, int prec) {
   const int U = a.n_local * a.M;
   const bool peers = dC_owner != nullptr && n_ranks > 1;
+  const bool split = prec != PREC_TF32;         // fp16 operand planes
   // SPLIT: the rows were closed by tc_fwd_rows(split) -- pass 1 and pass 2 both read row_stat_in / row_aux_in
   if (split && (!tc_split_supported(a.n_local, a.n_total, a.M, a.D, a.variant) || row_stat_in == nullptr ||
                 row_aux_in == nullptr))
@@ -1570,6 +1604,7 @@ int tc_step(const RowsArgs& a, int phases, const float* grad_out, const float* r
   // segment kind DE: owner = utterance tiles, stream = centroids; DC: owner = centroid tiles, stream = utterances
   TcParams p{};
   fill_common(p, a);
+  if (split) p.oslabs = (prec == PREC_SPLIT ? 2 : 1) * (a.D / 64);
   p.phases = phases;
   p.row_stat = row_stat_in; p.row_aux = row_aux_in; p.grad_out = grad_out; p.dwdb = dwdb_accum;
   p.row_stat_out = row_stat; p.row_aux_out = row_aux; p.row_scale_out = row_scale; p.loss_accum = loss_accum;
@@ -1606,10 +1641,11 @@ int tc_step(const RowsArgs& a, int phases, const float* grad_out, const float* r
     const int chunks_c = a.D / 64 / cg;
     if ((rc = make_map_h3(&tms.own[SEG_DE], a.e_hat, U, a.D, kTile)) != GE2E_OK) return rc;
     if ((rc = make_map_h3(&tms.strk[SEG_DE], a.c_hat_all, a.n_total, a.D, kBoxRows)) != GE2E_OK) return rc;
-    if ((rc = make_map_h4(&tms.strmn[SEG_DE], a.c_hat_all, a.n_total, a.D, chunks_c)) != GE2E_OK) return rc;
+    const int planes = prec == PREC_SPLIT ? 2 : 1;
+    if ((rc = make_map_h4(&tms.strmn[SEG_DE], a.c_hat_all, a.n_total, a.D, chunks_c, planes)) != GE2E_OK) return rc;
     if ((rc = make_map_h3(&tms.own[SEG_DC], a.c_hat_all, a.n_total, a.D, kTile)) != GE2E_OK) return rc;
     if ((rc = make_map_h3(&tms.strk[SEG_DC], a.e_hat, U, a.D, kBoxRows)) != GE2E_OK) return rc;
-    if ((rc = make_map_h4(&tms.strmn[SEG_DC], a.e_hat, U, a.D, chunks_c)) != GE2E_OK) return rc;
+    if ((rc = make_map_h4(&tms.strmn[SEG_DC], a.e_hat, U, a.D, chunks_c, planes)) != GE2E_OK) return rc;
   } else {
     if ((rc = make_map_2d(&tms.own[SEG_DE], a.e_hat, U, a.D, kTile)) != GE2E_OK) return rc;
     if ((rc = make_map_2d(&tms.strk[SEG_DE], a.c_hat_all, a.n_total, a.D, kBoxRows)) != GE2E_OK) return rc;
@@ -1628,7 +1664,7 @@ int tc_step(const RowsArgs& a, int phases, const float* grad_out, const float* r
       if ((rc = make_map_2d(&tms.out_peer[r], dC_owner[r], p.peer_rows, a.D, kTile)) != GE2E_OK) return rc;
     }
   }
-  if (split) return launch_tc_split<TC_STEP>(tms, sched, p, NC, phases != PASS_CENTROIDS, st);
+  if (split) return launch_tc_split<TC_STEP>(prec, tms, sched, p, NC, phases != PASS_CENTROIDS, st);
   return launch_tc_cg<TC_STEP, GE2E_SOFTMAX>(cg, tms, sched, p, NC, phases != PASS_CENTROIDS, st);
 }
 

@@ -110,7 +110,7 @@ def _index_ok(row_index: Optional[Tensor], U: int, dev) -> Optional[Tensor]:
 def _tc_softmax(N: int, M: int, D: int, variant: int, precision: int) -> bool:
     """True where the softmax loss runs on tensor cores: the forward then also leaves the un-normalised
     dE_hat rows + row_scale (include/ge2e_b200.h, ge2e_b200_fwd_rows) and the backward is one pass."""
-    return variant == _lib.SOFTMAX and lib().ge2e_b200_path(N, N, M, D, variant, precision) in (1, 2)
+    return variant == _lib.SOFTMAX and lib().ge2e_b200_path(N, N, M, D, variant, precision) in (1, 2, 3)
 
 
 def _fwd_impl(E: Tensor, w: Tensor, b: Tensor, eps: float, variant: int, precision: int, packed: bool,
@@ -309,7 +309,7 @@ class _EagerPlan:
         self.dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
         h = lib()
         self.path = h.ge2e_b200_path(N, N, M, D, variant, precision)
-        self.fused = variant == _lib.SOFTMAX and self.path in (1, 2)
+        self.fused = variant == _lib.SOFTMAX and self.path in (1, 2, 3)
         # the whole-step entry point (single-kernel step for reference-sized batches) may need more than the stages
         self.ws_bytes = max(h.ge2e_b200_workspace_bytes(N, N, M, D, variant, precision),
                             h.ge2e_b200_step_workspace_bytes(N, M, D, variant, precision))
@@ -534,7 +534,7 @@ def fwd_rows(e_hat, c_hat_all, cos_diag, n_local, n_total, spk_offset, M, D, w, 
     dev = e_hat.device
     U = n_local * M
     fused = (want_grad and variant == _lib.SOFTMAX and not sim
-             and lib().ge2e_b200_path(n_local, n_total, M, D, variant, precision) in (1, 2))
+             and lib().ge2e_b200_path(n_local, n_total, M, D, variant, precision) in (1, 2, 3))
     dE_hat = torch.empty((U, D), dtype=torch.float32, device=dev) if fused else None
     row_scale = torch.empty(U, dtype=torch.float32, device=dev) if fused else None
     row_stat = torch.empty(U, dtype=torch.float32, device=dev)

@@ -178,3 +178,23 @@ def test_split_workspace_reuse_and_graph(pkg):
     assert plan.loss.item() == pytest.approx(outs[1][0], rel=1e-6)
     assert trel(plan.dE, outs[1][1]) <= 2e-6
     assert plan.launches_per_step == 4      # prep, forward rows, step, finalize
+
+
+@pytest.mark.parametrize("N,M,D", [(1024, 10, 256), (300, 7, 128), (129, 10, 256), (2048, 2, 128)])
+def test_fp16_operand_path_holds_the_tf32_tolerance(pkg, N, M, D):
+    """precision="f16" (GE2E_F16): the hi plane alone -- fp16 operands carry TF32's 11-bit mantissa, so the path
+    belongs to the 2e-3 tolerance class (measured: the same 1.6e-5 on dE as the TF32 kernels at config 3)."""
+    E = torch.tensor(orc.make_embeddings(N, M, D, seed=N + M, kind="clustered"), device=DEV)
+    ref = orct.forward_backward(E, 10.0, -5.0, 1e-6, "softmax")
+    got, plan = run_plan(pkg, E, 10.0, -5.0, "f16")
+    assert plan.path == 3
+    check_dev(got, ref, N * M, tol=2e-3)
+    two = run_module(pkg, E, 10.0, -5.0, "f16")
+    check_dev(two, ref, N * M, tol=2e-3)
+    tf = run_module(pkg, E, 10.0, -5.0, "tf32")
+    assert trel(got["dE"], ref["dE"]) <= 3 * trel(tf["dE"], ref["dE"]) + 1e-6
+    # shapes the fp16-operand kernels do not cover fall back to the TF32 permission (contrast, odd D, small batches)
+    from speaker_embedding_ge2e_loss_b200 import _lib
+    assert _lib.resolve_precision("f16", 64, 64, 10, 256, 0) == _lib.TF32
+    assert _lib.resolve_precision("f16", 1024, 1024, 10, 256, 1) == _lib.TF32
+    assert _lib.resolve_precision("f16", 1024, 1024, 10, 256, 0) == _lib.F16

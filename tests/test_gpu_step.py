@@ -208,7 +208,7 @@ def run_shards(pkg, E, w, b, R, precision, one_launch, variant=0):
                                        dC_part.data_ptr(), ws.data_ptr() if nb else None, nb,
                                        torch.cuda.current_stream().cuda_stream)
             assert rc == 0, h.ge2e_b200_strerror(rc)
-            if not (h.ge2e_b200_path(nl, N, M, D, variant, prec) in (1, 2) and variant == 0):
+            if not (h.ge2e_b200_path(nl, N, M, D, variant, prec) in (1, 2, 3) and variant == 0):
                 s["row_scale"] = None
             torch.cuda.synchronize()
             assert not ws[:256].any(), "the workspace's counters must be zero again after the call"
