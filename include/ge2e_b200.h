@@ -82,6 +82,12 @@ int ge2e_b200_path(int n_local, int n_total, int M, int D, int variant, int prec
  * NULL switches it off.  kernel: -1 = all, 0 = forward-rows kernel, 1 = step kernel; | 0x100 = also one
  * mark per ring stage in the MMA warp.  Results are unaffected. */
 void ge2e_b200_debug_trace(unsigned long long* device_buf, int kernel);
+/* Tests / A-B timing: the GE2E_TF32 softmax step runs its first product (S = E_hat C_hat^T) on fp16 copies of the
+ * operands -- same 11-bit mantissa, half the shared-memory-bound MMA instructions; the copies are made by one
+ * conversion launch in front of the step kernel and live in the workspace -- for shapes of at least 2^26 (local
+ * utterance, speaker) pairs (config 4 and its shards; D % 64 == 0).  mode 0 = that rule (initial value), 1 = every
+ * supported shape, -1 = never.  Query ge2e_b200_workspace_bytes() AFTER setting it. */
+void ge2e_b200_debug_hybrid(int mode);
 /* Measurement: while device_buf is non-NULL every CTA of the tensor-core step kernel writes %globaltimer
  * at its start and at its end into device_buf[CTA]{start, end} (two stores per CTA; the production
  * kernel, results unaffected).  max(end) - min(start) is the kernel's duration inside a running step,

@@ -34,6 +34,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--reps", type=int, default=7)
     ap.add_argument("--trace", action="store_true")
+    ap.add_argument("--fine", action="store_true", help="with --trace: one mark per ring stage in the MMA warp")
+    ap.add_argument("--hybrid", type=int, default=0, help="ge2e_b200_debug_hybrid mode (-1 never, 0 default rule, 1 always)")
     a = ap.parse_args()
     N, M, D = CFG[a.shape] if a.shape in CFG else tuple(int(v) for v in a.shape.split(","))
     dev = torch.device("cuda:0")
@@ -41,8 +43,9 @@ def main():
     n_rot = max(2, int(np.ceil(1.5 * 126e6 / (U * D * 4))))
     batches = [batch(N, M, D, i, dev) for i in range(n_rot)]
     w, b = torch.tensor(10.0, device=dev), torch.tensor(-5.0, device=dev)
-    plan = GE2EPlan(N, M, D, a.variant, a.precision, device=dev)
     h = lib()
+    h.ge2e_b200_debug_hybrid(a.hybrid)
+    plan = GE2EPlan(N, M, D, a.variant, a.precision, device=dev)
     stamps = torch.zeros(2 * 148 * 2, dtype=torch.int64, device=dev)
     h.ge2e_b200_debug_stamps(stamps.data_ptr())
     g = plan.capture(batches, w, b, steps=a.steps)
@@ -73,7 +76,7 @@ def main():
     if a.trace:
         ev = 64
         tr = torch.zeros(148 * 3 * ev, dtype=torch.int64, device=dev)
-        h.ge2e_b200_debug_trace(tr.data_ptr(), 1)
+        h.ge2e_b200_debug_trace(tr.data_ptr(), 1 | (0x100 if a.fine else 0))
         plan.step(batches[0], w, b)
         torch.cuda.synchronize()
         h.ge2e_b200_debug_trace(None, -1)

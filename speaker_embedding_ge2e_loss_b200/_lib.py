@@ -41,6 +41,7 @@ PROTOTYPES = {
     "ge2e_b200_path": (C.c_int, [C.c_int] * 6),
     "ge2e_b200_debug_trace": (None, [C.c_void_p, C.c_int]),
     "ge2e_b200_debug_stamps": (None, [C.c_void_p]),
+    "ge2e_b200_debug_hybrid": (None, [C.c_int]),
     "ge2e_b200_debug_step_schedule": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_void_p]),
     "ge2e_b200_check_device": (C.c_int, []),

@@ -74,6 +74,8 @@ void ge2e_b200_debug_trace(unsigned long long* device_buf, int kernel) { tc_set_
 
 void ge2e_b200_debug_stamps(unsigned long long* device_buf) { tc_set_stamps(device_buf); }
 
+void ge2e_b200_debug_hybrid(int mode) { tc_set_hybrid(mode); }
+
 int ge2e_b200_debug_step_schedule(int u_local, int n_total, int cta_group, int max_clusters, int* de_begin_host,
                                   int* dc_begin_host, int* partial_host, int* units_host) {
   if (!de_begin_host || !dc_begin_host || !partial_host || !units_host) return GE2E_ERR_ARGUMENT;

@@ -177,6 +177,10 @@ int tail_bwd_gemms(const float* dY, const float* W, const float* X, long long x_
 bool tc_supported(int n_local, int n_total, int M, int D, int variant);
 // fp32-class precision on tensor cores (operands as two fp16 planes, see ge2e_tc.cu): softmax, D = 128 / 256
 bool tc_split_supported(int n_local, int n_total, int M, int D, int variant);
+// GE2E_TF32 softmax step with MMA1 on fp16 copies of the operands (see PREC_HYB in ge2e_tc.cu); mode: 0 = where it
+// was measured faster (default), 1 = every supported shape, -1 = never (tests / A-B timing)
+bool tc_hybrid_selected(int n_local, int n_total, int M, int D, int variant);
+void tc_set_hybrid(int mode);
 void tc_set_trace(unsigned long long* device_buf, int mode);
 void tc_set_stamps(unsigned long long* device_buf);
 int tc_debug_step_schedule(int u_local, int n_total, int cg, int max_clusters, int* de_begin, int* dc_begin,

@@ -84,7 +84,11 @@ enum { TC_FWD = 0, TC_STEP = 1 };
 // hi = fp16(x), lo = fp16(x - hi); a product is the three kind::f16 MMAs hi.hi + hi.lo + lo.hi)
 // F16: ONE fp16 plane (hi only): 11-bit mantissas as TF32, twice its MMA rate -- the TF32-tolerance class for the
 // shapes where the MMAs dominate (same kernels and row-closing order as SPLIT, one MMA per product)
-enum { PREC_TF32 = 0, PREC_SPLIT = 1, PREC_F16 = 2 };
+// HYB: the TF32 flow (fixed shift, one launch, P and MMA2 in TF32) with MMA1 alone on fp16 COPIES of the operands
+// (11-bit mantissas as TF32): MMA1 at n = 128 is bound by its shared-memory operand reads, an fp16 instruction reads
+// the same bytes for twice the K -- half the instructions.  The copies are made by a conversion kernel in front
+// of the step kernel and live in the workspace; chosen by tc_step for large shapes under GE2E_TF32.
+enum { PREC_TF32 = 0, PREC_SPLIT = 1, PREC_F16 = 2, PREC_HYB = 3 };
 // The probability planes carry p * 2^(14 + k): 2^14 keeps p <= 1 inside fp16, and k >= 0 lifts what is known to
 // be small -- pass 1: k_r from q_r = 1 - p_jj >= every off-diagonal probability of utterance row r (per owner
 // row, undone by row_scale); pass 2: k from the largest q of the whole batch (undone in the accumulator flush).
@@ -269,7 +273,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1)
 tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepSched sched, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr bool kBwd = (MODE != TC_FWD);
-  constexpr bool kSplit = (PREC != PREC_TF32);      // fp16 operand planes, rows closed by the forward kernel
+  constexpr bool kSplit = (PREC == PREC_SPLIT || PREC == PREC_F16);   // fp16 planes, rows closed by the forward kernel
+  constexpr bool kHyb = (PREC == PREC_HYB);
+  constexpr bool kOpF16 = kSplit || kHyb;           // MMA1 operands are fp16 (planes, or the workspace copies)
   constexpr int kPlanes = (PREC == PREC_SPLIT) ? 2 : 1;
   // stream rows (K of MMA2) per ring stage: a stage is 16 KB per CTA of a pair either way -- 32 rows of fp32 or of
   // two fp16 planes, 64 rows of ONE fp16 plane (with 32 the stages would be half empty and the ring would hold
@@ -375,7 +381,10 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
         for (int sl = 0; sl < nslab; ++sl)
           for (int r = 0; r < rows_cta; r += kBoxRows, dst += kBoxRows * 128) {
             const int s = ks0 + sl;
-            if (kSplit) {
+            if (kHyb) {
+              if (CG == 1) tma_load_2d(dst, tm, s * 64, row0 + r, full);
+              else tma_load_2d_2cta(dst, tm, s * 64, row0 + cr * rows_cta + r, full);
+            } else if (kSplit) {
               if (CG == 1) tma_load_3d(dst, tm, (s % hs) * 64, row0 + r, s / hs, full);
               else tma_load_3d_2cta(dst, tm, (s % hs) * 64, row0 + cr * rows_cta + r, s / hs, full);
             } else {
@@ -391,7 +400,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
     auto load_mn = [&](const CUtensorMap* tm, int row0) {
       mbar_wait(bar(BAR_EMPTY + stage), phase ^ 1);
       if (elect_one()) {
-        const int slabs_c = oslabs / CG;
+        const int slabs_c = (kSplit ? oslabs : kslabs) / CG;      // (HYB: the MN-major operand of MMA2 stays fp32)
         const uint32_t bytes = static_cast<uint32_t>(slabs_c * kM2 * 128);
         if (leader) mbar_expect_tx(bar(BAR_FULL + stage), bytes * CG);
         const uint32_t full = lbar(BAR_FULL + stage);
@@ -425,7 +434,10 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
         if (elect_one()) {
           if (leader) mbar_expect_tx(bar(BAR_A_FULL + ks), kSlabBytes * CG);
           const uint32_t dst = a_smem + ks * kSlabBytes;
-          if (kSplit) {
+          if (kHyb) {
+            if (CG == 1) tma_load_2d(dst, tm_own, ks * 64, ot * kTile, bar(BAR_A_FULL + ks));
+            else tma_load_2d_2cta(dst, tm_own, ks * 64, ot * kTile, lbar(BAR_A_FULL + ks));
+          } else if (kSplit) {
             if (CG == 1) tma_load_3d(dst, tm_own, (ks % hs) * 64, ot * kTile, ks / hs, bar(BAR_A_FULL + ks));
             else tma_load_3d_2cta(dst, tm_own, (ks % hs) * 64, ot * kTile, ks / hs, lbar(BAR_A_FULL + ks));
           } else {
@@ -488,7 +500,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
       };
       // MMA1 over one stage holding `nslab` (1 or 2) K-slabs of [rows_cta x 32] starting at slab ks0
       auto mma1_stage = [&](uint32_t d_tmem, uint32_t idesc1, int rows_cta, int ks0, int nslab, bool first_of_seg) {
-        if (kSplit) {
+        if (kOpF16) {
           // stream slab s = (plane, chunk c): a hi slab meets the owner's hi AND lo chunk c (8 MMAs), a lo slab
           // the owner's hi chunk (4 MMAs); lo.lo is below fp32 resolution and is not formed
           if (first_of_seg) {
@@ -531,7 +543,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
         }
         stage_done(probe);
       };
-      const uint32_t idesc_unit = kSplit ? idesc_f16(kTile * CG, kUnit, 0, 0) : idesc_tf32(kTile * CG, kUnit, 0, 0);
+      const uint32_t idesc_unit = kOpF16 ? idesc_f16(kTile * CG, kUnit, 0, 0) : idesc_tf32(kTile * CG, kUnit, 0, 0);
       auto mma1_unit = [&](int iter, bool first_of_seg) {   // BWD: n = 128 into T[iter & 1]
         const uint32_t d_tmem = tmem + (iter & 1) * kUnit;
         for (int ks = 0; ks < oslabs; ks += 2)
@@ -597,7 +609,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
             mbar_wait(bar(BAR_S_EMPTY + (it & 1)), ((it >> 1) & 1) ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem + (it & 1) * (kStepUnits * kUnit);
-            const uint32_t idesc_step = kSplit ? idesc_f16(kTile * CG, nu * kUnit, 0, 0)
+            const uint32_t idesc_step = kOpF16 ? idesc_f16(kTile * CG, nu * kUnit, 0, 0)
                                                : idesc_tf32(kTile * CG, nu * kUnit, 0, 0);
             for (int ks = 0; ks < oslabs; ++ks) mma1_stage(d_tmem, idesc_step, nu * kUnit / CG, ks, 1, u == s0);
             if (elect_one()) commit(BAR_S_FULL + (it & 1));
@@ -1269,6 +1281,41 @@ int make_map_h4(CUtensorMap* m, const void* base, int rows, int D, int box_chunk
   return r == CUDA_SUCCESS ? GE2E_OK : GE2E_ERR_LAUNCH;
 }
 
+// HYB operand copies: X as ONE compact fp16 matrix [rows][D]; box = [box_rows][64 cols], 128-byte swizzle.
+int make_map_h2(CUtensorMap* m, const void* base, int rows, int D, int box_rows) {
+  const MapKey key{base, rows, D, box_rows, 16};
+  if (map_lookup(key, m)) return GE2E_OK;
+  auto enc = get_encode();
+  if (enc == nullptr) return GE2E_ERR_LAUNCH;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(D) * 2};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS) map_store(key, *m);
+  return r == CUDA_SUCCESS ? GE2E_OK : GE2E_ERR_LAUNCH;
+}
+
+// fp32 -> fp16 copies of the two operand matrices (HYB), one launch between prep / the exchange and the step kernel
+__global__ void __launch_bounds__(256)
+to_f16_kernel(const float4* __restrict__ a, uint2* __restrict__ a16, long long na4, const float4* __restrict__ b,
+              uint2* __restrict__ b16, long long nb4) {
+  pdl_wait();
+  pdl_trigger();
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < na4 + nb4; i += stride) {
+    const float4 v = (i < na4) ? __ldcg(a + i) : __ldcg(b + (i - na4));
+    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&h0); o.y = *reinterpret_cast<const uint32_t*>(&h1);
+    if (i < na4) a16[i] = o; else b16[i - na4] = o;
+  }
+}
+
+int g_hybrid_mode = 0;                   // 0 = where it was measured faster, 1 = every supported shape, -1 = never
+
 unsigned long long* g_trace = nullptr;   // set through tc_set_trace (debug only)
 int g_trace_mode = -1;                   // -1: every kernel, else only TC_FWD / TC_STEP
 int g_trace_fine = 0;                    // 8: per-stage marks in the MMA warp's trace
@@ -1536,10 +1583,23 @@ bool tc_split_supported(int n_local, int n_total, int M, int D, int variant) {
   return variant == GE2E_SOFTMAX && (D == 128 || D == 256) && tc_supported(n_local, n_total, M, D, variant);
 }
 
-// workspace: [header 256 B: step counters][FWD seg_done][FWD seg_part][STEP row sums]
+void tc_set_hybrid(int mode) { g_hybrid_mode = mode < -1 || mode > 1 ? 0 : mode; }
+
+// GE2E_TF32, softmax step: MMA1 on fp16 copies of the operands (PREC_HYB) where the step is long enough to pay for
+// the conversion launch -- from 2^26 (local utterance, speaker) pairs: config 4 and its shards, not config 3
+bool tc_hybrid_selected(int n_local, int n_total, int M, int D, int variant) {
+  if (g_hybrid_mode < 0 || variant != GE2E_SOFTMAX || D % 64 != 0 || !tc_supported(n_local, n_total, M, D, variant))
+    return false;
+  return g_hybrid_mode > 0 || static_cast<long long>(n_local) * M * n_total >= (1LL << 26);
+}
+size_t f16_copy_bytes(int rows, int D) { return (static_cast<size_t>(rows) * D * 2 + 255) & ~static_cast<size_t>(255); }
+
+// workspace: [header 256 B: step counters][FWD seg_done][FWD seg_part][STEP row sums][HYB: e_hat, c_hat as fp16]
 size_t tc_workspace_bytes(int n_local, int n_total, int M, int D, int variant) {
   const Layout L = fwd_layout(n_local * M, n_total, D, variant);
-  return kWsHeaderBytes + L.done_bytes + L.part_bytes + rowsum_bytes(n_local * M);
+  size_t n = kWsHeaderBytes + L.done_bytes + L.part_bytes + rowsum_bytes(n_local * M);
+  if (tc_hybrid_selected(n_local, n_total, M, D, variant)) n += f16_copy_bytes(n_local * M, D) + f16_copy_bytes(n_total, D);
+  return n;
 }
 
 int tc_fwd_rows(const RowsArgs& a, float* row_stat, int32_t* row_kstar, float* row_aux, float* loss_accum,
@@ -1588,6 +1648,7 @@ int tc_step(const RowsArgs& a, int phases, const float* grad_out, const float* r
   const int U = a.n_local * a.M;
   const bool peers = dC_owner != nullptr && n_ranks > 1;
   const bool split = prec != PREC_TF32;         // fp16 operand planes
+  const bool hyb = !split && tc_hybrid_selected(a.n_local, a.n_total, a.M, a.D, a.variant);
   // SPLIT: the rows were closed by tc_fwd_rows(split) -- pass 1 and pass 2 both read row_stat_in / row_aux_in
   if (split && (!tc_split_supported(a.n_local, a.n_total, a.M, a.D, a.variant) || row_stat_in == nullptr ||
                 row_aux_in == nullptr))
@@ -1605,6 +1666,7 @@ int tc_step(const RowsArgs& a, int phases, const float* grad_out, const float* r
   TcParams p{};
   fill_common(p, a);
   if (split) p.oslabs = (prec == PREC_SPLIT ? 2 : 1) * (a.D / 64);
+  if (hyb) p.oslabs = a.D / 64;
   p.phases = phases;
   p.row_stat = row_stat_in; p.row_aux = row_aux_in; p.grad_out = grad_out; p.dwdb = dwdb_accum;
   p.row_stat_out = row_stat; p.row_aux_out = row_aux; p.row_scale_out = row_scale; p.loss_accum = loss_accum;
@@ -1646,6 +1708,23 @@ int tc_step(const RowsArgs& a, int phases, const float* grad_out, const float* r
     if ((rc = make_map_h3(&tms.own[SEG_DC], a.c_hat_all, a.n_total, a.D, kTile)) != GE2E_OK) return rc;
     if ((rc = make_map_h3(&tms.strk[SEG_DC], a.e_hat, U, a.D, kBoxRows)) != GE2E_OK) return rc;
     if ((rc = make_map_h4(&tms.strmn[SEG_DC], a.e_hat, U, a.D, chunks_c, planes)) != GE2E_OK) return rc;
+  } else if (hyb) {
+    // fp16 copies behind the row sums in the workspace; MMA1 reads them (K-major), MMA2 the fp32 originals (MN-major)
+    uint8_t* e16 = reinterpret_cast<uint8_t*>(p.rowsum) + rowsum_bytes(U);
+    uint8_t* c16 = e16 + f16_copy_bytes(U, a.D);
+    const long long na4 = static_cast<long long>(U) * a.D / 4, nb4 = static_cast<long long>(a.n_total) * a.D / 4;
+    const long long want = (na4 + nb4 + 255) / 256;
+    const unsigned blocks = static_cast<unsigned>(std::min<long long>(want, static_cast<long long>(sm_count()) * 8));
+    GE2E_CUDA_TRY(launch_pdl(to_f16_kernel, dim3(blocks), dim3(256), 0, st, phases != PASS_CENTROIDS,
+                             reinterpret_cast<const float4*>(a.e_hat), reinterpret_cast<uint2*>(e16), na4,
+                             reinterpret_cast<const float4*>(a.c_hat_all), reinterpret_cast<uint2*>(c16), nb4));
+    GE2E_LAUNCHED();
+    if ((rc = make_map_h2(&tms.own[SEG_DE], e16, U, a.D, kTile)) != GE2E_OK) return rc;
+    if ((rc = make_map_h2(&tms.strk[SEG_DE], c16, a.n_total, a.D, kBoxRows)) != GE2E_OK) return rc;
+    if ((rc = make_map_3d(&tms.strmn[SEG_DE], a.c_hat_all, a.n_total, a.D, slabs / cg)) != GE2E_OK) return rc;
+    if ((rc = make_map_h2(&tms.own[SEG_DC], c16, a.n_total, a.D, kTile)) != GE2E_OK) return rc;
+    if ((rc = make_map_h2(&tms.strk[SEG_DC], e16, U, a.D, kBoxRows)) != GE2E_OK) return rc;
+    if ((rc = make_map_3d(&tms.strmn[SEG_DC], a.e_hat, U, a.D, slabs / cg)) != GE2E_OK) return rc;
   } else {
     if ((rc = make_map_2d(&tms.own[SEG_DE], a.e_hat, U, a.D, kTile)) != GE2E_OK) return rc;
     if ((rc = make_map_2d(&tms.strk[SEG_DE], a.c_hat_all, a.n_total, a.D, kBoxRows)) != GE2E_OK) return rc;
@@ -1665,6 +1744,10 @@ int tc_step(const RowsArgs& a, int phases, const float* grad_out, const float* r
     }
   }
   if (split) return launch_tc_split<TC_STEP>(prec, tms, sched, p, NC, phases != PASS_CENTROIDS, st);
+  if (hyb) {
+    if (g_trace != nullptr) return launch_tc_impl<TC_STEP, GE2E_SOFTMAX, 2, PREC_HYB, true>(tms, sched, p, NC, true, st);
+    return launch_tc_impl<TC_STEP, GE2E_SOFTMAX, 2, PREC_HYB, false>(tms, sched, p, NC, true, st);
+  }
   return launch_tc_cg<TC_STEP, GE2E_SOFTMAX>(cg, tms, sched, p, NC, phases != PASS_CENTROIDS, st);
 }
 

@@ -286,3 +286,32 @@ def test_cfg3_contrast_tf32_gradients_on_robust_rows(pkg):
     err = trel(got["dE"][ok], ref["dE"][ok].float())
     assert err <= TF32_TOL, err
     assert abs(got["dw"] - ref["dw"]) <= 2e-2 * max(1.0, abs(ref["dw"]))
+
+
+# ------------------------------------------------------------------ TF32 step with MMA1 on fp16 copies of the operands
+@pytest.mark.parametrize("N,M,D", [(300, 7, 128), (1024, 10, 256), (700, 9, 192), (513, 3, 64)])
+def test_hybrid_operand_copies_match_the_tf32_step(pkg, N, M, D):
+    """Large shapes (>= 2^26 utterance x speaker pairs: config 4, covered by the full-size test above) run the first
+    product of the TF32 step on fp16 copies of e_hat / c_hat made by a conversion launch (ge2e_b200_debug_hybrid).
+    Forced on small shapes here: same tolerance class, results next to the plain TF32 step's, one more launch,
+    workspace counters restored; a speaker shard takes the same path."""
+    h = pkg.lib()
+    E = torch.tensor(orc.make_embeddings(N, M, D, seed=N + D, kind="clustered"), device=DEV)
+    ref = orct.forward_backward(E, 10.0, -5.0, 1e-6, "softmax")
+    plain, _ = run_plan(pkg, E, 10.0, -5.0, "tf32")
+    h.ge2e_b200_debug_hybrid(1)
+    try:
+        got, plan = run_plan(pkg, E, 10.0, -5.0, "tf32")
+        w, b = torch.tensor(10.0, device=DEV), torch.tensor(-5.0, device=DEV)
+        g = plan.capture(E, w, b, steps=2)
+        g.replay()
+        torch.cuda.synchronize()
+        assert plan.launches_per_step == 4          # prep, conversion, step, finalize
+        assert int(plan._ws[:256].max()) == 0
+        again = dict(loss=plan.loss.item(), dE=plan.dE.clone(), dw=plan.dw.item(), db=plan.db.item())
+        shards = run_shards(pkg, E, 10.0, -5.0, 3 if N % 3 == 0 else 1, "tf32", True)
+    finally:
+        h.ge2e_b200_debug_hybrid(0)
+    for r in (got, again, shards):
+        check_dev(r, ref, N * M, TF32_TOL)
+    assert trel(got["dE"], ref["dE"]) <= 2 * trel(plain["dE"], ref["dE"]) + 1e-6
