@@ -289,7 +289,10 @@ def step_kernel_in_situ(plan, batches, w, b, steps, warmup, reps=11, all_out=Non
             st = st[(st[:, 0] > 0) & (st[:, 1] > 0)]
             if len(st) == 0:
                 return None
-            vals.append(float(st[:, 1].max() - st[:, 0].min()) / 1e3)
+            # the longest per-CTA span (every CTA starts at the same event, the end of its predecessor grid): robust
+            # against %globaltimer offsets between SMs, which max(end) - min(start) across CTAs is not (seen on some
+            # boxes of the pool: cross-CTA spans LONGER than the whole step)
+            vals.append(float((st[:, 1] - st[:, 0]).max()) / 1e3)
     finally:
         h.ge2e_b200_debug_stamps(None)
     if all_out is not None:
@@ -563,11 +566,11 @@ def run_ours(args):
                                       all_out=kern_all) if path in (1, 2, 3) else None
         if kern_us is not None and path == 2:
             dom, how = "tc_strip_kernel<STEP, split fp16 planes> (dE_hat pass + dC_hat pass; the rows were closed by the forward kernel before it)", \
-                "in situ: max(CTA end) - min(CTA start) of the kernel's %globaltimer stamps in the last step of a graph replay"
+                "in situ: the longest per-CTA (end - start) of the kernel's %globaltimer stamps in the last step of a graph replay (all CTAs start at the same event), median of 11 replays"
             extra["step_us_outside_the_step_kernel"] = step_us - kern_us
         elif kern_us is not None:
             dom, how = "tc_strip_kernel<STEP> (forward rows + dE_hat pass, grid barrier, dC_hat pass)", \
-                "in situ: max(CTA end) - min(CTA start) of the kernel's %globaltimer stamps in the last step of a graph replay"
+                "in situ: the longest per-CTA (end - start) of the kernel's %globaltimer stamps in the last step of a graph replay (all CTAs start at the same event), median of 11 replays"
             extra["step_us_outside_the_step_kernel"] = step_us - kern_us
         elif getattr(plan, "single_kernel", False):
             dom, kern_us, how = "small_step_kernel (whole fwd+bwd step)", step_us, "the step is this one kernel: step time"
