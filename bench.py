@@ -14,7 +14,7 @@ One "step" = one GE2E forward + backward (grads to E, w, b) over one synthetic b
          and double-buffered; the fastest is the headline, all three are listed with the API they use).
   roofline      the dominant kernel (the tensor-core step kernel: forward rows + both gradient
                 contractions) priced IN SITU: every CTA stamps %globaltimer at its start and end
-                (ge2e_b200_debug_stamps), max(end) - min(start) over the last step of a replay is the
+                (ge2e_b200_debug_stamps), the longest per-CTA (end - start) in the last step of a replay is the
                 kernel's duration inside the running graph; algorithmic flops 6 U N D.
   fp32_path     cfg3 through the default precision of GE2ELoss(hp) ("fp32": fp32-class results; at this shape the
                 tensor cores with operands split into two fp16 planes), same timing; the SIMT FMA kernels beside it.
