@@ -425,9 +425,7 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
       const int ot = og * CG + cr;      // may be >= OT in the last group: TMA zero-fills, nothing is stored
       if (sg > 0) mbar_wait(bar(BAR_A_EMPTY), (sg - 1) & 1);      // every MMA1 of the previous segment has completed
       tr.mark();   // owner tile issue
-      for (int i = 0; i < oslabs; ++i) {
-        // SPLIT: chunk c of the hi plane is first used together with chunk c of the lo plane
-        const int ks = (kPlanes == 2) ? (i & 1) * hs + (i >> 1) : i;
+      auto load_own = [&](int ks) {
         // STEP: the previous segment's accumulator leaves through the owner area, slab by slab; slab ks is
         // free again once the TMA store that took it out has read it
         if (kBwd && sg > 0) mbar_wait(bar(BAR_A_FREE + ks), (sg - 1) & 1);
@@ -446,6 +444,14 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
           }
         }
         __syncwarp();
+      };
+      // TF32 / HYB step: the first unit's MMA1 stages are requested right behind the two owner slabs each of them
+      // meets, so MMA1 starts after ~48 KB have landed instead of after the whole 160 KB (every CTA fills at once:
+      // the fill is bound by the aggregate L2 bandwidth)
+      constexpr bool kInterleaveFill = kBwd && !kSplit;
+      if (!kInterleaveFill) {
+        for (int i = 0; i < oslabs; ++i)
+          load_own((kPlanes == 2) ? (i & 1) * hs + (i >> 1) : i);   // SPLIT: hi chunk c, then lo chunk c
       }
       if (!kBwd) {
         for (int u = s0; u < s1; u += kStepUnits) {
@@ -456,7 +462,15 @@ tc_strip_kernel(const __grid_constant__ TmSet tms, const __grid_constant__ StepS
         auto load_mma1_unit = [&](int u) {       // stages of two slabs, n = 128
           for (int ks = 0; ks < oslabs; ks += 2) load_k(tm_k, u * kUnit, kUnit / CG, ks, min(2, oslabs - ks));
         };
-        load_mma1_unit(s0);
+        if (kInterleaveFill) {
+          for (int ks = 0; ks < oslabs; ks += 2) {
+            const int n = min(2, oslabs - ks);
+            for (int q = 0; q < n; ++q) load_own(ks + q);
+            load_k(tm_k, s0 * kUnit, kUnit / CG, ks, n);
+          }
+        } else {
+          load_mma1_unit(s0);
+        }
         for (int u = s0; u < s1; ++u) {
           if (u + 1 < s1) load_mma1_unit(u + 1);
           for (int kc = 0; kc < kUnit / kM2; ++kc) load_mn(tm_mn, u * kUnit + kc * kM2);
