@@ -32,7 +32,8 @@ using namespace ptx;
 
 constexpr int kTailRows = 128;               // rows of X per CTA
 constexpr int kTailKc = 32;                  // K columns per ring stage (one 128-byte swizzled slab)
-constexpr int kTailStages = 4;
+constexpr int kTailStages = 4;               // (6 in the CTA-pair instantiation, same ring bytes)
+constexpr int kTailMaxStages = 6;
 constexpr int kTailABytes = kTailRows * 128;             // 16 KB
 constexpr int kTailBBytes = 256 * 128;                   // 32 KB (D <= 256 rows of W)
 constexpr int kTailStageBytes = kTailABytes + kTailBBytes;
@@ -41,7 +42,7 @@ constexpr int kTailEpiThreads = 128;
 constexpr int kTailSmemBytes = kTailStages * kTailStageBytes + 1024 /*alignment*/ + 2048 /*tail struct*/;
 
 struct TailShared {
-  unsigned long long full[kTailStages], empty[kTailStages], acc_full;
+  unsigned long long full[kTailMaxStages], empty[kTailMaxStages], acc_full;
   uint32_t tmem_base;
   float bias[256];
 };
@@ -52,32 +53,50 @@ struct TailParams {
   float* inv_norm;       // [U]
 };
 
+// CG = 2: two CTAs of a cluster own two consecutive 128-row tiles and run every MMA as a pair (cta_group::2, UMMA
+// M = 256); each fetches its own X slab and HALF of the W slab (rows [rank D/2, +D/2)).  Halving the W traffic per SM
+// alone changed nothing (24.6 us at U = 10240 either way: the K loop is a latency chain on the strided X slabs, not
+// an L2-feed limit); what the smaller stage buys is a ring of 6 stages instead of 4 in the same 192 KB (22.5 us).
+// The leader CTA issues the MMAs; the barriers it waits on live in the leader and are signalled by both CTAs (as in
+// ge2e_tc.cu).
+template <int CG>
 __global__ void __launch_bounds__(kTailThreads, 1)
 embed_tail_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                       const __grid_constant__ CUtensorMap tm_e, const TailParams p) {
   extern __shared__ uint8_t tail_raw[];
   const uint32_t raw = smem_u32(tail_raw);
   const uint32_t ring = (raw + 1023u) & ~1023u;                       // 1024-byte aligned (swizzle atom)
-  TailShared* sh = reinterpret_cast<TailShared*>(tail_raw + (ring - raw) + kTailStages * kTailStageBytes);
+  TailShared* sh = reinterpret_cast<TailShared*>(tail_raw + (ring - raw) + kTailStages * kTailStageBytes);   // (same offset in both instantiations)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * kTailRows;
   const int nchunks = (p.H + kTailKc - 1) / kTailKc;
   const int D = p.D;
+  // ring: 4 stages of [X 16 KB | W 32 KB] alone, 6 stages of [X 16 KB | W half 16 KB] as a pair (same 192 KB): the
+  // K loop is a latency chain (a stage comes back ~2.8 us after it was requested from HBM), depth is what it needs
+  constexpr int kStages = (CG == 2) ? 6 : kTailStages;
+  constexpr int kStageBytes = (CG == 2) ? kTailABytes + kTailBBytes / 2 : kTailStageBytes;
+  const int cr = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+  const bool leader = cr == 0;
+  const int Dw = D / CG;                                              // rows of W this CTA fetches per stage
+  auto lbar = [&](const unsigned long long* b) { return (CG == 2) ? mapa(smem_u32(b), 0) : smem_u32(b); };
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tm_x);
     prefetch_tmap(&tm_w);
     prefetch_tmap(&tm_e);
-    for (int s = 0; s < kTailStages; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       mbar_init(smem_u32(&sh->full[s]), 1);
       mbar_init(smem_u32(&sh->empty[s]), 1);
     }
     mbar_init(smem_u32(&sh->acc_full), 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<256>(smem_u32(&sh->tmem_base));
+  if (warp == 1) {
+    if (CG == 1) tmem_alloc<256>(smem_u32(&sh->tmem_base)); else tmem_alloc_2cta<256>(smem_u32(&sh->tmem_base));
+  }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();      // the peer's barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem = sh->tmem_base;
   pdl_wait();          // X comes from the stream predecessor (the LSTM)
@@ -86,42 +105,51 @@ embed_tail_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
-      const uint32_t bytes = static_cast<uint32_t>(kTailABytes + D * 128);
+      const uint32_t bytes = static_cast<uint32_t>(kTailABytes + Dw * 128);
       for (int c = 0; c < nchunks; ++c) {
-        const int s = c % kTailStages;
-        mbar_wait(smem_u32(&sh->empty[s]), ((c / kTailStages) & 1) ^ 1);
-        const uint32_t fb = smem_u32(&sh->full[s]);
-        mbar_expect_tx(fb, bytes);
-        tma_load_2d(ring + s * kTailStageBytes, &tm_x, c * kTailKc, row0, fb);
-        tma_load_2d(ring + s * kTailStageBytes + kTailABytes, &tm_w, c * kTailKc, 0, fb);
+        const int s = c % kStages;
+        mbar_wait(smem_u32(&sh->empty[s]), ((c / kStages) & 1) ^ 1);
+        const uint32_t fb = lbar(&sh->full[s]);
+        if (leader) mbar_expect_tx(smem_u32(&sh->full[s]), bytes * CG);
+        if (CG == 1) {
+          tma_load_2d(ring + s * kStageBytes, &tm_x, c * kTailKc, row0, fb);
+          tma_load_2d(ring + s * kStageBytes + kTailABytes, &tm_w, c * kTailKc, 0, fb);
+        } else {
+          tma_load_2d_2cta(ring + s * kStageBytes, &tm_x, c * kTailKc, row0, fb);
+          tma_load_2d_2cta(ring + s * kStageBytes + kTailABytes, &tm_w, c * kTailKc, cr * Dw, fb);
+        }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issue
-    const uint32_t idesc = idesc_tf32(kTailRows, D, 0, 0);
-    const uint64_t dk = smem_desc(0, 16, 1024, kLayoutSw128);          // K-major, 8-row groups 1024 B apart
-    bool ready = false;
-    uint32_t leader = 0;
-    for (int c = 0; c < nchunks; ++c) {
-      const int s = c % kTailStages;
-      const uint32_t ph = (c / kTailStages) & 1;
-      if (!ready) mbar_wait(smem_u32(&sh->full[s]), ph);
-      tc_fence_after();
-      const int sn = (s + 1 == kTailStages) ? 0 : s + 1;
-      const uint32_t pn = (s + 1 == kTailStages) ? (ph ^ 1) : ph;
-      uint32_t probe = 0;
-      if (elect_leader(leader)) {
-        const uint64_t da = dk | ((ring + s * kTailStageBytes) >> 4);
-        const uint64_t db = dk | ((ring + s * kTailStageBytes + kTailABytes) >> 4);
-        probe = umma_stage_ss<1, 1>(tmem, da, db, 0, 0, idesc, c != 0, smem_u32(&sh->empty[s]),
-                                    smem_u32(&sh->full[sn]), pn);
+    // ------------------------------------------------------------------ MMA issue (leader CTA of a pair)
+    if (leader) {
+      const uint32_t idesc = idesc_tf32(kTailRows * CG, D, 0, 0);
+      const uint64_t dk = smem_desc(0, 16, 1024, kLayoutSw128);          // K-major, 8-row groups 1024 B apart
+      bool ready = false;
+      uint32_t lead_lane = 0;
+      for (int c = 0; c < nchunks; ++c) {
+        const int s = c % kStages;
+        const uint32_t ph = (c / kStages) & 1;
+        if (!ready) mbar_wait(smem_u32(&sh->full[s]), ph);
+        tc_fence_after();
+        const int sn = (s + 1 == kStages) ? 0 : s + 1;
+        const uint32_t pn = (s + 1 == kStages) ? (ph ^ 1) : ph;
+        uint32_t probe = 0;
+        if (elect_leader(lead_lane)) {
+          const uint64_t da = dk | ((ring + s * kStageBytes) >> 4);
+          const uint64_t db = dk | ((ring + s * kStageBytes + kTailABytes) >> 4);
+          probe = umma_stage_ss<CG, 1>(tmem, da, db, 0, 0, idesc, c != 0, smem_u32(&sh->empty[s]),
+                                       smem_u32(&sh->full[sn]), pn);
+        }
+        __syncwarp();
+        ready = (c + 1 < nchunks) && __shfl_sync(0xffffffffu, probe, lead_lane) != 0;
+      }
+      if (elect_one()) {
+        if (CG == 1) umma_commit(smem_u32(&sh->acc_full)); else umma_commit_2cta(smem_u32(&sh->acc_full), 3);
       }
       __syncwarp();
-      ready = (c + 1 < nchunks) && __shfl_sync(0xffffffffu, probe, leader) != 0;
     }
-    if (elect_one()) umma_commit(smem_u32(&sh->acc_full));
-    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue: one thread per row
     const int q = warp & 3;                           // TMEM lane quarter this warp may read
@@ -176,7 +204,10 @@ embed_tail_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<256>(tmem);
+  if (CG == 2) cluster_sync_all();      // no CTA leaves while its peer may still arrive on it / read its smem
+  if (warp == 1) {
+    if (CG == 1) tmem_dealloc<256>(tmem); else tmem_dealloc_2cta<256>(tmem);
+  }
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 tail_encode() {
@@ -467,19 +498,37 @@ int tail_fwd(const float* X, long long x_row_stride, const float* W, const float
   CUtensorMap tm_x, tm_w, tm_e;
   int rc;
   if ((rc = tail_map(&tm_x, X, U, H, x_row_stride, kTailRows)) != GE2E_OK) return rc;
-  if ((rc = tail_map(&tm_w, W, D, H, H, D)) != GE2E_OK) return rc;
+  const int tiles = (U + kTailRows - 1) / kTailRows;
+  // CTA pairs from two tiles on (one W half per CTA); a single tile runs alone
+  const int cg = tiles >= 2 ? 2 : 1;
+  if ((rc = tail_map(&tm_w, W, D, H, H, D / cg)) != GE2E_OK) return rc;
   if ((rc = tail_map(&tm_e, E, U, D, D, kTailRows)) != GE2E_OK) return rc;
   static thread_local int attr_dev = -1;
   int dev = 0;
   GE2E_CUDA_TRY(cudaGetDevice(&dev));
   if (attr_dev != dev) {
-    GE2E_CUDA_TRY(cudaFuncSetAttribute(embed_tail_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    GE2E_CUDA_TRY(cudaFuncSetAttribute(embed_tail_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kTailSmemBytes));
+    GE2E_CUDA_TRY(cudaFuncSetAttribute(embed_tail_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kTailSmemBytes));
     attr_dev = dev;
   }
   TailParams p{U, H, D, bias, inv_norm};
-  const int grid = (U + kTailRows - 1) / kTailRows;
-  launch_pdl(embed_tail_fwd_kernel, dim3(grid), dim3(kTailThreads), (size_t)kTailSmemBytes, st, true, tm_x, tm_w, tm_e, p);
+  if (cg == 1) {
+    launch_pdl(embed_tail_fwd_kernel<1>, dim3(tiles), dim3(kTailThreads), (size_t)kTailSmemBytes, st, true, tm_x, tm_w,
+               tm_e, p);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((tiles + 1) / 2 * 2); cfg.blockDim = dim3(kTailThreads);
+    cfg.dynamicSmemBytes = kTailSmemBytes; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 2;
+    GE2E_CUDA_TRY(cudaLaunchKernelEx(&cfg, embed_tail_fwd_kernel<2>, tm_x, tm_w, tm_e, p));
+  }
   GE2E_LAUNCHED();
   return GE2E_OK;
 }
