@@ -172,3 +172,27 @@ def test_step_schedule_covers_every_pair_once(pkg, u_local, n_total, cg, max_cl)
         # a range never spans more than two groups unless groups are shorter than the level share
         if st >= level:
             assert all((begin[c + 1] - 1) // st - begin[c] // st <= 1 for c in range(nc) if loads[c] > 0)
+
+
+def test_precision_names_resolve_without_a_gpu():
+    """The Python layer's precision names -> C-ABI codes.  "fp32" asks ge2e_b200_path() whether the split-fp16
+    tensor-core kernels cover the shape; without a CUDA driver (this suite's CPU runs) nothing is covered and the
+    name falls back to the SIMT fp32 code -- never an exception, never a silent TF32."""
+    import torch
+    from speaker_embedding_ge2e_loss_b200 import _lib
+    h = _lib.lib()
+    got = _lib.resolve_precision("fp32", 1024, 1024, 10, 256, _lib.SOFTMAX)
+    if torch.cuda.is_available():
+        assert got == _lib.FP32_SPLIT and h.ge2e_b200_path(1024, 1024, 10, 256, 0, _lib.FP32_SPLIT) == 2
+    else:
+        assert got == _lib.FP32 and h.ge2e_b200_path(1024, 1024, 10, 256, 0, _lib.FP32_SPLIT) < 0
+    assert _lib.resolve_precision("fp32", 64, 64, 10, 256, _lib.SOFTMAX) == _lib.FP32          # reference-sized batch
+    assert _lib.resolve_precision("fp32", 1024, 1024, 10, 256, _lib.CONTRAST) == _lib.FP32    # contrast: SIMT backward
+    assert _lib.resolve_precision("fp32_simt", 1024, 1024, 10, 256, _lib.SOFTMAX) == _lib.FP32
+    assert _lib.resolve_precision("tf32", 8192, 8192, 16, 256, _lib.SOFTMAX) == _lib.TF32      # never fp16 operands unasked
+    assert _lib.resolve_precision("tf32_mma", 1024, 1024, 10, 256, _lib.SOFTMAX) == _lib.TF32
+    with __import__("pytest").raises(ValueError):
+        _lib.resolve_precision("bf16", 64, 64, 10, 256, _lib.SOFTMAX)
+    # argument checking of the new precision codes at the C level (no launch: a bad enum returns first)
+    assert h.ge2e_b200_path(64, 64, 10, 256, 0, 7) < 0
+    assert h.ge2e_b200_path(64, 64, 10, 256, 0, _lib.F16) < 0                 # below the tensor-core sizes
